@@ -1,0 +1,102 @@
+/*
+ * sourmash_b200.h -- batch extension of the sourmash C ABI for the B200 build.
+ *
+ * The reference ABI (sourmash.h) is per object: one sequence per kmerminhash_add_sequence call,
+ * one pair per kmerminhash_compare call.  The workloads this build exists for (10^8 reads,
+ * 10^4..10^6 sketches) need one call per BATCH, so that a single kernel launch covers it.  Every
+ * function below is defined as a loop over reference calls, and cites them; results are
+ * bit-identical to running that loop against the reference.
+ *
+ * Error convention: as sourmash.h (thread-local last error, zero return value).
+ * Pointers marked [host|device] are host pointers unless the call's `on_device` flag is set, in
+ * which case they are device pointers of the library's device (see smgpu_set_device) and no
+ * host<->device copy is made.
+ */
+#ifndef SOURMASH_B200_EXT_H
+#define SOURMASH_B200_EXT_H
+
+#include "sourmash.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- device ---------------------------------------------------------------------------------- */
+/* Select the CUDA device this process uses (one process per GPU).  Must precede the first call
+ * that touches the GPU; default is the calling thread's current device. */
+void smgpu_set_device(int32_t device);
+/* device ordinal in use (creates the context), SM count through *sm_count when non-NULL */
+int32_t smgpu_device(int32_t *sm_count);
+/* kernels this library has launched so far in this process */
+uint64_t smgpu_launch_count(void);
+/* page-locked host memory for batch buffers (host->device copies from it run at full PCIe rate
+ * and overlap with the kernels) */
+void *smgpu_alloc_pinned(uintptr_t bytes);
+void smgpu_free_pinned(void *ptr);
+/* frees what kmerminhash_get_mins / kmerminhash_get_abunds returned (reference: leaked, ffi.rs:97-122) */
+void kmerminhash_slice_free(const uint64_t *ptr);
+
+/* ---- batch sketching ------------------------------------------------------------------------- */
+/* for s in 0..n_seqs: for m in 0..n_mhs: kmerminhash_add_sequence(mhs[m], buf[offsets[s]..offsets[s+1]], force)
+ * (src/ffi.rs:55-70 -> src/lib.rs:252-274), sequences NOT NUL-terminated.  n_mhs <= 6.
+ * With force == false, each sketch keeps the k-mers that precede ITS first invalid k-mer in batch
+ * order and SOURMASH_ERROR_CODE_INVALID_D_N_A is recorded.
+ * A device `buf` must be 16-byte aligned and readable up to offsets[n_seqs] rounded up to 16. */
+void kmerminhash_add_sequences(KmerMinHash *const *mhs, uintptr_t n_mhs, const char *buf /*[host|device]*/,
+                               const uint64_t *offsets /*[host|device], n_seqs + 1 */, uint64_t n_seqs,
+                               bool force, bool on_device);
+/* same for n_reads fixed-length reads stored back to back (no offsets array) */
+void kmerminhash_add_reads(KmerMinHash *const *mhs, uintptr_t n_mhs, const char *buf /*[host|device]*/,
+                           uint64_t n_reads, uint32_t read_len, bool force, bool on_device);
+/* replace the sketch content: equivalent to a fresh sketch followed by n kmerminhash_mins_push and
+ * n_abunds kmerminhash_abunds_push calls (src/ffi.rs:143-150,179-188); abunds may be NULL */
+void kmerminhash_set_mins(KmerMinHash *ptr, const uint64_t *mins, uintptr_t n, const uint64_t *abunds,
+                          uintptr_t n_abunds);
+/* copy the sorted mins (and abundances when `abunds` is non-NULL and tracked) into caller memory
+ * of kmerminhash_get_mins_size elements; returns the element count */
+uintptr_t kmerminhash_copy_mins(KmerMinHash *ptr, uint64_t *mins /*[host|device]*/,
+                                uint64_t *abunds /*[host|device]*/, bool on_device);
+/* hex md5 of ksize + mins as stored in the Signature JSON (src/lib.rs:72-77,86) */
+SourmashStr kmerminhash_md5sum(KmerMinHash *ptr);
+
+/* ---- sketch collections: packed CSR of sorted u64 hashes in HBM ------------------------------- */
+typedef struct SketchCollection SketchCollection;
+SketchCollection *smgpu_collection_new(void);
+void smgpu_collection_free(SketchCollection *c);
+/* append a copy of the sketch's mins as the next row (the sketch must hold sorted, distinct mins) */
+void smgpu_collection_push(SketchCollection *c, KmerMinHash *mh);
+/* adopt a ready CSR: row i = hashes[offsets[i] .. offsets[i+1]); every row sorted ascending and
+ * distinct (checked); all rows share (num, ksize, is_protein = false, seed, max_hash) */
+SketchCollection *smgpu_collection_from_csr(const uint64_t *hashes /*[host|device]*/,
+                                            const uint64_t *offsets /*[host|device], n_rows + 1 */,
+                                            uint64_t n_rows, uint32_t num, uint32_t ksize, uint64_t seed,
+                                            uint64_t max_hash, bool on_device);
+uint64_t smgpu_collection_len(SketchCollection *c);
+/* device pointers of the packed arrays (valid until the collection is modified or freed) and the
+ * total number of hashes -- what a multi-GPU caller all-gathers */
+uint64_t smgpu_collection_csr(SketchCollection *c, const uint64_t **hashes_dev, const uint64_t **offsets_dev);
+
+/* Block [r0, r0+nr) x [c0, c0+nc) of the all-vs-all matrix, element (i, j) at out[(i-r0)*ld + (j-c0)].
+ * mode 0: rows[i].compare(cols[j])  -- common = |A n B n bottom_num(A u B)|, size = |bottom_num(A u B)|,
+ *         ratio = common / max(1, size)                       (src/lib.rs:470-508)
+ * mode 1: Leaf containment with the ROW as the node -- common = |A n B|, size = |A|, ratio = common/size
+ *         (src/index.rs:146-160; 0/0 = NaN)
+ * Any of common / size / ratio may be NULL.  Incompatible collections record the same error as
+ * kmerminhash_compare (src/lib.rs:176-190) and write nothing. */
+void smgpu_compare_matrix(SketchCollection *rows, uint64_t r0, uint64_t nr, SketchCollection *cols, uint64_t c0,
+                          uint64_t nc, int32_t mode, uint32_t *common /*[host|device]*/,
+                          uint32_t *size /*[host|device]*/, double *ratio /*[host|device]*/, uint64_t ld,
+                          bool out_on_device);
+/* LinearIndex::find (src/index/linear.rs:25-45) for every row of `queries` against `index`:
+ * mode 0 = search_minhashes (node.similarity(query) > threshold), mode 1 =
+ * search_minhashes_containment (node.containment(query) > threshold) (src/index/search.rs:3-9).
+ * hit_offsets (n_queries + 1, host) receives the CSR offsets of the per-query hit lists; hits
+ * (host, capacity hits_cap) the index row ids in insertion order.  Returns the total number of
+ * hits (which may exceed hits_cap: only the first hits_cap are stored). */
+uint64_t smgpu_linear_find(SketchCollection *index, SketchCollection *queries, int32_t mode, double threshold,
+                           uint64_t *hit_offsets, uint64_t *hits, uint64_t hits_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOURMASH_B200_EXT_H */

@@ -1,0 +1,461 @@
+"""sourmash_rust_b200 -- Python binding (ctypes) of this build's libsourmash.so.
+
+The product is the C ABI of include/sourmash.h + include/sourmash_b200.h; this module is the thin
+host-side mirror used by the tests and the benchmark, with the reference crate's names
+(KmerMinHash::new / add_sequence / add_hash / merge / compare / count_common ..., src/lib.rs:141-513;
+Signature, src/lib.rs:546-675).  Every call goes through the C ABI and runs on the GPU; there is
+no Python or CPU implementation behind it -- if the shared library is missing or no CUDA device is
+usable, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsourmash.so")
+
+u64, u32, i32, usz, vp, cb = C.c_uint64, C.c_uint32, C.c_int32, C.c_size_t, C.c_void_p, C.c_bool
+p_u64 = C.POINTER(C.c_uint64)
+
+
+class SourmashStr(C.Structure):
+    _fields_ = [("data", C.POINTER(C.c_char)), ("len", C.c_size_t), ("owned", C.c_bool)]
+
+
+# name -> (restype, argtypes); exactly the declarations of include/sourmash.h ...
+REFERENCE_ABI = {
+    "hash_murmur": (u64, [C.c_char_p, u64]),
+    "kmerminhash_new": (vp, [u32, u32, cb, u64, u64, cb]),
+    "kmerminhash_free": (None, [vp]),
+    "kmerminhash_add_sequence": (None, [vp, C.c_char_p, cb]),
+    "kmerminhash_add_hash": (None, [vp, u64]),
+    "kmerminhash_add_word": (None, [vp, C.c_char_p]),
+    "kmerminhash_add_from": (None, [vp, vp]),
+    "kmerminhash_mins_push": (None, [vp, u64]),
+    "kmerminhash_abunds_push": (None, [vp, u64]),
+    "kmerminhash_merge": (None, [vp, vp]),
+    "kmerminhash_compare": (C.c_double, [vp, vp]),
+    "kmerminhash_count_common": (u64, [vp, vp]),
+    "kmerminhash_intersection": (u64, [vp, vp]),
+    "kmerminhash_get_mins": (p_u64, [vp]),
+    "kmerminhash_get_abunds": (p_u64, [vp]),
+    "kmerminhash_get_mins_size": (usz, [vp]),
+    "kmerminhash_get_abunds_size": (usz, [vp]),
+    "kmerminhash_get_min_idx": (u64, [vp, u64]),
+    "kmerminhash_get_abund_idx": (u64, [vp, u64]),
+    "kmerminhash_is_protein": (cb, [vp]),
+    "kmerminhash_seed": (u64, [vp]),
+    "kmerminhash_track_abundance": (cb, [vp]),
+    "kmerminhash_num": (u32, [vp]),
+    "kmerminhash_ksize": (u32, [vp]),
+    "kmerminhash_max_hash": (u64, [vp]),
+    "signature_new": (vp, []),
+    "signature_free": (None, [vp]),
+    "signature_set_name": (None, [vp, C.c_char_p]),
+    "signature_set_filename": (None, [vp, C.c_char_p]),
+    "signature_push_mh": (None, [vp, vp]),
+    "signature_set_mh": (None, [vp, vp]),
+    "signature_get_name": (SourmashStr, [vp]),
+    "signature_get_filename": (SourmashStr, [vp]),
+    "signature_get_license": (SourmashStr, [vp]),
+    "signature_first_mh": (vp, [vp]),
+    "signature_get_mhs": (C.POINTER(vp), [vp, C.POINTER(usz)]),
+    "signature_eq": (cb, [vp, vp]),
+    "signature_save_json": (SourmashStr, [vp]),
+    "signatures_save_buffer": (SourmashStr, [C.POINTER(vp), usz]),
+    "signatures_load_path": (C.POINTER(vp), [C.c_char_p, cb, usz, C.c_char_p, C.POINTER(usz)]),
+    "signatures_load_buffer": (C.POINTER(vp), [C.c_char_p, usz, cb, usz, C.c_char_p, C.POINTER(usz)]),
+    "sourmash_init": (None, []),
+    "sourmash_err_clear": (None, []),
+    "sourmash_err_get_last_code": (u32, []),
+    "sourmash_err_get_last_message": (SourmashStr, []),
+    "sourmash_err_get_backtrace": (SourmashStr, []),
+    "sourmash_str_free": (None, [C.POINTER(SourmashStr)]),
+    "sourmash_str_from_cstr": (SourmashStr, [C.c_char_p]),
+}
+# ... and of include/sourmash_b200.h
+EXTENSION_ABI = {
+    "smgpu_set_device": (None, [i32]),
+    "smgpu_device": (i32, [C.POINTER(i32)]),
+    "smgpu_launch_count": (u64, []),
+    "smgpu_alloc_pinned": (vp, [usz]),
+    "smgpu_free_pinned": (None, [vp]),
+    "kmerminhash_slice_free": (None, [p_u64]),
+    "kmerminhash_add_sequences": (None, [C.POINTER(vp), usz, vp, vp, u64, cb, cb]),
+    "kmerminhash_add_reads": (None, [C.POINTER(vp), usz, vp, u64, u32, cb, cb]),
+    "kmerminhash_set_mins": (None, [vp, vp, usz, vp, usz]),
+    "kmerminhash_copy_mins": (usz, [vp, vp, vp, cb]),
+    "kmerminhash_md5sum": (SourmashStr, [vp]),
+    "smgpu_collection_new": (vp, []),
+    "smgpu_collection_free": (None, [vp]),
+    "smgpu_collection_push": (None, [vp, vp]),
+    "smgpu_collection_from_csr": (vp, [vp, vp, u64, u32, u32, u64, u64, cb]),
+    "smgpu_collection_len": (u64, [vp]),
+    "smgpu_collection_csr": (u64, [vp, C.POINTER(vp), C.POINTER(vp)]),
+    "smgpu_compare_matrix": (None, [vp, u64, u64, vp, u64, u64, i32, vp, vp, vp, u64, cb]),
+    "smgpu_linear_find": (u64, [vp, vp, i32, C.c_double, vp, vp, u64]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library (raises if it has not been built: see build.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s is missing: run `python -m sourmash_rust_b200.build` (there is no fallback path)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for table in (REFERENCE_ABI, EXTENSION_ABI):
+            for name, (res, args) in table.items():
+                f = getattr(L, name)
+                f.restype, f.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+class SourmashError(Exception):
+    def __init__(self, code, message):
+        super().__init__("[%d] %s" % (code, message))
+        self.code = code
+        self.message = message
+
+
+def _take_str(s: SourmashStr) -> bytes:
+    out = C.string_at(s.data, s.len) if s.len else b""
+    lib().sourmash_str_free(C.byref(s))
+    return out
+
+
+def _check():
+    """The caller protocol of the reference ABI: read the thread-local error after a call."""
+    L = lib()
+    code = L.sourmash_err_get_last_code()
+    if code:
+        msg = _take_str(L.sourmash_err_get_last_message()).decode("utf-8", "replace")
+        L.sourmash_err_clear()
+        raise SourmashError(code, msg)
+
+
+def _call(name, *args):
+    L = lib()
+    L.sourmash_err_clear()
+    r = getattr(L, name)(*args)
+    _check()
+    return r
+
+
+def hash_murmur(kmer: bytes, seed: int = 42) -> int:
+    return _call("hash_murmur", kmer, seed)
+
+
+def set_device(device: int):
+    _call("smgpu_set_device", device)
+
+
+def device_info():
+    sm = i32(0)
+    dev = _call("smgpu_device", C.byref(sm))
+    return dev, sm.value
+
+
+def launch_count() -> int:
+    return lib().smgpu_launch_count()
+
+
+def _vp(x):
+    """Host numpy array / bytes, or a raw integer device pointer -> c_void_p."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    if isinstance(x, np.ndarray):
+        return C.c_void_p(x.ctypes.data)
+    if isinstance(x, (bytes, bytearray)):
+        return C.cast(C.c_char_p(bytes(x)), C.c_void_p)
+    raise TypeError(type(x))
+
+
+class KmerMinHash:
+    """KmerMinHash::new(num, ksize, is_protein, seed, max_hash, track_abundance) (lib.rs:142-149)."""
+
+    def __init__(self, num, ksize, is_protein=False, seed=42, max_hash=0, track_abundance=False, _ptr=None):
+        self._p = _ptr if _ptr is not None else _call("kmerminhash_new", num, ksize, is_protein, seed, max_hash,
+                                                      track_abundance)
+
+    def __del__(self):
+        p, self._p = getattr(self, "_p", None), None
+        if p and _lib is not None:
+            _lib.kmerminhash_free(p)
+
+    # --- scalar getters -------------------------------------------------------------------
+    num = property(lambda s: _call("kmerminhash_num", s._p))
+    ksize = property(lambda s: _call("kmerminhash_ksize", s._p))
+    seed = property(lambda s: _call("kmerminhash_seed", s._p))
+    max_hash = property(lambda s: _call("kmerminhash_max_hash", s._p))
+    is_protein = property(lambda s: _call("kmerminhash_is_protein", s._p))
+
+    def track_abundance(self):
+        return _call("kmerminhash_track_abundance", self._p)
+
+    # --- ingest -----------------------------------------------------------------------------
+    def add_sequence(self, seq: bytes, force=False):
+        if b"\0" in seq:
+            raise ValueError("NUL inside a sequence (the C ABI takes NUL-terminated strings)")
+        _call("kmerminhash_add_sequence", self._p, seq, force)
+
+    def add_hash(self, h):
+        _call("kmerminhash_add_hash", self._p, h)
+
+    def add_word(self, w: bytes):
+        _call("kmerminhash_add_word", self._p, w)
+
+    def add_from(self, other):
+        _call("kmerminhash_add_from", self._p, other._p)
+
+    def add_many(self, hashes):
+        for h in hashes:
+            self.add_hash(int(h))
+
+    def mins_push(self, v):
+        _call("kmerminhash_mins_push", self._p, v)
+
+    def abunds_push(self, v):
+        _call("kmerminhash_abunds_push", self._p, v)
+
+    def set_mins(self, mins, abunds=None):
+        m = np.ascontiguousarray(mins, dtype=np.uint64)
+        a = None if abunds is None else np.ascontiguousarray(abunds, dtype=np.uint64)
+        _call("kmerminhash_set_mins", self._p, _vp(m), m.size, _vp(a), 0 if a is None else a.size)
+
+    def add_reads(self, buf, n_reads, read_len, force=True, on_device=False):
+        add_reads([self], buf, n_reads, read_len, force, on_device)
+
+    def add_sequences(self, buf, offsets, force=True, on_device=False, n_seqs=None):
+        add_sequences([self], buf, offsets, force, on_device, n_seqs)
+
+    # --- combine / compare ----------------------------------------------------------------
+    def merge(self, other):
+        _call("kmerminhash_merge", self._p, other._p)
+
+    def compare(self, other):
+        return _call("kmerminhash_compare", self._p, other._p)
+
+    jaccard = compare  # north_star alias; the reference's name is `compare` (lib.rs:501-508)
+
+    def count_common(self, other):
+        return _call("kmerminhash_count_common", self._p, other._p)
+
+    def intersection_union_size(self, other):
+        """kmerminhash_intersection: the (truncated) union size (ffi.rs:292-309)."""
+        return _call("kmerminhash_intersection", self._p, other._p)
+
+    def containment(self, query):
+        """Leaf<Signature>::containment with self as the node: |self n query| / |self| (index.rs:146-160)."""
+        common = self.count_common(query)
+        n = self.size()
+        return float("nan") if n == 0 else common / n
+
+    similarity = compare  # Leaf<Signature>::similarity (index.rs:131-144)
+
+    # --- read-out ---------------------------------------------------------------------------
+    def size(self):
+        return _call("kmerminhash_get_mins_size", self._p)
+
+    def mins_np(self):
+        n = self.size()
+        out = np.zeros(n, dtype=np.uint64)
+        if n:
+            _call("kmerminhash_copy_mins", self._p, _vp(out), None, False)
+        return out
+
+    def abunds_np(self):
+        if not self.track_abundance():
+            return None
+        n = _call("kmerminhash_get_abunds_size", self._p)
+        if n == 0:
+            return np.zeros(0, dtype=np.uint64)
+        p = _call("kmerminhash_get_abunds", self._p)
+        out = np.ctypeslib.as_array(p, shape=(n,)).copy()
+        lib().kmerminhash_slice_free(p)
+        return out
+
+    @property
+    def mins(self):
+        n = self.size()
+        p = _call("kmerminhash_get_mins", self._p)
+        out = [p[i] for i in range(n)]
+        lib().kmerminhash_slice_free(p)
+        return out
+
+    @property
+    def abunds(self):
+        a = self.abunds_np()
+        return None if a is None else [int(x) for x in a]
+
+    def get_min_idx(self, i):
+        return _call("kmerminhash_get_min_idx", self._p, i)
+
+    def get_abund_idx(self, i):
+        return _call("kmerminhash_get_abund_idx", self._p, i)
+
+    def md5sum(self):
+        return _take_str(_call("kmerminhash_md5sum", self._p)).decode()
+
+
+def _handles(mhs):
+    return (vp * len(mhs))(*[m._p for m in mhs])
+
+
+def add_reads(mhs, buf, n_reads, read_len, force=True, on_device=False):
+    """kmerminhash_add_reads: every read added to every sketch of `mhs` in one pass."""
+    keep = buf if on_device else (buf if isinstance(buf, np.ndarray) else bytes(buf))
+    _call("kmerminhash_add_reads", _handles(mhs), len(mhs), _vp(keep), n_reads, read_len, force, on_device)
+
+
+def add_sequences(mhs, buf, offsets, force=True, on_device=False, n_seqs=None):
+    """kmerminhash_add_sequences: sequence s = buf[offsets[s]:offsets[s+1]]."""
+    if on_device:
+        keep_b, keep_o = buf, offsets
+        assert n_seqs is not None
+    else:
+        keep_b = buf if isinstance(buf, np.ndarray) else bytes(buf)
+        keep_o = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n_seqs = keep_o.size - 1
+    _call("kmerminhash_add_sequences", _handles(mhs), len(mhs), _vp(keep_b), _vp(keep_o), n_seqs, force, on_device)
+
+
+class Signature:
+    """Signature (lib.rs:546-565) behind signature_* (ffi.rs:327-534)."""
+
+    def __init__(self, _ptr=None):
+        self._p = _ptr if _ptr is not None else _call("signature_new")
+
+    def __del__(self):
+        p, self._p = getattr(self, "_p", None), None
+        if p and _lib is not None:
+            _lib.signature_free(p)
+
+    def set_name(self, name: str):
+        _call("signature_set_name", self._p, name.encode())
+
+    def set_filename(self, name: str):
+        _call("signature_set_filename", self._p, name.encode())
+
+    def push_mh(self, mh):
+        _call("signature_push_mh", self._p, mh._p)
+
+    def set_mh(self, mh):
+        _call("signature_set_mh", self._p, mh._p)
+
+    name = property(lambda s: _take_str(_call("signature_get_name", s._p)).decode())
+    filename = property(lambda s: _take_str(_call("signature_get_filename", s._p)).decode())
+    license = property(lambda s: _take_str(_call("signature_get_license", s._p)).decode())
+
+    def first_mh(self):
+        return KmerMinHash(0, 0, _ptr=_call("signature_first_mh", self._p))
+
+    def mhs(self):
+        n = usz(0)
+        arr = _call("signature_get_mhs", self._p, C.byref(n))
+        return [KmerMinHash(0, 0, _ptr=arr[i]) for i in range(n.value)]
+
+    def __eq__(self, other):
+        return bool(_call("signature_eq", self._p, other._p))
+
+    __hash__ = None
+
+    def save_json(self) -> bytes:
+        return _take_str(_call("signature_save_json", self._p))
+
+
+def signatures_save_buffer(sigs) -> bytes:
+    arr = (vp * max(1, len(sigs)))(*[s._p for s in sigs])
+    return _take_str(_call("signatures_save_buffer", arr, len(sigs)))
+
+
+def _wrap_sigs(arr, n):
+    return [Signature(_ptr=arr[i]) for i in range(n)]
+
+
+def signatures_load_buffer(data: bytes, ksize=0, select_moltype=None, ignore_md5sum=False):
+    n = usz(0)
+    mt = None if select_moltype is None else select_moltype.encode()
+    arr = _call("signatures_load_buffer", data, len(data), ignore_md5sum, ksize, mt, C.byref(n))
+    return _wrap_sigs(arr, n.value)
+
+
+def signatures_load_path(path: str, ksize=0, select_moltype=None, ignore_md5sum=False):
+    n = usz(0)
+    mt = None if select_moltype is None else select_moltype.encode()
+    arr = _call("signatures_load_path", path.encode(), ignore_md5sum, ksize, mt, C.byref(n))
+    return _wrap_sigs(arr, n.value)
+
+
+class SketchCollection:
+    """Packed CSR of sorted sketches in HBM (include/sourmash_b200.h)."""
+
+    def __init__(self, _ptr=None):
+        self._p = _ptr if _ptr is not None else _call("smgpu_collection_new")
+
+    def __del__(self):
+        p, self._p = getattr(self, "_p", None), None
+        if p and _lib is not None:
+            _lib.smgpu_collection_free(p)
+
+    @classmethod
+    def from_sketches(cls, mhs):
+        c = cls()
+        for m in mhs:
+            c.push(m)
+        return c
+
+    @classmethod
+    def from_csr(cls, hashes, offsets, n_rows, num, ksize, seed=42, max_hash=0, on_device=False):
+        if not on_device:
+            hashes = np.ascontiguousarray(hashes, dtype=np.uint64)
+            offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        return cls(_ptr=_call("smgpu_collection_from_csr", _vp(hashes), _vp(offsets), n_rows, num, ksize, seed,
+                              max_hash, on_device))
+
+    def push(self, mh):
+        _call("smgpu_collection_push", self._p, mh._p)
+
+    def __len__(self):
+        return _call("smgpu_collection_len", self._p)
+
+    def csr_device(self):
+        h, o = vp(), vp()
+        n = _call("smgpu_collection_csr", self._p, C.byref(h), C.byref(o))
+        return h.value, o.value, n
+
+
+def compare_matrix(rows, cols, mode="compare", r0=0, nr=None, c0=0, nc=None, want=("common", "size", "ratio")):
+    """Block of the all-vs-all matrix as numpy arrays (host output)."""
+    nr = len(rows) - r0 if nr is None else nr
+    nc = len(cols) - c0 if nc is None else nc
+    common = np.zeros((nr, nc), dtype=np.uint32) if "common" in want else None
+    size = np.zeros((nr, nc), dtype=np.uint32) if "size" in want else None
+    ratio = np.zeros((nr, nc), dtype=np.float64) if "ratio" in want else None
+    _call("smgpu_compare_matrix", rows._p, r0, nr, cols._p, c0, nc, 1 if mode == "containment" else 0, _vp(common),
+          _vp(size), _vp(ratio), nc, False)
+    return common, size, ratio
+
+
+def compare_matrix_device(rows, cols, mode, r0, nr, c0, nc, common_ptr, size_ptr, ratio_ptr, ld):
+    """Same, writing into device memory the caller owns (raw pointers, e.g. torch tensors' data_ptr())."""
+    _call("smgpu_compare_matrix", rows._p, r0, nr, cols._p, c0, nc, 1 if mode == "containment" else 0,
+          _vp(common_ptr), _vp(size_ptr), _vp(ratio_ptr), ld, True)
+
+
+def linear_find(index, queries, mode, threshold, hits_cap=None):
+    """LinearIndex::find for every query (linear.rs:25-45); returns a list of hit-id lists."""
+    nq = len(queries)
+    cap = hits_cap if hits_cap is not None else max(1, len(index) * nq)
+    offs = np.zeros(nq + 1, dtype=np.uint64)
+    hits = np.zeros(cap, dtype=np.uint64)
+    total = _call("smgpu_linear_find", index._p, queries._p, 1 if mode == "containment" else 0, float(threshold),
+                  _vp(offs), _vp(hits), cap)
+    assert total <= cap
+    return [hits[int(offs[q]):int(offs[q + 1])].tolist() for q in range(nq)]

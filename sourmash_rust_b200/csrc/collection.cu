@@ -1,0 +1,182 @@
+// collection.cu -- host side of the collection-level operations: CSR packing, the blocked
+// all-vs-all matrix and LinearIndex::find over a whole query batch.
+#include "collection.hpp"
+
+#include <algorithm>
+#include <memory>
+
+#include "kernels.cuh"
+
+namespace smb200 {
+
+void SketchCollection::push(KmerMinHash &mh) {
+    if (!have_params) {
+        ksize = mh.ksize; is_protein = mh.is_protein; seed = mh.seed; max_hash = mh.max_hash;
+        have_params = true;
+    } else {
+        if (ksize != mh.ksize) throw SourmashError(ERR_MISMATCH_KSIZES, "different ksizes cannot be compared");
+        if (is_protein != mh.is_protein) throw SourmashError(ERR_MISMATCH_DNAPROT, "DNA/prot minhashes cannot be compared");
+        if (max_hash != mh.max_hash) throw SourmashError(ERR_MISMATCH_MAXHASH, "mismatch in max_hash; comparison fail");
+        if (seed != mh.seed) throw SourmashError(ERR_MISMATCH_SEED, "mismatch in seed; comparison fail");
+    }
+    const std::vector<uint64_t> &m = mh.mins();
+    for (size_t i = 1; i < m.size(); i++)
+        if (!(m[i - 1] < m[i])) throw_internal("collection rows must hold strictly ascending mins");
+    h_hashes.insert(h_hashes.end(), m.begin(), m.end());
+    h_offsets.push_back(h_hashes.size());
+    h_nums.push_back(mh.num);
+    dirty = true;
+}
+
+void SketchCollection::finalize() {
+    if (!dirty) return;
+    Context &ctx = Context::get();
+    n_rows = h_nums.size();
+    n_hashes = h_hashes.size();
+    d_hashes.reserve((n_hashes + 1) * 8);
+    d_offsets.reserve((n_rows + 1) * 8);
+    d_nums.reserve((n_rows + 1) * 4);
+    if (n_hashes) SM_CUDA(cudaMemcpyAsync(d_hashes.p, h_hashes.data(), n_hashes * 8, cudaMemcpyHostToDevice, ctx.stream));
+    SM_CUDA(cudaMemcpyAsync(d_offsets.p, h_offsets.data(), (n_rows + 1) * 8, cudaMemcpyHostToDevice, ctx.stream));
+    if (n_rows) SM_CUDA(cudaMemcpyAsync(d_nums.p, h_nums.data(), n_rows * 4, cudaMemcpyHostToDevice, ctx.stream));
+    ctx.sync();
+    max_len = 0;
+    for (uint64_t i = 0; i < n_rows; i++) max_len = std::max<uint32_t>(max_len, (uint32_t)(h_offsets[i + 1] - h_offsets[i]));
+    dirty = false;
+}
+
+SketchCollection *SketchCollection::from_csr(const uint64_t *hashes, const uint64_t *offsets, uint64_t n_rows_, uint32_t num,
+                                             uint32_t ksize_, uint64_t seed_, uint64_t max_hash_, bool on_device) {
+    Context &ctx = Context::get();
+    std::unique_ptr<SketchCollection> c(new SketchCollection());
+    c->have_params = true;
+    c->ksize = ksize_; c->seed = seed_; c->max_hash = max_hash_; c->is_protein = false;
+    c->n_rows = n_rows_;
+    c->h_offsets.resize(n_rows_ + 1);
+    const cudaMemcpyKind in_kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (on_device) {
+        SM_CUDA(cudaMemcpyAsync(c->h_offsets.data(), offsets, (n_rows_ + 1) * 8, cudaMemcpyDeviceToHost, ctx.stream));
+        ctx.sync();
+    } else {
+        std::copy(offsets, offsets + n_rows_ + 1, c->h_offsets.begin());
+    }
+    if (c->h_offsets[0] != 0) throw_internal("CSR offsets must start at 0");
+    for (uint64_t i = 0; i < n_rows_; i++) {
+        if (c->h_offsets[i + 1] < c->h_offsets[i]) throw_internal("CSR offsets must be non-decreasing");
+        if (c->h_offsets[i + 1] - c->h_offsets[i] > 0xFFFFFFFFull) throw_internal("CSR row too long");
+        c->max_len = std::max<uint32_t>(c->max_len, (uint32_t)(c->h_offsets[i + 1] - c->h_offsets[i]));
+    }
+    c->n_hashes = c->h_offsets[n_rows_];
+    c->h_nums.assign(n_rows_, num);
+    c->d_hashes.reserve((c->n_hashes + 1) * 8);
+    c->d_offsets.reserve((n_rows_ + 1) * 8);
+    c->d_nums.reserve((n_rows_ + 1) * 4);
+    if (c->n_hashes) SM_CUDA(cudaMemcpyAsync(c->d_hashes.p, hashes, c->n_hashes * 8, in_kind, ctx.stream));
+    SM_CUDA(cudaMemcpyAsync(c->d_offsets.p, c->h_offsets.data(), (n_rows_ + 1) * 8, cudaMemcpyHostToDevice, ctx.stream));
+    if (n_rows_) SM_CUDA(cudaMemcpyAsync(c->d_nums.p, c->h_nums.data(), n_rows_ * 4, cudaMemcpyHostToDevice, ctx.stream));
+    // every row strictly ascending (the two-pointer walk is undefined otherwise)
+    SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_FLAG), 0, 8, ctx.stream));
+    launch_csr_check_sorted(c->d_hashes.as<uint64_t>(), c->d_offsets.as<uint64_t>(), n_rows_, ctx.dsc(SC_FLAG), ctx.stream);
+    ctx.read_scalars();
+    if (ctx.h_scalars[SC_FLAG]) throw_internal("CSR rows must be strictly ascending");
+    c->dirty = false;
+    return c.release();
+}
+
+void SketchCollection::check_compatible(const SketchCollection &o) const {
+    if (!have_params || !o.have_params) return;
+    if (ksize != o.ksize) throw SourmashError(ERR_MISMATCH_KSIZES, "different ksizes cannot be compared");
+    if (is_protein != o.is_protein) throw SourmashError(ERR_MISMATCH_DNAPROT, "DNA/prot minhashes cannot be compared");
+    if (max_hash != o.max_hash) throw SourmashError(ERR_MISMATCH_MAXHASH, "mismatch in max_hash; comparison fail");
+    if (seed != o.seed) throw SourmashError(ERR_MISMATCH_SEED, "mismatch in seed; comparison fail");
+}
+
+void compare_matrix(SketchCollection &rows, uint64_t r0, uint64_t nr, SketchCollection &cols, uint64_t c0, uint64_t nc,
+                    int mode, uint32_t *common, uint32_t *size, double *ratio, uint64_t ld, bool out_on_device) {
+    rows.check_compatible(cols);
+    rows.finalize();
+    cols.finalize();
+    if (r0 + nr > rows.n_rows || c0 + nc > cols.n_rows) throw_internal("compare block outside the collections");
+    if (nr == 0 || nc == 0) return;
+    if (ld < nc) throw_internal("ld smaller than the block width");
+    Context &ctx = Context::get();
+    cudaStream_t st = ctx.stream;
+    if (out_on_device) {
+        launch_compare_cross(rows.d_hashes.as<uint64_t>(), rows.d_offsets.as<uint64_t>(), rows.d_nums.as<uint32_t>(), r0, nr,
+                             cols.d_hashes.as<uint64_t>(), cols.d_offsets.as<uint64_t>(), c0, nc, mode, common, size, ratio,
+                             ld, cols.max_len, ctx.sm_count, st);
+        ctx.sync();
+        return;
+    }
+    // host output: row blocks through device scratch, copied back block by block
+    const uint64_t block_rows = std::max<uint64_t>(1, std::min<uint64_t>(nr, (64ull << 20) / nc));
+    ctx.misc[0].reserve(block_rows * nc * 4);
+    ctx.misc[1].reserve(block_rows * nc * 4);
+    ctx.misc[2].reserve(block_rows * nc * 8);
+    for (uint64_t b0 = 0; b0 < nr; b0 += block_rows) {
+        const uint64_t bn = std::min(block_rows, nr - b0);
+        launch_compare_cross(rows.d_hashes.as<uint64_t>(), rows.d_offsets.as<uint64_t>(), rows.d_nums.as<uint32_t>(),
+                             r0 + b0, bn, cols.d_hashes.as<uint64_t>(), cols.d_offsets.as<uint64_t>(), c0, nc, mode,
+                             common ? ctx.misc[0].as<uint32_t>() : nullptr, size ? ctx.misc[1].as<uint32_t>() : nullptr,
+                             ratio ? ctx.misc[2].as<double>() : nullptr, nc, cols.max_len, ctx.sm_count, st);
+        if (common) SM_CUDA(cudaMemcpy2DAsync(common + b0 * ld, ld * 4, ctx.misc[0].p, nc * 4, nc * 4, bn, cudaMemcpyDeviceToHost, st));
+        if (size) SM_CUDA(cudaMemcpy2DAsync(size + b0 * ld, ld * 4, ctx.misc[1].p, nc * 4, nc * 4, bn, cudaMemcpyDeviceToHost, st));
+        if (ratio) SM_CUDA(cudaMemcpy2DAsync(ratio + b0 * ld, ld * 8, ctx.misc[2].p, nc * 8, nc * 8, bn, cudaMemcpyDeviceToHost, st));
+        ctx.sync();
+    }
+}
+
+uint64_t linear_find(SketchCollection &index, SketchCollection &queries, int mode, double threshold, uint64_t *hit_offsets,
+                     uint64_t *hits, uint64_t hits_cap) {
+    index.check_compatible(queries);
+    index.finalize();
+    queries.finalize();
+    const uint64_t ni = index.n_rows, nq = queries.n_rows;
+    std::vector<std::vector<uint64_t>> per_query(nq);
+    if (ni && nq) {
+        Context &ctx = Context::get();
+        cudaStream_t st = ctx.stream;
+        const uint64_t block_rows = std::max<uint64_t>(1, std::min<uint64_t>(ni, (32ull << 20) / nq));
+        const uint64_t cells = block_rows * nq;
+        ctx.misc[2].reserve(cells * 8);  // ratio, [index row][query]
+        ctx.misc[3].reserve((cells + 1) * 8);  // flags, [query][index row]
+        ctx.misc[4].reserve((cells + 1) * 8);  // scan
+        ctx.misc[5].reserve((cells + 1) * 8);  // compacted cell ids
+        ctx.scan_tmp.reserve(scan_tmp_bytes(cells) + 256);
+        std::vector<uint64_t> cellbuf;
+        for (uint64_t b0 = 0; b0 < ni; b0 += block_rows) {
+            const uint64_t bn = std::min(block_rows, ni - b0);
+            const uint64_t n_cells = bn * nq;
+            launch_compare_cross(index.d_hashes.as<uint64_t>(), index.d_offsets.as<uint64_t>(), index.d_nums.as<uint32_t>(), b0,
+                                 bn, queries.d_hashes.as<uint64_t>(), queries.d_offsets.as<uint64_t>(), 0, nq, mode, nullptr,
+                                 nullptr, ctx.misc[2].as<double>(), nq, queries.max_len, ctx.sm_count, st);
+            launch_threshold_flags_t(ctx.misc[2].as<double>(), bn, nq, threshold, ctx.misc[3].as<uint64_t>(), st);
+            scan_exclusive_u64(ctx.misc[3].as<uint64_t>(), ctx.misc[4].as<uint64_t>(), n_cells, ctx.scan_tmp.p, st);
+            launch_compact_indices(ctx.misc[3].as<uint64_t>(), ctx.misc[4].as<uint64_t>(), n_cells, ctx.misc[5].as<uint64_t>(), st);
+            // number of hits = scan[last] + flag[last]
+            uint64_t tail[2];
+            SM_CUDA(cudaMemcpyAsync(&tail[0], ctx.misc[4].as<uint64_t>() + (n_cells - 1), 8, cudaMemcpyDeviceToHost, st));
+            SM_CUDA(cudaMemcpyAsync(&tail[1], ctx.misc[3].as<uint64_t>() + (n_cells - 1), 8, cudaMemcpyDeviceToHost, st));
+            ctx.sync();
+            const uint64_t n_hit = tail[0] + tail[1];
+            cellbuf.resize(n_hit);
+            if (n_hit) {
+                SM_CUDA(cudaMemcpyAsync(cellbuf.data(), ctx.misc[5].p, n_hit * 8, cudaMemcpyDeviceToHost, st));
+                ctx.sync();
+            }
+            for (uint64_t cell : cellbuf) per_query[cell / bn].push_back(b0 + cell % bn);  // ascending index id per query
+        }
+    }
+    uint64_t total = 0;
+    for (uint64_t q = 0; q < nq; q++) {
+        if (hit_offsets) hit_offsets[q] = total;
+        for (uint64_t id : per_query[q]) {
+            if (hits && total < hits_cap) hits[total] = id;
+            total++;
+        }
+    }
+    if (hit_offsets) hit_offsets[nq] = total;
+    return total;
+}
+
+}  // namespace smb200

@@ -1,0 +1,41 @@
+// SketchCollection -- many sketches packed as one CSR array of sorted u64 hashes in HBM: the
+// operand layout of the all-vs-all compare and linear-search kernels (compare.cu).
+// Replaces, for whole collections, the reference's Vec<Leaf<Signature>> walked pair by pair
+// (src/index/linear.rs:25-45, src/index.rs:131-160).
+#pragma once
+#include <vector>
+
+#include "minhash.hpp"
+
+namespace smb200 {
+
+struct SketchCollection {
+    // parameters every row shares (checked on push; compared by check_compatible)
+    bool have_params = false;
+    uint32_t ksize = 0;
+    bool is_protein = false;
+    uint64_t seed = 0, max_hash = 0;
+    // rows pushed one sketch at a time are staged on the host and uploaded on first use
+    std::vector<uint64_t> h_hashes;
+    std::vector<uint64_t> h_offsets{0};
+    std::vector<uint32_t> h_nums;
+    bool dirty = false;
+    // device CSR
+    DevBuf d_hashes, d_offsets, d_nums;
+    uint64_t n_rows = 0, n_hashes = 0;
+    uint32_t max_len = 0;
+
+    void push(KmerMinHash &mh);
+    static SketchCollection *from_csr(const uint64_t *hashes, const uint64_t *offsets, uint64_t n_rows, uint32_t num,
+                                      uint32_t ksize, uint64_t seed, uint64_t max_hash, bool on_device);
+    void finalize();  // upload staged rows
+    void check_compatible(const SketchCollection &other) const;  // lib.rs:176-190
+};
+
+// see include/sourmash_b200.h
+void compare_matrix(SketchCollection &rows, uint64_t r0, uint64_t nr, SketchCollection &cols, uint64_t c0, uint64_t nc,
+                    int mode, uint32_t *common, uint32_t *size, double *ratio, uint64_t ld, bool out_on_device);
+uint64_t linear_find(SketchCollection &index, SketchCollection &queries, int mode, double threshold,
+                     uint64_t *hit_offsets, uint64_t *hits, uint64_t hits_cap);
+
+}  // namespace smb200

@@ -1,0 +1,121 @@
+// Device plumbing shared by every translation unit: error type, CUDA checks,
+// RAII device buffers, the per-process launch context (stream + scratch).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace smb200 {
+
+// Error codes of the reference (src/errors.rs:28-50, include/sourmash.h:10-27).
+enum ErrorCode : uint32_t {
+    ERR_NO_ERROR = 0,
+    ERR_PANIC = 1,
+    ERR_INTERNAL = 2,
+    ERR_MSG = 3,
+    ERR_UNKNOWN = 4,
+    ERR_MISMATCH_KSIZES = 101,
+    ERR_MISMATCH_DNAPROT = 102,
+    ERR_MISMATCH_MAXHASH = 103,
+    ERR_MISMATCH_SEED = 104,
+    ERR_INVALID_DNA = 1101,
+    ERR_INVALID_PROT = 1102,
+    ERR_IO = 100001,
+    ERR_UTF8 = 100002,
+    ERR_PARSE_INT = 100003,
+    ERR_SERDE = 100004,
+};
+
+// Thrown by the host classes; the C ABI turns it into the thread-local last
+// error (reference: utils.rs:154-166 landingpad).
+struct SourmashError : public std::runtime_error {
+    uint32_t code;
+    SourmashError(uint32_t c, const std::string &msg) : std::runtime_error(msg), code(c) {}
+};
+
+[[noreturn]] inline void throw_internal(const std::string &msg) {
+    throw SourmashError(ERR_INTERNAL, "internal error: " + msg);
+}
+
+#define SM_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            ::smb200::throw_internal(std::string("CUDA: ") + cudaGetErrorString(_e) + " at " +     \
+                                     __FILE__ + ":" + std::to_string(__LINE__) + " (" #expr ")");  \
+        }                                                                                          \
+    } while (0)
+
+// Number of kernels this library has launched (bench.py reports it as gpu_launches).
+extern std::atomic<uint64_t> g_launch_count;
+#define SM_LAUNCHED()                          \
+    do {                                       \
+        ::smb200::g_launch_count.fetch_add(1); \
+        SM_CUDA(cudaGetLastError());           \
+    } while (0)
+
+// Growable raw device allocation (never shrinks; contents not preserved on grow
+// unless keep=true).
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept {
+        if (this != &o) { release(); p = o.p; cap = o.cap; o.p = nullptr; o.cap = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+    }
+    void reserve(size_t bytes, cudaStream_t st = nullptr, bool keep = false, size_t keep_bytes = 0);
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    void reserve(size_t bytes);
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// One per process (per device in use): the stream every kernel of the library
+// is launched on, small device scalars, and reusable scratch.
+struct Context {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    // device scalars: [0] candidate counter, [1] first-invalid base, [2] overflow flag, [3..] misc
+    unsigned long long *d_scalars = nullptr;
+    unsigned long long *h_scalars = nullptr;  // pinned mirror
+    // scratch
+    DevBuf ascii, offsets, sort_tmp_k, sort_tmp_v, scan_tmp, misc[8];
+    std::vector<cudaEvent_t> chunk_events;
+
+    cudaStream_t copy_stream = nullptr;  // host->device staging, overlapped with `stream`
+
+    static Context &get();      // creates on first use; throws if no CUDA device
+    void sync() { SM_CUDA(cudaStreamSynchronize(stream)); }
+    void set_scalar(int idx, unsigned long long v);  // synchronous
+    void read_scalars();                              // d_scalars -> h_scalars, synchronous
+    unsigned long long *dsc(int idx) { return d_scalars + idx; }
+};
+// which device the context binds to when it is created (default: the thread's current device)
+void set_requested_device(int dev);
+
+enum { SC_FIRST_BAD = 0, SC_NUNIQ = 1, SC_TMAX = 2, SC_CNT = 3, SC_FLAG = 4, SC_LEN = 5, SC_PAIR0 = 6, SC_PAIR1 = 7,
+       SC_PAIR2 = 8, SC_THRESH = 9, SC_CAND0 = 10 /* .. SC_CAND0+5: per-handle candidate counters of one batch */,
+       SC_COUNT = 16 };
+
+}  // namespace smb200

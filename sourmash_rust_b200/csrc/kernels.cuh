@@ -1,0 +1,121 @@
+// Launchers of every hand-written sm_100a kernel in the library.
+// All take the stream explicitly; none synchronise.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace smb200 {
+
+// ---- sketch.cu --------------------------------------------------------------------------
+constexpr int SK_TILE = 2048;        // window starts per tile
+constexpr int SK_THREADS = 256;      // 8 windows per thread per tile
+constexpr int SK_CTAS_PER_SM = 6;    // resident persistent CTAs per SM
+constexpr int SK_MAX_GENERIC_K = 8192;
+
+// A batch of sequences resident in device memory as one ASCII buffer.
+//   offsets == nullptr && read_len == 0 : one sequence buf[0, n)
+//   offsets == nullptr && read_len  > 0 : n / read_len fixed-length sequences, back to back
+//   offsets != nullptr                  : sequence s = buf[offsets[s], offsets[s+1]), s < n_seqs
+// buf must be 16-byte aligned and readable up to n rounded up to 16 bytes.
+struct SketchBatch {
+    const uint8_t *buf;
+    uint64_t n;        // bytes in the batch
+    uint64_t n_limit;  // window starts >= n_limit are ignored (force=false replay up to the first bad k-mer)
+    const uint64_t *offsets;
+    uint64_t n_seqs;
+    uint32_t read_len;
+    uint32_t tile_lo;  // first tile this launch covers
+    uint64_t seed;
+    uint64_t pos_base;                  // added to the window start in out.pos / first_bad
+    unsigned long long *first_bad;      // nullable: atomicMin of the first window add_sequence fails on
+};
+// Survivors (hash <= *thr) are appended through *counter; entries beyond cap are dropped but
+// still counted, so the host can detect the overflow and re-run with a larger buffer.
+struct SketchOut {
+    const uint64_t *thr;
+    uint64_t *hash;
+    uint64_t *pos;  // nullable
+    uint64_t cap;
+    unsigned long long *counter;
+};
+uint32_t sketch_tile_count(uint64_t n, uint64_t n_limit);
+uint32_t sketch_tiles_ready(uint32_t K, uint64_t bytes_ready);
+// tiles [sb.tile_lo, tile_hi)
+void launch_sketch(uint32_t K, const SketchBatch &sb, const SketchOut &out, uint32_t tile_hi, int sm_count,
+                   cudaStream_t st);
+bool sketch_has_fast_path(uint32_t K);
+
+// ---- sortops.cu -------------------------------------------------------------------------
+// keep[i] = hashes[i] passing the state-independent gate (h <= max_hash || max_hash == 0) and
+// h <= *thr; compacted (order NOT preserved) into out via *counter.
+void launch_filter_hashes(const uint64_t *hashes, uint64_t n, uint64_t max_hash, const uint64_t *thr,
+                          uint64_t *out_hash, uint64_t *out_pos, unsigned long long *counter, cudaStream_t st);
+// LSD radix sort on key bits [0, end_bit); vals may be null.  Result ends in keys/vals.
+void radix_sort_pairs(uint64_t *keys, uint64_t *vals, uint64_t n, uint64_t *tmp_keys, uint64_t *tmp_vals,
+                      int end_bit, void *scan_tmp, size_t scan_tmp_bytes, cudaStream_t st);
+size_t radix_sort_scan_bytes(uint64_t n);
+// Exclusive prefix sum (u64), in place allowed.  tmp must hold scan_tmp_bytes(n).
+void scan_exclusive_u64(const uint64_t *in, uint64_t *out, uint64_t n, void *tmp, cudaStream_t st);
+size_t scan_tmp_bytes(uint64_t n);
+// Run-length reduce of a sorted key array: unique keys -> ukeys, sum of vals (or run lengths if
+// vals == null) -> usums (must be zeroed by the callee), number of runs -> *n_unique.
+// idx_tmp: n u64 of scratch.
+void reduce_by_key(const uint64_t *keys, const uint64_t *vals, uint64_t n, uint64_t *ukeys, uint64_t *usums,
+                   unsigned long long *n_unique, uint64_t *idx_tmp, void *scan_tmp, cudaStream_t st);
+// min over vals per run (first-occurrence positions); umins pre-filled with ~0 by the callee.
+void min_by_key(const uint64_t *keys, const uint64_t *vals, uint64_t n, const uint64_t *idx, uint64_t *umins,
+                cudaStream_t st);
+void launch_fill_u64(uint64_t *p, uint64_t v, uint64_t n, cudaStream_t st);
+// 1 if keys[0..n) is strictly ascending
+void launch_check_sorted(const uint64_t *keys, uint64_t n, unsigned long long *not_sorted_flag, cudaStream_t st);
+// num+abundance quirk (lib.rs:206-208): see minhash.cu
+// (x is read from device memory: the largest element of the freshly merged sketch)
+void launch_first_new_max(const uint64_t *ukeys, const uint64_t *ufirst, uint64_t nu, const uint64_t *old_keys,
+                          uint64_t n_old, const uint64_t *x, unsigned long long *t_max_plus1, cudaStream_t st);
+void launch_count_key_upto(const uint64_t *keys, const uint64_t *pos, uint64_t n, const uint64_t *x,
+                           const unsigned long long *t_max_plus1, unsigned long long *count, cudaStream_t st);
+void launch_fix_max_abund(uint64_t *abund_x, const uint64_t *ukeys, const uint64_t *ucounts, uint64_t nu,
+                          const uint64_t *x, const unsigned long long *count_upto, cudaStream_t st);
+// ordered replay of add_hash (lib.rs:192-245) for non-standard parameter combinations
+void launch_replay_add_hash(const uint64_t *events, uint64_t n_events, uint32_t num, uint64_t max_hash,
+                            uint64_t *mins, uint64_t *abunds /*nullable*/, unsigned long long *len_io,
+                            cudaStream_t st);
+
+// ---- compare.cu -------------------------------------------------------------------------
+// One pair: out[0] = |A∩B|, out[1] = |A∩B∩bottom_num(A∪B)| (== out[0] when num == 0),
+// out[2] = |combined| = min(num, |A∪B|) or |A∪B| (lib.rs:428-436, 470-499).
+void launch_pair_stats(const uint64_t *a, uint64_t na, const uint64_t *b, uint64_t nb, uint32_t num,
+                       unsigned long long *out3, cudaStream_t st);
+// flags[i] = 1 if a[i] occurs in b (both sorted, distinct)
+void launch_mark_common(const uint64_t *a, uint64_t na, const uint64_t *b, uint64_t nb, uint64_t *flags,
+                        cudaStream_t st);
+// out[i - pre[i]] = vals[i] for every unflagged i (pre = exclusive scan of flags)
+void launch_compact_unflagged(const uint64_t *vals, const uint64_t *flags, const uint64_t *pre, uint64_t n,
+                              uint64_t *out, cudaStream_t st);
+
+// CSR collections of sorted sketches: hashes[offsets[i] .. offsets[i+1]).
+// Block rows [r0, r0+nr) of the row collection x cols [c0, c0+nc) of the column collection; writes
+// common/size (u32) and/or ratio (f64) at out[(i - r0) * ld + (j - c0)].
+// mode 0: KmerMinHash::compare -- common = |A∩B∩bottom_num(A∪B)|, size = |combined|, num = row_nums[i]
+//         (lib.rs:470-508); ratio = common / max(1, size).
+// mode 1: count_common with size = |row| (Leaf containment, index.rs:146-160); ratio = common/|row|.
+void launch_compare_cross(const uint64_t *row_hashes, const uint64_t *row_offsets, const uint32_t *row_nums,
+                          uint64_t r0, uint64_t nr, const uint64_t *col_hashes, const uint64_t *col_offsets,
+                          uint64_t c0, uint64_t nc, int mode, uint32_t *common, uint32_t *size, double *ratio,
+                          uint64_t ld, uint32_t max_col_len, int sm_count, cudaStream_t st);
+// hits of a linear search: flags[j * nr + i] = ratio[i * nq + j] > threshold (strict '>',
+// search.rs:3-9; NaN never hits) -- transposed so that each query's hits are contiguous and in
+// index order
+void launch_threshold_flags_t(const double *ratio, uint64_t nr, uint64_t nq, double threshold, uint64_t *flags,
+                              cudaStream_t st);
+// *flag = 1 if some CSR row is not strictly ascending
+void launch_csr_check_sorted(const uint64_t *hashes, const uint64_t *offsets, uint64_t n_rows, unsigned long long *flag,
+                             cudaStream_t st);
+// out[pre[i]] = i for flagged i (ascending)
+void launch_compact_indices(const uint64_t *flags, const uint64_t *pre, uint64_t n, uint64_t *out,
+                            cudaStream_t st);
+
+// integer-pipe microbenchmark (bench.py: measured INT32 issue peak); returns via out[0] a checksum
+void launch_int_peak(uint32_t *out, int iters, int blocks, int mode, cudaStream_t st);
+
+}  // namespace smb200

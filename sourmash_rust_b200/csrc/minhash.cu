@@ -1,0 +1,675 @@
+// minhash.cu -- KmerMinHash host class: owns the sketch state in HBM and drives the kernels.
+//
+// How the reference's per-hash state machine (add_hash, src/lib.rs:192-245) is reproduced for a
+// whole batch of hashes at once:
+//   scaled sketch (num == 0, max_hash > 0): the result is the set of distinct hashes <= max_hash
+//       with their occurrence counts -- order independent.  Survivors of the sketch kernel are
+//       appended to a per-sketch candidate list and folded into the sorted state lazily
+//       (concatenate + radix sort + run-length reduce).
+//   num sketch (num > 0, max_hash == 0): the result is the `num` smallest distinct hashes.
+//       The kernel filters with a threshold (the current largest element once the sketch is full,
+//       otherwise an estimate that is verified and widened if it kept too few), then the same
+//       sort/reduce and a truncation.  With abundance tracking the reference does NOT count
+//       re-occurrences of the largest element of a full sketch (lib.rs:206-208); that is restored
+//       exactly from first-occurrence positions (see ingest()).
+//   any other combination (both set, or neither): order dependent in the reference, so the
+//       survivors are replayed in stream order by a single-CTA kernel (launch_replay_add_hash).
+#include "minhash.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+#include "kernels.cuh"
+#include "md5.hpp"
+#include "murmur3.cuh"
+
+namespace smb200 {
+
+static const uint64_t U64_MAX = ~0ull;
+static const uint64_t LAZY_CANDIDATES = 1ull << 22;  // scaled sketches fold their candidates in past this
+
+uint64_t hash_murmur_host(const uint8_t *kmer, size_t len, uint64_t seed) {
+    return murmur3_h1_bytes(kmer, (uint64_t)len, seed);
+}
+
+// small device helpers ------------------------------------------------------------------------
+__global__ void set_u64_kernel(unsigned long long *p, unsigned long long v) { *p = v; }
+static void set_u64(unsigned long long *p, unsigned long long v, cudaStream_t st) {
+    set_u64_kernel<<<1, 1, 0, st>>>(p, v);
+    SM_LAUNCHED();
+}
+// thr = largest kept element when the sketch is full, else `fallback`
+__global__ void thr_from_state_kernel(unsigned long long *thr, const uint64_t *mins, uint64_t n_mins, uint32_t num,
+                                      unsigned long long fallback) {
+    *thr = (num != 0 && n_mins >= num) ? mins[num - 1] : fallback;
+}
+__global__ void iota_ones_kernel(uint64_t *v, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) v[i] = 1;
+}
+
+static int bit_length(uint64_t x) {
+    int b = 0;
+    while (x) { b++; x >>= 1; }
+    return b;
+}
+
+// ---------------------------------------------------------------------------------------------
+KmerMinHash::KmerMinHash(uint32_t num_, uint32_t ksize_, bool is_protein_, uint64_t seed_, uint64_t max_hash_,
+                         bool track_abundance)
+    : num(num_), ksize(ksize_), is_protein(is_protein_), seed(seed_), max_hash(max_hash_),
+      has_abunds_(track_abundance) {}
+
+KmerMinHash::~KmerMinHash() {}
+
+KmerMinHash *KmerMinHash::clone() {
+    flush();
+    KmerMinHash *c = new KmerMinHash(num, ksize, is_protein, seed, max_hash, has_abunds_);
+    c->sorted_ = sorted_;
+    if (host_valid_) {
+        c->h_mins_ = h_mins_;
+        c->h_abunds_ = h_abunds_;
+        c->host_valid_ = true;
+        c->dev_valid_ = false;
+        c->n_mins_ = h_mins_.size();
+        c->n_abunds_ = h_abunds_.size();
+    } else {
+        Context &ctx = Context::get();
+        c->d_mins_.reserve((n_mins_ + 1) * 8);
+        c->d_abunds_.reserve((n_abunds_ + 1) * 8);
+        if (n_mins_) SM_CUDA(cudaMemcpyAsync(c->d_mins_.p, d_mins_.p, n_mins_ * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+        if (n_abunds_) SM_CUDA(cudaMemcpyAsync(c->d_abunds_.p, d_abunds_.p, n_abunds_ * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+        ctx.sync();
+        c->n_mins_ = n_mins_;
+        c->n_abunds_ = n_abunds_;
+        c->host_valid_ = false;
+        c->dev_valid_ = true;
+    }
+    return c;
+}
+
+KmerMinHash::Mode KmerMinHash::mode() const {
+    if (num == 0 && max_hash != 0) return MODE_SCALED;
+    if (num != 0 && max_hash == 0) return MODE_NUM;
+    return MODE_REPLAY;
+}
+
+unsigned long long *KmerMinHash::hs(int i) {
+    if (!d_hs_.p) {
+        d_hs_.reserve(64);
+        SM_CUDA(cudaMemsetAsync(d_hs_.p, 0, 64, Context::get().stream));
+    }
+    return d_hs_.as<unsigned long long>() + i;
+}
+
+void KmerMinHash::check_compatible(const KmerMinHash &other) const {
+    if (ksize != other.ksize) throw SourmashError(ERR_MISMATCH_KSIZES, "different ksizes cannot be compared");
+    if (is_protein != other.is_protein) throw SourmashError(ERR_MISMATCH_DNAPROT, "DNA/prot minhashes cannot be compared");
+    if (max_hash != other.max_hash) throw SourmashError(ERR_MISMATCH_MAXHASH, "mismatch in max_hash; comparison fail");
+    if (seed != other.seed) throw SourmashError(ERR_MISMATCH_SEED, "mismatch in seed; comparison fail");
+}
+
+// ---- host <-> device mirrors ------------------------------------------------------------------
+void KmerMinHash::ensure_dev() {
+    if (dev_valid_) return;
+    Context &ctx = Context::get();
+    n_mins_ = h_mins_.size();
+    n_abunds_ = h_abunds_.size();
+    d_mins_.reserve((n_mins_ + 1) * 8);
+    d_abunds_.reserve((n_abunds_ + 1) * 8);
+    if (n_mins_) SM_CUDA(cudaMemcpyAsync(d_mins_.p, h_mins_.data(), n_mins_ * 8, cudaMemcpyHostToDevice, ctx.stream));
+    if (n_abunds_) SM_CUDA(cudaMemcpyAsync(d_abunds_.p, h_abunds_.data(), n_abunds_ * 8, cudaMemcpyHostToDevice, ctx.stream));
+    ctx.sync();
+    dev_valid_ = true;
+}
+
+void KmerMinHash::ensure_host() {
+    flush();
+    if (host_valid_) return;
+    Context &ctx = Context::get();
+    h_mins_.resize(n_mins_);
+    h_abunds_.resize(n_abunds_);
+    if (n_mins_) SM_CUDA(cudaMemcpyAsync(h_mins_.data(), d_mins_.p, n_mins_ * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    if (n_abunds_) SM_CUDA(cudaMemcpyAsync(h_abunds_.data(), d_abunds_.p, n_abunds_ * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    ctx.sync();
+    host_valid_ = true;
+}
+
+void KmerMinHash::require_sorted(const char *what) {
+    if (sorted_ == 1) return;
+    ensure_dev();
+    if (sorted_ == -1) {
+        Context &ctx = Context::get();
+        set_u64(ctx.dsc(SC_FLAG), 0, ctx.stream);
+        launch_check_sorted(d_mins_.as<uint64_t>(), n_mins_, ctx.dsc(SC_FLAG), ctx.stream);
+        ctx.read_scalars();
+        sorted_ = ctx.h_scalars[SC_FLAG] ? 0 : 1;
+    }
+    if (sorted_ == 0)
+        throw_internal(std::string(what) + ": mins are not strictly ascending (raw mins_push of unsorted data); "
+                       "the reference's binary search / two-pointer walk is undefined on such input");
+}
+
+const std::vector<uint64_t> &KmerMinHash::mins() { ensure_host(); return h_mins_; }
+const std::vector<uint64_t> &KmerMinHash::abunds() { ensure_host(); return h_abunds_; }
+size_t KmerMinHash::size() { flush(); return dev_valid_ ? n_mins_ : h_mins_.size(); }
+
+void KmerMinHash::mins_push(uint64_t v) {
+    ensure_host();
+    if (sorted_ == 1 && !h_mins_.empty() && !(h_mins_.back() < v)) sorted_ = -1;
+    h_mins_.push_back(v);
+    dev_valid_ = false;
+}
+void KmerMinHash::abunds_push(uint64_t v) {
+    if (!has_abunds_) return;  // ffi.rs:179-188: only when tracking
+    ensure_host();
+    h_abunds_.push_back(v);
+    dev_valid_ = false;
+}
+void KmerMinHash::set_from_host(const uint64_t *mins_in, size_t n, const uint64_t *abunds_in, size_t n_abunds) {
+    pending_.clear();
+    n_cand_ = 0;
+    h_mins_.assign(mins_in, mins_in + n);
+    if (abunds_in) h_abunds_.assign(abunds_in, abunds_in + n_abunds); else h_abunds_.clear();
+    host_valid_ = true;
+    dev_valid_ = false;
+    sorted_ = std::is_sorted(h_mins_.begin(), h_mins_.end(), [](uint64_t a, uint64_t b) { return a <= b; }) ? 1 : 0;
+    if (n < 2) sorted_ = 1;
+}
+const uint64_t *KmerMinHash::device_mins(size_t *n) {
+    flush(); ensure_dev();
+    *n = n_mins_;
+    return d_mins_.as<uint64_t>();
+}
+const uint64_t *KmerMinHash::device_abunds(size_t *n) {
+    flush(); ensure_dev();
+    *n = n_abunds_;
+    return has_abunds_ ? d_abunds_.as<uint64_t>() : nullptr;
+}
+
+std::string KmerMinHash::md5sum() {
+    ensure_host();
+    Md5 ctx;
+    ctx.update(std::to_string(ksize));
+    for (uint64_t m : h_mins_) ctx.update(std::to_string(m));
+    return ctx.hex();
+}
+
+bool KmerMinHash::equals(KmerMinHash &o) {
+    ensure_host(); o.ensure_host();
+    return num == o.num && ksize == o.ksize && is_protein == o.is_protein && seed == o.seed && max_hash == o.max_hash &&
+           h_mins_ == o.h_mins_ && has_abunds_ == o.has_abunds_ && (!has_abunds_ || h_abunds_ == o.h_abunds_);
+}
+
+// ---- single-hash entry points -----------------------------------------------------------------
+void KmerMinHash::add_hash(uint64_t hash) { pending_.push_back(hash); }
+void KmerMinHash::add_word(const uint8_t *word, size_t len) { add_hash(hash_murmur_host(word, len, seed)); }
+void KmerMinHash::add_many(const uint64_t *hashes, size_t n) { pending_.insert(pending_.end(), hashes, hashes + n); }
+void KmerMinHash::add_from(KmerMinHash &other) {
+    const std::vector<uint64_t> &m = other.mins();
+    pending_.insert(pending_.end(), m.begin(), m.end());
+}
+
+void KmerMinHash::commit(DevBuf &mins, DevBuf &abunds, size_t n_mins, size_t n_abunds) {
+    std::swap(d_mins_, mins);
+    if (has_abunds_) std::swap(d_abunds_, abunds);
+    n_mins_ = n_mins;
+    n_abunds_ = has_abunds_ ? n_abunds : 0;
+    dev_valid_ = true;
+    host_valid_ = false;
+    sorted_ = 1;
+}
+
+void KmerMinHash::reserve_candidates(Context &ctx, uint64_t total) {
+    const size_t bytes = (size_t)(total + 64) * 8;
+    d_cand_hash_.reserve(bytes, ctx.stream, n_cand_ > 0, (size_t)n_cand_ * 8);
+    if (want_pos()) d_cand_pos_.reserve(bytes, ctx.stream, n_cand_ > 0, (size_t)n_cand_ * 8);
+}
+
+void KmerMinHash::replay(Context &ctx, const uint64_t *d_events, uint64_t n_events) {
+    if (!n_events) return;
+    ensure_dev();
+    require_sorted("add_hash");
+    if (has_abunds_ && n_abunds_ != n_mins_) throw_internal("abundances out of step with mins");
+    d_mins_.reserve((n_mins_ + n_events + 1) * 8, ctx.stream, true, n_mins_ * 8);
+    if (has_abunds_) d_abunds_.reserve((n_mins_ + n_events + 1) * 8, ctx.stream, true, n_abunds_ * 8);
+    set_u64(ctx.dsc(SC_LEN), n_mins_, ctx.stream);
+    launch_replay_add_hash(d_events, n_events, num, max_hash, d_mins_.as<uint64_t>(),
+                           has_abunds_ ? d_abunds_.as<uint64_t>() : nullptr, ctx.dsc(SC_LEN), ctx.stream);
+    ctx.read_scalars();
+    n_mins_ = ctx.h_scalars[SC_LEN];
+    n_abunds_ = has_abunds_ ? n_mins_ : 0;
+    host_valid_ = false;
+}
+
+// add_hash events buffered on the host -> candidates (or straight replay)
+void KmerMinHash::flush_pending() {
+    if (pending_.empty()) return;
+    Context &ctx = Context::get();
+    ensure_dev();
+    const uint64_t n = pending_.size();
+    ctx.misc[7].reserve((n + 1) * 8);
+    uint64_t *d_events = ctx.misc[7].as<uint64_t>();
+    SM_CUDA(cudaMemcpyAsync(d_events, pending_.data(), n * 8, cudaMemcpyHostToDevice, ctx.stream));
+    ctx.sync();
+    std::vector<uint64_t>().swap(pending_);
+    if (mode() == MODE_REPLAY) {
+        replay(ctx, d_events, n);
+        return;
+    }
+    require_sorted("add_hash");
+    if (mode() == MODE_NUM && n_cand_) ingest(ctx, false);
+    reserve_candidates(ctx, n_cand_ + n);
+    set_u64(hs(0), n_cand_, ctx.stream);
+    thr_from_state_kernel<<<1, 1, 0, ctx.stream>>>(hs(1), d_mins_.as<uint64_t>(), n_mins_, num,
+                                                   mode() == MODE_SCALED ? max_hash : U64_MAX);
+    SM_LAUNCHED();
+    // the counter starts at n_cand_, so the survivors land behind the candidates already held
+    launch_filter_hashes(d_events, n, max_hash, reinterpret_cast<const uint64_t *>(hs(1)), d_cand_hash_.as<uint64_t>(),
+                         want_pos() ? d_cand_pos_.as<uint64_t>() : nullptr, hs(0), ctx.stream);
+    SM_CUDA(cudaMemcpyAsync(ctx.h_scalars + SC_CAND0, hs(0), 8, cudaMemcpyDeviceToHost, ctx.stream));
+    ctx.sync();
+    n_cand_ = ctx.h_scalars[SC_CAND0];
+    if (mode() == MODE_NUM || n_cand_ > LAZY_CANDIDATES) ingest(ctx, false);
+}
+
+void KmerMinHash::flush() {
+    flush_pending();
+    if (n_cand_) ingest(Context::get(), false);
+}
+
+// ---------------------------------------------------------------------------------------------
+// candidates -> state.  Returns false (nothing committed, candidates dropped) when the threshold
+// was an estimate and turned out too tight to fill a num sketch.
+// ---------------------------------------------------------------------------------------------
+bool KmerMinHash::ingest(Context &ctx, bool thr_is_estimate) {
+    const uint64_t nc = n_cand_;
+    n_cand_ = 0;
+    if (nc == 0) return true;
+    ensure_dev();
+    require_sorted("add_hash");
+    if (has_abunds_ && n_abunds_ != n_mins_) throw_internal("abundances out of step with mins");
+    cudaStream_t st = ctx.stream;
+    const Mode m = mode();
+    const bool quirk = (m == MODE_NUM && has_abunds_);
+    const uint64_t na = n_mins_;
+    const int key_bits = (m == MODE_SCALED) ? bit_length(max_hash) : 64;
+
+    uint64_t *cand = d_cand_hash_.as<uint64_t>();
+    uint64_t *cpos = d_cand_pos_.as<uint64_t>();
+    const uint64_t n_max = na + nc;
+    ctx.sort_tmp_k.reserve((n_max + 1) * 8);
+    ctx.sort_tmp_v.reserve((n_max + 1) * 8);
+    ctx.scan_tmp.reserve(std::max(radix_sort_scan_bytes(n_max), scan_tmp_bytes(n_max)) + 256);
+    for (int i = 0; i < 6; i++) ctx.misc[i].reserve((n_max + 1) * 8);
+    uint64_t *cat_k = ctx.misc[0].as<uint64_t>(), *cat_v = ctx.misc[1].as<uint64_t>();
+    uint64_t *idx = ctx.misc[2].as<uint64_t>();
+    uint64_t *ukeys = ctx.misc[3].as<uint64_t>(), *ucnt = ctx.misc[4].as<uint64_t>(), *ufirst = ctx.misc[5].as<uint64_t>();
+
+    // second operand of the union: the candidates themselves, or (quirk) their run-length form
+    const uint64_t *b_keys = cand;
+    const uint64_t *b_vals = nullptr;  // nullptr = every entry counts 1
+    uint64_t nb = nc;
+    if (quirk) {
+        radix_sort_pairs(cand, cpos, nc, ctx.sort_tmp_k.as<uint64_t>(), ctx.sort_tmp_v.as<uint64_t>(), key_bits,
+                         ctx.scan_tmp.p, ctx.scan_tmp.cap, st);
+        reduce_by_key(cand, nullptr, nc, ukeys, ucnt, ctx.dsc(SC_NUNIQ), idx, ctx.scan_tmp.p, st);
+        launch_fill_u64(ufirst, U64_MAX, nc, st);
+        min_by_key(cand, cpos, nc, idx, ufirst, st);
+        ctx.read_scalars();
+        nb = ctx.h_scalars[SC_NUNIQ];
+        b_keys = ukeys;
+        b_vals = ucnt;
+    }
+    // concatenate state and second operand
+    const uint64_t n_cat = na + nb;
+    if (na) SM_CUDA(cudaMemcpyAsync(cat_k, d_mins_.p, na * 8, cudaMemcpyDeviceToDevice, st));
+    SM_CUDA(cudaMemcpyAsync(cat_k + na, b_keys, nb * 8, cudaMemcpyDeviceToDevice, st));
+    if (has_abunds_) {
+        if (na) SM_CUDA(cudaMemcpyAsync(cat_v, d_abunds_.p, na * 8, cudaMemcpyDeviceToDevice, st));
+        if (b_vals) SM_CUDA(cudaMemcpyAsync(cat_v + na, b_vals, nb * 8, cudaMemcpyDeviceToDevice, st));
+        else {
+            iota_ones_kernel<<<(unsigned)std::min<uint64_t>((nb + 255) / 256, 148 * 16), 256, 0, st>>>(cat_v + na, nb);
+            SM_LAUNCHED();
+        }
+    }
+    radix_sort_pairs(cat_k, has_abunds_ ? cat_v : nullptr, n_cat, ctx.sort_tmp_k.as<uint64_t>(),
+                     ctx.sort_tmp_v.as<uint64_t>(), key_bits, ctx.scan_tmp.p, ctx.scan_tmp.cap, st);
+    DevBuf &out_k = d_mins_alt_, &out_v = d_abunds_alt_;
+    out_k.reserve((n_cat + 1) * 8);
+    out_v.reserve((n_cat + 1) * 8);
+    uint64_t *idx2 = quirk ? ctx.sort_tmp_k.as<uint64_t>() : idx;  // idx still holds the candidates' run ids
+    reduce_by_key(cat_k, has_abunds_ ? cat_v : nullptr, n_cat, out_k.as<uint64_t>(), out_v.as<uint64_t>(),
+                  ctx.dsc(SC_NUNIQ), idx2, ctx.scan_tmp.p, st);
+    ctx.read_scalars();
+    const uint64_t n_new = ctx.h_scalars[SC_NUNIQ];
+    if (m == MODE_NUM && thr_is_estimate && n_new < num) return false;
+    const uint64_t n_keep = (num != 0 && n_new > num) ? num : n_new;
+    if (quirk && n_new >= num) {
+        // lib.rs:206-208: once the sketch is full, re-occurrences of its largest element X are
+        // ignored.  X's count = occurrences up to the moment T the last of the final elements
+        // first appeared (elements already in the old state appeared "before" this batch).
+        const uint64_t *x_ptr = out_k.as<uint64_t>() + (num - 1);
+        set_u64(ctx.dsc(SC_TMAX), 0, st);
+        set_u64(ctx.dsc(SC_CNT), 0, st);
+        launch_first_new_max(ukeys, ufirst, nb, d_mins_.as<uint64_t>(), na, x_ptr, ctx.dsc(SC_TMAX), st);
+        launch_count_key_upto(cand, cpos, nc, x_ptr, ctx.dsc(SC_TMAX), ctx.dsc(SC_CNT), st);
+        launch_fix_max_abund(out_v.as<uint64_t>() + (num - 1), ukeys, ucnt, nb, x_ptr, ctx.dsc(SC_CNT), st);
+        ctx.sync();
+    }
+    commit(out_k, out_v, n_keep, n_keep);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// add_sequence / add_sequences
+// ---------------------------------------------------------------------------------------------
+void KmerMinHash::add_sequence(const uint8_t *seq, size_t len, bool force) {
+    SeqBatch b;
+    b.buf = seq;
+    b.n_seqs = 1;
+    b.n_bytes = len;
+    KmerMinHash *self = this;
+    add_sequences(&self, 1, b, force);
+}
+
+namespace {
+struct PerSketch {
+    uint64_t prev_cand = 0;
+    uint64_t thr_fallback = U64_MAX;
+    bool estimate = false;
+    uint32_t tile_lo = 0;
+    uint32_t tiles_total = 0;
+    uint64_t first_bad = U64_MAX;
+};
+}  // namespace
+
+void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBatch &batch, bool force) {
+    if (n_mhs <= 0) return;
+    if (n_mhs > 6) throw_internal("at most 6 sketches per batch call");
+    for (int i = 0; i < n_mhs; i++) {
+        if (mhs[i]->is_protein)
+            throw_internal("protein (6-frame translated) sketching is outside the GPU hot path of this build");
+        if (mhs[i]->ksize == 0) throw_internal("ksize 0");
+    }
+    const uint64_t n = batch.n_bytes;
+    if (n == 0) return;
+    if (batch.offsets == nullptr && batch.read_len != 0 && n != batch.n_seqs * (uint64_t)batch.read_len)
+        throw_internal("fixed-length batch: n_bytes != n_seqs * read_len");
+    Context &ctx = Context::get();
+    cudaStream_t st = ctx.stream;
+
+    // ---- per-sketch preparation: order-dependent work first, thresholds, candidate space -------
+    std::vector<PerSketch> ps(n_mhs);
+    uint64_t windows_upper = n;
+    for (int i = 0; i < n_mhs; i++) {
+        KmerMinHash &mh = *mhs[i];
+        mh.flush_pending();
+        if (mh.mode() != MODE_SCALED && mh.n_cand_) mh.ingest(ctx, false);
+        mh.ensure_dev();
+        mh.require_sorted("add_sequence");
+        PerSketch &p = ps[i];
+        p.prev_cand = mh.n_cand_;
+        p.tiles_total = sketch_tile_count(n, n);
+        double frac = 1.0;  // expected fraction of windows that survive the threshold
+        if (mh.mode() == MODE_SCALED) {
+            p.thr_fallback = mh.max_hash;
+            frac = (double)mh.max_hash / 18446744073709551616.0;
+        } else if (mh.mode() == MODE_NUM) {
+            const double want = 8.0 * mh.num + 4096.0;
+            if ((double)windows_upper > 4.0 * want) {
+                frac = want / (double)windows_upper;
+                p.thr_fallback = (uint64_t)(frac * 18446744073709551616.0);
+                p.estimate = mh.n_mins_ < mh.num;  // a full sketch uses its own largest element instead
+            }
+        } else if (mh.max_hash) {
+            p.thr_fallback = mh.max_hash;
+            frac = (double)mh.max_hash / 18446744073709551616.0;
+        }
+        mh.reserve_candidates(ctx, mh.n_cand_ + (uint64_t)(frac * 1.25 * (double)windows_upper) + 65536);
+        set_u64(mh.hs(0), mh.n_cand_, st);
+        set_u64(mh.hs(2), U64_MAX, st);
+        thr_from_state_kernel<<<1, 1, 0, st>>>(mh.hs(1), mh.d_mins_.as<uint64_t>(), mh.n_mins_,
+                                               mh.mode() == MODE_NUM ? mh.num : 0, p.thr_fallback);
+        SM_LAUNCHED();
+    }
+
+    // ---- bring the batch to the device (chunked, overlapped with the kernels) ------------------
+    const uint8_t *d_buf = nullptr;
+    const uint64_t *d_off = nullptr;
+    if (batch.on_device) {
+        if ((reinterpret_cast<uintptr_t>(batch.buf) & 15) != 0) throw_internal("device sequence buffer must be 16-byte aligned");
+        d_buf = batch.buf;
+        d_off = batch.offsets;
+    } else {
+        ctx.ascii.reserve(((n + 15) & ~15ull) + 256);
+        d_buf = ctx.ascii.as<uint8_t>();
+        if (batch.offsets) {
+            ctx.offsets.reserve((batch.n_seqs + 1) * 8);
+            SM_CUDA(cudaMemcpyAsync(ctx.offsets.p, batch.offsets, (batch.n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
+            d_off = ctx.offsets.as<uint64_t>();
+        }
+    }
+    auto make_batch = [&](KmerMinHash &mh, uint64_t n_limit, uint32_t tile_lo) {
+        SketchBatch sb;
+        sb.buf = d_buf; sb.n = n; sb.n_limit = n_limit; sb.offsets = d_off; sb.n_seqs = batch.n_seqs;
+        sb.read_len = batch.offsets ? 0 : batch.read_len; sb.tile_lo = tile_lo; sb.seed = mh.seed; sb.pos_base = 0;
+        sb.first_bad = force ? nullptr : mh.hs(2);
+        return sb;
+    };
+    auto make_out = [&](KmerMinHash &mh) {
+        SketchOut o;
+        o.thr = reinterpret_cast<const uint64_t *>(mh.hs(1));
+        o.hash = mh.d_cand_hash_.as<uint64_t>();
+        o.pos = mh.want_pos() ? mh.d_cand_pos_.as<uint64_t>() : nullptr;
+        o.cap = mh.d_cand_hash_.cap / 8;
+        o.counter = mh.hs(0);
+        return o;
+    };
+    const uint64_t CHUNK = 32ull << 20;
+    uint64_t copied = batch.on_device ? n : 0;
+    if (!batch.on_device) SM_CUDA(cudaStreamSynchronize(st));  // scalars / offsets in place before the copy stream races ahead
+    size_t ev_i = 0;
+    do {
+        if (!batch.on_device) {
+            const uint64_t len = std::min<uint64_t>(CHUNK, n - copied);
+            SM_CUDA(cudaMemcpyAsync(const_cast<uint8_t *>(d_buf) + copied, batch.buf + copied, len, cudaMemcpyHostToDevice,
+                                    ctx.copy_stream));
+            copied += len;
+            if (ev_i >= ctx.chunk_events.size()) {
+                cudaEvent_t e;
+                SM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                ctx.chunk_events.push_back(e);
+            }
+            SM_CUDA(cudaEventRecord(ctx.chunk_events[ev_i], ctx.copy_stream));
+            SM_CUDA(cudaStreamWaitEvent(st, ctx.chunk_events[ev_i], 0));
+            ev_i++;
+        }
+        for (int i = 0; i < n_mhs; i++) {
+            KmerMinHash &mh = *mhs[i];
+            PerSketch &p = ps[i];
+            uint32_t hi = (copied >= n) ? p.tiles_total : std::min(p.tiles_total, sketch_tiles_ready(mh.ksize, copied));
+            if (hi <= p.tile_lo) continue;
+            launch_sketch(mh.ksize, make_batch(mh, n, p.tile_lo), make_out(mh), hi, ctx.sm_count, st);
+            p.tile_lo = hi;
+        }
+    } while (copied < n);
+
+    // ---- results: overflow / first failing k-mer / estimate too tight -> re-run from the device copy
+    std::string error_kmer;
+    int error_sketch = -1;
+    for (int i = 0; i < n_mhs; i++) {
+        KmerMinHash &mh = *mhs[i];
+        PerSketch &p = ps[i];
+        uint64_t n_limit = n;
+        for (int attempt = 0;; attempt++) {
+            SM_CUDA(cudaMemcpyAsync(ctx.h_scalars + SC_CAND0, mh.hs(0), 24, cudaMemcpyDeviceToHost, st));
+            ctx.sync();
+            const uint64_t count = ctx.h_scalars[SC_CAND0];
+            const uint64_t fb = ctx.h_scalars[SC_CAND0 + 2];
+            bool rerun = false;
+            if (!force && fb != U64_MAX && n_limit == n) {  // stop where the reference stops (lib.rs:268-273)
+                p.first_bad = fb;
+                n_limit = fb;
+                rerun = true;
+            }
+            if (count > mh.d_cand_hash_.cap / 8) {
+                mh.n_cand_ = p.prev_cand;
+                mh.reserve_candidates(ctx, count + 65536);
+                rerun = true;
+            }
+            if (!rerun) {
+                mh.n_cand_ = count;
+                mh.host_valid_ = mh.host_valid_ && count == p.prev_cand;
+                if (mh.mode() == MODE_SCALED) {
+                    if (mh.n_cand_ > LAZY_CANDIDATES) mh.ingest(ctx, false);
+                    break;
+                }
+                if (mh.mode() == MODE_REPLAY) {
+                    // events in stream order: sort (pos, hash) by pos, replay
+                    const uint64_t ne = mh.n_cand_;
+                    mh.n_cand_ = 0;
+                    if (ne) {
+                        ctx.sort_tmp_k.reserve((ne + 1) * 8);
+                        ctx.sort_tmp_v.reserve((ne + 1) * 8);
+                        ctx.scan_tmp.reserve(radix_sort_scan_bytes(ne) + 256);
+                        radix_sort_pairs(mh.d_cand_pos_.as<uint64_t>(), mh.d_cand_hash_.as<uint64_t>(), ne,
+                                         ctx.sort_tmp_k.as<uint64_t>(), ctx.sort_tmp_v.as<uint64_t>(), bit_length(n),
+                                         ctx.scan_tmp.p, ctx.scan_tmp.cap, st);
+                        mh.replay(ctx, mh.d_cand_hash_.as<uint64_t>(), ne);
+                    }
+                    break;
+                }
+                // MODE_NUM
+                if (mh.ingest(ctx, p.estimate)) break;
+                // estimate kept too few distinct hashes: widen and go again
+                p.thr_fallback = (p.thr_fallback > (U64_MAX >> 6)) ? U64_MAX : (p.thr_fallback << 6);
+                if (p.thr_fallback == U64_MAX) p.estimate = false;
+                mh.reserve_candidates(ctx, (uint64_t)((double)p.thr_fallback / 18446744073709551616.0 * 1.25 * (double)n) + 65536);
+            }
+            if (attempt > 40) throw_internal("sketch re-run loop did not converge");
+            // re-run over the device-resident batch
+            set_u64(mh.hs(0), p.prev_cand, st);
+            set_u64(mh.hs(2), U64_MAX, st);
+            thr_from_state_kernel<<<1, 1, 0, st>>>(mh.hs(1), mh.d_mins_.as<uint64_t>(), mh.n_mins_,
+                                                   mh.mode() == MODE_NUM ? mh.num : 0, p.thr_fallback);
+            SM_LAUNCHED();
+            SketchBatch sb = make_batch(mh, n_limit, 0);
+            sb.first_bad = nullptr;
+            launch_sketch(mh.ksize, sb, make_out(mh), sketch_tile_count(n, n_limit), ctx.sm_count, st);
+        }
+        if (p.first_bad != U64_MAX && error_sketch < 0) {
+            error_sketch = i;
+            std::vector<uint8_t> kmer(mh.ksize);
+            SM_CUDA(cudaMemcpyAsync(kmer.data(), d_buf + p.first_bad, mh.ksize, cudaMemcpyDeviceToHost, st));
+            ctx.sync();
+            for (auto &c : kmer) if (c >= 'a' && c <= 'z') c = (uint8_t)(c - 32);  // lib.rs:253-256
+            error_kmer.assign(kmer.begin(), kmer.end());
+        }
+    }
+    if (error_sketch >= 0)
+        throw SourmashError(ERR_INVALID_DNA, "invalid DNA character in input k-mer: " + error_kmer);
+}
+
+// ---------------------------------------------------------------------------------------------
+// merge / compare
+// ---------------------------------------------------------------------------------------------
+void KmerMinHash::merge(KmerMinHash &other) {
+    check_compatible(other);
+    flush(); other.flush();
+    ensure_dev(); other.ensure_dev();
+    require_sorted("merge"); other.require_sorted("merge");
+    Context &ctx = Context::get();
+    cudaStream_t st = ctx.stream;
+    const uint64_t na = n_mins_, nb = other.n_mins_;
+    const bool sa = has_abunds_, ob = other.has_abunds_;
+    if (sa && n_abunds_ != na) throw_internal("abundances out of step with mins");
+    if (ob && other.n_abunds_ != nb) throw_internal("abundances out of step with mins");
+    const bool both = sa && ob;
+    const uint64_t n_cat = na + nb;
+    ctx.sort_tmp_k.reserve((n_cat + 1) * 8);
+    ctx.sort_tmp_v.reserve((n_cat + 1) * 8);
+    ctx.scan_tmp.reserve(std::max(radix_sort_scan_bytes(n_cat), scan_tmp_bytes(n_cat)) + 256);
+    for (int i = 0; i < 4; i++) ctx.misc[i].reserve((n_cat + 1) * 8);
+    uint64_t *cat_k = ctx.misc[0].as<uint64_t>(), *cat_v = ctx.misc[1].as<uint64_t>(), *idx = ctx.misc[2].as<uint64_t>();
+    if (na) SM_CUDA(cudaMemcpyAsync(cat_k, d_mins_.p, na * 8, cudaMemcpyDeviceToDevice, st));
+    if (nb) SM_CUDA(cudaMemcpyAsync(cat_k + na, other.d_mins_.p, nb * 8, cudaMemcpyDeviceToDevice, st));
+    if (both) {
+        if (na) SM_CUDA(cudaMemcpyAsync(cat_v, d_abunds_.p, na * 8, cudaMemcpyDeviceToDevice, st));
+        if (nb) SM_CUDA(cudaMemcpyAsync(cat_v + na, other.d_abunds_.p, nb * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    radix_sort_pairs(cat_k, both ? cat_v : nullptr, n_cat, ctx.sort_tmp_k.as<uint64_t>(), ctx.sort_tmp_v.as<uint64_t>(),
+                     64, ctx.scan_tmp.p, ctx.scan_tmp.cap, st);
+    DevBuf &out_k = d_mins_alt_, &out_v = d_abunds_alt_;
+    out_k.reserve((n_cat + 1) * 8);
+    out_v.reserve((n_cat + 1) * 8);
+    // the reference sums abundances where both sides track them (lib.rs:354-367)
+    uint64_t *sums = both ? out_v.as<uint64_t>() : ctx.misc[3].as<uint64_t>();
+    reduce_by_key(cat_k, both ? cat_v : nullptr, n_cat, out_k.as<uint64_t>(), sums, ctx.dsc(SC_NUNIQ), idx, ctx.scan_tmp.p, st);
+    ctx.read_scalars();
+    const uint64_t n_union = ctx.h_scalars[SC_NUNIQ];
+    const uint64_t common = n_cat - n_union;
+    uint64_t n_ab = 0;
+    if (both) {
+        n_ab = n_union;  // NOT truncated with mins (lib.rs:395-400 TODO)
+    } else if (sa || ob) {
+        // only one side tracks: the reference pushes that side's abundance for the elements only
+        // that side holds, and nothing for the others (lib.rs:343-383)
+        const uint64_t *tk = sa ? d_mins_.as<uint64_t>() : other.d_mins_.as<uint64_t>();
+        const uint64_t *tv = sa ? d_abunds_.as<uint64_t>() : other.d_abunds_.as<uint64_t>();
+        const uint64_t nt = sa ? na : nb;
+        const uint64_t *ok = sa ? other.d_mins_.as<uint64_t>() : d_mins_.as<uint64_t>();
+        const uint64_t no = sa ? nb : na;
+        uint64_t *flags = ctx.misc[0].as<uint64_t>(), *pre = ctx.misc[1].as<uint64_t>();
+        launch_mark_common(tk, nt, ok, no, flags, st);
+        scan_exclusive_u64(flags, pre, nt, ctx.scan_tmp.p, st);
+        launch_compact_unflagged(tv, flags, pre, nt, out_v.as<uint64_t>(), st);
+        ctx.sync();
+        n_ab = nt - common;
+    }
+    const uint64_t n_keep = (num != 0 && n_union >= num) ? num : n_union;
+    has_abunds_ = true;  // lib.rs:393,400: abunds becomes Some(..) unconditionally
+    commit(out_k, out_v, n_keep, n_ab);
+}
+
+static void pair_stats(KmerMinHash &a, KmerMinHash &b, uint32_t num, uint64_t out[3]) {
+    size_t na, nb;
+    const uint64_t *da = a.device_mins(&na);
+    const uint64_t *db = b.device_mins(&nb);
+    Context &ctx = Context::get();
+    launch_pair_stats(da, na, db, nb, num, ctx.dsc(SC_PAIR0), ctx.stream);
+    ctx.read_scalars();
+    out[0] = ctx.h_scalars[SC_PAIR0];
+    out[1] = ctx.h_scalars[SC_PAIR1];
+    out[2] = ctx.h_scalars[SC_PAIR2];
+}
+
+uint64_t KmerMinHash::count_common(KmerMinHash &other) {
+    check_compatible(other);
+    flush(); other.flush();
+    require_sorted("count_common"); other.require_sorted("count_common");
+    uint64_t o[3];
+    pair_stats(*this, other, 0, o);
+    return o[0];
+}
+
+std::pair<uint64_t, uint64_t> KmerMinHash::intersection_size(KmerMinHash &other) {
+    check_compatible(other);
+    flush(); other.flush();
+    require_sorted("intersection"); other.require_sorted("intersection");
+    uint64_t o[3];
+    pair_stats(*this, other, num, o);  // uses self.num (lib.rs:473-480)
+    return {o[1], o[2]};
+}
+
+double KmerMinHash::compare(KmerMinHash &other) {
+    const std::pair<uint64_t, uint64_t> cs = intersection_size(other);
+    return (double)cs.first / (double)std::max<uint64_t>(1, cs.second);  // lib.rs:504
+}
+
+double KmerMinHash::containment(KmerMinHash &other) {
+    const uint64_t common = count_common(other);
+    return (double)common / (double)size();  // index.rs:152-154 (0/0 -> NaN)
+}
+
+}  // namespace smb200

@@ -1,0 +1,108 @@
+// MurmurHash3 x64_128 (seed as u64, h1 = h2 = seed) -- host + device.
+//
+// Replaces the third-party crate call `murmurhash3_x64_128(kmer, seed).0`
+// (reference src/lib.rs:29,33-35; crate murmurhash3 ~0.0.5, Cargo.toml:49).
+// Written from the published algorithm; pinned by tests/test.rs:5 and the
+// SMHasher verification value (see oracle/oracle.c).
+//
+// Two entry points:
+//   murmur3_h1_bytes(ptr, len, seed)   any byte string (host add_word / hash_murmur,
+//                                      generic-k device kernel)
+//   murmur3_h1_words<K>(w, seed)       K bytes already held as little-endian
+//                                      32-bit words in registers (templated kernel);
+//                                      bytes past K in the last word must be zero.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SM_HD __host__ __device__ __forceinline__
+#else
+#define SM_HD inline
+#endif
+
+namespace smb200 {
+
+constexpr uint64_t MM_C1 = 0x87c37b91114253d5ULL;
+constexpr uint64_t MM_C2 = 0x4cf5ad432745937fULL;
+
+SM_HD uint64_t mm_rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+
+SM_HD uint64_t mm_fmix64(uint64_t k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return k;
+}
+
+SM_HD uint64_t mm_mix_k1(uint64_t k1) {
+    k1 *= MM_C1; k1 = mm_rotl64(k1, 31); k1 *= MM_C2;
+    return k1;
+}
+SM_HD uint64_t mm_mix_k2(uint64_t k2) {
+    k2 *= MM_C2; k2 = mm_rotl64(k2, 33); k2 *= MM_C1;
+    return k2;
+}
+SM_HD void mm_body(uint64_t &h1, uint64_t &h2, uint64_t k1, uint64_t k2) {
+    h1 ^= mm_mix_k1(k1);
+    h1 = mm_rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+    h2 ^= mm_mix_k2(k2);
+    h2 = mm_rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+}
+SM_HD uint64_t mm_final_h1(uint64_t h1, uint64_t h2, uint64_t len) {
+    h1 ^= len; h2 ^= len;
+    h1 += h2; h2 += h1;
+    h1 = mm_fmix64(h1); h2 = mm_fmix64(h2);
+    h1 += h2;
+    return h1;  // .0 of the (h1, h2) pair
+}
+
+// Generic byte-string version (unaligned safe: assembles words bytewise).
+SM_HD uint64_t murmur3_h1_bytes(const uint8_t *data, uint64_t len, uint64_t seed) {
+    uint64_t h1 = seed, h2 = seed;
+    const uint64_t nblocks = len / 16;
+    for (uint64_t b = 0; b < nblocks; b++) {
+        uint64_t k1 = 0, k2 = 0;
+        for (int j = 7; j >= 0; j--) {
+            k1 = (k1 << 8) | data[16 * b + j];
+            k2 = (k2 << 8) | data[16 * b + 8 + j];
+        }
+        mm_body(h1, h2, k1, k2);
+    }
+    const uint8_t *tail = data + nblocks * 16;
+    const int rem = (int)(len & 15);
+    uint64_t k1 = 0, k2 = 0;
+    for (int j = rem - 1; j >= 8; j--) k2 = (k2 << 8) | tail[j];
+    for (int j = (rem < 8 ? rem : 8) - 1; j >= 0; j--) k1 = (k1 << 8) | tail[j];
+    if (rem > 8) h2 ^= mm_mix_k2(k2);
+    if (rem > 0) h1 ^= mm_mix_k1(k1);
+    return mm_final_h1(h1, h2, len);
+}
+
+// K bytes held in ceil(K/4) little-endian 32-bit words; fully unrolled.
+template <int K>
+SM_HD uint64_t murmur3_h1_words(const uint32_t *w, uint64_t seed) {
+    constexpr int NB = K / 16;
+    constexpr int REM = K % 16;
+    uint64_t h1 = seed, h2 = seed;
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        const uint64_t k1 = ((uint64_t)w[4 * b + 1] << 32) | w[4 * b + 0];
+        const uint64_t k2 = ((uint64_t)w[4 * b + 3] << 32) | w[4 * b + 2];
+        mm_body(h1, h2, k1, k2);
+    }
+    if (REM > 8) {
+        const uint32_t hi = (REM > 12) ? w[4 * NB + 3] : 0u;
+        const uint64_t k2 = ((uint64_t)hi << 32) | w[4 * NB + 2];
+        h2 ^= mm_mix_k2(k2);
+    }
+    if (REM > 0) {
+        const uint32_t hi = (REM > 4) ? w[4 * NB + 1] : 0u;
+        const uint64_t k1 = ((uint64_t)hi << 32) | w[4 * NB + 0];
+        h1 ^= mm_mix_k1(k1);
+    }
+    return mm_final_h1(h1, h2, (uint64_t)K);
+}
+
+}  // namespace smb200

@@ -1,0 +1,391 @@
+// sketch.cu -- the hot kernel: ASCII DNA in HBM -> canonical k-mers -> MurmurHash3 x64_128
+// -> threshold filter -> survivor list.  One launch covers a whole batch of sequences.
+//
+// Replaces the per-k-mer body of KmerMinHash::add_sequence (reference src/lib.rs:252-274):
+// the uppercase copy (lib.rs:253-256), _checkdna (lib.rs:795-804), the allocating revcomp
+// (lib.rs:677-689), the lexicographic min (lib.rs:263-267), _hash_murmur (lib.rs:33-35) and the
+// acceptance gate of add_hash (lib.rs:198-209).  The sorted insert of add_hash is done for all
+// survivors at once by the sort / reduce / merge kernels of sortops.cu.
+//
+// Shape of the kernel (sm_100a):
+//   * persistent CTAs, grid = SM count x resident CTAs; each CTA walks tiles of TILE window
+//     starts round-robin;
+//   * the tile's TILE + halo ASCII bytes are brought HBM -> shared memory by ONE TMA bulk copy
+//     (cp.async.bulk, completion on an mbarrier); the copy of the NEXT tile is issued as soon as
+//     the current raw bytes have been consumed, so it overlaps the whole hashing phase;
+//   * the CTA turns the raw bytes into five shared-memory views (kmer_bits.cuh): upper-cased
+//     forward ASCII, reverse-complement ASCII, both strands 2-bit packed, and an invalid-base
+//     bitmap; a second short phase dilates the invalid/sequence-end bitmaps into a
+//     "window start is unusable" bitmap;
+//   * one thread per k-mer: one bit test for validity, two unaligned 2-bit extractions + one
+//     integer compare for the canonical strand, one unaligned ASCII extraction of the chosen
+//     strand, MurmurHash3 x64_128 fully unrolled for the compile-time K, `<= threshold`,
+//     warp-aggregated append of the survivors.
+// Bound: the integer pipes (about 135 instructions per k-mer at k=31 for 1 byte of HBM
+// traffic), see DESIGN.md.
+#include "device.hpp"
+#include "kernels.cuh"
+#include "kmer_bits.cuh"
+#include "murmur3.cuh"
+
+namespace smb200 {
+
+// ---------------------------------------------------------------------------------------
+// mbarrier / TMA bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global -> shared; dst/src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// shared-memory tile
+// ---------------------------------------------------------------------------------------
+struct TileViews {
+    uint8_t *raw;     // B bytes, 128-byte aligned (TMA destination)
+    uint32_t *fA;     // B/4 + 2 words
+    uint32_t *rA;     // B/4 + 2 words
+    uint32_t *f2;     // B/16 + 2 words
+    uint32_t *r2;     // B/16 + 2 words
+    uint32_t *bad;    // B/32 + 3 words   invalid-base bitmap
+    uint32_t *end;    // B/32 + 3 words   "last base of a sequence" bitmap
+    uint32_t *sbad;   // TILE/32 words    window start unusable
+};
+__host__ __device__ constexpr int tile_bases(int K) { return SK_TILE + ((K - 1 + 15) / 16) * 16; }
+__host__ __device__ constexpr size_t tile_smem_bytes(int B) {
+    return (size_t)B                      // raw
+           + 2 * ((size_t)B + 8)          // fA, rA
+           + 2 * ((size_t)B / 4 + 8)      // f2, r2
+           + 2 * ((size_t)(B + 31) / 32 * 4 + 12)  // bad, end
+           + SK_TILE / 8                  // sbad
+           + 128;                         // alignment slack
+}
+__device__ __forceinline__ TileViews carve_tile(uint8_t *base, int B) {
+    TileViews v;
+    uint8_t *p = base;
+    v.raw = p; p += B;                                   // B is a multiple of 16
+    v.fA = reinterpret_cast<uint32_t *>(p); p += B + 8;
+    v.rA = reinterpret_cast<uint32_t *>(p); p += B + 8;
+    v.f2 = reinterpret_cast<uint32_t *>(p); p += B / 4 + 8;
+    v.r2 = reinterpret_cast<uint32_t *>(p); p += B / 4 + 8;
+    const int wm = (B + 31) / 32 + 3;
+    v.bad = reinterpret_cast<uint32_t *>(p); p += wm * 4;
+    v.end = reinterpret_cast<uint32_t *>(p); p += wm * 4;
+    v.sbad = reinterpret_cast<uint32_t *>(p);
+    return v;
+}
+
+// bytes the TMA copy of tile `tile` moves (0 when the tile starts at or after the buffer end)
+__device__ __forceinline__ uint32_t tile_copy_bytes(uint64_t t0, uint64_t n, int B) {
+    if (t0 >= n) return 0;
+    const uint64_t left = ((n - t0) + 15) & ~15ull;
+    return (uint32_t)(left < (uint64_t)B ? left : (uint64_t)B);
+}
+
+// raw -> fA, rA, f2, r2, bad, end   (all threads; ends with the views complete after a barrier
+// by the caller)
+__device__ __forceinline__ void build_views(const TileViews &v, int B, uint64_t t0, const SketchBatch &sb) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int wm = (B + 31) / 32 + 3;
+    for (int w = tid; w < wm; w += nthr) v.end[w] = 0;
+    for (int w = (B + 31) / 32 + tid; w < wm; w += nthr) v.bad[w] = 0xFFFFFFFFu;  // past the staged bases
+    if (tid < 2) {  // slack words unaligned extraction may touch
+        v.fA[B / 4 + tid] = 0; v.rA[B / 4 + tid] = 0; v.f2[B / 16 + tid] = 0; v.r2[B / 16 + tid] = 0;
+    }
+    const uint32_t *raw32 = reinterpret_cast<const uint32_t *>(v.raw);
+    uint16_t *f2h = reinterpret_cast<uint16_t *>(v.f2);
+    uint16_t *r2h = reinterpret_cast<uint16_t *>(v.r2);
+    uint8_t *badb = reinterpret_cast<uint8_t *>(v.bad);
+    const int groups = B / 8;
+    for (int g = tid; g < groups; g += nthr) {
+        const Oct o = classify8(raw32[2 * g], raw32[2 * g + 1]);
+        uint32_t bad8 = o.bad8;
+        const uint64_t b0 = t0 + (uint64_t)g * 8;
+        if (b0 + 8 > sb.n) bad8 |= (b0 >= sb.n) ? 0xFFu : (0xFFu << (uint32_t)(sb.n - b0)) & 0xFFu;
+        v.fA[2 * g] = o.fA0;
+        v.fA[2 * g + 1] = o.fA1;
+        const int rg = groups - 1 - g;
+        v.rA[2 * rg] = o.rA0;
+        v.rA[2 * rg + 1] = o.rA1;
+        f2h[g] = (uint16_t)o.f2;
+        r2h[rg] = (uint16_t)o.r2;
+        badb[g] = (uint8_t)bad8;
+    }
+    if (B % 32) {  // B is a multiple of 16: the upper half of the last bad word is past the tile
+        if (tid == 0) reinterpret_cast<uint16_t *>(v.bad)[B / 16] = 0xFFFFu;
+    }
+}
+
+// mark the last base of every sequence that ends inside [t0, t0 + B)  (after a barrier that
+// follows the zeroing in build_views)
+__device__ __forceinline__ void mark_sequence_ends(const TileViews &v, int B, uint64_t t0, const SketchBatch &sb) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const uint64_t hi = t0 + (uint64_t)B;  // exclusive
+    if (sb.offsets == nullptr && sb.read_len == 0) {  // one contiguous sequence ending at n
+        if (tid == 0 && sb.n - 1 >= t0 && sb.n - 1 < hi) {
+            const uint32_t j = (uint32_t)(sb.n - 1 - t0);
+            atomicOr(&v.end[j >> 5], 1u << (j & 31));
+        }
+    } else if (sb.offsets == nullptr) {
+        const uint64_t L = sb.read_len;
+        // ends are at m*L - 1 for m >= 1; first m with m*L - 1 >= t0
+        uint64_t m = (t0 + 1 + L - 1) / L;
+        if (m == 0) m = 1;
+        for (m += tid;; m += nthr) {
+            const uint64_t e = m * L - 1;
+            if (e >= hi || e >= sb.n) break;
+            const uint32_t j = (uint32_t)(e - t0);
+            atomicOr(&v.end[j >> 5], 1u << (j & 31));
+        }
+    } else {
+        // first sequence s with offsets[s+1] > t0 (its end is the first that can lie in the tile)
+        uint64_t a = 0, b = sb.n_seqs;  // invariant: offsets[a'] <= t0 for a' <= a ... search on s+1
+        while (a < b) {
+            const uint64_t mid = (a + b) >> 1;
+            if (sb.offsets[mid + 1] > t0) b = mid; else a = mid + 1;
+        }
+        for (uint64_t s = a + tid; s < sb.n_seqs; s += nthr) {
+            const uint64_t e1 = sb.offsets[s + 1];  // exclusive end, > t0
+            if (e1 - 1 >= hi) break;
+            const uint32_t j = (uint32_t)(e1 - 1 - t0);
+            atomicOr(&v.end[j >> 5], 1u << (j & 31));
+        }
+    }
+}
+
+// sbad[w] for the TILE window starts; reports the first window that the reference would fail on
+// (an invalid base inside a window that lies wholly inside one sequence, lib.rs:268-273)
+__device__ __forceinline__ void build_start_bitmap(const TileViews &v, int K, uint64_t t0, const SketchBatch &sb) {
+    for (int w = threadIdx.x; w < SK_TILE / 32; w += blockDim.x) {
+        uint32_t hasbad, crosses;
+        if (K <= 64) {
+            hasbad = dilate_word(v.bad[w], v.bad[w + 1], v.bad[w + 2], K);
+            crosses = dilate_word(v.end[w], v.end[w + 1], v.end[w + 2], K - 1);
+        } else {  // generic long k: bit by bit over prefix words
+            hasbad = 0; crosses = 0;
+            for (int p = 0; p < 32; p++) {
+                const int q = w * 32 + p;
+                bool hb = false, cr = false;
+                for (int j = q; j < q + K; j++) {
+                    const uint32_t bit = 1u << (j & 31);
+                    hb |= (v.bad[j >> 5] & bit) != 0;
+                    if (j < q + K - 1) cr |= (v.end[j >> 5] & bit) != 0;
+                }
+                hasbad |= (uint32_t)hb << p;
+                crosses |= (uint32_t)cr << p;
+            }
+        }
+        // starts at or beyond the limit / the buffer are never used
+        const uint64_t q0 = t0 + (uint64_t)w * 32;
+        uint32_t beyond = 0;
+        if (q0 + 32 > sb.n_limit) beyond = (q0 >= sb.n_limit) ? 0xFFFFFFFFu : (0xFFFFFFFFu << (uint32_t)(sb.n_limit - q0));
+        v.sbad[w] = hasbad | crosses | beyond;
+        const uint32_t err = hasbad & ~crosses & ~beyond;
+        if (err && sb.first_bad)
+            atomicMin(sb.first_bad, (unsigned long long)(sb.pos_base + q0 + (uint32_t)(__ffs(err) - 1)));
+    }
+}
+
+__device__ __forceinline__ void append_survivor(bool pass, uint64_t h, uint64_t pos, const SketchBatch &sb,
+                                                const SketchOut &out, int lane) {
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, pass);
+    if (bal) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(out.counter, (unsigned long long)__popc(bal));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (pass) {
+            const unsigned long long idx = base + __popc(bal & ((1u << lane) - 1u));
+            if (idx < out.cap) {
+                out.hash[idx] = h;
+                if (out.pos) out.pos[idx] = sb.pos_base + pos;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// fast path: compile-time K
+// ---------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(SK_THREADS) sketch_kernel(const SketchBatch sb, const SketchOut out,
+                                                            uint32_t n_tiles) {
+    constexpr int B = tile_bases(K);
+    using G = KmerGeom<K>;
+    extern __shared__ __align__(128) uint8_t s_dyn[];
+    __shared__ __align__(8) uint64_t s_bar;
+    const TileViews v = carve_tile(s_dyn, B);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint64_t thr = *out.thr;
+
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    uint32_t tile = sb.tile_lo + blockIdx.x;
+    uint32_t parity = 0;
+    if (tid == 0 && tile < n_tiles) {
+        const uint64_t t0 = (uint64_t)tile * SK_TILE;
+        const uint32_t bytes = tile_copy_bytes(t0, sb.n, B);
+        mbar_expect_tx(&s_bar, bytes);
+        if (bytes) tma_load_1d(v.raw, sb.buf + t0, bytes, &s_bar);
+    }
+    for (; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t t0 = (uint64_t)tile * SK_TILE;
+        mbar_wait(&s_bar, parity);
+        parity ^= 1u;
+        build_views(v, B, t0, sb);
+        __syncthreads();  // raw consumed, views + zeroed end bitmap visible
+        {
+            const uint32_t next = tile + gridDim.x;
+            if (tid == 0 && next < n_tiles) {  // prefetch: overlaps everything below
+                const uint64_t n0 = (uint64_t)next * SK_TILE;
+                const uint32_t bytes = tile_copy_bytes(n0, sb.n, B);
+                mbar_expect_tx(&s_bar, bytes);
+                if (bytes) tma_load_1d(v.raw, sb.buf + n0, bytes, &s_bar);
+            }
+        }
+        mark_sequence_ends(v, B, t0, sb);
+        __syncthreads();
+        build_start_bitmap(v, K, t0, sb);
+        __syncthreads();
+#pragma unroll 2
+        for (int r = 0; r < SK_TILE / SK_THREADS; r++) {
+            const int i = r * SK_THREADS + tid;  // window start inside the tile
+            const bool valid = ((v.sbad[i >> 5] >> (i & 31)) & 1u) == 0;
+            uint32_t ef[G::NE], er[G::NE];
+            extract2<K>(v.f2, i, ef);
+            const int ri = B - K - i;  // start of rc(window i) in the reverse-complement views
+            extract2<K>(v.r2, ri, er);
+            const bool use_fw = canonical_is_fw<K>(ef, er);
+            uint32_t kw[G::NW];
+            // rA sits (B + 8) bytes after fA (carve_tile): one base pointer, selected byte offset
+            extractA<K>(v.fA, use_fw ? i : (B + 8 + ri), kw);
+            const uint64_t h = murmur3_h1_words<K>(kw, sb.seed);
+            append_survivor(valid && h <= thr, h, t0 + i, sb, out, lane);
+        }
+        __syncthreads();  // views are rebuilt by the next tile
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// any other k: same staging, byte loops per window
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SK_THREADS) sketch_generic_kernel(const SketchBatch sb, const SketchOut out,
+                                                                    uint32_t n_tiles, int K) {
+    const int B = SK_TILE + ((K - 1 + 15) / 16) * 16;
+    extern __shared__ __align__(128) uint8_t s_dyn[];
+    __shared__ __align__(8) uint64_t s_bar;
+    const TileViews v = carve_tile(s_dyn, B);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint64_t thr = *out.thr;
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    uint32_t parity = 0;
+    for (uint32_t tile = sb.tile_lo + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t t0 = (uint64_t)tile * SK_TILE;
+        if (tid == 0) {
+            const uint32_t bytes = tile_copy_bytes(t0, sb.n, B);
+            mbar_expect_tx(&s_bar, bytes);
+            if (bytes) tma_load_1d(v.raw, sb.buf + t0, bytes, &s_bar);
+        }
+        mbar_wait(&s_bar, parity);
+        parity ^= 1u;
+        build_views(v, B, t0, sb);
+        __syncthreads();
+        mark_sequence_ends(v, B, t0, sb);
+        __syncthreads();
+        build_start_bitmap(v, K, t0, sb);
+        __syncthreads();
+        const uint8_t *fA = reinterpret_cast<const uint8_t *>(v.fA);
+        const uint8_t *rA = reinterpret_cast<const uint8_t *>(v.rA);
+        for (int r = 0; r < SK_TILE / SK_THREADS; r++) {
+            const int i = r * SK_THREADS + tid;
+            const bool valid = ((v.sbad[i >> 5] >> (i & 31)) & 1u) == 0;
+            uint64_t h = 0;
+            if (valid) {
+                const uint8_t *f = fA + i;
+                const uint8_t *rc = rA + (B - K - i);
+                int j = 0;
+                while (j < K && f[j] == rc[j]) j++;
+                const uint8_t *src = (j < K && f[j] < rc[j]) ? f : rc;  // lib.rs:263-267 (ties -> rc)
+                h = murmur3_h1_bytes(src, (uint64_t)K, sb.seed);
+            }
+            append_survivor(valid && h <= thr, h, t0 + i, sb, out, lane);
+        }
+        __syncthreads();
+    }
+}
+
+bool sketch_has_fast_path(uint32_t K) { return K == 21 || K == 31 || K == 51; }
+
+template <int K>
+static void launch_fast(const SketchBatch &sb, const SketchOut &out, uint32_t n_tiles, unsigned grid,
+                        cudaStream_t st) {
+    constexpr size_t smem = tile_smem_bytes(tile_bases(K));
+    static bool attr_set = false;
+    if (!attr_set) {
+        SM_CUDA(cudaFuncSetAttribute(sketch_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    sketch_kernel<K><<<grid, SK_THREADS, smem, st>>>(sb, out, n_tiles);
+}
+
+uint32_t sketch_tile_count(uint64_t n, uint64_t n_limit) {
+    const uint64_t span = n_limit < n ? n_limit : n;  // window starts worth visiting
+    const uint64_t tiles64 = (span + SK_TILE - 1) / SK_TILE;
+    if (tiles64 > 0xFFFFFFFFull) throw_internal("sequence batch too large for one launch");
+    return (uint32_t)tiles64;
+}
+// tiles whose staged bytes (window starts + halo) lie inside the first `bytes_ready` bytes
+uint32_t sketch_tiles_ready(uint32_t K, uint64_t bytes_ready) {
+    const uint64_t B = SK_TILE + (((uint64_t)K - 1 + 15) / 16) * 16;
+    if (bytes_ready < B) return 0;
+    return (uint32_t)((bytes_ready - B) / SK_TILE + 1);
+}
+
+void launch_sketch(uint32_t K, const SketchBatch &sb, const SketchOut &out, uint32_t tile_hi, int sm_count,
+                   cudaStream_t st) {
+    if (sb.n == 0 || sb.n_limit == 0 || K == 0 || tile_hi <= sb.tile_lo) return;
+    const uint32_t n_tiles = tile_hi;
+    unsigned grid = (unsigned)sm_count * SK_CTAS_PER_SM;  // persistent: a multiple of the SM count
+    if (grid > tile_hi - sb.tile_lo) grid = tile_hi - sb.tile_lo;
+    switch (K) {
+    case 21: launch_fast<21>(sb, out, n_tiles, grid, st); break;
+    case 31: launch_fast<31>(sb, out, n_tiles, grid, st); break;
+    case 51: launch_fast<51>(sb, out, n_tiles, grid, st); break;
+    default: {
+        if (K > (uint32_t)SK_MAX_GENERIC_K) throw_internal("ksize above 8192 is not supported by the GPU sketcher");
+        const int B = SK_TILE + (((int)K - 1 + 15) / 16) * 16;
+        const size_t smem = tile_smem_bytes(B);
+        SM_CUDA(cudaFuncSetAttribute(sketch_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sketch_generic_kernel<<<grid, SK_THREADS, smem, st>>>(sb, out, n_tiles, (int)K);
+    }
+    }
+    SM_LAUNCHED();
+}
+
+}  // namespace smb200
