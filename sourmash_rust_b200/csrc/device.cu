@@ -9,6 +9,7 @@
 namespace smb200 {
 
 std::atomic<uint64_t> g_launch_count{0};
+bool g_debug_sync = getenv("SMB200_DEBUG_SYNC") != nullptr;
 
 void DevBuf::reserve(size_t bytes, cudaStream_t st, bool keep, size_t keep_bytes) {
     if (bytes <= cap) return;

@@ -53,10 +53,14 @@ struct SourmashError : public std::runtime_error {
 
 // Number of kernels this library has launched (bench.py reports it as gpu_launches).
 extern std::atomic<uint64_t> g_launch_count;
-#define SM_LAUNCHED()                          \
-    do {                                       \
-        ::smb200::g_launch_count.fetch_add(1); \
-        SM_CUDA(cudaGetLastError());           \
+// SMB200_DEBUG_SYNC=1 in the environment: synchronise after every launch so that a faulting
+// kernel is reported at its own launch site
+extern bool g_debug_sync;
+#define SM_LAUNCHED()                                       \
+    do {                                                    \
+        ::smb200::g_launch_count.fetch_add(1);              \
+        SM_CUDA(cudaGetLastError());                        \
+        if (::smb200::g_debug_sync) SM_CUDA(cudaDeviceSynchronize()); \
     } while (0)
 
 // Growable raw device allocation (never shrinks; contents not preserved on grow

@@ -285,7 +285,7 @@ void KmerMinHash::flush() {
 bool KmerMinHash::ingest(Context &ctx, bool thr_is_estimate) {
     const uint64_t nc = n_cand_;
     n_cand_ = 0;
-    if (nc == 0) return true;
+    if (nc == 0) return !(mode() == MODE_NUM && thr_is_estimate && n_mins_ < num);  // nothing kept: estimate too tight?
     ensure_dev();
     require_sorted("add_hash");
     if (has_abunds_ && n_abunds_ != n_mins_) throw_internal("abundances out of step with mins");
@@ -612,20 +612,29 @@ void KmerMinHash::merge(KmerMinHash &other) {
     uint64_t n_ab = 0;
     if (both) {
         n_ab = n_union;  // NOT truncated with mins (lib.rs:395-400 TODO)
-    } else if (sa || ob) {
-        // only one side tracks: the reference pushes that side's abundance for the elements only
-        // that side holds, and nothing for the others (lib.rs:343-383)
-        const uint64_t *tk = sa ? d_mins_.as<uint64_t>() : other.d_mins_.as<uint64_t>();
-        const uint64_t *tv = sa ? d_abunds_.as<uint64_t>() : other.d_abunds_.as<uint64_t>();
-        const uint64_t nt = sa ? na : nb;
-        const uint64_t *ok = sa ? other.d_mins_.as<uint64_t>() : d_mins_.as<uint64_t>();
-        const uint64_t no = sa ? nb : na;
-        uint64_t *flags = ctx.misc[0].as<uint64_t>(), *pre = ctx.misc[1].as<uint64_t>();
-        launch_mark_common(tk, nt, ok, no, flags, st);
-        scan_exclusive_u64(flags, pre, nt, ctx.scan_tmp.p, st);
-        launch_compact_unflagged(tv, flags, pre, nt, out_v.as<uint64_t>(), st);
+    } else if (sa) {
+        // only self tracks.  The reference advances self's abundance iterator when it emits a
+        // self-only element and NOT on a common one (lib.rs:354-367: the inner `if let` chain
+        // starts from other's iterator, which is None), so the values it emits are simply the
+        // leading entries of self.abunds: one per self-only element, plus -- when other runs out
+        // first and the `None` arm fires (lib.rs:336-343) -- everything that is left.
+        uint64_t last_a = 0, last_b = 0;
+        if (na) SM_CUDA(cudaMemcpyAsync(&last_a, d_mins_.as<uint64_t>() + (na - 1), 8, cudaMemcpyDeviceToHost, st));
+        if (nb) SM_CUDA(cudaMemcpyAsync(&last_b, other.d_mins_.as<uint64_t>() + (nb - 1), 8, cudaMemcpyDeviceToHost, st));
         ctx.sync();
-        n_ab = nt - common;
+        const bool none_arm = na > 0 && (nb == 0 || last_a > last_b);
+        n_ab = none_arm ? na : na - common;
+        if (n_ab) SM_CUDA(cudaMemcpyAsync(out_v.p, d_abunds_.p, n_ab * 8, cudaMemcpyDeviceToDevice, st));
+        ctx.sync();
+    } else if (ob) {
+        // only other tracks: its iterator stays in step (advanced on common elements too), so the
+        // reference emits the abundances of the elements only other holds (lib.rs:344-352,384-388)
+        uint64_t *flags = ctx.misc[0].as<uint64_t>(), *pre = ctx.misc[1].as<uint64_t>();
+        launch_mark_common(other.d_mins_.as<uint64_t>(), nb, d_mins_.as<uint64_t>(), na, flags, st);
+        scan_exclusive_u64(flags, pre, nb, ctx.scan_tmp.p, st);
+        launch_compact_unflagged(other.d_abunds_.as<uint64_t>(), flags, pre, nb, out_v.as<uint64_t>(), st);
+        ctx.sync();
+        n_ab = nb - common;
     }
     const uint64_t n_keep = (num != 0 && n_union >= num) ? num : n_union;
     has_abunds_ = true;  // lib.rs:393,400: abunds becomes Some(..) unconditionally

@@ -249,14 +249,14 @@ void radix_sort_pairs(uint64_t *keys, uint64_t *vals, uint64_t n, uint64_t *tmp_
     if (passes < 1) passes = 1;
     if (passes & 1) passes++;  // even number of passes: the result lands back in keys/vals
     if (passes > 8) passes = 8;
-    uint64_t *src_k = keys, *src_v = vals, *dst_k = tmp_keys, *dst_v = tmp_vals;
+    const bool has_vals = vals != nullptr;
+    uint64_t *src_k = keys, *src_v = vals, *dst_k = tmp_keys, *dst_v = has_vals ? tmp_vals : nullptr;
     for (int p = 0; p < passes; p++) {
         const int shift = 8 * p;
         rs_hist_kernel<<<blocks, RS_THREADS, 0, st>>>(src_k, n, shift, counts, blocks);
         SM_LAUNCHED();
         scan_exclusive_u64(counts, counts, table, stmp, st);
-        rs_scatter_kernel<<<blocks, RS_THREADS, 0, st>>>(src_k, src_v, n, shift, counts, blocks, dst_k,
-                                                         src_v ? dst_v : nullptr);
+        rs_scatter_kernel<<<blocks, RS_THREADS, 0, st>>>(src_k, src_v, n, shift, counts, blocks, dst_k, dst_v);
         SM_LAUNCHED();
         uint64_t *t = src_k; src_k = dst_k; dst_k = t;
         t = src_v; src_v = dst_v; dst_v = t;
