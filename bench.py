@@ -1,0 +1,516 @@
+#!/usr/bin/env python
+"""bench.py -- sketch-and-compare hot path on N B200s (one process per GPU), or the reference
+algorithm's CPU path on the host cores (--impl reference).
+
+Workload (BASELINE.json configs[1], "cfg2"): scaled=1000 (max_hash = 18446744073709552), multi-k
+k=21/31/51, synthetic error-free 150 bp reads from a random-ACGT genome, track_abundance.  One
+step = one batch of READS_PER_STEP reads added to the three sketches (a batch is 315 MB of ASCII,
+larger than the 126 MB L2).  Metric: Gbp/s sketched = input bases per second (every base is
+sketched at all three k).  A second section times the all-vs-all Jaccard matrix of configs[2]
+("cfg3": 10,000 sketches, num=500, k=31) and reports comparisons/s.
+
+Prints ONE JSON line on rank 0 (see the keys below).  Timing: CUDA events on the library's own
+stream (wrapped as a torch ExternalStream), barrier + synchronize on both sides, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MAX_HASH_1000 = 18446744073709552
+KSIZES = (21, 31, 51)
+READ_LEN = 150
+GENOME_LEN = 100_000_000
+SEED_GENOME = 0x5EED0010
+SEED_READS = 0x5EED0011
+# SASS instructions executed per window by the sketch kernels (ncu smsp__inst_executed / windows,
+# profiles/), used only for the integer-pipe roofline
+INSTR_PER_WINDOW = {21: None, 31: None, 51: None}
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic inputs
+# ----------------------------------------------------------------------------------------------
+def np_genome(n, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n, dtype=np.uint8)]
+
+
+def np_reads(genome, n_reads, seed):
+    """error-free reads, uniform start, strand flipped w.p. 0.5"""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = np.empty((n_reads, READ_LEN), dtype=np.uint8)
+    comp = np.zeros(256, dtype=np.uint8)
+    comp[list(b"ACGT")] = list(b"TGCA")
+    ar = np.arange(READ_LEN, dtype=np.int64)
+    for lo in range(0, n_reads, 1 << 18):
+        hi = min(n_reads, lo + (1 << 18))
+        starts = rng.integers(0, len(genome) - READ_LEN, size=hi - lo, dtype=np.int64)
+        flips = rng.integers(0, 2, size=hi - lo, dtype=np.uint8).astype(bool)
+        r = genome[starts[:, None] + ar[None, :]]
+        r[flips] = comp[r[flips][:, ::-1]]
+        out[lo:hi] = r
+    return out.reshape(-1)
+
+
+def torch_reads(genome_t, n_reads, seed, device):
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty((n_reads, READ_LEN), dtype=torch.uint8, device=device)
+    comp = torch.zeros(256, dtype=torch.uint8, device=device)
+    comp[torch.tensor(list(b"ACGT"), device=device, dtype=torch.long)] = torch.tensor(list(b"TGCA"), dtype=torch.uint8, device=device)
+    ar = torch.arange(READ_LEN, device=device)
+    for lo in range(0, n_reads, 1 << 19):
+        hi = min(n_reads, lo + (1 << 19))
+        starts = torch.randint(0, genome_t.numel() - READ_LEN, (hi - lo,), generator=g, device=device)
+        flips = torch.randint(0, 2, (hi - lo,), generator=g, device=device).bool()
+        r = genome_t[starts[:, None] + ar[None, :]]
+        rc = comp[r.flip(1).long()]
+        out[lo:hi] = torch.where(flips[:, None], rc, r)
+    return out.reshape(-1)
+
+
+def planted_sketches(n_rows, num, seed):
+    """cfg3 compare-only input: 100-member clusters; a member keeps each hash of its
+    cluster root with the k-mer survival probability of its substitution rate and fills up with
+    fresh hashes; rows are the `num` smallest, sorted, distinct."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    rates = (0.001, 0.005, 0.01, 0.02, 0.05)
+    rows = np.empty((n_rows, num), dtype=np.uint64)
+    i = 0
+    while i < n_rows:
+        root = np.unique(rng.integers(0, 1 << 52, size=4 * num, dtype=np.uint64))
+        for m in range(min(100, n_rows - i)):
+            keep_p = (1.0 - rates[m % 5]) ** 31
+            kept = root[rng.random(root.size) < keep_p]
+            fresh = rng.integers(0, 1 << 52, size=4 * num - kept.size + 8, dtype=np.uint64)
+            row = np.unique(np.concatenate([kept, fresh]))[:num]
+            assert row.size == num
+            rows[i] = row
+            i += 1
+    return rows
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampled during the timed regions
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.samples = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self, windows):
+        sm, mx, reasons = [], 0, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for t, line in self.samples:
+            if not any(a <= t <= b for a, b in windows):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for nm, val in zip(names, f[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm restated in C (oracle/), all host threads
+# ----------------------------------------------------------------------------------------------
+def cpu_sketch_rate(reads, n_reads, threads):
+    from oracle import oracle as orc
+    t0 = time.perf_counter()
+    sk = orc.mt_sketch_reads(reads.tobytes() if isinstance(reads, np.ndarray) else reads, n_reads, READ_LEN,
+                             list(KSIZES), 0, MAX_HASH_1000, True, threads)
+    dt = time.perf_counter() - t0
+    return n_reads * READ_LEN / dt / 1e9, dt, sk
+
+
+def run_reference(args):
+    """--impl reference: same metric/config on the host cores.  The Rust crate cannot be built in
+    this image (no cargo/rustc), so this is the C restatement of its algorithm (oracle/oracle.c),
+    structured like the reference and pinned to its known-answer tests."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    orc.build()
+    threads = os.cpu_count() or 1
+    genome = np_genome(4_000_000, SEED_GENOME)
+    calib = np_reads(genome, 1 << 13, SEED_READS)
+    _, dt, _ = cpu_sketch_rate(calib, 1 << 13, threads)
+    per_step = int(min(1 << 20, max(1 << 13, (1 << 13) * 2.0 / max(dt, 1e-3))))  # about 2 s per step
+    batches = [np_reads(genome, per_step, SEED_READS + 1 + b) for b in range(2)]
+    for w in range(args.warmup):
+        cpu_sketch_rate(batches[w % 2], per_step, threads)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        cpu_sketch_rate(batches[s % 2], per_step, threads)
+    dt = time.perf_counter() - t0
+    value = args.steps * per_step * READ_LEN / dt / 1e9
+    line = {
+        "impl": "reference", "metric": "Gbp/s sketched", "value": value, "unit": "Gbp/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "cfg2: scaled=1000 (max_hash=18446744073709552), k=21/31/51 multi-k, 150 bp reads, "
+                               "track_abundance; each step a bounded sample of %d reads" % per_step,
+                   "reads_per_step": per_step, "read_len": READ_LEN},
+        "cpu_baseline": {"value": value, "unit": "Gbp/s", "cores": threads, "kind": "port",
+                         "sample": "%d steps x %d reads x 150 bp, 3 k-sizes per base, reads spread over %d threads "
+                                   "(oracle/baseline_mt.c)" % (args.steps, per_step, threads)},
+        "e2e": {"value": value, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import sourmash_rust_b200 as smb
+    from sourmash_rust_b200 import build
+    build.build_library()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: this build has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    smb.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _, sm_count = smb.device_info()
+    lib_stream = torch.cuda.ExternalStream(smb.stream_handle(), device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    R = args.reads_per_step
+    n_bytes = R * READ_LEN
+    # ---- inputs: same genome on every rank, rank-private read batches (sharded by read batch) ------
+    gg = torch.Generator(device=dev)
+    gg.manual_seed(SEED_GENOME)
+    genome_t = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)[
+        torch.randint(0, 4, (GENOME_LEN,), generator=gg, device=dev)]
+    n_batches = min(3, args.steps + args.warmup)
+    dev_batches = [torch_reads(genome_t, R, SEED_READS + 1000 * rank + b, dev) for b in range(n_batches)]
+    host_batches = []
+    for b in dev_batches:
+        h = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
+        h.copy_(b)
+        host_batches.append(h)
+    torch.cuda.synchronize()
+
+    def new_sketches():
+        return [smb.KmerMinHash(0, k, False, 42, MAX_HASH_1000, True) for k in KSIZES]
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    windows = []
+
+    # ---- device-resident path: `value` --------------------------------------------------------------
+    mhs = new_sketches()
+    for w in range(args.warmup):
+        smb.add_reads(mhs, dev_batches[w % n_batches].data_ptr(), R, READ_LEN, force=False, on_device=True)
+    for m in mhs:
+        m.size()
+    mhs = new_sketches()
+    smb.profile_enable(True)
+    for kind in smb.PROFILE_KINDS:
+        smb.profile_read(kind, reset=True)
+    barrier()
+    launches0 = smb.launch_count()
+    t_wall0 = time.time()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(lib_stream)
+    for s in range(args.steps):
+        smb.add_reads(mhs, dev_batches[s % n_batches].data_ptr(), R, READ_LEN, force=False, on_device=True)
+    sizes = [m.size() for m in mhs]  # folds the last candidates into the sorted sketches
+    ev1.record(lib_stream)
+    barrier()
+    windows.append((t_wall0, time.time()))
+    ms_dev = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = smb.launch_count() - launches0
+    kern = {kind: smb.profile_read(kind, reset=True) for kind in ("sketch_k21", "sketch_k31", "sketch_k51")}
+    smb.profile_enable(False)
+    total_bases = sum_over_ranks(float(args.steps * n_bytes))
+    value = total_bases / (ms_dev * 1e-3) / 1e9
+    md5_dev = [m.md5sum() for m in mhs]
+
+    # ---- end-to-end path: pinned host buffers in, sketches read back every step ------------------------
+    mhs2 = new_sketches()
+    out_m = [np.zeros(1 << 22, dtype=np.uint64) for _ in KSIZES]
+    out_a = [np.zeros(1 << 22, dtype=np.uint64) for _ in KSIZES]
+
+    def e2e_step(s):
+        smb.add_reads(mhs2, host_batches[s % n_batches].data_ptr(), R, READ_LEN, force=False, on_device=False)
+        d2h = 0
+        for i, m in enumerate(mhs2):
+            n = smb._call("kmerminhash_copy_mins", m._p, smb._vp(out_m[i]), smb._vp(out_a[i]), False)
+            d2h += 16 * n
+        return d2h
+
+    warm = new_sketches()
+    mhs2, keep = warm, mhs2
+    for w in range(min(args.warmup, 2)):
+        e2e_step(w)
+    mhs2 = keep
+    barrier()
+    t_wall0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(lib_stream)
+    d2h_total = 0
+    for s in range(args.steps):
+        d2h_total += e2e_step(s)
+    e1.record(lib_stream)
+    barrier()
+    windows.append((t_wall0, time.time()))
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = total_bases / (ms_e2e * 1e-3) / 1e9
+    assert [m.md5sum() for m in mhs2] == md5_dev, "device-resident and host-fed paths disagree"
+
+    # ---- roofline of the dominant kernel (k=51 is the heaviest of the three; k=31 is the metric's k) ---
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    k31_ms, k31_n = kern["sketch_k31"]
+    roof = None
+    per_k = {}
+    for k, kind in zip(KSIZES, ("sketch_k21", "sketch_k31", "sketch_k51")):
+        ms, n = kern[kind]
+        if n:
+            per_k["k%d" % k] = {"launches": n, "avg_ms": ms / n, "gbp_s": args.steps * n_bytes / (ms * 1e-3) / 1e9}
+    if k31_n:
+        bytes_per_launch = args.steps * n_bytes / k31_n  # 1 B (one ASCII base) per window, SURVEY 8(d)
+        achieved = bytes_per_launch / (k31_ms / k31_n * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "sketch_kernel<31>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": k31_ms / k31_n,
+                "note": "HBM is not the binding resource of this kernel: see int_pipe"}
+    int_peak = smb.int_peak(2) if rank == 0 else None
+    int_pipe = None
+    if rank == 0 and k31_n and INSTR_PER_WINDOW.get(31):
+        inst_rate = INSTR_PER_WINDOW[31] * (args.steps * n_bytes) / (k31_ms * 1e-3)
+        int_pipe = {"achieved_ginstr_s": inst_rate / 1e9, "peak_ginstr_s": int_peak / 1e9, "frac": inst_rate / int_peak,
+                    "instr_per_window": INSTR_PER_WINDOW[31]}
+    elif rank == 0:
+        int_pipe = {"peak_ginstr_s": int_peak / 1e9}
+
+    # ---- all-vs-all compare (cfg3), rows sharded by rank, CSR all-gathered over NCCL -------------------
+    compare = None
+    if not args.no_compare:
+        compare = bench_compare(args, smb, torch, dist, dev, rank, world, barrier, max_over_ranks, lib_stream, windows)
+
+    clocks.stop()
+
+    # ---- CPU baseline next to it (rank 0, N=1 only): bounded sample of the same workload --------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as orc
+        orc.build()
+        threads = os.cpu_count() or 1
+        sample_reads = host_batches[0].numpy()
+        _, dt, _ = cpu_sketch_rate(sample_reads[: (1 << 13) * READ_LEN], 1 << 13, threads)
+        n_s = int(min(R, max(1 << 13, (1 << 13) * 12.0 / max(dt, 1e-3))))
+        rate, dt, osk = cpu_sketch_rate(sample_reads[: n_s * READ_LEN], n_s, threads)
+        cpu = {"value": rate, "unit": "Gbp/s", "cores": threads, "kind": "port",
+               "sample": "first %d reads of batch 0 (%.1f s on %d threads), 3 k-sizes per base" % (n_s, dt, threads)}
+        # the same sample through the GPU path must give the same sketches
+        chk = new_sketches()
+        smb.add_reads(chk, host_batches[0].data_ptr(), n_s, READ_LEN, force=False, on_device=False)
+        for g, o in zip(chk, osk):
+            assert g.md5sum() == o.md5sum() and np.array_equal(g.abunds_np(), o.abunds_np()), "GPU/CPU sketches differ"
+        cpu["parity_checked"] = True
+
+    if rank == 0:
+        line = {
+            "metric": "Gbp/s sketched", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "cfg2: scaled=1000 (max_hash=18446744073709552), k=21/31/51 multi-k, 150 bp reads, "
+                                   "track_abundance, %d reads (%d MB ASCII) per step per GPU" % (R, n_bytes >> 20),
+                       "reads_per_step_per_gpu": R, "read_len": READ_LEN, "sharding": "read batches per rank, no collective",
+                       "l2": "inputs (%d MB per step) larger than the 126 MB L2; %d distinct batches cycled" % (n_bytes >> 20, n_batches),
+                       "sketch_sizes": sizes},
+            "e2e": {"value": e2e_value, "unit": "Gbp/s", "h2d_bytes_per_step": n_bytes,
+                    "d2h_bytes_per_step": d2h_total // max(1, args.steps), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "roofline": roof, "int_pipe": int_pipe, "sketch_kernels": per_k,
+            "cpu_baseline": cpu,
+            "clocks": clocks.summary(windows),
+            "compare": compare,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_compare(args, smb, torch, dist, dev, rank, world, barrier, max_over_ranks, lib_stream, windows):
+    N, NUM = args.compare_sketches, 500
+    rows = planted_sketches(N, NUM, 0x5EED0100)
+    per = (N + world - 1) // world
+    r0, r1 = min(N, rank * per), min(N, (rank + 1) * per)
+    offsets = (np.arange(N + 1, dtype=np.uint64) * np.uint64(NUM))
+    offs_t = torch.from_numpy(offsets.view(np.int64)).to(dev)
+    mine = torch.from_numpy(rows[r0:r1].view(np.int64).copy()).to(dev)
+    if world > 1 and mine.shape[0] < per:  # pad the last shard so the all-gather is uniform
+        pad = torch.zeros((per - mine.shape[0], NUM), dtype=torch.int64, device=dev)
+        mine = torch.cat([mine, pad])
+    common = torch.empty((r1 - r0, N), dtype=torch.int32, device=dev)
+    size = torch.empty((r1 - r0, N), dtype=torch.int32, device=dev)
+    ratio = torch.empty((r1 - r0, N), dtype=torch.float64, device=dev)
+    steps = max(1, min(args.steps, 5))
+
+    def step():
+        if world > 1:
+            full = torch.empty((per * world, NUM), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(full, mine)
+            torch.cuda.current_stream().synchronize()
+            full = full[:N]
+        else:
+            full = mine
+        coll = smb.SketchCollection.from_csr(full.data_ptr(), offs_t.data_ptr(), N, NUM, 31, 42, 0, on_device=True)
+        smb.compare_matrix_device(coll, coll, "compare", r0, r1 - r0, 0, N, common.data_ptr(), size.data_ptr(),
+                                  ratio.data_ptr(), N)
+        return coll
+
+    for _ in range(2):
+        step()
+    smb.profile_enable(True)
+    smb.profile_read("compare", reset=True)
+    barrier()
+    t_wall0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(lib_stream)
+    for _ in range(steps):
+        step()
+    e1.record(lib_stream)
+    barrier()
+    windows.append((t_wall0, time.time()))
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    kms, kn = smb.profile_read("compare", reset=True)
+    smb.profile_enable(False)
+    # end to end: host CSR in, f64 Jaccard matrix out to pinned host memory
+    out = torch.empty((r1 - r0, N), dtype=torch.float64, pin_memory=True)
+    rows_c = np.ascontiguousarray(rows)
+
+    def e2e():
+        coll = smb.SketchCollection.from_csr(rows_c.reshape(-1), offsets, N, NUM, 31, 42, 0, on_device=False)
+        smb._call("smgpu_compare_matrix", coll._p, r0, r1 - r0, coll._p, 0, N, 0, None, None, smb._vp(out.data_ptr()), N, False)
+
+    e2e()
+    barrier()
+    e0.record(lib_stream)
+    for _ in range(steps):
+        e2e()
+    e1.record(lib_stream)
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / steps
+    # spot parity: 64 x 64 block against the oracle
+    ok = None
+    if rank == 0:
+        from oracle import oracle as orc
+        osk = []
+        for i in range(64):
+            o = orc.KmerMinHash(NUM, 31)
+            o.add_many(rows[i])
+            osk.append(o)
+        oc, osz = orc.compare_matrix(osk, osk)
+        ok = bool(np.array_equal(common[:64, :64].cpu().numpy(), oc.astype(np.int32)) and
+                  np.array_equal(out[:64, :64].numpy(), oc / np.maximum(1, osz)))
+        assert ok, "compare matrix differs from the oracle"
+    pairs = float(N) * float(N)
+    return {"metric": "Jaccard comparisons/s all-vs-all", "value": pairs / (ms * 1e-3), "unit": "pairs/s",
+            "config": "cfg3: %d sketches, num=500, k=31, full ordered matrix (common,size u32 + Jaccard f64), rows "
+                      "sharded over %d rank(s), CSR all-gathered over NCCL inside the step" % (N, world),
+            "ms_per_step": ms, "steps": steps, "scaling": "strong",
+            "kernel_ms_per_step": (kms / kn * (kn / steps)) if kn else None,
+            "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(rows_c.nbytes + offsets.nbytes),
+                    "d2h_bytes_per_step": int((r1 - r0) * N * 8)},
+            "operand_bytes_per_pair": 2 * NUM * 8, "parity_checked_64x64": ok}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads-per-step", type=int, default=1 << 21)
+    ap.add_argument("--compare-sketches", type=int, default=10000)
+    ap.add_argument("--no-compare", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

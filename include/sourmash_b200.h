@@ -29,6 +29,18 @@ void smgpu_set_device(int32_t device);
 int32_t smgpu_device(int32_t *sm_count);
 /* kernels this library has launched so far in this process */
 uint64_t smgpu_launch_count(void);
+/* the CUDA stream (cudaStream_t, as an integer) every kernel of the library is launched on: lets a
+ * caller bracket calls with its own CUDA events */
+uint64_t smgpu_stream(void);
+/* per-kernel device timing with CUDA events on that stream: kinds 0/1/2 = sketch kernel k=21/31/51,
+ * 3 = sketch kernel other k, 4 = compare matrix kernel.  read() waits for the recorded events and
+ * returns the accumulated milliseconds and launch count (optionally resetting them). */
+void smgpu_profile_enable(bool on);
+void smgpu_profile_read(int32_t kind, double *ms, uint64_t *launches, bool reset);
+/* integer-pipe microbenchmark: thread-instructions per second of a dependent-chain kernel
+ * (mode 0 = IMAD only, 1 = LOP3/SHF only, 2 = both interleaved) -- the measured roofline
+ * denominator of the sketch kernel */
+double smgpu_int_peak(int32_t mode, int32_t iters, int32_t blocks);
 /* page-locked host memory for batch buffers (host->device copies from it run at full PCIe rate
  * and overlap with the kernels) */
 void *smgpu_alloc_pinned(uintptr_t bytes);

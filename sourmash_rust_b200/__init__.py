@@ -79,6 +79,10 @@ EXTENSION_ABI = {
     "smgpu_set_device": (None, [i32]),
     "smgpu_device": (i32, [C.POINTER(i32)]),
     "smgpu_launch_count": (u64, []),
+    "smgpu_stream": (u64, []),
+    "smgpu_profile_enable": (None, [cb]),
+    "smgpu_profile_read": (None, [i32, C.POINTER(C.c_double), C.POINTER(u64), cb]),
+    "smgpu_int_peak": (C.c_double, [i32, i32, i32]),
     "smgpu_alloc_pinned": (vp, [usz]),
     "smgpu_free_pinned": (None, [vp]),
     "kmerminhash_slice_free": (None, [p_u64]),
@@ -162,6 +166,27 @@ def device_info():
 
 def launch_count() -> int:
     return lib().smgpu_launch_count()
+
+
+def stream_handle() -> int:
+    return _call("smgpu_stream")
+
+
+def profile_enable(on=True):
+    lib().smgpu_profile_enable(on)
+
+
+PROFILE_KINDS = {"sketch_k21": 0, "sketch_k31": 1, "sketch_k51": 2, "sketch_other": 3, "compare": 4}
+
+
+def profile_read(kind, reset=False):
+    ms, n = C.c_double(0), u64(0)
+    _call("smgpu_profile_read", PROFILE_KINDS[kind], C.byref(ms), C.byref(n), reset)
+    return ms.value, n.value
+
+
+def int_peak(mode=2, iters=4096, blocks=148 * 8):
+    return _call("smgpu_int_peak", mode, iters, blocks)
 
 
 def _vp(x):
@@ -310,7 +335,7 @@ def _handles(mhs):
 
 def add_reads(mhs, buf, n_reads, read_len, force=True, on_device=False):
     """kmerminhash_add_reads: every read added to every sketch of `mhs` in one pass."""
-    keep = buf if on_device else (buf if isinstance(buf, np.ndarray) else bytes(buf))
+    keep = buf if (on_device or isinstance(buf, (int, np.ndarray))) else bytes(buf)  # int = raw pointer
     _call("kmerminhash_add_reads", _handles(mhs), len(mhs), _vp(keep), n_reads, read_len, force, on_device)
 
 
@@ -320,7 +345,7 @@ def add_sequences(mhs, buf, offsets, force=True, on_device=False, n_seqs=None):
         keep_b, keep_o = buf, offsets
         assert n_seqs is not None
     else:
-        keep_b = buf if isinstance(buf, np.ndarray) else bytes(buf)
+        keep_b = buf if isinstance(buf, (int, np.ndarray)) else bytes(buf)
         keep_o = np.ascontiguousarray(offsets, dtype=np.uint64)
         n_seqs = keep_o.size - 1
     _call("kmerminhash_add_sequences", _handles(mhs), len(mhs), _vp(keep_b), _vp(keep_o), n_seqs, force, on_device)

@@ -228,6 +228,7 @@ void launch_compare_cross(const uint64_t *row_hashes, const uint64_t *row_offset
     if (want_y < 1) want_y = 1;
     if (want_y > 65535) want_y = 65535;
     grid.y = (unsigned)want_y;
+    ProfScope prof(PROF_COMPARE, st);
     if (use_smem) {
         SM_CUDA(cudaFuncSetAttribute(compare_cross_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         compare_cross_kernel<true><<<grid, CM_THREADS, smem, st>>>(row_hashes, row_offsets, row_nums, r0, nr, col_hashes,

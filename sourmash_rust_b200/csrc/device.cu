@@ -11,28 +11,30 @@ namespace smb200 {
 std::atomic<uint64_t> g_launch_count{0};
 bool g_debug_sync = getenv("SMB200_DEBUG_SYNC") != nullptr;
 
-void DevBuf::reserve(size_t bytes, cudaStream_t st, bool keep, size_t keep_bytes) {
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync) on the library's
+// stream: growth and release are ordered with the kernels instead of synchronising the device,
+// and freed blocks stay cached in the pool (release threshold = max), so the scratch churn of the
+// sort/merge pipeline costs microseconds, not cudaMalloc/cudaFree round trips.
+void DevBuf::reserve(size_t bytes, cudaStream_t, bool keep, size_t keep_bytes) {
     if (bytes <= cap) return;
+    cudaStream_t st = Context::get().stream;
     size_t want = cap ? cap : 4096;
     while (want < bytes) want += want / 2 + 4096;
     want = (want + 255) / 256 * 256;
     void *np = nullptr;
-    SM_CUDA(cudaMalloc(&np, want));
-    if (keep && p && keep_bytes) {
-        SM_CUDA(cudaMemcpyAsync(np, p, keep_bytes, cudaMemcpyDeviceToDevice, st));
-        SM_CUDA(cudaStreamSynchronize(st));
-    }
-    if (p) cudaFree(p);  // cudaFree synchronises the device: no kernel still reads the old block
+    SM_CUDA(cudaMallocAsync(&np, want, st));
+    if (keep && p && keep_bytes) SM_CUDA(cudaMemcpyAsync(np, p, keep_bytes, cudaMemcpyDeviceToDevice, st));
+    if (p) SM_CUDA(cudaFreeAsync(p, st));
     p = np;
     cap = want;
 }
-
-void PinnedBuf::reserve(size_t bytes) {
-    if (bytes <= cap) return;
-    if (p) cudaFreeHost(p);
-    p = nullptr; cap = 0;
-    SM_CUDA(cudaMallocHost(&p, bytes));
-    cap = bytes;
+void DevBuf::release() {
+    if (p) {
+        Context *c = Context::peek();
+        if (c) cudaFreeAsync(p, c->stream); else cudaFree(p);
+    }
+    p = nullptr;
+    cap = 0;
 }
 
 static int g_requested_device = -1;
@@ -44,6 +46,8 @@ void set_requested_device(int dev) {
     if (g_ctx && g_ctx->device != dev) throw_internal("device already selected for this process");
     g_requested_device = dev;
 }
+
+Context *Context::peek() { return g_ctx; }
 
 Context &Context::get() {
     std::lock_guard<std::mutex> lk(g_ctx_mutex);
@@ -73,6 +77,12 @@ Context &Context::get() {
     Context *c = new Context();
     c->device = dev;
     c->sm_count = prop.multiProcessorCount;
+    {
+        cudaMemPool_t pool;
+        SM_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t keep_all = ~0ull;
+        SM_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all));
+    }
     SM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SM_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     c->own_stream = true;
@@ -81,6 +91,55 @@ Context &Context::get() {
     SM_CUDA(cudaMallocHost(&c->h_scalars, SC_COUNT * sizeof(unsigned long long)));
     g_ctx = c;
     return *g_ctx;
+}
+
+// ---- per-kernel timing ---------------------------------------------------------------------------
+namespace {
+struct ProfState {
+    bool enabled = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending[PROF_KINDS];
+    std::vector<cudaEvent_t> pool;
+    double ms[PROF_KINDS] = {0};
+    uint64_t launches[PROF_KINDS] = {0};
+} g_prof;
+cudaEvent_t prof_event() {
+    if (!g_prof.pool.empty()) {
+        cudaEvent_t e = g_prof.pool.back();
+        g_prof.pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    SM_CUDA(cudaEventCreate(&e));
+    return e;
+}
+}  // namespace
+ProfScope::ProfScope(int kind_, cudaStream_t st_) : kind(kind_), st(st_) {
+    if (!g_prof.enabled) return;
+    e0 = prof_event();
+    e1 = prof_event();
+    cudaEventRecord(e0, st);
+}
+ProfScope::~ProfScope() {
+    if (!e0) return;
+    cudaEventRecord(e1, st);
+    g_prof.pending[kind].emplace_back(e0, e1);
+}
+void prof_enable(bool on) { g_prof.enabled = on; }
+void prof_read(int kind, double *ms, uint64_t *launches, bool reset) {
+    if (kind < 0 || kind >= PROF_KINDS) throw_internal("bad profile kind");
+    for (auto &pr : g_prof.pending[kind]) {
+        SM_CUDA(cudaEventSynchronize(pr.second));
+        float t = 0;
+        SM_CUDA(cudaEventElapsedTime(&t, pr.first, pr.second));
+        g_prof.ms[kind] += t;
+        g_prof.launches[kind]++;
+        g_prof.pool.push_back(pr.first);
+        g_prof.pool.push_back(pr.second);
+    }
+    g_prof.pending[kind].clear();
+    if (ms) *ms = g_prof.ms[kind];
+    if (launches) *launches = g_prof.launches[kind];
+    if (reset) { g_prof.ms[kind] = 0; g_prof.launches[kind] = 0; }
 }
 
 void Context::set_scalar(int idx, unsigned long long v) {

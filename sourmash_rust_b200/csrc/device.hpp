@@ -77,19 +77,8 @@ struct DevBuf {
         return *this;
     }
     ~DevBuf() { release(); }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-    }
+    void release();
     void reserve(size_t bytes, cudaStream_t st = nullptr, bool keep = false, size_t keep_bytes = 0);
-    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
-};
-
-struct PinnedBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    ~PinnedBuf() { if (p) cudaFreeHost(p); }
-    void reserve(size_t bytes);
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
@@ -110,11 +99,25 @@ struct Context {
     cudaStream_t copy_stream = nullptr;  // host->device staging, overlapped with `stream`
 
     static Context &get();      // creates on first use; throws if no CUDA device
+    static Context *peek();     // nullptr before first use
     void sync() { SM_CUDA(cudaStreamSynchronize(stream)); }
     void set_scalar(int idx, unsigned long long v);  // synchronous
     void read_scalars();                              // d_scalars -> h_scalars, synchronous
     unsigned long long *dsc(int idx) { return d_scalars + idx; }
 };
+// Per-kernel device timing (CUDA events on the launching stream), off unless enabled through
+// smgpu_profile_enable: bench.py's roofline numbers come from here.
+enum { PROF_SKETCH_K21 = 0, PROF_SKETCH_K31 = 1, PROF_SKETCH_K51 = 2, PROF_SKETCH_OTHER = 3, PROF_COMPARE = 4,
+       PROF_SORT = 5, PROF_KINDS = 6 };
+struct ProfScope {
+    int kind;
+    cudaStream_t st;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ProfScope(int kind, cudaStream_t st);
+    ~ProfScope();
+};
+void prof_enable(bool on);
+void prof_read(int kind, double *ms, uint64_t *launches, bool reset);  // synchronises the recorded events
 // which device the context binds to when it is created (default: the thread's current device)
 void set_requested_device(int dev);
 

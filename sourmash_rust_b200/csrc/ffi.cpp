@@ -14,6 +14,7 @@
 
 #include "../../include/sourmash_b200.h"
 #include "collection.hpp"
+#include "kernels.cuh"
 #include "minhash.hpp"
 #include "signature.hpp"
 
@@ -372,6 +373,34 @@ int32_t smgpu_device(int32_t *sm_count) {
     });
 }
 uint64_t smgpu_launch_count(void) { return smb200::g_launch_count.load(); }
+uint64_t smgpu_stream(void) {
+    return landingpad<uint64_t>([&]() { return (uint64_t)reinterpret_cast<uintptr_t>(smb200::Context::get().stream); });
+}
+void smgpu_profile_enable(bool on) { smb200::prof_enable(on); }
+void smgpu_profile_read(int32_t kind, double *ms, uint64_t *launches, bool reset) {
+    landingpad_void([&]() { smb200::prof_read(kind, ms, launches, reset); });
+}
+double smgpu_int_peak(int32_t mode, int32_t iters, int32_t blocks) {
+    return landingpad<double>([&]() {
+        smb200::Context &ctx = smb200::Context::get();
+        ctx.misc[0].reserve(4096);
+        cudaEvent_t e0, e1;
+        SM_CUDA(cudaEventCreate(&e0));
+        SM_CUDA(cudaEventCreate(&e1));
+        smb200::launch_int_peak(ctx.misc[0].as<uint32_t>(), 16, blocks, mode, ctx.stream);  // warm
+        SM_CUDA(cudaEventRecord(e0, ctx.stream));
+        smb200::launch_int_peak(ctx.misc[0].as<uint32_t>(), iters, blocks, mode, ctx.stream);
+        SM_CUDA(cudaEventRecord(e1, ctx.stream));
+        SM_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        SM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        // 8 chains x 8 unrolled steps per iteration, one instruction each (mode 2: 4 IMAD + 4 LOP3/SHF pairs)
+        const double instr = (double)iters * 64.0 * 256.0 * (double)blocks;
+        return instr / (ms * 1e-3);
+    });
+}
 void *smgpu_alloc_pinned(uintptr_t bytes) {
     return landingpad<void *>([&]() {
         smb200::Context::get();

@@ -373,6 +373,7 @@ void launch_sketch(uint32_t K, const SketchBatch &sb, const SketchOut &out, uint
     const uint32_t n_tiles = tile_hi;
     unsigned grid = (unsigned)sm_count * SK_CTAS_PER_SM;  // persistent: a multiple of the SM count
     if (grid > tile_hi - sb.tile_lo) grid = tile_hi - sb.tile_lo;
+    ProfScope prof(K == 21 ? PROF_SKETCH_K21 : K == 31 ? PROF_SKETCH_K31 : K == 51 ? PROF_SKETCH_K51 : PROF_SKETCH_OTHER, st);
     switch (K) {
     case 21: launch_fast<21>(sb, out, n_tiles, grid, st); break;
     case 31: launch_fast<31>(sb, out, n_tiles, grid, st); break;
