@@ -7,9 +7,9 @@
 namespace smb200 {
 
 // ---- sketch.cu --------------------------------------------------------------------------
-constexpr int SK_TILE = 2048;        // window starts per tile
+constexpr int SK_TILE = 4096;        // window starts per tile
 constexpr int SK_THREADS = 256;      // 8 windows per thread per tile
-constexpr int SK_CTAS_PER_SM = 6;    // resident persistent CTAs per SM
+constexpr int SK_CTAS_PER_SM = 8;    // resident persistent CTAs per SM
 constexpr int SK_MAX_GENERIC_K = 8192;
 
 // A batch of sequences resident in device memory as one ASCII buffer.

@@ -140,9 +140,14 @@ KB_HD void extract2(const uint32_t *stream, int start, uint32_t (&e)[KmerGeom<K>
 // strands: with comp(c) = ~c, BE(fw) = ~E(rc) and BE(rc) = ~E(fw), so fw <lex rc <=> E(fw) < E(rc).
 template <int K>
 KB_HD bool canonical_is_fw(const uint32_t (&ef)[KmerGeom<K>::NE], const uint32_t (&er)[KmerGeom<K>::NE]) {
-    bool lt = false;  // ties -> rc, as the reference's `else` arm (identical bytes anyway)
+    // multi-word unsigned compare, most significant words first, as 64-bit pieces (ISETP + ISETP.EX);
+    // ties -> rc, as the reference's `else` arm (identical bytes anyway)
+    constexpr int NE = KmerGeom<K>::NE;
+    if (NE == 1) return ef[0] < er[0];
+    if (NE == 2) return (((uint64_t)ef[1] << 32) | ef[0]) < (((uint64_t)er[1] << 32) | er[0]);
+    bool lt = false;
 #pragma unroll
-    for (int j = 0; j < KmerGeom<K>::NE; j++) {  // least significant word first; later words override
+    for (int j = 0; j < NE; j++) {  // least significant word first; later words override
         if (ef[j] != er[j]) lt = ef[j] < er[j];
     }
     return lt;

@@ -204,8 +204,8 @@ def test_short_and_edge_sequences():
         g, o = pair(10, 5, 0, True)
         g.add_sequence(seq, True); o.add_sequence(seq, True)
         same(g, o)
-    # exactly one tile, one more, one less (tile = 2048 window starts)
-    for n in (2047, 2048, 2049, 2048 + 30, 2048 + 31, 4096 + 20, 6144):
+    # around the tile size (4096 window starts per tile) and its multiples
+    for n in (2047, 2048, 2049, 4095, 4096, 4097, 4096 + 30, 4096 + 31, 4096 + 50, 8192 + 20, 12288):
         seq = random_dna(n, n)
         for k in (21, 31, 51, 7):
             g, o = pair(0, k, MAX_HASH_1000 * 200, True)
