@@ -86,6 +86,20 @@ Context &Context::get() {
     SM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SM_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     c->own_stream = true;
+    {
+        // Reserve the pool's working set once (default 4 GiB of the 180 GB, SMB200_POOL_PREWARM_MB to
+        // change): getting fresh physical memory into the pool costs milliseconds per call, which
+        // would otherwise land inside whichever batch first grows a buffer.
+        size_t mb = 4096;
+        if (const char *e = getenv("SMB200_POOL_PREWARM_MB")) mb = (size_t)strtoull(e, nullptr, 10);
+        size_t free_b = 0, total_b = 0;
+        if (mb && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > (mb << 20) * 2) {
+            void *warm = nullptr;
+            if (cudaMallocAsync(&warm, mb << 20, c->stream) == cudaSuccess) cudaFreeAsync(warm, c->stream);
+            (void)cudaGetLastError();
+            SM_CUDA(cudaStreamSynchronize(c->stream));
+        }
+    }
     SM_CUDA(cudaMalloc(&c->d_scalars, SC_COUNT * sizeof(unsigned long long)));
     SM_CUDA(cudaMemset(c->d_scalars, 0, SC_COUNT * sizeof(unsigned long long)));
     SM_CUDA(cudaMallocHost(&c->h_scalars, SC_COUNT * sizeof(unsigned long long)));
