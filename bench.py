@@ -411,27 +411,20 @@ def run_ours(args):
 def bench_compare(args, smb, torch, dist, dev, rank, world, barrier, max_over_ranks, lib_stream, windows):
     N, NUM = args.compare_sketches, 500
     rows = planted_sketches(N, NUM, 0x5EED0100)
-    per = (N + world - 1) // world
-    r0, r1 = min(N, rank * per), min(N, (rank + 1) * per)
+    from sourmash_rust_b200 import sharding
+    r0, r1 = sharding.shard_range(N, rank, world)
     offsets = (np.arange(N + 1, dtype=np.uint64) * np.uint64(NUM))
     offs_t = torch.from_numpy(offsets.view(np.int64)).to(dev)
     mine = torch.from_numpy(rows[r0:r1].view(np.int64).copy()).to(dev)
-    if world > 1 and mine.shape[0] < per:  # pad the last shard so the all-gather is uniform
-        pad = torch.zeros((per - mine.shape[0], NUM), dtype=torch.int64, device=dev)
-        mine = torch.cat([mine, pad])
     common = torch.empty((r1 - r0, N), dtype=torch.int32, device=dev)
     size = torch.empty((r1 - r0, N), dtype=torch.int32, device=dev)
     ratio = torch.empty((r1 - r0, N), dtype=torch.float64, device=dev)
     steps = max(1, min(args.steps, 5))
 
     def step():
+        full = sharding.allgather_rows(mine, N)  # NCCL all-gather of the packed sketches (no-op at N=1)
         if world > 1:
-            full = torch.empty((per * world, NUM), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(full, mine)
             torch.cuda.current_stream().synchronize()
-            full = full[:N]
-        else:
-            full = mine
         coll = smb.SketchCollection.from_csr(full.data_ptr(), offs_t.data_ptr(), N, NUM, 31, 42, 0, on_device=True)
         smb.compare_matrix_device(coll, coll, "compare", r0, r1 - r0, 0, N, common.data_ptr(), size.data_ptr(),
                                   ratio.data_ptr(), N)
