@@ -99,6 +99,11 @@ void smgpu_compare_matrix(SketchCollection *rows, uint64_t r0, uint64_t nr, Sket
                           uint64_t nc, int32_t mode, uint32_t *common /*[host|device]*/,
                           uint32_t *size /*[host|device]*/, double *ratio /*[host|device]*/, uint64_t ld,
                           bool out_on_device);
+/* How smgpu_compare_matrix / smgpu_linear_find walk a block: 0 (default) decides from the data --
+ * an inverted index over the block's hashes finds the pairs that share at least one hash, and
+ * only those are walked when the (pair, shared hash) incidences are few against the dense work;
+ * 1 forces the dense tile kernel, 2 forces the inverted-index path.  Results are identical. */
+void smgpu_compare_path(int32_t path);
 /* LinearIndex::find (src/index/linear.rs:25-45) for every row of `queries` against `index`:
  * mode 0 = search_minhashes (node.similarity(query) > threshold), mode 1 =
  * search_minhashes_containment (node.containment(query) > threshold) (src/index/search.rs:3-9).

@@ -98,6 +98,7 @@ EXTENSION_ABI = {
     "smgpu_collection_len": (u64, [vp]),
     "smgpu_collection_csr": (u64, [vp, C.POINTER(vp), C.POINTER(vp)]),
     "smgpu_compare_matrix": (None, [vp, u64, u64, vp, u64, u64, i32, vp, vp, vp, u64, cb]),
+    "smgpu_compare_path": (None, [i32]),
     "smgpu_linear_find": (u64, [vp, vp, i32, C.c_double, vp, vp, u64]),
 }
 
@@ -176,7 +177,12 @@ def profile_enable(on=True):
     lib().smgpu_profile_enable(on)
 
 
-PROFILE_KINDS = {"sketch_k21": 0, "sketch_k31": 1, "sketch_k51": 2, "sketch_other": 3, "compare": 4}
+PROFILE_KINDS = {"sketch_k21": 0, "sketch_k31": 1, "sketch_k51": 2, "sketch_other": 3, "compare": 4, "join_sort": 5}
+
+
+def compare_path(path="auto"):
+    """'auto' | 'dense' | 'sparse' (smgpu_compare_path)"""
+    lib().smgpu_compare_path({"auto": 0, "dense": 1, "sparse": 2}[path])
 
 
 def profile_read(kind, reset=False):

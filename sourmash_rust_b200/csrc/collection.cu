@@ -3,6 +3,7 @@
 #include "collection.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <memory>
 
 #include "kernels.cuh"
@@ -91,6 +92,90 @@ void SketchCollection::check_compatible(const SketchCollection &o) const {
     if (seed != o.seed) throw SourmashError(ERR_MISMATCH_SEED, "mismatch in seed; comparison fail");
 }
 
+int g_compare_path = 0;  // 0 = choose from the data, 1 = dense tile kernel, 2 = inverted-index path
+
+static int bit_length64(uint64_t x) {
+    int b = 0;
+    while (x) { b++; x >>= 1; }
+    return b;
+}
+
+// One block of the matrix into DEVICE outputs.  Picks the sparse path (inverted index: only pairs
+// sharing a hash are walked) when the number of (pair, shared hash) incidences is small against
+// the dense work, else the dense tile kernel.  Same integers either way.
+static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t nr, SketchCollection &cols, uint64_t c0,
+                                 uint64_t nc, int mode, uint32_t *common, uint32_t *size, double *ratio, uint64_t ld) {
+    Context &ctx = Context::get();
+    cudaStream_t st = ctx.stream;
+    const uint64_t *rh = rows.d_hashes.as<uint64_t>(), *ro = rows.d_offsets.as<uint64_t>();
+    const uint64_t *ch = cols.d_hashes.as<uint64_t>(), *co = cols.d_offsets.as<uint64_t>();
+    const uint32_t *rnum = rows.d_nums.as<uint32_t>();
+    const uint64_t n_r = rows.h_offsets[r0 + nr] - rows.h_offsets[r0];
+    const uint64_t n_c = cols.h_offsets[c0 + nc] - cols.h_offsets[c0];
+    const uint64_t n = n_r + n_c;
+    const bool force_dense = g_compare_path == 1, force_sparse = g_compare_path == 2;
+    bool sparse = !force_dense && n > 0 && (force_sparse || nr * nc >= 4096) && nr < (1ull << 31) && nc < (1ull << 31);
+    uint64_t *keys = nullptr, *vals = nullptr;
+    if (sparse) {
+        ProfScope prof(PROF_SORT, st);
+        ctx.join[0].reserve((n + 1) * 8);
+        ctx.join[1].reserve((n + 1) * 8);
+        ctx.sort_tmp_k.reserve((n + 1) * 8);
+        ctx.sort_tmp_v.reserve((n + 1) * 8);
+        ctx.scan_tmp.reserve(std::max(radix_sort_scan_bytes(n), scan_tmp_bytes(std::max<uint64_t>(n, (nr * nc + 63) / 64))) + 256);
+        keys = ctx.join[0].as<uint64_t>();
+        vals = ctx.join[1].as<uint64_t>();
+        launch_postings(rh, ro, r0, nr, 0, keys, vals, st);
+        launch_postings(ch, co, c0, nc, 1, keys + n_r, vals + n_r, st);
+        radix_sort_pairs(keys, vals, n, ctx.sort_tmp_k.as<uint64_t>(), ctx.sort_tmp_v.as<uint64_t>(),
+                         rows.max_hash ? bit_length64(rows.max_hash) : 64, ctx.scan_tmp.p, ctx.scan_tmp.cap, st);
+        SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_CNT), 0, 8, st));
+        launch_count_incidences(keys, vals, n, ctx.dsc(SC_CNT), st);
+        ctx.read_scalars();
+        const uint64_t incidences = ctx.h_scalars[SC_CNT];
+        if (!force_sparse && incidences > 8 * nr * nc) sparse = false;  // mostly-related collections: the dense kernel wins
+    }
+    if (!sparse) {
+        launch_compare_cross(rh, ro, rnum, r0, nr, ch, co, c0, nc, mode, common, size, ratio, ld, cols.max_len, ctx.sm_count, st);
+        return;
+    }
+    ProfScope prof(PROF_COMPARE, st);
+    if (mode == 1) {
+        uint32_t *cmat = common;
+        uint64_t cld = ld;
+        if (!cmat) {
+            ctx.join[2].reserve(nr * nc * 4 + 256);
+            cmat = ctx.join[2].as<uint32_t>();
+            cld = nc;
+        }
+        SM_CUDA(cudaMemset2DAsync(cmat, cld * 4, 0, nc * 4, nr, st));
+        launch_incidences(true, keys, vals, n, cmat, cld, nullptr, nc, st);
+        launch_fill_cells(ro, rnum, r0, nr, co, c0, nc, 1, cmat, cld, common, size, ratio, ld, st);
+        return;
+    }
+    const uint64_t n_words = (nr * nc + 63) / 64;
+    ctx.join[2].reserve((n_words + 1) * 8);
+    ctx.join[3].reserve((n_words + 1) * 8);
+    ctx.join[4].reserve((n_words + 1) * 8);
+    unsigned long long *bitmap = ctx.join[2].as<unsigned long long>();
+    uint64_t *counts = ctx.join[3].as<uint64_t>(), *pre = ctx.join[4].as<uint64_t>();
+    SM_CUDA(cudaMemsetAsync(bitmap, 0, n_words * 8, st));
+    launch_incidences(false, keys, vals, n, nullptr, 0, bitmap, nc, st);
+    launch_fill_cells(ro, rnum, r0, nr, co, c0, nc, 0, nullptr, 0, common, size, ratio, ld, st);  // as if unrelated
+    launch_popc_words(bitmap, n_words, counts, st);
+    scan_exclusive_u64(counts, pre, n_words, ctx.scan_tmp.p, st);
+    uint64_t tail[2];
+    SM_CUDA(cudaMemcpyAsync(&tail[0], pre + (n_words - 1), 8, cudaMemcpyDeviceToHost, st));
+    SM_CUDA(cudaMemcpyAsync(&tail[1], counts + (n_words - 1), 8, cudaMemcpyDeviceToHost, st));
+    ctx.sync();
+    const uint64_t n_pairs = tail[0] + tail[1];
+    if (n_pairs) {
+        ctx.join[5].reserve((n_pairs + 1) * 8);
+        launch_expand_bits(bitmap, pre, n_words, ctx.join[5].as<uint64_t>(), st);
+        launch_walk_pairs(ctx.join[5].as<uint64_t>(), n_pairs, rh, ro, rnum, r0, ch, co, c0, nc, common, size, ratio, ld, st);
+    }
+}
+
 void compare_matrix(SketchCollection &rows, uint64_t r0, uint64_t nr, SketchCollection &cols, uint64_t c0, uint64_t nc,
                     int mode, uint32_t *common, uint32_t *size, double *ratio, uint64_t ld, bool out_on_device) {
     rows.check_compatible(cols);
@@ -102,26 +187,22 @@ void compare_matrix(SketchCollection &rows, uint64_t r0, uint64_t nr, SketchColl
     Context &ctx = Context::get();
     cudaStream_t st = ctx.stream;
     if (out_on_device) {
-        launch_compare_cross(rows.d_hashes.as<uint64_t>(), rows.d_offsets.as<uint64_t>(), rows.d_nums.as<uint32_t>(), r0, nr,
-                             cols.d_hashes.as<uint64_t>(), cols.d_offsets.as<uint64_t>(), c0, nc, mode, common, size, ratio,
-                             ld, cols.max_len, ctx.sm_count, st);
+        compare_block_device(rows, r0, nr, cols, c0, nc, mode, common, size, ratio, ld);
         ctx.sync();
         return;
     }
-    // host output: row blocks through device scratch, copied back block by block
-    const uint64_t block_rows = std::max<uint64_t>(1, std::min<uint64_t>(nr, (64ull << 20) / nc));
-    ctx.misc[0].reserve(block_rows * nc * 4);
-    ctx.misc[1].reserve(block_rows * nc * 4);
-    ctx.misc[2].reserve(block_rows * nc * 8);
+    // host output: row blocks of up to 2^28 cells through device scratch, copied back block by block
+    const uint64_t block_rows = std::max<uint64_t>(1, std::min<uint64_t>(nr, (1ull << 28) / nc));
+    ctx.misc[5].reserve(block_rows * nc * 4);
+    ctx.misc[6].reserve(block_rows * nc * 4);
+    ctx.misc[7].reserve(block_rows * nc * 8);
     for (uint64_t b0 = 0; b0 < nr; b0 += block_rows) {
         const uint64_t bn = std::min(block_rows, nr - b0);
-        launch_compare_cross(rows.d_hashes.as<uint64_t>(), rows.d_offsets.as<uint64_t>(), rows.d_nums.as<uint32_t>(),
-                             r0 + b0, bn, cols.d_hashes.as<uint64_t>(), cols.d_offsets.as<uint64_t>(), c0, nc, mode,
-                             common ? ctx.misc[0].as<uint32_t>() : nullptr, size ? ctx.misc[1].as<uint32_t>() : nullptr,
-                             ratio ? ctx.misc[2].as<double>() : nullptr, nc, cols.max_len, ctx.sm_count, st);
-        if (common) SM_CUDA(cudaMemcpy2DAsync(common + b0 * ld, ld * 4, ctx.misc[0].p, nc * 4, nc * 4, bn, cudaMemcpyDeviceToHost, st));
-        if (size) SM_CUDA(cudaMemcpy2DAsync(size + b0 * ld, ld * 4, ctx.misc[1].p, nc * 4, nc * 4, bn, cudaMemcpyDeviceToHost, st));
-        if (ratio) SM_CUDA(cudaMemcpy2DAsync(ratio + b0 * ld, ld * 8, ctx.misc[2].p, nc * 8, nc * 8, bn, cudaMemcpyDeviceToHost, st));
+        compare_block_device(rows, r0 + b0, bn, cols, c0, nc, mode, common ? ctx.misc[5].as<uint32_t>() : nullptr,
+                             size ? ctx.misc[6].as<uint32_t>() : nullptr, ratio ? ctx.misc[7].as<double>() : nullptr, nc);
+        if (common) SM_CUDA(cudaMemcpy2DAsync(common + b0 * ld, ld * 4, ctx.misc[5].p, nc * 4, nc * 4, bn, cudaMemcpyDeviceToHost, st));
+        if (size) SM_CUDA(cudaMemcpy2DAsync(size + b0 * ld, ld * 4, ctx.misc[6].p, nc * 4, nc * 4, bn, cudaMemcpyDeviceToHost, st));
+        if (ratio) SM_CUDA(cudaMemcpy2DAsync(ratio + b0 * ld, ld * 8, ctx.misc[7].p, nc * 8, nc * 8, bn, cudaMemcpyDeviceToHost, st));
         ctx.sync();
     }
 }
@@ -142,14 +223,12 @@ uint64_t linear_find(SketchCollection &index, SketchCollection &queries, int mod
         ctx.misc[3].reserve((cells + 1) * 8);  // flags, [query][index row]
         ctx.misc[4].reserve((cells + 1) * 8);  // scan
         ctx.misc[5].reserve((cells + 1) * 8);  // compacted cell ids
-        ctx.scan_tmp.reserve(scan_tmp_bytes(cells) + 256);
         std::vector<uint64_t> cellbuf;
         for (uint64_t b0 = 0; b0 < ni; b0 += block_rows) {
             const uint64_t bn = std::min(block_rows, ni - b0);
             const uint64_t n_cells = bn * nq;
-            launch_compare_cross(index.d_hashes.as<uint64_t>(), index.d_offsets.as<uint64_t>(), index.d_nums.as<uint32_t>(), b0,
-                                 bn, queries.d_hashes.as<uint64_t>(), queries.d_offsets.as<uint64_t>(), 0, nq, mode, nullptr,
-                                 nullptr, ctx.misc[2].as<double>(), nq, queries.max_len, ctx.sm_count, st);
+            compare_block_device(index, b0, bn, queries, 0, nq, mode, nullptr, nullptr, ctx.misc[2].as<double>(), nq);
+            ctx.scan_tmp.reserve(scan_tmp_bytes(cells) + 256);
             launch_threshold_flags_t(ctx.misc[2].as<double>(), bn, nq, threshold, ctx.misc[3].as<uint64_t>(), st);
             scan_exclusive_u64(ctx.misc[3].as<uint64_t>(), ctx.misc[4].as<uint64_t>(), n_cells, ctx.scan_tmp.p, st);
             launch_compact_indices(ctx.misc[3].as<uint64_t>(), ctx.misc[4].as<uint64_t>(), n_cells, ctx.misc[5].as<uint64_t>(), st);

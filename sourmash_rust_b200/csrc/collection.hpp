@@ -32,6 +32,7 @@ struct SketchCollection {
     void check_compatible(const SketchCollection &other) const;  // lib.rs:176-190
 };
 
+extern int g_compare_path;
 // see include/sourmash_b200.h
 void compare_matrix(SketchCollection &rows, uint64_t r0, uint64_t nr, SketchCollection &cols, uint64_t c0, uint64_t nc,
                     int mode, uint32_t *common, uint32_t *size, double *ratio, uint64_t ld, bool out_on_device);

@@ -93,7 +93,7 @@ struct Context {
     unsigned long long *d_scalars = nullptr;
     unsigned long long *h_scalars = nullptr;  // pinned mirror
     // scratch
-    DevBuf ascii, offsets, sort_tmp_k, sort_tmp_v, scan_tmp, misc[8];
+    DevBuf ascii, offsets, sort_tmp_k, sort_tmp_v, scan_tmp, misc[8], join[8];
     std::vector<cudaEvent_t> chunk_events;
 
     cudaStream_t copy_stream = nullptr;  // host->device staging, overlapped with `stream`

@@ -1,0 +1,222 @@
+// join.cu -- sparse all-vs-all: find the sketch pairs that share at least one hash with an
+// inverted index (sort all (hash, sketch) postings, walk the runs of equal hashes), so that the
+// merge walk of the reference (Intersection, src/lib.rs:515-544, inside intersection_size,
+// lib.rs:470-499) only runs for related pairs.  Unrelated pairs have common = 0 and
+// size = min(num, |A| + |B|) by definition, no walk needed.  For the untruncated intersection
+// (count_common, lib.rs:428-436; Leaf containment, index.rs:146-160) the postings walk yields
+// the counts directly.  Results are the same integers as the dense kernel's; which path runs is
+// decided from the number of (pair, shared hash) incidences.
+#include "device.hpp"
+#include "kernels.cuh"
+
+namespace smb200 {
+
+static unsigned blocks_for(uint64_t n, unsigned per_block, unsigned cap) {
+    uint64_t b = (n + per_block - 1) / per_block;
+    if (b == 0) b = 1;
+    return (unsigned)(b > cap ? cap : b);
+}
+
+// postings of rows [first, first + n_rows): key = hash, val = side << 63 | local row << 32 | position
+__global__ void __launch_bounds__(256) postings_kernel(const uint64_t *__restrict__ hashes,
+                                                       const uint64_t *__restrict__ offsets, uint64_t first,
+                                                       uint64_t n_rows, uint64_t side, uint64_t *__restrict__ keys,
+                                                       uint64_t *__restrict__ vals) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t base = offsets[first];
+    for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rows; r += warps) {
+        const uint64_t b = offsets[first + r], e = offsets[first + r + 1];
+        for (uint64_t i = b + lane; i < e; i += 32) {
+            keys[i - base] = hashes[i];
+            vals[i - base] = (side << 63) | (r << 32) | (i - b);
+        }
+    }
+}
+void launch_postings(const uint64_t *hashes, const uint64_t *offsets, uint64_t first, uint64_t n_rows, uint64_t side,
+                     uint64_t *keys, uint64_t *vals, cudaStream_t st) {
+    if (!n_rows) return;
+    postings_kernel<<<blocks_for(n_rows * 32, 256, 148 * 16), 256, 0, st>>>(hashes, offsets, first, n_rows, side, keys, vals);
+    SM_LAUNCHED();
+}
+
+// number of (row posting, column posting) incidences = sum over runs of equal hashes of
+// (row-side members) x (column-side members); the head of each run counts its run
+__global__ void __launch_bounds__(256) count_incidences_kernel(const uint64_t *__restrict__ keys,
+                                                               const uint64_t *__restrict__ vals, uint64_t n,
+                                                               unsigned long long *out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_round = (n + 31) / 32 * 32;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        unsigned long long local = 0;
+        if (i < n) {
+            const uint64_t key = keys[i];
+            if (i == 0 || keys[i - 1] != key) {
+                unsigned long long mr = 0, mc = 0;
+                for (uint64_t j = i; j < n && keys[j] == key; j++) {
+                    if (vals[j] >> 63) mc++; else mr++;
+                }
+                local = mr * mc;
+            }
+        }
+        for (int d = 16; d; d >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, d);
+        if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
+    }
+}
+void launch_count_incidences(const uint64_t *keys, const uint64_t *vals, uint64_t n, unsigned long long *out,
+                             cudaStream_t st) {
+    if (!n) return;
+    count_incidences_kernel<<<blocks_for(n, 256, 148 * 16), 256, 0, st>>>(keys, vals, n, out);
+    SM_LAUNCHED();
+}
+
+// Sorted postings (stable sort of [row postings, column postings]: inside a run of equal hashes the
+// row side comes first).  Every row posting walks forward over its run and, for each column posting,
+//   COUNT : atomicAdd(cmat[r * ld + c], 1)        (untruncated |A n B|)
+//   !COUNT: atomicOr on the related-pair bitmap   (bit r * nc + c)
+template <bool COUNT>
+__global__ void __launch_bounds__(256) incidences_kernel(const uint64_t *__restrict__ keys,
+                                                         const uint64_t *__restrict__ vals, uint64_t n,
+                                                         uint32_t *cmat, uint64_t ld, unsigned long long *bitmap,
+                                                         uint64_t nc) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t v = vals[i];
+        if (v >> 63) continue;  // column posting
+        const uint64_t key = keys[i];
+        const uint64_t r = (v >> 32) & 0x7FFFFFFFull;
+        for (uint64_t j = i + 1; j < n && keys[j] == key; j++) {
+            const uint64_t w = vals[j];
+            if (!(w >> 63)) continue;  // another row posting of the run
+            const uint64_t c = (w >> 32) & 0x7FFFFFFFull;
+            if (COUNT) {
+                atomicAdd(&cmat[r * ld + c], 1u);
+            } else {
+                const uint64_t bit = r * nc + c;
+                const unsigned long long m = 1ull << (bit & 63);
+                if (!(bitmap[bit >> 6] & m)) atomicOr(&bitmap[bit >> 6], m);  // test first: most incidences repeat a pair
+            }
+        }
+    }
+}
+void launch_incidences(bool count, const uint64_t *keys, const uint64_t *vals, uint64_t n, uint32_t *cmat, uint64_t ld,
+                       unsigned long long *bitmap, uint64_t nc, cudaStream_t st) {
+    if (!n) return;
+    if (count) incidences_kernel<true><<<blocks_for(n, 256, 148 * 32), 256, 0, st>>>(keys, vals, n, cmat, ld, bitmap, nc);
+    else incidences_kernel<false><<<blocks_for(n, 256, 148 * 32), 256, 0, st>>>(keys, vals, n, cmat, ld, bitmap, nc);
+    SM_LAUNCHED();
+}
+
+// bitmap -> per-word population counts (u64, for the scan)
+__global__ void popc_words_kernel(const unsigned long long *__restrict__ bitmap, uint64_t n_words, uint64_t *counts) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) counts[w] = __popcll(bitmap[w]);
+}
+void launch_popc_words(const unsigned long long *bitmap, uint64_t n_words, uint64_t *counts, cudaStream_t st) {
+    if (!n_words) return;
+    popc_words_kernel<<<blocks_for(n_words, 256, 148 * 16), 256, 0, st>>>(bitmap, n_words, counts);
+    SM_LAUNCHED();
+}
+// pairs[pre[w] + k] = index of the k-th set bit of word w (cell id r * nc + c, ascending)
+__global__ void expand_bits_kernel(const unsigned long long *__restrict__ bitmap, const uint64_t *__restrict__ pre,
+                                   uint64_t n_words, uint64_t *pairs) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+        unsigned long long m = bitmap[w];
+        uint64_t o = pre[w];
+        while (m) {
+            const int b = __ffsll((long long)m) - 1;
+            pairs[o++] = w * 64 + (uint64_t)b;
+            m &= m - 1;
+        }
+    }
+}
+void launch_expand_bits(const unsigned long long *bitmap, const uint64_t *pre, uint64_t n_words, uint64_t *pairs,
+                        cudaStream_t st) {
+    if (!n_words) return;
+    expand_bits_kernel<<<blocks_for(n_words, 256, 148 * 16), 256, 0, st>>>(bitmap, pre, n_words, pairs);
+    SM_LAUNCHED();
+}
+
+// every cell of the block as if the pair were unrelated (mode 0), or finished from the counts (mode 1)
+__global__ void __launch_bounds__(256) fill_cells_kernel(const uint64_t *__restrict__ ro, const uint32_t *__restrict__ rnum,
+                                                         uint64_t r0, uint64_t nr, const uint64_t *__restrict__ co,
+                                                         uint64_t c0, uint64_t nc, int mode, const uint32_t *cmat,
+                                                         uint64_t cld, uint32_t *common, uint32_t *size, double *ratio,
+                                                         uint64_t ld) {
+    const uint64_t n = nr * nc;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+        const uint64_t i = t / nc, j = t - i * nc;
+        const uint32_t na = (uint32_t)(ro[r0 + i + 1] - ro[r0 + i]);
+        uint32_t cm, sz;
+        double den;
+        if (mode == 0) {
+            const uint32_t nb = (uint32_t)(co[c0 + j + 1] - co[c0 + j]);
+            const uint32_t num = rnum ? rnum[r0 + i] : 0;
+            const uint64_t uni = (uint64_t)na + nb;
+            cm = 0;
+            sz = (uint32_t)((num != 0 && uni >= num) ? num : uni);  // lib.rs:391-401
+            den = (double)(sz > 1 ? sz : 1);
+        } else {
+            cm = cmat[i * cld + j];
+            sz = na;  // index.rs:152-154: the row (node) sketch is the denominator
+            den = (double)sz;
+        }
+        const size_t at = (size_t)i * ld + j;
+        if (common) common[at] = cm;
+        if (size) size[at] = sz;
+        if (ratio) ratio[at] = (double)cm / den;
+    }
+}
+void launch_fill_cells(const uint64_t *ro, const uint32_t *rnum, uint64_t r0, uint64_t nr, const uint64_t *co, uint64_t c0,
+                       uint64_t nc, int mode, const uint32_t *cmat, uint64_t cld, uint32_t *common, uint32_t *size,
+                       double *ratio, uint64_t ld, cudaStream_t st) {
+    if (!nr || !nc) return;
+    fill_cells_kernel<<<blocks_for(nr * nc, 256, 148 * 32), 256, 0, st>>>(ro, rnum, r0, nr, co, c0, nc, mode, cmat, cld, common,
+                                                                        size, ratio, ld);
+    SM_LAUNCHED();
+}
+
+// the reference's merge walk for the listed related pairs only (cell id = i * nc + j)
+__global__ void __launch_bounds__(256) walk_pairs_kernel(const uint64_t *__restrict__ pairs, uint64_t n_pairs,
+                                                         const uint64_t *__restrict__ rh, const uint64_t *__restrict__ ro,
+                                                         const uint32_t *__restrict__ rnum, uint64_t r0,
+                                                         const uint64_t *__restrict__ ch, const uint64_t *__restrict__ co,
+                                                         uint64_t c0, uint64_t nc, uint32_t *common, uint32_t *size,
+                                                         double *ratio, uint64_t ld) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_pairs; t += stride) {
+        const uint64_t cell = pairs[t];
+        const uint64_t i = cell / nc, j = cell - i * nc;
+        const uint64_t ab = ro[r0 + i], bb = co[c0 + j];
+        const uint32_t na = (uint32_t)(ro[r0 + i + 1] - ab), nb = (uint32_t)(co[c0 + j + 1] - bb);
+        const uint32_t num = rnum ? rnum[r0 + i] : 0;
+        const uint32_t limit = num ? num : 0xFFFFFFFFu;
+        const uint64_t *a = rh + ab, *b = ch + bb;
+        uint32_t x_i = 0, y_j = 0, c = 0, u = 0;
+        while (x_i < na && y_j < nb && u < limit) {  // lib.rs:470-499 in one pass
+            const uint64_t x = __ldg(a + x_i), y = __ldg(b + y_j);
+            c += (x == y);
+            x_i += (x <= y);
+            y_j += (y <= x);
+            u++;
+        }
+        const uint64_t uni = (uint64_t)u + (na - x_i) + (nb - y_j);
+        const uint32_t sz = (uint32_t)((num != 0 && uni >= num) ? num : uni);
+        const size_t at = (size_t)i * ld + j;
+        if (common) common[at] = c;
+        if (size) size[at] = sz;
+        if (ratio) ratio[at] = (double)c / (double)(sz > 1 ? sz : 1);
+    }
+}
+void launch_walk_pairs(const uint64_t *pairs, uint64_t n_pairs, const uint64_t *rh, const uint64_t *ro, const uint32_t *rnum,
+                       uint64_t r0, const uint64_t *ch, const uint64_t *co, uint64_t c0, uint64_t nc, uint32_t *common,
+                       uint32_t *size, double *ratio, uint64_t ld, cudaStream_t st) {
+    if (!n_pairs) return;
+    walk_pairs_kernel<<<blocks_for(n_pairs, 256, 148 * 16), 256, 0, st>>>(pairs, n_pairs, rh, ro, rnum, r0, ch, co, c0, nc, common,
+                                                                        size, ratio, ld);
+    SM_LAUNCHED();
+}
+
+}  // namespace smb200

@@ -115,6 +115,23 @@ void launch_csr_check_sorted(const uint64_t *hashes, const uint64_t *offsets, ui
 void launch_compact_indices(const uint64_t *flags, const uint64_t *pre, uint64_t n, uint64_t *out,
                             cudaStream_t st);
 
+// ---- join.cu: sparse all-vs-all through an inverted index (see the file header) ----------------
+void launch_postings(const uint64_t *hashes, const uint64_t *offsets, uint64_t first, uint64_t n_rows, uint64_t side,
+                     uint64_t *keys, uint64_t *vals, cudaStream_t st);
+void launch_count_incidences(const uint64_t *keys, const uint64_t *vals, uint64_t n, unsigned long long *out,
+                             cudaStream_t st);
+void launch_incidences(bool count, const uint64_t *keys, const uint64_t *vals, uint64_t n, uint32_t *cmat, uint64_t ld,
+                       unsigned long long *bitmap, uint64_t nc, cudaStream_t st);
+void launch_popc_words(const unsigned long long *bitmap, uint64_t n_words, uint64_t *counts, cudaStream_t st);
+void launch_expand_bits(const unsigned long long *bitmap, const uint64_t *pre, uint64_t n_words, uint64_t *pairs,
+                        cudaStream_t st);
+void launch_fill_cells(const uint64_t *ro, const uint32_t *rnum, uint64_t r0, uint64_t nr, const uint64_t *co, uint64_t c0,
+                       uint64_t nc, int mode, const uint32_t *cmat, uint64_t cld, uint32_t *common, uint32_t *size,
+                       double *ratio, uint64_t ld, cudaStream_t st);
+void launch_walk_pairs(const uint64_t *pairs, uint64_t n_pairs, const uint64_t *rh, const uint64_t *ro, const uint32_t *rnum,
+                       uint64_t r0, const uint64_t *ch, const uint64_t *co, uint64_t c0, uint64_t nc, uint32_t *common,
+                       uint32_t *size, double *ratio, uint64_t ld, cudaStream_t st);
+
 // integer-pipe microbenchmark (bench.py: measured INT32 issue peak); returns via out[0] a checksum
 void launch_int_peak(uint32_t *out, int iters, int blocks, int mode, cudaStream_t st);
 

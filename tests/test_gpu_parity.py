@@ -405,8 +405,16 @@ def _planted_rows(n_rows, n_hashes, seed, max_hash=None):
     return rows
 
 
+@pytest.fixture
+def compare_path(request):
+    smb.compare_path(request.param)
+    yield request.param
+    smb.compare_path("auto")
+
+
+@pytest.mark.parametrize("compare_path", ["auto", "dense", "sparse"], indirect=True)
 @pytest.mark.parametrize("num,n_hashes,mx", [(500, 500, 0), (0, 1200, MAX_HASH_1000 * 50), (100, 130, 0)])
-def test_compare_matrix_vs_oracle(num, n_hashes, mx):
+def test_compare_matrix_vs_oracle(num, n_hashes, mx, compare_path):
     rows = _planted_rows(96, n_hashes, 17 + num, mx or None)
     if num:
         rows = [r[:num] for r in rows]
@@ -441,6 +449,30 @@ def test_compare_matrix_vs_oracle(num, n_hashes, mx):
             got = smb.linear_find(coll, queries, mode, thr)
             for q in range(9):
                 assert got[q] == orc.linear_find(o_sk, o_sk[q], mode, thr)
+
+
+@pytest.mark.parametrize("compare_path", ["dense", "sparse"], indirect=True)
+def test_compare_mostly_unrelated_clusters(compare_path):
+    # the shape the sparse path is for: clusters of related sketches, everything else disjoint
+    import bench
+    N = 600
+    rows = bench.planted_sketches(N, 500, 99)
+    rows[17] = rows[16]  # identical pair
+    offs = np.arange(N + 1, dtype=np.uint64) * np.uint64(500)
+    coll = smb.SketchCollection.from_csr(rows.reshape(-1), offs, N, 500, 31)
+    common, size, ratio = smb.compare_matrix(coll, coll, "compare")
+    ccommon, csize, cratio = smb.compare_matrix(coll, coll, "containment")
+    osk = []
+    for i in range(N):
+        o = orc.KmerMinHash(500, 31)
+        o.add_many(rows[i])
+        osk.append(o)
+    oc, osz = orc.compare_matrix(osk, osk, 4)
+    assert np.array_equal(common, oc) and np.array_equal(size, osz)
+    assert np.array_equal(ratio, oc / np.maximum(1, osz))
+    assert np.array_equal(ccommon[:200, :200], orc.count_common_matrix(osk[:200], osk[:200]))
+    assert (csize == 500).all() and np.array_equal(cratio, ccommon / 500.0)
+    assert common[16, 17] == 500 and ratio[16, 17] == 1.0
 
 
 def test_unsorted_rows_rejected():  # .sbt.subset fixtures are stored unsorted
