@@ -31,9 +31,12 @@ READ_LEN = 150
 GENOME_LEN = 100_000_000
 SEED_GENOME = 0x5EED0010
 SEED_READS = 0x5EED0011
-# SASS instructions executed per window by the sketch kernels (ncu smsp__inst_executed / windows,
-# profiles/), used only for the integer-pipe roofline
-INSTR_PER_WINDOW = {21: None, 31: None, 51: None}
+# From the ncu --set full capture of the sketch kernels (profiles/sketch_r1_summary.md): executed SASS
+# thread-instructions per window (smsp__inst_executed x 32 / windows) and DRAM bytes per window
+# (dram__bytes_read + dram__bytes_write); used for the integer-issue roofline and roofline.traffic
+INSTR_PER_WINDOW = {21: 178.1, 31: 197.2, 51: 307.8}
+DRAM_BYTES_PER_WINDOW = {21: 1.031, 31: 1.024, 51: 1.026}
+NCU_ALU_PIPE_PCT = {21: 70.0, 31: 68.0, 51: 67.6}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -347,18 +350,12 @@ def run_ours(args):
         bytes_per_launch = args.steps * n_bytes / k31_n  # 1 B (one ASCII base) per window, SURVEY 8(d)
         achieved = bytes_per_launch / (k31_ms / k31_n * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "sketch_kernel<31>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": DRAM_BYTES_PER_WINDOW[31] * bytes_per_launch,
+                "traffic_source": "ncu dram__bytes_read+write per window (profiles/sketch_r1_summary.md) x windows per launch",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": k31_ms / k31_n,
                 "note": "HBM is not the binding resource of this kernel: see int_pipe"}
-    int_peak = smb.int_peak(2) if rank == 0 else None
     int_pipe = None
-    if rank == 0 and k31_n and INSTR_PER_WINDOW.get(31):
-        inst_rate = INSTR_PER_WINDOW[31] * (args.steps * n_bytes) / (k31_ms * 1e-3)
-        int_pipe = {"achieved_ginstr_s": inst_rate / 1e9, "peak_ginstr_s": int_peak / 1e9, "frac": inst_rate / int_peak,
-                    "instr_per_window": INSTR_PER_WINDOW[31]}
-    elif rank == 0:
-        int_pipe = {"peak_ginstr_s": int_peak / 1e9}
-
     # ---- all-vs-all compare (cfg3), rows sharded by rank, CSR all-gathered over NCCL -------------------
     compare = None
     if not args.no_compare:
@@ -385,6 +382,17 @@ def run_ours(args):
             assert g.md5sum() == o.md5sum() and np.array_equal(g.abunds_np(), o.abunds_np()), "GPU/CPU sketches differ"
         cpu["parity_checked"] = True
 
+    clk = clocks.summary(windows)
+    if rank == 0 and k31_n:
+        # integer-issue roofline: 4 warp instructions per clock per SM at the SM clock seen during the run
+        mhz = clk.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        issue_peak = 4 * 32 * sm_count * mhz * 1e6
+        inst_rate = INSTR_PER_WINDOW[31] * (args.steps * n_bytes) / (k31_ms * 1e-3)
+        int_pipe = {"kernel": "sketch_kernel<31>", "achieved_tinstr_s": inst_rate / 1e12, "peak_tinstr_s": issue_peak / 1e12,
+                    "frac": inst_rate / issue_peak, "instr_per_window": INSTR_PER_WINDOW[31],
+                    "peak_source": "4 warp-instr/clk/SM x 32 lanes x %d SMs x %.0f MHz (sampled during the run)" % (sm_count, mhz),
+                    "ncu_alu_pipe_pct": NCU_ALU_PIPE_PCT[31],
+                    "note": "binding resource of the sketch kernel; instruction count from the ncu capture in profiles/"}
     if rank == 0:
         line = {
             "metric": "Gbp/s sketched", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
@@ -400,7 +408,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": roof, "int_pipe": int_pipe, "sketch_kernels": per_k,
             "cpu_baseline": cpu,
-            "clocks": clocks.summary(windows),
+            "clocks": clk,
             "compare": compare,
         }
         print(json.dumps(line), flush=True)

@@ -488,6 +488,54 @@ def test_unsorted_rows_rejected():  # .sbt.subset fixtures are
         smb.SketchCollection.from_sketches([mh])
 
 
+def test_cfg4_containment_search_scaled():  # BASELINE config 4 shape, reduced: scaled index, query batch
+    r = np.random.Generator(np.random.PCG64(4))
+    mx = MAX_HASH_1000 * 4
+    index, o_index = [], []
+    base = [np.unique(r.integers(0, mx, size=3000, dtype=np.uint64)) for _ in range(12)]
+    for i in range(240):
+        b = base[i % 12]
+        keep = b[r.random(b.size) < (0.1, 0.3, 0.6, 0.9)[i % 4]]
+        row = np.unique(np.concatenate([keep, r.integers(0, mx, size=int(r.integers(50, 2500)), dtype=np.uint64)]))
+        g, o = pair(0, 31, mx)
+        g.set_mins(row); o.add_many(row)
+        index.append(g); o_index.append(o)
+    queries, o_queries = [], []
+    for q in range(10):
+        row = np.unique(np.concatenate([base[q][::2], r.integers(0, mx, size=1500, dtype=np.uint64)]))
+        g, o = pair(0, 31, mx)
+        g.set_mins(row); o.add_many(row)
+        queries.append(g); o_queries.append(o)
+    ic, qc = smb.SketchCollection.from_sketches(index), smb.SketchCollection.from_sketches(queries)
+    for path in ("dense", "sparse", "auto"):
+        smb.compare_path(path)
+        for mode in ("containment", "similarity"):
+            got = smb.linear_find(ic, qc, mode, 0.1)  # threshold of benches/index.rs:33
+            for q in range(10):
+                assert got[q] == orc.linear_find(o_index, o_queries[q], mode, 0.1), (path, mode, q)
+    smb.compare_path("auto")
+    assert any(len(h) for h in got)
+
+
+def test_cfg5_sketch_then_all_vs_all():  # BASELINE config 5 shape, reduced: genomes -> scaled sketches -> matrix
+    roots = [random_dna(120_000, 0x5EED2000 + c) for c in range(4)]
+    gs, os_ = [], []
+    for i in range(24):
+        genome = mutate(roots[i % 4], (0.001, 0.005, 0.01, 0.02, 0.05)[i % 5], 7000 + i)
+        g, o = pair(0, 31, MAX_HASH_1000 * 10)
+        g.add_sequence(genome); o.add_sequence(genome)
+        gs.append(g); os_.append(o)
+    coll = smb.SketchCollection.from_sketches(gs)
+    for path in ("dense", "sparse"):
+        smb.compare_path(path)
+        common, size, ratio = smb.compare_matrix(coll, coll, "compare")
+        oc, osz = orc.compare_matrix(os_, os_)
+        assert np.array_equal(common, oc) and np.array_equal(size, osz)
+        assert np.array_equal(ratio, oc / np.maximum(1, osz))
+    smb.compare_path("auto")
+    assert ratio[0, 4] > 0.3 and ratio[0, 1] < 0.01  # same root vs different roots
+
+
 # ------------------------------------------------------------------------------------------------
 # Signature JSON
 # ------------------------------------------------------------------------------------------------
