@@ -533,7 +533,7 @@ def test_cfg5_sketch_then_all_vs_all():  # BASELINE config 5 shape, reduced: gen
         assert np.array_equal(common, oc) and np.array_equal(size, osz)
         assert np.array_equal(ratio, oc / np.maximum(1, osz))
     smb.compare_path("auto")
-    assert ratio[0, 4] > 0.3 and ratio[0, 1] < 0.01  # same root vs different roots
+    assert ratio[0, 4] > 0.05 and ratio[0, 1] < 0.01  # same root (0.1% vs 5% mutated) vs different roots
 
 
 # ------------------------------------------------------------------------------------------------
