@@ -302,14 +302,15 @@ def run_ours(args):
 
     # ---- end-to-end path: pinned host buffers in, sketches read back every step ------------------------
     mhs2 = new_sketches()
-    out_m = [np.zeros(1 << 22, dtype=np.uint64) for _ in KSIZES]
-    out_a = [np.zeros(1 << 22, dtype=np.uint64) for _ in KSIZES]
+    # pinned host buffers for the sketches read back every step
+    out_m = [torch.zeros(1 << 22, dtype=torch.int64, pin_memory=True) for _ in KSIZES]
+    out_a = [torch.zeros(1 << 22, dtype=torch.int64, pin_memory=True) for _ in KSIZES]
 
     def e2e_step(s):
         smb.add_reads(mhs2, host_batches[s % n_batches].data_ptr(), R, READ_LEN, force=False, on_device=False)
         d2h = 0
         for i, m in enumerate(mhs2):
-            n = smb._call("kmerminhash_copy_mins", m._p, smb._vp(out_m[i]), smb._vp(out_a[i]), False)
+            n = smb._call("kmerminhash_copy_mins", m._p, smb._vp(out_m[i].data_ptr()), smb._vp(out_a[i].data_ptr()), False)
             d2h += 16 * n
         return d2h
 

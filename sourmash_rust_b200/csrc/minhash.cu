@@ -466,13 +466,16 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
         o.counter = mh.hs(0);
         return o;
     };
-    const uint64_t CHUNK = 32ull << 20;
+    // copy chunks grow 4 -> 32 MiB: the first kernels start after a short copy, later chunks amortise launches
+    uint64_t chunk = 4ull << 20;
+    const uint64_t CHUNK_MAX = 32ull << 20;
     uint64_t copied = batch.on_device ? n : 0;
     if (!batch.on_device) SM_CUDA(cudaStreamSynchronize(st));  // scalars / offsets in place before the copy stream races ahead
     size_t ev_i = 0;
     do {
         if (!batch.on_device) {
-            const uint64_t len = std::min<uint64_t>(CHUNK, n - copied);
+            const uint64_t len = std::min<uint64_t>(chunk, n - copied);
+            chunk = std::min<uint64_t>(chunk * 2, CHUNK_MAX);
             SM_CUDA(cudaMemcpyAsync(const_cast<uint8_t *>(d_buf) + copied, batch.buf + copied, len, cudaMemcpyHostToDevice,
                                     ctx.copy_stream));
             copied += len;

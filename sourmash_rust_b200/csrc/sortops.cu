@@ -247,7 +247,6 @@ void radix_sort_pairs(uint64_t *keys, uint64_t *vals, uint64_t n, uint64_t *tmp_
     void *stmp = reinterpret_cast<char *>(scan_tmp) + ((table * sizeof(uint64_t) + 255) / 256 * 256);
     int passes = (end_bit + 7) / 8;
     if (passes < 1) passes = 1;
-    if (passes & 1) passes++;  // even number of passes: the result lands back in keys/vals
     if (passes > 8) passes = 8;
     const bool has_vals = vals != nullptr;
     uint64_t *src_k = keys, *src_v = vals, *dst_k = tmp_keys, *dst_v = has_vals ? tmp_vals : nullptr;
@@ -260,6 +259,10 @@ void radix_sort_pairs(uint64_t *keys, uint64_t *vals, uint64_t n, uint64_t *tmp_
         SM_LAUNCHED();
         uint64_t *t = src_k; src_k = dst_k; dst_k = t;
         t = src_v; src_v = dst_v; dst_v = t;
+    }
+    if (src_k != keys) {  // odd number of passes: the sorted data sits in the temporaries
+        SM_CUDA(cudaMemcpyAsync(keys, src_k, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+        if (has_vals) SM_CUDA(cudaMemcpyAsync(vals, src_v, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
     }
 }
 
