@@ -110,7 +110,10 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
     const uint64_t *rh = rows.d_hashes.as<uint64_t>(), *ro = rows.d_offsets.as<uint64_t>();
     const uint64_t *ch = cols.d_hashes.as<uint64_t>(), *co = cols.d_offsets.as<uint64_t>();
     const uint32_t *rnum = rows.d_nums.as<uint32_t>();
-    const uint64_t n_r = rows.h_offsets[r0 + nr] - rows.h_offsets[r0];
+    // rows and columns from the same collection with the row range inside the column range (the
+    // all-vs-all case, whole or row-sharded): one postings set serves both sides
+    const bool shared = (&rows == &cols) && r0 >= c0 && r0 + nr <= c0 + nc;
+    const uint64_t n_r = shared ? 0 : rows.h_offsets[r0 + nr] - rows.h_offsets[r0];
     const uint64_t n_c = cols.h_offsets[c0 + nc] - cols.h_offsets[c0];
     const uint64_t n = n_r + n_c;
     const bool force_dense = g_compare_path == 1, force_sparse = g_compare_path == 2;
@@ -125,12 +128,16 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
         ctx.scan_tmp.reserve(std::max(radix_sort_scan_bytes(n), scan_tmp_bytes(std::max<uint64_t>(n, (nr * nc + 63) / 64))) + 256);
         keys = ctx.join[0].as<uint64_t>();
         vals = ctx.join[1].as<uint64_t>();
-        launch_postings(rh, ro, r0, nr, 0, keys, vals, st);
-        launch_postings(ch, co, c0, nc, 1, keys + n_r, vals + n_r, st);
+        if (!shared) launch_postings(rh, ro, r0, nr, 0, keys, vals, st);
+        launch_postings(ch, co, c0, nc, shared ? 0 : 1, keys + n_r, vals + n_r, st);
+        SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_TMAX), 0, 8, st));
+        launch_max_u64(keys, n, ctx.dsc(SC_TMAX), st);
+        ctx.read_scalars();
         radix_sort_pairs(keys, vals, n, ctx.sort_tmp_k.as<uint64_t>(), ctx.sort_tmp_v.as<uint64_t>(),
-                         rows.max_hash ? bit_length64(rows.max_hash) : 64, ctx.scan_tmp.p, ctx.scan_tmp.cap, st);
+                         std::max(1, bit_length64(ctx.h_scalars[SC_TMAX])), ctx.scan_tmp.p, ctx.scan_tmp.cap, st);
         SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_CNT), 0, 8, st));
-        launch_count_incidences(keys, vals, n, ctx.dsc(SC_CNT), st);
+        if (shared) launch_count_incidences_shared(keys, vals, n, r0 - c0, nr, ctx.dsc(SC_CNT), st);
+        else launch_count_incidences(keys, vals, n, ctx.dsc(SC_CNT), st);
         ctx.read_scalars();
         const uint64_t incidences = ctx.h_scalars[SC_CNT];
         if (!force_sparse && incidences > 8 * nr * nc) sparse = false;  // mostly-related collections: the dense kernel wins
@@ -149,7 +156,8 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
             cld = nc;
         }
         SM_CUDA(cudaMemset2DAsync(cmat, cld * 4, 0, nc * 4, nr, st));
-        launch_incidences(true, keys, vals, n, cmat, cld, nullptr, nc, st);
+        if (shared) launch_incidences_shared(true, keys, vals, n, r0 - c0, nr, cmat, cld, nullptr, nc, st);
+        else launch_incidences(true, keys, vals, n, cmat, cld, nullptr, nc, st);
         launch_fill_cells(ro, rnum, r0, nr, co, c0, nc, 1, cmat, cld, common, size, ratio, ld, st);
         return;
     }
@@ -160,7 +168,8 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
     unsigned long long *bitmap = ctx.join[2].as<unsigned long long>();
     uint64_t *counts = ctx.join[3].as<uint64_t>(), *pre = ctx.join[4].as<uint64_t>();
     SM_CUDA(cudaMemsetAsync(bitmap, 0, n_words * 8, st));
-    launch_incidences(false, keys, vals, n, nullptr, 0, bitmap, nc, st);
+    if (shared) launch_incidences_shared(false, keys, vals, n, r0 - c0, nr, nullptr, 0, bitmap, nc, st);
+    else launch_incidences(false, keys, vals, n, nullptr, 0, bitmap, nc, st);
     launch_fill_cells(ro, rnum, r0, nr, co, c0, nc, 0, nullptr, 0, common, size, ratio, ld, st);  // as if unrelated
     launch_popc_words(bitmap, n_words, counts, st);
     scan_exclusive_u64(counts, pre, n_words, ctx.scan_tmp.p, st);

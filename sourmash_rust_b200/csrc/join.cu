@@ -70,6 +70,91 @@ void launch_count_incidences(const uint64_t *keys, const uint64_t *vals, uint64_
     SM_LAUNCHED();
 }
 
+// max over the keys (decides how many radix passes the sort needs)
+__global__ void max_u64_kernel(const uint64_t *__restrict__ keys, uint64_t n, unsigned long long *out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long m = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) m = max(m, (unsigned long long)keys[i]);
+    for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, d));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+void launch_max_u64(const uint64_t *keys, uint64_t n, unsigned long long *out, cudaStream_t st) {
+    if (!n) return;
+    max_u64_kernel<<<blocks_for(n, 256, 148 * 8), 256, 0, st>>>(keys, n, out);
+    SM_LAUNCHED();
+}
+
+// One postings set for both sides (rows and columns come from the same collection and the row range
+// lies inside the column range): posting value = column-local sketch id << 32 | position; a posting is
+// also a row posting when its sketch lies in [row_lo, row_lo + nr) (column-local ids).  Each posting
+// walks forward over its run and handles both ordered pairs it forms with every later member, plus
+// the pair with itself.
+template <bool COUNT>
+__global__ void __launch_bounds__(256) incidences_shared_kernel(const uint64_t *__restrict__ keys,
+                                                                const uint64_t *__restrict__ vals, uint64_t n,
+                                                                uint64_t row_lo, uint64_t nr, uint32_t *cmat, uint64_t ld,
+                                                                unsigned long long *bitmap, uint64_t nc) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    auto hit = [&](uint64_t r, uint64_t c) {
+        if (COUNT) {
+            atomicAdd(&cmat[r * ld + c], 1u);
+        } else {
+            const uint64_t bit = r * nc + c;
+            const unsigned long long m = 1ull << (bit & 63);
+            if (!(bitmap[bit >> 6] & m)) atomicOr(&bitmap[bit >> 6], m);
+        }
+    };
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t key = keys[i];
+        const uint64_t ci = vals[i] >> 32;
+        const bool i_row = ci >= row_lo && ci - row_lo < nr;
+        if (i_row) hit(ci - row_lo, ci);
+        for (uint64_t j = i + 1; j < n && keys[j] == key; j++) {
+            const uint64_t cj = vals[j] >> 32;
+            if (i_row) hit(ci - row_lo, cj);
+            if (cj >= row_lo && cj - row_lo < nr) hit(cj - row_lo, ci);
+        }
+    }
+}
+void launch_incidences_shared(bool count, const uint64_t *keys, const uint64_t *vals, uint64_t n, uint64_t row_lo,
+                              uint64_t nr, uint32_t *cmat, uint64_t ld, unsigned long long *bitmap, uint64_t nc,
+                              cudaStream_t st) {
+    if (!n) return;
+    if (count) incidences_shared_kernel<true><<<blocks_for(n, 256, 148 * 32), 256, 0, st>>>(keys, vals, n, row_lo, nr, cmat, ld, bitmap, nc);
+    else incidences_shared_kernel<false><<<blocks_for(n, 256, 148 * 32), 256, 0, st>>>(keys, vals, n, row_lo, nr, cmat, ld, bitmap, nc);
+    SM_LAUNCHED();
+}
+// incidences of the shared-postings form: per run of m members of which mr are rows: mr * m
+__global__ void __launch_bounds__(256) count_incidences_shared_kernel(const uint64_t *__restrict__ keys,
+                                                                      const uint64_t *__restrict__ vals, uint64_t n,
+                                                                      uint64_t row_lo, uint64_t nr, unsigned long long *out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_round = (n + 31) / 32 * 32;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        unsigned long long local = 0;
+        if (i < n) {
+            const uint64_t key = keys[i];
+            if (i == 0 || keys[i - 1] != key) {
+                unsigned long long m = 0, mr = 0;
+                for (uint64_t j = i; j < n && keys[j] == key; j++) {
+                    const uint64_t c = vals[j] >> 32;
+                    m++;
+                    mr += (c >= row_lo && c - row_lo < nr);
+                }
+                local = mr * m;
+            }
+        }
+        for (int d = 16; d; d >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, d);
+        if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
+    }
+}
+void launch_count_incidences_shared(const uint64_t *keys, const uint64_t *vals, uint64_t n, uint64_t row_lo, uint64_t nr,
+                                    unsigned long long *out, cudaStream_t st) {
+    if (!n) return;
+    count_incidences_shared_kernel<<<blocks_for(n, 256, 148 * 16), 256, 0, st>>>(keys, vals, n, row_lo, nr, out);
+    SM_LAUNCHED();
+}
+
 // Sorted postings (stable sort of [row postings, column postings]: inside a run of equal hashes the
 // row side comes first).  Every row posting walks forward over its run and, for each column posting,
 //   COUNT : atomicAdd(cmat[r * ld + c], 1)        (untruncated |A n B|)

@@ -122,6 +122,12 @@ void launch_count_incidences(const uint64_t *keys, const uint64_t *vals, uint64_
                              cudaStream_t st);
 void launch_incidences(bool count, const uint64_t *keys, const uint64_t *vals, uint64_t n, uint32_t *cmat, uint64_t ld,
                        unsigned long long *bitmap, uint64_t nc, cudaStream_t st);
+void launch_max_u64(const uint64_t *keys, uint64_t n, unsigned long long *out, cudaStream_t st);
+void launch_incidences_shared(bool count, const uint64_t *keys, const uint64_t *vals, uint64_t n, uint64_t row_lo,
+                              uint64_t nr, uint32_t *cmat, uint64_t ld, unsigned long long *bitmap, uint64_t nc,
+                              cudaStream_t st);
+void launch_count_incidences_shared(const uint64_t *keys, const uint64_t *vals, uint64_t n, uint64_t row_lo, uint64_t nr,
+                                    unsigned long long *out, cudaStream_t st);
 void launch_popc_words(const unsigned long long *bitmap, uint64_t n_words, uint64_t *counts, cudaStream_t st);
 void launch_expand_bits(const unsigned long long *bitmap, const uint64_t *pre, uint64_t n_words, uint64_t *pairs,
                         cudaStream_t st);

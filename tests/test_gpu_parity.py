@@ -473,6 +473,14 @@ def test_compare_mostly_unrelated_clusters(compare_path):
     assert np.array_equal(ccommon[:200, :200], orc.count_common_matrix(osk[:200], osk[:200]))
     assert (csize == 500).all() and np.array_equal(cratio, ccommon / 500.0)
     assert common[16, 17] == 500 and ratio[16, 17] == 1.0
+    # row-sharded block of the same collection (one postings set serves both sides) ...
+    c2, s2, r2 = smb.compare_matrix(coll, coll, "compare", r0=100, nr=150, c0=0, nc=N)
+    assert np.array_equal(c2, oc[100:250]) and np.array_equal(s2, osz[100:250])
+    c2, s2, r2 = smb.compare_matrix(coll, coll, "containment", r0=100, nr=150, c0=50, nc=300)
+    assert np.array_equal(c2, ccommon[100:250, 50:350])
+    # ... and a row range that sticks out of the column range (two postings sets)
+    c2, s2, r2 = smb.compare_matrix(coll, coll, "compare", r0=0, nr=300, c0=200, nc=300)
+    assert np.array_equal(c2, oc[0:300, 200:500]) and np.array_equal(r2, (oc / np.maximum(1, osz))[0:300, 200:500])
 
 
 def test_unsorted_rows_rejected():  # .sbt.subset fixtures are stored unsorted
