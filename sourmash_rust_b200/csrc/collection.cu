@@ -92,6 +92,18 @@ void SketchCollection::check_compatible(const SketchCollection &o) const {
     if (seed != o.seed) throw SourmashError(ERR_MISMATCH_SEED, "mismatch in seed; comparison fail");
 }
 
+// every sketch of rows [first, first + n) holds exactly `len` hashes and has num == len
+static bool block_is_full(const SketchCollection &c, uint64_t first, uint64_t n, uint32_t *len_out) {
+    if (!n) return false;
+    const uint64_t len = c.h_offsets[first + 1] - c.h_offsets[first];
+    if (len == 0 || len > 0xFFFFFFFFull) return false;
+    for (uint64_t i = 0; i < n; i++) {
+        if (c.h_offsets[first + i + 1] - c.h_offsets[first + i] != len || c.h_nums[first + i] != len) return false;
+    }
+    *len_out = (uint32_t)len;
+    return true;
+}
+
 int g_compare_path = 0;  // 0 = choose from the data, 1 = dense tile kernel, 2 = inverted-index path
 
 static int bit_length64(uint64_t x) {
@@ -117,9 +129,14 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
     const uint64_t n_c = cols.h_offsets[c0 + nc] - cols.h_offsets[c0];
     const uint64_t n = n_r + n_c;
     const bool force_dense = g_compare_path == 1, force_sparse = g_compare_path == 2;
-    bool sparse = !force_dense && n > 0 && (force_sparse || nr * nc >= 4096) && nr < (1ull << 31) && nc < (1ull << 31);
+    const bool big = n > 0 && nr * nc >= 4096 && nr < (1ull << 31) && nc < (1ull << 31);
+    bool sparse = !force_dense && n > 0 && (force_sparse || big) && nr < (1ull << 31) && nc < (1ull << 31);
+    // full num sketches (Jaccard): the dense walk can run on 32-bit ranks with a fixed trip count
+    uint32_t L = 0, Lc = 0;
+    const bool full = mode == 0 && big && block_is_full(rows, r0, nr, &L) && block_is_full(cols, c0, nc, &Lc) && L == Lc &&
+                      compare_full_fits(L);
     uint64_t *keys = nullptr, *vals = nullptr;
-    if (sparse) {
+    if (sparse || (full && !force_sparse)) {
         ProfScope prof(PROF_SORT, st);
         ctx.join[0].reserve((n + 1) * 8);
         ctx.join[1].reserve((n + 1) * 8);
@@ -141,6 +158,21 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
         ctx.read_scalars();
         const uint64_t incidences = ctx.h_scalars[SC_CNT];
         if (!force_sparse && incidences > 8 * nr * nc) sparse = false;  // mostly-related collections: the dense kernel wins
+    }
+    if (!sparse && full && keys) {
+        // ranks from the sorted postings: head flags -> scan -> scatter back to sketch order
+        ctx.join[2].reserve((n + 1) * 8);
+        ctx.join[3].reserve((n + 1) * 8);
+        ctx.join[6].reserve((n + 1) * 4);
+        uint64_t *flags = ctx.join[2].as<uint64_t>(), *pre = ctx.join[3].as<uint64_t>();
+        uint32_t *ranks = ctx.join[6].as<uint32_t>();
+        launch_heads(keys, n, flags, st);
+        scan_exclusive_u64(flags, pre, n, ctx.scan_tmp.p, st);
+        launch_scatter_ranks(keys, vals, pre, n, L, n_r, ranks, st);
+        const uint32_t *rb = ranks + n_r;                                  // column sketches
+        const uint32_t *ra = shared ? rb + (r0 - c0) * (uint64_t)L : ranks;  // row sketches
+        launch_compare_full(ra, rb, L, nr, nc, common, size, ratio, ld, st);
+        return;
     }
     if (!sparse) {
         launch_compare_cross(rh, ro, rnum, r0, nr, ch, co, c0, nc, mode, common, size, ratio, ld, cols.max_len, ctx.sm_count, st);

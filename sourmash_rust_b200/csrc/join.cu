@@ -305,3 +305,95 @@ void launch_walk_pairs(const uint64_t *pairs, uint64_t n_pairs, const uint64_t *
 }
 
 }  // namespace smb200
+
+// =====================================================================================
+// Dense path for FULL num sketches (every sketch of the block holds exactly L = num hashes):
+// the hashes are replaced by their dense ranks (u32) among all hashes of the block -- order and
+// equality are preserved, so the merge walk sees the same comparisons -- and the walk becomes a
+// loop of exactly L steps (the union of two full sketches always has >= num elements, so
+// intersection_size stops after num union elements, lib.rs:470-499).
+// =====================================================================================
+namespace smb200 {
+
+// sorted postings -> rank of every posting's hash, scattered back to sketch order:
+// out[(side ? b_base : 0) + row * L + pos] = number of distinct hashes smaller than it
+__global__ void __launch_bounds__(256) scatter_ranks_kernel(const uint64_t *__restrict__ keys,
+                                                            const uint64_t *__restrict__ vals,
+                                                            const uint64_t *__restrict__ pre, uint64_t n, uint32_t L,
+                                                            uint64_t b_base, uint32_t *__restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const bool head = (i == 0) || keys[i] != keys[i - 1];
+        const uint64_t rank = pre[i] + (head ? 1 : 0) - 1;  // pre = exclusive scan of the head flags
+        const uint64_t v = vals[i];
+        const uint64_t row = (v >> 32) & 0x7FFFFFFFull, pos = v & 0xFFFFFFFFull;
+        out[((v >> 63) ? b_base : 0) + row * L + pos] = (uint32_t)rank;
+    }
+}
+void launch_scatter_ranks(const uint64_t *keys, const uint64_t *vals, const uint64_t *pre, uint64_t n, uint32_t L,
+                          uint64_t b_base, uint32_t *out, cudaStream_t st) {
+    if (!n) return;
+    scatter_ranks_kernel<<<blocks_for(n, 256, 148 * 16), 256, 0, st>>>(keys, vals, pre, n, L, b_base, out);
+    SM_LAUNCHED();
+}
+
+// CTA = 32 rows x 32 columns = 1024 pairs = 1024 threads.  Both tiles sit in shared memory
+// element-major, [element][sketch]: the lane that owns sketch s always touches bank s.  Warp w
+// takes the w-th diagonal: lane l walks (row l, column (l + w) mod 32), so within a warp every
+// row AND every column is used by exactly one lane -- no bank conflict on either operand, whatever
+// the two walk positions are.  One extra all-ones element per sketch stops a finished list.
+constexpr int CF_THREADS = 1024;
+__global__ void __launch_bounds__(CF_THREADS, 1)
+compare_full_kernel(const uint32_t *__restrict__ ra, const uint32_t *__restrict__ rb, uint32_t L, uint64_t nr,
+                    uint64_t nc, uint32_t *common, uint32_t *size, double *ratio, uint64_t ld) {
+    extern __shared__ __align__(16) uint32_t s_rank[];  // A: (L+1) x 32, then B: (L+1) x 32
+    uint32_t *sA = s_rank, *sB = s_rank + (size_t)(L + 1) * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t row0 = (uint64_t)blockIdx.y * 32, col0 = (uint64_t)blockIdx.x * 32;
+    // stage: lane <-> sketch (bank = lane), warp strides over the elements
+    {
+        const uint64_t r = min(row0 + lane, nr - 1), c = min(col0 + lane, nc - 1);
+        const uint32_t *ga = ra + r * L, *gb = rb + c * L;
+        for (uint32_t e = warp; e < L; e += CF_THREADS / 32) {
+            sA[e * 32 + lane] = __ldg(ga + e);
+            sB[e * 32 + lane] = __ldg(gb + e);
+        }
+        if (warp == 0) { sA[L * 32 + lane] = 0xFFFFFFFFu; sB[L * 32 + lane] = 0xFFFFFFFFu; }
+    }
+    __syncthreads();
+    const int cl = (lane + warp) & 31;
+    const uint32_t *a = sA + lane, *b = sB + cl;
+    uint32_t ia = 0, jb = 0;  // element indices, pre-multiplied by 32 (words)
+    uint32_t x = a[0], y = b[0];
+#pragma unroll 4
+    for (uint32_t u = 0; u < L; u++) {  // one union element per step
+        const bool adv_a = x <= y, adv_b = y <= x;
+        ia += adv_a ? 32u : 0u;
+        jb += adv_b ? 32u : 0u;
+        x = a[ia];
+        y = b[jb];
+    }
+    // every step consumes one element of A, of B, or (when equal) one of each: i + j = L + common
+    const uint32_t c = (ia + jb) / 32 - L;
+    const uint64_t row = row0 + lane, col = col0 + cl;
+    if (row < nr && col < nc) {
+        const size_t at = (size_t)row * ld + col;
+        if (common) common[at] = c;
+        if (size) size[at] = L;
+        if (ratio) ratio[at] = (double)c / (double)(L > 1 ? L : 1);
+    }
+}
+bool compare_full_fits(uint32_t L) { return L >= 1 && (size_t)(L + 1) * 32 * 4 * 2 <= 220 * 1024; }
+void launch_compare_full(const uint32_t *ra, const uint32_t *rb, uint32_t L, uint64_t nr, uint64_t nc, uint32_t *common,
+                         uint32_t *size, double *ratio, uint64_t ld, cudaStream_t st) {
+    if (!nr || !nc) return;
+    const size_t smem = (size_t)(L + 1) * 32 * 4 * 2;
+    SM_CUDA(cudaFuncSetAttribute(compare_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((nc + 31) / 32), (unsigned)((nr + 31) / 32));
+    if (grid.y > 65535) throw_internal("row block too tall for one launch");
+    ProfScope prof(PROF_COMPARE, st);
+    compare_full_kernel<<<grid, CF_THREADS, smem, st>>>(ra, rb, L, nr, nc, common, size, ratio, ld);
+    SM_LAUNCHED();
+}
+
+}  // namespace smb200

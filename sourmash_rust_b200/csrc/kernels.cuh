@@ -138,6 +138,14 @@ void launch_walk_pairs(const uint64_t *pairs, uint64_t n_pairs, const uint64_t *
                        uint64_t r0, const uint64_t *ch, const uint64_t *co, uint64_t c0, uint64_t nc, uint32_t *common,
                        uint32_t *size, double *ratio, uint64_t ld, cudaStream_t st);
 
+// dense path for full num sketches: dense u32 ranks + fixed-length walk (join.cu)
+void launch_scatter_ranks(const uint64_t *keys, const uint64_t *vals, const uint64_t *pre, uint64_t n, uint32_t L,
+                          uint64_t b_base, uint32_t *out, cudaStream_t st);
+bool compare_full_fits(uint32_t L);
+void launch_compare_full(const uint32_t *ra, const uint32_t *rb, uint32_t L, uint64_t nr, uint64_t nc, uint32_t *common,
+                         uint32_t *size, double *ratio, uint64_t ld, cudaStream_t st);
+void launch_heads(const uint64_t *keys, uint64_t n, uint64_t *flags, cudaStream_t st);
+
 // integer-pipe microbenchmark (bench.py: measured INT32 issue peak); returns via out[0] a checksum
 void launch_int_peak(uint32_t *out, int iters, int blocks, int mode, cudaStream_t st);
 

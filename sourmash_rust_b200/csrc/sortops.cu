@@ -274,6 +274,11 @@ __global__ void heads_kernel(const uint64_t *__restrict__ keys, uint64_t n, uint
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
 }
+void launch_heads(const uint64_t *keys, uint64_t n, uint64_t *flags, cudaStream_t st) {
+    if (!n) return;
+    heads_kernel<<<grid_for(n, 256), 256, 0, st>>>(keys, n, flags);
+    SM_LAUNCHED();
+}
 // idx[i] = exclusive scan of head flags; run id of element i = idx[i] + head(i) - 1
 __global__ void rbk_scatter_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ vals,
                                    uint64_t n, uint64_t *__restrict__ idx, uint64_t *__restrict__ ukeys,

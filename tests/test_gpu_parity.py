@@ -483,6 +483,38 @@ def test_compare_mostly_unrelated_clusters(compare_path):
     assert np.array_equal(c2, oc[0:300, 200:500]) and np.array_equal(r2, (oc / np.maximum(1, osz))[0:300, 200:500])
 
 
+@pytest.mark.parametrize("compare_path", ["auto", "dense", "sparse"], indirect=True)
+def test_compare_mostly_related_full_sketches(compare_path):
+    # one big family: every pair shares most hashes -> the data-driven choice is the dense walk,
+    # which for full num sketches runs on 32-bit ranks with a fixed trip count
+    r = np.random.Generator(np.random.PCG64(12))
+    N, NUM = 150, 256
+    root = np.unique(r.integers(0, 1 << 63, size=3 * NUM, dtype=np.uint64))
+    rows = np.empty((N, NUM), dtype=np.uint64)
+    for i in range(N):
+        kept = root[r.random(root.size) < 0.8]
+        fresh = r.integers(0, 1 << 63, size=NUM, dtype=np.uint64)
+        rows[i] = np.unique(np.concatenate([kept, fresh]))[:NUM]
+    rows[3] = rows[2]
+    offs = np.arange(N + 1, dtype=np.uint64) * np.uint64(NUM)
+    coll = smb.SketchCollection.from_csr(rows.reshape(-1), offs, N, NUM, 31)
+    other = smb.SketchCollection.from_csr(rows[40:110].reshape(-1), offs[:71], 70, NUM, 31)
+    osk = []
+    for i in range(N):
+        o = orc.KmerMinHash(NUM, 31)
+        o.add_many(rows[i])
+        osk.append(o)
+    oc, osz = orc.compare_matrix(osk, osk, 4)
+    common, size, ratio = smb.compare_matrix(coll, coll, "compare")
+    assert np.array_equal(common, oc) and np.array_equal(size, osz) and np.array_equal(ratio, oc / np.maximum(1, osz))
+    assert common[2, 3] == NUM and (size == NUM).all()
+    # ragged tile edges, a row-sharded block, and two different collections
+    c2, s2, r2 = smb.compare_matrix(coll, coll, "compare", r0=33, nr=70, c0=0, nc=N)
+    assert np.array_equal(c2, oc[33:103])
+    c2, s2, r2 = smb.compare_matrix(coll, other, "compare", r0=5, nr=100, c0=0, nc=70)
+    assert np.array_equal(c2, oc[5:105, 40:110]) and np.array_equal(r2, (oc / np.maximum(1, osz))[5:105, 40:110])
+
+
 def test_unsorted_rows_rejected():  # .sbt.subset fixtures are stored unsorted
     g = golden("subset_scaled.json")
     sk = g["leaves"][0]["sketch"]
