@@ -455,6 +455,17 @@ def bench_compare(args, smb, torch, dist, dev, rank, world, barrier, max_over_ra
     ms = max_over_ranks(e0.elapsed_time(e1)) / steps
     kms, kn = smb.profile_read("compare", reset=True)
     smb.profile_enable(False)
+    # the same matrix with the data-driven path choice overridden: every pair walked (dense kernel)
+    smb.compare_path("dense")
+    step()
+    barrier()
+    e0.record(lib_stream)
+    for _ in range(2):
+        step()
+    e1.record(lib_stream)
+    barrier()
+    ms_dense = max_over_ranks(e0.elapsed_time(e1)) / 2
+    smb.compare_path("auto")
     # end to end: host CSR in, f64 Jaccard matrix out to pinned host memory
     out = torch.empty((r1 - r0, N), dtype=torch.float64, pin_memory=True)
     rows_c = np.ascontiguousarray(rows)
@@ -493,6 +504,9 @@ def bench_compare(args, smb, torch, dist, dev, rank, world, barrier, max_over_ra
             "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(rows_c.nbytes + offsets.nbytes),
                     "d2h_bytes_per_step": int((r1 - r0) * N * 8)},
+            "path": "auto: inverted-index join finds the related pairs (here 1% of all), only those are walked",
+            "dense_path": {"value": pairs / (ms_dense * 1e-3), "unit": "pairs/s", "ms_per_step": ms_dense,
+                           "note": "every pair walked: rank-compressed fixed-length walk, smgpu_compare_path(1)"},
             "operand_bytes_per_pair": 2 * NUM * 8, "parity_checked_64x64": ok}
 
 

@@ -362,19 +362,22 @@ compare_full_kernel(const uint32_t *__restrict__ ra, const uint32_t *__restrict_
     }
     __syncthreads();
     const int cl = (lane + warp) & 31;
-    const uint32_t *a = sA + lane, *b = sB + cl;
-    uint32_t ia = 0, jb = 0;  // element indices, pre-multiplied by 32 (words)
-    uint32_t x = a[0], y = b[0];
-#pragma unroll 4
+    // walk with two shared-memory byte addresses only: per step two compares, two predicated
+    // address bumps, two loads
+    const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(sA + lane), b0 = (uint32_t)__cvta_generic_to_shared(sB + cl);
+    uint32_t pa = a0, pb = b0;
+    uint32_t x, y;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(pa));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(y) : "r"(pb));
+#pragma unroll 8
     for (uint32_t u = 0; u < L; u++) {  // one union element per step
-        const bool adv_a = x <= y, adv_b = y <= x;
-        ia += adv_a ? 32u : 0u;
-        jb += adv_b ? 32u : 0u;
-        x = a[ia];
-        y = b[jb];
+        if (x <= y) pa += 128;
+        if (y <= x) pb += 128;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(pa));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(y) : "r"(pb));
     }
     // every step consumes one element of A, of B, or (when equal) one of each: i + j = L + common
-    const uint32_t c = (ia + jb) / 32 - L;
+    const uint32_t c = ((pa - a0) + (pb - b0)) / 128 - L;
     const uint64_t row = row0 + lane, col = col0 + cl;
     if (row < nr && col < nc) {
         const size_t at = (size_t)row * ld + col;
