@@ -99,6 +99,13 @@ void smgpu_compare_matrix(SketchCollection *rows, uint64_t r0, uint64_t nr, Sket
                           uint64_t nc, int32_t mode, uint32_t *common /*[host|device]*/,
                           uint32_t *size /*[host|device]*/, double *ratio /*[host|device]*/, uint64_t ld,
                           bool out_on_device);
+/* The leaf-pairing pass of `scaffold` (src/index/sbt.rs:356-381): repeatedly take the LAST remaining
+ * row, pair it with the first remaining row that has the strictly largest count_common with it
+ * (the first remaining row when all counts are 0), remove both.  pairs_first[p] / pairs_second[p]
+ * (host, capacity (n + 1) / 2) receive the row ids of pair p in processing order; pairs_second is
+ * UINT64_MAX for an unpaired last row.  Returns the number of pairs.  The N x N count_common
+ * matrix behind it is one smgpu_compare_matrix(mode 1) block. */
+uint64_t smgpu_scaffold_pairs(SketchCollection *c, uint64_t *pairs_first, uint64_t *pairs_second);
 /* How smgpu_compare_matrix / smgpu_linear_find walk a block: 0 (default) decides from the data --
  * an inverted index over the block's hashes finds the pairs that share at least one hash, and
  * only those are walked when the (pair, shared hash) incidences are few against the dense work;

@@ -484,6 +484,37 @@ void orc_count_common_matrix(OrcMinHash *const *rows, size_t nr, OrcMinHash *con
             common[i * nc + j] = (uint32_t)c;
         }
 }
+/* scaffold's leaf-pairing pass (src/index/sbt.rs:356-381): pop the LAST dataset, find among the
+ * remaining ones (in order) the first with the strictly largest count_common (position 0 when all
+ * counts are zero), remove it, pair the two.  pairs_first[p] / pairs_second[p] receive the dataset
+ * ids of pair p in processing order; second = UINT64_MAX for the unpaired last leaf.  Returns the
+ * number of pairs. */
+size_t orc_scaffold_pairs(OrcMinHash *const *leaves, size_t n, uint64_t *pairs_first, uint64_t *pairs_second) {
+    size_t *alive = (size_t *)malloc((n ? n : 1) * sizeof(size_t));
+    size_t n_alive = n, n_pairs = 0;
+    for (size_t i = 0; i < n; i++) alive[i] = i;
+    while (n_alive) {
+        const size_t next = alive[--n_alive];
+        if (n_alive == 0) {
+            pairs_first[n_pairs] = next;
+            pairs_second[n_pairs++] = UINT64_MAX;
+            break;
+        }
+        size_t similar_pos = 0;
+        uint64_t current_max = 0;
+        for (size_t pos = 0; pos < n_alive; pos++) {
+            uint64_t common = 0;
+            orc_mh_count_common(leaves[next], leaves[alive[pos]], &common);
+            if (common > current_max) { current_max = common; similar_pos = pos; }
+        }
+        pairs_first[n_pairs] = next;
+        pairs_second[n_pairs++] = alive[similar_pos];
+        memmove(alive + similar_pos, alive + similar_pos + 1, (n_alive - similar_pos - 1) * sizeof(size_t));
+        n_alive--;
+    }
+    free(alive);
+    return n_pairs;
+}
 /* reads of fixed length laid out back to back; every read is one add_sequence */
 int orc_mh_add_reads(OrcMinHash *mh, const uint8_t *buf, size_t nreads, size_t readlen, int force) {
     for (size_t r = 0; r < nreads; r++) {

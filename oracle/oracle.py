@@ -59,6 +59,7 @@ def lib():
             "orc_linear_find": (sz, [C.POINTER(vp), sz, vp, i, C.c_double, C.POINTER(u64)]),
             "orc_compare_matrix": (None, [C.POINTER(vp), sz, C.POINTER(vp), sz, vp, vp, vp]),
             "orc_count_common_matrix": (None, [C.POINTER(vp), sz, C.POINTER(vp), sz, vp]),
+            "orc_scaffold_pairs": (sz, [C.POINTER(vp), sz, C.POINTER(u64), C.POINTER(u64)]),
             "orc_md5_hex": (None, [C.c_char_p, sz, C.c_char_p]),
             "orc_mh_md5sum": (None, [vp, C.c_char_p]),
             "orc_signature_json": (vp, [C.c_char_p, C.c_char_p, C.POINTER(vp), sz]),
@@ -228,6 +229,14 @@ def linear_find(leaves, query, mode, threshold):
     n = lib().orc_linear_find(_ptr_array(leaves), len(leaves), query._p,
                               1 if mode == "containment" else 0, threshold, hits)
     return [hits[i] for i in range(n)]
+
+
+def scaffold_pairs(leaves):
+    """Leaf-pairing pass of scaffold (sbt.rs:356-381): [(next_leaf, similar_leaf | None)] in processing order."""
+    n = len(leaves)
+    a, b = (C.c_uint64 * max(1, n))(), (C.c_uint64 * max(1, n))()
+    k = lib().orc_scaffold_pairs(_ptr_array(leaves), n, a, b)
+    return [(a[i], None if b[i] == 0xFFFFFFFFFFFFFFFF else b[i]) for i in range(k)]
 
 
 def compare_matrix(rows, cols, nthreads=1):

@@ -98,6 +98,7 @@ EXTENSION_ABI = {
     "smgpu_collection_len": (u64, [vp]),
     "smgpu_collection_csr": (u64, [vp, C.POINTER(vp), C.POINTER(vp)]),
     "smgpu_compare_matrix": (None, [vp, u64, u64, vp, u64, u64, i32, vp, vp, vp, u64, cb]),
+    "smgpu_scaffold_pairs": (u64, [vp, vp, vp]),
     "smgpu_compare_path": (None, [i32]),
     "smgpu_linear_find": (u64, [vp, vp, i32, C.c_double, vp, vp, u64]),
 }
@@ -478,6 +479,14 @@ def compare_matrix_device(rows, cols, mode, r0, nr, c0, nc, common_ptr, size_ptr
     """Same, writing into device memory the caller owns (raw pointers, e.g. torch tensors' data_ptr())."""
     _call("smgpu_compare_matrix", rows._p, r0, nr, cols._p, c0, nc, 1 if mode == "containment" else 0,
           _vp(common_ptr), _vp(size_ptr), _vp(ratio_ptr), ld, True)
+
+
+def scaffold_pairs(coll):
+    """Leaf-pairing pass of scaffold (sbt.rs:356-381): [(next_leaf, similar_leaf | None)] in processing order."""
+    n = len(coll)
+    a, b = np.zeros(max(1, (n + 1) // 2), dtype=np.uint64), np.zeros(max(1, (n + 1) // 2), dtype=np.uint64)
+    k = _call("smgpu_scaffold_pairs", coll._p, _vp(a), _vp(b))
+    return [(int(a[i]), None if b[i] == np.uint64(0xFFFFFFFFFFFFFFFF) else int(b[i])) for i in range(k)]
 
 
 def linear_find(index, queries, mode, threshold, hits_cap=None):

@@ -248,6 +248,46 @@ void compare_matrix(SketchCollection &rows, uint64_t r0, uint64_t nr, SketchColl
     }
 }
 
+// Leaf-pairing pass of scaffold (src/index/sbt.rs:356-381).  The reference runs count_common of the
+// popped leaf against every remaining leaf -- O(N^2) intersections; here the whole count matrix
+// comes from one compare_block_device call and the pass itself is a scan of its rows.
+uint64_t scaffold_pairs(SketchCollection &c, uint64_t *pairs_first, uint64_t *pairs_second) {
+    c.finalize();
+    const uint64_t n = c.n_rows;
+    if (n == 0) return 0;
+    Context &ctx = Context::get();
+    std::vector<uint32_t> common((size_t)n * n);
+    {
+        ctx.misc[5].reserve(n * n * 4 + 256);
+        compare_block_device(c, 0, n, c, 0, n, 1, ctx.misc[5].as<uint32_t>(), nullptr, nullptr, n);
+        SM_CUDA(cudaMemcpyAsync(common.data(), ctx.misc[5].p, n * n * 4, cudaMemcpyDeviceToHost, ctx.stream));
+        ctx.sync();
+    }
+    std::vector<uint64_t> alive(n);
+    for (uint64_t i = 0; i < n; i++) alive[i] = i;
+    uint64_t n_pairs = 0;
+    while (!alive.empty()) {
+        const uint64_t next = alive.back();
+        alive.pop_back();
+        if (alive.empty()) {
+            pairs_first[n_pairs] = next;
+            pairs_second[n_pairs++] = ~0ull;
+            break;
+        }
+        const uint32_t *row = common.data() + (size_t)next * n;
+        size_t similar_pos = 0;
+        uint32_t current_max = 0;
+        for (size_t pos = 0; pos < alive.size(); pos++) {
+            const uint32_t cm = row[alive[pos]];
+            if (cm > current_max) { current_max = cm; similar_pos = pos; }  // strict: the first maximum wins
+        }
+        pairs_first[n_pairs] = next;
+        pairs_second[n_pairs++] = alive[similar_pos];
+        alive.erase(alive.begin() + (std::ptrdiff_t)similar_pos);
+    }
+    return n_pairs;
+}
+
 uint64_t linear_find(SketchCollection &index, SketchCollection &queries, int mode, double threshold, uint64_t *hit_offsets,
                      uint64_t *hits, uint64_t hits_cap) {
     index.check_compatible(queries);

@@ -36,6 +36,7 @@ extern int g_compare_path;
 // see include/sourmash_b200.h
 void compare_matrix(SketchCollection &rows, uint64_t r0, uint64_t nr, SketchCollection &cols, uint64_t c0, uint64_t nc,
                     int mode, uint32_t *common, uint32_t *size, double *ratio, uint64_t ld, bool out_on_device);
+uint64_t scaffold_pairs(SketchCollection &c, uint64_t *pairs_first, uint64_t *pairs_second);
 uint64_t linear_find(SketchCollection &index, SketchCollection &queries, int mode, double threshold,
                      uint64_t *hit_offsets, uint64_t *hits, uint64_t hits_cap);
 

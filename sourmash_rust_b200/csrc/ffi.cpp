@@ -517,6 +517,13 @@ void smgpu_compare_matrix(SketchCollection *rows, uint64_t r0, uint64_t nr, Sket
         smb200::compare_matrix(*coll(rows), r0, nr, *coll(cols), c0, nc, mode, common, size, ratio, ld, out_on_device);
     });
 }
+uint64_t smgpu_scaffold_pairs(SketchCollection *c, uint64_t *pairs_first, uint64_t *pairs_second) {
+    return landingpad<uint64_t>([&]() {
+        nonnull(pairs_first, "pairs_first");
+        nonnull(pairs_second, "pairs_second");
+        return smb200::scaffold_pairs(*coll(c), pairs_first, pairs_second);
+    });
+}
 void smgpu_compare_path(int32_t path) { smb200::g_compare_path = (path == 1 || path == 2) ? path : 0; }
 uint64_t smgpu_linear_find(SketchCollection *index, SketchCollection *queries, int32_t mode, double threshold,
                            uint64_t *hit_offsets, uint64_t *hits, uint64_t hits_cap) {

@@ -515,6 +515,26 @@ def test_compare_mostly_related_full_sketches(compare_path):
     assert np.array_equal(c2, oc[5:105, 40:110]) and np.array_equal(r2, (oc / np.maximum(1, osz))[5:105, 40:110])
 
 
+def test_scaffold_leaf_pairing():  # src/index/sbt.rs:356-381
+    g = golden("sbt_v5_leaves.json")
+    pos = sorted(g["leaves"], key=int)
+    gl = [_load(smb, g["leaves"][p]["sketch"]) for p in pos]
+    ol = [_load(orc, g["leaves"][p]["sketch"]) for p in pos]
+    got = smb.scaffold_pairs(smb.SketchCollection.from_sketches(gl))
+    assert got == orc.scaffold_pairs(ol)
+    assert len(got) == 4 and got[-1][1] is None  # 7 leaves -> 3 pairs + 1 single (scaffold_sbt keeps 7 leaves)
+    # clusters + unrelated sketches + an odd/even count, scaled sketches of different sizes
+    import bench
+    rows = bench.planted_sketches(301, 120, 77)
+    gs, os_ = [], []
+    for i in range(301):
+        a, o = pair(120, 31)
+        a.set_mins(rows[i]); o.add_many(rows[i])
+        gs.append(a); os_.append(o)
+    for n in (301, 300, 2, 1):
+        assert smb.scaffold_pairs(smb.SketchCollection.from_sketches(gs[:n])) == orc.scaffold_pairs(os_[:n])
+
+
 def test_unsorted_rows_rejected():  # .sbt.subset fixtures are stored unsorted
     g = golden("subset_scaled.json")
     sk = g["leaves"][0]["sketch"]

@@ -192,3 +192,15 @@ def test_check_compatible_order():  # lib.rs:176-190
         with pytest.raises(orc.SourmashError) as e:
             a.compare(orc.KmerMinHash(*args))
         assert e.value.code == code
+
+
+def test_scaffold_leaf_pairing():  # src/index/sbt.rs:356-381 over the v5 fixture (scaffold_sbt test, sbt.rs:592-601)
+    g = golden("sbt_v5_leaves.json")
+    pos = sorted(g["leaves"], key=int)
+    leaves = [_load(g["leaves"][p]["sketch"]) for p in pos]
+    pairs = orc.scaffold_pairs(leaves)
+    # every leaf appears exactly once: the reference's scaffold keeps all 7 leaves
+    seen = sorted([a for a, b in pairs] + [b for a, b in pairs if b is not None])
+    assert seen == list(range(7)) and len(pairs) == 4
+    # leaf 12 (last) is popped first and pairs with its nearest neighbour by count_common: leaf 8 (275 > 273)
+    assert [int(pos[a]) for a, b in pairs][0] == 12 and int(pos[pairs[0][1]]) == 8
