@@ -466,9 +466,10 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
         o.counter = mh.hs(0);
         return o;
     };
-    // copy chunks grow 4 -> 32 MiB: the first kernels start after a short copy, later chunks amortise launches
+    // copy chunks grow 4 -> 128 MiB: the first kernels start after a short copy, later chunks amortise
+    // launches (the copy engine outruns the kernels, so a large chunk never stalls them)
     uint64_t chunk = 4ull << 20;
-    const uint64_t CHUNK_MAX = 32ull << 20;
+    const uint64_t CHUNK_MAX = 128ull << 20;
     uint64_t copied = batch.on_device ? n : 0;
     if (!batch.on_device) SM_CUDA(cudaStreamSynchronize(st));  // scalars / offsets in place before the copy stream races ahead
     size_t ev_i = 0;
