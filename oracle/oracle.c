@@ -302,12 +302,31 @@ static uint8_t *revcomp_alloc(const uint8_t *s, size_t n) {
     return rc;
 }
 
-/* lib.rs:252-305 (DNA arm).  On an invalid k-mer with !force returns
- * ORC_INVALID_DNA and copies the offending (uppercased) k-mer into badkmer
- * (ksize bytes + NUL) -- k-mers before it stay added (partial mutation).
- * The protein arm (lib.rs:275-302) is out of the hot-path scope. */
+/* CODONTABLE (lib.rs:691-763): the standard genetic code, stops as '*'; anything that is not three
+ * upper-case ACGT letters has no entry */
+static int codon_code(uint8_t c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
+static uint8_t codon_lookup(const uint8_t *c3) {
+    static const char table[65] = "KNKNTTTTRSRSIIMIQHQHPPPPRRRRLLLLEDEDAAAAGGGGVVVV*Y*YSSSS*CWCLFLF"; /* index 16a+4b+c, A0 C1 G2 T3 */
+    const int a = codon_code(c3[0]), b = codon_code(c3[1]), c = codon_code(c3[2]);
+    if (a < 0 || b < 0 || c < 0) return 0;
+    return (uint8_t)table[16 * a + 4 * b + c];
+}
+/* to_aa (lib.rs:776-793): chunks of 3, an incomplete last chunk ends it, unknown codons are skipped */
+static size_t to_aa(const uint8_t *s, size_t n, uint8_t *out) {
+    size_t m = 0;
+    for (size_t i = 0; i + 3 <= n; i += 3) {
+        const uint8_t aa = codon_lookup(s + i);
+        if (aa) out[m++] = aa;
+    }
+    return m;
+}
+
+/* lib.rs:252-305.  DNA arm: on an invalid k-mer with !force returns ORC_INVALID_DNA and copies the
+ * offending (uppercased) k-mer into badkmer (ksize bytes + NUL) -- k-mers before it stay added
+ * (partial mutation).  Protein arm (lib.rs:275-302): the three forward frames and the three frames
+ * of the reverse complement are translated and every window of ksize/3 residues is hashed; no
+ * validity check, `force` is not consulted. */
 int orc_mh_add_sequence(OrcMinHash *mh, const uint8_t *seq, size_t len, int force, char *badkmer) {
-    if (mh->is_protein) return ORC_UNSUPPORTED;
     uint8_t *sequence = (uint8_t *)malloc(len ? len : 1);
     for (size_t i = 0; i < len; i++) {
         uint8_t c = seq[i];
@@ -315,6 +334,25 @@ int orc_mh_add_sequence(OrcMinHash *mh, const uint8_t *seq, size_t len, int forc
     }
     int rc_code = ORC_OK;
     size_t k = mh->ksize;
+    if (mh->is_protein) {
+        if (len >= k) {
+            const size_t aa_k = k / 3;
+            if (aa_k == 0) { free(sequence); return ORC_UNSUPPORTED; } /* slice::windows(0) panics */
+            uint8_t *rc = revcomp_alloc(sequence, len);
+            uint8_t *aa = (uint8_t *)malloc(len / 3 + 1);
+            for (size_t i = 0; i < 3; i++) {
+                const size_t sub = len >= i ? len - i : 0;
+                size_t m = to_aa(sequence + (len >= i ? i : len), sub, aa);
+                for (size_t w = 0; w + aa_k <= m; w++) orc_mh_add_word(mh, aa + w, aa_k);
+                m = to_aa(rc + (len >= i ? i : len), sub, aa);
+                for (size_t w = 0; w + aa_k <= m; w++) orc_mh_add_word(mh, aa + w, aa_k);
+            }
+            free(aa);
+            free(rc);
+        }
+        free(sequence);
+        return ORC_OK;
+    }
     if (len >= k && k > 0) {
         for (size_t i = 0; i + k <= len; i++) {
             const uint8_t *kmer = sequence + i;

@@ -45,6 +45,21 @@ void launch_sketch(uint32_t K, const SketchBatch &sb, const SketchOut &out, uint
                    cudaStream_t st);
 bool sketch_has_fast_path(uint32_t K);
 
+// ---- protein.cu: 6-frame translated sketching (reference src/lib.rs:275-302) --------------------
+struct ProteinBatch {
+    const uint8_t *buf;
+    uint64_t n;
+    const uint64_t *offsets;
+    uint64_t n_seqs;
+    uint32_t read_len;
+    uint32_t ksize;
+    uint64_t seed;
+};
+uint64_t protein_slots(uint64_t n_bytes, uint64_t n_seqs);
+// aa, comp: protein_slots + 1 bytes; flags, pre: protein_slots + 1 u64; scan_tmp: scan_tmp_bytes(protein_slots + 1)
+void launch_protein_sketch(const ProteinBatch &pb, const SketchOut &out, uint8_t *aa, uint8_t *comp, uint64_t *flags,
+                           uint64_t *pre, void *scan_tmp, cudaStream_t st);
+
 // ---- sortops.cu -------------------------------------------------------------------------
 // keep[i] = hashes[i] passing the state-independent gate (h <= max_hash || max_hash == 0) and
 // h <= *thr; compacted (order NOT preserved) into out via *counter.

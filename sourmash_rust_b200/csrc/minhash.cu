@@ -388,9 +388,9 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
     if (n_mhs <= 0) return;
     if (n_mhs > 6) throw_internal("at most 6 sketches per batch call");
     for (int i = 0; i < n_mhs; i++) {
-        if (mhs[i]->is_protein)
-            throw_internal("protein (6-frame translated) sketching is outside the GPU hot path of this build");
         if (mhs[i]->ksize == 0) throw_internal("ksize 0");
+        if (mhs[i]->is_protein && mhs[i]->ksize < 3)  // the reference reaches slice::windows(0), which panics
+            throw SourmashError(ERR_PANIC, "sourmash panicked: size is zero");
     }
     const uint64_t n = batch.n_bytes;
     if (n == 0) return;
@@ -401,9 +401,10 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
 
     // ---- per-sketch preparation: order-dependent work first, thresholds, candidate space -------
     std::vector<PerSketch> ps(n_mhs);
-    uint64_t windows_upper = n;
     for (int i = 0; i < n_mhs; i++) {
         KmerMinHash &mh = *mhs[i];
+        // hashes this call can produce at most: one per base (DNA) / per codon slot of the six frames
+        const uint64_t windows_upper = mh.is_protein ? protein_slots(n, batch.n_seqs) : n;
         mh.flush_pending();
         if (mh.mode() != MODE_SCALED && mh.n_cand_) mh.ingest(ctx, false);
         mh.ensure_dev();
@@ -457,6 +458,26 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
         sb.first_bad = force ? nullptr : mh.hs(2);
         return sb;
     };
+    // protein sketches: translate / compact / hash over the whole device-resident batch (protein.cu)
+    auto launch_protein = [&](KmerMinHash &mh) {
+        const uint64_t total = protein_slots(n, batch.n_seqs);
+        ctx.misc[0].reserve(total + 64);
+        ctx.misc[1].reserve(total + 64);
+        ctx.misc[2].reserve((total + 2) * 8);
+        ctx.misc[3].reserve((total + 2) * 8);
+        ctx.scan_tmp.reserve(scan_tmp_bytes(total + 1) + 256);
+        ProteinBatch pb;
+        pb.buf = d_buf; pb.n = n; pb.offsets = d_off; pb.n_seqs = batch.n_seqs;
+        pb.read_len = batch.offsets ? 0 : batch.read_len; pb.ksize = mh.ksize; pb.seed = mh.seed;
+        SketchOut o;
+        o.thr = reinterpret_cast<const uint64_t *>(mh.hs(1));
+        o.hash = mh.d_cand_hash_.as<uint64_t>();
+        o.pos = mh.want_pos() ? mh.d_cand_pos_.as<uint64_t>() : nullptr;
+        o.cap = mh.d_cand_hash_.cap / 8;
+        o.counter = mh.hs(0);
+        launch_protein_sketch(pb, o, ctx.misc[0].as<uint8_t>(), ctx.misc[1].as<uint8_t>(), ctx.misc[2].as<uint64_t>(),
+                              ctx.misc[3].as<uint64_t>(), ctx.scan_tmp.p, st);
+    };
     auto make_out = [&](KmerMinHash &mh) {
         SketchOut o;
         o.thr = reinterpret_cast<const uint64_t *>(mh.hs(1));
@@ -492,12 +513,15 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
         for (int i = 0; i < n_mhs; i++) {
             KmerMinHash &mh = *mhs[i];
             PerSketch &p = ps[i];
+            if (mh.is_protein) continue;  // after the whole batch has arrived
             uint32_t hi = (copied >= n) ? p.tiles_total : std::min(p.tiles_total, sketch_tiles_ready(mh.ksize, copied));
             if (hi <= p.tile_lo) continue;
             launch_sketch(mh.ksize, make_batch(mh, n, p.tile_lo), make_out(mh), hi, ctx.sm_count, st);
             p.tile_lo = hi;
         }
     } while (copied < n);
+    for (int i = 0; i < n_mhs; i++)
+        if (mhs[i]->is_protein) launch_protein(*mhs[i]);
 
     // ---- results: overflow / first failing k-mer / estimate too tight -> re-run from the device copy
     std::string error_kmer;
@@ -549,7 +573,8 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
                 // estimate kept too few distinct hashes: widen and go again
                 p.thr_fallback = (p.thr_fallback > (U64_MAX >> 6)) ? U64_MAX : (p.thr_fallback << 6);
                 if (p.thr_fallback == U64_MAX) p.estimate = false;
-                mh.reserve_candidates(ctx, (uint64_t)((double)p.thr_fallback / 18446744073709551616.0 * 1.25 * (double)n) + 65536);
+                mh.reserve_candidates(ctx, (uint64_t)((double)p.thr_fallback / 18446744073709551616.0 * 1.25 *
+                                                      (double)(mh.is_protein ? protein_slots(n, batch.n_seqs) : n)) + 65536);
             }
             if (attempt > 40) throw_internal("sketch re-run loop did not converge");
             // re-run over the device-resident batch
@@ -558,9 +583,13 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
             thr_from_state_kernel<<<1, 1, 0, st>>>(mh.hs(1), mh.d_mins_.as<uint64_t>(), mh.n_mins_,
                                                    mh.mode() == MODE_NUM ? mh.num : 0, p.thr_fallback);
             SM_LAUNCHED();
-            SketchBatch sb = make_batch(mh, n_limit, 0);
-            sb.first_bad = nullptr;
-            launch_sketch(mh.ksize, sb, make_out(mh), sketch_tile_count(n, n_limit), ctx.sm_count, st);
+            if (mh.is_protein) {
+                launch_protein(mh);
+            } else {
+                SketchBatch sb = make_batch(mh, n_limit, 0);
+                sb.first_bad = nullptr;
+                launch_sketch(mh.ksize, sb, make_out(mh), sketch_tile_count(n, n_limit), ctx.sm_count, st);
+            }
         }
         if (p.first_bad != U64_MAX && error_sketch < 0) {
             error_sketch = i;

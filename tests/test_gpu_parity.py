@@ -214,6 +214,55 @@ def test_short_and_edge_sequences():
 
 
 # ------------------------------------------------------------------------------------------------
+# protein sketches: 6-frame translation (lib.rs:275-302), SURVEY 8(f) rank 4
+# ------------------------------------------------------------------------------------------------
+def ppair(num, k, max_hash=0, abund=False):
+    return smb.KmerMinHash(num, k, True, 42, max_hash, abund), orc.KmerMinHash(num, k, True, 42, max_hash, abund)
+
+
+@pytest.mark.parametrize("k", [21, 30, 57, 3, 4, 10])
+@pytest.mark.parametrize("kind", ["num", "scaled_abund", "num_abund"])
+def test_protein_add_sequence_parity(k, kind):
+    seq = dirty(random_dna(30011, 0x700 + k), 5 + k, n_bad=40)
+    num = 300 if kind.startswith("num") else 0
+    mx = 0 if kind.startswith("num") else MAX_HASH_1000 * 100
+    g, o = ppair(num, k, mx, kind.endswith("abund"))
+    g.add_sequence(seq, False); o.add_sequence(seq, False)  # no validity check in the protein arm
+    same(g, o)
+    g.add_sequence(seq[:5000], True); o.add_sequence(seq[:5000], True)
+    same(g, o)
+    for short in (b"", b"AC", b"ACG", b"ACGTACGTAC"[: k - 1], b"ACGTNNACGTACGATCGATCGACTGACTAGCTAGCTAGCATCGAT"):
+        g.add_sequence(short, True); o.add_sequence(short, True)
+    same(g, o)
+
+
+def test_protein_batches_and_mixed_sketches():
+    genome = random_dna(50_000, 0x5EED0010)
+    n_reads = 900
+    reads = make_reads(genome, n_reads, 150, 0x5EED0011)
+    gp, op = ppair(0, 21, MAX_HASH_1000 * 50, True)
+    gd, od = pair(0, 21, MAX_HASH_1000 * 50, True)
+    smb.add_reads([gd, gp], reads, n_reads, 150)  # a DNA and a protein sketch from the same pass
+    od.add_reads(reads, n_reads, 150); op.add_reads(reads, n_reads, 150)
+    same(gp, op); same(gd, od)
+    lens = [0, 2, 20, 21, 22, 23, 24, 300, 7, 1000, 0, 64]
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    buf = dirty(random_dna(int(offsets[-1]), 3), 4, n_bad=5)
+    g, o = ppair(50, 21, 0, True)
+    g.add_sequences(buf, offsets)
+    for i in range(len(lens)):
+        o.add_sequence(buf[int(offsets[i]):int(offsets[i + 1])], True)
+    same(g, o)
+    with pytest.raises(smb.SourmashError) as e:  # ksize < 3: the reference panics in slice::windows(0)
+        smb.KmerMinHash(10, 2, True).add_sequence(b"ACGTACGT")
+    assert e.value.code == 1
+    # protein and DNA sketches do not compare (lib.rs:179-181)
+    with pytest.raises(smb.SourmashError) as e:
+        gp.compare(gd)
+    assert e.value.code == 102
+
+
+# ------------------------------------------------------------------------------------------------
 # batches: reads and ragged sequences, several sketches per pass
 # ------------------------------------------------------------------------------------------------
 def test_add_reads_multi_k():  # BASELINE config 2 shape, reduced
