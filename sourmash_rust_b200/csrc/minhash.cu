@@ -276,6 +276,14 @@ void KmerMinHash::flush_pending() {
 void KmerMinHash::flush() {
     flush_pending();
     if (n_cand_) ingest(Context::get(), false);
+    // Many sketches may be alive at once (10^4..10^6): scratch that dwarfs the sketch itself goes back
+    // to the stream-ordered pool (the next batch gets it again in microseconds); scratch of the same
+    // order as the state stays, so a sketch that is read between batches does not churn.
+    const size_t keep = 16 * std::max<size_t>((n_mins_ + n_abunds_) * 8, 16 * 1024);
+    if (d_cand_hash_.cap > keep) d_cand_hash_.release();
+    if (d_cand_pos_.cap > keep) d_cand_pos_.release();
+    if (d_mins_alt_.cap > keep) d_mins_alt_.release();
+    if (d_abunds_alt_.cap > keep) d_abunds_alt_.release();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -427,7 +435,7 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
             p.thr_fallback = mh.max_hash;
             frac = (double)mh.max_hash / 18446744073709551616.0;
         }
-        mh.reserve_candidates(ctx, mh.n_cand_ + (uint64_t)(frac * 1.25 * (double)windows_upper) + 65536);
+        mh.reserve_candidates(ctx, mh.n_cand_ + (uint64_t)(frac * 1.25 * (double)windows_upper) + 4096);
         set_u64(mh.hs(0), mh.n_cand_, st);
         set_u64(mh.hs(2), U64_MAX, st);
         thr_from_state_kernel<<<1, 1, 0, st>>>(mh.hs(1), mh.d_mins_.as<uint64_t>(), mh.n_mins_,
@@ -487,10 +495,11 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
         o.counter = mh.hs(0);
         return o;
     };
-    // copy chunks grow 4 -> 128 MiB: the first kernels start after a short copy, later chunks amortise
-    // launches (the copy engine outruns the kernels, so a large chunk never stalls them)
+    // copy chunks grow 4 -> 32 MiB: the first kernels start after a short copy, later chunks amortise
+    // launches.  (Larger caps were measured slower: while the chunk size doubles, the copy of chunk
+    // c+1 takes longer than the kernels of chunk c, and the kernels starve.)
     uint64_t chunk = 4ull << 20;
-    const uint64_t CHUNK_MAX = 128ull << 20;
+    const uint64_t CHUNK_MAX = 32ull << 20;
     uint64_t copied = batch.on_device ? n : 0;
     if (!batch.on_device) SM_CUDA(cudaStreamSynchronize(st));  // scalars / offsets in place before the copy stream races ahead
     size_t ev_i = 0;
@@ -543,7 +552,7 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
             }
             if (count > mh.d_cand_hash_.cap / 8) {
                 mh.n_cand_ = p.prev_cand;
-                mh.reserve_candidates(ctx, count + 65536);
+                mh.reserve_candidates(ctx, count + 4096);
                 rerun = true;
             }
             if (!rerun) {
@@ -574,7 +583,7 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
                 p.thr_fallback = (p.thr_fallback > (U64_MAX >> 6)) ? U64_MAX : (p.thr_fallback << 6);
                 if (p.thr_fallback == U64_MAX) p.estimate = false;
                 mh.reserve_candidates(ctx, (uint64_t)((double)p.thr_fallback / 18446744073709551616.0 * 1.25 *
-                                                      (double)(mh.is_protein ? protein_slots(n, batch.n_seqs) : n)) + 65536);
+                                                      (double)(mh.is_protein ? protein_slots(n, batch.n_seqs) : n)) + 4096);
             }
             if (attempt > 40) throw_internal("sketch re-run loop did not converge");
             // re-run over the device-resident batch

@@ -106,12 +106,11 @@ class KmerMinHash {
     Mode mode() const;
     bool want_pos() const { return mode() == MODE_REPLAY || (mode() == MODE_NUM && has_abunds_); }
     unsigned long long *hs(int i);
-    void flush();          // pending_ + candidates -> canonical device state
+    void flush();          // pending_ + candidates -> canonical device state; gives scratch back to the pool
     void flush_pending();
     void ensure_dev();
     void ensure_host();
     void require_sorted(const char *what);
-    uint64_t threshold_now(uint64_t n_events, bool *is_estimate);
     void reserve_candidates(Context &ctx, uint64_t extra);
     bool ingest(Context &ctx, bool thr_is_estimate);
     void replay(Context &ctx, const uint64_t *d_events, uint64_t n_events);

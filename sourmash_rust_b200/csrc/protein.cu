@@ -19,12 +19,6 @@ __device__ __forceinline__ void pr_seq(const ProteinBatch &pb, uint64_t s, uint6
     else if (pb.read_len) { begin = s * (uint64_t)pb.read_len; len = pb.read_len; }
     else { begin = 0; len = pb.n; }
 }
-__device__ __forceinline__ uint64_t pr_region(const ProteinBatch &pb, uint64_t s) {
-    uint64_t begin, len;
-    if (s >= pb.n_seqs) return 2 * pb.n + 6 * pb.n_seqs;
-    pr_seq(pb, s, begin, len);
-    return 2 * begin + 6 * s;
-}
 // sequence owning slot t
 __device__ __forceinline__ uint64_t pr_find(const ProteinBatch &pb, uint64_t t) {
     if (!pb.offsets) return pb.read_len ? t / (2ull * pb.read_len + 6) : 0;
