@@ -85,6 +85,11 @@ Context &Context::get() {
     }
     SM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SM_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 6; i++) {
+        SM_CUDA(cudaStreamCreateWithFlags(&c->k_streams[i], cudaStreamNonBlocking));
+        SM_CUDA(cudaEventCreateWithFlags(&c->k_events[i], cudaEventDisableTiming));
+    }
+    SM_CUDA(cudaEventCreateWithFlags(&c->prep_event, cudaEventDisableTiming));
     c->own_stream = true;
     {
         // Reserve the pool's working set once (default 4 GiB of the 180 GB, SMB200_POOL_PREWARM_MB to
@@ -139,6 +144,7 @@ ProfScope::~ProfScope() {
     g_prof.pending[kind].emplace_back(e0, e1);
 }
 void prof_enable(bool on) { g_prof.enabled = on; }
+bool prof_enabled() { return g_prof.enabled; }
 void prof_read(int kind, double *ms, uint64_t *launches, bool reset) {
     if (kind < 0 || kind >= PROF_KINDS) throw_internal("bad profile kind");
     for (auto &pr : g_prof.pending[kind]) {

@@ -97,6 +97,9 @@ struct Context {
     std::vector<cudaEvent_t> chunk_events;
 
     cudaStream_t copy_stream = nullptr;  // host->device staging, overlapped with `stream`
+    cudaStream_t k_streams[6] = {nullptr};  // one per sketch of a batch call: their kernels fill each other's tails
+    cudaEvent_t k_events[6] = {nullptr};
+    cudaEvent_t prep_event = nullptr;
 
     static Context &get();      // creates on first use; throws if no CUDA device
     static Context *peek();     // nullptr before first use
@@ -117,6 +120,7 @@ struct ProfScope {
     ~ProfScope();
 };
 void prof_enable(bool on);
+bool prof_enabled();
 void prof_read(int kind, double *ms, uint64_t *launches, bool reset);  // synchronises the recorded events
 // which device the context binds to when it is created (default: the thread's current device)
 void set_requested_device(int dev);

@@ -502,6 +502,16 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
     const uint64_t CHUNK_MAX = 32ull << 20;
     uint64_t copied = batch.on_device ? n : 0;
     if (!batch.on_device) SM_CUDA(cudaStreamSynchronize(st));  // scalars / offsets in place before the copy stream races ahead
+    // every sketch's kernels go to its own stream, ordered after the preparation above and after
+    // the chunk they read: the three k-sizes of a multi-k batch then overlap at their edges
+    // (with per-kernel timing switched on they stay on one stream, so that each duration is the
+    // kernel's own)
+    const bool fan_out = !prof_enabled() && n_mhs > 1;
+    auto kstream = [&](int i) { return fan_out ? ctx.k_streams[i] : st; };
+    if (fan_out) {
+        SM_CUDA(cudaEventRecord(ctx.prep_event, st));
+        for (int i = 0; i < n_mhs; i++) SM_CUDA(cudaStreamWaitEvent(ctx.k_streams[i], ctx.prep_event, 0));
+    }
     size_t ev_i = 0;
     do {
         if (!batch.on_device) {
@@ -516,7 +526,11 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
                 ctx.chunk_events.push_back(e);
             }
             SM_CUDA(cudaEventRecord(ctx.chunk_events[ev_i], ctx.copy_stream));
-            SM_CUDA(cudaStreamWaitEvent(st, ctx.chunk_events[ev_i], 0));
+            if (fan_out) {
+                for (int i = 0; i < n_mhs; i++) SM_CUDA(cudaStreamWaitEvent(ctx.k_streams[i], ctx.chunk_events[ev_i], 0));
+            } else {
+                SM_CUDA(cudaStreamWaitEvent(st, ctx.chunk_events[ev_i], 0));
+            }
             ev_i++;
         }
         for (int i = 0; i < n_mhs; i++) {
@@ -525,10 +539,14 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
             if (mh.is_protein) continue;  // after the whole batch has arrived
             uint32_t hi = (copied >= n) ? p.tiles_total : std::min(p.tiles_total, sketch_tiles_ready(mh.ksize, copied));
             if (hi <= p.tile_lo) continue;
-            launch_sketch(mh.ksize, make_batch(mh, n, p.tile_lo), make_out(mh), hi, ctx.sm_count, st);
+            launch_sketch(mh.ksize, make_batch(mh, n, p.tile_lo), make_out(mh), hi, ctx.sm_count, kstream(i));
             p.tile_lo = hi;
         }
     } while (copied < n);
+    for (int i = 0; fan_out && i < n_mhs; i++) {  // back onto the library's stream
+        SM_CUDA(cudaEventRecord(ctx.k_events[i], ctx.k_streams[i]));
+        SM_CUDA(cudaStreamWaitEvent(st, ctx.k_events[i], 0));
+    }
     for (int i = 0; i < n_mhs; i++)
         if (mhs[i]->is_protein) launch_protein(*mhs[i]);
 
