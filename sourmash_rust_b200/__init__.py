@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsourmash.so")
+LIB_PATH = os.environ.get("SMB200_LIB") or os.path.join(_HERE, "libsourmash.so")  # override: kernel A/B runs
 
 u64, u32, i32, usz, vp, cb = C.c_uint64, C.c_uint32, C.c_int32, C.c_size_t, C.c_void_p, C.c_bool
 p_u64 = C.POINTER(C.c_uint64)

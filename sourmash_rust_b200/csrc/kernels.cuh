@@ -7,9 +7,18 @@
 namespace smb200 {
 
 // ---- sketch.cu --------------------------------------------------------------------------
-constexpr int SK_TILE = 4096;        // window starts per tile
-constexpr int SK_THREADS = 256;      // 8 windows per thread per tile
-constexpr int SK_CTAS_PER_SM = 8;    // resident persistent CTAs per SM
+#ifndef SK_TILE_V          // overridable for kernel A/B builds (tests/manual/build_variant.py)
+#define SK_TILE_V 4096
+#endif
+#ifndef SK_THREADS_V
+#define SK_THREADS_V 256
+#endif
+#ifndef SK_CTAS_V
+#define SK_CTAS_V 8
+#endif
+constexpr int SK_TILE = SK_TILE_V;          // window starts per tile
+constexpr int SK_THREADS = SK_THREADS_V;    // SK_TILE / SK_THREADS windows per thread per tile
+constexpr int SK_CTAS_PER_SM = SK_CTAS_V;   // resident persistent CTAs per SM
 constexpr int SK_MAX_GENERIC_K = 8192;
 
 // A batch of sequences resident in device memory as one ASCII buffer.
@@ -28,6 +37,8 @@ struct SketchBatch {
     uint64_t seed;
     uint64_t pos_base;                  // added to the window start in out.pos / first_bad
     unsigned long long *first_bad;      // nullable: atomicMin of the first window add_sequence fails on
+    uint32_t *tile_ctr;                 // two zeroed words: dynamic tile counter + finished-CTA counter (the last
+                                        // CTA of a launch zeroes both again); launches sharing it must be ordered
 };
 // Survivors (hash <= *thr) are appended through *counter; entries beyond cap are dropped but
 // still counted, so the host can detect the overflow and re-run with a larger buffer.

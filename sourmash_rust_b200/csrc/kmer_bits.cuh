@@ -136,6 +136,20 @@ KB_HD void extract2(const uint32_t *stream, int start, uint32_t (&e)[KmerGeom<K>
     e[KmerGeom<K>::NE - 1] &= KmerGeom<K>::TOP2;
 }
 
+// same as extract2 with the word pointer and the bit shift already split (the kernel keeps both
+// loop-invariant per thread); only the low 5 bits of `s` are used (funnel shift wraps)
+template <int K>
+KB_HD void extract2w(const uint32_t *w, uint32_t s, uint32_t (&e)[KmerGeom<K>::NE]) {
+    uint32_t prev = w[0];
+#pragma unroll
+    for (int j = 0; j < KmerGeom<K>::NE; j++) {
+        const uint32_t next = w[j + 1];
+        e[j] = kb_funnel_r(prev, next, s);
+        prev = next;
+    }
+    e[KmerGeom<K>::NE - 1] &= KmerGeom<K>::TOP2;
+}
+
 // lexicographic `fw < rc` (src/lib.rs:263) from the little-endian 2-bit integers of the two
 // strands: with comp(c) = ~c, BE(fw) = ~E(rc) and BE(rc) = ~E(fw), so fw <lex rc <=> E(fw) < E(rc).
 template <int K>
@@ -163,6 +177,19 @@ KB_HD void extractA(const uint32_t *words, int start, uint32_t (&kw)[KmerGeom<K>
 #pragma unroll
     for (int j = 0; j < KmerGeom<K>::NW; j++) {
         const uint32_t next = words[w + j + 1];
+        kw[j] = kb_funnel_r(prev, next, s);
+        prev = next;
+    }
+    kw[KmerGeom<K>::NW - 1] &= KmerGeom<K>::TOPA;
+}
+
+// same with the word pointer and the bit shift (low 5 bits used) already split
+template <int K>
+KB_HD void extractAw(const uint32_t *w, uint32_t s, uint32_t (&kw)[KmerGeom<K>::NW]) {
+    uint32_t prev = w[0];
+#pragma unroll
+    for (int j = 0; j < KmerGeom<K>::NW; j++) {
+        const uint32_t next = w[j + 1];
         kw[j] = kb_funnel_r(prev, next, s);
         prev = next;
     }

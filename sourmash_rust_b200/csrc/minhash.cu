@@ -464,6 +464,7 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
         sb.buf = d_buf; sb.n = n; sb.n_limit = n_limit; sb.offsets = d_off; sb.n_seqs = batch.n_seqs;
         sb.read_len = batch.offsets ? 0 : batch.read_len; sb.tile_lo = tile_lo; sb.seed = mh.seed; sb.pos_base = 0;
         sb.first_bad = force ? nullptr : mh.hs(2);
+        sb.tile_ctr = reinterpret_cast<uint32_t *>(mh.hs(3));  // this sketch's launches are stream-ordered
         return sb;
     };
     // protein sketches: translate / compact / hash over the whole device-resident batch (protein.cu)

@@ -81,12 +81,24 @@ SM_HD uint64_t mm_rotl64(uint64_t x) {
 #endif
 }
 
+// k ^ (k >> 33): only the low word changes, by hi >> 1.  On the device the shift is spelled as the
+// high half of hi * 2^31 (IMAD.HI, FMA pipe) because the kernel's busiest pipe is the ALU one.
+SM_HD uint64_t mm_xorshift33(uint64_t k) {
+#if defined(__CUDA_ARCH__)
+    uint32_t lo = (uint32_t)k, hi = (uint32_t)(k >> 32), t;
+    asm("mul.hi.u32 %0, %1, 0x80000000;" : "=r"(t) : "r"(hi));
+    lo ^= t;
+    return ((uint64_t)hi << 32) | lo;
+#else
+    return k ^ (k >> 33);
+#endif
+}
 SM_HD uint64_t mm_fmix64(uint64_t k) {
-    k ^= k >> 33;
+    k = mm_xorshift33(k);
     k = mm_mulc<0xff51afd7ed558ccdULL>(k);
-    k ^= k >> 33;
+    k = mm_xorshift33(k);
     k = mm_mulc<0xc4ceb9fe1a85ec53ULL>(k);
-    k ^= k >> 33;
+    k = mm_xorshift33(k);
     return k;
 }
 

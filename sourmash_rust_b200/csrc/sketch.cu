@@ -30,6 +30,13 @@
 
 namespace smb200 {
 
+#ifndef SK_UNROLL
+#define SK_UNROLL 2   // windows per trip of the k-mer loop (SK_TILE / SK_THREADS must be a multiple)
+#endif
+#ifndef SK_MIN_CTAS
+#define SK_MIN_CTAS SK_CTAS_PER_SM
+#endif
+
 // ---------------------------------------------------------------------------------------
 // mbarrier / TMA bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP)
 // ---------------------------------------------------------------------------------------
@@ -233,7 +240,7 @@ __device__ __forceinline__ void append_survivor(bool pass, uint64_t h, uint64_t 
 // fast path: compile-time K
 // ---------------------------------------------------------------------------------------
 template <int K>
-__global__ void __launch_bounds__(SK_THREADS) sketch_kernel(const SketchBatch sb, const SketchOut out,
+__global__ void __launch_bounds__(SK_THREADS, SK_MIN_CTAS) sketch_kernel(const SketchBatch sb, const SketchOut out,
                                                             uint32_t n_tiles) {
     constexpr int B = tile_bases(K);
     using G = KmerGeom<K>;
@@ -243,7 +250,29 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(const SketchBatch sb
     const int tid = threadIdx.x, lane = tid & 31;
     const uint64_t thr = *out.thr;
 
-    if (tid == 0) mbar_init(&s_bar, 1);
+    // per-thread constants of the k-mer loop (window i = r * SK_THREADS + tid):
+    //   2-bit views: word (i >> 4), bit shift 2 * (i & 15); ASCII views: word (i >> 2), bit shift
+    //   8 * (i & 3); rc(window i) starts at base B - K - i of the reverse-complement views, and rA
+    //   sits (B + 8) bytes after fA (carve_tile), so one base pointer serves both ASCII strands.
+    //   SK_THREADS is a multiple of 16, so the r-dependence is a pure word offset.
+    static_assert(SK_THREADS % 32 == 0, "k-mer loop addressing");
+    const int ri0 = B - K - tid, ra0 = B + 8 + ri0;
+    const uint32_t *const pf2 = v.f2 + (tid >> 4), *const pr2 = v.r2 + (ri0 >> 4);
+    const uint32_t *const pfa = v.fA + (tid >> 2), *const pra = v.fA + (ra0 >> 2);
+    const uint32_t sf2 = (uint32_t)tid * 2u, sr2 = (uint32_t)ri0 * 2u;  // funnel shifts use the low 5 bits
+    const uint32_t sfa = (uint32_t)tid * 8u, sra = (uint32_t)ra0 * 8u;
+    const uint32_t *const psb = v.sbad + (tid >> 5);
+    const uint32_t mb = 1u << lane;
+
+    // Tiles are handed out dynamically: a CTA's first tile is its block index, every further one
+    // comes from an atomic counter.  (With a static round-robin the warp scheduler's fixed priority
+    // lets some CTAs run ahead and retire early; the SM then finishes the launch with a third of
+    // its warp slots empty -- ncu showed 10.5 of 16 warps per scheduler on average.)
+    __shared__ uint32_t s_next;
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        s_next = sb.tile_lo + gridDim.x + atomicAdd(sb.tile_ctr, 1u);
+    }
     __syncthreads();
     uint32_t tile = sb.tile_lo + blockIdx.x;
     uint32_t parity = 0;
@@ -253,41 +282,64 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(const SketchBatch sb
         mbar_expect_tx(&s_bar, bytes);
         if (bytes) tma_load_1d(v.raw, sb.buf + t0, bytes, &s_bar);
     }
-    for (; tile < n_tiles; tile += gridDim.x) {
+    while (tile < n_tiles) {
         const uint64_t t0 = (uint64_t)tile * SK_TILE;
+        const uint32_t next = s_next;  // written before the last barrier of the previous trip
+        uint32_t after_next = 0;
         mbar_wait(&s_bar, parity);
         parity ^= 1u;
         build_views(v, B, t0, sb);
         __syncthreads();  // raw consumed, views + zeroed end bitmap visible
-        {
-            const uint32_t next = tile + gridDim.x;
-            if (tid == 0 && next < n_tiles) {  // prefetch: overlaps everything below
+        if (tid == 0) {
+            if (next < n_tiles) {  // prefetch: overlaps everything below
                 const uint64_t n0 = (uint64_t)next * SK_TILE;
                 const uint32_t bytes = tile_copy_bytes(n0, sb.n, B);
                 mbar_expect_tx(&s_bar, bytes);
                 if (bytes) tma_load_1d(v.raw, sb.buf + n0, bytes, &s_bar);
+                after_next = sb.tile_lo + gridDim.x + atomicAdd(sb.tile_ctr, 1u);  // needed one trip from now
+            } else {
+                after_next = next;
             }
         }
         mark_sequence_ends(v, B, t0, sb);
         __syncthreads();
         build_start_bitmap(v, K, t0, sb);
         __syncthreads();
-#pragma unroll 2
-        for (int r = 0; r < SK_TILE / SK_THREADS; r++) {
-            const int i = r * SK_THREADS + tid;  // window start inside the tile
-            const bool valid = ((v.sbad[i >> 5] >> (i & 31)) & 1u) == 0;
-            uint32_t ef[G::NE], er[G::NE];
-            extract2<K>(v.f2, i, ef);
-            const int ri = B - K - i;  // start of rc(window i) in the reverse-complement views
-            extract2<K>(v.r2, ri, er);
-            const bool use_fw = canonical_is_fw<K>(ef, er);
-            uint32_t kw[G::NW];
-            // rA sits (B + 8) bytes after fA (carve_tile): one base pointer, selected byte offset
-            extractA<K>(v.fA, use_fw ? i : (B + 8 + ri), kw);
-            const uint64_t h = murmur3_h1_words<K>(kw, sb.seed);
-            append_survivor(valid && h <= thr, h, t0 + i, sb, out, lane);
+        {
+            // running word pointers: stepped once per SK_UNROLL windows, constant offsets inside
+            const uint32_t *qf2 = pf2, *qr2 = pr2, *qfa = pfa, *qra = pra, *qsb = psb;
+            uint32_t i = (uint32_t)tid;
+#pragma unroll 1
+            for (int r = 0; r < SK_TILE / SK_THREADS; r += SK_UNROLL) {
+#pragma unroll
+                for (int u = 0; u < SK_UNROLL; u++) {
+                    const bool valid = (qsb[u * (SK_THREADS / 32)] & mb) == 0;
+                    uint32_t ef[G::NE], er[G::NE];
+                    extract2w<K>(qf2 + u * (SK_THREADS / 16), sf2, ef);
+                    extract2w<K>(qr2 - u * (SK_THREADS / 16), sr2, er);  // rc(window i) starts at B - K - i
+                    const bool use_fw = canonical_is_fw<K>(ef, er);
+                    uint32_t kw[G::NW];
+                    const uint32_t *pa = use_fw ? qfa + u * (SK_THREADS / 4) : qra - u * (SK_THREADS / 4);
+                    extractAw<K>(pa, use_fw ? sfa : sra, kw);
+                    const uint64_t h = murmur3_h1_words<K>(kw, sb.seed);
+                    append_survivor(valid && h <= thr, h, t0 + (i + u * SK_THREADS), sb, out, lane);
+                }
+                qf2 += SK_UNROLL * (SK_THREADS / 16); qr2 -= SK_UNROLL * (SK_THREADS / 16);
+                qfa += SK_UNROLL * (SK_THREADS / 4);  qra -= SK_UNROLL * (SK_THREADS / 4);
+                qsb += SK_UNROLL * (SK_THREADS / 32); i += SK_UNROLL * SK_THREADS;
+            }
         }
+        if (tid == 0) s_next = after_next;
         __syncthreads();  // views are rebuilt by the next tile
+        tile = next;
+    }
+    if (tid == 0) {  // the last CTA to leave re-arms the counters for the next launch
+        __threadfence();
+        if (atomicAdd(sb.tile_ctr + 1, 1u) == gridDim.x - 1) {
+            sb.tile_ctr[0] = 0;
+            sb.tile_ctr[1] = 0;
+            __threadfence();
+        }
     }
 }
 
