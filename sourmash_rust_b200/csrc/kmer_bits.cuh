@@ -150,6 +150,23 @@ KB_HD void extract2w(const uint32_t *w, uint32_t s, uint32_t (&e)[KmerGeom<K>::N
     e[KmerGeom<K>::NE - 1] &= KmerGeom<K>::TOP2;
 }
 
+// NE words whose TOP bits are the k-mer's last base: `w`/`s` address bit 2 * (start + K) - 32 * NE of
+// the stream, so the 32 * NE - 2K low bits are whatever precedes the k-mer.  For ODD K that is
+// harmless to canonical_is_fw: a k-mer of odd length never equals its reverse complement, so the
+// comparison is decided inside the K real bases, which sit above the extra low bits on both sides.
+// Saves the two top-word masks of extract2.
+template <int K>
+KB_HD void extract2_end(const uint32_t *w, uint32_t s, uint32_t (&e)[KmerGeom<K>::NE]) {
+    static_assert(K % 2 == 1, "end-aligned strand comparison needs an odd k");
+    uint32_t prev = w[0];
+#pragma unroll
+    for (int j = 0; j < KmerGeom<K>::NE; j++) {
+        const uint32_t next = w[j + 1];
+        e[j] = kb_funnel_r(prev, next, s);
+        prev = next;
+    }
+}
+
 // lexicographic `fw < rc` (src/lib.rs:263) from the little-endian 2-bit integers of the two
 // strands: with comp(c) = ~c, BE(fw) = ~E(rc) and BE(rc) = ~E(fw), so fw <lex rc <=> E(fw) < E(rc).
 template <int K>

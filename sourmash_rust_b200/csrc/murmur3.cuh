@@ -52,7 +52,7 @@ SM_HD uint64_t mm_mulc(uint64_t x) {
 // x * 5 + ADD
 template <uint32_t ADD>
 SM_HD uint64_t mm_mul5add(uint64_t x) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(MM_MUL5_WIDE)
     uint64_t r;
     asm("{\n\t.reg .u32 lo, hi, rl, rh;\n\t.reg .u64 t;\n\t"
         "mov.b64 {lo, hi}, %1;\n\t"
@@ -81,10 +81,11 @@ SM_HD uint64_t mm_rotl64(uint64_t x) {
 #endif
 }
 
-// k ^ (k >> 33): only the low word changes, by hi >> 1.  On the device the shift is spelled as the
-// high half of hi * 2^31 (IMAD.HI, FMA pipe) because the kernel's busiest pipe is the ALU one.
+// k ^ (k >> 33): only the low word changes, by hi >> 1.  (MM_XS_IMADHI spells the shift as the high
+// half of hi * 2^31 to move it from the ALU to the FMA pipe; IMAD.HI occupies that pipe for 4 cycles
+// on sm_100a -- tests/manual/intpeak.py -- and measured slower, so it is off.)
 SM_HD uint64_t mm_xorshift33(uint64_t k) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(MM_XS_IMADHI)
     uint32_t lo = (uint32_t)k, hi = (uint32_t)(k >> 32), t;
     asm("mul.hi.u32 %0, %1, 0x80000000;" : "=r"(t) : "r"(hi));
     lo ^= t;

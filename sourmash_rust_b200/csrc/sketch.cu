@@ -31,7 +31,7 @@
 namespace smb200 {
 
 #ifndef SK_UNROLL
-#define SK_UNROLL 2   // windows per trip of the k-mer loop (SK_TILE / SK_THREADS must be a multiple)
+#define SK_UNROLL 4   // windows per trip of the k-mer loop (SK_TILE / SK_THREADS must be a multiple)
 #endif
 #ifndef SK_MIN_CTAS
 #define SK_MIN_CTAS SK_CTAS_PER_SM
@@ -78,17 +78,18 @@ struct TileViews {
     uint8_t *raw;     // B bytes, 128-byte aligned (TMA destination)
     uint32_t *fA;     // B/4 + 2 words
     uint32_t *rA;     // B/4 + 2 words
-    uint32_t *f2;     // B/16 + 2 words
-    uint32_t *r2;     // B/16 + 2 words
+    uint32_t *f2;     // SK_PAD2 + B/16 + 2 words (f2 points past the pad: end-aligned extraction reads before base 0)
+    uint32_t *r2;     // SK_PAD2 + B/16 + 2 words
     uint32_t *bad;    // B/32 + 3 words   invalid-base bitmap
     uint32_t *end;    // B/32 + 3 words   "last base of a sequence" bitmap
     uint32_t *sbad;   // TILE/32 words    window start unusable
 };
+constexpr int SK_PAD2 = 4;  // words in front of each 2-bit stream (extract2_end reaches up to 64 bases back)
 __host__ __device__ constexpr int tile_bases(int K) { return SK_TILE + ((K - 1 + 15) / 16) * 16; }
 __host__ __device__ constexpr size_t tile_smem_bytes(int B) {
     return (size_t)B                      // raw
            + 2 * ((size_t)B + 8)          // fA, rA
-           + 2 * ((size_t)B / 4 + 8)      // f2, r2
+           + 2 * ((size_t)B / 4 + 8 + 4 * SK_PAD2)  // f2, r2
            + 2 * ((size_t)(B + 31) / 32 * 4 + 12)  // bad, end
            + SK_TILE / 8                  // sbad
            + 128;                         // alignment slack
@@ -99,8 +100,8 @@ __device__ __forceinline__ TileViews carve_tile(uint8_t *base, int B) {
     v.raw = p; p += B;                                   // B is a multiple of 16
     v.fA = reinterpret_cast<uint32_t *>(p); p += B + 8;
     v.rA = reinterpret_cast<uint32_t *>(p); p += B + 8;
-    v.f2 = reinterpret_cast<uint32_t *>(p); p += B / 4 + 8;
-    v.r2 = reinterpret_cast<uint32_t *>(p); p += B / 4 + 8;
+    v.f2 = reinterpret_cast<uint32_t *>(p) + SK_PAD2; p += B / 4 + 8 + 4 * SK_PAD2;
+    v.r2 = reinterpret_cast<uint32_t *>(p) + SK_PAD2; p += B / 4 + 8 + 4 * SK_PAD2;
     const int wm = (B + 31) / 32 + 3;
     v.bad = reinterpret_cast<uint32_t *>(p); p += wm * 4;
     v.end = reinterpret_cast<uint32_t *>(p); p += wm * 4;
@@ -125,6 +126,7 @@ __device__ __forceinline__ void build_views(const TileViews &v, int B, uint64_t 
     if (tid < 2) {  // slack words unaligned extraction may touch
         v.fA[B / 4 + tid] = 0; v.rA[B / 4 + tid] = 0; v.f2[B / 16 + tid] = 0; v.r2[B / 16 + tid] = 0;
     }
+    if (tid < SK_PAD2) { v.f2[-1 - tid] = 0; v.r2[-1 - tid] = 0; }
     const uint32_t *raw32 = reinterpret_cast<const uint32_t *>(v.raw);
     uint16_t *f2h = reinterpret_cast<uint16_t *>(v.f2);
     uint16_t *r2h = reinterpret_cast<uint16_t *>(v.r2);
@@ -219,19 +221,26 @@ __device__ __forceinline__ void build_start_bitmap(const TileViews &v, int K, ui
     }
 }
 
-__device__ __forceinline__ void append_survivor(bool pass, uint64_t h, uint64_t pos, const SketchBatch &sb,
-                                                const SketchOut &out, int lane) {
-    const unsigned bal = __ballot_sync(0xFFFFFFFFu, pass);
-    if (bal) {
+// Survivors are rare (1 window in 1000 for scaled=1000), so the common path is one predicated
+// branch; the threads that do pass aggregate their slot request over whoever is in the branch
+// with them (a num sketch that is still filling passes every window: one atomic per warp then).
+__device__ __forceinline__ void append_survivor(bool pass, uint64_t h, uint64_t pos0, const SketchBatch &sb,
+                                                const SketchOut &out) {
+    if (pass) {
+        // lane and thread index are read here, inside the rare path, so that no register has to hold
+        // them across the k-mer loop; the window start is pos0 + threadIdx.x
+        unsigned lane, tid;
+        asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+        asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+        const unsigned grp = __activemask();
+        const int leader = __ffs(grp) - 1;
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(out.counter, (unsigned long long)__popc(bal));
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (pass) {
-            const unsigned long long idx = base + __popc(bal & ((1u << lane) - 1u));
-            if (idx < out.cap) {
-                out.hash[idx] = h;
-                if (out.pos) out.pos[idx] = sb.pos_base + pos;
-            }
+        if ((int)lane == leader) base = atomicAdd(out.counter, (unsigned long long)__popc(grp));
+        base = __shfl_sync(grp, base, leader);
+        const unsigned long long idx = base + __popc(grp & ((1u << lane) - 1u));
+        if (idx < out.cap) {
+            out.hash[idx] = h;
+            if (out.pos) out.pos[idx] = sb.pos_base + pos0 + tid;
         }
     }
 }
@@ -255,14 +264,17 @@ __global__ void __launch_bounds__(SK_THREADS, SK_MIN_CTAS) sketch_kernel(const S
     //   8 * (i & 3); rc(window i) starts at base B - K - i of the reverse-complement views, and rA
     //   sits (B + 8) bytes after fA (carve_tile), so one base pointer serves both ASCII strands.
     //   SK_THREADS is a multiple of 16, so the r-dependence is a pure word offset.
-    static_assert(SK_THREADS % 32 == 0, "k-mer loop addressing");
+    static_assert(SK_THREADS % 32 == 0 && 16 * G::NE - K <= 16 * SK_PAD2, "k-mer loop addressing");
     const int ri0 = B - K - tid, ra0 = B + 8 + ri0;
-    const uint32_t *const pf2 = v.f2 + (tid >> 4), *const pr2 = v.r2 + (ri0 >> 4);
+    // 2-bit k-mers are taken end-aligned (extract2_end): NE words ending at base start + K
+    const int ef0 = tid + K - 16 * G::NE, er0 = ri0 + K - 16 * G::NE;  // >= -16 * SK_PAD2
+    const uint32_t *const pf2 = v.f2 + (ef0 >> 4), *const pr2 = v.r2 + (er0 >> 4);  // arithmetic shifts: floor
     const uint32_t *const pfa = v.fA + (tid >> 2), *const pra = v.fA + (ra0 >> 2);
-    const uint32_t sf2 = (uint32_t)tid * 2u, sr2 = (uint32_t)ri0 * 2u;  // funnel shifts use the low 5 bits
+    const uint32_t sf2 = (uint32_t)ef0 * 2u, sr2 = (uint32_t)er0 * 2u;  // funnel shifts use the low 5 bits
     const uint32_t sfa = (uint32_t)tid * 8u, sra = (uint32_t)ra0 * 8u;
     const uint32_t *const psb = v.sbad + (tid >> 5);
-    const uint32_t mb = 1u << lane;
+    uint32_t mb = 1u << lane;
+    asm("" : "+r"(mb));  // opaque: keeps the validity test a single LOP3 against a resident mask
 
     // Tiles are handed out dynamically: a CTA's first tile is its block index, every further one
     // comes from an atomic counter.  (With a static round-robin the warp scheduler's fixed priority
@@ -308,25 +320,24 @@ __global__ void __launch_bounds__(SK_THREADS, SK_MIN_CTAS) sketch_kernel(const S
         {
             // running word pointers: stepped once per SK_UNROLL windows, constant offsets inside
             const uint32_t *qf2 = pf2, *qr2 = pr2, *qfa = pfa, *qra = pra, *qsb = psb;
-            uint32_t i = (uint32_t)tid;
 #pragma unroll 1
             for (int r = 0; r < SK_TILE / SK_THREADS; r += SK_UNROLL) {
 #pragma unroll
                 for (int u = 0; u < SK_UNROLL; u++) {
                     const bool valid = (qsb[u * (SK_THREADS / 32)] & mb) == 0;
                     uint32_t ef[G::NE], er[G::NE];
-                    extract2w<K>(qf2 + u * (SK_THREADS / 16), sf2, ef);
-                    extract2w<K>(qr2 - u * (SK_THREADS / 16), sr2, er);  // rc(window i) starts at B - K - i
+                    extract2_end<K>(qf2 + u * (SK_THREADS / 16), sf2, ef);
+                    extract2_end<K>(qr2 - u * (SK_THREADS / 16), sr2, er);  // rc(window i) starts at B - K - i
                     const bool use_fw = canonical_is_fw<K>(ef, er);
                     uint32_t kw[G::NW];
                     const uint32_t *pa = use_fw ? qfa + u * (SK_THREADS / 4) : qra - u * (SK_THREADS / 4);
                     extractAw<K>(pa, use_fw ? sfa : sra, kw);
                     const uint64_t h = murmur3_h1_words<K>(kw, sb.seed);
-                    append_survivor(valid && h <= thr, h, t0 + (i + u * SK_THREADS), sb, out, lane);
+                    append_survivor(valid && h <= thr, h, t0 + (uint32_t)((r + u) * SK_THREADS), sb, out);
                 }
                 qf2 += SK_UNROLL * (SK_THREADS / 16); qr2 -= SK_UNROLL * (SK_THREADS / 16);
                 qfa += SK_UNROLL * (SK_THREADS / 4);  qra -= SK_UNROLL * (SK_THREADS / 4);
-                qsb += SK_UNROLL * (SK_THREADS / 32); i += SK_UNROLL * SK_THREADS;
+                qsb += SK_UNROLL * (SK_THREADS / 32);
             }
         }
         if (tid == 0) s_next = after_next;
@@ -386,7 +397,7 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_generic_kernel(const Sketch
                 const uint8_t *src = (j < K && f[j] < rc[j]) ? f : rc;  // lib.rs:263-267 (ties -> rc)
                 h = murmur3_h1_bytes(src, (uint64_t)K, sb.seed);
             }
-            append_survivor(valid && h <= thr, h, t0 + i, sb, out, lane);
+            append_survivor(valid && h <= thr, h, t0 + (uint32_t)(r * SK_THREADS), sb, out);
         }
         __syncthreads();
     }

@@ -1,10 +1,16 @@
+"""Integer-pipe microbenchmarks on the device (roofline denominators of the sketch kernel).
+Modes 0-2: dependent chains (legacy); 3-9: eight independent chains per pipe, SASS counted with cuobjdump."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import sourmash_rust_b200 as smb
 dev, sms = smb.device_info()
-# counted instructions per unrolled step: mode 0 = 8 IMAD, mode 1 = 4 SHF + 8 LOP3 (two per chain element) , mode 2 = 4 IMAD + 2 SHF + 4 LOP3
-real = {0: 8, 1: 12, 2: 10}
-for mode in (0, 1, 2):
+# SASS instructions per inner step (per 8-chain sweep); smgpu_int_peak reports 8 per sweep for modes 0-2
+# and we pass iters so that its "64 per iteration" bookkeeping is rescaled here
+spec = {3: ("8 LOP3", 8), 4: ("8 SHF", 8), 5: ("8 IMAD + 8 LOP3", 16), 6: ("8 IMAD.WIDE + 8 LOP3", 16),
+        7: ("4 IMAD.WIDE + 8 IMAD + 12 LOP3/SHF", 24), 8: ("8 IMAD.HI", 8), 9: ("8 IMAD + 8 SHF", 16)}
+for mode, (what, per_sweep) in spec.items():
     for blocks in (sms * 4, sms * 8):
-        r = smb.int_peak(mode, 8192, blocks) * real[mode] / 8.0
-        print("mode %d blocks %d: %.2f T thread-instr/s = %.1f instr/clk/SM at 1965 MHz" % (mode, blocks, r / 1e12, r / 1.965e9 / sms))
+        # the C side counts iters * 64 * 256 * blocks "instructions"; real = iters * 4 sweeps * per_sweep
+        r = smb.int_peak(mode, 4096, blocks) * (4 * per_sweep) / 64.0
+        print("mode %d (%s) blocks %d: %.2f T thread-instr/s = %.1f thread-instr/clk/SM at 1965 MHz" %
+              (mode, what, blocks, r / 1e12, r / 1.965e9 / sms))
