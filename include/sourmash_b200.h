@@ -111,6 +111,10 @@ uint64_t smgpu_scaffold_pairs(SketchCollection *c, uint64_t *pairs_first, uint64
  * only those are walked when the (pair, shared hash) incidences are few against the dense work;
  * 1 forces the dense tile kernel, 2 forces the inverted-index path.  Results are identical. */
 void smgpu_compare_path(int32_t path);
+/* Batch sketching of several k-sizes over the same sequences (smgpu_add_* with more than one
+ * handle): on (default) = sketches with distinct k in {21, 31, 51} and one seed share a fused
+ * launch that stages each tile of bases once; off = one launch per sketch.  Results are identical. */
+void smgpu_fuse_multi_k(bool on);
 /* LinearIndex::find (src/index/linear.rs:25-45) for every row of `queries` against `index`:
  * mode 0 = search_minhashes (node.similarity(query) > threshold), mode 1 =
  * search_minhashes_containment (node.containment(query) > threshold) (src/index/search.rs:3-9).

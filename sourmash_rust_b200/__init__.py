@@ -83,6 +83,7 @@ EXTENSION_ABI = {
     "smgpu_profile_enable": (None, [cb]),
     "smgpu_profile_read": (None, [i32, C.POINTER(C.c_double), C.POINTER(u64), cb]),
     "smgpu_int_peak": (C.c_double, [i32, i32, i32]),
+    "smgpu_fuse_multi_k": (None, [C.c_bool]),
     "smgpu_alloc_pinned": (vp, [usz]),
     "smgpu_free_pinned": (None, [vp]),
     "kmerminhash_slice_free": (None, [p_u64]),
@@ -178,12 +179,18 @@ def profile_enable(on=True):
     lib().smgpu_profile_enable(on)
 
 
-PROFILE_KINDS = {"sketch_k21": 0, "sketch_k31": 1, "sketch_k51": 2, "sketch_other": 3, "compare": 4, "join_sort": 5}
+PROFILE_KINDS = {"sketch_k21": 0, "sketch_k31": 1, "sketch_k51": 2, "sketch_other": 3, "compare": 4, "join_sort": 5,
+                 "sketch_multi": 6}
 
 
 def compare_path(path="auto"):
     """'auto' | 'dense' | 'sparse' (smgpu_compare_path)"""
     lib().smgpu_compare_path({"auto": 0, "dense": 1, "sparse": 2}[path])
+
+
+def fuse_multi_k(on=True):
+    """Fused multi-k launches in batch sketching on/off (smgpu_fuse_multi_k)."""
+    lib().smgpu_fuse_multi_k(bool(on))
 
 
 def profile_read(kind, reset=False):

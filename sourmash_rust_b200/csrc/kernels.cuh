@@ -49,12 +49,19 @@ struct SketchOut {
     uint64_t cap;
     unsigned long long *counter;
 };
+struct SketchOuts {  // per k-size outputs of a fused multi-k launch
+    SketchOut o[3];
+    unsigned long long *first_bad[3];  // nullable
+};
 uint32_t sketch_tile_count(uint64_t n, uint64_t n_limit);
 uint32_t sketch_tiles_ready(uint32_t K, uint64_t bytes_ready);
 // tiles [sb.tile_lo, tile_hi)
 void launch_sketch(uint32_t K, const SketchBatch &sb, const SketchOut &out, uint32_t tile_hi, int sm_count,
                    cudaStream_t st);
 bool sketch_has_fast_path(uint32_t K);
+bool sketch_multi_supported(const uint32_t *ks, int nk);
+void launch_sketch_multi(const uint32_t *ks, int nk, const SketchBatch &sb, const SketchOuts &outs, uint32_t tile_hi,
+                         int sm_count, cudaStream_t st);
 
 // ---- protein.cu: 6-frame translated sketching (reference src/lib.rs:275-302) --------------------
 struct ProteinBatch {

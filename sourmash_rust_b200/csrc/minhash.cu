@@ -25,6 +25,8 @@
 
 namespace smb200 {
 
+bool g_fuse_multi_k = true;
+
 static const uint64_t U64_MAX = ~0ull;
 static const uint64_t LAZY_CANDIDATES = 1ull << 22;  // scaled sketches fold their candidates in past this
 
@@ -513,6 +515,21 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
         SM_CUDA(cudaEventRecord(ctx.prep_event, st));
         for (int i = 0; i < n_mhs; i++) SM_CUDA(cudaStreamWaitEvent(ctx.k_streams[i], ctx.prep_event, 0));
     }
+    // DNA sketches with distinct fast-path k-sizes and one seed share a fused launch per chunk: the
+    // tile is staged once and every k-size walks it (sketch.cu).  Member order = ascending k.
+    std::vector<int> fused;
+    if (g_fuse_multi_k) {
+        for (int i = 0; i < n_mhs; i++) {
+            const KmerMinHash &mh = *mhs[i];
+            if (mh.is_protein || !sketch_has_fast_path(mh.ksize)) continue;
+            bool ok = fused.empty() || mhs[fused[0]]->seed == mh.seed;
+            for (int j : fused) ok = ok && mhs[j]->ksize != mh.ksize;
+            if (ok && fused.size() < 3) fused.push_back(i);
+        }
+        std::sort(fused.begin(), fused.end(), [&](int a, int b) { return mhs[a]->ksize < mhs[b]->ksize; });
+        if (fused.size() < 2) fused.clear();
+    }
+    auto in_fused = [&](int i) { return std::find(fused.begin(), fused.end(), i) != fused.end(); };
     size_t ev_i = 0;
     do {
         if (!batch.on_device) {
@@ -534,10 +551,29 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
             }
             ev_i++;
         }
+        if (!fused.empty()) {
+            const int lead = fused[0];
+            PerSketch &p = ps[lead];
+            const uint32_t kmax = mhs[fused.back()]->ksize;  // the widest halo decides which tiles are complete
+            const uint32_t hi = (copied >= n) ? p.tiles_total : std::min(p.tiles_total, sketch_tiles_ready(kmax, copied));
+            if (hi > p.tile_lo) {
+                uint32_t ks[3];
+                SketchOuts outs;
+                for (size_t j = 0; j < 3; j++) {
+                    KmerMinHash &m = *mhs[fused[std::min(j, fused.size() - 1)]];
+                    outs.o[j] = make_out(m);
+                    outs.first_bad[j] = force ? nullptr : m.hs(2);
+                    if (j < fused.size()) ks[j] = m.ksize;
+                }
+                launch_sketch_multi(ks, (int)fused.size(), make_batch(*mhs[lead], n, p.tile_lo), outs, hi, ctx.sm_count,
+                                    kstream(lead));
+                for (int j : fused) ps[j].tile_lo = hi;
+            }
+        }
         for (int i = 0; i < n_mhs; i++) {
             KmerMinHash &mh = *mhs[i];
             PerSketch &p = ps[i];
-            if (mh.is_protein) continue;  // after the whole batch has arrived
+            if (mh.is_protein || in_fused(i)) continue;  // protein: after the whole batch has arrived
             uint32_t hi = (copied >= n) ? p.tiles_total : std::min(p.tiles_total, sketch_tiles_ready(mh.ksize, copied));
             if (hi <= p.tile_lo) continue;
             launch_sketch(mh.ksize, make_batch(mh, n, p.tile_lo), make_out(mh), hi, ctx.sm_count, kstream(i));

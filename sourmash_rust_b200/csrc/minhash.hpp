@@ -17,6 +17,9 @@
 
 namespace smb200 {
 
+// add_sequences: share one fused launch among the fast-path k-sizes of a batch (smgpu_fuse_multi_k)
+extern bool g_fuse_multi_k;
+
 // A batch of sequences as the caller holds it (host or device memory).
 //   offsets == nullptr && read_len == 0 : one sequence of n_bytes
 //   offsets == nullptr && read_len  > 0 : n_seqs reads of read_len bytes, back to back

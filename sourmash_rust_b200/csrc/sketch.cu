@@ -82,16 +82,16 @@ struct TileViews {
     uint32_t *r2;     // SK_PAD2 + B/16 + 2 words
     uint32_t *bad;    // B/32 + 3 words   invalid-base bitmap
     uint32_t *end;    // B/32 + 3 words   "last base of a sequence" bitmap
-    uint32_t *sbad;   // TILE/32 words    window start unusable
+    uint32_t *sbad;   // nk * TILE/32 words   window start unusable, one bitmap per k-size of the launch
 };
 constexpr int SK_PAD2 = 4;  // words in front of each 2-bit stream (extract2_end reaches up to 64 bases back)
 __host__ __device__ constexpr int tile_bases(int K) { return SK_TILE + ((K - 1 + 15) / 16) * 16; }
-__host__ __device__ constexpr size_t tile_smem_bytes(int B) {
+__host__ __device__ constexpr size_t tile_smem_bytes(int B, int nk = 1) {
     return (size_t)B                      // raw
            + 2 * ((size_t)B + 8)          // fA, rA
            + 2 * ((size_t)B / 4 + 8 + 4 * SK_PAD2)  // f2, r2
            + 2 * ((size_t)(B + 31) / 32 * 4 + 12)  // bad, end
-           + SK_TILE / 8                  // sbad
+           + (size_t)nk * (SK_TILE / 8)   // sbad
            + 128;                         // alignment slack
 }
 __device__ __forceinline__ TileViews carve_tile(uint8_t *base, int B) {
@@ -190,7 +190,8 @@ __device__ __forceinline__ void mark_sequence_ends(const TileViews &v, int B, ui
 
 // sbad[w] for the TILE window starts; reports the first window that the reference would fail on
 // (an invalid base inside a window that lies wholly inside one sequence, lib.rs:268-273)
-__device__ __forceinline__ void build_start_bitmap(const TileViews &v, int K, uint64_t t0, const SketchBatch &sb) {
+__device__ __forceinline__ void build_start_bitmap(const TileViews &v, uint32_t *sbad, int K, uint64_t t0,
+                                                   const SketchBatch &sb, unsigned long long *first_bad) {
     for (int w = threadIdx.x; w < SK_TILE / 32; w += blockDim.x) {
         uint32_t hasbad, crosses;
         if (K <= 64) {
@@ -214,10 +215,10 @@ __device__ __forceinline__ void build_start_bitmap(const TileViews &v, int K, ui
         const uint64_t q0 = t0 + (uint64_t)w * 32;
         uint32_t beyond = 0;
         if (q0 + 32 > sb.n_limit) beyond = (q0 >= sb.n_limit) ? 0xFFFFFFFFu : (0xFFFFFFFFu << (uint32_t)(sb.n_limit - q0));
-        v.sbad[w] = hasbad | crosses | beyond;
+        sbad[w] = hasbad | crosses | beyond;
         const uint32_t err = hasbad & ~crosses & ~beyond;
-        if (err && sb.first_bad)
-            atomicMin(sb.first_bad, (unsigned long long)(sb.pos_base + q0 + (uint32_t)(__ffs(err) - 1)));
+        if (err && first_bad)
+            atomicMin(first_bad, (unsigned long long)(sb.pos_base + q0 + (uint32_t)(__ffs(err) - 1)));
     }
 }
 
@@ -246,35 +247,68 @@ __device__ __forceinline__ void append_survivor(bool pass, uint64_t h, uint64_t 
 }
 
 // ---------------------------------------------------------------------------------------
-// fast path: compile-time K
+// fast path: compile-time k-sizes; one launch serves up to three sketches of the same batch
 // ---------------------------------------------------------------------------------------
-template <int K>
-__global__ void __launch_bounds__(SK_THREADS, SK_MIN_CTAS) sketch_kernel(const SketchBatch sb, const SketchOut out,
-                                                            uint32_t n_tiles) {
-    constexpr int B = tile_bases(K);
+// The k-mer loop of one k-size over a staged tile of B bases: one thread per window start
+// i = r * SK_THREADS + tid.  Per-thread constants:
+//   2-bit views: word (i >> 4), bit shift 2 * (i & 15); ASCII views: word (i >> 2), bit shift
+//   8 * (i & 3); rc(window i) starts at base B - K - i of the reverse-complement views, and rA
+//   sits (B + 8) bytes after fA (carve_tile), so one base pointer serves both ASCII strands.
+//   SK_THREADS is a multiple of 32, so the r-dependence is a pure word offset.
+template <int K, int B>
+__device__ __forceinline__ void kmer_loop(const TileViews &v, const uint32_t *sbad, const uint64_t thr, const uint64_t t0,
+                                          const SketchBatch &sb, const SketchOut &out) {
     using G = KmerGeom<K>;
-    extern __shared__ __align__(128) uint8_t s_dyn[];
-    __shared__ __align__(8) uint64_t s_bar;
-    const TileViews v = carve_tile(s_dyn, B);
-    const int tid = threadIdx.x, lane = tid & 31;
-    const uint64_t thr = *out.thr;
-
-    // per-thread constants of the k-mer loop (window i = r * SK_THREADS + tid):
-    //   2-bit views: word (i >> 4), bit shift 2 * (i & 15); ASCII views: word (i >> 2), bit shift
-    //   8 * (i & 3); rc(window i) starts at base B - K - i of the reverse-complement views, and rA
-    //   sits (B + 8) bytes after fA (carve_tile), so one base pointer serves both ASCII strands.
-    //   SK_THREADS is a multiple of 16, so the r-dependence is a pure word offset.
     static_assert(SK_THREADS % 32 == 0 && 16 * G::NE - K <= 16 * SK_PAD2, "k-mer loop addressing");
+    const int tid = threadIdx.x;
     const int ri0 = B - K - tid, ra0 = B + 8 + ri0;
     // 2-bit k-mers are taken end-aligned (extract2_end): NE words ending at base start + K
     const int ef0 = tid + K - 16 * G::NE, er0 = ri0 + K - 16 * G::NE;  // >= -16 * SK_PAD2
-    const uint32_t *const pf2 = v.f2 + (ef0 >> 4), *const pr2 = v.r2 + (er0 >> 4);  // arithmetic shifts: floor
-    const uint32_t *const pfa = v.fA + (tid >> 2), *const pra = v.fA + (ra0 >> 2);
+    const uint32_t *qf2 = v.f2 + (ef0 >> 4), *qr2 = v.r2 + (er0 >> 4);  // arithmetic shifts: floor
+    const uint32_t *qfa = v.fA + (tid >> 2), *qra = v.fA + (ra0 >> 2);
     const uint32_t sf2 = (uint32_t)ef0 * 2u, sr2 = (uint32_t)er0 * 2u;  // funnel shifts use the low 5 bits
     const uint32_t sfa = (uint32_t)tid * 8u, sra = (uint32_t)ra0 * 8u;
-    const uint32_t *const psb = v.sbad + (tid >> 5);
-    uint32_t mb = 1u << lane;
+    const uint32_t *qsb = sbad + (tid >> 5);
+    uint32_t mb = 1u << (tid & 31);
     asm("" : "+r"(mb));  // opaque: keeps the validity test a single LOP3 against a resident mask
+    // running word pointers: stepped once per SK_UNROLL windows, constant offsets inside
+#pragma unroll 1
+    for (int r = 0; r < SK_TILE / SK_THREADS; r += SK_UNROLL) {
+#pragma unroll
+        for (int u = 0; u < SK_UNROLL; u++) {
+            const bool valid = (qsb[u * (SK_THREADS / 32)] & mb) == 0;
+            uint32_t ef[G::NE], er[G::NE];
+            extract2_end<K>(qf2 + u * (SK_THREADS / 16), sf2, ef);
+            extract2_end<K>(qr2 - u * (SK_THREADS / 16), sr2, er);  // rc(window i) starts at B - K - i
+            const bool use_fw = canonical_is_fw<K>(ef, er);
+            uint32_t kw[G::NW];
+            const uint32_t *pa = use_fw ? qfa + u * (SK_THREADS / 4) : qra - u * (SK_THREADS / 4);
+            extractAw<K>(pa, use_fw ? sfa : sra, kw);
+            const uint64_t h = murmur3_h1_words<K>(kw, sb.seed);
+            append_survivor(valid && h <= thr, h, t0 + (uint32_t)((r + u) * SK_THREADS), sb, out);
+        }
+        qf2 += SK_UNROLL * (SK_THREADS / 16); qr2 -= SK_UNROLL * (SK_THREADS / 16);
+        qfa += SK_UNROLL * (SK_THREADS / 4);  qra -= SK_UNROLL * (SK_THREADS / 4);
+        qsb += SK_UNROLL * (SK_THREADS / 32);
+    }
+}
+
+__host__ __device__ constexpr int kmax3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
+
+// KB / KC = 0: absent.  The tile (TMA copy, five views, sequence-end bitmap) is staged ONCE and every
+// k-size walks it: a multi-k batch (BASELINE cfg2: k = 21, 31, 51 over the same reads) reads each
+// base from HBM once and pays the per-base staging work once instead of once per k-size.
+template <int KA, int KB, int KC>
+__global__ void __launch_bounds__(SK_THREADS, SK_MIN_CTAS) sketch_kernel(const SketchBatch sb, const SketchOuts outs,
+                                                                         uint32_t n_tiles) {
+    constexpr int B = tile_bases(kmax3(KA, KB, KC));
+    extern __shared__ __align__(128) uint8_t s_dyn[];
+    __shared__ __align__(8) uint64_t s_bar;
+    const TileViews v = carve_tile(s_dyn, B);
+    const int tid = threadIdx.x;
+    const uint64_t thrA = *outs.o[0].thr;
+    const uint64_t thrB = KB ? *outs.o[1].thr : 0;
+    const uint64_t thrC = KC ? *outs.o[2].thr : 0;
 
     // Tiles are handed out dynamically: a CTA's first tile is its block index, every further one
     // comes from an atomic counter.  (With a static round-robin the warp scheduler's fixed priority
@@ -315,31 +349,13 @@ __global__ void __launch_bounds__(SK_THREADS, SK_MIN_CTAS) sketch_kernel(const S
         }
         mark_sequence_ends(v, B, t0, sb);
         __syncthreads();
-        build_start_bitmap(v, K, t0, sb);
+        build_start_bitmap(v, v.sbad, KA, t0, sb, outs.first_bad[0]);
+        if (KB) build_start_bitmap(v, v.sbad + SK_TILE / 32, KB, t0, sb, outs.first_bad[1]);
+        if (KC) build_start_bitmap(v, v.sbad + 2 * (SK_TILE / 32), KC, t0, sb, outs.first_bad[2]);
         __syncthreads();
-        {
-            // running word pointers: stepped once per SK_UNROLL windows, constant offsets inside
-            const uint32_t *qf2 = pf2, *qr2 = pr2, *qfa = pfa, *qra = pra, *qsb = psb;
-#pragma unroll 1
-            for (int r = 0; r < SK_TILE / SK_THREADS; r += SK_UNROLL) {
-#pragma unroll
-                for (int u = 0; u < SK_UNROLL; u++) {
-                    const bool valid = (qsb[u * (SK_THREADS / 32)] & mb) == 0;
-                    uint32_t ef[G::NE], er[G::NE];
-                    extract2_end<K>(qf2 + u * (SK_THREADS / 16), sf2, ef);
-                    extract2_end<K>(qr2 - u * (SK_THREADS / 16), sr2, er);  // rc(window i) starts at B - K - i
-                    const bool use_fw = canonical_is_fw<K>(ef, er);
-                    uint32_t kw[G::NW];
-                    const uint32_t *pa = use_fw ? qfa + u * (SK_THREADS / 4) : qra - u * (SK_THREADS / 4);
-                    extractAw<K>(pa, use_fw ? sfa : sra, kw);
-                    const uint64_t h = murmur3_h1_words<K>(kw, sb.seed);
-                    append_survivor(valid && h <= thr, h, t0 + (uint32_t)((r + u) * SK_THREADS), sb, out);
-                }
-                qf2 += SK_UNROLL * (SK_THREADS / 16); qr2 -= SK_UNROLL * (SK_THREADS / 16);
-                qfa += SK_UNROLL * (SK_THREADS / 4);  qra -= SK_UNROLL * (SK_THREADS / 4);
-                qsb += SK_UNROLL * (SK_THREADS / 32);
-            }
-        }
+        kmer_loop<KA, B>(v, v.sbad, thrA, t0, sb, outs.o[0]);
+        if (KB) kmer_loop<(KB ? KB : KA), B>(v, v.sbad + SK_TILE / 32, thrB, t0, sb, outs.o[1]);
+        if (KC) kmer_loop<(KC ? KC : KA), B>(v, v.sbad + 2 * (SK_TILE / 32), thrC, t0, sb, outs.o[2]);
         if (tid == 0) s_next = after_next;
         __syncthreads();  // views are rebuilt by the next tile
         tile = next;
@@ -381,7 +397,7 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_generic_kernel(const Sketch
         __syncthreads();
         mark_sequence_ends(v, B, t0, sb);
         __syncthreads();
-        build_start_bitmap(v, K, t0, sb);
+        build_start_bitmap(v, v.sbad, K, t0, sb, sb.first_bad);
         __syncthreads();
         const uint8_t *fA = reinterpret_cast<const uint8_t *>(v.fA);
         const uint8_t *rA = reinterpret_cast<const uint8_t *>(v.rA);
@@ -404,17 +420,26 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_generic_kernel(const Sketch
 }
 
 bool sketch_has_fast_path(uint32_t K) { return K == 21 || K == 31 || K == 51; }
+// distinct fast-path k-sizes in ascending order, two or three of them
+bool sketch_multi_supported(const uint32_t *ks, int nk) {
+    if (nk < 2 || nk > 3) return false;
+    for (int i = 0; i < nk; i++) {
+        if (!sketch_has_fast_path(ks[i])) return false;
+        if (i && ks[i] <= ks[i - 1]) return false;
+    }
+    return true;
+}
 
-template <int K>
-static void launch_fast(const SketchBatch &sb, const SketchOut &out, uint32_t n_tiles, unsigned grid,
-                        cudaStream_t st) {
-    constexpr size_t smem = tile_smem_bytes(tile_bases(K));
+template <int KA, int KB, int KC>
+static void launch_fast(const SketchBatch &sb, const SketchOuts &outs, uint32_t n_tiles, unsigned grid, cudaStream_t st) {
+    constexpr int NK = 1 + (KB ? 1 : 0) + (KC ? 1 : 0);
+    constexpr size_t smem = tile_smem_bytes(tile_bases(kmax3(KA, KB, KC)), NK);
     static bool attr_set = false;
     if (!attr_set) {
-        SM_CUDA(cudaFuncSetAttribute(sketch_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SM_CUDA(cudaFuncSetAttribute(sketch_kernel<KA, KB, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    sketch_kernel<K><<<grid, SK_THREADS, smem, st>>>(sb, out, n_tiles);
+    sketch_kernel<KA, KB, KC><<<grid, SK_THREADS, smem, st>>>(sb, outs, n_tiles);
 }
 
 uint32_t sketch_tile_count(uint64_t n, uint64_t n_limit) {
@@ -430,17 +455,25 @@ uint32_t sketch_tiles_ready(uint32_t K, uint64_t bytes_ready) {
     return (uint32_t)((bytes_ready - B) / SK_TILE + 1);
 }
 
+static unsigned sketch_grid(const SketchBatch &sb, uint32_t tile_hi, int sm_count) {
+    unsigned grid = (unsigned)sm_count * SK_CTAS_PER_SM;  // persistent: a multiple of the SM count
+    if (grid > tile_hi - sb.tile_lo) grid = tile_hi - sb.tile_lo;
+    return grid;
+}
+
 void launch_sketch(uint32_t K, const SketchBatch &sb, const SketchOut &out, uint32_t tile_hi, int sm_count,
                    cudaStream_t st) {
     if (sb.n == 0 || sb.n_limit == 0 || K == 0 || tile_hi <= sb.tile_lo) return;
     const uint32_t n_tiles = tile_hi;
-    unsigned grid = (unsigned)sm_count * SK_CTAS_PER_SM;  // persistent: a multiple of the SM count
-    if (grid > tile_hi - sb.tile_lo) grid = tile_hi - sb.tile_lo;
+    const unsigned grid = sketch_grid(sb, tile_hi, sm_count);
     ProfScope prof(K == 21 ? PROF_SKETCH_K21 : K == 31 ? PROF_SKETCH_K31 : K == 51 ? PROF_SKETCH_K51 : PROF_SKETCH_OTHER, st);
+    SketchOuts outs;
+    outs.o[0] = out; outs.o[1] = out; outs.o[2] = out;
+    outs.first_bad[0] = sb.first_bad; outs.first_bad[1] = nullptr; outs.first_bad[2] = nullptr;
     switch (K) {
-    case 21: launch_fast<21>(sb, out, n_tiles, grid, st); break;
-    case 31: launch_fast<31>(sb, out, n_tiles, grid, st); break;
-    case 51: launch_fast<51>(sb, out, n_tiles, grid, st); break;
+    case 21: launch_fast<21, 0, 0>(sb, outs, n_tiles, grid, st); break;
+    case 31: launch_fast<31, 0, 0>(sb, outs, n_tiles, grid, st); break;
+    case 51: launch_fast<51, 0, 0>(sb, outs, n_tiles, grid, st); break;
     default: {
         if (K > (uint32_t)SK_MAX_GENERIC_K) throw_internal("ksize above 8192 is not supported by the GPU sketcher");
         const int B = SK_TILE + (((int)K - 1 + 15) / 16) * 16;
@@ -449,6 +482,21 @@ void launch_sketch(uint32_t K, const SketchBatch &sb, const SketchOut &out, uint
         sketch_generic_kernel<<<grid, SK_THREADS, smem, st>>>(sb, out, n_tiles, (int)K);
     }
     }
+    SM_LAUNCHED();
+}
+
+// two or three sketches of the same batch in one launch (sketch_multi_supported(ks, nk)); outs.o[j] /
+// outs.first_bad[j] belong to ks[j]; sb.seed and sb.tile_ctr are shared
+void launch_sketch_multi(const uint32_t *ks, int nk, const SketchBatch &sb, const SketchOuts &outs, uint32_t tile_hi,
+                         int sm_count, cudaStream_t st) {
+    if (!sketch_multi_supported(ks, nk)) throw_internal("unsupported k-size combination for the fused sketch kernel");
+    if (sb.n == 0 || sb.n_limit == 0 || tile_hi <= sb.tile_lo) return;
+    const unsigned grid = sketch_grid(sb, tile_hi, sm_count);
+    ProfScope prof(PROF_SKETCH_MULTI, st);
+    if (nk == 3) launch_fast<21, 31, 51>(sb, outs, tile_hi, grid, st);
+    else if (ks[0] == 21 && ks[1] == 31) launch_fast<21, 31, 0>(sb, outs, tile_hi, grid, st);
+    else if (ks[0] == 21 && ks[1] == 51) launch_fast<21, 51, 0>(sb, outs, tile_hi, grid, st);
+    else launch_fast<31, 51, 0>(sb, outs, tile_hi, grid, st);
     SM_LAUNCHED();
 }
 

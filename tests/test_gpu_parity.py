@@ -284,6 +284,66 @@ def test_add_reads_multi_k():  # BASELINE config 2 shape, reduced
         same(g, o)
 
 
+@pytest.mark.parametrize("ks", [(21, 31), (21, 51), (31, 51), (21, 31, 51), (51, 31, 21), (31, 31, 21), (21, 9, 51, 33)])
+def test_fused_multi_k_launch(ks):
+    """Batch calls share one fused launch among distinct k in {21, 31, 51} (smgpu_fuse_multi_k): the
+    fused kernel, the per-sketch kernels and the oracle must agree -- dirty, ragged input, mixed sketch
+    kinds, force on and off (the first failing k-mer differs per k)."""
+    r = splitmix64(777 + sum(ks), 200)
+    lens = [int(x % np.uint64(900)) for x in r[:150]] + [0, 20, 21, 22, 30, 31, 32, 50, 51, 52, 9000, 0]
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    clean = random_dna(int(offsets[-1]), 5 + len(ks))
+    buf = dirty(clean, 99)
+    kinds = [(0, MAX_HASH_1000 * 40, True), (300, 0, False), (0, MAX_HASH_1000 * 40, False), (150, 0, True)]
+
+    def sketches():
+        gs, os_ = [], []
+        for j, k in enumerate(ks):
+            num, mx, ab = kinds[j % len(kinds)]
+            g, o = pair(num, k, mx, ab)
+            gs.append(g); os_.append(o)
+        return gs, os_
+
+    results = {}
+    for fuse in (True, False):
+        smb.fuse_multi_k(fuse)
+        try:
+            gs, os_ = sketches()
+            smb.add_sequences(gs, buf, offsets, force=True)
+            for o in os_:
+                for s in range(len(lens)):
+                    o.add_sequence(buf[int(offsets[s]):int(offsets[s + 1])], True)
+            for g, o in zip(gs, os_):
+                same(g, o)
+            # a second, clean batch of fixed-length reads accumulates into the same sketches
+            reads = make_reads(clean[:60000], 700, 150, 31)
+            smb.add_reads(gs, reads, 700, 150, force=False)
+            for g, o in zip(gs, os_):
+                o.add_reads(reads, 700, 150)
+                same(g, o)
+            results[fuse] = [g.md5sum() for g in gs]
+            # force=False on the dirty batch: error of the first sketch that fails, partial state kept
+            gs, os_ = sketches()
+            with pytest.raises(smb.SourmashError) as ge:
+                smb.add_sequences(gs, buf, offsets, force=False)
+            msgs = []
+            for o in os_:
+                msg = None
+                for s in range(len(lens)):
+                    try:
+                        o.add_sequence(buf[int(offsets[s]):int(offsets[s + 1])], False)
+                    except orc.SourmashError as e:
+                        msg = e.message
+                        break
+                msgs.append(msg)
+            assert ge.value.message in msgs
+            for g, o in zip(gs, os_):
+                same(g, o)
+        finally:
+            smb.fuse_multi_k(True)
+    assert results[True] == results[False]
+
+
 @pytest.mark.parametrize("read_len", [30, 31, 32, 100, 151, 2048, 5000])
 def test_add_reads_lengths(read_len):
     n_reads = max(3, 200000 // read_len)
