@@ -32,11 +32,14 @@ GENOME_LEN = 100_000_000
 SEED_GENOME = 0x5EED0010
 SEED_READS = 0x5EED0011
 # From the ncu --set full capture of the sketch kernels (profiles/sketch_r1_summary.md): executed SASS
-# thread-instructions per window (smsp__inst_executed x 32 / windows) and DRAM bytes per window
-# (dram__bytes_read + dram__bytes_write); used for the integer-issue roofline and roofline.traffic
-INSTR_PER_WINDOW = {21: 178.1, 31: 197.2, 51: 307.8}
-DRAM_BYTES_PER_WINDOW = {21: 1.031, 31: 1.024, 51: 1.026}
-NCU_ALU_PIPE_PCT = {21: 70.0, 31: 68.0, 51: 67.6}
+# thread-instructions per window (smsp__inst_executed x 32 / windows), DRAM bytes per window
+# (dram__bytes_read + dram__bytes_write) and pipe utilisations; used for the integer-issue roofline and
+# roofline.traffic.  "multi" = the fused k=21/31/51 kernel (three hashes per window start).
+INSTR_PER_WINDOW = {21: 145.9, 31: 159.5, 51: 249.7, "multi": 510.6}
+DRAM_BYTES_PER_WINDOW = {21: 1.037, 31: 1.039, 51: 1.047, "multi": 1.059}
+NCU_ALU_PIPE_PCT = {21: 67.8, 31: 67.8, 51: 69.7, "multi": 67.5}
+NCU_FMAHEAVY_PIPE_PCT = {21: 64.3, 31: 65.7, 51: 61.3, "multi": 64.8}
+NCU_ISSUE_PCT = {21: 73.6, 31: 74.5, 51: 70.1, "multi": 70.8}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -294,19 +297,26 @@ def run_ours(args):
     # the same K steps once more with per-kernel CUDA events: the three kernels of a step then run
     # one after the other on the library's stream (in the pass above they overlap at their edges on
     # three streams), so that each duration is the kernel's own -- the roofline's denominator
-    mhs_k = new_sketches()
+    # (the timed pass uses the fused k=21/31/51 launch; here first the fused kernel alone, then -- with
+    # fusion switched off -- one kernel per k-size, so that the k=31 kernel the metric names is measured too)
     smb.profile_enable(True)
-    for kind in smb.PROFILE_KINDS:
-        smb.profile_read(kind, reset=True)
-    barrier()
-    t_wall0 = time.time()
-    for s in range(args.steps):
-        smb.add_reads(mhs_k, dev_batches[s % n_batches].data_ptr(), R, READ_LEN, force=False, on_device=True)
-    barrier()
-    windows.append((t_wall0, time.time()))
-    kern = {kind: smb.profile_read(kind, reset=True) for kind in ("sketch_k21", "sketch_k31", "sketch_k51")}
+    kern = {}
+    for fuse, kinds in ((True, ("sketch_multi",)), (False, ("sketch_k21", "sketch_k31", "sketch_k51"))):
+        mhs_k = new_sketches()
+        smb.fuse_multi_k(fuse)
+        for kind in smb.PROFILE_KINDS:
+            smb.profile_read(kind, reset=True)
+        barrier()
+        t_wall0 = time.time()
+        for s in range(args.steps):
+            smb.add_reads(mhs_k, dev_batches[s % n_batches].data_ptr(), R, READ_LEN, force=False, on_device=True)
+        barrier()
+        windows.append((t_wall0, time.time()))
+        for kind in kinds:
+            kern[kind] = smb.profile_read(kind, reset=True)
+        del mhs_k
+    smb.fuse_multi_k(True)
     smb.profile_enable(False)
-    del mhs_k
     total_bases = sum_over_ranks(float(args.steps * n_bytes))
     value = total_bases / (ms_dev * 1e-3) / 1e9
     md5_dev = [m.md5sum() for m in mhs]
@@ -352,23 +362,24 @@ def run_ours(args):
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
     k31_ms, k31_n = kern["sketch_k31"]
+    km_ms, km_n = kern["sketch_multi"]
     roof = None
     per_k = {}
-    for k, kind in zip(KSIZES, ("sketch_k21", "sketch_k31", "sketch_k51")):
+    for k, kind in zip(KSIZES + ("multi",), ("sketch_k21", "sketch_k31", "sketch_k51", "sketch_multi")):
         ms, n = kern[kind]
         if n:
-            per_k["k%d" % k] = {"launches": n, "avg_ms": ms / n, "gbp_s": args.steps * n_bytes / (ms * 1e-3) / 1e9}
-    if k31_n:
-        bytes_per_launch = args.steps * n_bytes / k31_n  # 1 B (one ASCII base) per window, SURVEY 8(d)
-        achieved = bytes_per_launch / (k31_ms / k31_n * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "sketch_kernel<31>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": DRAM_BYTES_PER_WINDOW[31] * bytes_per_launch,
+            per_k["k%s" % k] = {"launches": n, "avg_ms": ms / n, "gbp_s": args.steps * n_bytes / (ms * 1e-3) / 1e9}
+    if km_n:
+        # the dominant kernel of the timed step is the fused launch: it reads every base once
+        bytes_per_launch = args.steps * n_bytes / km_n  # 1 B (one ASCII base) per window start, SURVEY 8(d)
+        achieved = bytes_per_launch / (km_ms / km_n * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "sketch_kernel<21,31,51>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": DRAM_BYTES_PER_WINDOW["multi"] * bytes_per_launch,
                 "traffic_source": "ncu dram__bytes_read+write per window (profiles/sketch_r1_summary.md) x windows per launch",
                 "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": k31_ms / k31_n,
-                "duration_source": "CUDA events around each launch, second pass of the same K steps with the three "
-                                   "kernels of a step serialized on the library's stream",
-                "note": "HBM is not the binding resource of this kernel: see int_pipe"}
+                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": km_ms / km_n,
+                "duration_source": "CUDA events around each launch on the library's stream, separate pass of the same K steps",
+                "note": "HBM is not the binding resource of this kernel (three MurmurHash3 per byte read): see int_pipe"}
     int_pipe = None
     # ---- all-vs-all compare (cfg3), rows sharded by rank, CSR all-gathered over NCCL -------------------
     compare = None
@@ -397,16 +408,31 @@ def run_ours(args):
         cpu["parity_checked"] = True
 
     clk = clocks.summary(windows)
-    if rank == 0 and k31_n:
-        # integer-issue roofline: 4 warp instructions per clock per SM at the SM clock seen during the run
+    if rank == 0 and km_n:
+        # integer roofline of the fused kernel, two ways: (1) issue slots -- 4 warp instructions per clock
+        # per SM at the SM clock seen during the run; (2) the hash-only ceiling -- MurmurHash3 of
+        # register-resident k-mers and nothing else, measured live (smgpu_int_peak modes 10-12)
         mhz = clk.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
         issue_peak = 4 * 32 * sm_count * mhz * 1e6
-        inst_rate = INSTR_PER_WINDOW[31] * (args.steps * n_bytes) / (k31_ms * 1e-3)
-        int_pipe = {"kernel": "sketch_kernel<31>", "achieved_tinstr_s": inst_rate / 1e12, "peak_tinstr_s": issue_peak / 1e12,
-                    "frac": inst_rate / issue_peak, "instr_per_window": INSTR_PER_WINDOW[31],
+        inst_rate = INSTR_PER_WINDOW["multi"] * (args.steps * n_bytes) / (km_ms * 1e-3)
+        hash_rate = {k: smb.int_peak(mode, 256, sm_count * 8) for mode, k in ((10, 21), (11, 31), (12, 51))}
+        ceiling = 1.0 / sum(1.0 / hash_rate[k] for k in KSIZES)  # windows/s if the three hashes were all there is
+        achieved_w = (args.steps * n_bytes) / (km_ms * 1e-3)
+        int_pipe = {"kernel": "sketch_kernel<21,31,51>", "achieved_tinstr_s": inst_rate / 1e12, "peak_tinstr_s": issue_peak / 1e12,
+                    "frac": inst_rate / issue_peak, "instr_per_window": INSTR_PER_WINDOW["multi"],
                     "peak_source": "4 warp-instr/clk/SM x 32 lanes x %d SMs x %.0f MHz (sampled during the run)" % (sm_count, mhz),
-                    "ncu_alu_pipe_pct": NCU_ALU_PIPE_PCT[31],
-                    "note": "binding resource of the sketch kernel; instruction count from the ncu capture in profiles/"}
+                    "ncu_issue_slots_pct": NCU_ISSUE_PCT["multi"], "ncu_alu_pipe_pct": NCU_ALU_PIPE_PCT["multi"],
+                    "ncu_fmaheavy_pipe_pct": NCU_FMAHEAVY_PIPE_PCT["multi"],
+                    "hash_only_ceiling": {"g_hashes_s": {"k%d" % k: hash_rate[k] / 1e9 for k in KSIZES},
+                                          "fused_gbp_s": ceiling / 1e9, "frac": achieved_w / ceiling,
+                                          "how": "MurmurHash3 x64_128 of register-resident k-mers, no staging / strand "
+                                                 "choice / shared memory (hash_peak_kernel), measured in this run"},
+                    "k31_kernel": {"gbp_s": args.steps * n_bytes / (k31_ms * 1e-3) / 1e9 if k31_n else None,
+                                   "instr_per_window": INSTR_PER_WINDOW[31],
+                                   "issue_frac": (INSTR_PER_WINDOW[31] * (args.steps * n_bytes) / (k31_ms * 1e-3) / issue_peak) if k31_n else None,
+                                   "hash_only_frac": (args.steps * n_bytes / (k31_ms * 1e-3) / hash_rate[31]) if k31_n else None},
+                    "note": "binding resource of the sketch kernels: ALU + FMA-heavy (IMAD) pipes; instruction counts and "
+                            "pipe utilisations from the ncu capture in profiles/"}
     if rank == 0:
         line = {
             "metric": "Gbp/s sketched", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
@@ -481,10 +507,13 @@ def bench_compare(args, smb, torch, dist, dev, rank, world, barrier, max_over_ra
     smb.compare_path("auto")
     # end to end: host CSR in, f64 Jaccard matrix out to pinned host memory
     out = torch.empty((r1 - r0, N), dtype=torch.float64, pin_memory=True)
-    rows_c = np.ascontiguousarray(rows)
+    # inputs in pinned host memory (numpy views of pinned torch buffers), as the sketch arm's are
+    rows_pin = torch.from_numpy(np.ascontiguousarray(rows).view(np.int64).reshape(-1)).pin_memory()
+    offs_pin = torch.from_numpy(np.ascontiguousarray(offsets).view(np.int64)).pin_memory()
+    rows_c, offs_c = rows_pin.numpy().view(np.uint64), offs_pin.numpy().view(np.uint64)
 
     def e2e():
-        coll = smb.SketchCollection.from_csr(rows_c.reshape(-1), offsets, N, NUM, 31, 42, 0, on_device=False)
+        coll = smb.SketchCollection.from_csr(rows_c, offs_c, N, NUM, 31, 42, 0, on_device=False)
         smb._call("smgpu_compare_matrix", coll._p, r0, r1 - r0, coll._p, 0, N, 0, None, None, smb._vp(out.data_ptr()), N, False)
 
     e2e()
@@ -515,7 +544,7 @@ def bench_compare(args, smb, torch, dist, dev, rank, world, barrier, max_over_ra
             "ms_per_step": ms, "steps": steps, "scaling": "strong",
             "kernel_ms_per_step": (kms / kn * (kn / steps)) if kn else None,
             "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(rows_c.nbytes + offsets.nbytes),
+                    "h2d_bytes_per_step": int(rows_c.nbytes + offs_c.nbytes),
                     "d2h_bytes_per_step": int((r1 - r0) * N * 8)},
             "path": "auto: inverted-index join finds the related pairs (here 1% of all), only those are walked",
             "dense_path": {"value": pairs / (ms_dense * 1e-3), "unit": "pairs/s", "ms_per_step": ms_dense,

@@ -206,9 +206,7 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
     launch_popc_words(bitmap, n_words, counts, st);
     scan_exclusive_u64(counts, pre, n_words, ctx.scan_tmp.p, st);
     uint64_t tail[2];
-    SM_CUDA(cudaMemcpyAsync(&tail[0], pre + (n_words - 1), 8, cudaMemcpyDeviceToHost, st));
-    SM_CUDA(cudaMemcpyAsync(&tail[1], counts + (n_words - 1), 8, cudaMemcpyDeviceToHost, st));
-    ctx.sync();
+    ctx.fetch2(pre + (n_words - 1), counts + (n_words - 1), tail);
     const uint64_t n_pairs = tail[0] + tail[1];
     if (n_pairs) {
         ctx.join[5].reserve((n_pairs + 1) * 8);
@@ -232,20 +230,44 @@ void compare_matrix(SketchCollection &rows, uint64_t r0, uint64_t nr, SketchColl
         ctx.sync();
         return;
     }
-    // host output: row blocks of up to 2^28 cells through device scratch, copied back block by block
-    const uint64_t block_rows = std::max<uint64_t>(1, std::min<uint64_t>(nr, (1ull << 28) / nc));
-    ctx.misc[5].reserve(block_rows * nc * 4);
-    ctx.misc[6].reserve(block_rows * nc * 4);
-    ctx.misc[7].reserve(block_rows * nc * 8);
-    for (uint64_t b0 = 0; b0 < nr; b0 += block_rows) {
-        const uint64_t bn = std::min(block_rows, nr - b0);
-        compare_block_device(rows, r0 + b0, bn, cols, c0, nc, mode, common ? ctx.misc[5].as<uint32_t>() : nullptr,
-                             size ? ctx.misc[6].as<uint32_t>() : nullptr, ratio ? ctx.misc[7].as<double>() : nullptr, nc);
-        if (common) SM_CUDA(cudaMemcpy2DAsync(common + b0 * ld, ld * 4, ctx.misc[5].p, nc * 4, nc * 4, bn, cudaMemcpyDeviceToHost, st));
-        if (size) SM_CUDA(cudaMemcpy2DAsync(size + b0 * ld, ld * 4, ctx.misc[6].p, nc * 4, nc * 4, bn, cudaMemcpyDeviceToHost, st));
-        if (ratio) SM_CUDA(cudaMemcpy2DAsync(ratio + b0 * ld, ld * 8, ctx.misc[7].p, nc * 8, nc * 8, bn, cudaMemcpyDeviceToHost, st));
-        ctx.sync();
+    // host output: row blocks of up to 2^25 cells through two sets of device scratch; the copy of
+    // block b back to the host (copy stream) overlaps the kernels of block b + 1 (library stream)
+    const uint64_t block_rows = std::max<uint64_t>(1, std::min<uint64_t>(nr, (1ull << 25) / nc));
+    DevBuf *bc[2] = {&ctx.misc[5], &ctx.misc[2]}, *bs[2] = {&ctx.misc[6], &ctx.misc[3]}, *br[2] = {&ctx.misc[7], &ctx.misc[4]};
+    const int n_sets = nr > block_rows ? 2 : 1;
+    for (int k = 0; k < n_sets; k++) {
+        if (common) bc[k]->reserve(block_rows * nc * 4);
+        if (size) bs[k]->reserve(block_rows * nc * 4);
+        if (ratio) br[k]->reserve(block_rows * nc * 8);
     }
+    static cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    for (int k = 0; k < 2; k++) {
+        if (!ev_done[k]) SM_CUDA(cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming));
+        if (!ev_free[k]) SM_CUDA(cudaEventCreateWithFlags(&ev_free[k], cudaEventDisableTiming));
+    }
+    cudaStream_t cs = ctx.copy_stream;
+    auto copy_back = [&](void *dst, uint64_t dst_ld_bytes, const void *src, uint64_t row_bytes, uint64_t n_rows_blk) {
+        if (dst_ld_bytes == row_bytes)  // contiguous: one linear copy
+            SM_CUDA(cudaMemcpyAsync(dst, src, row_bytes * n_rows_blk, cudaMemcpyDeviceToHost, cs));
+        else
+            SM_CUDA(cudaMemcpy2DAsync(dst, dst_ld_bytes, src, row_bytes, row_bytes, n_rows_blk, cudaMemcpyDeviceToHost, cs));
+    };
+    uint64_t blk = 0;
+    for (uint64_t b0 = 0; b0 < nr; b0 += block_rows, blk++) {
+        const uint64_t bn = std::min(block_rows, nr - b0);
+        const int k = (int)(blk & 1);
+        if (blk >= 2) SM_CUDA(cudaStreamWaitEvent(st, ev_free[k], 0));  // this set's previous copy has left
+        compare_block_device(rows, r0 + b0, bn, cols, c0, nc, mode, common ? bc[k]->as<uint32_t>() : nullptr,
+                             size ? bs[k]->as<uint32_t>() : nullptr, ratio ? br[k]->as<double>() : nullptr, nc);
+        SM_CUDA(cudaEventRecord(ev_done[k], st));
+        SM_CUDA(cudaStreamWaitEvent(cs, ev_done[k], 0));
+        if (common) copy_back(common + b0 * ld, ld * 4, bc[k]->p, nc * 4, bn);
+        if (size) copy_back(size + b0 * ld, ld * 4, bs[k]->p, nc * 4, bn);
+        if (ratio) copy_back(ratio + b0 * ld, ld * 8, br[k]->p, nc * 8, bn);
+        SM_CUDA(cudaEventRecord(ev_free[k], cs));
+    }
+    SM_CUDA(cudaStreamSynchronize(cs));
+    ctx.sync();
 }
 
 // Leaf-pairing pass of scaffold (src/index/sbt.rs:356-381).  The reference runs count_common of the

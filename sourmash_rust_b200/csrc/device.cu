@@ -108,6 +108,7 @@ Context &Context::get() {
     SM_CUDA(cudaMalloc(&c->d_scalars, SC_COUNT * sizeof(unsigned long long)));
     SM_CUDA(cudaMemset(c->d_scalars, 0, SC_COUNT * sizeof(unsigned long long)));
     SM_CUDA(cudaMallocHost(&c->h_scalars, SC_COUNT * sizeof(unsigned long long)));
+    SM_CUDA(cudaMallocHost(&c->h_fetch, 2 * sizeof(unsigned long long)));
     g_ctx = c;
     return *g_ctx;
 }
@@ -167,9 +168,28 @@ void Context::set_scalar(int idx, unsigned long long v) {
     SM_CUDA(cudaMemcpyAsync(d_scalars + idx, h_scalars + idx, sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
     SM_CUDA(cudaStreamSynchronize(stream));
 }
+// Small device -> host reads go through a one-warp kernel that stores into pinned (UVA-mapped) host
+// memory instead of a cudaMemcpy: a memcpy queues on the device-to-host copy engine behind whatever
+// large read-back is in flight on another stream (the compare matrix), a kernel store does not.
+__global__ void scalars_to_host_kernel(const unsigned long long *src, unsigned long long *dst, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+__global__ void fetch2_kernel(const unsigned long long *a, const unsigned long long *b, unsigned long long *dst) {
+    if (threadIdx.x == 0) dst[0] = *a;
+    if (threadIdx.x == 1) dst[1] = *b;
+}
 void Context::read_scalars() {
-    SM_CUDA(cudaMemcpyAsync(h_scalars, d_scalars, SC_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    scalars_to_host_kernel<<<1, 32, 0, stream>>>(d_scalars, h_scalars, SC_COUNT);
+    SM_LAUNCHED();
     SM_CUDA(cudaStreamSynchronize(stream));
+}
+void Context::fetch2(const void *a, const void *b, uint64_t out[2]) {
+    fetch2_kernel<<<1, 32, 0, stream>>>(static_cast<const unsigned long long *>(a), static_cast<const unsigned long long *>(b),
+                                        h_fetch);
+    SM_LAUNCHED();
+    SM_CUDA(cudaStreamSynchronize(stream));
+    out[0] = h_fetch[0];
+    out[1] = h_fetch[1];
 }
 
 }  // namespace smb200

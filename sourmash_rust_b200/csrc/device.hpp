@@ -106,6 +106,8 @@ struct Context {
     void sync() { SM_CUDA(cudaStreamSynchronize(stream)); }
     void set_scalar(int idx, unsigned long long v);  // synchronous
     void read_scalars();                              // d_scalars -> h_scalars, synchronous
+    void fetch2(const void *a, const void *b, uint64_t out[2]);  // two device u64 -> host, synchronous, no copy engine
+    unsigned long long *h_fetch = nullptr;
     unsigned long long *dsc(int idx) { return d_scalars + idx; }
 };
 // Per-kernel device timing (CUDA events on the launching stream), off unless enabled through

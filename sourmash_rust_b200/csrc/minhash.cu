@@ -533,7 +533,11 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
     size_t ev_i = 0;
     do {
         if (!batch.on_device) {
-            const uint64_t len = std::min<uint64_t>(chunk, n - copied);
+            // ... and taper off again (half of what is left, not below 2 MiB): what remains after the
+            // last copy has landed is the kernel of the last chunk only
+            const uint64_t left = n - copied;
+            uint64_t len = std::min<uint64_t>(chunk, left);
+            if (left > (2ull << 20)) len = std::min<uint64_t>(len, std::max<uint64_t>((left / 2 + 4095) & ~4095ull, 2ull << 20));
             chunk = std::min<uint64_t>(chunk * 2, CHUNK_MAX);
             SM_CUDA(cudaMemcpyAsync(const_cast<uint8_t *>(d_buf) + copied, batch.buf + copied, len, cudaMemcpyHostToDevice,
                                     ctx.copy_stream));

@@ -5,6 +5,7 @@
 // replay used for non-standard parameter combinations.
 #include "device.hpp"
 #include "kernels.cuh"
+#include "murmur3.cuh"
 
 namespace smb200 {
 
@@ -539,7 +540,35 @@ __global__ void __launch_bounds__(256) int_peak2_kernel(uint32_t *out, int iters
     for (int j = 0; j < 8; j++) r ^= a[j] ^ b[j] ^ (uint32_t)w[j] ^ (uint32_t)(w[j] >> 32);
     if (r == 0x12345678u) out[0] = r;  // keep the chains alive
 }
+// Mode 10/11/12: MurmurHash3 x64_128 of a K = 21 / 31 / 51 byte k-mer held in registers, nothing else
+// (no staging, no strand choice, no shared memory): the hash-only ceiling of the sketch kernel.
+// One "instruction" in the returned count = one hash (iters * 64 hashes per thread).
+template <int K>
+__global__ void __launch_bounds__(256, 8) hash_peak_kernel(uint32_t *out, int iters, uint32_t m, uint64_t seed) {
+    constexpr int NW = (K + 3) / 4;
+    uint32_t w[NW];
+#pragma unroll
+    for (int j = 0; j < NW; j++) w[j] = (threadIdx.x + blockIdx.x * 256u) * 0x9E3779B9u + j * m;
+    w[NW - 1] &= (K % 4) ? ((1u << ((K % 4) * 8)) - 1u) : 0xFFFFFFFFu;
+    uint64_t acc = 0;
+    for (int i = 0; i < iters * 64; i++) {
+        const uint64_t h = murmur3_h1_words<K>(w, seed);
+        acc ^= h;
+#pragma unroll
+        for (int j = 0; j < NW - 1; j++) w[j] += m + j;  // next k-mer: every word changes (NW - 1 extra adds per hash)
+        w[NW - 1] = (w[NW - 1] + m) & ((K % 4) ? ((1u << ((K % 4) * 8)) - 1u) : 0xFFFFFFFFu);
+    }
+    if (acc == 0x12345678u) out[0] = (uint32_t)acc;
+}
 void launch_int_peak(uint32_t *out, int iters, int blocks, int mode, cudaStream_t st) {
+    if (mode >= 10 && mode <= 12) {
+        const uint32_t mm = 0x01000193u | (uint32_t)blocks;
+        if (mode == 10) hash_peak_kernel<21><<<blocks, 256, 0, st>>>(out, iters, mm, 42);
+        if (mode == 11) hash_peak_kernel<31><<<blocks, 256, 0, st>>>(out, iters, mm, 42);
+        if (mode == 12) hash_peak_kernel<51><<<blocks, 256, 0, st>>>(out, iters, mm, 42);
+        SM_LAUNCHED();
+        return;
+    }
     const uint32_t m = 0x01000193u | (uint32_t)blocks, c = 0x9E3779B9u;  // opaque to the compiler
     switch (mode) {
     case 3: int_peak2_kernel<3><<<blocks, 256, 0, st>>>(out, iters, m, c); break;

@@ -14,3 +14,8 @@ for mode, (what, per_sweep) in spec.items():
         r = smb.int_peak(mode, 4096, blocks) * (4 * per_sweep) / 64.0
         print("mode %d (%s) blocks %d: %.2f T thread-instr/s = %.1f thread-instr/clk/SM at 1965 MHz" %
               (mode, what, blocks, r / 1e12, r / 1.965e9 / sms))
+
+# hash-only ceiling: smgpu_int_peak counts iters * 64 * 256 * blocks "instructions" = hashes
+for mode, k in ((10, 21), (11, 31), (12, 51)):
+    r = smb.int_peak(mode, 256, sms * 8)
+    print("mode %d (MurmurHash3 x64_128 of %d register-resident bytes only): %.1f G hashes/s" % (mode, k, r / 1e9))

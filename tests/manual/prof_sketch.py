@@ -11,6 +11,11 @@ g = torch.Generator(device=dev); g.manual_seed(7)
 genome = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)[torch.randint(0, 4, (20_000_000,), generator=g, device=dev)]
 reads = torch_reads(genome, R, 11, dev)
 mhs = [smb.KmerMinHash(0, k, False, 42, MAX_HASH_1000, True) for k in (21, 31, 51)]
+# launches 1-9: three passes with one kernel per k-size; launches 10-12: three passes of the fused kernel
+smb.fuse_multi_k(False)
+for i in range(3):
+    smb.add_reads(mhs, reads.data_ptr(), R, 150, force=False, on_device=True)
+smb.fuse_multi_k(True)
 for i in range(3):
     smb.add_reads(mhs, reads.data_ptr(), R, 150, force=False, on_device=True)
 print([m.size() for m in mhs])
