@@ -33,6 +33,9 @@ namespace smb200 {
 #ifndef SK_UNROLL
 #define SK_UNROLL 4   // windows per trip of the k-mer loop (SK_TILE / SK_THREADS must be a multiple)
 #endif
+#ifndef SK_UNROLL_FUSED
+#define SK_UNROLL_FUSED 2
+#endif
 #ifndef SK_MIN_CTAS
 #define SK_MIN_CTAS SK_CTAS_PER_SM
 #endif
@@ -255,7 +258,7 @@ __device__ __forceinline__ void append_survivor(bool pass, uint64_t h, uint64_t 
 //   8 * (i & 3); rc(window i) starts at base B - K - i of the reverse-complement views, and rA
 //   sits (B + 8) bytes after fA (carve_tile), so one base pointer serves both ASCII strands.
 //   SK_THREADS is a multiple of 32, so the r-dependence is a pure word offset.
-template <int K, int B>
+template <int K, int B, int UNROLL>
 __device__ __forceinline__ void kmer_loop(const TileViews &v, const uint32_t *sbad, const uint64_t thr, const uint64_t t0,
                                           const SketchBatch &sb, const SketchOut &out) {
     using G = KmerGeom<K>;
@@ -271,11 +274,11 @@ __device__ __forceinline__ void kmer_loop(const TileViews &v, const uint32_t *sb
     const uint32_t *qsb = sbad + (tid >> 5);
     uint32_t mb = 1u << (tid & 31);
     asm("" : "+r"(mb));  // opaque: keeps the validity test a single LOP3 against a resident mask
-    // running word pointers: stepped once per SK_UNROLL windows, constant offsets inside
+    // running word pointers: stepped once per UNROLL windows, constant offsets inside
 #pragma unroll 1
-    for (int r = 0; r < SK_TILE / SK_THREADS; r += SK_UNROLL) {
+    for (int r = 0; r < SK_TILE / SK_THREADS; r += UNROLL) {
 #pragma unroll
-        for (int u = 0; u < SK_UNROLL; u++) {
+        for (int u = 0; u < UNROLL; u++) {
             const bool valid = (qsb[u * (SK_THREADS / 32)] & mb) == 0;
             uint32_t ef[G::NE], er[G::NE];
             extract2_end<K>(qf2 + u * (SK_THREADS / 16), sf2, ef);
@@ -287,9 +290,9 @@ __device__ __forceinline__ void kmer_loop(const TileViews &v, const uint32_t *sb
             const uint64_t h = murmur3_h1_words<K>(kw, sb.seed);
             append_survivor(valid && h <= thr, h, t0 + (uint32_t)((r + u) * SK_THREADS), sb, out);
         }
-        qf2 += SK_UNROLL * (SK_THREADS / 16); qr2 -= SK_UNROLL * (SK_THREADS / 16);
-        qfa += SK_UNROLL * (SK_THREADS / 4);  qra -= SK_UNROLL * (SK_THREADS / 4);
-        qsb += SK_UNROLL * (SK_THREADS / 32);
+        qf2 += UNROLL * (SK_THREADS / 16); qr2 -= UNROLL * (SK_THREADS / 16);
+        qfa += UNROLL * (SK_THREADS / 4);  qra -= UNROLL * (SK_THREADS / 4);
+        qsb += UNROLL * (SK_THREADS / 32);
     }
 }
 
@@ -353,9 +356,12 @@ __global__ void __launch_bounds__(SK_THREADS, SK_MIN_CTAS) sketch_kernel(const S
         if (KB) build_start_bitmap(v, v.sbad + SK_TILE / 32, KB, t0, sb, outs.first_bad[1]);
         if (KC) build_start_bitmap(v, v.sbad + 2 * (SK_TILE / 32), KC, t0, sb, outs.first_bad[2]);
         __syncthreads();
-        kmer_loop<KA, B>(v, v.sbad, thrA, t0, sb, outs.o[0]);
-        if (KB) kmer_loop<(KB ? KB : KA), B>(v, v.sbad + SK_TILE / 32, thrB, t0, sb, outs.o[1]);
-        if (KC) kmer_loop<(KC ? KC : KA), B>(v, v.sbad + 2 * (SK_TILE / 32), thrC, t0, sb, outs.o[2]);
+        // (the fused forms unroll less: three loops unrolled by four no longer fit the instruction cache --
+        // ncu showed 11 % `no instruction` stalls)
+        constexpr int U = KB ? SK_UNROLL_FUSED : SK_UNROLL;
+        kmer_loop<KA, B, U>(v, v.sbad, thrA, t0, sb, outs.o[0]);
+        if (KB) kmer_loop<(KB ? KB : KA), B, U>(v, v.sbad + SK_TILE / 32, thrB, t0, sb, outs.o[1]);
+        if (KC) kmer_loop<(KC ? KC : KA), B, U>(v, v.sbad + 2 * (SK_TILE / 32), thrC, t0, sb, outs.o[2]);
         if (tid == 0) s_next = after_next;
         __syncthreads();  // views are rebuilt by the next tile
         tile = next;
