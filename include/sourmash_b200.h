@@ -124,6 +124,53 @@ void smgpu_fuse_multi_k(bool on);
 uint64_t smgpu_linear_find(SketchCollection *index, SketchCollection *queries, int32_t mode, double threshold,
                            uint64_t *hit_offsets, uint64_t *hits, uint64_t hits_cap);
 
+/* ---- Nodegraph (khmer bloom filter) and SBT search: src/index/nodegraph.rs, src/index/sbt.rs ------ */
+/* The reference keeps these behind its Rust API only (no extern "C" in src/ffi.rs); the functions
+ * below give them the same C-ABI shape as the rest of this header.  Bitsets live in HBM. */
+typedef struct Nodegraph Nodegraph;
+/* Nodegraph::new(tablesizes, ksize) (nodegraph.rs:20-32); at most 255 tables */
+Nodegraph *smgpu_nodegraph_new(const uint64_t *tablesizes, uintptr_t n_tables, uint64_t ksize);
+void smgpu_nodegraph_free(Nodegraph *ng);
+/* Nodegraph::from_reader over a khmer "OXLI" version-4 Nodegraph file image (nodegraph.rs:135-181);
+ * a failed assertion / short read records a Panic error */
+Nodegraph *smgpu_nodegraph_from_buffer(const uint8_t *data, uintptr_t len);
+/* Nodegraph::save_to_writer (nodegraph.rs:99-133): returns the number of bytes of the file image and
+ * writes it when cap is large enough */
+uintptr_t smgpu_nodegraph_save(Nodegraph *ng, uint8_t *out, uintptr_t cap);
+/* for i in 0..n: is_new[i] = ng.count(hashes[i]) (nodegraph.rs:34-50), in that order -- a bin set by an
+ * earlier hash of the batch is not new for a later one.  Returns the number of new k-mers;
+ * is_new may be NULL. */
+uint64_t smgpu_nodegraph_count_many(Nodegraph *ng, const uint64_t *hashes /*[host|device]*/, uint64_t n,
+                                    uint8_t *is_new /*[host|device]*/, bool on_device);
+/* sum over i of ng.get(hashes[i]) (nodegraph.rs:52-60); present[i] = that value, may be NULL */
+uint64_t smgpu_nodegraph_get_many(Nodegraph *ng, const uint64_t *hashes /*[host|device]*/, uint64_t n,
+                                  uint8_t *present /*[host|device]*/, bool on_device);
+/* sum of ng.get(h) over the sketch's mins: the numerator of Node<Nodegraph> x Leaf<Signature>
+ * similarity / containment (sbt.rs:245,266) */
+uint64_t smgpu_nodegraph_matches(Nodegraph *ng, KmerMinHash *mh);
+/* Nodegraph::update (nodegraph.rs:63-91): ng |= other, table by table */
+void smgpu_nodegraph_update(Nodegraph *ng, Nodegraph *other);
+/* Nodegraph::similarity / containment (nodegraph.rs:199-224) */
+double smgpu_nodegraph_similarity(Nodegraph *ng, Nodegraph *other);
+double smgpu_nodegraph_containment(Nodegraph *ng, Nodegraph *other);
+/* tablesizes() into out (capacity cap); returns the number of tables */
+uintptr_t smgpu_nodegraph_tablesizes(Nodegraph *ng, uint64_t *out, uintptr_t cap);
+uint64_t smgpu_nodegraph_ksize(Nodegraph *ng);
+uint64_t smgpu_nodegraph_n_occupied_bins(Nodegraph *ng);
+uint64_t smgpu_nodegraph_unique_kmers(Nodegraph *ng);
+/* SBT::find (sbt.rs:147-175) for every row of `queries`, with search_minhashes (mode 0) or
+ * search_minhashes_containment (mode 1) (search.rs:3-9).  The tree is given by position (root 0,
+ * children of p at d*p+1 .. d*p+d): internal node i sits at node_positions[i] with bloom filter
+ * nodes[i] and metadata min_n_below[i]; leaf i (row i of `leaves`) at leaf_positions[i].
+ * Internal nodes compare as sbt.rs:233-277 (matches / min_n_below, matches / |query|), leaves as
+ * index.rs:131-160.  hit_offsets (n_queries + 1, host) / hits (host, capacity hits_cap) receive, per
+ * query, the POSITIONS of the matching leaves in the order the reference's depth-first walk
+ * reaches them.  Returns the total number of hits. */
+uint64_t smgpu_sbt_find(uint32_t d, const uint64_t *node_positions, Nodegraph *const *nodes, const uint64_t *min_n_below,
+                        uint64_t n_nodes, const uint64_t *leaf_positions, SketchCollection *leaves,
+                        SketchCollection *queries, int32_t mode, double threshold, uint64_t *hit_offsets, uint64_t *hits,
+                        uint64_t hits_cap);
+
 #ifdef __cplusplus
 }
 #endif

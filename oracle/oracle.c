@@ -718,3 +718,227 @@ char *orc_signature_json(const char *name, const char *filename, OrcMinHash *con
     return s.p;
 }
 void orc_free(void *p) { free(p); }
+
+/* ===========================================================================================
+ * Nodegraph (khmer bloom filter) -- src/index/nodegraph.rs:11-225 -- and SBT::find
+ * (src/index/sbt.rs:147-175) with the Node<Nodegraph> x Leaf<Signature> comparisons
+ * (src/index/sbt.rs:233-277).  SURVEY 8(f) rank 3.  FixedBitSet = u32 blocks, bit i at block i / 32,
+ * bit i % 32.
+ * =========================================================================================== */
+typedef struct OrcNodegraph {
+    size_t n_tables;
+    size_t *len;       /* bits per table */
+    uint32_t **bs;     /* ceil(len / 32) blocks per table */
+    size_t ksize, occupied_bins, unique_kmers;
+} OrcNodegraph;
+
+/* Nodegraph::new, nodegraph.rs:20-32 */
+OrcNodegraph *orc_ng_new(const uint64_t *tablesizes, size_t n_tables, size_t ksize) {
+    OrcNodegraph *ng = (OrcNodegraph *)calloc(1, sizeof *ng);
+    ng->n_tables = n_tables;
+    ng->len = (size_t *)calloc(n_tables ? n_tables : 1, sizeof(size_t));
+    ng->bs = (uint32_t **)calloc(n_tables ? n_tables : 1, sizeof(uint32_t *));
+    for (size_t t = 0; t < n_tables; t++) {
+        ng->len[t] = (size_t)tablesizes[t];
+        ng->bs[t] = (uint32_t *)calloc((ng->len[t] + 31) / 32 + 1, sizeof(uint32_t));
+    }
+    ng->ksize = ksize;
+    return ng;
+}
+void orc_ng_free(OrcNodegraph *ng) {
+    if (!ng) return;
+    for (size_t t = 0; t < ng->n_tables; t++) free(ng->bs[t]);
+    free(ng->bs); free(ng->len); free(ng);
+}
+static int ng_put(uint32_t *bs, size_t bit) { /* FixedBitSet::put: sets, returns the previous value */
+    const uint32_t m = 1u << (bit & 31);
+    const int prev = (bs[bit >> 5] & m) != 0;
+    bs[bit >> 5] |= m;
+    return prev;
+}
+/* Nodegraph::count, nodegraph.rs:34-50 */
+int orc_ng_count(OrcNodegraph *ng, uint64_t hash) {
+    int is_new = 0;
+    for (size_t t = 0; t < ng->n_tables; t++) {
+        const uint64_t bin = hash % (uint64_t)ng->len[t];
+        if (!ng_put(ng->bs[t], (size_t)bin)) { ng->occupied_bins += 1; is_new = 1; }
+    }
+    if (is_new) ng->unique_kmers += 1;
+    return is_new;
+}
+/* Nodegraph::get, nodegraph.rs:52-60 */
+size_t orc_ng_get(const OrcNodegraph *ng, uint64_t hash) {
+    for (size_t t = 0; t < ng->n_tables; t++) {
+        const uint64_t bin = hash % (uint64_t)ng->len[t];
+        if (!(ng->bs[t][bin >> 5] & (1u << (bin & 31)))) return 0;
+    }
+    return 1;
+}
+/* Nodegraph::update, nodegraph.rs:63-91 (occupied_bins deliberately not updated there).
+ * Returns -1 where the reference would panic (a set bit of `other` beyond self's table). */
+int orc_ng_update(OrcNodegraph *ng, const OrcNodegraph *other) {
+    const size_t nt = ng->n_tables < other->n_tables ? ng->n_tables : other->n_tables; /* zip */
+    for (size_t t = 0; t < nt; t++)
+        for (size_t x = 0; x < other->len[t]; x++)
+            if (other->bs[t][x >> 5] & (1u << (x & 31))) {
+                if (x >= ng->len[t]) return -1;
+                ng_put(ng->bs[t], x);
+            }
+    return 0;
+}
+/* Nodegraph::save_to_writer, nodegraph.rs:99-133; returns the byte count, writes when it fits */
+size_t orc_ng_save(const OrcNodegraph *ng, uint8_t *out, size_t cap) {
+    size_t n = 0;
+#define NG_PUT8(v) do { if (n < cap) out[n] = (uint8_t)(v); n++; } while (0)
+#define NG_PUTLE(v, bytes) do { uint64_t _v = (uint64_t)(v); for (int _b = 0; _b < (bytes); _b++) NG_PUT8(_v >> (8 * _b)); } while (0)
+    NG_PUT8('O'); NG_PUT8('X'); NG_PUT8('L'); NG_PUT8('I');
+    NG_PUT8(4);                         /* version */
+    NG_PUT8(2);                         /* ht_type */
+    NG_PUTLE(ng->ksize, 4);
+    NG_PUT8(ng->n_tables);
+    NG_PUTLE(ng->occupied_bins, 8);
+    for (size_t t = 0; t < ng->n_tables; t++) {
+        const size_t len = ng->len[t], blocks = (len + 31) / 32;
+        NG_PUTLE(len, 8);
+        for (size_t i = 0; i < blocks; i++) {
+            const uint32_t chunk = ng->bs[t][i];
+            const size_t next = (i + 1) * 32;
+            if (next <= len) {
+                NG_PUTLE(chunk, 4);
+            } else {
+                const size_t rem = len - i * 32;
+                const size_t remainder = (rem % 8 != 0) ? rem / 8 + 1 : rem / 8;
+                if (remainder == 0) NG_PUT8(0);
+                else for (size_t pos = 0; pos < remainder; pos++) NG_PUT8((chunk >> (pos * 8)) & 0xff);
+            }
+        }
+    }
+#undef NG_PUT8
+#undef NG_PUTLE
+    return n;
+}
+/* Nodegraph::from_reader, nodegraph.rs:135-181; NULL where the reference's asserts / reads fail */
+OrcNodegraph *orc_ng_load(const uint8_t *d, size_t n) {
+    size_t p = 0;
+    if (n < 19) return NULL;
+    if (!(d[0] == 0x4f && d[1] == 0x58 && d[2] == 0x4c && d[3] == 0x49)) return NULL;
+    if (d[4] != 0x04 || d[5] != 0x02) return NULL;
+    const uint32_t ksize = (uint32_t)d[6] | ((uint32_t)d[7] << 8) | ((uint32_t)d[8] << 16) | ((uint32_t)d[9] << 24);
+    const size_t n_tables = d[10];
+    uint64_t occ = 0;
+    for (int b = 0; b < 8; b++) occ |= (uint64_t)d[11 + b] << (8 * b);
+    p = 19;
+    uint64_t *sizes = (uint64_t *)calloc(n_tables ? n_tables : 1, sizeof(uint64_t));
+    /* first pass over the table headers to size the bitsets */
+    size_t q = p;
+    for (size_t t = 0; t < n_tables; t++) {
+        if (q + 8 > n) { free(sizes); return NULL; }
+        uint64_t ts = 0;
+        for (int b = 0; b < 8; b++) ts |= (uint64_t)d[q + b] << (8 * b);
+        sizes[t] = ts;
+        q += 8 + (size_t)(ts / 8 + 1);
+        if (q > n) { free(sizes); return NULL; }
+    }
+    OrcNodegraph *ng = orc_ng_new(sizes, n_tables, ksize);
+    free(sizes);
+    for (size_t t = 0; t < n_tables; t++) {
+        const size_t tablesize = ng->len[t], byte_size = tablesize / 8 + 1;
+        p += 8;
+        for (size_t pos = 0; pos < byte_size; pos++) {
+            const uint8_t byte = d[p++];
+            if (byte == 0) continue;
+            for (unsigned i = 0; i < 8; i++)
+                if (byte & (1u << i)) {
+                    const size_t bit = pos * 8 + i;
+                    if (bit >= tablesize) { orc_ng_free(ng); return NULL; } /* FixedBitSet::insert panics */
+                    ng->bs[t][bit >> 5] |= 1u << (bit & 31);
+                }
+        }
+    }
+    ng->occupied_bins = (size_t)occ;
+    ng->unique_kmers = 0; /* "a khmer issue, it doesn't save unique_kmers" */
+    return ng;
+}
+size_t orc_ng_n_tables(const OrcNodegraph *ng) { return ng->n_tables; }
+uint64_t orc_ng_tablesize(const OrcNodegraph *ng, size_t t) { return ng->len[t]; }
+size_t orc_ng_ksize(const OrcNodegraph *ng) { return ng->ksize; }
+size_t orc_ng_occupied_bins(const OrcNodegraph *ng) { return ng->occupied_bins; }
+size_t orc_ng_unique_kmers(const OrcNodegraph *ng) { return ng->unique_kmers; }
+const uint32_t *orc_ng_blocks(const OrcNodegraph *ng, size_t t) { return ng->bs[t]; }
+static void ng_and_or_counts(const OrcNodegraph *a, const OrcNodegraph *b, size_t *n_and, size_t *n_or) {
+    /* FixedBitSet::intersection / union walk the set bits of the operands; over tables of equal
+     * length that is a popcount of AND / OR (bits beyond len are never set) */
+    const size_t nt = a->n_tables < b->n_tables ? a->n_tables : b->n_tables;
+    *n_and = 0; *n_or = 0;
+    for (size_t t = 0; t < nt; t++) {
+        const size_t ba = (a->len[t] + 31) / 32, bb = (b->len[t] + 31) / 32, lo = ba < bb ? ba : bb;
+        for (size_t i = 0; i < lo; i++) {
+            *n_and += (size_t)__builtin_popcount(a->bs[t][i] & b->bs[t][i]);
+            *n_or += (size_t)__builtin_popcount(a->bs[t][i] | b->bs[t][i]);
+        }
+        for (size_t i = lo; i < ba; i++) *n_or += (size_t)__builtin_popcount(a->bs[t][i]);
+        for (size_t i = lo; i < bb; i++) *n_or += (size_t)__builtin_popcount(b->bs[t][i]);
+    }
+}
+/* Nodegraph::similarity, nodegraph.rs:199-213 */
+double orc_ng_similarity(const OrcNodegraph *a, const OrcNodegraph *b) {
+    size_t x, u;
+    ng_and_or_counts(a, b, &x, &u);
+    return (double)x / (double)u;
+}
+/* Nodegraph::containment, nodegraph.rs:215-224: the denominator is the total table LENGTH of self */
+double orc_ng_containment(const OrcNodegraph *a, const OrcNodegraph *b) {
+    size_t x, u, size = 0;
+    ng_and_or_counts(a, b, &x, &u);
+    for (size_t t = 0; t < a->n_tables; t++) size += a->len[t];
+    return (double)x / (double)size;
+}
+/* sum of get(h) over a sketch's mins: the numerator of Node<Nodegraph> x Leaf<Signature>, sbt.rs:245,266 */
+uint64_t orc_ng_matches(const OrcNodegraph *ng, const OrcMinHash *mh) {
+    uint64_t m = 0;
+    for (size_t i = 0; i < mh->mins.len; i++) m += orc_ng_get(ng, mh->mins.p[i]);
+    return m;
+}
+/* Comparable<Leaf<Signature>> for Node<Nodegraph>, sbt.rs:233-277 */
+double orc_node_similarity(const OrcNodegraph *ng, uint64_t min_n_below, const OrcMinHash *query) {
+    if (query->mins.len == 0) return 0.0;
+    return (double)orc_ng_matches(ng, query) / (double)min_n_below;
+}
+double orc_node_containment(const OrcNodegraph *ng, const OrcMinHash *query) {
+    if (query->mins.len == 0) return 0.0;
+    return (double)orc_ng_matches(ng, query) / (double)query->mins.len;
+}
+/* SBT::find, sbt.rs:147-175, with search_minhashes (mode 0) / search_minhashes_containment (mode 1),
+ * search.rs:3-9.  Nodes and leaves are given by tree position; hits_pos receives the positions of the
+ * matching leaves in the order the depth-first walk meets them (children are pushed 0..d-1 and popped
+ * from the back, so the LAST child is visited first). */
+size_t orc_sbt_find(uint32_t d, const uint64_t *node_pos, OrcNodegraph *const *nodes, const uint64_t *min_n_below,
+                    size_t n_nodes, const uint64_t *leaf_pos, OrcMinHash *const *leaves, size_t n_leaves,
+                    const OrcMinHash *query, int mode, double threshold, uint64_t *hits_pos) {
+    size_t n_hits = 0, cap = 64, top = 0;
+    uint64_t *stack = (uint64_t *)malloc(cap * sizeof(uint64_t));
+    stack[top++] = 0;
+    while (top) {
+        const uint64_t pos = stack[--top];
+        /* positions are unique in a d-ary heap layout, so the reference's `visited` set never fires */
+        size_t ni = n_nodes, li = n_leaves;
+        for (size_t i = 0; i < n_nodes; i++) if (node_pos[i] == pos) { ni = i; break; }
+        if (ni < n_nodes) {
+            const double v = mode ? orc_node_containment(nodes[ni], query) : orc_node_similarity(nodes[ni], min_n_below[ni], query);
+            if (v > threshold) {
+                for (uint32_t c = 0; c < d; c++) {
+                    if (top == cap) { cap *= 2; stack = (uint64_t *)realloc(stack, cap * sizeof(uint64_t)); }
+                    stack[top++] = (uint64_t)d * pos + c + 1;
+                }
+            }
+            continue;
+        }
+        for (size_t i = 0; i < n_leaves; i++) if (leaf_pos[i] == pos) { li = i; break; }
+        if (li < n_leaves) {
+            const double v = mode ? orc_leaf_containment(leaves[li], query) : orc_leaf_similarity(leaves[li], query);
+            if (v > threshold) hits_pos[n_hits++] = pos;
+        }
+    }
+    free(stack);
+    return n_hits;
+}

@@ -66,6 +66,25 @@ def lib():
             "orc_free": (None, [vp]),
             "orc_mt_sketch_reads": (None, [C.c_char_p, sz, sz, C.POINTER(u32), i, u32, u64, i, i, C.POINTER(vp)]),
             "orc_mt_compare_matrix": (None, [C.POINTER(vp), sz, C.POINTER(vp), sz, vp, vp, i]),
+            "orc_ng_new": (vp, [C.POINTER(u64), sz, sz]),
+            "orc_ng_free": (None, [vp]),
+            "orc_ng_count": (i, [vp, u64]),
+            "orc_ng_get": (sz, [vp, u64]),
+            "orc_ng_update": (i, [vp, vp]),
+            "orc_ng_save": (sz, [vp, C.c_char_p, sz]),
+            "orc_ng_load": (vp, [C.c_char_p, sz]),
+            "orc_ng_n_tables": (sz, [vp]),
+            "orc_ng_tablesize": (u64, [vp, sz]),
+            "orc_ng_ksize": (sz, [vp]),
+            "orc_ng_occupied_bins": (sz, [vp]),
+            "orc_ng_unique_kmers": (sz, [vp]),
+            "orc_ng_similarity": (C.c_double, [vp, vp]),
+            "orc_ng_containment": (C.c_double, [vp, vp]),
+            "orc_ng_matches": (u64, [vp, vp]),
+            "orc_node_similarity": (C.c_double, [vp, u64, vp]),
+            "orc_node_containment": (C.c_double, [vp, vp]),
+            "orc_sbt_find": (sz, [u32, C.POINTER(u64), C.POINTER(vp), C.POINTER(u64), sz, C.POINTER(u64), C.POINTER(vp), sz,
+                                  vp, i, C.c_double, C.POINTER(u64)]),
         }
         for name, (res, args) in sig.items():
             f = getattr(L, name)
@@ -277,3 +296,88 @@ def mt_sketch_reads(buf: bytes, nreads, readlen, ksizes, num, max_hash, track_ab
     out = (C.c_void_p * len(ksizes))()
     L.orc_mt_sketch_reads(buf, nreads, readlen, ks, len(ksizes), num, max_hash, int(track_abundance), nthreads, out)
     return [KmerMinHash(num, k, False, 42, max_hash, track_abundance, _ptr=out[i]) for i, k in enumerate(ksizes)]
+
+
+class Nodegraph:
+    """Oracle khmer bloom filter (src/index/nodegraph.rs:11-225)."""
+
+    def __init__(self, tablesizes=None, ksize=0, _ptr=None):
+        self._L = lib()
+        if _ptr is not None:
+            self._p = _ptr
+        else:
+            ts = (C.c_uint64 * max(1, len(tablesizes)))(*tablesizes)
+            self._p = self._L.orc_ng_new(ts, len(tablesizes), ksize)
+
+    def __del__(self):
+        if getattr(self, "_p", None):
+            self._L.orc_ng_free(self._p)
+            self._p = None
+
+    @classmethod
+    def from_buffer(cls, data: bytes):
+        p = lib().orc_ng_load(data, len(data))
+        if not p:
+            raise SourmashError(1, "Nodegraph::from_reader failed")
+        return cls(_ptr=p)
+
+    def save(self) -> bytes:
+        n = self._L.orc_ng_save(self._p, None, 0)
+        buf = C.create_string_buffer(n)
+        self._L.orc_ng_save(self._p, buf, n)
+        return buf.raw
+
+    def count(self, h):
+        return bool(self._L.orc_ng_count(self._p, h))
+
+    def get(self, h):
+        return self._L.orc_ng_get(self._p, h)
+
+    def update(self, other):
+        if self._L.orc_ng_update(self._p, other._p):
+            raise SourmashError(1, "FixedBitSet::put out of bounds")
+
+    def tablesizes(self):
+        return [self._L.orc_ng_tablesize(self._p, t) for t in range(self._L.orc_ng_n_tables(self._p))]
+
+    def ksize(self):
+        return self._L.orc_ng_ksize(self._p)
+
+    def n_occupied_bins(self):
+        return self._L.orc_ng_occupied_bins(self._p)
+
+    def unique_kmers(self):
+        return self._L.orc_ng_unique_kmers(self._p)
+
+    def similarity(self, other):
+        return self._L.orc_ng_similarity(self._p, other._p)
+
+    def containment(self, other):
+        return self._L.orc_ng_containment(self._p, other._p)
+
+    def matches(self, mh):
+        return self._L.orc_ng_matches(self._p, mh._p)
+
+
+def node_similarity(ng, min_n_below, query):  # sbt.rs:233-254
+    return lib().orc_node_similarity(ng._p, min_n_below, query._p)
+
+
+def node_containment(ng, query):  # sbt.rs:256-277
+    return lib().orc_node_containment(ng._p, query._p)
+
+
+def sbt_find(d, nodes, leaves, query, mode, threshold):
+    """SBT::find (sbt.rs:147-175).  nodes: {position: (Nodegraph, min_n_below)}, leaves: {position: KmerMinHash};
+    returns the positions of the matching leaves in visit order."""
+    npos = sorted(nodes)
+    lpos = sorted(leaves)
+    a_np = (C.c_uint64 * max(1, len(npos)))(*npos)
+    a_ng = (C.c_void_p * max(1, len(npos)))(*[nodes[p][0]._p for p in npos])
+    a_mb = (C.c_uint64 * max(1, len(npos)))(*[nodes[p][1] for p in npos])
+    a_lp = (C.c_uint64 * max(1, len(lpos)))(*lpos)
+    a_lm = (C.c_void_p * max(1, len(lpos)))(*[leaves[p]._p for p in lpos])
+    hits = (C.c_uint64 * max(1, len(lpos)))()
+    n = lib().orc_sbt_find(d, a_np, a_ng, a_mb, len(npos), a_lp, a_lm, len(lpos), query._p,
+                           1 if mode == "containment" else 0, threshold, hits)
+    return [hits[i] for i in range(n)]

@@ -102,6 +102,21 @@ EXTENSION_ABI = {
     "smgpu_scaffold_pairs": (u64, [vp, vp, vp]),
     "smgpu_compare_path": (None, [i32]),
     "smgpu_linear_find": (u64, [vp, vp, i32, C.c_double, vp, vp, u64]),
+    "smgpu_nodegraph_new": (vp, [vp, usz, u64]),
+    "smgpu_nodegraph_free": (None, [vp]),
+    "smgpu_nodegraph_from_buffer": (vp, [C.c_char_p, usz]),
+    "smgpu_nodegraph_save": (usz, [vp, vp, usz]),
+    "smgpu_nodegraph_count_many": (u64, [vp, vp, u64, vp, cb]),
+    "smgpu_nodegraph_get_many": (u64, [vp, vp, u64, vp, cb]),
+    "smgpu_nodegraph_matches": (u64, [vp, vp]),
+    "smgpu_nodegraph_update": (None, [vp, vp]),
+    "smgpu_nodegraph_similarity": (C.c_double, [vp, vp]),
+    "smgpu_nodegraph_containment": (C.c_double, [vp, vp]),
+    "smgpu_nodegraph_tablesizes": (usz, [vp, vp, usz]),
+    "smgpu_nodegraph_ksize": (u64, [vp]),
+    "smgpu_nodegraph_n_occupied_bins": (u64, [vp]),
+    "smgpu_nodegraph_unique_kmers": (u64, [vp]),
+    "smgpu_sbt_find": (u64, [u32, vp, vp, vp, u64, vp, vp, vp, i32, C.c_double, vp, vp, u64]),
 }
 
 _lib = None
@@ -506,3 +521,94 @@ def linear_find(index, queries, mode, threshold, hits_cap=None):
                   _vp(offs), _vp(hits), cap)
     assert total <= cap
     return [hits[int(offs[q]):int(offs[q + 1])].tolist() for q in range(nq)]
+
+
+class Nodegraph:
+    """Nodegraph (src/index/nodegraph.rs:11-225) with its bitsets in HBM, behind smgpu_nodegraph_*."""
+
+    def __init__(self, tablesizes=None, ksize=0, _ptr=None):
+        if _ptr is not None:
+            self._p = _ptr
+        else:
+            ts = np.ascontiguousarray(tablesizes, dtype=np.uint64)
+            self._p = _call("smgpu_nodegraph_new", _vp(ts), ts.size, ksize)
+
+    def __del__(self):
+        p, self._p = getattr(self, "_p", None), None
+        if p and _lib is not None:
+            _lib.smgpu_nodegraph_free(p)
+
+    @classmethod
+    def from_buffer(cls, data: bytes):
+        """Nodegraph::from_reader over a khmer OXLI v4 file image."""
+        return cls(_ptr=_call("smgpu_nodegraph_from_buffer", data, len(data)))
+
+    def save(self) -> bytes:
+        n = _call("smgpu_nodegraph_save", self._p, None, 0)
+        out = np.zeros(n, dtype=np.uint8)
+        _call("smgpu_nodegraph_save", self._p, _vp(out), n)
+        return out.tobytes()
+
+    def count_many(self, hashes):
+        """(number of new k-mers, per-hash return value of Nodegraph::count in batch order)"""
+        h = np.ascontiguousarray(hashes, dtype=np.uint64)
+        flags = np.zeros(h.size, dtype=np.uint8)
+        n = _call("smgpu_nodegraph_count_many", self._p, _vp(h), h.size, _vp(flags), False) if h.size else 0
+        return n, flags.astype(bool)
+
+    def count(self, h):
+        return bool(self.count_many([h])[1][0])
+
+    def get_many(self, hashes):
+        h = np.ascontiguousarray(hashes, dtype=np.uint64)
+        flags = np.zeros(h.size, dtype=np.uint8)
+        n = _call("smgpu_nodegraph_get_many", self._p, _vp(h), h.size, _vp(flags), False) if h.size else 0
+        return n, flags
+
+    def get(self, h):
+        return int(self.get_many([h])[1][0])
+
+    def matches(self, mh):
+        return _call("smgpu_nodegraph_matches", self._p, mh._p)
+
+    def update(self, other):
+        _call("smgpu_nodegraph_update", self._p, other._p)
+
+    def similarity(self, other):
+        return _call("smgpu_nodegraph_similarity", self._p, other._p)
+
+    def containment(self, other):
+        return _call("smgpu_nodegraph_containment", self._p, other._p)
+
+    def tablesizes(self):
+        n = _call("smgpu_nodegraph_tablesizes", self._p, None, 0)
+        out = np.zeros(max(1, n), dtype=np.uint64)
+        _call("smgpu_nodegraph_tablesizes", self._p, _vp(out), n)
+        return [int(x) for x in out[:n]]
+
+    def ksize(self):
+        return _call("smgpu_nodegraph_ksize", self._p)
+
+    def n_occupied_bins(self):
+        return _call("smgpu_nodegraph_n_occupied_bins", self._p)
+
+    def unique_kmers(self):
+        return _call("smgpu_nodegraph_unique_kmers", self._p)
+
+
+def sbt_find(d, nodes, leaf_positions, leaves, queries, mode="similarity", threshold=0.0):
+    """SBT::find (src/index/sbt.rs:147-175) for every row of `queries`.
+    nodes: {position: (Nodegraph, min_n_below)}; leaves: SketchCollection whose row i sits at leaf_positions[i].
+    Returns, per query, the positions of the matching leaves in the reference's visit order."""
+    npos = sorted(nodes)
+    a_np = np.ascontiguousarray(npos, dtype=np.uint64)
+    a_ng = (C.c_void_p * max(1, len(npos)))(*[nodes[p][0]._p for p in npos])
+    a_mb = np.ascontiguousarray([nodes[p][1] for p in npos], dtype=np.uint64)
+    a_lp = np.ascontiguousarray(leaf_positions, dtype=np.uint64)
+    nq = len(queries)
+    offs = np.zeros(nq + 1, dtype=np.uint64)
+    cap = max(1, nq * max(1, len(leaf_positions)))
+    hits = np.zeros(cap, dtype=np.uint64)
+    _call("smgpu_sbt_find", d, _vp(a_np), C.cast(a_ng, C.c_void_p), _vp(a_mb), len(npos), _vp(a_lp), leaves._p, queries._p,
+          1 if mode == "containment" else 0, threshold, _vp(offs), _vp(hits), cap)
+    return [[int(x) for x in hits[int(offs[q]):int(offs[q + 1])]] for q in range(nq)]

@@ -16,12 +16,14 @@
 #include "collection.hpp"
 #include "kernels.cuh"
 #include "minhash.hpp"
+#include "nodegraph.hpp"
 #include "signature.hpp"
 
 using smb200::SourmashError;
 typedef smb200::KmerMinHash MH;
 typedef smb200::Signature SIG;
 typedef smb200::SketchCollection COLL;
+typedef smb200::Nodegraph NG;
 
 namespace {
 
@@ -71,6 +73,7 @@ MH *mh(KmerMinHash *p) { return reinterpret_cast<MH *>(nonnull(p, "ptr")); }
 MH *mh(const KmerMinHash *p) { return reinterpret_cast<MH *>(const_cast<KmerMinHash *>(nonnull(p, "other"))); }
 SIG *sig(Signature *p) { return reinterpret_cast<SIG *>(nonnull(p, "ptr")); }
 COLL *coll(SketchCollection *p) { return reinterpret_cast<COLL *>(nonnull(p, "collection")); }
+NG *ngp(Nodegraph *p) { return reinterpret_cast<NG *>(nonnull(p, "nodegraph")); }
 
 SourmashStr str_from(const std::string &s) {  // SourmashStr::from_string, utils.rs:194-204
     SourmashStr r;
@@ -531,6 +534,80 @@ uint64_t smgpu_linear_find(SketchCollection *index, SketchCollection *queries, i
     return landingpad<uint64_t>([&]() {
         if (mode != 0 && mode != 1) smb200::throw_internal("mode must be 0 (similarity) or 1 (containment)");
         return smb200::linear_find(*coll(index), *coll(queries), mode, threshold, hit_offsets, hits, hits_cap);
+    });
+}
+
+
+// ---- Nodegraph / SBT (src/index/nodegraph.rs, src/index/sbt.rs) ---------------------------------------
+Nodegraph *smgpu_nodegraph_new(const uint64_t *tablesizes, uintptr_t n_tables, uint64_t ksize) {
+    return landingpad<Nodegraph *>([&]() {
+        if (n_tables) nonnull(tablesizes, "tablesizes");
+        return reinterpret_cast<Nodegraph *>(new NG(tablesizes, n_tables, ksize));
+    });
+}
+void smgpu_nodegraph_free(Nodegraph *ng) {
+    landingpad_void([&]() { delete reinterpret_cast<NG *>(ng); });
+}
+Nodegraph *smgpu_nodegraph_from_buffer(const uint8_t *data, uintptr_t len) {
+    return landingpad<Nodegraph *>([&]() {
+        nonnull(data, "data");
+        return reinterpret_cast<Nodegraph *>(NG::from_buffer(data, len));
+    });
+}
+uintptr_t smgpu_nodegraph_save(Nodegraph *ng, uint8_t *out, uintptr_t cap) {
+    return landingpad<uintptr_t>([&]() -> uintptr_t { return ngp(ng)->save(out, out ? cap : 0); });
+}
+uint64_t smgpu_nodegraph_count_many(Nodegraph *ng, const uint64_t *hashes, uint64_t n, uint8_t *is_new, bool on_device) {
+    return landingpad<uint64_t>([&]() -> uint64_t {
+        if (n) nonnull(hashes, "hashes");
+        return ngp(ng)->count_many(hashes, n, is_new, on_device);
+    });
+}
+uint64_t smgpu_nodegraph_get_many(Nodegraph *ng, const uint64_t *hashes, uint64_t n, uint8_t *present, bool on_device) {
+    return landingpad<uint64_t>([&]() -> uint64_t {
+        if (n) nonnull(hashes, "hashes");
+        return ngp(ng)->get_many(hashes, n, present, on_device);
+    });
+}
+uint64_t smgpu_nodegraph_matches(Nodegraph *ng, KmerMinHash *ptr) {
+    return landingpad<uint64_t>([&]() -> uint64_t {
+        size_t n = 0;
+        const uint64_t *dm = mh(ptr)->device_mins(&n);
+        return ngp(ng)->get_many(dm, n, nullptr, true);
+    });
+}
+void smgpu_nodegraph_update(Nodegraph *ng, Nodegraph *other) {
+    landingpad_void([&]() { ngp(ng)->update(*ngp(other)); });
+}
+double smgpu_nodegraph_similarity(Nodegraph *ng, Nodegraph *other) {
+    return landingpad<double>([&]() { return ngp(ng)->similarity(*ngp(other)); });
+}
+double smgpu_nodegraph_containment(Nodegraph *ng, Nodegraph *other) {
+    return landingpad<double>([&]() { return ngp(ng)->containment(*ngp(other)); });
+}
+uintptr_t smgpu_nodegraph_tablesizes(Nodegraph *ng, uint64_t *out, uintptr_t cap) {
+    return landingpad<uintptr_t>([&]() -> uintptr_t {
+        NG *g = ngp(ng);
+        for (size_t t = 0; out && t < g->tables.size() && t < cap; t++) out[t] = g->tables[t].len;
+        return g->tables.size();
+    });
+}
+uint64_t smgpu_nodegraph_ksize(Nodegraph *ng) { return landingpad<uint64_t>([&]() { return ngp(ng)->ksize; }); }
+uint64_t smgpu_nodegraph_n_occupied_bins(Nodegraph *ng) { return landingpad<uint64_t>([&]() { return ngp(ng)->occupied_bins; }); }
+uint64_t smgpu_nodegraph_unique_kmers(Nodegraph *ng) { return landingpad<uint64_t>([&]() { return ngp(ng)->unique_kmers; }); }
+uint64_t smgpu_sbt_find(uint32_t d, const uint64_t *node_positions, Nodegraph *const *nodes, const uint64_t *min_n_below,
+                        uint64_t n_nodes, const uint64_t *leaf_positions, SketchCollection *leaves, SketchCollection *queries,
+                        int32_t mode, double threshold, uint64_t *hit_offsets, uint64_t *hits, uint64_t hits_cap) {
+    return landingpad<uint64_t>([&]() -> uint64_t {
+        if (mode != 0 && mode != 1) smb200::throw_internal("mode must be 0 (similarity) or 1 (containment)");
+        if (d == 0) smb200::throw_internal("d must be at least 1");
+        if (n_nodes) { nonnull(node_positions, "node_positions"); nonnull(nodes, "nodes"); nonnull(min_n_below, "min_n_below"); }
+        for (uint64_t i = 0; i < n_nodes; i++) ngp(nodes[i]);
+        COLL *l = coll(leaves);
+        l->finalize();
+        if (l->n_rows) nonnull(leaf_positions, "leaf_positions");
+        return smb200::sbt_find(d, node_positions, reinterpret_cast<NG *const *>(nodes), min_n_below, n_nodes, leaf_positions, *l,
+                                *coll(queries), mode, threshold, hit_offsets, hits, hits_cap);
     });
 }
 

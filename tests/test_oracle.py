@@ -204,3 +204,77 @@ def test_scaffold_leaf_pairing():  # src/index/sbt.rs:356-381 over the v5 fixtur
     assert seen == list(range(7)) and len(pairs) == 4
     # leaf 12 (last) is popped first and pairs with its nearest neighbour by count_common: leaf 8 (275 > 273)
     assert [int(pos[a]) for a, b in pairs][0] == 12 and int(pos[pairs[0][1]]) == 8
+
+
+# ------------------------------------------------------------------------------------------------
+# Nodegraph / SBT: src/index/nodegraph.rs tests and the sbt.find half of load_sbt
+# ------------------------------------------------------------------------------------------------
+def _oracle_tree():
+    from util import sbt_v5_tree
+    d, nodes, leaf_positions, t = sbt_v5_tree()
+    ngs = {p: (orc.Nodegraph.from_buffer(raw), mnb) for p, (raw, mnb) in nodes.items()}
+    leaves = {int(p): _load(v["sketch"]) for p, v in golden("sbt_v5_leaves.json")["leaves"].items()}
+    assert sorted(leaves) == leaf_positions
+    return d, nodes, ngs, leaves, t
+
+
+def test_nodegraph_count_and_get():  # nodegraph.rs:236-254
+    ng = orc.Nodegraph([10], 3)
+    assert ng.count(801084876663808) is True
+    assert ng.get(801084876663808) == 1 and ng.unique_kmers() == 1
+    assert ng.count(801084876663808) is False and ng.unique_kmers() == 1
+    for h in (0, 1, 9, 10, 2**64 - 1, 0x123456789ABCDEF):  # the proptest property on a few values
+        g = orc.Nodegraph([10], 3)
+        g.count(h)
+        assert g.get(h) == 1
+
+
+def test_nodegraph_load_save_roundtrip():  # nodegraph.rs:256-279: byte-identical re-serialisation
+    d, nodes, ngs, leaves, t = _oracle_tree()
+    for p, (raw, _) in nodes.items():
+        assert ngs[p][0].save() == raw
+
+
+def test_nodegraph_load_fixture():  # nodegraph.rs:292-821
+    d, nodes, ngs, leaves, t = _oracle_tree()
+    spec = t["load_nodegraph"]
+    ng = ngs[0][0]
+    assert ng.tablesizes() == spec["tablesizes"]
+    for h in spec["absent"]:
+        assert ng.get(h) == 0
+    assert len(spec["present"]) == 500
+    for h in spec["present"]:
+        assert ng.get(h) == 1
+
+
+def test_nodegraph_update_fixture():  # nodegraph.rs:271-290: internal.1 | internal.2 == internal.0
+    d, nodes, ngs, leaves, t = _oracle_tree()
+    ng0 = orc.Nodegraph([99991, 99989, 99971, 99961], 1)
+    ng0.update(ngs[1][0])
+    ng0.update(ngs[2][0])
+    assert ng0.save()[19:] == nodes[0][0][19:]  # the bitsets (the header holds ksize / occupied_bins)
+    assert ng0.similarity(ngs[0][0]) == 1.0
+
+
+def test_sbt_find_fixture():  # sbt.rs:543-551: 1 hit above 0.5, 2 above 0.1 for leaf 7
+    d, nodes, ngs, leaves, t = _oracle_tree()
+    q = leaves[t["asserted_sbt_find"]["query_position"]]
+    h5 = orc.sbt_find(d, ngs, leaves, q, "similarity", 0.5)
+    h1 = orc.sbt_find(d, ngs, leaves, q, "similarity", 0.1)
+    assert len(h5) == t["asserted_sbt_find"]["similarity@0.5"] and len(h1) == t["asserted_sbt_find"]["similarity@0.1"]
+    assert h5 == [7] and sorted(h1) == [7, 11]
+    # the tree search and the linear scan agree on this fixture (sbt.rs:566-574 asserts the same counts)
+    order = sorted(leaves)
+    lin = orc.linear_find([leaves[p] for p in order], q, "similarity", 0.1)
+    assert sorted(order[i] for i in lin) == sorted(h1)
+    # every internal node of the fixture holds all hashes of the leaves below it
+    for p, (ng, mnb) in ngs.items():
+        below = [l for l in leaves if any(_is_ancestor(p, l, d))]
+        for l in below:
+            assert ng.matches(leaves[l]) == leaves[l].size()
+
+
+def _is_ancestor(a, pos, d):
+    while pos:
+        pos = (pos - 1) // d
+        yield pos == a

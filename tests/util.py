@@ -58,3 +58,13 @@ def make_reads(genome: bytes, nreads, readlen, seed):
         rd = genome[s:s + readlen]
         out += revcomp(rd) if f else rd
     return bytes(out)
+
+
+def sbt_v5_tree():
+    """The reference's tests/data/v5.sbt.json tree (golden copy): (d, {pos: (oxli_bytes, min_n_below)},
+    leaf positions, the raw golden dict)."""
+    import base64
+    import zlib
+    t = golden("sbt_v5_tree.json")
+    nodes = {int(p): (zlib.decompress(base64.b64decode(n["oxli_zlib_b64"])), n["min_n_below"]) for p, n in t["nodes"].items()}
+    return t["d"], nodes, t["leaf_positions"], t
