@@ -546,7 +546,7 @@ def bench_compare(args, smb, torch, dist, dev, rank, world, barrier, max_over_ra
             "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(rows_c.nbytes + offs_c.nbytes),
                     "d2h_bytes_per_step": int((r1 - r0) * N * 8)},
-            "path": "auto: inverted-index join finds the related pairs (here 1% of all), only those are walked",
+            "path": "auto: hash-grouped inverted-index join (row hashes in a hash table, column hashes probe it) finds the related pairs (here 1% of all), only those are walked",
             "dense_path": {"value": pairs / (ms_dense * 1e-3), "unit": "pairs/s", "ms_per_step": ms_dense,
                            "note": "every pair walked: rank-compressed fixed-length walk, smgpu_compare_path(1)"},
             "operand_bytes_per_pair": 2 * NUM * 8, "parity_checked_64x64": ok}

@@ -109,7 +109,10 @@ uint64_t smgpu_scaffold_pairs(SketchCollection *c, uint64_t *pairs_first, uint64
 /* How smgpu_compare_matrix / smgpu_linear_find walk a block: 0 (default) decides from the data --
  * an inverted index over the block's hashes finds the pairs that share at least one hash, and
  * only those are walked when the (pair, shared hash) incidences are few against the dense work;
- * 1 forces the dense tile kernel, 2 forces the inverted-index path.  Results are identical. */
+ * 1 forces the dense tile kernel, 2 forces the inverted-index path, 3 = as 0 but with the
+ * sorted-postings join instead of the hash-grouped one (the default; it builds a hash table over
+ * the ROW block's hashes only, so a row shard of an all-vs-all matrix costs its share of the rows).
+ * Results are identical. */
 void smgpu_compare_path(int32_t path);
 /* Batch sketching of several k-sizes over the same sequences (smgpu_add_* with more than one
  * handle): on (default) = sketches with distinct k in {21, 31, 51} and one seed share a fused

@@ -199,8 +199,8 @@ PROFILE_KINDS = {"sketch_k21": 0, "sketch_k31": 1, "sketch_k51": 2, "sketch_othe
 
 
 def compare_path(path="auto"):
-    """'auto' | 'dense' | 'sparse' (smgpu_compare_path)"""
-    lib().smgpu_compare_path({"auto": 0, "dense": 1, "sparse": 2}[path])
+    """'auto' | 'dense' | 'sparse' | 'noprobe' (smgpu_compare_path)"""
+    lib().smgpu_compare_path({"auto": 0, "dense": 1, "sparse": 2, "noprobe": 3, "probe": 4}[path])
 
 
 def fuse_multi_k(on=True):

@@ -27,6 +27,7 @@ void SketchCollection::push(KmerMinHash &mh) {
     h_offsets.push_back(h_hashes.size());
     h_nums.push_back(mh.num);
     dirty = true;
+    probe_checked = probe_dense_preferred = false;
 }
 
 void SketchCollection::finalize() {
@@ -104,7 +105,7 @@ static bool block_is_full(const SketchCollection &c, uint64_t first, uint64_t n,
     return true;
 }
 
-int g_compare_path = 0;  // 0 = choose from the data, 1 = dense tile kernel, 2 = inverted-index path
+int g_compare_path = 0;  // 0 = choose from the data, 1 = dense tile kernel, 2 = inverted-index path, 3 = inverted index without the probe form
 
 static int bit_length64(uint64_t x) {
     int b = 0;
@@ -128,7 +129,7 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
     const uint64_t n_r = shared ? 0 : rows.h_offsets[r0 + nr] - rows.h_offsets[r0];
     const uint64_t n_c = cols.h_offsets[c0 + nc] - cols.h_offsets[c0];
     const uint64_t n = n_r + n_c;
-    const bool force_dense = g_compare_path == 1, force_sparse = g_compare_path == 2;
+    const bool force_dense = g_compare_path == 1, force_sparse = g_compare_path == 2 || g_compare_path == 4;
     const bool big = n > 0 && nr * nc >= 4096 && nr < (1ull << 31) && nc < (1ull << 31);
     bool sparse = !force_dense && n > 0 && (force_sparse || big) && nr < (1ull << 31) && nc < (1ull << 31);
     // full num sketches (Jaccard): the dense walk can run on 32-bit ranks with a fixed trip count
@@ -136,6 +137,87 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
     const bool full = mode == 0 && big && block_is_full(rows, r0, nr, &L) && block_is_full(cols, c0, nc, &Lc) && L == Lc &&
                       compare_full_fits(L);
     uint64_t *keys = nullptr, *vals = nullptr;
+    // Probe form of the join (the default sparse path): the row postings are grouped by hash in a hash
+    // table and every column hash looks its run up -- O(rows) to build, no sort, and no host round trip
+    // anywhere in the block as long as the pair list fits the cell count.  A row shard of the all-vs-all
+    // matrix therefore costs its share of the rows, which is what lets the matrix scale over GPUs; the
+    // sorted-postings join below remains for smgpu_compare_path(3) and feeds the dense rank kernel.
+    const uint64_t n_rp = rows.h_offsets[r0 + nr] - rows.h_offsets[r0];
+    const bool probe = sparse && g_compare_path != 3 && n_rp > 0 && n_rp < (1ull << 31) &&
+                       !(rows.probe_dense_preferred && !force_sparse);
+    if (probe) {
+        int log2_t = 12;
+        while ((1ull << log2_t) < 2 * n_rp) log2_t++;
+        const uint64_t T = 1ull << log2_t;
+        ctx.join[0].reserve((T + 2) * 8);
+        ctx.join[1].reserve((T + 2) * 8);
+        ctx.sort_tmp_k.reserve((T + 2) * 8);
+        ctx.sort_tmp_v.reserve((T + 2) * 4);
+        ctx.join[6].reserve((n_rp + 1) * 4);
+        ctx.join[7].reserve((n_rp + 1) * 4);
+        const uint64_t n_words = (nr * nc + 63) / 64;
+        ctx.scan_tmp.reserve(scan_tmp_bytes(std::max<uint64_t>(T + 2, n_words)) + 256);
+        unsigned long long *tkey = ctx.join[0].as<unsigned long long>(), *tcount = ctx.join[1].as<unsigned long long>();
+        uint64_t *toff = ctx.sort_tmp_k.as<uint64_t>();
+        uint32_t *tcursor = ctx.sort_tmp_v.as<uint32_t>(), *slot_of = ctx.join[6].as<uint32_t>(), *grows = ctx.join[7].as<uint32_t>();
+        {
+            ProfScope prof(PROF_SORT, st);
+            SM_CUDA(cudaMemsetAsync(tkey, 0xFF, (T + 1) * 8, st));
+            SM_CUDA(cudaMemsetAsync(tcount, 0, (T + 2) * 8, st));
+            SM_CUDA(cudaMemsetAsync(tcursor, 0, (T + 1) * 4, st));
+            SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_CNT), 0, 8, st));
+            launch_group_insert(rh, ro, r0, nr, tkey, tcount, slot_of, log2_t, st);
+            scan_exclusive_u64(reinterpret_cast<uint64_t *>(tcount), toff, T + 2, ctx.scan_tmp.p, st);
+            launch_group_fill(ro, r0, nr, slot_of, toff, tcursor, grows, st);
+        }
+        ProfScope prof(PROF_COMPARE, st);
+        if (mode == 1) {
+            uint32_t *cmat = common;
+            uint64_t cld = ld;
+            if (!cmat) {
+                ctx.join[2].reserve(nr * nc * 4 + 256);
+                cmat = ctx.join[2].as<uint32_t>();
+                cld = nc;
+            }
+            SM_CUDA(cudaMemset2DAsync(cmat, cld * 4, 0, nc * 4, nr, st));
+            launch_probe_group(true, tkey, toff, grows, log2_t, ch, co, c0, nc, cmat, cld, nullptr, ctx.dsc(SC_CNT), st);
+            launch_fill_cells(ro, rnum, r0, nr, co, c0, nc, 1, cmat, cld, common, size, ratio, ld, st);
+        } else {
+            ctx.join[2].reserve((n_words + 1) * 8);
+            ctx.join[3].reserve((n_words + 1) * 8);
+            ctx.join[4].reserve((n_words + 1) * 8);
+            unsigned long long *bitmap = ctx.join[2].as<unsigned long long>();
+            uint64_t *counts = ctx.join[3].as<uint64_t>(), *pre = ctx.join[4].as<uint64_t>();
+            SM_CUDA(cudaMemsetAsync(bitmap, 0, n_words * 8, st));
+            launch_probe_group(false, tkey, toff, grows, log2_t, ch, co, c0, nc, nullptr, 0, bitmap, ctx.dsc(SC_CNT), st);
+            launch_fill_cells(ro, rnum, r0, nr, co, c0, nc, 0, nullptr, 0, common, size, ratio, ld, st);  // as if unrelated
+            launch_popc_words(bitmap, n_words, counts, st);
+            scan_exclusive_u64(counts, pre, n_words, ctx.scan_tmp.p, st);
+            // the pair list can hold every cell of a block of up to 2^26 cells: then the walk reads its
+            // count on the device and nothing waits for the host; larger blocks size the list first
+            uint64_t cap = nr * nc;
+            if (cap > (1ull << 26)) {
+                uint64_t tail[2];
+                ctx.fetch2(pre + (n_words - 1), counts + (n_words - 1), tail);
+                cap = tail[0] + tail[1];
+            }
+            if (cap) {
+                ctx.join[5].reserve((cap + 1) * 8);
+                launch_expand_bits(bitmap, pre, n_words, ctx.join[5].as<uint64_t>(), st, cap);
+                launch_walk_pairs(ctx.join[5].as<uint64_t>(), cap, rh, ro, rnum, r0, ch, co, c0, nc, common, size, ratio, ld, st,
+                                  pre + (n_words - 1), counts + (n_words - 1));
+            }
+        }
+        // The probe path is exact whatever the data; whether the dense kernels would have been faster
+        // (mostly-related collections) is learned once per row collection, from its first block.
+        if (!rows.probe_checked && !force_sparse) {
+            ctx.read_scalars();
+            rows.probe_checked = true;
+            rows.probe_dense_preferred = ctx.h_scalars[SC_CNT] > 8 * nr * nc;
+        }
+        return;
+    }
+    keys = nullptr; vals = nullptr;
     if (sparse || (full && !force_sparse)) {
         ProfScope prof(PROF_SORT, st);
         ctx.join[0].reserve((n + 1) * 8);

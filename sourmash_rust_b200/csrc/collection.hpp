@@ -24,6 +24,9 @@ struct SketchCollection {
     DevBuf d_hashes, d_offsets, d_nums;
     uint64_t n_rows = 0, n_hashes = 0;
     uint32_t max_len = 0;
+    // compare path bookkeeping (collection.cu): has a block with these rows gone through the probe form of
+    // the join yet, and did it find so many incidences that the dense kernels are the better choice
+    bool probe_checked = false, probe_dense_preferred = false;
 
     void push(KmerMinHash &mh);
     static SketchCollection *from_csr(const uint64_t *hashes, const uint64_t *offsets, uint64_t n_rows, uint32_t num,

@@ -84,6 +84,128 @@ void launch_max_u64(const uint64_t *keys, uint64_t n, unsigned long long *out, c
     SM_LAUNCHED();
 }
 
+// ---- probe form: the ROW postings are grouped by hash in a hash table; every column hash looks its run up ---
+// Used when the row block is much smaller than the column block (a row shard of an all-vs-all matrix,
+// a query batch against an index): building the row side costs O(rows) and no sort, which is what lets
+// the row-sharded matrix scale with the number of GPUs.
+//   group_insert: every row posting claims / finds the slot of its hash (open addressing, linear probing,
+//                 atomicCAS) and counts itself there; remembers the slot
+//   (exclusive scan of the slot counts = start of each hash's run in `grows`)
+//   group_fill:   every row posting writes its local row id into its hash's run
+//   probe_group:  one warp per column sketch; each hash finds its slot (an empty slot = no row has it)
+//                 and marks (row, column) for every row of the run
+// The hash value ~0 cannot be told from an empty slot, so it owns the extra slot T.
+constexpr unsigned long long GROUP_EMPTY = ~0ull;
+__device__ __forceinline__ uint64_t group_slot0(uint64_t h, int log2_t) { return (h * 0x9E3779B97F4A7C15ull) >> (64 - log2_t); }
+
+__global__ void __launch_bounds__(256) group_insert_kernel(const uint64_t *__restrict__ rh, const uint64_t *__restrict__ ro,
+                                                           uint64_t r0, uint64_t nr, unsigned long long *tkey,
+                                                           unsigned long long *tcount, uint32_t *slot_of, int log2_t) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t T = 1ull << log2_t, base = ro[r0];
+    for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nr; r += warps) {
+        const uint64_t b = ro[r0 + r], e = ro[r0 + r + 1];
+        for (uint64_t i = b + lane; i < e; i += 32) {
+            const unsigned long long h = rh[i];
+            uint64_t s;
+            if (h == GROUP_EMPTY) {
+                s = T;
+            } else {
+                s = group_slot0(h, log2_t);
+                for (;;) {
+                    unsigned long long cur = tkey[s];
+                    if (cur == GROUP_EMPTY) cur = atomicCAS(&tkey[s], GROUP_EMPTY, h);
+                    if (cur == GROUP_EMPTY || cur == h) break;
+                    s = (s + 1) & (T - 1);
+                }
+            }
+            atomicAdd(&tcount[s], 1ull);
+            slot_of[i - base] = (uint32_t)s;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) group_fill_kernel(const uint64_t *__restrict__ ro, uint64_t r0, uint64_t nr,
+                                                         const uint32_t *__restrict__ slot_of, const uint64_t *__restrict__ toff,
+                                                         uint32_t *tcursor, uint32_t *grows) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t base = ro[r0];
+    for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nr; r += warps) {
+        const uint64_t b = ro[r0 + r], e = ro[r0 + r + 1];
+        for (uint64_t i = b + lane; i < e; i += 32) {
+            const uint32_t s = slot_of[i - base];
+            grows[toff[s] + atomicAdd(&tcursor[s], 1u)] = (uint32_t)r;
+        }
+    }
+}
+// COUNT: atomicAdd into cmat, else set bits of the related-pairs bitmap; *incidences += number of (row, column hash) hits
+template <bool COUNT>
+__global__ void __launch_bounds__(256) probe_group_kernel(const unsigned long long *__restrict__ tkey,
+                                                          const uint64_t *__restrict__ toff, const uint32_t *__restrict__ grows,
+                                                          int log2_t, const uint64_t *__restrict__ ch,
+                                                          const uint64_t *__restrict__ co, uint64_t c0, uint64_t nc, uint32_t *cmat,
+                                                          uint64_t ld, unsigned long long *bitmap, unsigned long long *incidences) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t T = 1ull << log2_t;
+    unsigned long long local = 0;
+    for (uint64_t c = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < nc; c += warps) {
+        const uint64_t b = co[c0 + c], e = co[c0 + c + 1];
+        for (uint64_t i = b + lane; i < e; i += 32) {
+            const unsigned long long h = ch[i];
+            uint64_t s;
+            if (h == GROUP_EMPTY) {
+                s = T;
+            } else {
+                s = group_slot0(h, log2_t);
+                for (;;) {
+                    const unsigned long long cur = tkey[s];
+                    if (cur == h) break;
+                    if (cur == GROUP_EMPTY) { s = ~0ull; break; }
+                    s = (s + 1) & (T - 1);
+                }
+                if (s == ~0ull) continue;
+            }
+            const uint64_t jb = toff[s], je = toff[s + 1];
+            local += je - jb;
+            for (uint64_t j = jb; j < je; j++) {
+                const uint64_t r = grows[j];
+                if (COUNT) {
+                    atomicAdd(&cmat[r * ld + c], 1u);
+                } else {
+                    const uint64_t bit = r * nc + c;
+                    const unsigned long long m = 1ull << (bit & 63);
+                    if (!(bitmap[bit >> 6] & m)) atomicOr(&bitmap[bit >> 6], m);
+                }
+            }
+        }
+    }
+    for (int d = 16; d; d >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, d);
+    if (lane == 0 && local) atomicAdd(incidences, local);
+}
+void launch_group_insert(const uint64_t *rh, const uint64_t *ro, uint64_t r0, uint64_t nr, unsigned long long *tkey,
+                         unsigned long long *tcount, uint32_t *slot_of, int log2_t, cudaStream_t st) {
+    if (!nr) return;
+    group_insert_kernel<<<blocks_for(nr * 32, 256, 148 * 16), 256, 0, st>>>(rh, ro, r0, nr, tkey, tcount, slot_of, log2_t);
+    SM_LAUNCHED();
+}
+void launch_group_fill(const uint64_t *ro, uint64_t r0, uint64_t nr, const uint32_t *slot_of, const uint64_t *toff,
+                       uint32_t *tcursor, uint32_t *grows, cudaStream_t st) {
+    if (!nr) return;
+    group_fill_kernel<<<blocks_for(nr * 32, 256, 148 * 16), 256, 0, st>>>(ro, r0, nr, slot_of, toff, tcursor, grows);
+    SM_LAUNCHED();
+}
+void launch_probe_group(bool count, const unsigned long long *tkey, const uint64_t *toff, const uint32_t *grows, int log2_t,
+                        const uint64_t *ch, const uint64_t *co, uint64_t c0, uint64_t nc, uint32_t *cmat, uint64_t ld,
+                        unsigned long long *bitmap, unsigned long long *incidences, cudaStream_t st) {
+    if (!nc) return;
+    const unsigned grid = blocks_for(nc * 32, 256, 148 * 16);
+    if (count) probe_group_kernel<true><<<grid, 256, 0, st>>>(tkey, toff, grows, log2_t, ch, co, c0, nc, cmat, ld, bitmap, incidences);
+    else probe_group_kernel<false><<<grid, 256, 0, st>>>(tkey, toff, grows, log2_t, ch, co, c0, nc, cmat, ld, bitmap, incidences);
+    SM_LAUNCHED();
+}
+
 // One postings set for both sides (rows and columns come from the same collection and the row range
 // lies inside the column range): posting value = column-local sketch id << 32 | position; a posting is
 // also a row posting when its sketch lies in [row_lo, row_lo + nr) (column-local ids).  Each posting
@@ -204,22 +326,23 @@ void launch_popc_words(const unsigned long long *bitmap, uint64_t n_words, uint6
 }
 // pairs[pre[w] + k] = index of the k-th set bit of word w (cell id r * nc + c, ascending)
 __global__ void expand_bits_kernel(const unsigned long long *__restrict__ bitmap, const uint64_t *__restrict__ pre,
-                                   uint64_t n_words, uint64_t *pairs) {
+                                   uint64_t n_words, uint64_t *pairs, uint64_t cap) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
         unsigned long long m = bitmap[w];
         uint64_t o = pre[w];
         while (m) {
             const int b = __ffsll((long long)m) - 1;
-            pairs[o++] = w * 64 + (uint64_t)b;
+            if (o < cap) pairs[o] = w * 64 + (uint64_t)b;
+            o++;
             m &= m - 1;
         }
     }
 }
 void launch_expand_bits(const unsigned long long *bitmap, const uint64_t *pre, uint64_t n_words, uint64_t *pairs,
-                        cudaStream_t st) {
+                        cudaStream_t st, uint64_t cap) {
     if (!n_words) return;
-    expand_bits_kernel<<<blocks_for(n_words, 256, 148 * 16), 256, 0, st>>>(bitmap, pre, n_words, pairs);
+    expand_bits_kernel<<<blocks_for(n_words, 256, 148 * 16), 256, 0, st>>>(bitmap, pre, n_words, pairs, cap);
     SM_LAUNCHED();
 }
 
@@ -269,7 +392,14 @@ __global__ void __launch_bounds__(256) walk_pairs_kernel(const uint64_t *__restr
                                                          const uint32_t *__restrict__ rnum, uint64_t r0,
                                                          const uint64_t *__restrict__ ch, const uint64_t *__restrict__ co,
                                                          uint64_t c0, uint64_t nc, uint32_t *common, uint32_t *size,
-                                                         double *ratio, uint64_t ld) {
+                                                         double *ratio, uint64_t ld, const uint64_t *n_dev_a,
+                                                         const uint64_t *n_dev_b) {
+    // the pair count either comes from the host or is read here as *n_dev_a + *n_dev_b (the tail of the
+    // bitmap scan), capped by n_pairs: the launch then needs no host round trip
+    if (n_dev_a) {
+        const uint64_t nd = *n_dev_a + *n_dev_b;
+        if (nd < n_pairs) n_pairs = nd;
+    }
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_pairs; t += stride) {
         const uint64_t cell = pairs[t];
@@ -297,10 +427,11 @@ __global__ void __launch_bounds__(256) walk_pairs_kernel(const uint64_t *__restr
 }
 void launch_walk_pairs(const uint64_t *pairs, uint64_t n_pairs, const uint64_t *rh, const uint64_t *ro, const uint32_t *rnum,
                        uint64_t r0, const uint64_t *ch, const uint64_t *co, uint64_t c0, uint64_t nc, uint32_t *common,
-                       uint32_t *size, double *ratio, uint64_t ld, cudaStream_t st) {
+                       uint32_t *size, double *ratio, uint64_t ld, cudaStream_t st, const uint64_t *n_dev_a,
+                       const uint64_t *n_dev_b) {
     if (!n_pairs) return;
     walk_pairs_kernel<<<blocks_for(n_pairs, 256, 148 * 16), 256, 0, st>>>(pairs, n_pairs, rh, ro, rnum, r0, ch, co, c0, nc, common,
-                                                                        size, ratio, ld);
+                                                                        size, ratio, ld, n_dev_a, n_dev_b);
     SM_LAUNCHED();
 }
 

@@ -156,6 +156,17 @@ void launch_count_incidences(const uint64_t *keys, const uint64_t *vals, uint64_
 void launch_incidences(bool count, const uint64_t *keys, const uint64_t *vals, uint64_t n, uint32_t *cmat, uint64_t ld,
                        unsigned long long *bitmap, uint64_t nc, cudaStream_t st);
 void launch_max_u64(const uint64_t *keys, uint64_t n, unsigned long long *out, cudaStream_t st);
+// probe form of the join (join.cu): row postings grouped by hash in a hash table of 2^log2_t (+1) slots
+//   tkey  (2^log2_t + 1) u64, preset to ~0;  tcount (2^log2_t + 2) u64, zeroed;  tcursor (2^log2_t + 1) u32, zeroed
+//   slot_of, grows: one u32 per row posting;  toff = exclusive scan of tcount over 2^log2_t + 2 entries
+void launch_group_insert(const uint64_t *rh, const uint64_t *ro, uint64_t r0, uint64_t nr, unsigned long long *tkey,
+                         unsigned long long *tcount, uint32_t *slot_of, int log2_t, cudaStream_t st);
+void launch_group_fill(const uint64_t *ro, uint64_t r0, uint64_t nr, const uint32_t *slot_of, const uint64_t *toff,
+                       uint32_t *tcursor, uint32_t *grows, cudaStream_t st);
+// count: counts into cmat, else related-pairs bitmap; *incidences += hits
+void launch_probe_group(bool count, const unsigned long long *tkey, const uint64_t *toff, const uint32_t *grows, int log2_t,
+                        const uint64_t *ch, const uint64_t *co, uint64_t c0, uint64_t nc, uint32_t *cmat, uint64_t ld,
+                        unsigned long long *bitmap, unsigned long long *incidences, cudaStream_t st);
 void launch_incidences_shared(bool count, const uint64_t *keys, const uint64_t *vals, uint64_t n, uint64_t row_lo,
                               uint64_t nr, uint32_t *cmat, uint64_t ld, unsigned long long *bitmap, uint64_t nc,
                               cudaStream_t st);
@@ -163,13 +174,14 @@ void launch_count_incidences_shared(const uint64_t *keys, const uint64_t *vals, 
                                     unsigned long long *out, cudaStream_t st);
 void launch_popc_words(const unsigned long long *bitmap, uint64_t n_words, uint64_t *counts, cudaStream_t st);
 void launch_expand_bits(const unsigned long long *bitmap, const uint64_t *pre, uint64_t n_words, uint64_t *pairs,
-                        cudaStream_t st);
+                        cudaStream_t st, uint64_t cap = ~0ull);
 void launch_fill_cells(const uint64_t *ro, const uint32_t *rnum, uint64_t r0, uint64_t nr, const uint64_t *co, uint64_t c0,
                        uint64_t nc, int mode, const uint32_t *cmat, uint64_t cld, uint32_t *common, uint32_t *size,
                        double *ratio, uint64_t ld, cudaStream_t st);
 void launch_walk_pairs(const uint64_t *pairs, uint64_t n_pairs, const uint64_t *rh, const uint64_t *ro, const uint32_t *rnum,
                        uint64_t r0, const uint64_t *ch, const uint64_t *co, uint64_t c0, uint64_t nc, uint32_t *common,
-                       uint32_t *size, double *ratio, uint64_t ld, cudaStream_t st);
+                       uint32_t *size, double *ratio, uint64_t ld, cudaStream_t st, const uint64_t *n_dev_a = nullptr,
+                       const uint64_t *n_dev_b = nullptr);
 
 // dense path for full num sketches: dense u32 ranks + fixed-length walk (join.cu)
 void launch_scatter_ranks(const uint64_t *keys, const uint64_t *vals, const uint64_t *pre, uint64_t n, uint32_t L,

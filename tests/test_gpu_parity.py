@@ -560,6 +560,49 @@ def test_compare_matrix_vs_oracle(num, n_hashes, mx, compare_path):
                 assert got[q] == orc.linear_find(o_sk, o_sk[q], mode, thr)
 
 
+@pytest.mark.parametrize("compare_path", ["auto", "sparse", "noprobe", "dense"], indirect=True)
+@pytest.mark.parametrize("num,n_hashes,mx", [(400, 400, 0), (0, 900, MAX_HASH_1000 * 50)])
+def test_compare_row_shards_and_query_batches(num, n_hashes, mx, compare_path):
+    """Row blocks much narrower than the column block -- a rank's shard of the all-vs-all matrix, a query
+    batch against an index -- take the probe form of the join (only the row postings are sorted); every
+    path must give the oracle's integers."""
+    rows = _planted_rows(240, n_hashes, 91 + num, mx or None)
+    if num:
+        rows = [r[:num] for r in rows]
+    rows[50] = rows[50][:0]
+    rows[51] = rows[51][:2]
+    g_sk, o_sk = [], []
+    for r in rows:
+        g, o = pair(num, 31, mx)
+        g.set_mins(r)
+        for v in r:
+            o.mins_push(int(v))
+        g_sk.append(g); o_sk.append(o)
+    coll = smb.SketchCollection.from_sketches(g_sk)
+    oc, osz = orc.compare_matrix(o_sk, o_sk)
+    occ = orc.count_common_matrix(o_sk, o_sk)
+    lens = np.array([len(r) for r in rows], dtype=np.uint32)
+    for r0, nr in ((0, 30), (40, 60), (200, 40), (50, 2)):  # shards of the same collection
+        common, size, ratio = smb.compare_matrix(coll, coll, "compare", r0=r0, nr=nr)
+        assert np.array_equal(common, oc[r0:r0 + nr]) and np.array_equal(size, osz[r0:r0 + nr])
+        assert np.array_equal(ratio, oc[r0:r0 + nr].astype(np.float64) / np.maximum(1, osz[r0:r0 + nr]).astype(np.float64))
+        common, size, ratio = smb.compare_matrix(coll, coll, "containment", r0=r0, nr=nr)
+        assert np.array_equal(common, occ[r0:r0 + nr])
+        assert np.array_equal(size, np.repeat(lens[r0:r0 + nr, None], len(rows), 1))
+    # a separate (small) query collection as the ROW side, the index as columns, and the other way round
+    queries = smb.SketchCollection.from_sketches(g_sk[100:120])
+    common, size, ratio = smb.compare_matrix(queries, coll, "compare")
+    assert np.array_equal(common, oc[100:120]) and np.array_equal(size, osz[100:120])
+    common, size, ratio = smb.compare_matrix(queries, coll, "containment")
+    assert np.array_equal(common, occ[100:120])
+    common, size, ratio = smb.compare_matrix(coll, queries, "containment")
+    assert np.array_equal(common, occ[:, 100:120])
+    for mode in ("similarity", "containment"):
+        got = smb.linear_find(coll, queries, mode, 0.1)
+        for q in range(20):
+            assert got[q] == orc.linear_find(o_sk, o_sk[100 + q], mode, 0.1)
+
+
 @pytest.mark.parametrize("compare_path", ["dense", "sparse"], indirect=True)
 def test_compare_mostly_unrelated_clusters(compare_path):
     # the shape the sparse path is for: clusters of related sketches, everything else disjoint
