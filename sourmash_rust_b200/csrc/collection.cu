@@ -180,7 +180,7 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
                 cld = nc;
             }
             SM_CUDA(cudaMemset2DAsync(cmat, cld * 4, 0, nc * 4, nr, st));
-            launch_probe_group(true, tkey, toff, grows, log2_t, ch, co, c0, nc, cmat, cld, nullptr, ctx.dsc(SC_CNT), st);
+            launch_probe_group(true, tkey, toff, grows, log2_t, ch, co, c0, nc, cmat, cld, nullptr, nr, ctx.dsc(SC_CNT), st);
             launch_fill_cells(ro, rnum, r0, nr, co, c0, nc, 1, cmat, cld, common, size, ratio, ld, st);
         } else {
             ctx.join[2].reserve((n_words + 1) * 8);
@@ -189,7 +189,7 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
             unsigned long long *bitmap = ctx.join[2].as<unsigned long long>();
             uint64_t *counts = ctx.join[3].as<uint64_t>(), *pre = ctx.join[4].as<uint64_t>();
             SM_CUDA(cudaMemsetAsync(bitmap, 0, n_words * 8, st));
-            launch_probe_group(false, tkey, toff, grows, log2_t, ch, co, c0, nc, nullptr, 0, bitmap, ctx.dsc(SC_CNT), st);
+            launch_probe_group(false, tkey, toff, grows, log2_t, ch, co, c0, nc, nullptr, 0, bitmap, nr, ctx.dsc(SC_CNT), st);
             launch_fill_cells(ro, rnum, r0, nr, co, c0, nc, 0, nullptr, 0, common, size, ratio, ld, st);  // as if unrelated
             launch_popc_words(bitmap, n_words, counts, st);
             scan_exclusive_u64(counts, pre, n_words, ctx.scan_tmp.p, st);
@@ -205,7 +205,7 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
                 ctx.join[5].reserve((cap + 1) * 8);
                 launch_expand_bits(bitmap, pre, n_words, ctx.join[5].as<uint64_t>(), st, cap);
                 launch_walk_pairs(ctx.join[5].as<uint64_t>(), cap, rh, ro, rnum, r0, ch, co, c0, nc, common, size, ratio, ld, st,
-                                  pre + (n_words - 1), counts + (n_words - 1));
+                                  pre + (n_words - 1), counts + (n_words - 1), nr);
             }
         }
         // The probe path is exact whatever the data; whether the dense kernels would have been faster

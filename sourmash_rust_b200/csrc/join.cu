@@ -145,7 +145,10 @@ __global__ void __launch_bounds__(256) probe_group_kernel(const unsigned long lo
                                                           const uint64_t *__restrict__ toff, const uint32_t *__restrict__ grows,
                                                           int log2_t, const uint64_t *__restrict__ ch,
                                                           const uint64_t *__restrict__ co, uint64_t c0, uint64_t nc, uint32_t *cmat,
-                                                          uint64_t ld, unsigned long long *bitmap, unsigned long long *incidences) {
+                                                          uint64_t ld, unsigned long long *bitmap, uint64_t nr,
+                                                          unsigned long long *incidences) {
+    // the bitmap of this form is COLUMN-major (bit = c * nr + r): a warp works on one column sketch, so
+    // all its bit tests -- hundreds per pair it ends up marking -- fall into one nr-bit stretch
     const int lane = threadIdx.x & 31;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint64_t T = 1ull << log2_t;
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(256) probe_group_kernel(const unsigned long lo
                 if (COUNT) {
                     atomicAdd(&cmat[r * ld + c], 1u);
                 } else {
-                    const uint64_t bit = r * nc + c;
+                    const uint64_t bit = c * nr + r;
                     const unsigned long long m = 1ull << (bit & 63);
                     if (!(bitmap[bit >> 6] & m)) atomicOr(&bitmap[bit >> 6], m);
                 }
@@ -198,11 +201,11 @@ void launch_group_fill(const uint64_t *ro, uint64_t r0, uint64_t nr, const uint3
 }
 void launch_probe_group(bool count, const unsigned long long *tkey, const uint64_t *toff, const uint32_t *grows, int log2_t,
                         const uint64_t *ch, const uint64_t *co, uint64_t c0, uint64_t nc, uint32_t *cmat, uint64_t ld,
-                        unsigned long long *bitmap, unsigned long long *incidences, cudaStream_t st) {
+                        unsigned long long *bitmap, uint64_t nr, unsigned long long *incidences, cudaStream_t st) {
     if (!nc) return;
     const unsigned grid = blocks_for(nc * 32, 256, 148 * 16);
-    if (count) probe_group_kernel<true><<<grid, 256, 0, st>>>(tkey, toff, grows, log2_t, ch, co, c0, nc, cmat, ld, bitmap, incidences);
-    else probe_group_kernel<false><<<grid, 256, 0, st>>>(tkey, toff, grows, log2_t, ch, co, c0, nc, cmat, ld, bitmap, incidences);
+    if (count) probe_group_kernel<true><<<grid, 256, 0, st>>>(tkey, toff, grows, log2_t, ch, co, c0, nc, cmat, ld, bitmap, nr, incidences);
+    else probe_group_kernel<false><<<grid, 256, 0, st>>>(tkey, toff, grows, log2_t, ch, co, c0, nc, cmat, ld, bitmap, nr, incidences);
     SM_LAUNCHED();
 }
 
@@ -393,7 +396,7 @@ __global__ void __launch_bounds__(256) walk_pairs_kernel(const uint64_t *__restr
                                                          const uint64_t *__restrict__ ch, const uint64_t *__restrict__ co,
                                                          uint64_t c0, uint64_t nc, uint32_t *common, uint32_t *size,
                                                          double *ratio, uint64_t ld, const uint64_t *n_dev_a,
-                                                         const uint64_t *n_dev_b) {
+                                                         const uint64_t *n_dev_b, uint64_t nr_transposed) {
     // the pair count either comes from the host or is read here as *n_dev_a + *n_dev_b (the tail of the
     // bitmap scan), capped by n_pairs: the launch then needs no host round trip
     if (n_dev_a) {
@@ -403,7 +406,9 @@ __global__ void __launch_bounds__(256) walk_pairs_kernel(const uint64_t *__restr
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_pairs; t += stride) {
         const uint64_t cell = pairs[t];
-        const uint64_t i = cell / nc, j = cell - i * nc;
+        uint64_t i, j;
+        if (nr_transposed) { j = cell / nr_transposed; i = cell - j * nr_transposed; }  // column-major cell ids (probe join)
+        else { i = cell / nc; j = cell - i * nc; }
         const uint64_t ab = ro[r0 + i], bb = co[c0 + j];
         const uint32_t na = (uint32_t)(ro[r0 + i + 1] - ab), nb = (uint32_t)(co[c0 + j + 1] - bb);
         const uint32_t num = rnum ? rnum[r0 + i] : 0;
@@ -428,10 +433,10 @@ __global__ void __launch_bounds__(256) walk_pairs_kernel(const uint64_t *__restr
 void launch_walk_pairs(const uint64_t *pairs, uint64_t n_pairs, const uint64_t *rh, const uint64_t *ro, const uint32_t *rnum,
                        uint64_t r0, const uint64_t *ch, const uint64_t *co, uint64_t c0, uint64_t nc, uint32_t *common,
                        uint32_t *size, double *ratio, uint64_t ld, cudaStream_t st, const uint64_t *n_dev_a,
-                       const uint64_t *n_dev_b) {
+                       const uint64_t *n_dev_b, uint64_t nr_transposed) {
     if (!n_pairs) return;
     walk_pairs_kernel<<<blocks_for(n_pairs, 256, 148 * 16), 256, 0, st>>>(pairs, n_pairs, rh, ro, rnum, r0, ch, co, c0, nc, common,
-                                                                        size, ratio, ld, n_dev_a, n_dev_b);
+                                                                        size, ratio, ld, n_dev_a, n_dev_b, nr_transposed);
     SM_LAUNCHED();
 }
 

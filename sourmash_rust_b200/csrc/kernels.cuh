@@ -166,7 +166,8 @@ void launch_group_fill(const uint64_t *ro, uint64_t r0, uint64_t nr, const uint3
 // count: counts into cmat, else related-pairs bitmap; *incidences += hits
 void launch_probe_group(bool count, const unsigned long long *tkey, const uint64_t *toff, const uint32_t *grows, int log2_t,
                         const uint64_t *ch, const uint64_t *co, uint64_t c0, uint64_t nc, uint32_t *cmat, uint64_t ld,
-                        unsigned long long *bitmap, unsigned long long *incidences, cudaStream_t st);
+                        unsigned long long *bitmap /* column-major: bit c * nr + r */, uint64_t nr,
+                        unsigned long long *incidences, cudaStream_t st);
 void launch_incidences_shared(bool count, const uint64_t *keys, const uint64_t *vals, uint64_t n, uint64_t row_lo,
                               uint64_t nr, uint32_t *cmat, uint64_t ld, unsigned long long *bitmap, uint64_t nc,
                               cudaStream_t st);
@@ -181,7 +182,7 @@ void launch_fill_cells(const uint64_t *ro, const uint32_t *rnum, uint64_t r0, ui
 void launch_walk_pairs(const uint64_t *pairs, uint64_t n_pairs, const uint64_t *rh, const uint64_t *ro, const uint32_t *rnum,
                        uint64_t r0, const uint64_t *ch, const uint64_t *co, uint64_t c0, uint64_t nc, uint32_t *common,
                        uint32_t *size, double *ratio, uint64_t ld, cudaStream_t st, const uint64_t *n_dev_a = nullptr,
-                       const uint64_t *n_dev_b = nullptr);
+                       const uint64_t *n_dev_b = nullptr, uint64_t nr_transposed = 0);
 
 // dense path for full num sketches: dense u32 ranks + fixed-length walk (join.cu)
 void launch_scatter_ranks(const uint64_t *keys, const uint64_t *vals, const uint64_t *pre, uint64_t n, uint32_t L,
