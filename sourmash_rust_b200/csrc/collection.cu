@@ -143,18 +143,23 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
     // matrix therefore costs its share of the rows, which is what lets the matrix scale over GPUs; the
     // sorted-postings join below remains for smgpu_compare_path(3) and feeds the dense rank kernel.
     const uint64_t n_rp = rows.h_offsets[r0 + nr] - rows.h_offsets[r0];
-    const bool probe = sparse && g_compare_path != 3 && n_rp > 0 && n_rp < (1ull << 31) &&
+    // the table goes over the side with fewer hashes (a query batch against an index block: the queries)
+    const bool build_cols = n_c < n_rp;
+    const uint64_t n_bp = build_cols ? n_c : n_rp, n_build = build_cols ? nc : nr;
+    const uint64_t *bh = build_cols ? ch : rh, *bo = build_cols ? co : ro, *ph = build_cols ? rh : ch, *po = build_cols ? ro : co;
+    const uint64_t b0 = build_cols ? c0 : r0, p0 = build_cols ? r0 : c0, n_probe = build_cols ? nr : nc;
+    const bool probe = sparse && g_compare_path != 3 && n_bp > 0 && n_bp < (1ull << 31) &&
                        !(rows.probe_dense_preferred && !force_sparse);
     if (probe) {
         int log2_t = 12;
-        while ((1ull << log2_t) < 2 * n_rp) log2_t++;
+        while ((1ull << log2_t) < 2 * n_bp) log2_t++;
         const uint64_t T = 1ull << log2_t;
         ctx.join[0].reserve((T + 2) * 8);
         ctx.join[1].reserve((T + 2) * 8);
         ctx.sort_tmp_k.reserve((T + 2) * 8);
         ctx.sort_tmp_v.reserve((T + 2) * 4);
-        ctx.join[6].reserve((n_rp + 1) * 4);
-        ctx.join[7].reserve((n_rp + 1) * 4);
+        ctx.join[6].reserve((n_bp + 1) * 4);
+        ctx.join[7].reserve((n_bp + 1) * 4);
         const uint64_t n_words = (nr * nc + 63) / 64;
         ctx.scan_tmp.reserve(scan_tmp_bytes(std::max<uint64_t>(T + 2, n_words)) + 256);
         unsigned long long *tkey = ctx.join[0].as<unsigned long long>(), *tcount = ctx.join[1].as<unsigned long long>();
@@ -166,9 +171,9 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
             SM_CUDA(cudaMemsetAsync(tcount, 0, (T + 2) * 8, st));
             SM_CUDA(cudaMemsetAsync(tcursor, 0, (T + 1) * 4, st));
             SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_CNT), 0, 8, st));
-            launch_group_insert(rh, ro, r0, nr, tkey, tcount, slot_of, log2_t, st);
+            launch_group_insert(bh, bo, b0, n_build, tkey, tcount, slot_of, log2_t, st);
             scan_exclusive_u64(reinterpret_cast<uint64_t *>(tcount), toff, T + 2, ctx.scan_tmp.p, st);
-            launch_group_fill(ro, r0, nr, slot_of, toff, tcursor, grows, st);
+            launch_group_fill(bo, b0, n_build, slot_of, toff, tcursor, grows, st);
         }
         ProfScope prof(PROF_COMPARE, st);
         if (mode == 1) {
@@ -180,7 +185,7 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
                 cld = nc;
             }
             SM_CUDA(cudaMemset2DAsync(cmat, cld * 4, 0, nc * 4, nr, st));
-            launch_probe_group(true, tkey, toff, grows, log2_t, ch, co, c0, nc, cmat, cld, nullptr, nr, ctx.dsc(SC_CNT), st);
+            launch_probe_group(true, build_cols, tkey, toff, grows, log2_t, ph, po, p0, n_probe, cmat, cld, nullptr, n_build, ctx.dsc(SC_CNT), st);
             launch_fill_cells(ro, rnum, r0, nr, co, c0, nc, 1, cmat, cld, common, size, ratio, ld, st);
         } else {
             ctx.join[2].reserve((n_words + 1) * 8);
@@ -189,7 +194,7 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
             unsigned long long *bitmap = ctx.join[2].as<unsigned long long>();
             uint64_t *counts = ctx.join[3].as<uint64_t>(), *pre = ctx.join[4].as<uint64_t>();
             SM_CUDA(cudaMemsetAsync(bitmap, 0, n_words * 8, st));
-            launch_probe_group(false, tkey, toff, grows, log2_t, ch, co, c0, nc, nullptr, 0, bitmap, nr, ctx.dsc(SC_CNT), st);
+            launch_probe_group(false, build_cols, tkey, toff, grows, log2_t, ph, po, p0, n_probe, nullptr, 0, bitmap, n_build, ctx.dsc(SC_CNT), st);
             launch_fill_cells(ro, rnum, r0, nr, co, c0, nc, 0, nullptr, 0, common, size, ratio, ld, st);  // as if unrelated
             launch_popc_words(bitmap, n_words, counts, st);
             scan_exclusive_u64(counts, pre, n_words, ctx.scan_tmp.p, st);
@@ -205,7 +210,7 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
                 ctx.join[5].reserve((cap + 1) * 8);
                 launch_expand_bits(bitmap, pre, n_words, ctx.join[5].as<uint64_t>(), st, cap);
                 launch_walk_pairs(ctx.join[5].as<uint64_t>(), cap, rh, ro, rnum, r0, ch, co, c0, nc, common, size, ratio, ld, st,
-                                  pre + (n_words - 1), counts + (n_words - 1), nr);
+                                  pre + (n_words - 1), counts + (n_words - 1), build_cols ? 0 : nr);  // probe-major cell ids
             }
         }
         // The probe path is exact whatever the data; whether the dense kernels would have been faster

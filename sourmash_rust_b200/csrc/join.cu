@@ -139,24 +139,27 @@ __global__ void __launch_bounds__(256) group_fill_kernel(const uint64_t *__restr
         }
     }
 }
-// COUNT: atomicAdd into cmat, else set bits of the related-pairs bitmap; *incidences += number of (row, column hash) hits
-template <bool COUNT>
+// The table is built over one side of the block (the smaller one: "build" side, `grows` holds its local
+// sketch ids) and probed with the sketches of the other; BUILD_COLS tells which is which.
+// COUNT: atomicAdd into cmat[r * ld + c], else set the pair's bit in the related-pairs bitmap, which is
+// PROBE-major (bit = p * n_build + b): a warp works on one probing sketch, so all its bit tests --
+// hundreds per pair it ends up marking -- fall into one n_build-bit stretch.
+// *incidences += number of (build sketch, probe hash) hits.
+template <bool COUNT, bool BUILD_COLS>
 __global__ void __launch_bounds__(256) probe_group_kernel(const unsigned long long *__restrict__ tkey,
                                                           const uint64_t *__restrict__ toff, const uint32_t *__restrict__ grows,
-                                                          int log2_t, const uint64_t *__restrict__ ch,
-                                                          const uint64_t *__restrict__ co, uint64_t c0, uint64_t nc, uint32_t *cmat,
-                                                          uint64_t ld, unsigned long long *bitmap, uint64_t nr,
+                                                          int log2_t, const uint64_t *__restrict__ ph,
+                                                          const uint64_t *__restrict__ po, uint64_t p0, uint64_t np, uint32_t *cmat,
+                                                          uint64_t ld, unsigned long long *bitmap, uint64_t n_build,
                                                           unsigned long long *incidences) {
-    // the bitmap of this form is COLUMN-major (bit = c * nr + r): a warp works on one column sketch, so
-    // all its bit tests -- hundreds per pair it ends up marking -- fall into one nr-bit stretch
     const int lane = threadIdx.x & 31;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint64_t T = 1ull << log2_t;
     unsigned long long local = 0;
-    for (uint64_t c = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < nc; c += warps) {
-        const uint64_t b = co[c0 + c], e = co[c0 + c + 1];
+    for (uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < np; p += warps) {
+        const uint64_t b = po[p0 + p], e = po[p0 + p + 1];
         for (uint64_t i = b + lane; i < e; i += 32) {
-            const unsigned long long h = ch[i];
+            const unsigned long long h = ph[i];
             uint64_t s;
             if (h == GROUP_EMPTY) {
                 s = T;
@@ -173,11 +176,11 @@ __global__ void __launch_bounds__(256) probe_group_kernel(const unsigned long lo
             const uint64_t jb = toff[s], je = toff[s + 1];
             local += je - jb;
             for (uint64_t j = jb; j < je; j++) {
-                const uint64_t r = grows[j];
+                const uint64_t q = grows[j];
                 if (COUNT) {
-                    atomicAdd(&cmat[r * ld + c], 1u);
+                    atomicAdd(BUILD_COLS ? &cmat[p * ld + q] : &cmat[q * ld + p], 1u);
                 } else {
-                    const uint64_t bit = c * nr + r;
+                    const uint64_t bit = p * n_build + q;
                     const unsigned long long m = 1ull << (bit & 63);
                     if (!(bitmap[bit >> 6] & m)) atomicOr(&bitmap[bit >> 6], m);
                 }
@@ -199,13 +202,15 @@ void launch_group_fill(const uint64_t *ro, uint64_t r0, uint64_t nr, const uint3
     group_fill_kernel<<<blocks_for(nr * 32, 256, 148 * 16), 256, 0, st>>>(ro, r0, nr, slot_of, toff, tcursor, grows);
     SM_LAUNCHED();
 }
-void launch_probe_group(bool count, const unsigned long long *tkey, const uint64_t *toff, const uint32_t *grows, int log2_t,
-                        const uint64_t *ch, const uint64_t *co, uint64_t c0, uint64_t nc, uint32_t *cmat, uint64_t ld,
-                        unsigned long long *bitmap, uint64_t nr, unsigned long long *incidences, cudaStream_t st) {
-    if (!nc) return;
-    const unsigned grid = blocks_for(nc * 32, 256, 148 * 16);
-    if (count) probe_group_kernel<true><<<grid, 256, 0, st>>>(tkey, toff, grows, log2_t, ch, co, c0, nc, cmat, ld, bitmap, nr, incidences);
-    else probe_group_kernel<false><<<grid, 256, 0, st>>>(tkey, toff, grows, log2_t, ch, co, c0, nc, cmat, ld, bitmap, nr, incidences);
+void launch_probe_group(bool count, bool build_cols, const unsigned long long *tkey, const uint64_t *toff, const uint32_t *grows,
+                        int log2_t, const uint64_t *ph, const uint64_t *po, uint64_t p0, uint64_t np, uint32_t *cmat, uint64_t ld,
+                        unsigned long long *bitmap, uint64_t n_build, unsigned long long *incidences, cudaStream_t st) {
+    if (!np) return;
+    const unsigned grid = blocks_for(np * 32, 256, 148 * 16);
+#define SM_PROBE(C, B) probe_group_kernel<C, B><<<grid, 256, 0, st>>>(tkey, toff, grows, log2_t, ph, po, p0, np, cmat, ld, bitmap, n_build, incidences)
+    if (count) { if (build_cols) SM_PROBE(true, true); else SM_PROBE(true, false); }
+    else { if (build_cols) SM_PROBE(false, true); else SM_PROBE(false, false); }
+#undef SM_PROBE
     SM_LAUNCHED();
 }
 

@@ -163,11 +163,12 @@ void launch_group_insert(const uint64_t *rh, const uint64_t *ro, uint64_t r0, ui
                          unsigned long long *tcount, uint32_t *slot_of, int log2_t, cudaStream_t st);
 void launch_group_fill(const uint64_t *ro, uint64_t r0, uint64_t nr, const uint32_t *slot_of, const uint64_t *toff,
                        uint32_t *tcursor, uint32_t *grows, cudaStream_t st);
-// count: counts into cmat, else related-pairs bitmap; *incidences += hits
-void launch_probe_group(bool count, const unsigned long long *tkey, const uint64_t *toff, const uint32_t *grows, int log2_t,
-                        const uint64_t *ch, const uint64_t *co, uint64_t c0, uint64_t nc, uint32_t *cmat, uint64_t ld,
-                        unsigned long long *bitmap /* column-major: bit c * nr + r */, uint64_t nr,
-                        unsigned long long *incidences, cudaStream_t st);
+// the table was built over the rows (build_cols = false) or the columns of the block; the other side's
+// sketches [p0, p0 + np) probe it.  count: counts into cmat[r * ld + c], else related-pairs bitmap with
+// bit = probe sketch * n_build + build sketch; *incidences += hits
+void launch_probe_group(bool count, bool build_cols, const unsigned long long *tkey, const uint64_t *toff, const uint32_t *grows,
+                        int log2_t, const uint64_t *ph, const uint64_t *po, uint64_t p0, uint64_t np, uint32_t *cmat, uint64_t ld,
+                        unsigned long long *bitmap, uint64_t n_build, unsigned long long *incidences, cudaStream_t st);
 void launch_incidences_shared(bool count, const uint64_t *keys, const uint64_t *vals, uint64_t n, uint64_t row_lo,
                               uint64_t nr, uint32_t *cmat, uint64_t ld, unsigned long long *bitmap, uint64_t nc,
                               cudaStream_t st);
