@@ -215,14 +215,36 @@ KB_HD void extractAw(const uint32_t *w, uint32_t s, uint32_t (&kw)[KmerGeom<K>::
 
 // window-start bitmap: bit p of the result word covers start q = 32*w + p and is set when any
 // of `span` stream bits q .. q+span-1 is set.  in[0..2] are stream words w, w+1, w+2 (span <= 64).
-KB_HD uint32_t dilate_word(uint32_t in0, uint32_t in1, uint32_t in2, int span) {
-    uint32_t acc = 0;
-    for (int j = 0; j < span; j++) {
-        const uint32_t a = (j < 32) ? in0 : in1;
-        const uint32_t b = (j < 32) ? in1 : in2;
-        acc |= kb_funnel_r(a, b, (uint32_t)(j & 31));
+// Doubling on the 96-bit window V: D_1 = V, D_2s = D_s | (D_s >> s), and for the largest power of two
+// a <= span, D_span = D_a | (D_a >> (span - a)) -- about 30 operations for k = 31 instead of 2 per base
+// of the span.
+KB_HD void kb_shr96(uint32_t &x0, uint32_t &x1, uint32_t &x2, int s) {  // (x2:x1:x0) >>= s, 0 < s < 64
+    if (s < 32) {
+        x0 = kb_funnel_r(x0, x1, (uint32_t)s);
+        x1 = kb_funnel_r(x1, x2, (uint32_t)s);
+        x2 >>= s;
+    } else {
+        x0 = kb_funnel_r(x1, x2, (uint32_t)(s - 32));  // s == 32: funnel by 0 returns x1
+        x1 = (s == 32) ? x2 : (x2 >> (s - 32));
+        x2 = 0;
     }
-    return acc;
+}
+KB_HD uint32_t dilate_word(uint32_t in0, uint32_t in1, uint32_t in2, int span) {
+    if (span <= 0) return 0;
+    uint32_t d0 = in0, d1 = in1, d2 = in2;
+    int a = 1;
+    while (2 * a <= span) {
+        uint32_t y0 = d0, y1 = d1, y2 = d2;
+        kb_shr96(y0, y1, y2, a);
+        d0 |= y0; d1 |= y1; d2 |= y2;
+        a *= 2;
+    }
+    if (span > a) {
+        uint32_t y0 = d0, y1 = d1, y2 = d2;
+        kb_shr96(y0, y1, y2, span - a);
+        d0 |= y0;
+    }
+    return d0;
 }
 
 }  // namespace smb200

@@ -165,15 +165,19 @@ __device__ __forceinline__ void mark_sequence_ends(const TileViews &v, int B, ui
             atomicOr(&v.end[j >> 5], 1u << (j & 31));
         }
     } else if (sb.offsets == nullptr) {
-        const uint64_t L = sb.read_len;
-        // ends are at m*L - 1 for m >= 1; first m with m*L - 1 >= t0
-        uint64_t m = (t0 + 1 + L - 1) / L;
-        if (m == 0) m = 1;
-        for (m += tid;; m += nthr) {
-            const uint64_t e = m * L - 1;
-            if (e >= hi || e >= sb.n) break;
-            const uint32_t j = (uint32_t)(e - t0);
-            atomicOr(&v.end[j >> 5], 1u << (j & 31));
+        // one warp does it: the 64-bit division below costs ~150 instructions per WARP, and a tile of reads
+        // holds a few dozen read ends at most
+        if (tid < 32) {
+            const uint64_t L = sb.read_len;
+            // ends are at m*L - 1 for m >= 1; first m with m*L - 1 >= t0
+            uint64_t m = (t0 + 1 + L - 1) / L;
+            if (m == 0) m = 1;
+            for (m += tid;; m += 32) {
+                const uint64_t e = m * L - 1;
+                if (e >= hi || e >= sb.n) break;
+                const uint32_t j = (uint32_t)(e - t0);
+                atomicOr(&v.end[j >> 5], 1u << (j & 31));
+            }
         }
     } else {
         // first sequence s with offsets[s+1] > t0 (its end is the first that can lie in the tile)

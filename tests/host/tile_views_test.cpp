@@ -102,6 +102,28 @@ static int run(int TILE, int trials) {
     return fails;
 }
 
+// dilate_word for every span 0..64 against the bit-by-bit definition
+static int dilate_spans() {
+    int fails = 0;
+    uint64_t x = 0x9E3779B97F4A7C15ull;
+    for (int trial = 0; trial < 400; trial++) {
+        uint32_t in[3];
+        for (int j = 0; j < 3; j++) {
+            x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+            in[j] = (uint32_t)x & ((trial % 3) ? (uint32_t)(x >> 32) : 0xFFFFFFFFu) & ((trial % 5 == 0) ? (uint32_t)(x >> 20) : 0xFFFFFFFFu);
+        }
+        for (int span = 0; span <= 64; span++) {
+            const uint32_t d = dilate_word(in[0], in[1], in[2], span);
+            for (int p = 0; p < 32; p++) {
+                bool any = false;
+                for (int j = p; j < p + span; j++) any |= (in[j >> 5] >> (j & 31)) & 1u;
+                if ((bool)((d >> p) & 1) != any) { if (fails++ < 5) printf("dilate span %d mismatch at bit %d\n", span, p); }
+            }
+        }
+    }
+    return fails;
+}
+
 int main() {
     // known answers: tests/test.rs:5 of the reference, and the oracle-derived k=21/31/51 vectors
     int fails = 0;
@@ -109,6 +131,7 @@ int main() {
     if (murmur3_h1_bytes((const uint8_t *)"GTCACCCGGTGCTGGGCGGCA", 21, 42) != 529147935188082428ULL) { printf("KAT k21 failed\n"); fails++; }
     if (murmur3_h1_bytes((const uint8_t *)"GCTCAACCTAGTCACCCGGTGCTGGGCGGCA", 31, 42) != 13824550005532878703ULL) { printf("KAT k31 failed\n"); fails++; }
     if (murmur3_h1_bytes((const uint8_t *)"CTCATTGCAGGTTAATCATGGCTCAACCTAGTCACCCGGTGCTGGGCGGCA", 51, 42) != 14476355676789784531ULL) { printf("KAT k51 failed\n"); fails++; }
+    fails += dilate_spans();
     fails += run<21>(2048, 6);
     fails += run<31>(2048, 6);
     fails += run<51>(2048, 6);
