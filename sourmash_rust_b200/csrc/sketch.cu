@@ -8,21 +8,23 @@
 // survivors at once by the sort / reduce / merge kernels of sortops.cu.
 //
 // Shape of the kernel (sm_100a):
-//   * persistent CTAs, grid = SM count x resident CTAs; each CTA walks tiles of TILE window
-//     starts round-robin;
+//   * persistent CTAs, grid = SM count x resident CTAs; tiles of TILE window starts are handed out
+//     dynamically (first tile = block index, then an atomic counter fetched one tile ahead);
 //   * the tile's TILE + halo ASCII bytes are brought HBM -> shared memory by ONE TMA bulk copy
 //     (cp.async.bulk, completion on an mbarrier); the copy of the NEXT tile is issued as soon as
 //     the current raw bytes have been consumed, so it overlaps the whole hashing phase;
 //   * the CTA turns the raw bytes into five shared-memory views (kmer_bits.cuh): upper-cased
 //     forward ASCII, reverse-complement ASCII, both strands 2-bit packed, and an invalid-base
 //     bitmap; a second short phase dilates the invalid/sequence-end bitmaps into a
-//     "window start is unusable" bitmap;
-//   * one thread per k-mer: one bit test for validity, two unaligned 2-bit extractions + one
-//     integer compare for the canonical strand, one unaligned ASCII extraction of the chosen
-//     strand, MurmurHash3 x64_128 fully unrolled for the compile-time K, `<= threshold`,
-//     warp-aggregated append of the survivors.
-// Bound: the integer pipes (about 135 instructions per k-mer at k=31 for 1 byte of HBM
-// traffic), see DESIGN.md.
+//     "window start is unusable" bitmap per k-size;
+//   * one launch serves up to three sketches (k-sizes) of the same batch: the staging above is
+//     done once per tile, then one k-mer loop per k-size walks it;
+//   * one thread per k-mer: one bit test for validity, two unaligned end-aligned 2-bit extractions
+//     + one integer compare for the canonical strand, one unaligned ASCII extraction of the
+//     chosen strand, MurmurHash3 x64_128 fully unrolled for the compile-time K (murmur3.cuh),
+//     `<= threshold`; survivors leave through a predicated branch.
+// Bound: the ALU and FMA-heavy integer pipes (160 executed instructions per k-mer at k=31 for
+// 1 byte of HBM traffic; 59-70 % of a kernel that does nothing but the hash), see DESIGN.md 4.1.
 #include "device.hpp"
 #include "kernels.cuh"
 #include "kmer_bits.cuh"
