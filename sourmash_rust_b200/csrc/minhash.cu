@@ -17,6 +17,7 @@
 #include "minhash.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.cuh"
@@ -26,6 +27,12 @@
 namespace smb200 {
 
 bool g_fuse_multi_k = true;
+static uint64_t h2d_chunk_from_env() {
+    const char *e = getenv("SMB200_H2D_CHUNK_MB");
+    uint64_t mb = e ? strtoull(e, nullptr, 10) : 8;
+    return (mb ? mb : 1) << 20;
+}
+uint64_t g_h2d_chunk_bytes = h2d_chunk_from_env();  // SMB200_H2D_CHUNK_MB overrides the 8 MiB default
 
 static const uint64_t U64_MAX = ~0ull;
 static const uint64_t LAZY_CANDIDATES = 1ull << 22;  // scaled sketches fold their candidates in past this
@@ -498,11 +505,12 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
         o.counter = mh.hs(0);
         return o;
     };
-    // copy chunks grow 4 -> 32 MiB: the first kernels start after a short copy, later chunks amortise
-    // launches.  (Larger caps were measured slower: while the chunk size doubles, the copy of chunk
-    // c+1 takes longer than the kernels of chunk c, and the kernels starve.)
-    uint64_t chunk = 4ull << 20;
-    const uint64_t CHUNK_MAX = 32ull << 20;
+    // Copy chunks of a fixed 8 MiB (tapering off at the end of the batch).  The fused multi-k kernel
+    // consumes bases at about the rate PCIe delivers them, so a chunk size that GROWS makes the kernels
+    // of chunk c finish long before the (larger) chunk c+1 has landed -- the old 4 -> 32 MiB doubling
+    // idled the GPU for ~0.5 ms per 300 MB batch.  With equal chunks only the first copy is exposed.
+    uint64_t chunk = g_h2d_chunk_bytes;
+    const uint64_t CHUNK_MAX = g_h2d_chunk_bytes;
     uint64_t copied = batch.on_device ? n : 0;
     if (!batch.on_device) SM_CUDA(cudaStreamSynchronize(st));  // scalars / offsets in place before the copy stream races ahead
     // every sketch's kernels go to its own stream, ordered after the preparation above and after
@@ -531,6 +539,7 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
     }
     auto in_fused = [&](int i) { return std::find(fused.begin(), fused.end(), i) != fused.end(); };
     size_t ev_i = 0;
+    unsigned fused_turn = 0;
     do {
         if (!batch.on_device) {
             // ... and taper off again (half of what is left, not below 2 MiB): what remains after the
@@ -569,8 +578,14 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
                     outs.first_bad[j] = force ? nullptr : m.hs(2);
                     if (j < fused.size()) ks[j] = m.ksize;
                 }
-                launch_sketch_multi(ks, (int)fused.size(), make_batch(*mhs[lead], n, p.tile_lo), outs, hi, ctx.sm_count,
-                                    kstream(lead));
+                // consecutive chunks go to two streams in turn (each with its own tile counter: the group's
+                // first two members lend theirs), so that the tail of one launch -- CTAs finishing their
+                // last tile -- is filled by the next launch instead of idling the SMs
+                const int turn = fused[fused_turn & 1];
+                fused_turn++;
+                SketchBatch sbm = make_batch(*mhs[lead], n, p.tile_lo);
+                sbm.tile_ctr = reinterpret_cast<uint32_t *>(mhs[turn]->hs(3));
+                launch_sketch_multi(ks, (int)fused.size(), sbm, outs, hi, ctx.sm_count, kstream(turn));
                 for (int j : fused) ps[j].tile_lo = hi;
             }
         }

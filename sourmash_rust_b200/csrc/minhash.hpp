@@ -19,6 +19,8 @@ namespace smb200 {
 
 // add_sequences: share one fused launch among the fast-path k-sizes of a batch (smgpu_fuse_multi_k)
 extern bool g_fuse_multi_k;
+// host batches are copied to the device in chunks of this size, overlapped with the kernels (minhash.cu)
+extern uint64_t g_h2d_chunk_bytes;
 
 // A batch of sequences as the caller holds it (host or device memory).
 //   offsets == nullptr && read_len == 0 : one sequence of n_bytes
