@@ -109,6 +109,16 @@ void launch_count_key_upto(const uint64_t *keys, const uint64_t *pos, uint64_t n
                            const unsigned long long *t_max_plus1, unsigned long long *count, cudaStream_t st);
 void launch_fix_max_abund(uint64_t *abund_x, const uint64_t *ukeys, const uint64_t *ucounts, uint64_t nu,
                           const uint64_t *x, const unsigned long long *count_upto, cudaStream_t st);
+// fast fold of scaled-sketch candidates (minhash.cu: ingest): candidates already in the sorted state bump
+// their abundance in place, the others are appended to news[] (capacity nc) through *n_news
+void launch_fold_match(const uint64_t *cand, uint64_t nc, const uint64_t *mins, uint64_t na, uint64_t *abunds /*nullable*/,
+                       uint64_t *news, unsigned long long *n_news, cudaStream_t st);
+// n_news <= fold_small_limit() new hashes: one CTA sorts and run-length reduces them (ukeys, ucnt, *n_unique),
+// then state and new keys are merged by rank into out_k / out_v (out_v nullable; abunds nullable)
+int fold_small_limit();
+void launch_fold_small(const uint64_t *news, uint32_t n_news, const uint64_t *mins, const uint64_t *abunds, uint64_t na,
+                       uint64_t *ukeys, uint64_t *ucnt, unsigned long long *n_unique, uint64_t *out_k, uint64_t *out_v,
+                       cudaStream_t st);
 // ordered replay of add_hash (lib.rs:192-245) for non-standard parameter combinations
 void launch_replay_add_hash(const uint64_t *events, uint64_t n_events, uint32_t num, uint64_t max_hash,
                             uint64_t *mins, uint64_t *abunds /*nullable*/, unsigned long long *len_io,

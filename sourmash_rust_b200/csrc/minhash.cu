@@ -314,7 +314,38 @@ bool KmerMinHash::ingest(Context &ctx, bool thr_is_estimate) {
 
     uint64_t *cand = d_cand_hash_.as<uint64_t>();
     uint64_t *cpos = d_cand_pos_.as<uint64_t>();
-    const uint64_t n_max = na + nc;
+    uint64_t nc_generic = nc;  // candidates the sort-based union below still has to take
+    if (m == MODE_SCALED && na > 0) {
+        // Fast path: a scaled sketch that has already seen the sample holds nearly every candidate.  Look
+        // each one up in the sorted state (abundance += 1 in place); only the hashes that are new go on.
+        ctx.misc[6].reserve((nc + 1) * 8);
+        uint64_t *news = ctx.misc[6].as<uint64_t>();
+        SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_NUNIQ), 0, 8, st));
+        launch_fold_match(cand, nc, d_mins_.as<uint64_t>(), na, has_abunds_ ? d_abunds_.as<uint64_t>() : nullptr, news,
+                          ctx.dsc(SC_NUNIQ), st);
+        ctx.read_scalars();
+        const uint64_t n_news = ctx.h_scalars[SC_NUNIQ];
+        host_valid_ = false;
+        if (n_news == 0) return true;
+        if (n_news <= (uint64_t)fold_small_limit()) {
+            // few new hashes: one CTA sorts them, then a merge by rank
+            ctx.misc[3].reserve((n_news + 1) * 8);
+            ctx.misc[4].reserve((n_news + 1) * 8);
+            d_mins_alt_.reserve((na + n_news + 1) * 8);
+            if (has_abunds_) d_abunds_alt_.reserve((na + n_news + 1) * 8);
+            launch_fold_small(news, (uint32_t)n_news, d_mins_.as<uint64_t>(), has_abunds_ ? d_abunds_.as<uint64_t>() : nullptr, na,
+                              ctx.misc[3].as<uint64_t>(), ctx.misc[4].as<uint64_t>(), ctx.dsc(SC_NUNIQ),
+                              d_mins_alt_.as<uint64_t>(), has_abunds_ ? d_abunds_alt_.as<uint64_t>() : nullptr, st);
+            ctx.read_scalars();
+            const uint64_t n_out = na + ctx.h_scalars[SC_NUNIQ];
+            commit(d_mins_alt_, d_abunds_alt_, n_out, n_out);
+            return true;
+        }
+        // many new hashes: they are the candidates of the generic union (the matched ones are already counted)
+        SM_CUDA(cudaMemcpyAsync(cand, news, n_news * 8, cudaMemcpyDeviceToDevice, st));
+        nc_generic = n_news;
+    }
+    const uint64_t n_max = na + nc_generic;
     ctx.sort_tmp_k.reserve((n_max + 1) * 8);
     ctx.sort_tmp_v.reserve((n_max + 1) * 8);
     ctx.scan_tmp.reserve(std::max(radix_sort_scan_bytes(n_max), scan_tmp_bytes(n_max)) + 256);
@@ -326,7 +357,7 @@ bool KmerMinHash::ingest(Context &ctx, bool thr_is_estimate) {
     // second operand of the union: the candidates themselves, or (quirk) their run-length form
     const uint64_t *b_keys = cand;
     const uint64_t *b_vals = nullptr;  // nullptr = every entry counts 1
-    uint64_t nb = nc;
+    uint64_t nb = nc_generic;
     if (quirk) {
         radix_sort_pairs(cand, cpos, nc, ctx.sort_tmp_k.as<uint64_t>(), ctx.sort_tmp_v.as<uint64_t>(), key_bits,
                          ctx.scan_tmp.p, ctx.scan_tmp.cap, st);

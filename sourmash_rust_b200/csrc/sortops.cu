@@ -3,6 +3,8 @@
 // hashes at once: LSD radix sort, run-length reduce (distinct hashes + abundance sums),
 // prefix scan, plus the small helpers of the num+abundance corner case and the ordered
 // replay used for non-standard parameter combinations.
+#include <algorithm>
+
 #include "device.hpp"
 #include "kernels.cuh"
 #include "murmur3.cuh"
@@ -468,6 +470,126 @@ void launch_replay_add_hash(const uint64_t *events, uint64_t n_events, uint32_t 
     replay_add_hash_kernel<<<1, RP_THREADS, 0, st>>>(events, n_events, num, max_hash, mins, abunds, len_io);
     SM_LAUNCHED();
 }
+
+// =====================================================================================
+// Fast fold of scaled-sketch candidates into a sorted state (minhash.cu: ingest).
+// Once a sketch has seen a few batches of a sample, nearly every candidate hash is already in the
+// state: the fold is then "look each candidate up, count it" and no sort at all.
+// =====================================================================================
+// found: abunds[pos] += 1 (when tracked); not found: appended to news[] through *n_news
+__global__ void __launch_bounds__(256) fold_match_kernel(const uint64_t *__restrict__ cand, uint64_t nc,
+                                                         const uint64_t *__restrict__ mins, uint64_t na,
+                                                         unsigned long long *abunds, uint64_t *news,
+                                                         unsigned long long *n_news) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_round = (nc + 31) / 32 * 32;
+    const int lane = threadIdx.x & 31;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        bool is_new = false;
+        uint64_t h = 0;
+        if (i < nc) {
+            h = cand[i];
+            uint64_t lo = 0, hi = na;
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi) >> 1;
+                if (mins[mid] < h) lo = mid + 1; else hi = mid;
+            }
+            if (lo < na && mins[lo] == h) {
+                if (abunds) atomicAdd(&abunds[lo], 1ull);
+            } else {
+                is_new = true;
+            }
+        }
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, is_new);
+        if (bal) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(n_news, (unsigned long long)__popc(bal));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (is_new) news[base + __popc(bal & ((1u << lane) - 1u))] = h;
+        }
+    }
+}
+void launch_fold_match(const uint64_t *cand, uint64_t nc, const uint64_t *mins, uint64_t na, uint64_t *abunds, uint64_t *news,
+                       unsigned long long *n_news, cudaStream_t st) {
+    if (!nc) return;
+    const uint64_t blocks = std::min<uint64_t>((nc + 255) / 256, 148 * 16);
+    fold_match_kernel<<<(unsigned)blocks, 256, 0, st>>>(cand, nc, mins, na, reinterpret_cast<unsigned long long *>(abunds), news, n_news);
+    SM_LAUNCHED();
+}
+// up to FOLD_SMALL new hashes: sorted and run-length reduced by ONE CTA in shared memory (bitonic),
+// ukeys / ucnt / *n_unique out
+constexpr int FOLD_SMALL = 2048;
+__global__ void __launch_bounds__(1024) fold_small_sort_kernel(const uint64_t *__restrict__ news, uint32_t n, uint64_t *ukeys,
+                                                               uint64_t *ucnt, unsigned long long *n_unique) {
+    __shared__ uint64_t s_k[FOLD_SMALL];
+    __shared__ uint32_t s_head[FOLD_SMALL];
+    __shared__ uint32_t s_cnt[FOLD_SMALL];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < FOLD_SMALL; i += blockDim.x) { s_k[i] = i < (int)n ? news[i] : ~0ull; s_cnt[i] = 0; }
+    __syncthreads();
+    for (int k = 2; k <= FOLD_SMALL; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < FOLD_SMALL; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const uint64_t a = s_k[i], b = s_k[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { s_k[i] = b; s_k[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // heads of runs among the first n sorted entries -> inclusive scan (serial over 2048 by warp 0 is enough: rare path)
+    for (int i = tid; i < FOLD_SMALL; i += blockDim.x) s_head[i] = (i < (int)n && (i == 0 || s_k[i] != s_k[i - 1])) ? 1u : 0u;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (uint32_t i = 0; i < n; i++) { run += s_head[i]; s_head[i] = run; }  // s_head[i] = 1-based run id
+        *n_unique = run;
+    }
+    __syncthreads();
+    for (int i = tid; i < (int)n; i += blockDim.x) {
+        const uint32_t r = s_head[i] - 1;
+        atomicAdd(&s_cnt[r], 1u);
+        if (i == 0 || s_k[i] != s_k[i - 1]) ukeys[r] = s_k[i];
+    }
+    __syncthreads();
+    const uint32_t nu = n ? s_head[n - 1] : 0;
+    for (int i = tid; i < (int)nu; i += blockDim.x) ucnt[i] = s_cnt[i];
+}
+// two sorted, disjoint key lists (a: state with values av or null; b: new keys with counts bv, *nb_dev entries)
+// -> merged into out_k / out_v by rank
+__global__ void __launch_bounds__(256) fold_merge_kernel(const uint64_t *__restrict__ a, const uint64_t *__restrict__ av, uint64_t na,
+                                                         const uint64_t *__restrict__ b, const uint64_t *__restrict__ bv,
+                                                         const unsigned long long *nb_dev, uint64_t *out_k, uint64_t *out_v) {
+    const uint64_t nb = *nb_dev;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < na + nb; t += stride) {
+        const bool from_a = t < na;
+        const uint64_t idx = from_a ? t : t - na;
+        const uint64_t key = from_a ? a[idx] : b[idx];
+        const uint64_t *o = from_a ? b : a;
+        uint64_t lo = 0, hi = from_a ? nb : na;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (o[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        out_k[idx + lo] = key;
+        if (out_v) out_v[idx + lo] = from_a ? (av ? av[idx] : 0) : bv[idx];
+    }
+}
+void launch_fold_small(const uint64_t *news, uint32_t n_news, const uint64_t *mins, const uint64_t *abunds, uint64_t na,
+                       uint64_t *ukeys, uint64_t *ucnt, unsigned long long *n_unique, uint64_t *out_k, uint64_t *out_v,
+                       cudaStream_t st) {
+    if (n_news > (uint32_t)FOLD_SMALL) throw_internal("fold_small: too many new hashes");
+    fold_small_sort_kernel<<<1, 1024, 0, st>>>(news, n_news, ukeys, ucnt, n_unique);
+    SM_LAUNCHED();
+    const uint64_t blocks = std::min<uint64_t>((na + n_news + 255) / 256, 148 * 8);
+    fold_merge_kernel<<<(unsigned)blocks, 256, 0, st>>>(mins, abunds, na, ukeys, ucnt, n_unique, out_k, out_v);
+    SM_LAUNCHED();
+}
+int fold_small_limit() { return FOLD_SMALL; }
 
 // =====================================================================================
 // INT32 issue-rate microbenchmark (roofline denominator for sketch.cu, measured live)

@@ -436,6 +436,29 @@ def test_add_hash_random_streams(abund):
         same(g, o)
 
 
+@pytest.mark.parametrize("abund", [False, True])
+def test_scaled_fold_paths(abund):
+    """Folding candidates into a scaled sketch that already holds hashes: candidates found in the state only
+    bump abundances; new ones are merged in by the one-CTA sort (up to 2048 of them) or by the generic union.
+    Batches are sized to land on every path and on the boundaries, with repeats inside a batch."""
+    mx = MAX_HASH_1000 * 100
+    pool = splitmix64(31 + abund, 40000) % np.uint64(mx)
+    g, o = pair(0, 31, mx, abund)
+    cursor = 0
+    for n_new in (3000, 0, 1, 7, 2047, 2048, 2049, 5000, 0, 300):
+        fresh = pool[cursor:cursor + n_new]
+        cursor += n_new
+        seen = pool[:cursor - n_new]
+        old = seen[:: max(1, len(seen) // 900)] if len(seen) else seen  # hashes the sketch already holds
+        batch = np.concatenate([fresh, old, fresh[::3], old[::2], np.array([mx + 5, mx + 1], dtype=np.uint64)])
+        rng = splitmix64(cursor + 1, len(batch))
+        batch = batch[np.argsort(rng, kind="stable")]  # shuffled
+        g.add_many(batch)
+        o.add_many(batch)
+        same(g, o)  # reading the sketch folds the candidates
+    assert g.md5sum() == o.md5sum()
+
+
 def test_add_word_and_add_from():
     g, o = pair(10, 5)
     for w in (b"ACGTA", b"hello", b"x" * 40, b"ACG"):
