@@ -14,7 +14,7 @@ namespace smb200 {
 #define SK_THREADS_V 256
 #endif
 #ifndef SK_CTAS_V
-#define SK_CTAS_V 8
+#define SK_CTAS_V 5   // 42 KB of tile views per CTA (byte-shifted ASCII copies): five fit the 227 KB of an SM
 #endif
 constexpr int SK_TILE = SK_TILE_V;          // window starts per tile
 constexpr int SK_THREADS = SK_THREADS_V;    // SK_TILE / SK_THREADS windows per thread per tile

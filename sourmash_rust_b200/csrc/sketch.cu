@@ -35,6 +35,9 @@ namespace smb200 {
 #ifndef SK_UNROLL
 #define SK_UNROLL 4   // windows per trip of the k-mer loop (SK_TILE / SK_THREADS must be a multiple)
 #endif
+#ifndef SK_SHIFTED
+#define SK_SHIFTED 1  // four byte-shifted copies of each ASCII strand: the k-mer loop reads aligned words (0: funnel shifts)
+#endif
 #ifndef SK_UNROLL_FUSED
 #define SK_UNROLL_FUSED 2
 #endif
@@ -93,7 +96,7 @@ constexpr int SK_PAD2 = 4;  // words in front of each 2-bit stream (extract2_end
 __host__ __device__ constexpr int tile_bases(int K) { return SK_TILE + ((K - 1 + 15) / 16) * 16; }
 __host__ __device__ constexpr size_t tile_smem_bytes(int B, int nk = 1) {
     return (size_t)B                      // raw
-           + 2 * ((size_t)B + 8)          // fA, rA
+           + (SK_SHIFTED ? 8 : 2) * ((size_t)B + 8)   // fA, rA (+ their byte-shifted copies)
            + 2 * ((size_t)B / 4 + 8 + 4 * SK_PAD2)  // f2, r2
            + 2 * ((size_t)(B + 31) / 32 * 4 + 12)  // bad, end
            + (size_t)nk * (SK_TILE / 8)   // sbad
@@ -103,8 +106,9 @@ __device__ __forceinline__ TileViews carve_tile(uint8_t *base, int B) {
     TileViews v;
     uint8_t *p = base;
     v.raw = p; p += B;                                   // B is a multiple of 16
-    v.fA = reinterpret_cast<uint32_t *>(p); p += B + 8;
-    v.rA = reinterpret_cast<uint32_t *>(p); p += B + 8;
+    // with SK_SHIFTED, copy c (bytes shifted down by c) of a strand sits c * (B + 8) bytes after copy 0
+    v.fA = reinterpret_cast<uint32_t *>(p); p += (SK_SHIFTED ? 4 : 1) * (B + 8);
+    v.rA = reinterpret_cast<uint32_t *>(p); p += (SK_SHIFTED ? 4 : 1) * (B + 8);
     v.f2 = reinterpret_cast<uint32_t *>(p) + SK_PAD2; p += B / 4 + 8 + 4 * SK_PAD2;
     v.r2 = reinterpret_cast<uint32_t *>(p) + SK_PAD2; p += B / 4 + 8 + 4 * SK_PAD2;
     const int wm = (B + 31) / 32 + 3;
@@ -153,6 +157,20 @@ __device__ __forceinline__ void build_views(const TileViews &v, int B, uint64_t 
     }
     if (B % 32) {  // B is a multiple of 16: the upper half of the last bad word is past the tile
         if (tid == 0) reinterpret_cast<uint16_t *>(v.bad)[B / 16] = 0xFFFFu;
+    }
+}
+
+// SK_SHIFTED: copies 1..3 of both ASCII strands (word w of copy c = bytes 4w + c .. 4w + c + 3), after the
+// barrier that completes fA / rA.  A k-mer starting at byte s is then words (s >> 2) .. of copy (s & 3).
+__device__ __forceinline__ void build_shifted_copies(const TileViews &v, int B) {
+    const int words = B / 4 + 1, stride = (B + 8) / 4;
+    for (int w = threadIdx.x; w < 2 * words; w += blockDim.x) {
+        uint32_t *x = (w < words) ? v.fA : v.rA;
+        const int j = (w < words) ? w : w - words;
+        const uint32_t a = x[j], b = x[j + 1];
+        x[stride + j] = kb_funnel_r(a, b, 8);
+        x[2 * stride + j] = kb_funnel_r(a, b, 16);
+        x[3 * stride + j] = kb_funnel_r(a, b, 24);
     }
 }
 
@@ -274,9 +292,15 @@ __device__ __forceinline__ void kmer_loop(const TileViews &v, const uint32_t *sb
     // 2-bit k-mers are taken end-aligned (extract2_end): NE words ending at base start + K
     const int ef0 = tid + K - 16 * G::NE, er0 = ri0 + K - 16 * G::NE;  // >= -16 * SK_PAD2
     const uint32_t *qf2 = v.f2 + (ef0 >> 4), *qr2 = v.r2 + (er0 >> 4);  // arithmetic shifts: floor
+#if SK_SHIFTED
+    constexpr int CS = (B + 8) / 4;  // words between the byte-shifted copies of a strand
+    const uint32_t *qfa = v.fA + (tid & 3) * CS + (tid >> 2), *qra = v.rA + (ri0 & 3) * CS + (ri0 >> 2);
+    (void)ra0;
+#else
     const uint32_t *qfa = v.fA + (tid >> 2), *qra = v.fA + (ra0 >> 2);
-    const uint32_t sf2 = (uint32_t)ef0 * 2u, sr2 = (uint32_t)er0 * 2u;  // funnel shifts use the low 5 bits
     const uint32_t sfa = (uint32_t)tid * 8u, sra = (uint32_t)ra0 * 8u;
+#endif
+    const uint32_t sf2 = (uint32_t)ef0 * 2u, sr2 = (uint32_t)er0 * 2u;  // funnel shifts use the low 5 bits
     const uint32_t *qsb = sbad + (tid >> 5);
     uint32_t mb = 1u << (tid & 31);
     asm("" : "+r"(mb));  // opaque: keeps the validity test a single LOP3 against a resident mask
@@ -292,7 +316,13 @@ __device__ __forceinline__ void kmer_loop(const TileViews &v, const uint32_t *sb
             const bool use_fw = canonical_is_fw<K>(ef, er);
             uint32_t kw[G::NW];
             const uint32_t *pa = use_fw ? qfa + u * (SK_THREADS / 4) : qra - u * (SK_THREADS / 4);
+#if SK_SHIFTED
+#pragma unroll
+            for (int j = 0; j < G::NW; j++) kw[j] = pa[j];
+            kw[G::NW - 1] &= G::TOPA;
+#else
             extractAw<K>(pa, use_fw ? sfa : sra, kw);
+#endif
             const uint64_t h = murmur3_h1_words<K>(kw, sb.seed);
             append_survivor(valid && h <= thr, h, t0 + (uint32_t)((r + u) * SK_THREADS), sb, out);
         }
@@ -357,6 +387,9 @@ __global__ void __launch_bounds__(SK_THREADS, SK_MIN_CTAS) sketch_kernel(const S
             }
         }
         mark_sequence_ends(v, B, t0, sb);
+#if SK_SHIFTED
+        build_shifted_copies(v, B);
+#endif
         __syncthreads();
         build_start_bitmap(v, v.sbad, KA, t0, sb, outs.first_bad[0]);
         if (KB) build_start_bitmap(v, v.sbad + SK_TILE / 32, KB, t0, sb, outs.first_bad[1]);
