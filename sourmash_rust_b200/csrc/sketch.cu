@@ -94,9 +94,16 @@ struct TileViews {
 };
 constexpr int SK_PAD2 = 4;  // words in front of each 2-bit stream (extract2_end reaches up to 64 bases back)
 __host__ __device__ constexpr int tile_bases(int K) { return SK_TILE + ((K - 1 + 15) / 16) * 16; }
+// words between the byte-shifted copies of an ASCII strand: at least the (B + 8) bytes of one copy, and
+// = 8 (mod 32) so that the 4 copies x 8 consecutive words a warp touches fall into 32 different banks
+__host__ __device__ constexpr int copy_stride_words(int B) {
+    int w = (B + 8) / 4;
+    while (w % 32 != 8) w++;
+    return w;
+}
 __host__ __device__ constexpr size_t tile_smem_bytes(int B, int nk = 1) {
     return (size_t)B                      // raw
-           + (SK_SHIFTED ? 8 : 2) * ((size_t)B + 8)   // fA, rA (+ their byte-shifted copies)
+           + (SK_SHIFTED ? 8 * (size_t)copy_stride_words(B) * 4 : 2 * ((size_t)B + 8))   // fA, rA (+ their byte-shifted copies)
            + 2 * ((size_t)B / 4 + 8 + 4 * SK_PAD2)  // f2, r2
            + 2 * ((size_t)(B + 31) / 32 * 4 + 12)  // bad, end
            + (size_t)nk * (SK_TILE / 8)   // sbad
@@ -106,9 +113,9 @@ __device__ __forceinline__ TileViews carve_tile(uint8_t *base, int B) {
     TileViews v;
     uint8_t *p = base;
     v.raw = p; p += B;                                   // B is a multiple of 16
-    // with SK_SHIFTED, copy c (bytes shifted down by c) of a strand sits c * (B + 8) bytes after copy 0
-    v.fA = reinterpret_cast<uint32_t *>(p); p += (SK_SHIFTED ? 4 : 1) * (B + 8);
-    v.rA = reinterpret_cast<uint32_t *>(p); p += (SK_SHIFTED ? 4 : 1) * (B + 8);
+    // with SK_SHIFTED, copy c (bytes shifted down by c) of a strand sits c * copy_stride_words(B) words after copy 0
+    v.fA = reinterpret_cast<uint32_t *>(p); p += SK_SHIFTED ? 16 * copy_stride_words(B) : (B + 8);
+    v.rA = reinterpret_cast<uint32_t *>(p); p += SK_SHIFTED ? 16 * copy_stride_words(B) : (B + 8);
     v.f2 = reinterpret_cast<uint32_t *>(p) + SK_PAD2; p += B / 4 + 8 + 4 * SK_PAD2;
     v.r2 = reinterpret_cast<uint32_t *>(p) + SK_PAD2; p += B / 4 + 8 + 4 * SK_PAD2;
     const int wm = (B + 31) / 32 + 3;
@@ -163,7 +170,7 @@ __device__ __forceinline__ void build_views(const TileViews &v, int B, uint64_t 
 // SK_SHIFTED: copies 1..3 of both ASCII strands (word w of copy c = bytes 4w + c .. 4w + c + 3), after the
 // barrier that completes fA / rA.  A k-mer starting at byte s is then words (s >> 2) .. of copy (s & 3).
 __device__ __forceinline__ void build_shifted_copies(const TileViews &v, int B) {
-    const int words = B / 4 + 1, stride = (B + 8) / 4;
+    const int words = B / 4 + 1, stride = copy_stride_words(B);
     for (int w = threadIdx.x; w < 2 * words; w += blockDim.x) {
         uint32_t *x = (w < words) ? v.fA : v.rA;
         const int j = (w < words) ? w : w - words;
@@ -293,7 +300,7 @@ __device__ __forceinline__ void kmer_loop(const TileViews &v, const uint32_t *sb
     const int ef0 = tid + K - 16 * G::NE, er0 = ri0 + K - 16 * G::NE;  // >= -16 * SK_PAD2
     const uint32_t *qf2 = v.f2 + (ef0 >> 4), *qr2 = v.r2 + (er0 >> 4);  // arithmetic shifts: floor
 #if SK_SHIFTED
-    constexpr int CS = (B + 8) / 4;  // words between the byte-shifted copies of a strand
+    constexpr int CS = copy_stride_words(B);  // words between the byte-shifted copies of a strand
     const uint32_t *qfa = v.fA + (tid & 3) * CS + (tid >> 2), *qra = v.rA + (ri0 & 3) * CS + (ri0 >> 2);
     (void)ra0;
 #else
