@@ -35,11 +35,11 @@ SEED_READS = 0x5EED0011
 # thread-instructions per window (smsp__inst_executed x 32 / windows), DRAM bytes per window
 # (dram__bytes_read + dram__bytes_write) and pipe utilisations; used for the integer-issue roofline and
 # roofline.traffic.  "multi" = the fused k=21/31/51 kernel (three hashes per window start).
-INSTR_PER_WINDOW = {21: 145.9, 31: 159.5, 51: 249.7, "multi": 510.6}
-DRAM_BYTES_PER_WINDOW = {21: 1.037, 31: 1.039, 51: 1.047, "multi": 1.059}
-NCU_ALU_PIPE_PCT = {21: 67.8, 31: 67.8, 51: 69.7, "multi": 67.5}
-NCU_FMAHEAVY_PIPE_PCT = {21: 64.3, 31: 65.7, 51: 61.3, "multi": 64.8}
-NCU_ISSUE_PCT = {21: 73.6, 31: 74.5, 51: 70.1, "multi": 70.8}
+INSTR_PER_WINDOW = {21: 141.0, 31: 151.9, 51: 233.9, "multi": 483.2}
+DRAM_BYTES_PER_WINDOW = {21: 1.028, 31: 1.028, 51: 1.042, "multi": 1.035}
+NCU_ALU_PIPE_PCT = {21: 66.6, 31: 64.6, 51: 68.3, "multi": 66.1}
+NCU_FMAHEAVY_PIPE_PCT = {21: 65.0, 31: 68.0, 51: 67.1, "multi": 71.9}
+NCU_ISSUE_PCT = {21: 74.6, 31: 74.4, 51: 72.6, "multi": 74.1}
 
 
 # ----------------------------------------------------------------------------------------------
