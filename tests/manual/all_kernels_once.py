@@ -1,4 +1,4 @@
-"""Small end-to-end run for compute-sanitizer (memcheck / racecheck): every kernel family once."""
+"""Small end-to-end run that launches every kernel family once (a quick check after kernel changes)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
