@@ -97,13 +97,13 @@ __host__ __device__ constexpr int tile_bases(int K) { return SK_TILE + ((K - 1 +
 // words between the byte-shifted copies of an ASCII strand: at least the (B + 8) bytes of one copy, and
 // = 8 (mod 32) so that the 4 copies x 8 consecutive words a warp touches fall into 32 different banks
 __host__ __device__ constexpr int copy_stride_words(int B) {
-    int w = (B + 8) / 4;
+    int w = (B + 8) / 4 + 4;  // (+ 4: the copy builder reads one quad past the slack words)
     while (w % 32 != 8) w++;
     return w;
 }
 __host__ __device__ constexpr size_t tile_smem_bytes(int B, int nk = 1) {
     return (size_t)B                      // raw
-           + (SK_SHIFTED ? 8 * (size_t)copy_stride_words(B) * 4 : 2 * ((size_t)B + 8))   // fA, rA (+ their byte-shifted copies)
+           + (SK_SHIFTED ? 8 * (size_t)copy_stride_words(B) * 4 : 2 * ((size_t)B + 16))   // fA, rA (+ their byte-shifted copies)
            + 2 * ((size_t)B / 4 + 8 + 4 * SK_PAD2)  // f2, r2
            + 2 * ((size_t)(B + 31) / 32 * 4 + 12)  // bad, end
            + (size_t)nk * (SK_TILE / 8)   // sbad
@@ -114,8 +114,8 @@ __device__ __forceinline__ TileViews carve_tile(uint8_t *base, int B) {
     uint8_t *p = base;
     v.raw = p; p += B;                                   // B is a multiple of 16
     // with SK_SHIFTED, copy c (bytes shifted down by c) of a strand sits c * copy_stride_words(B) words after copy 0
-    v.fA = reinterpret_cast<uint32_t *>(p); p += SK_SHIFTED ? 16 * copy_stride_words(B) : (B + 8);
-    v.rA = reinterpret_cast<uint32_t *>(p); p += SK_SHIFTED ? 16 * copy_stride_words(B) : (B + 8);
+    v.fA = reinterpret_cast<uint32_t *>(p); p += SK_SHIFTED ? 16 * copy_stride_words(B) : (B + 16);  // 16-byte aligned strands
+    v.rA = reinterpret_cast<uint32_t *>(p); p += SK_SHIFTED ? 16 * copy_stride_words(B) : (B + 16);
     v.f2 = reinterpret_cast<uint32_t *>(p) + SK_PAD2; p += B / 4 + 8 + 4 * SK_PAD2;
     v.r2 = reinterpret_cast<uint32_t *>(p) + SK_PAD2; p += B / 4 + 8 + 4 * SK_PAD2;
     const int wm = (B + 31) / 32 + 3;
@@ -143,24 +143,24 @@ __device__ __forceinline__ void build_views(const TileViews &v, int B, uint64_t 
         v.fA[B / 4 + tid] = 0; v.rA[B / 4 + tid] = 0; v.f2[B / 16 + tid] = 0; v.r2[B / 16 + tid] = 0;
     }
     if (tid < SK_PAD2) { v.f2[-1 - tid] = 0; v.r2[-1 - tid] = 0; }
-    const uint32_t *raw32 = reinterpret_cast<const uint32_t *>(v.raw);
-    uint16_t *f2h = reinterpret_cast<uint16_t *>(v.f2);
-    uint16_t *r2h = reinterpret_cast<uint16_t *>(v.r2);
-    uint8_t *badb = reinterpret_cast<uint8_t *>(v.bad);
-    const int groups = B / 8;
+    // 16 bases per trip: one 128-bit load of raw bytes, 128-bit stores of both ASCII strands, one word
+    // each of the 2-bit strands, a halfword of the invalid-base bitmap
+    const uint4 *raw128 = reinterpret_cast<const uint4 *>(v.raw);
+    uint4 *fA128 = reinterpret_cast<uint4 *>(v.fA), *rA128 = reinterpret_cast<uint4 *>(v.rA);
+    uint16_t *badh = reinterpret_cast<uint16_t *>(v.bad);
+    const int groups = B / 16;
     for (int g = tid; g < groups; g += nthr) {
-        const Oct o = classify8(raw32[2 * g], raw32[2 * g + 1]);
-        uint32_t bad8 = o.bad8;
-        const uint64_t b0 = t0 + (uint64_t)g * 8;
-        if (b0 + 8 > sb.n) bad8 |= (b0 >= sb.n) ? 0xFFu : (0xFFu << (uint32_t)(sb.n - b0)) & 0xFFu;
-        v.fA[2 * g] = o.fA0;
-        v.fA[2 * g + 1] = o.fA1;
-        const int rg = groups - 1 - g;
-        v.rA[2 * rg] = o.rA0;
-        v.rA[2 * rg + 1] = o.rA1;
-        f2h[g] = (uint16_t)o.f2;
-        r2h[rg] = (uint16_t)o.r2;
-        badb[g] = (uint8_t)bad8;
+        const uint4 raw = raw128[g];
+        const Oct o1 = classify8(raw.x, raw.y), o2 = classify8(raw.z, raw.w);
+        uint32_t bad16 = o1.bad8 | (o2.bad8 << 8);
+        const uint64_t b0 = t0 + (uint64_t)g * 16;
+        if (b0 + 16 > sb.n) bad16 |= (b0 >= sb.n) ? 0xFFFFu : (0xFFFFu << (uint32_t)(sb.n - b0)) & 0xFFFFu;
+        fA128[g] = make_uint4(o1.fA0, o1.fA1, o2.fA0, o2.fA1);
+        const int rg = groups - 1 - g;  // the reverse-complement strand runs the other way
+        rA128[rg] = make_uint4(o2.rA0, o2.rA1, o1.rA0, o1.rA1);
+        v.f2[g] = o1.f2 | (o2.f2 << 16);
+        v.r2[rg] = o2.r2 | (o1.r2 << 16);
+        badh[g] = (uint16_t)bad16;
     }
     if (B % 32) {  // B is a multiple of 16: the upper half of the last bad word is past the tile
         if (tid == 0) reinterpret_cast<uint16_t *>(v.bad)[B / 16] = 0xFFFFu;
@@ -170,14 +170,18 @@ __device__ __forceinline__ void build_views(const TileViews &v, int B, uint64_t 
 // SK_SHIFTED: copies 1..3 of both ASCII strands (word w of copy c = bytes 4w + c .. 4w + c + 3), after the
 // barrier that completes fA / rA.  A k-mer starting at byte s is then words (s >> 2) .. of copy (s & 3).
 __device__ __forceinline__ void build_shifted_copies(const TileViews &v, int B) {
-    const int words = B / 4 + 1, stride = copy_stride_words(B);
-    for (int w = threadIdx.x; w < 2 * words; w += blockDim.x) {
-        uint32_t *x = (w < words) ? v.fA : v.rA;
-        const int j = (w < words) ? w : w - words;
-        const uint32_t a = x[j], b = x[j + 1];
-        x[stride + j] = kb_funnel_r(a, b, 8);
-        x[2 * stride + j] = kb_funnel_r(a, b, 16);
-        x[3 * stride + j] = kb_funnel_r(a, b, 24);
+    // four words per trip: 128-bit load (+ the next word), three 128-bit stores
+    const int quads = (B / 4 + 1 + 3) / 4, stride4 = copy_stride_words(B) / 4;
+    for (int q = threadIdx.x; q < 2 * quads; q += blockDim.x) {
+        uint32_t *x = (q < quads) ? v.fA : v.rA;
+        const int j = (q < quads) ? q : q - quads;
+        const uint4 a = reinterpret_cast<const uint4 *>(x)[j];
+        const uint32_t n = x[4 * j + 4];  // first word of the next quad (slack words are zeroed)
+        uint4 *c = reinterpret_cast<uint4 *>(x);
+#pragma unroll
+        for (int s = 1; s < 4; s++)
+            c[s * stride4 + j] = make_uint4(kb_funnel_r(a.x, a.y, 8 * s), kb_funnel_r(a.y, a.z, 8 * s), kb_funnel_r(a.z, a.w, 8 * s),
+                                            kb_funnel_r(a.w, n, 8 * s));
     }
 }
 
@@ -287,7 +291,7 @@ __device__ __forceinline__ void append_survivor(bool pass, uint64_t h, uint64_t 
 // i = r * SK_THREADS + tid.  Per-thread constants:
 //   2-bit views: word (i >> 4), bit shift 2 * (i & 15); ASCII views: word (i >> 2), bit shift
 //   8 * (i & 3); rc(window i) starts at base B - K - i of the reverse-complement views, and rA
-//   sits (B + 8) bytes after fA (carve_tile), so one base pointer serves both ASCII strands.
+//   sits (B + 16) bytes after fA when SK_SHIFTED is off (carve_tile): one base pointer serves both strands.
 //   SK_THREADS is a multiple of 32, so the r-dependence is a pure word offset.
 template <int K, int B, int UNROLL>
 __device__ __forceinline__ void kmer_loop(const TileViews &v, const uint32_t *sbad, const uint64_t thr, const uint64_t t0,
@@ -295,7 +299,7 @@ __device__ __forceinline__ void kmer_loop(const TileViews &v, const uint32_t *sb
     using G = KmerGeom<K>;
     static_assert(SK_THREADS % 32 == 0 && 16 * G::NE - K <= 16 * SK_PAD2, "k-mer loop addressing");
     const int tid = threadIdx.x;
-    const int ri0 = B - K - tid, ra0 = B + 8 + ri0;
+    const int ri0 = B - K - tid, ra0 = B + 16 + ri0;
     // 2-bit k-mers are taken end-aligned (extract2_end): NE words ending at base start + K
     const int ef0 = tid + K - 16 * G::NE, er0 = ri0 + K - 16 * G::NE;  // >= -16 * SK_PAD2
     const uint32_t *qf2 = v.f2 + (ef0 >> 4), *qr2 = v.r2 + (er0 >> 4);  // arithmetic shifts: floor
