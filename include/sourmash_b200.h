@@ -83,7 +83,20 @@ SketchCollection *smgpu_collection_from_csr(const uint64_t *hashes /*[host|devic
                                             const uint64_t *offsets /*[host|device], n_rows + 1 */,
                                             uint64_t n_rows, uint32_t num, uint32_t ksize, uint64_t seed,
                                             uint64_t max_hash, bool on_device);
+/* One fresh sketch per sequence, pushed in order:
+ *   for s in 0..n_seqs { mh = kmerminhash_new(num, ksize, false, seed, max_hash, false);
+ *                        kmerminhash_add_sequence(mh, buf[offsets[s]..offsets[s+1]], force = true);
+ *                        smgpu_collection_push(c, mh) }
+ * (src/lib.rs:142-174, 252-274) -- the sketching half of "sketch N genomes, compare them all" -- in ONE
+ * pass over the batch instead of N calls.  Either num > 0 (bottom-num sketches) or max_hash > 0 (scaled);
+ * DNA only; invalid k-mers are skipped (force = true).  A device `buf` must be 16-byte aligned. */
+SketchCollection *smgpu_sketch_collection(const char *buf /*[host|device]*/, const uint64_t *offsets /*[host|device], n_seqs + 1 */,
+                                          uint64_t n_seqs, uint32_t num, uint32_t ksize, uint64_t seed, uint64_t max_hash,
+                                          bool on_device);
 uint64_t smgpu_collection_len(SketchCollection *c);
+/* copy the packed rows to the host: hashes (capacity = the returned total) and offsets (n_rows + 1);
+ * either may be NULL (call once with NULLs for the size) */
+uint64_t smgpu_collection_copy(SketchCollection *c, uint64_t *hashes, uint64_t *offsets);
 /* device pointers of the packed arrays (valid until the collection is modified or freed) and the
  * total number of hashes -- what a multi-GPU caller all-gathers */
 uint64_t smgpu_collection_csr(SketchCollection *c, const uint64_t **hashes_dev, const uint64_t **offsets_dev);

@@ -96,7 +96,9 @@ EXTENSION_ABI = {
     "smgpu_collection_free": (None, [vp]),
     "smgpu_collection_push": (None, [vp, vp]),
     "smgpu_collection_from_csr": (vp, [vp, vp, u64, u32, u32, u64, u64, cb]),
+    "smgpu_sketch_collection": (vp, [vp, vp, u64, u32, u32, u64, u64, cb]),
     "smgpu_collection_len": (u64, [vp]),
+    "smgpu_collection_copy": (u64, [vp, vp, vp]),
     "smgpu_collection_csr": (u64, [vp, C.POINTER(vp), C.POINTER(vp)]),
     "smgpu_compare_matrix": (None, [vp, u64, u64, vp, u64, u64, i32, vp, vp, vp, u64, cb]),
     "smgpu_scaffold_pairs": (u64, [vp, vp, vp]),
@@ -472,6 +474,27 @@ class SketchCollection:
             offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         return cls(_ptr=_call("smgpu_collection_from_csr", _vp(hashes), _vp(offsets), n_rows, num, ksize, seed,
                               max_hash, on_device))
+
+    @classmethod
+    def sketch_sequences(cls, buf, offsets, num, ksize, seed=42, max_hash=0, on_device=False, n_seqs=None):
+        """One fresh sketch per sequence buf[offsets[s]:offsets[s+1]], in one pass (smgpu_sketch_collection)."""
+        if on_device:
+            assert n_seqs is not None
+            keep_b, keep_o = buf, offsets
+        else:
+            keep_b = buf if isinstance(buf, (int, np.ndarray)) else bytes(buf)
+            keep_o = np.ascontiguousarray(offsets, dtype=np.uint64)
+            n_seqs = keep_o.size - 1
+        return cls(_ptr=_call("smgpu_sketch_collection", _vp(keep_b), _vp(keep_o), n_seqs, num, ksize, seed, max_hash, on_device))
+
+    def rows_np(self):
+        """The packed sketches as a list of numpy arrays (copies the CSR to the host)."""
+        n = len(self)
+        total = _call("smgpu_collection_copy", self._p, None, None)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        hashes = np.zeros(max(1, total), dtype=np.uint64)
+        _call("smgpu_collection_copy", self._p, _vp(hashes), _vp(offs))
+        return [hashes[int(offs[i]):int(offs[i + 1])].copy() for i in range(n)]
 
     def push(self, mh):
         _call("smgpu_collection_push", self._p, mh._p)

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libsourmash.so")
-SOURCES = ["device.cu", "sketch.cu", "sortops.cu", "compare.cu", "join.cu", "protein.cu", "minhash.cu", "collection.cu", "nodegraph.cu", "signature.cpp", "ffi.cpp"]
+SOURCES = ["device.cu", "sketch.cu", "sortops.cu", "compare.cu", "join.cu", "protein.cu", "minhash.cu", "collection.cu", "sketch_many.cu", "nodegraph.cu", "signature.cpp", "ffi.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-Wall",
          "-x", "cu"]

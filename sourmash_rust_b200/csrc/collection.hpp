@@ -35,6 +35,10 @@ struct SketchCollection {
     void check_compatible(const SketchCollection &other) const;  // lib.rs:176-190
 };
 
+// one fresh sketch per sequence of the batch, in one pass (sketch_many.cu); see include/sourmash_b200.h
+SketchCollection *sketch_collection(const uint8_t *buf, const uint64_t *offsets, uint64_t n_seqs, uint32_t num, uint32_t ksize,
+                                    uint64_t seed, uint64_t max_hash, bool on_device);
+
 extern int g_compare_path;
 // see include/sourmash_b200.h
 void compare_matrix(SketchCollection &rows, uint64_t r0, uint64_t nr, SketchCollection &cols, uint64_t c0, uint64_t nc,

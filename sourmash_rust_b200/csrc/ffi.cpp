@@ -6,6 +6,7 @@
 // returns an all-zero value.  Here the catch-all is try/catch and the slot holds (code, message).
 // The reference leaves some entry points unwrapped (they assert on NULL and abort); this build
 // wraps all of them, which only adds recorded errors where the reference would have aborted.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -501,8 +502,29 @@ SketchCollection *smgpu_collection_from_csr(const uint64_t *hashes, const uint64
         return reinterpret_cast<SketchCollection *>(COLL::from_csr(hashes, offsets, n_rows, num, ksize, seed, max_hash, on_device));
     });
 }
+SketchCollection *smgpu_sketch_collection(const char *buf, const uint64_t *offsets, uint64_t n_seqs, uint32_t num, uint32_t ksize,
+                                          uint64_t seed, uint64_t max_hash, bool on_device) {
+    return landingpad<SketchCollection *>([&]() {
+        if (n_seqs) { nonnull(offsets, "offsets"); }
+        return reinterpret_cast<SketchCollection *>(smb200::sketch_collection(reinterpret_cast<const uint8_t *>(buf), offsets, n_seqs, num,
+                                                                              ksize, seed, max_hash, on_device));
+    });
+}
 uint64_t smgpu_collection_len(SketchCollection *c) {
     return landingpad<uint64_t>([&]() { COLL *cc = coll(c); return cc->dirty ? (uint64_t)cc->h_nums.size() : cc->n_rows; });
+}
+uint64_t smgpu_collection_copy(SketchCollection *c, uint64_t *hashes, uint64_t *offsets) {
+    return landingpad<uint64_t>([&]() -> uint64_t {
+        COLL *cc = coll(c);
+        cc->finalize();
+        smb200::Context &ctx = smb200::Context::get();
+        if (offsets) std::copy(cc->h_offsets.begin(), cc->h_offsets.begin() + cc->n_rows + 1, offsets);
+        if (hashes && cc->n_hashes) {
+            SM_CUDA(cudaMemcpyAsync(hashes, cc->d_hashes.p, cc->n_hashes * 8, cudaMemcpyDeviceToHost, ctx.stream));
+            ctx.sync();
+        }
+        return cc->n_hashes;
+    });
 }
 uint64_t smgpu_collection_csr(SketchCollection *c, const uint64_t **hashes_dev, const uint64_t **offsets_dev) {
     return landingpad<uint64_t>([&]() {

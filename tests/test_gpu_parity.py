@@ -752,6 +752,44 @@ def test_cfg4_containment_search_scaled():  # BASELINE config 4 shape, reduced: 
     assert any(len(h) for h in got)
 
 
+@pytest.mark.parametrize("k", [21, 31, 51, 9])
+@pytest.mark.parametrize("num,mx", [(0, MAX_HASH_1000 * 20), (120, 0)])
+def test_sketch_collection_one_pass(k, num, mx):
+    """smgpu_sketch_collection: one fresh sketch per sequence in a single pass == the loop of
+    new + add_sequence(force=true) + push, for scaled and num sketches, ragged lengths (empty, shorter than k,
+    a few much shorter than the median so that the num threshold estimate cuts them short), dirty input."""
+    r = splitmix64(5150 + k + num, 64)
+    lens = [int(20000 + x % np.uint64(9000)) for x in r[:14]] + [0, k - 1, k, k + 5, 300, 2500, 0, 60000]
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    buf = dirty(random_dna(int(offsets[-1]), 77 + k), 88, n_bad=40)
+    # two sequences share most of their content (related sketches), one is a repeat of a short motif
+    a, b = int(offsets[1]), int(offsets[2])
+    buf = buf[:a] + buf[:b - a] + buf[b:]
+    m0 = int(offsets[5])
+    motif = (b"ACGTTGCA" * 4000)[: lens[5]]
+    buf = buf[:m0] + motif + buf[m0 + lens[5]:]
+    coll = smb.SketchCollection.sketch_sequences(buf, offsets, num, k, 42, mx)
+    assert len(coll) == len(lens)
+    rows = coll.rows_np()
+    os_ = []
+    for s in range(len(lens)):
+        o = orc.KmerMinHash(num, k, False, 42, mx, False)
+        o.add_sequence(buf[int(offsets[s]):int(offsets[s + 1])], True)
+        os_.append(o)
+        assert np.array_equal(rows[s], o.mins_np()), (s, lens[s], len(rows[s]), o.size())
+    # ... and the collection behaves like one built by pushing the sketches
+    common, size, ratio = smb.compare_matrix(coll, coll, "compare")
+    oc, osz = orc.compare_matrix(os_, os_)
+    assert np.array_equal(common, oc) and np.array_equal(size, osz)
+    # device-resident input gives the same rows
+    import torch
+    t = torch.frombuffer(bytearray(buf + b"\0" * 64), dtype=torch.uint8).cuda()
+    to = torch.from_numpy(offsets.view(np.int64)).cuda()
+    coll2 = smb.SketchCollection.sketch_sequences(t.data_ptr(), to.data_ptr(), num, k, 42, mx, on_device=True, n_seqs=len(lens))
+    for x, y in zip(rows, coll2.rows_np()):
+        assert np.array_equal(x, y)
+
+
 def test_cfg5_sketch_then_all_vs_all():  # BASELINE config 5 shape, reduced: genomes -> scaled sketches -> matrix
     roots = [random_dna(120_000, 0x5EED2000 + c) for c in range(4)]
     gs, os_ = [], []
