@@ -143,6 +143,12 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
     // matrix therefore costs its share of the rows, which is what lets the matrix scale over GPUs; the
     // sorted-postings join below remains for smgpu_compare_path(3) and feeds the dense rank kernel.
     const uint64_t n_rp = rows.h_offsets[r0 + nr] - rows.h_offsets[r0];
+    // When is the dense walk the better choice?  It costs about (|row| + |column|) / 2 steps per cell; the
+    // sparse paths cost one bitmap test per incidence plus the walk of the related pairs.  Measured at
+    // num = 500 the break-even was 8 incidences per cell, i.e. one per ~60 walk steps; scale with the
+    // sketch sizes (scaled sketches of 5 000 hashes: 80 per cell).
+    const double avg_len = 0.5 * ((double)(rows.h_offsets[r0 + nr] - rows.h_offsets[r0]) / (double)nr + (double)n_c / (double)nc);
+    const uint64_t dense_if_above = (uint64_t)((double)nr * (double)nc * std::max(1.0, avg_len / 60.0));
     // the table goes over the side with fewer hashes (a query batch against an index block: the queries)
     const bool build_cols = n_c < n_rp;
     const uint64_t n_bp = build_cols ? n_c : n_rp, n_build = build_cols ? nc : nr;
@@ -218,7 +224,7 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
         if (!rows.probe_checked && !force_sparse) {
             ctx.read_scalars();
             rows.probe_checked = true;
-            rows.probe_dense_preferred = ctx.h_scalars[SC_CNT] > 8 * nr * nc;
+            rows.probe_dense_preferred = ctx.h_scalars[SC_CNT] > dense_if_above;
         }
         return;
     }
@@ -244,7 +250,7 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
         else launch_count_incidences(keys, vals, n, ctx.dsc(SC_CNT), st);
         ctx.read_scalars();
         const uint64_t incidences = ctx.h_scalars[SC_CNT];
-        if (!force_sparse && incidences > 8 * nr * nc) sparse = false;  // mostly-related collections: the dense kernel wins
+        if (!force_sparse && incidences > dense_if_above) sparse = false;  // mostly-related collections: the dense kernel wins
     }
     if (!sparse && full && keys) {
         // ranks from the sorted postings: head flags -> scan -> scatter back to sketch order
