@@ -1,5 +1,5 @@
-"""cfg5 shape on one GPU (BASELINE.json configs[4], reduced): N synthetic 5 Mbp genomes in clusters ->
-scaled=1000, k=31 sketches -> all-vs-all Jaccard.  One-pass sketching (smgpu_sketch_collection) against the
+"""cfg5 / cfg3 shape on one GPU (BASELINE.json configs[4] reduced, configs[2] in full with --genomes 10000 --num 500
+--cluster 100): N synthetic 5 Mbp genomes in clusters -> scaled=1000 (or num) k=31 sketches -> all-vs-all Jaccard.  One-pass sketching (smgpu_sketch_collection) against the
 per-genome loop through the reference ABI."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -8,11 +8,15 @@ import numpy as np, torch
 import sourmash_rust_b200 as smb
 MAX_HASH = 18446744073709552
 N = int(sys.argv[sys.argv.index("--genomes") + 1]) if "--genomes" in sys.argv else 128
+NUM = int(sys.argv[sys.argv.index("--num") + 1]) if "--num" in sys.argv else 0   # --num 500: cfg3's sketches instead of scaled=1000
+CLUSTER = int(sys.argv[sys.argv.index("--cluster") + 1]) if "--cluster" in sys.argv else 16
+if NUM:
+    MAX_HASH = 0
 L = 5_000_000
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev); g.manual_seed(0x5EED2000)
 acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
-n_roots = max(1, N // 16)
+n_roots = max(1, N // CLUSTER)
 roots = [torch.randint(0, 4, (L,), generator=g, device=dev, dtype=torch.uint8) for _ in range(n_roots)]
 buf = torch.empty(N * L + 64, dtype=torch.uint8, device=dev)
 for i in range(N):
@@ -25,13 +29,13 @@ offs = torch.arange(N + 1, device=dev, dtype=torch.int64) * L
 torch.cuda.synchronize()
 for rep in range(2):
     t0 = time.perf_counter()
-    coll = smb.SketchCollection.sketch_sequences(buf.data_ptr(), offs.data_ptr(), 0, 31, 42, MAX_HASH, on_device=True, n_seqs=N)
+    coll = smb.SketchCollection.sketch_sequences(buf.data_ptr(), offs.data_ptr(), NUM, 31, 42, MAX_HASH, on_device=True, n_seqs=N)
     torch.cuda.synchronize(); t1 = time.perf_counter()
 print("one pass: %d genomes x %d bp sketched in %.1f ms = %.1f Gbp/s" % (N, L, (t1 - t0) * 1e3, N * L / (t1 - t0) / 1e9))
 t0 = time.perf_counter()
 sk = []
 for i in range(min(N, 32)):
-    m = smb.KmerMinHash(0, 31, False, 42, MAX_HASH, False)
+    m = smb.KmerMinHash(NUM, 31, False, 42, MAX_HASH, False)
     m.add_reads(buf.data_ptr() + i * L, 1, L, on_device=True)  # 5 MB slices are 16-byte aligned (L % 16 == 0)
     m.size()
     sk.append(m)
@@ -45,5 +49,5 @@ for rep in range(2):
     t0 = time.perf_counter()
     smb.compare_matrix_device(coll, coll, "compare", 0, N, 0, N, common.data_ptr(), size.data_ptr(), ratio.data_ptr(), N)
     torch.cuda.synchronize(); t1 = time.perf_counter()
-print("all-vs-all of %d scaled sketches (%d hashes avg): %.2f ms = %.3g pairs/s; related pairs %d" % (
+print("all-vs-all of %d sketches (%d hashes avg): %.2f ms = %.3g pairs/s; related pairs %d" % (
     N, sum(len(r) for r in rows) // N, (t1 - t0) * 1e3, N * N / (t1 - t0), int((ratio > 0.05).sum().item())))
