@@ -1,0 +1,140 @@
+"""BASELINE.json configs[4] end to end: sketch + all-vs-all Jaccard of N synthetic 5 Mbp genomes (scaled=1000, k=31),
+sharded over the GPUs of one node.  Launch with torchrun (one process per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29544 \
+        tests/manual/run_cfg5.py --genomes 100000 --cluster 100
+
+Each rank generates its own genomes on the device (clusters of related genomes: a random root, members with
+0.1-5 % substitutions), sketches them in one pass (smgpu_sketch_collection), the packed sketches are
+all-gathered over NCCL, and each rank computes its row block of the N x N matrix.  Times are device-side,
+max over ranks.  A few cells are checked against the per-object reference ABI."""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import numpy as np, torch, torch.distributed as dist
+import sourmash_rust_b200 as smb
+
+def arg(name, default):
+    return int(sys.argv[sys.argv.index(name) + 1]) if name in sys.argv else default
+
+N, CLUSTER, L = arg("--genomes", 1024), arg("--cluster", 16), arg("--length", 5_000_000)
+MAX_HASH = 18446744073709552
+rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+local = int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+smb.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+assert N % world == 0 and (N // world) % CLUSTER == 0, "genomes per rank must be a whole number of clusters"
+per = N // world
+lo = rank * per
+
+class _Ptr:  # zero-copy torch view of library-owned device memory
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+def sync_max(x):
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+# ---- synthetic genomes, generated on the device -----------------------------------------------------------
+g = torch.Generator(device=dev); g.manual_seed(0x5EED2000 + rank)
+acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+buf = torch.empty(per * L + 64, dtype=torch.uint8, device=dev)
+t0 = time.time()
+for c in range(per // CLUSTER):
+    root = torch.randint(0, 4, (L,), generator=g, device=dev, dtype=torch.uint8)
+    for m in range(CLUSTER):
+        i = c * CLUSTER + m
+        rate = (0.001, 0.005, 0.01, 0.02, 0.05)[m % 5]
+        hit = torch.rand(L, generator=g, device=dev) < rate
+        codes = torch.where(hit, (root + torch.randint(1, 4, (L,), generator=g, device=dev, dtype=torch.uint8)) % 4, root)
+        buf[i * L:(i + 1) * L] = acgt[codes.long()]
+offs = torch.arange(per + 1, device=dev, dtype=torch.int64) * L
+torch.cuda.synchronize()
+gen_s = time.time() - t0
+lib_stream = torch.cuda.ExternalStream(smb._call("smgpu_stream"))
+if world > 1:
+    dist.barrier()
+
+# ---- sketch: one pass over this rank's genomes ----------------------------------------------------------------
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+smb.SketchCollection.sketch_sequences(buf.data_ptr(), offs.data_ptr(), 0, 31, 42, MAX_HASH, on_device=True, n_seqs=min(per, 8))  # warm
+e0.record(lib_stream)
+mine = smb.SketchCollection.sketch_sequences(buf.data_ptr(), offs.data_ptr(), 0, 31, 42, MAX_HASH, on_device=True, n_seqs=per)
+e1.record(lib_stream)
+torch.cuda.synchronize()
+sketch_ms = sync_max(e0.elapsed_time(e1))
+# two sketches through the per-object ABI, for the spot check below
+ref = []
+for i in (0, 1):
+    m = smb.KmerMinHash(0, 31, False, 42, MAX_HASH, False)
+    m.add_reads(buf.data_ptr() + i * L, 1, L, on_device=True)
+    ref.append(m)
+ref_j, ref_mins = ref[0].compare(ref[1]), [r.mins_np() for r in ref]
+del buf
+torch.cuda.empty_cache()
+
+# ---- exchange: all-gather of the packed sketches (variable row lengths) ---------------------------------------------
+if world > 1:
+    warm = torch.empty(world * 1024, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(warm, torch.zeros(1024, dtype=torch.int64, device=dev))  # communicator set-up is not the exchange
+    dist.barrier()
+    torch.cuda.synchronize()
+t_x0 = torch.cuda.Event(enable_timing=True); t_x1 = torch.cuda.Event(enable_timing=True); t_c1 = torch.cuda.Event(enable_timing=True)
+t_x0.record()
+h_ptr, o_ptr, total = mine.csr_device()
+my_h = torch.as_tensor(_Ptr(h_ptr, max(1, total)), device=dev)[:total]
+my_o = torch.as_tensor(_Ptr(o_ptr, per + 1), device=dev)
+lens = (my_o[1:] - my_o[:-1]).contiguous()
+if world > 1:
+    all_lens = torch.empty(N, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_lens, lens)
+    totals = all_lens.view(world, per).sum(dim=1)
+    width = int(totals.max().item())
+    padded = torch.zeros(width, dtype=torch.int64, device=dev)
+    padded[:total] = my_h
+    gathered = torch.empty(world * width, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(gathered, padded)
+    full_h = torch.cat([gathered[r * width: r * width + int(totals[r].item())] for r in range(world)])
+    del gathered, padded
+else:
+    all_lens, full_h = lens, my_h.clone()
+full_o = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+full_o[1:] = torch.cumsum(all_lens, 0)
+torch.cuda.synchronize()
+t_x1.record()
+# ---- compare: this rank's row block of the N x N matrix -----------------------------------------------------------------
+coll = smb.SketchCollection.from_csr(full_h.data_ptr(), full_o.data_ptr(), N, 0, 31, 42, MAX_HASH, on_device=True)
+common = torch.empty((per, N), dtype=torch.int32, device=dev)
+size = torch.empty((per, N), dtype=torch.int32, device=dev)
+ratio = torch.empty((per, N), dtype=torch.float64, device=dev)
+smb.compare_matrix_device(coll, coll, "compare", lo, per, 0, N, common.data_ptr(), size.data_ptr(), ratio.data_ptr(), N)
+torch.cuda.synchronize()
+t_c1.record()
+torch.cuda.synchronize()
+exch_ms, cmp_ms = sync_max(t_x0.elapsed_time(t_x1)), sync_max(t_x1.elapsed_time(t_c1))
+
+# ---- checks ------------------------------------------------------------------------------------------------------------
+rows01 = [full_h[int(full_o[lo + i].item()): int(full_o[lo + i + 1].item())].cpu().numpy().view(np.uint64) for i in (0, 1)]
+assert all(np.array_equal(a, b) for a, b in zip(rows01, ref_mins)), "one-pass sketch differs from the per-object ABI"
+assert float(ratio[0, lo + 1].item()) == ref_j, "matrix cell differs from kmerminhash_compare"
+assert bool((ratio[torch.arange(per, device=dev), lo + torch.arange(per, device=dev)] == 1.0).all().item())
+related = int((ratio > 0.02).sum().item())
+rel = torch.tensor([related], dtype=torch.int64, device=dev)
+if world > 1:
+    dist.all_reduce(rel)
+if rank == 0:
+    print(json.dumps({
+        "workload": "cfg5: %d genomes x %d bp, scaled=1000, k=31, clusters of %d; sketch + all-vs-all Jaccard" % (N, L, CLUSTER),
+        "n_gpus": world, "genomes_per_gpu": per, "generate_s_per_rank": round(gen_s, 1),
+        "sketch_ms": sketch_ms, "sketch_gbp_s": N * L / (sketch_ms * 1e-3) / 1e9,
+        "exchange_ms": exch_ms, "compare_ms": cmp_ms, "pairs": N * N, "pairs_per_s": N * N / (cmp_ms * 1e-3),
+        "end_to_end_ms": sketch_ms + exch_ms + cmp_ms, "hashes_total": int(full_o[-1].item()),
+        "related_pairs_ratio_gt_0.02": int(rel.item()), "spot_checks": "rows 0,1 and cell (0,1) equal the per-object ABI; diagonal = 1.0"}),
+        flush=True)
+if world > 1:
+    dist.destroy_process_group()
