@@ -1,0 +1,81 @@
+"""BASELINE.json configs[3] end to end: containment search (search_minhashes_containment, threshold 0.1) of 1,000
+scaled=1000 query sketches against a linear index of N sketches (~5,000 hashes each), the index sharded over the GPUs
+of one node.  Launch with torchrun (one process per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29545 \
+        tests/manual/run_cfg4.py --index 1000000
+
+Every rank holds N / world index sketches (sorted distinct random hashes <= max_hash) in HBM; each query is half the
+hashes of one index sketch plus fresh ones; the query batch is all-gathered, each rank runs smgpu_linear_find over its
+shard, hit lists are concatenated in rank order (= LinearIndex::find's insertion order).  Times are host wall clock
+around the search call, max over ranks."""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import numpy as np, torch, torch.distributed as dist
+import sourmash_rust_b200 as smb
+
+def arg(name, default):
+    return int(sys.argv[sys.argv.index(name) + 1]) if name in sys.argv else default
+
+N, NQ, L = arg("--index", 100_000), arg("--queries", 1000), 5000
+MAX_HASH = 18446744073709552
+rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+local = int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+smb.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+assert N % world == 0 and NQ % world == 0
+per, qper = N // world, NQ // world
+g = torch.Generator(device=dev); g.manual_seed(0x5EED1000 + rank)
+idx = torch.empty((per, L), dtype=torch.int64, device=dev)
+for b0 in range(0, per, 25000):  # generate and sort in slabs
+    b1 = min(per, b0 + 25000)
+    x = torch.randint(0, MAX_HASH, (b1 - b0, L), generator=g, device=dev, dtype=torch.int64)
+    idx[b0:b1], _ = torch.sort(x, dim=1)
+    del x
+assert not (idx[:, 1:] == idx[:, :-1]).any().item()
+# this rank's share of the queries: half of the hashes of local index sketch src, half fresh
+src = (torch.arange(qper, device=dev) * 37 + 11) % per
+q = torch.cat([idx[src][:, ::2], torch.randint(0, MAX_HASH, (qper, L - L // 2), generator=g, device=dev, dtype=torch.int64)], dim=1)
+q, _ = torch.sort(q, dim=1)
+assert not (q[:, 1:] == q[:, :-1]).any().item()
+if world > 1:
+    allq = torch.empty((NQ, L), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allq, q.contiguous())
+else:
+    allq = q
+offs_i = torch.arange(per + 1, device=dev, dtype=torch.int64) * L
+offs_q = torch.arange(NQ + 1, device=dev, dtype=torch.int64) * L
+index = smb.SketchCollection.from_csr(idx.data_ptr(), offs_i.data_ptr(), per, 0, 31, 42, MAX_HASH, on_device=True)
+queries = smb.SketchCollection.from_csr(allq.data_ptr(), offs_q.data_ptr(), NQ, 0, 31, 42, MAX_HASH, on_device=True)
+del idx
+torch.cuda.empty_cache()
+times = []
+for rep in range(3):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    hits = smb.linear_find(index, queries, "containment", 0.1, hits_cap=64 * NQ)
+    torch.cuda.synchronize(); times.append(time.perf_counter() - t0)
+t = torch.tensor([min(times[1:])], dtype=torch.float64, device=dev)
+if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+# every query must be found by the rank that owns its source sketch, at the source's local row id
+own = all(int(src[j]) in hits[rank * qper + j] for j in range(qper))
+n_local = sum(len(h) for h in hits)
+stat = torch.tensor([n_local, int(own)], dtype=torch.int64, device=dev)
+mn = stat.clone()
+if world > 1:
+    dist.all_reduce(stat)
+    dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+if rank == 0:
+    sec = float(t.item())
+    print(json.dumps({"workload": "cfg4: %d scaled=1000 queries x %d-sketch linear index (~%d hashes each), containment > 0.1" % (NQ, N, L),
+                      "n_gpus": world, "index_sketches_per_gpu": per, "index_bytes_per_gpu": per * L * 8,
+                      "search_ms": sec * 1e3, "pairs": N * NQ, "pairs_per_s": N * NQ / sec, "index_sketches_per_s": N / sec,
+                      "hits_total": int(stat[0].item()), "every_planted_source_found": bool(mn[1].item())}), flush=True)
+if world > 1:
+    dist.destroy_process_group()
