@@ -168,6 +168,17 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
         ctx.join[7].reserve((n_bp + 1) * 4);
         const uint64_t n_words = (nr * nc + 63) / 64;
         ctx.scan_tmp.reserve(scan_tmp_bytes(std::max<uint64_t>(T + 2, n_words)) + 256);
+        // presence filter in front of the key table when the probing side is a different, larger collection
+        // (16 bits per build-side hash, 2^20 .. 2^30 bits)
+        const uint64_t n_pp = build_cols ? n_rp : n_c;
+        const bool use_filter = (&rows != &cols) && n_pp >= 4 * n_bp;
+        int log2_f = 20;
+        while (log2_f < 30 && (1ull << log2_f) < 16 * n_bp) log2_f++;
+        uint32_t *filter = nullptr;
+        if (use_filter) {
+            ctx.misc[1].reserve((1ull << log2_f) / 8 + 256);
+            filter = ctx.misc[1].as<uint32_t>();
+        }
         unsigned long long *tkey = ctx.join[0].as<unsigned long long>(), *tcount = ctx.join[1].as<unsigned long long>();
         uint64_t *toff = ctx.sort_tmp_k.as<uint64_t>();
         uint32_t *tcursor = ctx.sort_tmp_v.as<uint32_t>(), *slot_of = ctx.join[6].as<uint32_t>(), *grows = ctx.join[7].as<uint32_t>();
@@ -177,7 +188,8 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
             SM_CUDA(cudaMemsetAsync(tcount, 0, (T + 2) * 8, st));
             SM_CUDA(cudaMemsetAsync(tcursor, 0, (T + 1) * 4, st));
             SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_CNT), 0, 8, st));
-            launch_group_insert(bh, bo, b0, n_build, tkey, tcount, slot_of, log2_t, st);
+            if (use_filter) SM_CUDA(cudaMemsetAsync(filter, 0, (1ull << log2_f) / 8, st));
+            launch_group_insert(bh, bo, b0, n_build, tkey, tcount, slot_of, log2_t, filter, log2_f, st);
             scan_exclusive_u64(reinterpret_cast<uint64_t *>(tcount), toff, T + 2, ctx.scan_tmp.p, st);
             launch_group_fill(bo, b0, n_build, slot_of, toff, tcursor, grows, st);
         }
@@ -191,7 +203,8 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
                 cld = nc;
             }
             SM_CUDA(cudaMemset2DAsync(cmat, cld * 4, 0, nc * 4, nr, st));
-            launch_probe_group(true, build_cols, tkey, toff, grows, log2_t, ph, po, p0, n_probe, cmat, cld, nullptr, n_build, ctx.dsc(SC_CNT), st);
+            launch_probe_group(true, build_cols, tkey, toff, grows, log2_t, ph, po, p0, n_probe, cmat, cld, nullptr, n_build, ctx.dsc(SC_CNT), filter,
+                               log2_f, st);
             launch_fill_cells(ro, rnum, r0, nr, co, c0, nc, 1, cmat, cld, common, size, ratio, ld, st);
         } else {
             ctx.join[2].reserve((n_words + 1) * 8);
@@ -200,7 +213,8 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
             unsigned long long *bitmap = ctx.join[2].as<unsigned long long>();
             uint64_t *counts = ctx.join[3].as<uint64_t>(), *pre = ctx.join[4].as<uint64_t>();
             SM_CUDA(cudaMemsetAsync(bitmap, 0, n_words * 8, st));
-            launch_probe_group(false, build_cols, tkey, toff, grows, log2_t, ph, po, p0, n_probe, nullptr, 0, bitmap, n_build, ctx.dsc(SC_CNT), st);
+            launch_probe_group(false, build_cols, tkey, toff, grows, log2_t, ph, po, p0, n_probe, nullptr, 0, bitmap, n_build, ctx.dsc(SC_CNT),
+                               filter, log2_f, st);
             launch_fill_cells(ro, rnum, r0, nr, co, c0, nc, 0, nullptr, 0, common, size, ratio, ld, st);  // as if unrelated
             launch_popc_words(bitmap, n_words, counts, st);
             scan_exclusive_u64(counts, pre, n_words, ctx.scan_tmp.p, st);

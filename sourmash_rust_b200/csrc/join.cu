@@ -100,7 +100,8 @@ __device__ __forceinline__ uint64_t group_slot0(uint64_t h, int log2_t) { return
 
 __global__ void __launch_bounds__(256) group_insert_kernel(const uint64_t *__restrict__ rh, const uint64_t *__restrict__ ro,
                                                            uint64_t r0, uint64_t nr, unsigned long long *tkey,
-                                                           unsigned long long *tcount, uint32_t *slot_of, int log2_t) {
+                                                           unsigned long long *tcount, uint32_t *slot_of, int log2_t,
+                                                           uint32_t *filter, int log2_f) {
     const int lane = threadIdx.x & 31;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint64_t T = 1ull << log2_t, base = ro[r0];
@@ -122,6 +123,11 @@ __global__ void __launch_bounds__(256) group_insert_kernel(const uint64_t *__res
             }
             atomicAdd(&tcount[s], 1ull);
             slot_of[i - base] = (uint32_t)s;
+            if (filter) {  // presence bit (see probe_group_kernel)
+                const uint64_t fb = (h * 0xD6E8FEB86659FD93ull) >> (64 - log2_f);
+                const uint32_t m = 1u << (fb & 31);
+                if (!(filter[fb >> 5] & m)) atomicOr(&filter[fb >> 5], m);
+            }
         }
     }
 }
@@ -151,7 +157,11 @@ __global__ void __launch_bounds__(256) probe_group_kernel(const unsigned long lo
                                                           int log2_t, const uint64_t *__restrict__ ph,
                                                           const uint64_t *__restrict__ po, uint64_t p0, uint64_t np, uint32_t *cmat,
                                                           uint64_t ld, unsigned long long *bitmap, uint64_t n_build,
-                                                          unsigned long long *incidences) {
+                                                          unsigned long long *incidences, const uint32_t *__restrict__ filter,
+                                                          int log2_f) {
+    // `filter` (optional): one presence bit per build-side hash in a table small enough to stay in L2.  When
+    // the two sides are unrelated collections (a query batch against an index) almost every probing hash is
+    // turned away by that one bit instead of a random read in the (much larger) key table.
     const int lane = threadIdx.x & 31;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint64_t T = 1ull << log2_t;
@@ -160,6 +170,10 @@ __global__ void __launch_bounds__(256) probe_group_kernel(const unsigned long lo
         const uint64_t b = po[p0 + p], e = po[p0 + p + 1];
         for (uint64_t i = b + lane; i < e; i += 32) {
             const unsigned long long h = ph[i];
+            if (filter) {
+                const uint64_t fb = (h * 0xD6E8FEB86659FD93ull) >> (64 - log2_f);
+                if (!((filter[fb >> 5] >> (fb & 31)) & 1u)) continue;
+            }
             uint64_t s;
             if (h == GROUP_EMPTY) {
                 s = T;
@@ -191,9 +205,10 @@ __global__ void __launch_bounds__(256) probe_group_kernel(const unsigned long lo
     if (lane == 0 && local) atomicAdd(incidences, local);
 }
 void launch_group_insert(const uint64_t *rh, const uint64_t *ro, uint64_t r0, uint64_t nr, unsigned long long *tkey,
-                         unsigned long long *tcount, uint32_t *slot_of, int log2_t, cudaStream_t st) {
+                         unsigned long long *tcount, uint32_t *slot_of, int log2_t, uint32_t *filter, int log2_f, cudaStream_t st) {
     if (!nr) return;
-    group_insert_kernel<<<blocks_for(nr * 32, 256, 148 * 16), 256, 0, st>>>(rh, ro, r0, nr, tkey, tcount, slot_of, log2_t);
+    group_insert_kernel<<<blocks_for(nr * 32, 256, 148 * 16), 256, 0, st>>>(rh, ro, r0, nr, tkey, tcount, slot_of, log2_t, filter,
+                                                                           log2_f);
     SM_LAUNCHED();
 }
 void launch_group_fill(const uint64_t *ro, uint64_t r0, uint64_t nr, const uint32_t *slot_of, const uint64_t *toff,
@@ -204,10 +219,11 @@ void launch_group_fill(const uint64_t *ro, uint64_t r0, uint64_t nr, const uint3
 }
 void launch_probe_group(bool count, bool build_cols, const unsigned long long *tkey, const uint64_t *toff, const uint32_t *grows,
                         int log2_t, const uint64_t *ph, const uint64_t *po, uint64_t p0, uint64_t np, uint32_t *cmat, uint64_t ld,
-                        unsigned long long *bitmap, uint64_t n_build, unsigned long long *incidences, cudaStream_t st) {
+                        unsigned long long *bitmap, uint64_t n_build, unsigned long long *incidences, const uint32_t *filter,
+                        int log2_f, cudaStream_t st) {
     if (!np) return;
     const unsigned grid = blocks_for(np * 32, 256, 148 * 16);
-#define SM_PROBE(C, B) probe_group_kernel<C, B><<<grid, 256, 0, st>>>(tkey, toff, grows, log2_t, ph, po, p0, np, cmat, ld, bitmap, n_build, incidences)
+#define SM_PROBE(C, B) probe_group_kernel<C, B><<<grid, 256, 0, st>>>(tkey, toff, grows, log2_t, ph, po, p0, np, cmat, ld, bitmap, n_build, incidences, filter, log2_f)
     if (count) { if (build_cols) SM_PROBE(true, true); else SM_PROBE(true, false); }
     else { if (build_cols) SM_PROBE(false, true); else SM_PROBE(false, false); }
 #undef SM_PROBE

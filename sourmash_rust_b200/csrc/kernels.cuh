@@ -170,7 +170,8 @@ void launch_max_u64(const uint64_t *keys, uint64_t n, unsigned long long *out, c
 //   tkey  (2^log2_t + 1) u64, preset to ~0;  tcount (2^log2_t + 2) u64, zeroed;  tcursor (2^log2_t + 1) u32, zeroed
 //   slot_of, grows: one u32 per row posting;  toff = exclusive scan of tcount over 2^log2_t + 2 entries
 void launch_group_insert(const uint64_t *rh, const uint64_t *ro, uint64_t r0, uint64_t nr, unsigned long long *tkey,
-                         unsigned long long *tcount, uint32_t *slot_of, int log2_t, cudaStream_t st);
+                         unsigned long long *tcount, uint32_t *slot_of, int log2_t, uint32_t *filter /*nullable, zeroed, 2^log2_f bits*/,
+                         int log2_f, cudaStream_t st);
 void launch_group_fill(const uint64_t *ro, uint64_t r0, uint64_t nr, const uint32_t *slot_of, const uint64_t *toff,
                        uint32_t *tcursor, uint32_t *grows, cudaStream_t st);
 // the table was built over the rows (build_cols = false) or the columns of the block; the other side's
@@ -178,7 +179,8 @@ void launch_group_fill(const uint64_t *ro, uint64_t r0, uint64_t nr, const uint3
 // bit = probe sketch * n_build + build sketch; *incidences += hits
 void launch_probe_group(bool count, bool build_cols, const unsigned long long *tkey, const uint64_t *toff, const uint32_t *grows,
                         int log2_t, const uint64_t *ph, const uint64_t *po, uint64_t p0, uint64_t np, uint32_t *cmat, uint64_t ld,
-                        unsigned long long *bitmap, uint64_t n_build, unsigned long long *incidences, cudaStream_t st);
+                        unsigned long long *bitmap, uint64_t n_build, unsigned long long *incidences,
+                        const uint32_t *filter /*nullable: presence bits filled by launch_group_insert*/, int log2_f, cudaStream_t st);
 void launch_incidences_shared(bool count, const uint64_t *keys, const uint64_t *vals, uint64_t n, uint64_t row_lo,
                               uint64_t nr, uint32_t *cmat, uint64_t ld, unsigned long long *bitmap, uint64_t nc,
                               cudaStream_t st);
