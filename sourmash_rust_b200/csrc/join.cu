@@ -6,6 +6,8 @@
 // (count_common, lib.rs:428-436; Leaf containment, index.rs:146-160) the postings walk yields
 // the counts directly.  Results are the same integers as the dense kernel's; which path runs is
 // decided from the number of (pair, shared hash) incidences.
+#include <algorithm>
+
 #include "device.hpp"
 #include "kernels.cuh"
 
@@ -370,43 +372,45 @@ void launch_expand_bits(const unsigned long long *bitmap, const uint64_t *pre, u
     SM_LAUNCHED();
 }
 
-// every cell of the block as if the pair were unrelated (mode 0), or finished from the counts (mode 1)
+// every cell of the block as if the pair were unrelated (mode 0), or finished from the counts (mode 1).
+// One CTA row per block row (blockIdx.y strides over rows, threads over columns): no index division, the
+// row's length and num are read once per row, writes are coalesced along the row.
 __global__ void __launch_bounds__(256) fill_cells_kernel(const uint64_t *__restrict__ ro, const uint32_t *__restrict__ rnum,
                                                          uint64_t r0, uint64_t nr, const uint64_t *__restrict__ co,
                                                          uint64_t c0, uint64_t nc, int mode, const uint32_t *cmat,
                                                          uint64_t cld, uint32_t *common, uint32_t *size, double *ratio,
                                                          uint64_t ld) {
-    const uint64_t n = nr * nc;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
-        const uint64_t i = t / nc, j = t - i * nc;
+    for (uint64_t i = blockIdx.y; i < nr; i += gridDim.y) {
         const uint32_t na = (uint32_t)(ro[r0 + i + 1] - ro[r0 + i]);
-        uint32_t cm, sz;
-        double den;
-        if (mode == 0) {
-            const uint32_t nb = (uint32_t)(co[c0 + j + 1] - co[c0 + j]);
-            const uint32_t num = rnum ? rnum[r0 + i] : 0;
-            const uint64_t uni = (uint64_t)na + nb;
-            cm = 0;
-            sz = (uint32_t)((num != 0 && uni >= num) ? num : uni);  // lib.rs:391-401
-            den = (double)(sz > 1 ? sz : 1);
-        } else {
-            cm = cmat[i * cld + j];
-            sz = na;  // index.rs:152-154: the row (node) sketch is the denominator
-            den = (double)sz;
+        const uint32_t num = rnum ? rnum[r0 + i] : 0;
+        for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nc; j += (uint64_t)gridDim.x * blockDim.x) {
+            uint32_t cm, sz;
+            double den;
+            if (mode == 0) {
+                const uint32_t nb = (uint32_t)(co[c0 + j + 1] - co[c0 + j]);
+                const uint64_t uni = (uint64_t)na + nb;
+                cm = 0;
+                sz = (uint32_t)((num != 0 && uni >= num) ? num : uni);  // lib.rs:391-401
+                den = (double)(sz > 1 ? sz : 1);
+            } else {
+                cm = cmat[i * cld + j];
+                sz = na;  // index.rs:152-154: the row (node) sketch is the denominator
+                den = (double)sz;
+            }
+            const size_t at = (size_t)i * ld + j;
+            if (common) common[at] = cm;
+            if (size) size[at] = sz;
+            if (ratio) ratio[at] = (double)cm / den;
         }
-        const size_t at = (size_t)i * ld + j;
-        if (common) common[at] = cm;
-        if (size) size[at] = sz;
-        if (ratio) ratio[at] = (double)cm / den;
     }
 }
 void launch_fill_cells(const uint64_t *ro, const uint32_t *rnum, uint64_t r0, uint64_t nr, const uint64_t *co, uint64_t c0,
                        uint64_t nc, int mode, const uint32_t *cmat, uint64_t cld, uint32_t *common, uint32_t *size,
                        double *ratio, uint64_t ld, cudaStream_t st) {
     if (!nr || !nc) return;
-    fill_cells_kernel<<<blocks_for(nr * nc, 256, 148 * 32), 256, 0, st>>>(ro, rnum, r0, nr, co, c0, nc, mode, cmat, cld, common,
-                                                                        size, ratio, ld);
+    const unsigned gx = (unsigned)std::min<uint64_t>((nc + 255) / 256, 64);
+    const unsigned gy = (unsigned)std::min<uint64_t>(nr, std::max<uint64_t>(1, (148 * 32) / gx));
+    fill_cells_kernel<<<dim3(gx, gy), 256, 0, st>>>(ro, rnum, r0, nr, co, c0, nc, mode, cmat, cld, common, size, ratio, ld);
     SM_LAUNCHED();
 }
 
@@ -436,11 +440,24 @@ __global__ void __launch_bounds__(256) walk_pairs_kernel(const uint64_t *__restr
         const uint32_t limit = num ? num : 0xFFFFFFFFu;
         const uint64_t *a = rh + ab, *b = ch + bb;
         uint32_t x_i = 0, y_j = 0, c = 0, u = 0;
-        while (x_i < na && y_j < nb && u < limit) {  // lib.rs:470-499 in one pass
-            const uint64_t x = __ldg(a + x_i), y = __ldg(b + y_j);
+        // lib.rs:470-499 in one pass.  The element after the current one is loaded one step ahead on both
+        // sides (whichever side advances, its next element is already in a register), so the load latency
+        // overlaps the compare chain instead of heading it.
+        uint64_t x = na ? __ldg(a) : 0, y = nb ? __ldg(b) : 0;
+        uint64_t xn = na > 1 ? __ldg(a + 1) : 0, yn = nb > 1 ? __ldg(b + 1) : 0;
+        while (x_i < na && y_j < nb && u < limit) {
+            const bool adv_a = x <= y, adv_b = y <= x;
             c += (x == y);
-            x_i += (x <= y);
-            y_j += (y <= x);
+            if (adv_a) {
+                x_i++;
+                x = xn;
+                if (x_i + 1 < na) xn = __ldg(a + x_i + 1);
+            }
+            if (adv_b) {
+                y_j++;
+                y = yn;
+                if (y_j + 1 < nb) yn = __ldg(b + y_j + 1);
+            }
             u++;
         }
         const uint64_t uni = (uint64_t)u + (na - x_i) + (nb - y_j);
