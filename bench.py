@@ -212,6 +212,29 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host buffer is allocated:
+    first-touch then places the staging buffers on that node, so that eight ranks feeding eight GPUs do not all pull
+    their batches across the socket interconnect.  Best effort: returns the node or None."""
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -226,6 +249,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: this build has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank)
     smb.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -442,7 +466,7 @@ def run_ours(args):
                                    "track_abundance, %d reads (%d MB ASCII) per step per GPU" % (R, n_bytes >> 20),
                        "reads_per_step_per_gpu": R, "read_len": READ_LEN, "sharding": "read batches per rank, no collective",
                        "l2": "inputs (%d MB per step) larger than the 126 MB L2; %d distinct batches cycled" % (n_bytes >> 20, n_batches),
-                       "sketch_sizes": sizes},
+                       "sketch_sizes": sizes, "host_numa_node": numa},
             "e2e": {"value": e2e_value, "unit": "Gbp/s", "h2d_bytes_per_step": n_bytes,
                     "d2h_bytes_per_step": d2h_total // max(1, args.steps), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
