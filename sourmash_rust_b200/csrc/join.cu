@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(256) probe_group_kernel(const unsigned long lo
                                                           const uint64_t *__restrict__ po, uint64_t p0, uint64_t np, uint32_t *cmat,
                                                           uint64_t ld, unsigned long long *bitmap, uint64_t n_build,
                                                           unsigned long long *incidences, const uint32_t *__restrict__ filter,
-                                                          int log2_f) {
+                                                          int log2_f, bool smem_rows) {
     // `filter` (optional): one presence bit per build-side hash in a table small enough to stay in L2.  When
     // the two sides are unrelated collections (a query batch against an index) almost every probing hash is
     // turned away by that one bit instead of a random read in the (much larger) key table.
@@ -168,8 +168,16 @@ __global__ void __launch_bounds__(256) probe_group_kernel(const unsigned long lo
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint64_t T = 1ull << log2_t;
     unsigned long long local = 0;
+    // bitmap mode with a build side of up to PROBE_SMEM_ROWS sketches: one shared-memory bitmap per warp
+    extern __shared__ uint32_t s_probe[];
+    const uint32_t row_words = (uint32_t)((n_build + 31) / 32);
+    uint32_t *s_rows = (!COUNT && smem_rows) ? s_probe + (threadIdx.x >> 5) * row_words : nullptr;
     for (uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < np; p += warps) {
         const uint64_t b = po[p0 + p], e = po[p0 + p + 1];
+        if (s_rows) {
+            for (uint32_t w = lane; w < row_words; w += 32) s_rows[w] = 0;
+            __syncwarp();
+        }
         for (uint64_t i = b + lane; i < e; i += 32) {
             const unsigned long long h = ph[i];
             if (filter) {
@@ -191,21 +199,45 @@ __global__ void __launch_bounds__(256) probe_group_kernel(const unsigned long lo
             }
             const uint64_t jb = toff[s], je = toff[s + 1];
             local += je - jb;
-            for (uint64_t j = jb; j < je; j++) {
+            uint64_t j = jb;
+            if (!COUNT && s_rows) {
+                // related rows of this probing sketch are collected in the warp's shared-memory bitmap: the
+                // hundreds of repeat hits per pair cost a shared-memory test, not a global one
+                for (; j < je; j++) {
+                    const uint32_t q = grows[j];
+                    const uint32_t m = 1u << (q & 31);
+                    if (!(s_rows[q >> 5] & m)) atomicOr(&s_rows[q >> 5], m);
+                }
+            }
+            for (; j < je; j++) {
                 const uint64_t q = grows[j];
                 if (COUNT) {
                     atomicAdd(BUILD_COLS ? &cmat[p * ld + q] : &cmat[q * ld + p], 1u);
                 } else {
                     const uint64_t bit = p * n_build + q;
                     const unsigned long long m = 1ull << (bit & 63);
-                    if (!(bitmap[bit >> 6] & m)) atomicOr(&bitmap[bit >> 6], m);
+                    if (!(__ldcg(&bitmap[bit >> 6]) & m)) atomicOr(&bitmap[bit >> 6], m);  // L2 view: atomics land there
                 }
             }
+        }
+        if (s_rows) {  // flush the warp's row set into the probe-major global bitmap (32 rows per word, any alignment)
+            __syncwarp();
+            for (uint32_t w = lane; w < row_words; w += 32) {
+                const unsigned long long v = s_rows[w];
+                if (v) {
+                    const uint64_t g = p * n_build + 32ull * w;
+                    const unsigned sh = (unsigned)(g & 63);
+                    atomicOr(&bitmap[g >> 6], v << sh);
+                    if (sh > 32) atomicOr(&bitmap[(g >> 6) + 1], v >> (64 - sh));
+                }
+            }
+            __syncwarp();
         }
     }
     for (int d = 16; d; d >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, d);
     if (lane == 0 && local) atomicAdd(incidences, local);
 }
+constexpr uint64_t PROBE_SMEM_ROWS = 65536;  // 8 KB of bitmap per warp, 64 KB per CTA
 void launch_group_insert(const uint64_t *rh, const uint64_t *ro, uint64_t r0, uint64_t nr, unsigned long long *tkey,
                          unsigned long long *tcount, uint32_t *slot_of, int log2_t, uint32_t *filter, int log2_f, cudaStream_t st) {
     if (!nr) return;
@@ -224,8 +256,19 @@ void launch_probe_group(bool count, bool build_cols, const unsigned long long *t
                         unsigned long long *bitmap, uint64_t n_build, unsigned long long *incidences, const uint32_t *filter,
                         int log2_f, cudaStream_t st) {
     if (!np) return;
-    const unsigned grid = blocks_for(np * 32, 256, 148 * 16);
-#define SM_PROBE(C, B) probe_group_kernel<C, B><<<grid, 256, 0, st>>>(tkey, toff, grows, log2_t, ph, po, p0, np, cmat, ld, bitmap, n_build, incidences, filter, log2_f)
+    const bool smem_rows = !count && n_build <= PROBE_SMEM_ROWS;
+    const size_t smem = smem_rows ? 8 * ((n_build + 31) / 32) * 4 : 0;
+    // resident CTAs are limited by the shared-memory bitmaps: size the grid to what fits, a multiple of the SM count
+    unsigned per_sm = 8;
+    if (smem) per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 1024)));
+    const unsigned grid = blocks_for(np * 32, 256, 148 * std::max(2u, per_sm * 2));
+    static bool attr_set = false;
+    if (!attr_set) {
+        SM_CUDA(cudaFuncSetAttribute(probe_group_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        SM_CUDA(cudaFuncSetAttribute(probe_group_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_set = true;
+    }
+#define SM_PROBE(C, B) probe_group_kernel<C, B><<<grid, 256, smem, st>>>(tkey, toff, grows, log2_t, ph, po, p0, np, cmat, ld, bitmap, n_build, incidences, filter, log2_f, smem_rows)
     if (count) { if (build_cols) SM_PROBE(true, true); else SM_PROBE(true, false); }
     else { if (build_cols) SM_PROBE(false, true); else SM_PROBE(false, false); }
 #undef SM_PROBE
