@@ -443,7 +443,9 @@ __global__ void __launch_bounds__(256) fill_cells_kernel(const uint64_t *__restr
             const size_t at = (size_t)i * ld + j;
             if (common) common[at] = cm;
             if (size) size[at] = sz;
-            if (ratio) ratio[at] = (double)cm / den;
+            // 0 / den is +0.0 for every den > 0 (0 / 0 stays NaN below): nearly every cell of a sparse block, and
+            // an FP64 division is a ~100-instruction sequence
+            if (ratio) ratio[at] = (cm == 0 && den > 0.0) ? 0.0 : (double)cm / den;
         }
     }
 }
