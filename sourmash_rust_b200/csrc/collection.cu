@@ -105,6 +105,13 @@ static bool block_is_full(const SketchCollection &c, uint64_t first, uint64_t n,
     return true;
 }
 
+// cells (index rows x queries) per block of linear_find: SMB200_FIND_BLOCK_MCELLS overrides the default (128 M)
+static uint64_t find_block_cells_from_env() {
+    const char *e = getenv("SMB200_FIND_BLOCK_MCELLS");
+    const uint64_t m = e ? strtoull(e, nullptr, 10) : 128;
+    return (m ? m : 1) << 20;
+}
+static const uint64_t g_find_block_cells = find_block_cells_from_env();
 int g_compare_path = 0;  // 0 = choose from the data, 1 = dense tile kernel, 2 = inverted-index path, 3 = inverted index without the probe form
 
 static int bit_length64(uint64_t x) {
@@ -205,7 +212,8 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
             SM_CUDA(cudaMemset2DAsync(cmat, cld * 4, 0, nc * 4, nr, st));
             launch_probe_group(true, build_cols, tkey, toff, grows, log2_t, ph, po, p0, n_probe, cmat, cld, nullptr, n_build, ctx.dsc(SC_CNT), filter,
                                log2_f, st);
-            launch_fill_cells(ro, rnum, r0, nr, co, c0, nc, 1, cmat, cld, common, size, ratio, ld, st);
+            if (size || ratio || cmat != common)  // (counts only, straight into the caller's matrix: nothing left to do)
+                launch_fill_cells(ro, rnum, r0, nr, co, c0, nc, 1, cmat, cld, common, size, ratio, ld, st);
         } else {
             ctx.join[2].reserve((n_words + 1) * 8);
             ctx.join[3].reserve((n_words + 1) * 8);
@@ -427,14 +435,37 @@ uint64_t linear_find(SketchCollection &index, SketchCollection &queries, int mod
     if (ni && nq) {
         Context &ctx = Context::get();
         cudaStream_t st = ctx.stream;
-        const uint64_t block_rows = std::max<uint64_t>(1, std::min<uint64_t>(ni, (32ull << 20) / nq));
+        const uint64_t block_rows = std::max<uint64_t>(1, std::min<uint64_t>(ni, (g_find_block_cells) / nq));
         const uint64_t cells = block_rows * nq;
         ctx.misc[2].reserve(cells * 8);  // ratio, [index row][query]
         ctx.misc[3].reserve((cells + 1) * 8);  // flags, [query][index row]
         ctx.misc[4].reserve((cells + 1) * 8);  // scan
         ctx.misc[5].reserve((cells + 1) * 8);  // compacted cell ids
         std::vector<uint64_t> cellbuf;
-        for (uint64_t b0 = 0; b0 < ni; b0 += block_rows) {
+        // Containment with a threshold >= 0: a cell can only hit when the pair shares a hash, and the join leaves
+        // the shared-hash COUNT of every cell in a u32 matrix.  One pass over that matrix picks the hits (count
+        // > 0 and count / |node| > threshold); the f64 ratio matrix, the flag matrix, its scan and the compaction
+        // of the general path (7 GB of traffic per 128 M cells) are never materialised.
+        const bool count_path = mode == 1 && threshold >= 0.0;
+        for (uint64_t b0 = 0; count_path && b0 < ni; b0 += block_rows) {
+            const uint64_t bn = std::min(block_rows, ni - b0);
+            uint32_t *cmat = ctx.misc[2].as<uint32_t>();  // cells * 8 bytes reserved: room for the u32 counts
+            uint64_t *found = ctx.misc[3].as<uint64_t>();
+            compare_block_device(index, b0, bn, queries, 0, nq, 1, cmat, nullptr, nullptr, nq);
+            SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_CNT), 0, 8, st));
+            launch_count_hits(cmat, bn, nq, index.d_offsets.as<uint64_t>(), b0, threshold, found, cells, ctx.dsc(SC_CNT), st);
+            ctx.read_scalars();
+            const uint64_t n_hit = ctx.h_scalars[SC_CNT];
+            if (n_hit > cells) throw_internal("linear_find: hit list overflow");
+            cellbuf.resize(n_hit);
+            if (n_hit) {
+                SM_CUDA(cudaMemcpyAsync(cellbuf.data(), found, n_hit * 8, cudaMemcpyDeviceToHost, st));
+                ctx.sync();
+            }
+            std::sort(cellbuf.begin(), cellbuf.end());  // cell id = query * bn + row: per query, ascending index id
+            for (uint64_t cell : cellbuf) per_query[cell / bn].push_back(b0 + cell % bn);
+        }
+        for (uint64_t b0 = 0; !count_path && b0 < ni; b0 += block_rows) {
             const uint64_t bn = std::min(block_rows, ni - b0);
             const uint64_t n_cells = bn * nq;
             compare_block_device(index, b0, bn, queries, 0, nq, mode, nullptr, nullptr, ctx.misc[2].as<double>(), nq);

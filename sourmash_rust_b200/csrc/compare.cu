@@ -13,6 +13,8 @@
 //                    the per-lane column pointer never conflicts), the 8 row sketches of the
 //                    CTA are read through L1.  Bound: shared-memory/L1 wavefronts, not HBM.
 //   pair kernel    : one CTA per pair for the per-object C ABI (rank formulation, below).
+#include <algorithm>
+
 #include "device.hpp"
 #include "kernels.cuh"
 
@@ -293,6 +295,32 @@ void launch_compact_indices(const uint64_t *flags, const uint64_t *pre, uint64_t
     uint64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     compact_indices_kernel<<<(unsigned)blocks, 256, 0, st>>>(flags, pre, n, out);
+    SM_LAUNCHED();
+}
+
+// linear_find, containment with threshold >= 0: cells of the count matrix (row-major [index row][query], ld = nq) whose
+// count is non-zero and whose count / |node| exceeds the threshold (strict '>', search.rs:7-9; index.rs:152-154) are
+// appended as query * nr + row through *n_found (entries beyond cap are counted, not stored)
+__global__ void __launch_bounds__(256) count_hits_kernel(const uint32_t *__restrict__ cmat, uint64_t nr, uint64_t nq,
+                                                         const uint64_t *__restrict__ row_offsets, uint64_t r0, double threshold,
+                                                         uint64_t *found, uint64_t cap, unsigned long long *n_found) {
+    for (uint64_t i = blockIdx.y; i < nr; i += gridDim.y) {
+        const double den = (double)(row_offsets[r0 + i + 1] - row_offsets[r0 + i]);
+        for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nq; j += (uint64_t)gridDim.x * blockDim.x) {
+            const uint32_t cm = cmat[i * nq + j];
+            if (cm != 0 && (double)cm / den > threshold) {
+                const unsigned long long at = atomicAdd(n_found, 1ull);
+                if (at < cap) found[at] = j * nr + i;
+            }
+        }
+    }
+}
+void launch_count_hits(const uint32_t *cmat, uint64_t nr, uint64_t nq, const uint64_t *row_offsets, uint64_t r0, double threshold,
+                       uint64_t *found, uint64_t cap, unsigned long long *n_found, cudaStream_t st) {
+    if (!nr || !nq) return;
+    const unsigned gx = (unsigned)std::min<uint64_t>((nq + 255) / 256, 64);
+    const unsigned gy = (unsigned)std::min<uint64_t>(nr, std::max<uint64_t>(1, (148 * 32) / gx));
+    count_hits_kernel<<<dim3(gx, gy), 256, 0, st>>>(cmat, nr, nq, row_offsets, r0, threshold, found, cap, n_found);
     SM_LAUNCHED();
 }
 
