@@ -6,8 +6,9 @@ between ranks.  It works on any backend (NCCL on the B200 box, gloo in the CPU t
   * sketching shards by read batch / sample: no collective until the partial sketches of one
     sample are combined (allgather_sketch_state + merge, the reference's KmerMinHash::merge rule,
     src/lib.rs:307-403: set union, abundances summed);
-  * the all-vs-all matrix shards by row block; every rank needs all columns, so the packed CSR of
-    fixed-`num` sketches is all-gathered (allgather_rows);
+  * the all-vs-all matrix shards by row block; every rank needs all columns, so the packed CSR is
+    all-gathered: fixed-width rows of `num` sketches (allgather_rows), variable-length rows of scaled
+    sketches (allgather_csr);
   * linear search shards the index; per-rank hit lists are concatenated in rank order, which keeps
     LinearIndex::find's insertion order (src/index/linear.rs:34-44) (merge_hit_lists).
 """
@@ -38,6 +39,30 @@ def allgather_rows(mine, n_total, group=None):
     full = torch.empty((per * world,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
     dist.all_gather_into_tensor(full, mine.contiguous(), group=group)
     return full[:n_total]
+
+
+def allgather_csr(hashes, lens, group=None):
+    """Packed sketches with VARIABLE row lengths (scaled sketches): this rank's `hashes` (1-D int64, its rows back to
+    back) and `lens` (1-D int64, one per row; every rank holds the same number of rows) -> (all hashes in rank order,
+    offsets of all rows, n_rows + 1).  Lengths travel first; the hash arrays are padded to the longest rank for the
+    collective and the padding is dropped."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    dev = hashes.device
+    if world == 1:
+        all_lens, full = lens, hashes
+    else:
+        all_lens = torch.empty(world * lens.numel(), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_lens, lens.contiguous(), group=group)
+        totals = all_lens.view(world, lens.numel()).sum(dim=1).cpu().tolist()
+        width = max(1, max(totals))
+        padded = torch.zeros(width, dtype=torch.int64, device=dev)
+        padded[:hashes.numel()] = hashes
+        gathered = torch.empty(world * width, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gathered, padded, group=group)
+        full = torch.cat([gathered[r * width: r * width + totals[r]] for r in range(world)])
+    offsets = torch.zeros(all_lens.numel() + 1, dtype=torch.int64, device=dev)
+    offsets[1:] = torch.cumsum(all_lens, 0)
+    return full, offsets
 
 
 def allgather_sketch_state(mins, abunds=None, group=None, device=None):

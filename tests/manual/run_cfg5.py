@@ -90,21 +90,10 @@ h_ptr, o_ptr, total = mine.csr_device()
 my_h = torch.as_tensor(_Ptr(h_ptr, max(1, total)), device=dev)[:total]
 my_o = torch.as_tensor(_Ptr(o_ptr, per + 1), device=dev)
 lens = (my_o[1:] - my_o[:-1]).contiguous()
-if world > 1:
-    all_lens = torch.empty(N, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(all_lens, lens)
-    totals = all_lens.view(world, per).sum(dim=1)
-    width = int(totals.max().item())
-    padded = torch.zeros(width, dtype=torch.int64, device=dev)
-    padded[:total] = my_h
-    gathered = torch.empty(world * width, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(gathered, padded)
-    full_h = torch.cat([gathered[r * width: r * width + int(totals[r].item())] for r in range(world)])
-    del gathered, padded
-else:
-    all_lens, full_h = lens, my_h.clone()
-full_o = torch.zeros(N + 1, dtype=torch.int64, device=dev)
-full_o[1:] = torch.cumsum(all_lens, 0)
+from sourmash_rust_b200 import sharding
+full_h, full_o = sharding.allgather_csr(my_h, lens)  # lengths first, then the padded hash arrays; NCCL over NVLink
+if world == 1:
+    full_h = full_h.clone()
 torch.cuda.synchronize()
 t_x1.record()
 # ---- compare: this rank's row block of the N x N matrix -----------------------------------------------------------------

@@ -33,6 +33,17 @@ def _worker(rank, world, port, ret):
         owned = sorted(i for r in range(world) for i in range(*sharding.shard_range(n_total, r, world)))
         assert owned == list(range(n_total))
 
+        # --- all-gather of variable-length rows (scaled sketches), one rank with an empty row ------------
+        per = 3
+        rng = np.random.default_rng(7)
+        all_rows = [np.sort(rng.integers(0, 1 << 50, size=n)).astype(np.int64) for n in (5, 0, 9, 2, 7, 4)]
+        mine_rows = all_rows[rank * per:(rank + 1) * per]
+        h = torch.from_numpy(np.concatenate(mine_rows)) if sum(len(r) for r in mine_rows) else torch.zeros(0, dtype=torch.int64)
+        ln = torch.tensor([len(r) for r in mine_rows], dtype=torch.int64)
+        full_h, full_o = sharding.allgather_csr(h, ln)
+        assert full_o.tolist() == np.concatenate([[0], np.cumsum([len(r) for r in all_rows])]).tolist()
+        assert np.array_equal(full_h.numpy(), np.concatenate(all_rows))
+
         # --- sharded sketching of one sample: reads split by rank, partial sketches merged --------
         genome = random_dna(60_000, 0x5EED0010)
         n_reads = 3001
