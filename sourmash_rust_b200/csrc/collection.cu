@@ -35,7 +35,7 @@ void SketchCollection::finalize() {
     Context &ctx = Context::get();
     n_rows = h_nums.size();
     n_hashes = h_hashes.size();
-    d_hashes.reserve((n_hashes + 1) * 8);
+    d_hashes.reserve((n_hashes + 4) * 8);  // slack: the pair walk reads up to two elements past a row
     d_offsets.reserve((n_rows + 1) * 8);
     d_nums.reserve((n_rows + 1) * 4);
     if (n_hashes) SM_CUDA(cudaMemcpyAsync(d_hashes.p, h_hashes.data(), n_hashes * 8, cudaMemcpyHostToDevice, ctx.stream));
@@ -70,7 +70,7 @@ SketchCollection *SketchCollection::from_csr(const uint64_t *hashes, const uint6
     }
     c->n_hashes = c->h_offsets[n_rows_];
     c->h_nums.assign(n_rows_, num);
-    c->d_hashes.reserve((c->n_hashes + 1) * 8);
+    c->d_hashes.reserve((c->n_hashes + 4) * 8);
     c->d_offsets.reserve((n_rows_ + 1) * 8);
     c->d_nums.reserve((n_rows_ + 1) * 4);
     if (c->n_hashes) SM_CUDA(cudaMemcpyAsync(c->d_hashes.p, hashes, c->n_hashes * 8, in_kind, ctx.stream));

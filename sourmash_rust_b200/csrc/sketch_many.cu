@@ -212,7 +212,7 @@ SketchCollection *sketch_collection(const uint8_t *buf, const uint64_t *offsets,
         uint64_t total = 0;
         for (uint64_t s = 0; s < n_seqs; s++) { c->h_offsets[s] = total; total += h_kept[s]; }
         c->h_offsets[n_seqs] = total;
-        c->d_hashes.reserve((total + 1) * 8);
+        c->d_hashes.reserve((total + 4) * 8);
         many_compact_kernel<<<grid_for(count), 256, 0, st>>>(hash, keep, pre, count, c->d_hashes.as<uint64_t>());
         SM_LAUNCHED();
         c->n_hashes = total;
@@ -259,7 +259,7 @@ SketchCollection *sketch_collection(const uint8_t *buf, const uint64_t *offsets,
         out_o[n_seqs] = out_h.size();
         c->h_offsets = out_o;
         c->n_hashes = out_h.size();
-        c->d_hashes.reserve((c->n_hashes + 1) * 8);
+        c->d_hashes.reserve((c->n_hashes + 4) * 8);
         if (c->n_hashes) SM_CUDA(cudaMemcpyAsync(c->d_hashes.p, out_h.data(), c->n_hashes * 8, cudaMemcpyHostToDevice, st));
         ctx.sync();
     }
