@@ -289,10 +289,12 @@ __device__ __forceinline__ void append_survivor(bool pass, uint64_t h, uint64_t 
 // ---------------------------------------------------------------------------------------
 // The k-mer loop of one k-size over a staged tile of B bases: one thread per window start
 // i = r * SK_THREADS + tid.  Per-thread constants:
-//   2-bit views: word (i >> 4), bit shift 2 * (i & 15); ASCII views: word (i >> 2), bit shift
-//   8 * (i & 3); rc(window i) starts at base B - K - i of the reverse-complement views, and rA
-//   sits (B + 16) bytes after fA when SK_SHIFTED is off (carve_tile): one base pointer serves both strands.
-//   SK_THREADS is a multiple of 32, so the r-dependence is a pure word offset.
+//   2-bit views: word (i >> 4), bit shift 2 * (i & 15); rc(window i) starts at base B - K - i of the
+//   reverse-complement views.  ASCII views: a k-mer starting at byte s is words (s >> 2).. of the copy
+//   shifted by (s & 3) bytes -- and (s & 3) is the same for all of a thread's windows, because
+//   SK_THREADS is a multiple of 32: the r-dependence of every address is a pure word offset.
+//   (SK_SHIFTED off: one copy per strand, funnel shifts by 8 * (s & 3); rA then sits (B + 16) bytes after
+//   fA (carve_tile), so that one base pointer serves both strands.)
 template <int K, int B, int UNROLL>
 __device__ __forceinline__ void kmer_loop(const TileViews &v, const uint32_t *sbad, const uint64_t thr, const uint64_t t0,
                                           const SketchBatch &sb, const SketchOut &out) {
