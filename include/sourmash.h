@@ -149,7 +149,8 @@ SourmashStr signature_save_json(Signature *ptr);
 SourmashStr signatures_save_buffer(Signature **ptr, uintptr_t size);
 /* one Signature per stored sketch that passes the ksize (0 = any) / moltype (NULL = any, "dna" or
  * "protein", case-insensitive) filter; ignore_md5sum is accepted and ignored as in the
- * reference.  src/ffi.rs:536-604 -> src/lib.rs:593-645 */
+ * reference.  The path form reads `-` as stdin and inflates gzip input (src/file.rs:47-77).
+ * src/ffi.rs:536-604 -> src/lib.rs:593-645 */
 Signature **signatures_load_path(const char *ptr, bool ignore_md5sum, uintptr_t ksize,
                                  const char *select_moltype, uintptr_t *size);
 Signature **signatures_load_buffer(const char *ptr, uintptr_t insize, bool ignore_md5sum,

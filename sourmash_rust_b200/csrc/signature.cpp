@@ -8,7 +8,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <iostream>
 #include <sstream>
+
+#include <zlib.h>
 
 namespace smb200 {
 
@@ -362,14 +365,62 @@ std::vector<std::unique_ptr<Signature>> load_signatures(const char *data, size_t
     return out;
 }
 
+// First gzip member of `data`, inflated (what flate2::read::GzDecoder yields; src/file.rs:62-66).
+static std::string gunzip_first_member(const std::string &data) {
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, 16 + MAX_WBITS) != Z_OK) throw_internal("zlib: inflateInit2 failed");
+    std::string out;
+    std::vector<unsigned char> chunk(1 << 16);
+    size_t consumed = 0;
+    int rc = Z_OK;
+    while (rc != Z_STREAM_END) {
+        if (zs.avail_in == 0) {
+            const size_t left = data.size() - consumed;
+            if (left == 0) break;
+            const size_t take = left < (size_t(1) << 30) ? left : (size_t(1) << 30);
+            zs.next_in = (Bytef *)(data.data() + consumed);
+            zs.avail_in = (uInt)take;
+            consumed += take;
+        }
+        zs.next_out = chunk.data();
+        zs.avail_out = (uInt)chunk.size();
+        rc = inflate(&zs, Z_NO_FLUSH);
+        if (rc != Z_OK && rc != Z_STREAM_END && rc != Z_BUF_ERROR) {
+            inflateEnd(&zs);
+            throw SourmashError(ERR_SERDE, "corrupt gzip stream");
+        }
+        out.append((const char *)chunk.data(), chunk.size() - zs.avail_out);
+        if (rc == Z_BUF_ERROR && zs.avail_in == 0 && consumed == data.size()) break;
+    }
+    inflateEnd(&zs);
+    if (rc != Z_STREAM_END) throw SourmashError(ERR_SERDE, "unexpected end of gzip stream");
+    return out;
+}
+
+// Signature::from_path by way of file.rs:47-77: "-" is stdin, otherwise the file; the first bytes pick the
+// decoder (0x1F8B gzip, 0x425A bzip2, 0xFD377A585A xz).  gzip is inflated here; this image carries no bzip2 or
+// xz development files, so those two report an error instead of being decoded.
 std::vector<std::unique_ptr<Signature>> load_signatures_path(const char *path, size_t ksize, const char *moltype) {
-    std::ifstream f(path, std::ios::binary);
-    if (!f) throw SourmashError(ERR_UNKNOWN, std::string("cannot open ") + path);
     std::stringstream ss;
-    ss << f.rdbuf();
-    const std::string data = ss.str();
-    if (data.size() >= 2 && (unsigned char)data[0] == 0x1f && (unsigned char)data[1] == 0x8b)
-        throw_internal("compressed signature files are outside the scope of this build (reference src/file.rs)");
+    if (strcmp(path, "-") == 0) {
+        ss << std::cin.rdbuf();
+    } else {
+        std::ifstream f(path, std::ios::binary);
+        if (!f) throw SourmashError(ERR_PANIC, std::string("Can't open input file ") + path);  // file.rs:83 expect()
+        ss << f.rdbuf();
+    }
+    std::string data = ss.str();
+    auto starts = [&](std::initializer_list<unsigned char> magic) {
+        if (data.size() < magic.size()) return false;
+        size_t i = 0;
+        for (unsigned char m : magic)
+            if ((unsigned char)data[i++] != m) return false;
+        return true;
+    };
+    if (starts({0xFD, 0x37, 0x7A, 0x58, 0x5A})) throw_internal("xz-compressed signature files are not supported by this build");
+    if (starts({0x42, 0x5A})) throw_internal("bzip2-compressed signature files are not supported by this build");
+    if (starts({0x1F, 0x8B})) data = gunzip_first_member(data);
     return load_signatures(data.data(), data.size(), ksize, moltype);
 }
 

@@ -76,3 +76,54 @@ def test_host_bit_helpers(tmp_path):
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "host", "tile_views_test.cpp")])
     out = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
     assert out.returncode == 0, out.stdout
+
+
+def _signature_text():
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import golden
+    g = golden("genome_s10_s11.json")
+    doc = [{"class": g["class"], "email": g["email"], "hash_function": g["hash_function"], "filename": g["filename"],
+            "name": g["name"], "license": "CC0", "signatures": g["sketches"], "version": 0.4}]
+    return json.dumps(doc).encode()
+
+
+def test_load_path_sniffs_compression(smb, tmp_path):
+    """signatures_load_path goes through get_input (reference src/ffi.rs:557, src/file.rs:47-77): gzip is inflated
+    (first member only, as flate2's GzDecoder does), a plain file is read as is, and both parse to the same thing."""
+    import gzip
+    txt = _signature_text()
+    plain, packed, twice, cut = (str(tmp_path / n) for n in ("a.sig", "a.sig.gz", "two.sig.gz", "cut.sig.gz"))
+    open(plain, "wb").write(txt)
+    open(packed, "wb").write(gzip.compress(txt, 9))
+    open(twice, "wb").write(gzip.compress(txt, 1) + gzip.compress(b"trailing member, never parsed"))
+    open(cut, "wb").write(gzip.compress(txt, 9)[:-40])
+    want = [s.save_json() for s in smb.signatures_load_buffer(txt)]
+    assert len(want) == 4
+    for path in (plain, packed, twice):
+        got = smb.signatures_load_path(path)
+        assert [s.save_json() for s in got] == want, path
+    # the filters still apply after inflation
+    assert len(smb.signatures_load_path(packed, ksize=21)) == sum(1 for s in smb.signatures_load_buffer(txt, ksize=21))
+    with pytest.raises(smb.SourmashError) as e:
+        smb.signatures_load_path(cut)
+    assert e.value.code == 100004          # SerdeError: the reader fails under serde_json::from_reader
+    with pytest.raises(smb.SourmashError) as e:
+        smb.signatures_load_path(str(tmp_path / "missing.sig"))
+    assert e.value.code == 1               # Panic: file.rs:83 expect()
+    for magic in (b"BZh91AY&SY", b"\xfd7zXZ\x00\x00"):
+        p = str(tmp_path / "other.bin")
+        open(p, "wb").write(magic + b"\0" * 32)
+        with pytest.raises(smb.SourmashError) as e:
+            smb.signatures_load_path(p)
+        assert e.value.code == 2 and "not supported" in e.value.message
+
+
+def test_load_path_reads_stdin(smb, tmp_path):
+    """`-` names standard input (file.rs:49-51)."""
+    txt = _signature_text()
+    code = ("import sys; sys.path.insert(0, %r); import sourmash_rust_b200 as s; "
+            "print(len(s.signatures_load_path('-', ksize=31)))" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], input=txt, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert r.returncode == 0, r.stderr.decode()
+    assert int(r.stdout.split()[-1]) == len(smb.signatures_load_buffer(txt, ksize=31))
