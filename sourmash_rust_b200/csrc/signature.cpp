@@ -3,6 +3,8 @@
 // src/lib.rs:593-645).
 #include "signature.hpp"
 
+#include "md5.hpp"
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -37,39 +39,102 @@ static void put_str(std::string &o, const std::string &s) {  // serde_json strin
     }
     o.push_back('"');
 }
-static void put_u64(std::string &o, uint64_t v) {
-    char buf[24];
-    int n = 0;
-    do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
-    while (n) o.push_back(buf[--n]);
+// Decimal digits of v into buf, returns the count (1..20).  buf must have 20 writable bytes: all 20 are
+// stored, the first `count` are the number.  The value is cut into 4 + 8 + 8 digits so that the three
+// conversions are independent 32-bit chains rather than one 64-bit divide chain.
+static const char kDigitPairs[] =
+    "0001020304050607080910111213141516171819202122232425262728293031323334353637383940414243444546474849"
+    "5051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
+static inline void put_8_digits(uint32_t x, char *out) {  // x < 10^8, zero padded
+    const uint32_t hi = x / 10000, lo = x % 10000;
+    memcpy(out + 0, kDigitPairs + 2 * (hi / 100), 2);
+    memcpy(out + 2, kDigitPairs + 2 * (hi % 100), 2);
+    memcpy(out + 4, kDigitPairs + 2 * (lo / 100), 2);
+    memcpy(out + 6, kDigitPairs + 2 * (lo % 100), 2);
 }
-static void put_u64_array(std::string &o, const std::vector<uint64_t> &v) {
-    o.push_back('[');
+static inline int u64_digits(uint64_t v, char *buf) {
+    char tmp[40];
+    const uint64_t top = v / 10000000000000000ull, rest = v % 10000000000000000ull;  // top < 1845
+    const uint32_t mid = (uint32_t)(rest / 100000000ull), low = (uint32_t)(rest % 100000000ull);
+    memcpy(tmp + 0, kDigitPairs + 2 * (top / 100), 2);
+    memcpy(tmp + 2, kDigitPairs + 2 * (top % 100), 2);
+    put_8_digits(mid, tmp + 4);
+    put_8_digits(low, tmp + 12);
+    int lz = 0;
+    while (lz < 19 && tmp[lz] == '0') lz++;
+    memcpy(buf, tmp + lz, 20);
+    return 20 - lz;
+}
+static void put_u64(std::string &o, uint64_t v) {
+    char buf[20];
+    o.append(buf, (size_t)u64_digits(v, buf));
+}
+// "[a,b,c]"; when `md5` is given it also receives every element's digits (no separators), which is what the
+// md5sum field is taken over (lib.rs:72-77)
+static void put_u64_array(std::string &o, const std::vector<uint64_t> &v, Md5 *md5 = nullptr) {
+    const size_t base = o.size();
+    o.resize(base + 2 + v.size() * 21);
+    char *w = &o[base];
+    char plain[4096 + 20];
+    size_t np = 0;
+    *w++ = '[';
     for (size_t i = 0; i < v.size(); i++) {
-        if (i) o.push_back(',');
-        put_u64(o, v[i]);
+        if (i) *w++ = ',';
+        const int n = u64_digits(v[i], w);
+        if (md5) {
+            memcpy(plain + np, w, (size_t)n);
+            np += (size_t)n;
+            if (np >= 4096) { md5->update(reinterpret_cast<const uint8_t *>(plain), np); np = 0; }
+        }
+        w += n;
     }
-    o.push_back(']');
+    *w++ = ']';
+    if (md5 && np) md5->update(reinterpret_cast<const uint8_t *>(plain), np);
+    o.resize((size_t)(w - o.data()));
 }
 // shortest decimal that round-trips, in the shape serde_json (ryu) prints: "0.4", "1.0", "1e21"
+// f64 the way serde_json writes it (the ryu crate's `pretty` layout): the shortest digit string that
+// round-trips, then with kk = position of the decimal point relative to those digits
+//   digits then zeros then ".0" when the value is an integer below 1e16, "12.34", "0.001234" down to 1e-5,
+//   and d[.ddd]e[-]x otherwise.
 static void put_f64(std::string &o, double x) {
     if (!std::isfinite(x)) { o += "null"; return; }
-    char buf[40];
-    for (int prec = 1; prec <= 17; prec++) {
-        snprintf(buf, sizeof buf, "%.*g", prec, x);
+    if (x == 0) { o += std::signbit(x) ? "-0.0" : "0.0"; return; }
+    char buf[48];
+    for (int prec = 0; prec <= 16; prec++) {
+        snprintf(buf, sizeof buf, "%.*e", prec, x);
         if (strtod(buf, nullptr) == x) break;
     }
-    std::string s(buf);
-    const size_t e = s.find('e');
-    std::string mant = (e == std::string::npos) ? s : s.substr(0, e);
-    if (e == std::string::npos) {
-        if (mant.find('.') == std::string::npos) mant += ".0";
-        o += mant;
+    const char *p = buf;
+    if (*p == '-') { o.push_back('-'); p++; }
+    std::string digits;
+    for (; *p && *p != 'e'; p++)
+        if (*p != '.') digits.push_back(*p);
+    const int e10 = atoi(p + 1);                    // value = d.ddd x 10^e10
+    while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+    const int len = (int)digits.size();
+    const int k = e10 - (len - 1);                  // value = digits x 10^k
+    const int kk = len + k;
+    if (k >= 0 && kk <= 16) {
+        o += digits;
+        o.append((size_t)k, '0');
+        o += ".0";
+    } else if (kk > 0 && kk <= 16) {
+        o.append(digits, 0, (size_t)kk);
+        o.push_back('.');
+        o.append(digits, (size_t)kk, std::string::npos);
+    } else if (kk > -5 && kk <= 0) {
+        o += "0.";
+        o.append((size_t)(-kk), '0');
+        o += digits;
     } else {
-        int ex = atoi(s.c_str() + e + 1);
-        o += mant;
+        o.push_back(digits[0]);
+        if (len > 1) {
+            o.push_back('.');
+            o.append(digits, 1, std::string::npos);
+        }
         o.push_back('e');
-        o += std::to_string(ex);
+        o += std::to_string(kk - 1);
     }
 }
 static void put_minhash(std::string &o, KmerMinHash &mh) {  // lib.rs:62-102
@@ -77,8 +142,10 @@ static void put_minhash(std::string &o, KmerMinHash &mh) {  // lib.rs:62-102
     o += ",\"ksize\":"; put_u64(o, mh.ksize);
     o += ",\"seed\":"; put_u64(o, mh.seed);
     o += ",\"max_hash\":"; put_u64(o, mh.max_hash);
-    o += ",\"mins\":"; put_u64_array(o, mh.mins());
-    o += ",\"md5sum\":"; put_str(o, mh.md5sum());
+    Md5 md5;                                     // over ksize and every min in decimal, lib.rs:72-77
+    md5.update(std::to_string(mh.ksize));
+    o += ",\"mins\":"; put_u64_array(o, mh.mins(), &md5);
+    o += ",\"md5sum\":\""; o += md5.hex(); o.push_back('"');
     if (mh.track_abundance()) { o += ",\"abundances\":"; put_u64_array(o, mh.abunds()); }
     o += ",\"molecule\":"; o += mh.is_protein ? "\"protein\"" : "\"DNA\"";
     o.push_back('}');
@@ -130,35 +197,74 @@ bool Signature::equals(Signature &o) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// reader: a small recursive-descent JSON parser producing a tree of values
+// reader: a typed, single-pass JSON reader with the acceptance rules of serde_json + the serde derive
+// of the two structs (lib.rs:104-139 TempSig, lib.rs:546-565 Signature): strict RFC 8259 grammar,
+// unknown fields skipped, duplicate known fields rejected, integers must fit the field's type, both
+// the map and the sequence form of a struct are read.  `mins` / `abundances` go straight into u64
+// vectors -- no value tree is built.
 // ---------------------------------------------------------------------------------------------
 namespace {
-struct JVal {
-    enum T { NUL, BOOL, NUM, STR, ARR, OBJ } t = NUL;
-    bool b = false;
-    bool is_u64 = false;
-    uint64_t u = 0;
-    double d = 0;
-    std::string s;
-    std::vector<JVal> a;
-    std::vector<std::pair<std::string, JVal>> o;
-    const JVal *get(const char *k) const {
-        for (auto &kv : o) if (kv.first == k) return &kv.second;
-        return nullptr;
-    }
-};
 [[noreturn]] void jfail(const std::string &m) { throw SourmashError(ERR_UNKNOWN, "JSON error: " + m); }
-struct JParser {
+
+// strict UTF-8 (what Rust's str::from_utf8 accepts): no overlong forms, no surrogates, nothing above U+10FFFF
+bool utf8_ok(const std::string &s) {
+    const unsigned char *p = reinterpret_cast<const unsigned char *>(s.data()), *e = p + s.size();
+    while (p < e) {
+        const unsigned c = *p;
+        if (c < 0x80) { p++; continue; }
+        int n;
+        unsigned lo = 0x80, hi = 0xBF;
+        if (c >= 0xC2 && c <= 0xDF) n = 1;
+        else if (c == 0xE0) { n = 2; lo = 0xA0; }
+        else if (c == 0xED) { n = 2; hi = 0x9F; }
+        else if (c >= 0xE1 && c <= 0xEF) n = 2;
+        else if (c == 0xF0) { n = 3; lo = 0x90; }
+        else if (c >= 0xF1 && c <= 0xF3) n = 3;
+        else if (c == 0xF4) { n = 3; hi = 0x8F; }
+        else return false;
+        if (e - p <= n) return false;
+        if (p[1] < lo || p[1] > hi) return false;
+        for (int i = 2; i <= n; i++)
+            if (p[i] < 0x80 || p[i] > 0xBF) return false;
+        p += n + 1;
+    }
+    return true;
+}
+
+struct JReader {
     const char *p, *e;
+    JReader(const char *d, size_t n) : p(d), e(d + n) {}
+
     void ws() { while (p < e && (*p == ' ' || *p == '\n' || *p == '\r' || *p == '\t')) p++; }
-    static void utf8(std::string &s, uint32_t cp) {
+    char peek() {
+        ws();
+        if (p >= e) jfail("EOF while parsing a value");
+        return *p;
+    }
+    bool eat(char c) {
+        ws();
+        if (p < e && *p == c) { p++; return true; }
+        return false;
+    }
+    void literal(const char *word) {
+        const size_t n = strlen(word);
+        if ((size_t)(e - p) < n || strncmp(p, word, n) != 0) jfail("expected ident");
+        p += n;
+    }
+    bool null() {  // consumes `null` if that is the next value
+        if (peek() != 'n') return false;
+        literal("null");
+        return true;
+    }
+
+    static void put_utf8(std::string &s, uint32_t cp) {
         if (cp < 0x80) s.push_back((char)cp);
         else if (cp < 0x800) { s.push_back((char)(0xC0 | (cp >> 6))); s.push_back((char)(0x80 | (cp & 63))); }
         else if (cp < 0x10000) { s.push_back((char)(0xE0 | (cp >> 12))); s.push_back((char)(0x80 | ((cp >> 6) & 63))); s.push_back((char)(0x80 | (cp & 63))); }
         else { s.push_back((char)(0xF0 | (cp >> 18))); s.push_back((char)(0x80 | ((cp >> 12) & 63))); s.push_back((char)(0x80 | ((cp >> 6) & 63))); s.push_back((char)(0x80 | (cp & 63))); }
     }
     uint32_t hex4() {
-        if (e - p < 4) jfail("truncated \\u escape");
+        if (e - p < 4) jfail("EOF while parsing a string");
         uint32_t v = 0;
         for (int i = 0; i < 4; i++) {
             const char c = *p++;
@@ -166,152 +272,273 @@ struct JParser {
             if (c >= '0' && c <= '9') v |= (uint32_t)(c - '0');
             else if (c >= 'a' && c <= 'f') v |= (uint32_t)(c - 'a' + 10);
             else if (c >= 'A' && c <= 'F') v |= (uint32_t)(c - 'A' + 10);
-            else jfail("bad \\u escape");
+            else jfail("invalid escape");
         }
         return v;
     }
-    std::string str() {
-        std::string s;
-        p++;  // opening quote
+    // A string whose opening quote is at *p.  out == nullptr: the value is being skipped (same grammar checks,
+    // nothing kept).  Kept strings must be valid UTF-8.
+    void string(std::string *out) {
+        if (peek() != '"') jfail("invalid type: expected a string");
+        p++;
+        if (out) out->clear();
         while (true) {
-            if (p >= e) jfail("unterminated string");
+            const char *run = p;
+            while (p < e && *p != '"' && *p != '\\' && (unsigned char)*p >= 0x20) p++;
+            if (out) out->append(run, p);
+            if (p >= e) jfail("EOF while parsing a string");
             const char c = *p++;
             if (c == '"') break;
-            if (c != '\\') { s.push_back(c); continue; }
-            if (p >= e) jfail("unterminated escape");
+            if (c != '\\') jfail("control character (\\u0000-\\u001F) found while parsing a string");
+            if (p >= e) jfail("EOF while parsing a string");
             const char x = *p++;
+            uint32_t cp;
             switch (x) {
-            case '"': s.push_back('"'); break;
-            case '\\': s.push_back('\\'); break;
-            case '/': s.push_back('/'); break;
-            case 'b': s.push_back('\b'); break;
-            case 'f': s.push_back('\f'); break;
-            case 'n': s.push_back('\n'); break;
-            case 'r': s.push_back('\r'); break;
-            case 't': s.push_back('\t'); break;
-            case 'u': {
-                uint32_t cp = hex4();
-                if (cp >= 0xD800 && cp < 0xDC00 && e - p >= 6 && p[0] == '\\' && p[1] == 'u') {
+            case '"': cp = '"'; break;
+            case '\\': cp = '\\'; break;
+            case '/': cp = '/'; break;
+            case 'b': cp = '\b'; break;
+            case 'f': cp = '\f'; break;
+            case 'n': cp = '\n'; break;
+            case 'r': cp = '\r'; break;
+            case 't': cp = '\t'; break;
+            case 'u':
+                cp = hex4();
+                if (cp >= 0xDC00 && cp <= 0xDFFF) jfail("lone leading surrogate in hex escape");
+                if (cp >= 0xD800 && cp <= 0xDBFF) {
+                    if (e - p < 2 || p[0] != '\\' || p[1] != 'u') jfail("unexpected end of hex escape");
                     p += 2;
                     const uint32_t lo = hex4();
+                    if (lo < 0xDC00 || lo > 0xDFFF) jfail("lone leading surrogate in hex escape");
                     cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
                 }
-                utf8(s, cp);
                 break;
+            default: jfail("invalid escape");
             }
-            default: jfail("bad escape");
+            if (out) put_utf8(*out, cp);
+        }
+        if (out && !utf8_ok(*out)) jfail("invalid unicode code point");
+    }
+
+    // Number token at *p, checked against -?(0|[1-9][0-9]*)(\.[0-9]+)?([eE][+-]?[0-9]+)?.  Returns its extent;
+    // *plain_uint says it was digits only (no sign, fraction or exponent).
+    const char *number(bool *plain_uint) {
+        const char *s0 = p;
+        bool plain = true;
+        if (p < e && *p == '-') { plain = false; p++; }
+        if (p >= e || *p < '0' || *p > '9') jfail("invalid number");
+        if (*p == '0') {
+            p++;
+            if (p < e && *p >= '0' && *p <= '9') jfail("invalid number");
+        } else {
+            while (p < e && *p >= '0' && *p <= '9') p++;
+        }
+        if (p < e && *p == '.') {
+            plain = false;
+            p++;
+            if (p >= e || *p < '0' || *p > '9') jfail("invalid number");
+            while (p < e && *p >= '0' && *p <= '9') p++;
+        }
+        if (p < e && (*p == 'e' || *p == 'E')) {
+            plain = false;
+            p++;
+            if (p < e && (*p == '+' || *p == '-')) p++;
+            if (p >= e || *p < '0' || *p > '9') jfail("invalid number");
+            while (p < e && *p >= '0' && *p <= '9') p++;
+        }
+        *plain_uint = plain;
+        return s0;
+    }
+    // an unsigned integer field of at most `maxv` (u32 / u64 visitors: anything negative, fractional, with an
+    // exponent, or out of range is an error)
+    uint64_t uint_field(uint64_t maxv, const char *what) {
+        const char c = peek();
+        if (c != '-' && (c < '0' || c > '9')) jfail(std::string("invalid type for ") + what + ": expected an unsigned integer");
+        bool plain;
+        const char *s0 = number(&plain);
+        if (!plain) jfail(std::string("invalid type or value for ") + what + ": expected an unsigned integer");
+        uint64_t u = 0;
+        for (const char *q = s0; q < p; q++) {
+            const uint64_t d = (uint64_t)(*q - '0');
+            if (u > (~0ull - d) / 10) jfail(std::string("invalid value for ") + what + ": integer out of range");
+            u = u * 10 + d;
+        }
+        if (u > maxv) jfail(std::string("invalid value for ") + what + ": integer out of range");
+        return u;
+    }
+    double f64_field(const char *what) {
+        const char c = peek();
+        if (c != '-' && (c < '0' || c > '9')) jfail(std::string("invalid type for ") + what + ": expected a number");
+        bool plain;
+        const char *s0 = number(&plain);
+        const std::string tok(s0, p);
+        const double d = strtod(tok.c_str(), nullptr);
+        if (!std::isfinite(d)) jfail("number out of range");
+        return d;
+    }
+    // Vec<u64>
+    void u64_array(std::vector<uint64_t> &out, const char *what) {
+        if (peek() != '[') jfail(std::string("invalid type for ") + what + ": expected a sequence");
+        p++;
+        out.clear();
+        if (eat(']')) return;
+        while (true) {
+            ws();
+            // fast path: a run of digits not starting with 0
+            if (p < e && *p >= '1' && *p <= '9') {
+                const char *s0 = p;
+                uint64_t u = 0;
+                while (p < e && *p >= '0' && *p <= '9') { u = u * 10 + (uint64_t)(*p - '0'); p++; }
+                const char nx = p < e ? *p : '\0';
+                if (p - s0 <= 19 && nx != '.' && nx != 'e' && nx != 'E') {
+                    out.push_back(u);
+                } else {
+                    p = s0;
+                    out.push_back(uint_field(~0ull, what));
+                }
+            } else {
+                out.push_back(uint_field(~0ull, what));
+            }
+            if (eat(',')) continue;
+            if (eat(']')) break;
+            if (p >= e) jfail("EOF while parsing a list");
+            jfail("expected `,` or `]`");
+        }
+    }
+
+    // any value, discarded (unknown fields).  Iterative: nesting depth costs heap, not stack.
+    void skip_value() {
+        std::vector<char> open;  // '[' or '{' per enclosing container
+        while (true) {
+            const char c = peek();
+            bool container = false;
+            if (c == '"') string(nullptr);
+            else if (c == 't') literal("true");
+            else if (c == 'f') literal("false");
+            else if (c == 'n') literal("null");
+            else if (c == '-' || (c >= '0' && c <= '9')) { bool plain; number(&plain); }
+            else if (c == '[') {
+                p++;
+                if (!eat(']')) { open.push_back('['); container = true; }
+            } else if (c == '{') {
+                p++;
+                if (!eat('}')) { open.push_back('{'); container = true; }
+            } else jfail("expected value");
+            if (container) {
+                if (open.back() == '{') skip_key();
+                continue;
+            }
+            // a value just ended: close / continue the enclosing containers
+            while (true) {
+                if (open.empty()) return;
+                if (eat(',')) {
+                    if (open.back() == '{') skip_key();
+                    break;
+                }
+                if (eat(open.back() == '[' ? ']' : '}')) { open.pop_back(); continue; }
+                if (p >= e) jfail(open.back() == '[' ? "EOF while parsing a list" : "EOF while parsing an object");
+                jfail(open.back() == '[' ? "expected `,` or `]`" : "expected `,` or `}`");
             }
         }
-        return s;
     }
-    JVal val() {
-        ws();
-        if (p >= e) jfail("unexpected end of input");
-        JVal v;
-        const char c = *p;
+    void skip_key() {
+        if (peek() != '"') jfail("key must be a string");
+        std::string k;
+        string(&k);
+        if (!eat(':')) jfail("expected `:`");
+    }
+
+    // Drive a struct visitor over the map form {"name": value, ...} or the sequence form [value, ...].
+    // names[0..n): the struct's fields in declaration order; field(i) must consume field i's value.
+    template <typename F>
+    void read_struct(const char *const *names, int n, uint32_t *seen, const char *what, F field) {
+        *seen = 0;
+        const char c = peek();
         if (c == '{') {
-            v.t = JVal::OBJ; p++; ws();
-            if (p < e && *p == '}') { p++; return v; }
+            p++;
+            if (eat('}')) return;
+            std::string key;
             while (true) {
-                ws();
-                if (p >= e || *p != '"') jfail("expected object key");
-                std::string k = str();
-                ws();
-                if (p >= e || *p != ':') jfail("expected ':'");
-                p++;
-                v.o.emplace_back(std::move(k), val());
-                ws();
-                if (p < e && *p == ',') { p++; continue; }
-                if (p < e && *p == '}') { p++; break; }
-                jfail("expected ',' or '}'");
+                if (peek() != '"') jfail("key must be a string");
+                string(&key);
+                if (!eat(':')) jfail("expected `:`");
+                int idx = -1;
+                for (int i = 0; i < n; i++)
+                    if (key == names[i]) { idx = i; break; }
+                if (idx < 0) {
+                    skip_value();
+                } else {
+                    if (*seen & (1u << idx)) jfail(std::string("duplicate field `") + names[idx] + "`");
+                    *seen |= 1u << idx;
+                    field(idx);
+                }
+                if (eat(',')) continue;
+                if (eat('}')) break;
+                if (p >= e) jfail("EOF while parsing an object");
+                jfail("expected `,` or `}`");
             }
         } else if (c == '[') {
-            v.t = JVal::ARR; p++; ws();
-            if (p < e && *p == ']') { p++; return v; }
-            while (true) {
-                v.a.push_back(val());
-                ws();
-                if (p < e && *p == ',') { p++; continue; }
-                if (p < e && *p == ']') { p++; break; }
-                jfail("expected ',' or ']'");
-            }
-        } else if (c == '"') {
-            v.t = JVal::STR; v.s = str();
-        } else if (c == 't' && e - p >= 4 && !strncmp(p, "true", 4)) { v.t = JVal::BOOL; v.b = true; p += 4; }
-        else if (c == 'f' && e - p >= 5 && !strncmp(p, "false", 5)) { v.t = JVal::BOOL; v.b = false; p += 5; }
-        else if (c == 'n' && e - p >= 4 && !strncmp(p, "null", 4)) { v.t = JVal::NUL; p += 4; }
-        else if (c == '-' || (c >= '0' && c <= '9')) {
-            const char *s0 = p;
-            if (*p == '-') p++;
-            bool integral = true;
-            while (p < e && ((*p >= '0' && *p <= '9') || *p == '.' || *p == 'e' || *p == 'E' || *p == '+' || *p == '-')) {
-                if (*p == '.' || *p == 'e' || *p == 'E') integral = false;
-                p++;
-            }
-            const std::string tok(s0, p);
-            v.t = JVal::NUM;
-            v.d = strtod(tok.c_str(), nullptr);
-            if (integral && tok[0] != '-' && tok.size() <= 20) {
-                uint64_t u = 0;
-                bool ok = true;
-                for (char ch : tok) {
-                    const uint64_t nu = u * 10 + (uint64_t)(ch - '0');
-                    if (u > (~0ull) / 10 || nu < u * 10) { ok = false; break; }
-                    u = nu;
+            p++;
+            int idx = 0;
+            if (!eat(']')) {
+                while (true) {
+                    if (idx >= n) jfail("trailing characters");  // more elements than fields
+                    *seen |= 1u << idx;
+                    field(idx++);
+                    if (eat(',')) continue;
+                    if (eat(']')) break;
+                    if (p >= e) jfail("EOF while parsing a list");
+                    jfail("expected `,` or `]`");
                 }
-                v.is_u64 = ok;
-                v.u = u;
             }
-        } else jfail(std::string("unexpected character '") + c + "'");
-        return v;
+            // a sequence is positional: what it does not reach is filled from #[serde(default)] or fails, in order
+            *seen |= 0x80000000u;
+        } else {
+            jfail(std::string("invalid type: expected struct ") + what);
+        }
     }
 };
 
-uint64_t need_u64(const JVal &o, const char *k, uint64_t maxv) {
-    const JVal *v = o.get(k);
-    if (!v) jfail(std::string("missing field `") + k + "`");
-    if (v->t != JVal::NUM || !v->is_u64 || v->u > maxv) jfail(std::string("invalid value for `") + k + "`");
-    return v->u;
-}
-std::vector<uint64_t> u64_array(const JVal &v, const char *k) {
-    if (v.t != JVal::ARR) jfail(std::string("`") + k + "` is not an array");
-    std::vector<uint64_t> out;
-    out.reserve(v.a.size());
-    for (auto &x : v.a) {
-        if (x.t != JVal::NUM || !x.is_u64) jfail(std::string("non-u64 entry in `") + k + "`");
-        out.push_back(x.u);
-    }
-    return out;
-}
-std::string opt_str(const JVal &o, const char *k, const std::string &dflt, bool *present = nullptr) {
-    const JVal *v = o.get(k);
-    if (present) *present = false;
-    if (!v || v->t == JVal::NUL) return dflt;
-    if (v->t != JVal::STR) jfail(std::string("`") + k + "` is not a string");
-    if (present) *present = true;
-    return v->s;
-}
+struct SketchFields {  // TempSig, lib.rs:109-119
+    uint32_t num = 0, ksize = 0;
+    uint64_t seed = 0, max_hash = 0;
+    std::string md5sum, molecule;
+    std::vector<uint64_t> mins, abunds;
+    bool has_abunds = false;
+};
 }  // namespace
 
 // KmerMinHash Deserialize, lib.rs:104-139
-static std::unique_ptr<KmerMinHash> minhash_from_json(const JVal &o) {
-    if (o.t != JVal::OBJ) jfail("sketch is not an object");
-    const uint32_t num_in = (uint32_t)need_u64(o, "num", 0xFFFFFFFFull);
-    const uint32_t ksize = (uint32_t)need_u64(o, "ksize", 0xFFFFFFFFull);
-    const uint64_t seed = need_u64(o, "seed", ~0ull);
-    const uint64_t max_hash = need_u64(o, "max_hash", ~0ull);
-    if (!o.get("md5sum") || o.get("md5sum")->t != JVal::STR) jfail("missing field `md5sum`");
-    if (!o.get("mins")) jfail("missing field `mins`");
-    if (!o.get("molecule") || o.get("molecule")->t != JVal::STR) jfail("missing field `molecule`");
-    const std::vector<uint64_t> mins = u64_array(*o.get("mins"), "mins");
-    const JVal *ab = o.get("abundances");
-    const bool has_ab = ab && ab->t != JVal::NUL;
-    std::vector<uint64_t> abunds;
-    if (has_ab) abunds = u64_array(*ab, "abundances");
-    const uint32_t num = max_hash != 0 ? 0 : num_in;            // lib.rs:124
-    const bool prot = o.get("molecule")->s == "protein";        // lib.rs:132-136 (anything else: DNA)
-    std::unique_ptr<KmerMinHash> mh(new KmerMinHash(num, ksize, prot, seed, max_hash, has_ab));
-    mh->set_from_host(mins.data(), mins.size(), has_ab ? abunds.data() : nullptr, abunds.size());
+static std::unique_ptr<KmerMinHash> read_minhash(JReader &r, SketchFields &f) {
+    static const char *const names[8] = {"num", "ksize", "seed", "max_hash", "md5sum", "mins", "abundances", "molecule"};
+    f.has_abunds = false;
+    uint32_t seen;
+    r.read_struct(names, 8, &seen, "TempSig", [&](int i) {
+        switch (i) {
+        case 0: f.num = (uint32_t)r.uint_field(0xFFFFFFFFull, "`num`"); break;
+        case 1: f.ksize = (uint32_t)r.uint_field(0xFFFFFFFFull, "`ksize`"); break;
+        case 2: f.seed = r.uint_field(~0ull, "`seed`"); break;
+        case 3: f.max_hash = r.uint_field(~0ull, "`max_hash`"); break;
+        case 4: r.string(&f.md5sum); break;
+        case 5: r.u64_array(f.mins, "`mins`"); break;
+        case 6:
+            f.has_abunds = !r.null();
+            if (f.has_abunds) r.u64_array(f.abunds, "`abundances`");
+            break;
+        default: r.string(&f.molecule); break;
+        }
+    });
+    const bool positional = (seen & 0x80000000u) != 0;
+    for (int i = 0; i < 8; i++) {
+        if (seen & (1u << i)) continue;
+        if (i == 6 && !positional) continue;  // Option<_>: absent from a map means None
+        if (positional) jfail("invalid length " + std::to_string(i) + ", expected struct TempSig with 8 elements");
+        jfail(std::string("missing field `") + names[i] + "`");
+    }
+    const uint32_t num = f.max_hash != 0 ? 0 : f.num;  // lib.rs:124
+    const bool prot = f.molecule == "protein";          // lib.rs:132-136 (anything else: DNA)
+    std::unique_ptr<KmerMinHash> mh(new KmerMinHash(num, f.ksize, prot, f.seed, f.max_hash, f.has_abunds));
+    mh->set_from_host(f.mins.data(), f.mins.size(), f.has_abunds ? f.abunds.data() : nullptr, f.abunds.size());
     return mh;
 }
 
@@ -326,30 +553,55 @@ static bool ieq(const char *a, const char *b) {
 }
 
 std::vector<std::unique_ptr<Signature>> load_signatures(const char *data, size_t len, size_t ksize, const char *moltype) {
-    JParser jp{data, data + len};
-    const JVal root = jp.val();
-    jp.ws();
-    if (jp.p != jp.e) jfail("trailing characters");
-    if (root.t != JVal::ARR) jfail("expected an array of signatures");
+    static const char *const names[8] = {"class", "email", "hash_function", "filename", "name", "license", "signatures", "version"};
+    JReader r(data, len);
     std::vector<std::unique_ptr<Signature>> out;
-    for (const JVal &js : root.a) {
-        if (js.t != JVal::OBJ) jfail("signature is not an object");
+    SketchFields scratch;
+    auto read_signature = [&]() {
         Signature meta;
-        meta.class_ = opt_str(js, "class", "sourmash_signature");
-        meta.email = opt_str(js, "email", "");
-        if (!js.get("hash_function") || js.get("hash_function")->t != JVal::STR) jfail("missing field `hash_function`");
-        meta.hash_function = js.get("hash_function")->s;
-        meta.filename = opt_str(js, "filename", "", &meta.has_filename);
-        meta.name = opt_str(js, "name", "", &meta.has_name);
-        meta.license = opt_str(js, "license", "CC0");
-        const JVal *ver = js.get("version");
-        if (ver && ver->t == JVal::NUM) meta.version = ver->d;
-        else if (ver && ver->t != JVal::NUL) jfail("`version` is not a number");
-        const JVal *sk = js.get("signatures");
-        if (!sk || sk->t != JVal::ARR) jfail("missing field `signatures`");
+        std::vector<std::unique_ptr<KmerMinHash>> sketches;
+        uint32_t seen;
+        r.read_struct(names, 8, &seen, "Signature", [&](int i) {
+            switch (i) {
+            case 0: r.string(&meta.class_); break;
+            case 1: r.string(&meta.email); break;
+            case 2: r.string(&meta.hash_function); break;
+            case 3:
+                meta.has_filename = !r.null();
+                if (meta.has_filename) r.string(&meta.filename);
+                break;
+            case 4:
+                meta.has_name = !r.null();
+                if (meta.has_name) r.string(&meta.name);
+                break;
+            case 5: r.string(&meta.license); break;
+            case 6:
+                if (r.peek() != '[') jfail("invalid type for `signatures`: expected a sequence");
+                r.p++;
+                if (!r.eat(']')) {
+                    while (true) {
+                        sketches.push_back(read_minhash(r, scratch));
+                        if (r.eat(',')) continue;
+                        if (r.eat(']')) break;
+                        if (r.p >= r.e) jfail("EOF while parsing a list");
+                        jfail("expected `,` or `]`");
+                    }
+                }
+                break;
+            default: meta.version = r.f64_field("`version`"); break;
+            }
+        });
+        const bool positional = (seen & 0x80000000u) != 0;
+        for (int i = 0; i < 8; i++) {
+            if (seen & (1u << i)) continue;
+            const bool has_default = i == 0 || i == 1 || i == 5 || i == 7;       // #[serde(default ...)], lib.rs:548-564
+            if (has_default) continue;                                           // Signature() already holds them
+            if ((i == 3 || i == 4) && !positional) continue;                     // Option<_>: absent from a map means None
+            if (positional) jfail("invalid length " + std::to_string(i) + ", expected struct Signature with 8 elements");
+            jfail(std::string("missing field `") + names[i] + "`");
+        }
         // flatten: one Signature per sketch, then filter (lib.rs:603-644)
-        for (const JVal &jm : sk->a) {
-            std::unique_ptr<KmerMinHash> mh = minhash_from_json(jm);
+        for (auto &mh : sketches) {
             bool keep = false;
             if (ksize == 0 || ksize == (size_t)mh->ksize) {
                 if (!moltype) keep = true;
@@ -361,7 +613,20 @@ std::vector<std::unique_ptr<Signature>> load_signatures(const char *data, size_t
             s->signatures.push_back(std::move(mh));
             out.push_back(std::move(s));
         }
+    };
+    if (r.peek() != '[') jfail("invalid type: expected a sequence of signatures");
+    r.p++;
+    if (!r.eat(']')) {
+        while (true) {
+            read_signature();
+            if (r.eat(',')) continue;
+            if (r.eat(']')) break;
+            if (r.p >= r.e) jfail("EOF while parsing a list");
+            jfail("expected `,` or `]`");
+        }
     }
+    r.ws();
+    if (r.p != r.e) jfail("trailing characters");
     return out;
 }
 
@@ -388,13 +653,13 @@ static std::string gunzip_first_member(const std::string &data) {
         rc = inflate(&zs, Z_NO_FLUSH);
         if (rc != Z_OK && rc != Z_STREAM_END && rc != Z_BUF_ERROR) {
             inflateEnd(&zs);
-            throw SourmashError(ERR_SERDE, "corrupt gzip stream");
+            throw SourmashError(ERR_UNKNOWN, "corrupt gzip stream");
         }
         out.append((const char *)chunk.data(), chunk.size() - zs.avail_out);
         if (rc == Z_BUF_ERROR && zs.avail_in == 0 && consumed == data.size()) break;
     }
     inflateEnd(&zs);
-    if (rc != Z_STREAM_END) throw SourmashError(ERR_SERDE, "unexpected end of gzip stream");
+    if (rc != Z_STREAM_END) throw SourmashError(ERR_UNKNOWN, "unexpected end of gzip stream");
     return out;
 }
 

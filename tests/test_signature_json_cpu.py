@@ -1,0 +1,270 @@
+"""Signature JSON on the host (no GPU needed): the reader accepts and rejects what serde_json plus the serde derive of
+the reference's two structs do (src/lib.rs:104-139 TempSig, src/lib.rs:546-577 Signature), and the writer reproduces
+serde_json's compact output byte for byte (field order lib.rs:79-100, md5sum rule lib.rs:72-77, f64 in ryu's layout).
+The expected strings are built by an independent writer in this file, not by the oracle."""
+import hashlib
+import json
+import os
+import random
+import sys
+from decimal import Decimal
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def smb():
+    from sourmash_rust_b200 import build
+    build.build_library()
+    import sourmash_rust_b200 as s
+    s.lib()
+    return s
+
+
+# ---- an independent statement of the expected output -----------------------------------------------------------------
+def ryu_layout(x: float) -> str:
+    """The `pretty` layout of the ryu crate (what serde_json prints for an f64) over Python's shortest repr digits."""
+    x = float(x)
+    if x == 0:
+        return "-0.0" if str(x).startswith("-") else "0.0"
+    sign, digits, exp = Decimal(repr(x)).as_tuple()
+    digits = list(digits)
+    while len(digits) > 1 and digits[-1] == 0:
+        digits.pop()
+        exp += 1
+    ds = "".join(map(str, digits))
+    k, kk = exp, len(ds) + exp
+    neg = "-" if sign else ""
+    if 0 <= k and kk <= 16:
+        return neg + ds + "0" * k + ".0"
+    if 0 < kk <= 16:
+        return neg + ds[:kk] + "." + ds[kk:]
+    if -5 < kk <= 0:
+        return neg + "0." + "0" * (-kk) + ds
+    if len(ds) == 1:
+        return neg + ds + "e" + str(kk - 1)
+    return neg + ds[0] + "." + ds[1:] + "e" + str(kk - 1)
+
+
+def canon_sketch(m):
+    num = 0 if m["max_hash"] != 0 else m["num"]                                     # lib.rs:124
+    md5 = hashlib.md5((str(m["ksize"]) + "".join(str(x) for x in m["mins"])).encode()).hexdigest()
+    parts = ['"num":%d' % num, '"ksize":%d' % m["ksize"], '"seed":%d' % m["seed"], '"max_hash":%d' % m["max_hash"],
+             '"mins":[%s]' % ",".join(map(str, m["mins"])), '"md5sum":"%s"' % md5]
+    if m.get("abundances") is not None:
+        parts.append('"abundances":[%s]' % ",".join(map(str, m["abundances"])))
+    parts.append('"molecule":"%s"' % ("protein" if m["molecule"] == "protein" else "DNA"))  # lib.rs:132-136
+    return "{" + ",".join(parts) + "}"
+
+
+def jstr(s):
+    return "null" if s is None else json.dumps(s, ensure_ascii=False)
+
+
+def canon_signature(d, m):
+    return ('{"class":%s,"email":%s,"hash_function":%s,"filename":%s,"name":%s,"license":%s,"signatures":[%s],"version":%s}'
+            % (jstr(d.get("class", "sourmash_signature")), jstr(d.get("email", "")), jstr(d["hash_function"]),
+               jstr(d.get("filename")), jstr(d.get("name")), jstr(d.get("license", "CC0")), canon_sketch(m),
+               ryu_layout(float(d.get("version", 0.4)))))
+
+
+# ---- tests -----------------------------------------------------------------------------------------------------------
+def test_roundtrip_fuzz(smb):
+    rng = random.Random(20240611)
+    alphabet = ['a', 'Z', '0', ' ', '"', '\\', '/', '\n', '\t', '\r', '\b', '\f', '\x01', '\x1f', '\x7f', 'é', '日', '😀',
+                ' ', '{', '}', '[', ']', ',', ':']
+    versions = [0.4, 1, 2.5, 0.30000000000000004, 1e21, 1e-7, 1e-5, 123456789.125, 5e-324, 1.7976931348623157e308, 100.0,
+                1e15, 1e16, 123456789012345680.0, -3, -0.001, 0.1 + 0.7, 2 ** 53, 1 / 3]
+
+    def rstr():
+        return "".join(rng.choice(alphabet) for _ in range(rng.randrange(0, 12)))
+
+    for it in range(200):
+        docs, want = [], []
+        for _ in range(rng.randrange(0, 4)):
+            d = {"hash_function": rstr()}
+            for key in ("class", "email", "filename", "name", "license"):
+                r = rng.random()
+                if r < 0.5:
+                    d[key] = rstr()
+                elif r < 0.7 and key in ("filename", "name"):
+                    d[key] = None
+            if rng.random() < 0.6:
+                d["version"] = rng.choice(versions) if rng.random() < 0.7 else rng.uniform(-1e3, 1e3) * 10 ** rng.randrange(-30, 30)
+            sketches = []
+            for _ in range(rng.randrange(0, 4)):
+                n = rng.randrange(0, 20)
+                mins = sorted({rng.getrandbits(rng.choice([5, 31, 64])) for _ in range(n)})
+                if rng.random() < 0.2 and mins:
+                    mins[-1] = 2 ** 64 - 1
+                m = {"num": rng.choice([0, 1, 500, 2 ** 32 - 1]), "ksize": rng.choice([1, 21, 31, 51, 2 ** 32 - 1]),
+                     "seed": rng.choice([42, 0, 2 ** 64 - 1]), "max_hash": rng.choice([0, 0, 2 ** 64 - 1, 18446744073709552]),
+                     "md5sum": rstr(), "mins": mins, "molecule": rng.choice(["DNA", "protein", "dna", "other", ""])}
+                r = rng.random()
+                if r < 0.4:
+                    m["abundances"] = [rng.getrandbits(rng.choice([3, 64])) for _ in mins]
+                elif r < 0.5:
+                    m["abundances"] = None
+                if rng.random() < 0.3:
+                    m["extra_field"] = {"nested": [1, -2.5e-3, "x\n", None, True, {"a": [], "b": {}}]}
+                items = list(m.items())
+                rng.shuffle(items)
+                sketches.append(dict(items))
+                want.append(canon_signature(d, m))
+            d["signatures"] = sketches
+            if rng.random() < 0.3:
+                d["unknown"] = [1, {"b": "c"}]
+            items = list(d.items())
+            rng.shuffle(items)
+            docs.append(dict(items))
+        txt = json.dumps(docs, ensure_ascii=rng.random() < 0.5, indent=rng.choice([None, None, 1, 4]),
+                         separators=rng.choice([None, (",", ":"), (" ,\t", " :\r\n")]))
+        sigs = smb.signatures_load_buffer(txt.encode())
+        got = [s.save_json().decode() for s in sigs]
+        assert got == want, "iteration %d" % it
+        assert smb.signatures_save_buffer(sigs).decode() == "[" + ",".join(want) + "]"
+        # what was written loads again to the same thing
+        assert [s.save_json().decode() for s in smb.signatures_load_buffer(("[" + ",".join(got) + "]").encode())] == want
+
+
+SKETCH = '{"num":1,"ksize":21,"seed":42,"max_hash":0,"mins":[1,2],"md5sum":"x","molecule":"DNA"}'
+
+
+def _doc(m=SKETCH, extra="", pre='"hash_function":"h",'):
+    return '[{%s"signatures":[%s]%s}]' % (pre, m, extra)
+
+
+ACCEPTANCE = {
+    # name: (text, number of signatures loaded, or None when serde_json reports an error)
+    "plain": (_doc(), 1),
+    "trailing whitespace": (_doc() + " \n\t\r", 1),
+    "trailing junk": (_doc() + "x", None),
+    "second value": (_doc() + "[]", None),
+    "top level object": ('{"a":1}', None),
+    "empty input": ("", None),
+    "empty array": ("[]", 0),
+    "no sketches": ('[{"hash_function":"h","signatures":[]}]', 0),
+    "missing hash_function": (_doc(pre=""), None),
+    "missing signatures": ('[{"hash_function":"h"}]', None),
+    "duplicate field in Signature": ('[{"hash_function":"h","hash_function":"h","signatures":[]}]', None),
+    "duplicate field in sketch": (_doc(SKETCH[:-1] + ',"num":2}'), None),
+    "duplicate unknown field": (_doc(SKETCH[:-1] + ',"zz":2,"zz":3}'), 1),
+    "num as float": (_doc(SKETCH.replace('"num":1', '"num":1.0')), None),
+    "num negative": (_doc(SKETCH.replace('"num":1', '"num":-1')), None),
+    "num with exponent": (_doc(SKETCH.replace('"num":1', '"num":1e0')), None),
+    "num above u32": (_doc(SKETCH.replace('"num":1', '"num":4294967296')), None),
+    "num at u32 max": (_doc(SKETCH.replace('"num":1', '"num":4294967295')), 1),
+    "num as bool": (_doc(SKETCH.replace('"num":1', '"num":true')), None),
+    "ksize above u32": (_doc(SKETCH.replace('"ksize":21', '"ksize":99999999999')), None),
+    "min above u64": (_doc(SKETCH.replace("[1,2]", "[1,18446744073709551616]")), None),
+    "min at u64 max": (_doc(SKETCH.replace("[1,2]", "[1,18446744073709551615]")), 1),
+    "min 25 digits": (_doc(SKETCH.replace("[1,2]", "[1000000000000000000000000]")), None),
+    "min -0": (_doc(SKETCH.replace("[1,2]", "[-0]")), None),
+    "min with exponent": (_doc(SKETCH.replace("[1,2]", "[1e3]")), None),
+    "min with fraction": (_doc(SKETCH.replace("[1,2]", "[12.0]")), None),
+    "min with leading zero": (_doc(SKETCH.replace("[1,2]", "[01]")), None),
+    "min zero": (_doc(SKETCH.replace("[1,2]", "[0 , 5 ]")), 1),
+    "mins trailing comma": (_doc(SKETCH.replace("[1,2]", "[1,2,]")), None),
+    "mins not a list": (_doc(SKETCH.replace("[1,2]", "7")), None),
+    "mins null": (_doc(SKETCH.replace("[1,2]", "null")), None),
+    "name as number": (_doc(extra=',"name":3'), None),
+    "name null": (_doc(extra=',"name":null'), 1),
+    "email null": (_doc(extra=',"email":null'), None),
+    "license null": (_doc(extra=',"license":null'), None),
+    "version integer": (_doc(extra=',"version":1'), 1),
+    "version negative integer": (_doc(extra=',"version":-3'), 1),
+    "version string": (_doc(extra=',"version":"1"'), None),
+    "version null": (_doc(extra=',"version":null'), None),
+    "version overflows f64": (_doc(extra=',"version":1e400'), None),
+    "version NaN": (_doc(extra=',"version":NaN'), None),
+    "number 1.": (_doc(extra=',"version":1.'), None),
+    "number .5": (_doc(extra=',"version":.5'), None),
+    "number +1": (_doc(extra=',"version":+1'), None),
+    "number 1e": (_doc(extra=',"version":1e'), None),
+    "bad number in unknown field": (_doc(extra=',"zz":1.'), None),
+    "molecule missing": (_doc(SKETCH.replace(',"molecule":"DNA"', "")), None),
+    "md5sum missing": (_doc(SKETCH.replace(',"md5sum":"x"', "")), None),
+    "abundances null": (_doc(SKETCH[:-1] + ',"abundances":null}'), 1),
+    "abundances string": (_doc(SKETCH[:-1] + ',"abundances":"x"}'), None),
+    "lone leading surrogate": (_doc(extra=',"name":"\\ud800"'), None),
+    "lone trailing surrogate": (_doc(extra=',"name":"\\udc00"'), None),
+    "leading surrogate + non-surrogate": (_doc(extra=',"name":"\\ud800\\u0041"'), None),
+    "surrogate pair": (_doc(extra=',"name":"\\ud83d\\ude00"'), 1),
+    "bad escape": (_doc(extra=',"name":"\\x"'), None),
+    "short \\u escape": (_doc(extra=',"name":"\\u12"'), None),
+    "raw control character": (_doc(extra=',"name":"a\nb"'), None),
+    "raw control character in unknown field": (_doc(extra=',"zz":"a\nb"'), None),
+    "object trailing comma": (_doc(SKETCH[:-1] + ",}"), None),
+    "key not a string": ("[{1:2}]", None),
+    "signature null": ("[null]", None),
+    "signature number": ("[1]", None),
+    "unterminated": (_doc()[:-3], None),
+    "byte order mark": ("﻿" + _doc(), None),
+    "unknown field nested 100000 deep": (_doc(extra=',"u":' + "[" * 100000 + "]" * 100000), 1),
+    "unknown field unbalanced": (_doc(extra=',"u":[{"a":[1,2}]'), None),
+    # serde's derive also reads a struct from a sequence, fields in declaration order
+    "sketch as sequence": (_doc('[1,21,42,0,"x",[1,2],null,"DNA"]'), 1),
+    "sketch as short sequence": (_doc('[1,21,42,0,"x",[1,2],null]'), None),
+    "sketch as long sequence": (_doc('[1,21,42,0,"x",[1,2],null,"DNA",1]'), None),
+    "signature as sequence": ('[["c","e","h",null,null,"CC0",[' + SKETCH + '],0.4]]', 1),
+    "signature as sequence, version defaulted": ('[["c","e","h",null,null,"CC0",[]]]', 0),
+    "signature as sequence, too short": ('[["c","e","h",null,null,"CC0"]]', None),
+}
+
+
+@pytest.mark.parametrize("name", sorted(ACCEPTANCE))
+def test_reader_acceptance(smb, name):
+    text, want = ACCEPTANCE[name]
+    if want is None:
+        with pytest.raises(smb.SourmashError) as e:
+            smb.signatures_load_buffer(text.encode())
+        assert e.value.code == 4, e.value.message   # errors.rs:54-77: a serde_json error maps to Unknown
+    else:
+        assert len(smb.signatures_load_buffer(text.encode())) == want
+
+
+def test_reader_rejects_invalid_utf8(smb):
+    for raw in (b"\xff", b"\xc0\x80", b"\xed\xa0\x80", b"\xf4\x90\x80\x80", b"\xe2\x82"):
+        with pytest.raises(smb.SourmashError):
+            smb.signatures_load_buffer(b'[{"hash_function":"' + raw + b'","signatures":[]}]')
+    ok = smb.signatures_load_buffer(b'[{"hash_function":"\xf0\x9f\x98\x80\xed\x9f\xbf","signatures":[' + SKETCH.encode() + b']}]')
+    assert len(ok) == 1
+
+
+def test_f64_layout(smb):
+    rng = random.Random(7)
+    values = [0.0, 0.4, 1.0, 10.0, 100.0, 1e15, 9999999999999998.0, 1e16, 1.5e16, 1e17, 1e-4, 1e-5, 1.5e-5, 1e-6, 123.456, 5e-324,
+              2.2250738585072014e-308, 1.7976931348623157e308, 0.1 + 0.2, 1 / 3, 2 ** 63, 2.0 ** -20, -7.25, 1234567.0, 12345678901234567.0]
+    values += [rng.uniform(-10, 10) * 10.0 ** rng.randrange(-320, 308) for _ in range(300)]
+    values += [float(rng.randrange(0, 10 ** rng.randrange(1, 20))) for _ in range(100)]
+    for v in values:
+        txt = _doc(extra=',"version":%r' % v)
+        s = smb.signatures_load_buffer(txt.encode())[0].save_json().decode()
+        assert s.endswith('"version":%s}' % ryu_layout(v)), (v, s[-40:])
+
+
+def test_large_file_throughput(smb):
+    """10^6 hashes in 2000 signatures: guards the single-pass reader / writer against a return of per-value allocation
+    (a value tree ran this at 50 MB/s; the bound here is far below what the current code does)."""
+    import time
+    rng = random.Random(3)
+    parts = []
+    for i in range(2000):
+        mins = sorted(rng.getrandbits(63) for _ in range(500))
+        parts.append('{"class":"sourmash_signature","email":"","hash_function":"0.murmur64","filename":"f%d","name":"n%d",'
+                     '"license":"CC0","signatures":[{"num":500,"ksize":31,"seed":42,"max_hash":0,"mins":[%s],"md5sum":"%s",'
+                     '"molecule":"DNA"}],"version":0.4}' % (i, i, ",".join(map(str, mins)),
+                                                           hashlib.md5(("31" + "".join(map(str, mins))).encode()).hexdigest()))
+    txt = ("[" + ",".join(parts) + "]").encode()
+    best_load = best_save = 1e9
+    for _ in range(3):
+        t = time.perf_counter()
+        sigs = smb.signatures_load_buffer(txt)
+        best_load = min(best_load, time.perf_counter() - t)
+        t = time.perf_counter()
+        out = smb.signatures_save_buffer(sigs)
+        best_save = min(best_save, time.perf_counter() - t)
+    assert out == txt                                    # byte-identical round trip, md5sum recomputed
+    assert len(txt) / best_load > 100e6 and len(txt) / best_save > 40e6, (len(txt) / best_load / 1e6, len(txt) / best_save / 1e6)
