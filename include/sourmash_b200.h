@@ -77,6 +77,10 @@ SketchCollection *smgpu_collection_new(void);
 void smgpu_collection_free(SketchCollection *c);
 /* append a copy of the sketch's mins as the next row (the sketch must hold sorted, distinct mins) */
 void smgpu_collection_push(SketchCollection *c, KmerMinHash *mh);
+/* the same for the first sketch of each of n loaded signatures, in one call: the rows a
+ * LinearIndex<Leaf<Signature>> holds after `insert` of each (src/index/linear.rs:33-36; a leaf compares through
+ * signatures[0], src/index.rs:131-160).  A signature without a sketch is an error, as the reference panics on it. */
+void smgpu_collection_push_signatures(SketchCollection *c, Signature *const *sigs, uintptr_t n);
 /* adopt a ready CSR: row i = hashes[offsets[i] .. offsets[i+1]); every row sorted ascending and
  * distinct (checked); all rows share (num, ksize, is_protein = false, seed, max_hash) */
 SketchCollection *smgpu_collection_from_csr(const uint64_t *hashes /*[host|device]*/,

@@ -95,6 +95,7 @@ EXTENSION_ABI = {
     "smgpu_collection_new": (vp, []),
     "smgpu_collection_free": (None, [vp]),
     "smgpu_collection_push": (None, [vp, vp]),
+    "smgpu_collection_push_signatures": (None, [vp, vp, usz]),
     "smgpu_collection_from_csr": (vp, [vp, vp, u64, u32, u32, u64, u64, cb]),
     "smgpu_sketch_collection": (vp, [vp, vp, u64, u32, u32, u64, u64, cb]),
     "smgpu_collection_len": (u64, [vp]),
@@ -498,6 +499,14 @@ class SketchCollection:
 
     def push(self, mh):
         _call("smgpu_collection_push", self._p, mh._p)
+
+    @classmethod
+    def from_signatures(cls, sigs):
+        """One row per loaded signature (its first sketch), pushed in one call."""
+        c = cls()
+        arr = (vp * max(1, len(sigs)))(*[s._p for s in sigs])
+        _call("smgpu_collection_push_signatures", c._p, arr, len(sigs))
+        return c
 
     def __len__(self):
         return _call("smgpu_collection_len", self._p)

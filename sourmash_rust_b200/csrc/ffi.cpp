@@ -495,6 +495,18 @@ void smgpu_collection_free(SketchCollection *c) {
 void smgpu_collection_push(SketchCollection *c, KmerMinHash *m) {
     landingpad_void([&]() { coll(c)->push(*mh(m)); });
 }
+void smgpu_collection_push_signatures(SketchCollection *c, Signature *const *sigs, uintptr_t n) {
+    landingpad_void([&]() {
+        COLL *cc = coll(c);
+        if (n) nonnull(sigs, "sigs");
+        for (uintptr_t i = 0; i < n; i++) {
+            SIG *s = sig(sigs[i]);
+            if (s->signatures.empty())
+                throw SourmashError(smb200::ERR_PANIC, "sourmash panicked: index out of bounds: the len is 0 but the index is 0");
+            cc->push(*s->signatures[0]);
+        }
+    });
+}
 SketchCollection *smgpu_collection_from_csr(const uint64_t *hashes, const uint64_t *offsets, uint64_t n_rows, uint32_t num,
                                             uint32_t ksize, uint64_t seed, uint64_t max_hash, bool on_device) {
     return landingpad<SketchCollection *>([&]() {

@@ -127,3 +127,26 @@ def test_load_path_reads_stdin(smb, tmp_path):
     r = subprocess.run([sys.executable, "-c", code], input=txt, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
     assert r.returncode == 0, r.stderr.decode()
     assert int(r.stdout.split()[-1]) == len(smb.signatures_load_buffer(txt, ksize=31))
+
+
+def test_collection_push_signatures_host_side(smb):
+    """Rows are staged on the host until first use, so the row count and the compatibility checks of
+    smgpu_collection_push_signatures need no GPU (check order of lib.rs:176-190; empty signature = the reference's panic)."""
+    import json
+    sk = {"num": 3, "ksize": 21, "seed": 42, "max_hash": 0, "mins": [1, 5, 9], "md5sum": "", "molecule": "DNA"}
+    def sigs(*sketch_lists):
+        return smb.signatures_load_buffer(json.dumps([{"hash_function": "h", "signatures": [dict(sk, **kw) for kw in sl]} for sl in sketch_lists]).encode())
+    ok = sigs([{}], [{"mins": [2, 3]}], [{"mins": []}])
+    assert len(smb.SketchCollection.from_signatures(ok)) == 3
+    assert len(smb.SketchCollection.from_signatures([])) == 0
+    for kw, code in (({"ksize": 31}, 101), ({"molecule": "protein"}, 102), ({"max_hash": 7, "num": 0}, 103), ({"seed": 1}, 104)):
+        with pytest.raises(smb.SourmashError) as e:
+            smb.SketchCollection.from_signatures(sigs([{}], [kw]))
+        assert e.value.code == code
+    with pytest.raises(smb.SourmashError) as e:      # unsorted mins cannot be a row
+        smb.SketchCollection.from_signatures(sigs([{"mins": [5, 1]}]))
+    assert e.value.code == 2
+    empty = smb.Signature()
+    with pytest.raises(smb.SourmashError) as e:
+        smb.SketchCollection.from_signatures([empty])
+    assert e.value.code == 1

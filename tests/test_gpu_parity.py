@@ -870,6 +870,21 @@ def test_signature_fixture_file():  # tests/signature.rs:10-32 through the golde
         assert json.loads(sg.save_json())["signatures"][0]["mins"] == sk["mins"]
 
 
+def test_collection_from_signatures():  # JSON -> CSR in one call == pushing each first sketch (linear.rs:33-36)
+    s = golden("sbt_v5_leaves.json")
+    doc = [{"hash_function": "0.murmur64", "name": lf["sig_name"], "filename": lf["filename"], "signatures": [lf["sketch"]]}
+           for _, lf in sorted(s["leaves"].items(), key=lambda kv: int(kv[0]))]
+    sigs = smb.signatures_load_buffer(json.dumps(doc).encode())
+    a = smb.SketchCollection.from_signatures(sigs)
+    b = smb.SketchCollection.from_sketches([sg.first_mh() for sg in sigs])
+    assert len(a) == len(b) == len(sigs)
+    for x, y in zip(a.rows_np(), b.rows_np()):
+        assert np.array_equal(x, y)
+    ca, sa, ra = smb.compare_matrix(a, a)
+    cb, sb_, rb = smb.compare_matrix(b, b)
+    assert np.array_equal(ca, cb) and np.array_equal(sa, sb_) and np.array_equal(ra, rb)
+
+
 # ------------------------------------------------------------------------------------------------
 # size-independent properties at BASELINE sizes (no oracle run needed)
 # ------------------------------------------------------------------------------------------------
