@@ -499,12 +499,17 @@ void smgpu_collection_push_signatures(SketchCollection *c, Signature *const *sig
     landingpad_void([&]() {
         COLL *cc = coll(c);
         if (n) nonnull(sigs, "sigs");
+        size_t extra = 0;
         for (uintptr_t i = 0; i < n; i++) {
             SIG *s = sig(sigs[i]);
             if (s->signatures.empty())
                 throw SourmashError(smb200::ERR_PANIC, "sourmash panicked: index out of bounds: the len is 0 but the index is 0");
-            cc->push(*s->signatures[0]);
+            extra += s->signatures[0]->mins().size();
         }
+        cc->h_hashes.reserve(cc->h_hashes.size() + extra);
+        cc->h_offsets.reserve(cc->h_offsets.size() + n);
+        cc->h_nums.reserve(cc->h_nums.size() + n);
+        for (uintptr_t i = 0; i < n; i++) cc->push(*sig(sigs[i])->signatures[0]);
     });
 }
 SketchCollection *smgpu_collection_from_csr(const uint64_t *hashes, const uint64_t *offsets, uint64_t n_rows, uint32_t num,
