@@ -128,7 +128,8 @@ uint64_t smgpu_scaffold_pairs(SketchCollection *c, uint64_t *pairs_first, uint64
  * only those are walked when the (pair, shared hash) incidences are few against the dense work;
  * 1 forces the dense tile kernel, 2 forces the inverted-index path, 3 = as 0 but with the
  * sorted-postings join instead of the hash-grouped one (the default; it builds a hash table over
- * the ROW block's hashes only, so a row shard of an all-vs-all matrix costs its share of the rows).
+ * the ROW block's hashes only, so a row shard of an all-vs-all matrix costs its share of the rows),
+ * 4 = as 2, and a block whose probe found many incidences is not handed to the dense kernels.
  * Results are identical. */
 void smgpu_compare_path(int32_t path);
 /* Batch sketching of several k-sizes over the same sequences (smgpu_add_* with more than one

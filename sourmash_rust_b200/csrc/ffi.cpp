@@ -305,7 +305,12 @@ SourmashStr signature_save_json(Signature *ptr) {
 SourmashStr signatures_save_buffer(Signature **ptr, uintptr_t size) {
     return landingpad<SourmashStr>([&]() {
         nonnull(ptr, "ptr");
-        return str_from(smb200::signatures_to_json(reinterpret_cast<SIG *const *>(ptr), size));
+        SourmashStr r;
+        size_t len = 0;
+        r.data = smb200::signatures_to_json(reinterpret_cast<SIG *const *>(ptr), size, &len);
+        r.len = len;
+        r.owned = true;
+        return r;
     });
 }
 static Signature **hand_over(std::vector<std::unique_ptr<SIG>> &sigs, uintptr_t *size) {

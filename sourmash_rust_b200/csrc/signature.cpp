@@ -5,13 +5,16 @@
 
 #include "md5.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <fstream>
 #include <iostream>
 #include <sstream>
+#include <thread>
 
 #include <zlib.h>
 
@@ -167,15 +170,68 @@ void Signature::to_json(std::string &o) {
     o.push_back('}');
 }
 
-std::string signatures_to_json(Signature *const *sigs, size_t n) {
-    std::string o = "[";
-    for (size_t i = 0; i < n; i++) {
-        if (i) o.push_back(',');
+// host threads for reading / writing large signature files (SMB200_JSON_THREADS; default min(8, cores))
+static unsigned json_threads() {
+    static const unsigned n = [] {
+        const char *e = getenv("SMB200_JSON_THREADS");
+        if (e && *e) return (unsigned)std::max(1, atoi(e));
+        return std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    }();
+    return n;
+}
+
+// Output goes to a malloc'd buffer the C ABI hands to the caller as is (SourmashStr, freed by sourmash_str_free).
+// Large outputs are written in contiguous runs of signatures on several host threads; each thread then copies
+// its run into place.  The host copies of the sketches are fetched first, on the calling thread (a device
+// read-back is not thread-safe).
+char *signatures_to_json(Signature *const *sigs, size_t n, size_t *len) {
+    for (size_t i = 0; i < n; i++)
         if (!sigs[i]) throw SourmashError(ERR_PANIC, "sourmash panicked: null signature pointer");
-        sigs[i]->to_json(o);
+    size_t hashes = 0;
+    for (size_t i = 0; i < n; i++)
+        for (auto &mh : sigs[i]->signatures) hashes += mh->mins().size();
+    const unsigned T = std::max(1u, (unsigned)std::min<size_t>({(size_t)json_threads(), n, hashes / 50000}));
+    std::vector<std::string> parts(T);
+    std::vector<std::exception_ptr> errs(T);
+    auto write_run = [&](unsigned t) {
+        try {
+            const size_t lo = n * t / T, hi = n * (t + 1) / T;
+            for (size_t i = lo; i < hi; i++) {
+                if (i > lo) parts[t].push_back(',');
+                sigs[i]->to_json(parts[t]);
+            }
+        } catch (...) {
+            errs[t] = std::current_exception();
+        }
+    };
+    auto on_threads = [&](auto fn) {
+        std::vector<std::thread> workers;
+        for (unsigned t = 1; t < T; t++) workers.emplace_back(fn, t);
+        fn(0);
+        for (auto &w : workers) w.join();
+    };
+    on_threads(write_run);
+    for (auto &e : errs)
+        if (e) std::rethrow_exception(e);
+    std::vector<size_t> at(T);
+    size_t total = 1;  // '['
+    for (unsigned t = 0; t < T; t++) {
+        if (t) total++;  // ',' between runs
+        at[t] = total;
+        total += parts[t].size();
     }
-    o.push_back(']');
-    return o;
+    total++;  // ']'
+    char *out = static_cast<char *>(malloc(total));
+    if (!out) throw std::bad_alloc();
+    out[0] = '[';
+    out[total - 1] = ']';
+    on_threads([&](unsigned t) {
+        if (t) out[at[t] - 1] = ',';
+        memcpy(out + at[t], parts[t].data(), parts[t].size());
+        std::string().swap(parts[t]);
+    });
+    *len = total;
+    return out;
 }
 
 Signature *Signature::clone_meta() const {
@@ -552,73 +608,82 @@ static bool ieq(const char *a, const char *b) {
     return *a == *b;
 }
 
-std::vector<std::unique_ptr<Signature>> load_signatures(const char *data, size_t len, size_t ksize, const char *moltype) {
+namespace {
+typedef std::vector<std::unique_ptr<Signature>> SigList;
+struct LoadFilter {
+    size_t ksize;         // 0: any
+    const char *moltype;  // nullptr: any
+};
+
+// One element of the top-level array: a Signature, flattened to one Signature per sketch and filtered
+// (lib.rs:603-644), appended to `out`.
+void read_signature(JReader &r, SketchFields &scratch, const LoadFilter &flt, SigList &out) {
     static const char *const names[8] = {"class", "email", "hash_function", "filename", "name", "license", "signatures", "version"};
-    JReader r(data, len);
-    std::vector<std::unique_ptr<Signature>> out;
-    SketchFields scratch;
-    auto read_signature = [&]() {
-        Signature meta;
-        std::vector<std::unique_ptr<KmerMinHash>> sketches;
-        uint32_t seen;
-        r.read_struct(names, 8, &seen, "Signature", [&](int i) {
-            switch (i) {
-            case 0: r.string(&meta.class_); break;
-            case 1: r.string(&meta.email); break;
-            case 2: r.string(&meta.hash_function); break;
-            case 3:
-                meta.has_filename = !r.null();
-                if (meta.has_filename) r.string(&meta.filename);
-                break;
-            case 4:
-                meta.has_name = !r.null();
-                if (meta.has_name) r.string(&meta.name);
-                break;
-            case 5: r.string(&meta.license); break;
-            case 6:
-                if (r.peek() != '[') jfail("invalid type for `signatures`: expected a sequence");
-                r.p++;
-                if (!r.eat(']')) {
-                    while (true) {
-                        sketches.push_back(read_minhash(r, scratch));
-                        if (r.eat(',')) continue;
-                        if (r.eat(']')) break;
-                        if (r.p >= r.e) jfail("EOF while parsing a list");
-                        jfail("expected `,` or `]`");
-                    }
+    Signature meta;
+    std::vector<std::unique_ptr<KmerMinHash>> sketches;
+    uint32_t seen;
+    r.read_struct(names, 8, &seen, "Signature", [&](int i) {
+        switch (i) {
+        case 0: r.string(&meta.class_); break;
+        case 1: r.string(&meta.email); break;
+        case 2: r.string(&meta.hash_function); break;
+        case 3:
+            meta.has_filename = !r.null();
+            if (meta.has_filename) r.string(&meta.filename);
+            break;
+        case 4:
+            meta.has_name = !r.null();
+            if (meta.has_name) r.string(&meta.name);
+            break;
+        case 5: r.string(&meta.license); break;
+        case 6:
+            if (r.peek() != '[') jfail("invalid type for `signatures`: expected a sequence");
+            r.p++;
+            if (!r.eat(']')) {
+                while (true) {
+                    sketches.push_back(read_minhash(r, scratch));
+                    if (r.eat(',')) continue;
+                    if (r.eat(']')) break;
+                    if (r.p >= r.e) jfail("EOF while parsing a list");
+                    jfail("expected `,` or `]`");
                 }
-                break;
-            default: meta.version = r.f64_field("`version`"); break;
             }
-        });
-        const bool positional = (seen & 0x80000000u) != 0;
-        for (int i = 0; i < 8; i++) {
-            if (seen & (1u << i)) continue;
-            const bool has_default = i == 0 || i == 1 || i == 5 || i == 7;       // #[serde(default ...)], lib.rs:548-564
-            if (has_default) continue;                                           // Signature() already holds them
-            if ((i == 3 || i == 4) && !positional) continue;                     // Option<_>: absent from a map means None
-            if (positional) jfail("invalid length " + std::to_string(i) + ", expected struct Signature with 8 elements");
-            jfail(std::string("missing field `") + names[i] + "`");
+            break;
+        default: meta.version = r.f64_field("`version`"); break;
         }
-        // flatten: one Signature per sketch, then filter (lib.rs:603-644)
-        for (auto &mh : sketches) {
-            bool keep = false;
-            if (ksize == 0 || ksize == (size_t)mh->ksize) {
-                if (!moltype) keep = true;
-                else if (ieq(moltype, "dna") && !mh->is_protein) keep = true;
-                else if (ieq(moltype, "protein") && mh->is_protein) keep = true;
-            }
-            if (!keep) continue;
-            std::unique_ptr<Signature> s(meta.clone_meta());
-            s->signatures.push_back(std::move(mh));
-            out.push_back(std::move(s));
+    });
+    const bool positional = (seen & 0x80000000u) != 0;
+    for (int i = 0; i < 8; i++) {
+        if (seen & (1u << i)) continue;
+        const bool has_default = i == 0 || i == 1 || i == 5 || i == 7;       // #[serde(default ...)], lib.rs:548-564
+        if (has_default) continue;                                           // Signature() already holds them
+        if ((i == 3 || i == 4) && !positional) continue;                     // Option<_>: absent from a map means None
+        if (positional) jfail("invalid length " + std::to_string(i) + ", expected struct Signature with 8 elements");
+        jfail(std::string("missing field `") + names[i] + "`");
+    }
+    for (auto &mh : sketches) {
+        bool keep = false;
+        if (flt.ksize == 0 || flt.ksize == (size_t)mh->ksize) {
+            if (!flt.moltype) keep = true;
+            else if (ieq(flt.moltype, "dna") && !mh->is_protein) keep = true;
+            else if (ieq(flt.moltype, "protein") && mh->is_protein) keep = true;
         }
-    };
+        if (!keep) continue;
+        std::unique_ptr<Signature> s(meta.clone_meta());
+        s->signatures.push_back(std::move(mh));
+        out.push_back(std::move(s));
+    }
+}
+
+SigList load_sequential(const char *data, size_t len, const LoadFilter &flt) {
+    JReader r(data, len);
+    SigList out;
+    SketchFields scratch;
     if (r.peek() != '[') jfail("invalid type: expected a sequence of signatures");
     r.p++;
     if (!r.eat(']')) {
         while (true) {
-            read_signature();
+            read_signature(r, scratch, flt, out);
             if (r.eat(',')) continue;
             if (r.eat(']')) break;
             if (r.p >= r.e) jfail("EOF while parsing a list");
@@ -628,6 +693,102 @@ std::vector<std::unique_ptr<Signature>> load_signatures(const char *data, size_t
     r.ws();
     if (r.p != r.e) jfail("trailing characters");
     return out;
+}
+
+// Large files: the top-level array is cut into pieces that are parsed on several host threads.  The cuts are
+// guesses -- a `{` that follows `} ,` and is followed by the key "class" (first in the output of both the Rust
+// and the Python writer) -- and every guess is verified: piece t counts only if piece t-1, which by induction
+// started on a true element boundary, ends exactly on piece t's first byte.  Any failed guess, and any error
+// inside any piece, discards the attempt; the caller then parses sequentially, so the result and the error
+// reported are always those of the single-pass reader.
+bool is_ws(char c) { return c == ' ' || c == '\n' || c == '\r' || c == '\t'; }
+const char *guess_element_start(const char *data, const char *from, const char *to) {
+    static const char key[] = "\"class\"";
+    for (const char *p = from; p < to; p++) {
+        if (*p != '{') continue;
+        const char *b = p - 1;
+        while (b > data && is_ws(*b)) b--;
+        if (b <= data || *b != ',') continue;
+        b--;
+        while (b > data && is_ws(*b)) b--;
+        if (*b != '}') continue;
+        const char *f = p + 1;
+        while (f < to && is_ws(*f)) f++;
+        if ((size_t)(to - f) >= sizeof(key) - 1 && memcmp(f, key, sizeof(key) - 1) == 0) return p;
+    }
+    return nullptr;
+}
+
+bool load_parallel(const char *data, size_t len, const LoadFilter &flt, SigList &out) {
+    const size_t piece_min = size_t(1) << 20;
+    unsigned T = (unsigned)std::min<size_t>(json_threads(), len / piece_min);
+    if (T < 2) return false;
+    const char *end = data + len;
+    JReader head(data, len);
+    head.ws();
+    if (head.p >= end || *head.p != '[') return false;
+    head.p++;
+    head.ws();
+    if (head.p >= end || *head.p != '{') return false;
+    std::vector<const char *> start{head.p};
+    for (unsigned t = 1; t < T; t++) {
+        const char *from = std::max(data + len / T * t, start.back() + 1);
+        const char *g = guess_element_start(data, from, std::min(end, from + len / T));
+        if (g) start.push_back(g);
+    }
+    T = (unsigned)start.size();
+    if (T < 2) return false;
+    std::vector<SigList> parts(T);
+    std::vector<char> ok(T, 0);
+    auto piece = [&](unsigned t) {
+        try {
+            JReader r(start[t], (size_t)(end - start[t]));
+            const char *stop = t + 1 < T ? start[t + 1] : nullptr;
+            SketchFields scratch;
+            while (true) {
+                read_signature(r, scratch, flt, parts[t]);
+                if (stop) {
+                    if (!r.eat(',')) return;
+                    r.ws();
+                    if (r.p == stop) break;
+                    if (r.p > stop) return;
+                } else {
+                    if (r.eat(',')) continue;
+                    if (!r.eat(']')) return;
+                    r.ws();
+                    if (r.p != r.e) return;
+                    break;
+                }
+            }
+            ok[t] = 1;
+        } catch (...) {
+        }
+    };
+    std::vector<std::thread> workers;
+    for (unsigned t = 1; t < T; t++) workers.emplace_back(piece, t);
+    piece(0);
+    for (auto &w : workers) w.join();
+    for (unsigned t = 0; t < T; t++)
+        if (!ok[t]) return false;
+    size_t total = 0;
+    for (auto &p : parts) total += p.size();
+    out.reserve(total);
+    for (auto &p : parts)
+        for (auto &s : p) out.push_back(std::move(s));
+    return true;
+}
+}  // namespace
+
+std::vector<std::unique_ptr<Signature>> load_signatures(const char *data, size_t len, size_t ksize, const char *moltype) {
+    const LoadFilter flt{ksize, moltype};
+    static const bool trace = getenv("SMB200_JSON_TRACE") != nullptr;  // which reader ran, for the tests
+    SigList out;
+    if (load_parallel(data, len, flt, out)) {
+        if (trace) fprintf(stderr, "smb200 json: %zu bytes read in pieces\n", len);
+        return out;
+    }
+    if (trace) fprintf(stderr, "smb200 json: %zu bytes read in one pass\n", len);
+    return load_sequential(data, len, flt);
 }
 
 // First gzip member of `data`, inflated (what flate2::read::GzDecoder yields; src/file.rs:62-66).

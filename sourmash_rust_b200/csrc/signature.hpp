@@ -29,8 +29,8 @@ struct Signature {
     void to_json(std::string &out);  // serde_json::to_string(&Signature), ffi.rs:498
 };
 
-// serde_json::to_string(&Vec<&Signature>) (ffi.rs:531)
-std::string signatures_to_json(Signature *const *sigs, size_t n);
+// serde_json::to_string(&Vec<&Signature>) (ffi.rs:531) into a malloc'd buffer of *len bytes (not NUL-terminated)
+char *signatures_to_json(Signature *const *sigs, size_t n, size_t *len);
 // Signature::load_signatures (lib.rs:593-645): parse a JSON array of signatures, flatten to one
 // Signature per sketch, keep those passing the ksize / moltype filter.  Throws SourmashError.
 std::vector<std::unique_ptr<Signature>> load_signatures(const char *data, size_t len, size_t ksize,

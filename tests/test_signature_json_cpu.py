@@ -268,3 +268,90 @@ def test_large_file_throughput(smb):
         best_save = min(best_save, time.perf_counter() - t)
     assert out == txt                                    # byte-identical round trip, md5sum recomputed
     assert len(txt) / best_load > 100e6 and len(txt) / best_save > 40e6, (len(txt) / best_load / 1e6, len(txt) / best_save / 1e6)
+
+
+_PARALLEL_PROBE = r"""
+import hashlib, json, sys
+sys.path.insert(0, %(root)r)
+import sourmash_rust_b200 as smb
+out = {}
+for path in sys.argv[1:]:
+    data = open(path, "rb").read()
+    try:
+        sigs = smb.signatures_load_buffer(data)
+        per = "".join(s.save_json().decode() for s in sigs)
+        whole = smb.signatures_save_buffer(sigs).decode()
+        assert whole == "[" + ",".join(s.save_json().decode() for s in sigs) + "]"
+        out[path] = [len(sigs), hashlib.md5(per.encode()).hexdigest()]
+    except smb.SourmashError as e:
+        out[path] = ["error", e.code, e.message]
+print(json.dumps(out))
+"""
+
+
+def test_threaded_reader_and_writer_match_single_thread(tmp_path):
+    """Files above a few MB are cut at guessed element boundaries and parsed on several threads, each guess verified
+    by the piece before it (signature.cpp, load_parallel); large outputs are written in runs.  Whatever the file
+    looks like, the result -- and the error, for a broken file -- must be that of the single-pass reader."""
+    import subprocess
+    rng = random.Random(11)
+
+    def sketch(k, n):
+        mins = sorted({rng.getrandbits(64) for _ in range(n)})
+        return {"num": 0, "ksize": k, "seed": 42, "max_hash": 2 ** 64 - 1, "mins": mins, "md5sum": "", "molecule": "DNA",
+                "abundances": [rng.randrange(1, 50) for _ in mins]}
+
+    bait = '},{"class":"x","hash_function":"y","signatures":[]},{"class"'
+    def signatures(n, per_sig, n_hashes, names=lambda i: "g%d" % i, extra=None):
+        docs = []
+        for i in range(n):
+            d = {"class": "sourmash_signature", "email": "", "hash_function": "0.murmur64", "filename": None, "name": names(i),
+                 "license": "CC0", "signatures": [sketch(k, n_hashes) for k in (21, 31, 51)[:per_sig]], "version": 0.4}
+            if extra:
+                d.update(extra(i))
+            docs.append(d)
+        return docs
+
+    files = {}
+    def put(name, text):
+        files[name] = str(tmp_path / name)
+        open(files[name], "w", encoding="utf-8").write(text)
+
+    compact = signatures(400, 3, 300)
+    put("compact.sig", json.dumps(compact, separators=(",", ":")))
+    put("pretty_sorted.sig", json.dumps(compact, indent=4, sort_keys=True))                    # what the Python writer emits
+    put("bait_in_names.sig", json.dumps(signatures(400, 3, 300, names=lambda i: bait * (i % 3)), separators=(",", ":")))
+    # an unknown field holding objects that look exactly like array elements: guesses land inside it and must be refused
+    # (the real elements start with "email" here, so every guess there is lands inside `zz_history`)
+    nested = signatures(60, 1, 200, extra=lambda i: {"zz_history": signatures(12, 1, 300)})
+    nested = [dict([("email", d["email"])] + [kv for kv in d.items() if kv[0] != "email"]) for d in nested]
+    put("bait_in_unknown_field.sig", json.dumps(nested, separators=(", ", ": ")))
+    put("class_not_first.sig", json.dumps([dict(reversed(list(d.items()))) for d in compact], separators=(",", ":")))
+    broken = json.dumps(compact, separators=(",", ":"))
+    cut = broken.rindex('"ksize":51')
+    put("late_error.sig", broken[:cut] + '"ksize":-51' + broken[cut + len('"ksize":51'):])    # an error deep in the last piece
+    put("truncated.sig", broken[:len(broken) * 3 // 4])
+    put("trailing.sig", broken + " x")
+    assert all(os.path.getsize(p) > 4 << 20 for p in files.values())
+
+    def run(threads):
+        env = dict(os.environ, SMB200_JSON_THREADS=str(threads), SMB200_JSON_TRACE="1")
+        r = subprocess.run([sys.executable, "-c", _PARALLEL_PROBE % {"root": ROOT}] + list(files.values()), env=env,
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+        assert r.returncode == 0, r.stderr.decode()
+        trace = [ln.split(" bytes ")[1] for ln in r.stderr.decode().splitlines() if ln.startswith("smb200 json:")]
+        how = dict(zip(files, trace))
+        assert len(trace) == len(files)
+        if threads > 1:  # the guesses hold for both writers' layouts and are refused where they must be
+            assert how["compact.sig"] == how["pretty_sorted.sig"] == how["bait_in_names.sig"] == "read in pieces", how
+            assert how["class_not_first.sig"] == how["late_error.sig"] == how["truncated.sig"] == "read in one pass", how
+            assert how["bait_in_unknown_field.sig"] == "read in one pass", how   # a guess inside `zz_history` was refused
+        else:
+            assert set(how.values()) == {"read in one pass"}
+        return json.loads(r.stdout.decode().strip().splitlines()[-1])
+
+    single = run(1)
+    assert single[files["compact.sig"]][0] == 1200 and single[files["pretty_sorted.sig"]] == single[files["compact.sig"]]
+    assert single[files["late_error.sig"]][0] == "error" and single[files["truncated.sig"]][0] == "error"
+    for threads in (2, 5, 8):
+        assert run(threads) == single, threads
