@@ -14,6 +14,7 @@
 #include <fstream>
 #include <iostream>
 #include <sstream>
+#include <system_error>
 #include <thread>
 
 #include <zlib.h>
@@ -180,6 +181,23 @@ static unsigned json_threads() {
     return n;
 }
 
+// fn(0) .. fn(T-1), each on its own thread (fn(0) on the caller's); a piece whose thread cannot be started runs
+// on the caller's thread instead.  fn must not throw.
+template <typename F>
+static void run_pieces(unsigned T, F fn) {
+    std::vector<std::thread> workers;
+    std::vector<unsigned> inline_pieces{0};
+    for (unsigned t = 1; t < T; t++) {
+        try {
+            workers.emplace_back(fn, t);
+        } catch (const std::system_error &) {
+            inline_pieces.push_back(t);
+        }
+    }
+    for (unsigned t : inline_pieces) fn(t);
+    for (auto &w : workers) w.join();
+}
+
 // Output goes to a malloc'd buffer the C ABI hands to the caller as is (SourmashStr, freed by sourmash_str_free).
 // Large outputs are written in contiguous runs of signatures on several host threads; each thread then copies
 // its run into place.  The host copies of the sketches are fetched first, on the calling thread (a device
@@ -204,13 +222,7 @@ char *signatures_to_json(Signature *const *sigs, size_t n, size_t *len) {
             errs[t] = std::current_exception();
         }
     };
-    auto on_threads = [&](auto fn) {
-        std::vector<std::thread> workers;
-        for (unsigned t = 1; t < T; t++) workers.emplace_back(fn, t);
-        fn(0);
-        for (auto &w : workers) w.join();
-    };
-    on_threads(write_run);
+    run_pieces(T, write_run);
     for (auto &e : errs)
         if (e) std::rethrow_exception(e);
     std::vector<size_t> at(T);
@@ -225,7 +237,7 @@ char *signatures_to_json(Signature *const *sigs, size_t n, size_t *len) {
     if (!out) throw std::bad_alloc();
     out[0] = '[';
     out[total - 1] = ']';
-    on_threads([&](unsigned t) {
+    run_pieces(T, [&](unsigned t) {
         if (t) out[at[t] - 1] = ',';
         memcpy(out + at[t], parts[t].data(), parts[t].size());
         std::string().swap(parts[t]);
@@ -764,10 +776,7 @@ bool load_parallel(const char *data, size_t len, const LoadFilter &flt, SigList 
         } catch (...) {
         }
     };
-    std::vector<std::thread> workers;
-    for (unsigned t = 1; t < T; t++) workers.emplace_back(piece, t);
-    piece(0);
-    for (auto &w : workers) w.join();
+    run_pieces(T, piece);
     for (unsigned t = 0; t < T; t++)
         if (!ok[t]) return false;
     size_t total = 0;
