@@ -150,3 +150,16 @@ def test_collection_push_signatures_host_side(smb):
     with pytest.raises(smb.SourmashError) as e:
         smb.SketchCollection.from_signatures([empty])
     assert e.value.code == 1
+
+
+def test_host_hash_matches_oracle_over_lengths_and_seeds(smb):
+    """hash_murmur is a scalar call answered on the host (lib.rs:33-35): every tail length 0..15 with 0..4 body
+    blocks, several seeds (NUL-free bytes: the ABI takes a C string, ffi.rs:16-24)."""
+    import random
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as orc
+    rng = random.Random(99)
+    for n in list(range(0, 81)) + [127, 128, 129, 1000]:
+        for seed in (42, 0, 1, 0xFFFFFFFF, 123456789):
+            word = bytes(rng.randrange(1, 256) for _ in range(n))
+            assert smb.hash_murmur(word, seed) == orc.hash_murmur(word, seed), (n, seed)
