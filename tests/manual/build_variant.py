@@ -16,5 +16,5 @@ obj = os.path.join(b.OBJ, "%s_%s.o" % (os.path.splitext(src)[0], name))
 subprocess.run([b.NVCC] + b.FLAGS + extra + ["-c", os.path.join(b.CSRC, src), "-o", obj], check=True)
 objs = [os.path.join(b.OBJ, os.path.splitext(s)[0] + ".o") for s in b.SOURCES if s != src] + [obj]
 out = os.path.join(b.OBJ, "libsourmash_%s.so" % name)
-subprocess.run([b.NVCC, "-shared", "-o", out] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"], check=True)
+subprocess.run([b.NVCC, "-shared", "-o", out] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt", "-lz"], check=True)
 print(out)
