@@ -81,7 +81,10 @@ def _worker(rank, world, port, ret):
 
 def test_world_size_2_gloo():
     world = 2
-    port = 29500 + (os.getpid() % 400)
+    import socket
+    with socket.socket() as s:  # a port nobody holds right now
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
