@@ -382,7 +382,7 @@ def run_ours(args):
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except OSError:
+    except (OSError, ValueError):
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
     k31_ms, k31_n = kern["sketch_k31"]
