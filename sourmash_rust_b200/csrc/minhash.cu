@@ -16,6 +16,8 @@
 //       survivors are replayed in stream order by a single-CTA kernel (launch_replay_add_hash).
 #include "minhash.hpp"
 
+#include <atomic>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -69,7 +71,12 @@ KmerMinHash::KmerMinHash(uint32_t num_, uint32_t ksize_, bool is_protein_, uint6
     : num(num_), ksize(ksize_), is_protein(is_protein_), seed(seed_), max_hash(max_hash_),
       has_abunds_(track_abundance) {}
 
-KmerMinHash::~KmerMinHash() {}
+// Bytes of deferred add_sequence calls waiting in all sketches together (see "deferral of short sequences" below):
+// many live sketches (10^5 genomes, one handle each) must not pile up host memory without bound -- above
+// kDeferTotalCap a sketch flushes on every call until others have drained.
+static std::atomic<size_t> g_seq_pending_total{0};
+
+KmerMinHash::~KmerMinHash() { g_seq_pending_total -= seq_pending_.size(); }
 
 KmerMinHash *KmerMinHash::clone() {
     flush();
@@ -177,6 +184,7 @@ void KmerMinHash::abunds_push(uint64_t v) {
 }
 void KmerMinHash::set_from_host(const uint64_t *mins_in, size_t n, const uint64_t *abunds_in, size_t n_abunds) {
     pending_.clear();
+    g_seq_pending_total -= seq_pending_.size();
     seq_pending_.clear();
     seq_offsets_.assign(1, 0);
     n_cand_ = 0;
@@ -436,6 +444,7 @@ bool g_defer_small_sequences = [] {
 }();
 namespace {
 const size_t kDeferMaxLen = size_t(1) << 16, kDeferFlushBytes = size_t(8) << 20;
+const size_t kDeferTotalCap = size_t(1) << 30;  // see g_seq_pending_total
 bool all_acgt(const uint8_t *s, size_t n) {
     static const struct Lut {
         uint8_t ok[256];
@@ -456,6 +465,7 @@ void KmerMinHash::flush_sequences() {
     std::vector<uint64_t> offs(1, 0);
     bytes.swap(seq_pending_);   // taken out first: add_sequences comes back here through flush_pending()
     offs.swap(seq_offsets_);
+    g_seq_pending_total -= bytes.size();
     SeqBatch b;
     b.buf = bytes.data();
     b.offsets = offs.data();
@@ -480,7 +490,8 @@ void KmerMinHash::add_sequence(const uint8_t *seq, size_t len, bool force) {
         seq_force_ = force;
         seq_pending_.insert(seq_pending_.end(), seq, seq + len);
         seq_offsets_.push_back(seq_pending_.size());
-        if (seq_pending_.size() >= kDeferFlushBytes) flush_sequences();
+        const size_t total = (g_seq_pending_total += len);
+        if (seq_pending_.size() >= kDeferFlushBytes || total > kDeferTotalCap) flush_sequences();
         return;
     }
     SeqBatch b;
