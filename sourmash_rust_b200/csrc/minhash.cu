@@ -16,6 +16,8 @@
 //       survivors are replayed in stream order by a single-CTA kernel (launch_replay_add_hash).
 #include "minhash.hpp"
 
+#include <atomic>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -69,7 +71,12 @@ KmerMinHash::KmerMinHash(uint32_t num_, uint32_t ksize_, bool is_protein_, uint6
     : num(num_), ksize(ksize_), is_protein(is_protein_), seed(seed_), max_hash(max_hash_),
       has_abunds_(track_abundance) {}
 
-KmerMinHash::~KmerMinHash() {}
+// Bytes of deferred add_sequence calls waiting in all sketches together (see "deferral of short sequences" below):
+// many live sketches (10^5 genomes, one handle each) must not pile up host memory without bound -- above
+// kDeferTotalCap a sketch flushes on every call until others have drained.
+static std::atomic<size_t> g_seq_pending_total{0};
+
+KmerMinHash::~KmerMinHash() { g_seq_pending_total -= seq_pending_.size(); }
 
 KmerMinHash *KmerMinHash::clone() {
     flush();
@@ -177,6 +184,9 @@ void KmerMinHash::abunds_push(uint64_t v) {
 }
 void KmerMinHash::set_from_host(const uint64_t *mins_in, size_t n, const uint64_t *abunds_in, size_t n_abunds) {
     pending_.clear();
+    g_seq_pending_total -= seq_pending_.size();
+    seq_pending_.clear();
+    seq_offsets_.assign(1, 0);
     n_cand_ = 0;
     h_mins_.assign(mins_in, mins_in + n);
     if (abunds_in) h_abunds_.assign(abunds_in, abunds_in + n_abunds); else h_abunds_.clear();
@@ -211,10 +221,17 @@ bool KmerMinHash::equals(KmerMinHash &o) {
 }
 
 // ---- single-hash entry points -----------------------------------------------------------------
-void KmerMinHash::add_hash(uint64_t hash) { pending_.push_back(hash); }
+void KmerMinHash::add_hash(uint64_t hash) {
+    flush_sequences();  // deferred sequences came first
+    pending_.push_back(hash);
+}
 void KmerMinHash::add_word(const uint8_t *word, size_t len) { add_hash(hash_murmur_host(word, len, seed)); }
-void KmerMinHash::add_many(const uint64_t *hashes, size_t n) { pending_.insert(pending_.end(), hashes, hashes + n); }
+void KmerMinHash::add_many(const uint64_t *hashes, size_t n) {
+    flush_sequences();
+    pending_.insert(pending_.end(), hashes, hashes + n);
+}
 void KmerMinHash::add_from(KmerMinHash &other) {
+    flush_sequences();
     const std::vector<uint64_t> &m = other.mins();
     pending_.insert(pending_.end(), m.begin(), m.end());
 }
@@ -253,6 +270,7 @@ void KmerMinHash::replay(Context &ctx, const uint64_t *d_events, uint64_t n_even
 
 // add_hash events buffered on the host -> candidates (or straight replay)
 void KmerMinHash::flush_pending() {
+    flush_sequences();
     if (pending_.empty()) return;
     Context &ctx = Context::get();
     ensure_dev();
@@ -412,7 +430,70 @@ bool KmerMinHash::ingest(Context &ctx, bool thr_is_estimate) {
 // ---------------------------------------------------------------------------------------------
 // add_sequence / add_sequences
 // ---------------------------------------------------------------------------------------------
+// ---- deferral of short sequences ---------------------------------------------------------------------------
+// A caller of the unmodified reference ABI feeds reads one call at a time (150 bp per call in BASELINE cfg2); going to
+// the device per call costs 45 us whatever the length.  A short sequence that cannot raise an error -- only
+// ACGT/acgt, or force == true (invalid windows are skipped, lib.rs:268-273) -- is therefore appended to a host-side
+// batch and the call returns; the batch goes through add_sequences (which keeps per-sequence order semantics) when it
+// reaches kDeferFlushBytes or when anything reads, combines or otherwise touches the sketch (flush_pending() is the
+// gate).  A sequence that CAN raise InvalidDNA takes the synchronous path below -- after the deferred ones, in call
+// order -- so the error, and the partial mutation before it, belong to the call that caused them.
+bool g_defer_small_sequences = [] {
+    const char *e = getenv("SMB200_DEFER_SEQ");
+    return !(e && e[0] == '0');
+}();
+namespace {
+const size_t kDeferMaxLen = size_t(1) << 16, kDeferFlushBytes = size_t(8) << 20;
+const size_t kDeferTotalCap = size_t(1) << 30;  // see g_seq_pending_total
+bool all_acgt(const uint8_t *s, size_t n) {
+    static const struct Lut {
+        uint8_t ok[256];
+        Lut() {
+            memset(ok, 0, sizeof ok);
+            for (const char *c = "ACGTacgt"; *c; c++) ok[(uint8_t)*c] = 1;
+        }
+    } lut;
+    uint8_t all = 1;
+    for (size_t i = 0; i < n; i++) all &= lut.ok[s[i]];
+    return all != 0;
+}
+}  // namespace
+
+void KmerMinHash::flush_sequences() {
+    if (seq_offsets_.size() <= 1) return;
+    std::vector<uint8_t> bytes;
+    std::vector<uint64_t> offs(1, 0);
+    bytes.swap(seq_pending_);   // taken out first: add_sequences comes back here through flush_pending()
+    offs.swap(seq_offsets_);
+    g_seq_pending_total -= bytes.size();
+    SeqBatch b;
+    b.buf = bytes.data();
+    b.offsets = offs.data();
+    b.n_seqs = offs.size() - 1;
+    b.n_bytes = bytes.size();
+    KmerMinHash *self = this;
+    add_sequences(&self, 1, b, seq_force_);
+    if (seq_pending_.empty() && seq_offsets_.size() == 1) {  // keep the (already touched) storage for the next batch
+        bytes.clear();
+        offs.assign(1, 0);
+        seq_pending_.swap(bytes);
+        seq_offsets_.swap(offs);
+    }
+}
+
 void KmerMinHash::add_sequence(const uint8_t *seq, size_t len, bool force) {
+    if (g_defer_small_sequences && !is_protein && ksize != 0 && len <= kDeferMaxLen && (force || all_acgt(seq, len))) {
+        Context::get();  // no device: fail on this call, as the synchronous path would
+        if (len < ksize) return;  // lib.rs:258: shorter than k adds nothing
+        if (!pending_.empty()) flush_pending();  // add_hash events came first
+        if (seq_offsets_.size() > 1 && seq_force_ != force) flush_sequences();
+        seq_force_ = force;
+        seq_pending_.insert(seq_pending_.end(), seq, seq + len);
+        seq_offsets_.push_back(seq_pending_.size());
+        const size_t total = (g_seq_pending_total += len);
+        if (seq_pending_.size() >= kDeferFlushBytes || total > kDeferTotalCap) flush_sequences();
+        return;
+    }
     SeqBatch b;
     b.buf = seq;
     b.n_seqs = 1;
@@ -440,6 +521,7 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
         if (mhs[i]->is_protein && mhs[i]->ksize < 3)  // the reference reaches slice::windows(0), which panics
             throw SourmashError(ERR_PANIC, "sourmash panicked: size is zero");
     }
+    for (int i = 0; i < n_mhs; i++) mhs[i]->flush_sequences();  // deferred add_sequence calls came first
     const uint64_t n = batch.n_bytes;
     if (n == 0) return;
     if (batch.offsets == nullptr && batch.read_len != 0 && n != batch.n_seqs * (uint64_t)batch.read_len)

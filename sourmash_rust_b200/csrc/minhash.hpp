@@ -101,6 +101,12 @@ class KmerMinHash {
     int sorted_ = 1;
     // add_hash events not yet ingested (stream order)
     std::vector<uint64_t> pending_;
+    // small sequences of add_sequence calls not yet sketched (host side, call order; see add_sequence).  At most
+    // one of pending_ / seq_pending_ is non-empty at any time, so call order between the two kinds is kept.
+    std::vector<uint8_t> seq_pending_;
+    std::vector<uint64_t> seq_offsets_{0};
+    bool seq_force_ = false;
+    void flush_sequences();
     // survivors of the sketch kernel not yet merged into the state (scaled sketches merge lazily)
     DevBuf d_cand_hash_, d_cand_pos_;
     uint64_t n_cand_ = 0;
@@ -121,6 +127,10 @@ class KmerMinHash {
     void replay(Context &ctx, const uint64_t *d_events, uint64_t n_events);
     void commit(DevBuf &mins, DevBuf &abunds, size_t n_mins, size_t n_abunds);
 };
+
+// add_sequence calls on short valid sequences are collected on the host and sketched as one batch
+// (SMB200_DEFER_SEQ=0 switches this off)
+extern bool g_defer_small_sequences;
 
 // host scalar hash (ffi.rs:15-24)
 uint64_t hash_murmur_host(const uint8_t *kmer, size_t len, uint64_t seed);

@@ -1,4 +1,5 @@
-"""Cost of ONE kmerminhash_add_sequence call on a 150 bp read (the unmodified reference ABI, one read per call)."""
+"""Cost of ONE kmerminhash_add_sequence call on a 150 bp read (the unmodified reference ABI, one read per call).
+SMB200_DEFER_SEQ=0 gives the synchronous path (45 us per call in round 1)."""
 import os, sys, time, random
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import sourmash_rust_b200 as smb
