@@ -446,14 +446,20 @@ uint64_t linear_find(SketchCollection &index, SketchCollection &queries, int mod
         // the shared-hash COUNT of every cell in a u32 matrix.  One pass over that matrix picks the hits (count
         // > 0 and count / |node| > threshold); the f64 ratio matrix, the flag matrix, its scan and the compaction
         // of the general path (7 GB of traffic per 128 M cells) are never materialised.
-        const bool count_path = mode == 1 && threshold >= 0.0;
+        // Similarity takes the same path when no index sketch has a `num` (scaled sketches): lib.rs:470-499 with
+        // self.num == 0 gives common = |A n B| and size = |A u B| = |A| + |B| - common, both known from the count.
+        bool index_unbounded = true;
+        for (uint32_t v : index.h_nums) index_unbounded &= v == 0;
+        const bool count_sim = mode == 0 && index_unbounded;
+        const bool count_path = (mode == 1 || count_sim) && threshold >= 0.0;
         for (uint64_t b0 = 0; count_path && b0 < ni; b0 += block_rows) {
             const uint64_t bn = std::min(block_rows, ni - b0);
             uint32_t *cmat = ctx.misc[2].as<uint32_t>();  // cells * 8 bytes reserved: room for the u32 counts
             uint64_t *found = ctx.misc[3].as<uint64_t>();
             compare_block_device(index, b0, bn, queries, 0, nq, 1, cmat, nullptr, nullptr, nq);
             SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_CNT), 0, 8, st));
-            launch_count_hits(cmat, bn, nq, index.d_offsets.as<uint64_t>(), b0, threshold, found, cells, ctx.dsc(SC_CNT), st);
+            launch_count_hits(cmat, bn, nq, index.d_offsets.as<uint64_t>(), b0, count_sim ? queries.d_offsets.as<uint64_t>() : nullptr,
+                              threshold, found, cells, ctx.dsc(SC_CNT), st);
             ctx.read_scalars();
             const uint64_t n_hit = ctx.h_scalars[SC_CNT];
             if (n_hit > cells) throw_internal("linear_find: hit list overflow");

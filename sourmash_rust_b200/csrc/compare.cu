@@ -301,26 +301,33 @@ void launch_compact_indices(const uint64_t *flags, const uint64_t *pre, uint64_t
 // linear_find, containment with threshold >= 0: cells of the count matrix (row-major [index row][query], ld = nq) whose
 // count is non-zero and whose count / |node| exceeds the threshold (strict '>', search.rs:7-9; index.rs:152-154) are
 // appended as query * nr + row through *n_found (entries beyond cap are counted, not stored)
+// q_offsets != nullptr: similarity of sketches whose node side has num == 0 (lib.rs:470-508 with self.num == 0:
+// common = |A n B|, size = |A u B| = |A| + |B| - common), the denominator max(1, size) of lib.rs:504
 __global__ void __launch_bounds__(256) count_hits_kernel(const uint32_t *__restrict__ cmat, uint64_t nr, uint64_t nq,
-                                                         const uint64_t *__restrict__ row_offsets, uint64_t r0, double threshold,
+                                                         const uint64_t *__restrict__ row_offsets, uint64_t r0,
+                                                         const uint64_t *__restrict__ q_offsets, double threshold,
                                                          uint64_t *found, uint64_t cap, unsigned long long *n_found) {
     for (uint64_t i = blockIdx.y; i < nr; i += gridDim.y) {
-        const double den = (double)(row_offsets[r0 + i + 1] - row_offsets[r0 + i]);
+        const uint64_t la = row_offsets[r0 + i + 1] - row_offsets[r0 + i];
         for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nq; j += (uint64_t)gridDim.x * blockDim.x) {
             const uint32_t cm = cmat[i * nq + j];
-            if (cm != 0 && (double)cm / den > threshold) {
+            if (cm == 0) continue;
+            double den = (double)la;
+            if (q_offsets) den = (double)(la + (q_offsets[j + 1] - q_offsets[j]) - cm);  // >= 1 when cm >= 1
+            if ((double)cm / den > threshold) {
                 const unsigned long long at = atomicAdd(n_found, 1ull);
                 if (at < cap) found[at] = j * nr + i;
             }
         }
     }
 }
-void launch_count_hits(const uint32_t *cmat, uint64_t nr, uint64_t nq, const uint64_t *row_offsets, uint64_t r0, double threshold,
-                       uint64_t *found, uint64_t cap, unsigned long long *n_found, cudaStream_t st) {
+void launch_count_hits(const uint32_t *cmat, uint64_t nr, uint64_t nq, const uint64_t *row_offsets, uint64_t r0,
+                       const uint64_t *q_offsets, double threshold, uint64_t *found, uint64_t cap, unsigned long long *n_found,
+                       cudaStream_t st) {
     if (!nr || !nq) return;
     const unsigned gx = (unsigned)std::min<uint64_t>((nq + 255) / 256, 64);
     const unsigned gy = (unsigned)std::min<uint64_t>(nr, std::max<uint64_t>(1, (148 * 32) / gx));
-    count_hits_kernel<<<dim3(gx, gy), 256, 0, st>>>(cmat, nr, nq, row_offsets, r0, threshold, found, cap, n_found);
+    count_hits_kernel<<<dim3(gx, gy), 256, 0, st>>>(cmat, nr, nq, row_offsets, r0, q_offsets, threshold, found, cap, n_found);
     SM_LAUNCHED();
 }
 

@@ -152,8 +152,10 @@ void launch_compare_cross(const uint64_t *row_hashes, const uint64_t *row_offset
 void launch_threshold_flags_t(const double *ratio, uint64_t nr, uint64_t nq, double threshold, uint64_t *flags,
                               cudaStream_t st);
 // linear_find's containment fast path: hits straight from the u32 count matrix (see compare.cu)
-void launch_count_hits(const uint32_t *cmat, uint64_t nr, uint64_t nq, const uint64_t *row_offsets, uint64_t r0, double threshold,
-                       uint64_t *found, uint64_t cap, unsigned long long *n_found, cudaStream_t st);
+// (q_offsets: the queries' CSR offsets for the similarity form over num == 0 sketches, else nullptr)
+void launch_count_hits(const uint32_t *cmat, uint64_t nr, uint64_t nq, const uint64_t *row_offsets, uint64_t r0,
+                       const uint64_t *q_offsets, double threshold, uint64_t *found, uint64_t cap, unsigned long long *n_found,
+                       cudaStream_t st);
 // *flag = 1 if some CSR row is not strictly ascending
 void launch_csr_check_sorted(const uint64_t *hashes, const uint64_t *offsets, uint64_t n_rows, unsigned long long *flag,
                              cudaStream_t st);
