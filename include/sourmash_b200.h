@@ -8,6 +8,9 @@
  * bit-identical to running that loop against the reference.
  *
  * Error convention: as sourmash.h (thread-local last error, zero return value).
+ * Threading: as the reference (src/utils.rs:14-16) -- no library-wide lock.  Every host thread that calls in
+ * gets its own CUDA stream and scratch; distinct handles may be driven from distinct threads at the same
+ * time, and a handle may move between threads (the new thread waits for what the old one queued).
  * Pointers marked [host|device] are host pointers unless the call's `on_device` flag is set, in
  * which case they are device pointers of the library's device (see smgpu_set_device) and no
  * host<->device copy is made.
@@ -29,8 +32,8 @@ void smgpu_set_device(int32_t device);
 int32_t smgpu_device(int32_t *sm_count);
 /* kernels this library has launched so far in this process */
 uint64_t smgpu_launch_count(void);
-/* the CUDA stream (cudaStream_t, as an integer) every kernel of the library is launched on: lets a
- * caller bracket calls with its own CUDA events */
+/* the CUDA stream (cudaStream_t, as an integer) the kernels launched from the CALLING THREAD go to: lets a
+ * caller bracket its calls with its own CUDA events */
 uint64_t smgpu_stream(void);
 /* per-kernel device timing with CUDA events on that stream: kinds 0/1/2 = sketch kernel k=21/31/51,
  * 3 = sketch kernel other k, 4 = compare matrix kernel.  read() waits for the recorded events and
@@ -47,6 +50,19 @@ void *smgpu_alloc_pinned(uintptr_t bytes);
 void smgpu_free_pinned(void *ptr);
 /* frees what kmerminhash_get_mins / kmerminhash_get_abunds returned (reference: leaked, ffi.rs:97-122) */
 void kmerminhash_slice_free(const uint64_t *ptr);
+
+/* ---- names and results the crate has but src/ffi.rs does not export ---------------------------------- */
+/* north_star's names: jaccard = KmerMinHash::compare (src/lib.rs:501-508);
+ * containment = |ptr n other| / |ptr|, the sketch `ptr` in the role of the node of
+ * Leaf::containment (src/index.rs:146-160; 0/0 = NaN).  Errors as kmerminhash_compare / _count_common. */
+double kmerminhash_jaccard(KmerMinHash *ptr, const KmerMinHash *other);
+double kmerminhash_containment(KmerMinHash *ptr, const KmerMinHash *other);
+/* KmerMinHash::intersection (src/lib.rs:438-468): the hashes common to both sketches that are also among
+ * combined = bottom_num(ptr u other), ascending; *n_common = how many, *size (nullable) = |combined|.
+ * (kmerminhash_intersection, src/ffi.rs:292-309, returns only |combined|.)  The returned array is the
+ * caller's: kmerminhash_slice_free.  On error: NULL, *n_common untouched. */
+const uint64_t *kmerminhash_intersection_hashes(KmerMinHash *ptr, const KmerMinHash *other, uintptr_t *n_common,
+                                                uint64_t *size);
 
 /* ---- batch sketching ------------------------------------------------------------------------- */
 /* for s in 0..n_seqs: for m in 0..n_mhs: kmerminhash_add_sequence(mhs[m], buf[offsets[s]..offsets[s+1]], force)
@@ -93,7 +109,8 @@ SketchCollection *smgpu_collection_from_csr(const uint64_t *hashes /*[host|devic
  *                        smgpu_collection_push(c, mh) }
  * (src/lib.rs:142-174, 252-274) -- the sketching half of "sketch N genomes, compare them all" -- in ONE
  * pass over the batch instead of N calls.  Either num > 0 (bottom-num sketches) or max_hash > 0 (scaled);
- * DNA only; invalid k-mers are skipped (force = true).  A device `buf` must be 16-byte aligned. */
+ * DNA only; invalid k-mers are skipped (force = true).  A device `buf` must be 16-byte aligned and readable
+ * up to offsets[n_seqs] rounded up to 16 (the kernel's bulk copies move whole 16-byte groups). */
 SketchCollection *smgpu_sketch_collection(const char *buf /*[host|device]*/, const uint64_t *offsets /*[host|device], n_seqs + 1 */,
                                           uint64_t n_seqs, uint32_t num, uint32_t ksize, uint64_t seed, uint64_t max_hash,
                                           bool on_device);

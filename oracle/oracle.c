@@ -466,6 +466,26 @@ int orc_mh_intersection_size(const OrcMinHash *a, const OrcMinHash *b, uint64_t 
     return ORC_OK;
 }
 
+/* lib.rs:438-468: the common hashes themselves (those of A n B also in combined) and |combined|.
+ * out receives at most cap of them; *n_common the number there are. */
+int orc_mh_intersection(const OrcMinHash *a, const OrcMinHash *b, uint64_t *out, size_t cap, uint64_t *n_common, uint64_t *size) {
+    int e = orc_mh_check_compatible(a, b);
+    *n_common = 0; *size = 0;
+    if (e) return e;
+    OrcMinHash *comb = orc_mh_new(a->num, a->ksize, a->is_protein, a->seed, a->max_hash, a->has_abunds);
+    orc_mh_merge(comb, a);
+    orc_mh_merge(comb, b);
+    vec64 i1 = {0}, common = {0};
+    intersection_walk(a->mins.p, a->mins.len, b->mins.p, b->mins.len, &i1);
+    intersection_walk(i1.p, i1.len, comb->mins.p, comb->mins.len, &common);
+    *n_common = common.len;
+    *size = comb->mins.len;
+    for (size_t i = 0; i < common.len && i < cap; i++) out[i] = common.p[i];
+    v_free(&i1); v_free(&common);
+    orc_mh_free(comb);
+    return ORC_OK;
+}
+
 /* lib.rs:501-508 */
 int orc_mh_compare(const OrcMinHash *a, const OrcMinHash *b, double *out) {
     uint64_t common, size;

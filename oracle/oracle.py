@@ -6,6 +6,8 @@ package.  Mirrors the reference's crate API names (KmerMinHash::new,
 add_sequence, add_hash, merge, compare, count_common, ...; src/lib.rs:141-513).
 """
 import ctypes as C
+
+import numpy as np
 import os
 import subprocess
 
@@ -53,6 +55,7 @@ def lib():
             "orc_mh_merge": (i, [vp, vp]),
             "orc_mh_count_common": (i, [vp, vp, C.POINTER(u64)]),
             "orc_mh_intersection_size": (i, [vp, vp, C.POINTER(u64), C.POINTER(u64)]),
+            "orc_mh_intersection": (i, [vp, vp, C.POINTER(u64), sz, C.POINTER(u64), C.POINTER(u64)]),
             "orc_mh_compare": (i, [vp, vp, C.POINTER(C.c_double)]),
             "orc_leaf_similarity": (C.c_double, [vp, vp]),
             "orc_leaf_containment": (C.c_double, [vp, vp]),
@@ -217,6 +220,15 @@ class KmerMinHash:
         if e:
             raise SourmashError(e, _MESSAGES.get(e, ""))
         return c.value, s.value
+
+    def intersection(self, other):  # lib.rs:438-468
+        cap = min(self.size(), other.size())
+        buf = (C.c_uint64 * max(1, cap))()
+        n, s = C.c_uint64(), C.c_uint64()
+        e = self._L.orc_mh_intersection(self._p, other._p, buf, cap, C.byref(n), C.byref(s))
+        if e:
+            raise SourmashError(e, _MESSAGES.get(e, ""))
+        return np.array(buf[:n.value], dtype=np.uint64), s.value
 
     def compare(self, other):
         d = C.c_double()

@@ -87,6 +87,9 @@ EXTENSION_ABI = {
     "smgpu_alloc_pinned": (vp, [usz]),
     "smgpu_free_pinned": (None, [vp]),
     "kmerminhash_slice_free": (None, [p_u64]),
+    "kmerminhash_jaccard": (C.c_double, [vp, vp]),
+    "kmerminhash_containment": (C.c_double, [vp, vp]),
+    "kmerminhash_intersection_hashes": (p_u64, [vp, vp, C.POINTER(usz), C.POINTER(u64)]),
     "kmerminhash_add_sequences": (None, [C.POINTER(vp), usz, vp, vp, u64, cb, cb]),
     "kmerminhash_add_reads": (None, [C.POINTER(vp), usz, vp, u64, u32, cb, cb]),
     "kmerminhash_set_mins": (None, [vp, vp, usz, vp, usz]),
@@ -299,7 +302,17 @@ class KmerMinHash:
     def compare(self, other):
         return _call("kmerminhash_compare", self._p, other._p)
 
-    jaccard = compare  # north_star alias; the reference's name is `compare` (lib.rs:501-508)
+    def jaccard(self, other):
+        """north_star's name for `compare` (lib.rs:501-508), through its own C symbol."""
+        return _call("kmerminhash_jaccard", self._p, other._p)
+
+    def intersection(self, other):
+        """KmerMinHash::intersection (lib.rs:438-468): (common hashes within combined, |combined|)."""
+        n, size = usz(0), u64(0)
+        p = _call("kmerminhash_intersection_hashes", self._p, other._p, C.byref(n), C.byref(size))
+        out = np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.zeros(0, dtype=np.uint64)
+        lib().kmerminhash_slice_free(p)
+        return out, size.value
 
     def count_common(self, other):
         return _call("kmerminhash_count_common", self._p, other._p)
@@ -310,9 +323,7 @@ class KmerMinHash:
 
     def containment(self, query):
         """Leaf<Signature>::containment with self as the node: |self n query| / |self| (index.rs:146-160)."""
-        common = self.count_common(query)
-        n = self.size()
-        return float("nan") if n == 0 else common / n
+        return _call("kmerminhash_containment", self._p, query._p)
 
     similarity = compare  # Leaf<Signature>::similarity (index.rs:131-144)
 
@@ -381,6 +392,33 @@ def add_sequences(mhs, buf, offsets, force=True, on_device=False, n_seqs=None):
         keep_o = np.ascontiguousarray(offsets, dtype=np.uint64)
         n_seqs = keep_o.size - 1
     _call("kmerminhash_add_sequences", _handles(mhs), len(mhs), _vp(keep_b), _vp(keep_o), n_seqs, force, on_device)
+
+
+_feed = None
+
+
+def feed_reads(mh_groups, reads: np.ndarray, n_reads, stride, force=False):
+    """The reference's calling pattern for a read set, timed natively: a C loop (host/feed_reads.c) calls
+    kmerminhash_add_sequence once per read and per sketch.  `reads` holds n_reads NUL-terminated strings, one
+    every `stride` bytes; mh_groups is a list (one entry per host thread) of equally long lists of sketches --
+    thread t feeds its sketches with its contiguous share of the reads.  Returns the loop's wall time in seconds
+    (the sketches still hold deferred work: read them to include the flush)."""
+    global _feed
+    if _feed is None:
+        path = os.path.join(_HERE, "libfeedreads.so")
+        if not os.path.exists(path):
+            raise RuntimeError("%s is missing: run `python -m sourmash_rust_b200.build`" % path)
+        F = C.CDLL(path)
+        F.feed_reads_mt.restype = u64
+        F.feed_reads_mt.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, vp, u64, u64, cb]
+        _feed = F
+    n_mhs = len(mh_groups[0])
+    assert all(len(g) == n_mhs for g in mh_groups)
+    flat = (vp * (n_mhs * len(mh_groups)))(*[m._p for g in mh_groups for m in g])
+    fn = C.cast(lib().kmerminhash_add_sequence, vp)
+    lib().sourmash_err_clear()
+    ns = _feed.feed_reads_mt(fn, flat, n_mhs, len(mh_groups), _vp(reads), n_reads, stride, force)
+    return ns * 1e-9
 
 
 class Signature:

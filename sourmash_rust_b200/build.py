@@ -9,6 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libsourmash.so")
+FEED_SRC = os.path.join(HERE, "host", "feed_reads.c")   # a C caller's loop over the reference ABI (bench / percall timing)
+FEED_LIB = os.path.join(HERE, "libfeedreads.so")
 SOURCES = ["device.cu", "sketch.cu", "sortops.cu", "compare.cu", "join.cu", "protein.cu", "minhash.cu", "collection.cu", "sketch_many.cu", "nodegraph.cu", "signature.cpp", "ffi.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-Wall",
@@ -36,7 +38,14 @@ def _compile(src):
     return obj
 
 
+def build_feed(force=False):
+    if force or not os.path.exists(FEED_LIB) or os.path.getmtime(FEED_SRC) > os.path.getmtime(FEED_LIB):
+        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-Wall", "-o", FEED_LIB, FEED_SRC, "-lpthread"])
+    return FEED_LIB
+
+
 def build_library(force=False, verbose=False):
+    build_feed(force)
     if not force and not is_stale():
         return LIB
     os.makedirs(OBJ, exist_ok=True)

@@ -31,8 +31,9 @@ void SketchCollection::push(KmerMinHash &mh) {
 }
 
 void SketchCollection::finalize() {
-    if (!dirty) return;
     Context &ctx = Context::get();
+    ctx.adopt(owner);  // last used from another thread: wait for what that thread queued
+    if (!dirty) return;
     n_rows = h_nums.size();
     n_hashes = h_hashes.size();
     d_hashes.reserve((n_hashes + 4) * 8);  // slack: the pair walk reads up to two elements past a row
@@ -51,6 +52,7 @@ SketchCollection *SketchCollection::from_csr(const uint64_t *hashes, const uint6
                                              uint32_t ksize_, uint64_t seed_, uint64_t max_hash_, bool on_device) {
     Context &ctx = Context::get();
     std::unique_ptr<SketchCollection> c(new SketchCollection());
+    ctx.adopt(c->owner);
     c->have_params = true;
     c->ksize = ksize_; c->seed = seed_; c->max_hash = max_hash_; c->is_protein = false;
     c->n_rows = n_rows_;
@@ -355,11 +357,7 @@ void compare_matrix(SketchCollection &rows, uint64_t r0, uint64_t nr, SketchColl
         if (size) bs[k]->reserve(block_rows * nc * 4);
         if (ratio) br[k]->reserve(block_rows * nc * 8);
     }
-    static cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
-    for (int k = 0; k < 2; k++) {
-        if (!ev_done[k]) SM_CUDA(cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming));
-        if (!ev_free[k]) SM_CUDA(cudaEventCreateWithFlags(&ev_free[k], cudaEventDisableTiming));
-    }
+    cudaEvent_t *ev_done = ctx.ev_done, *ev_free = ctx.ev_free;
     cudaStream_t cs = ctx.copy_stream;
     auto copy_back = [&](void *dst, uint64_t dst_ld_bytes, const void *src, uint64_t row_bytes, uint64_t n_rows_blk) {
         if (dst_ld_bytes == row_bytes)  // contiguous: one linear copy

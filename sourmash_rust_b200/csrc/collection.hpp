@@ -27,6 +27,8 @@ struct SketchCollection {
     // compare path bookkeeping (collection.cu): has a block with these rows gone through the probe form of
     // the join yet, and did it find so many incidences that the dense kernels are the better choice
     bool probe_checked = false, probe_dense_preferred = false;
+    std::mutex mu;      // as KmerMinHash::mu
+    StreamOwner owner;  // thread context that last queued work on the device arrays (finalize() re-homes)
 
     void push(KmerMinHash &mh);
     static SketchCollection *from_csr(const uint64_t *hashes, const uint64_t *offsets, uint64_t n_rows, uint32_t num,

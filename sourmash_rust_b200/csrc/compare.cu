@@ -114,6 +114,21 @@ void launch_compact_unflagged(const uint64_t *vals, const uint64_t *flags, const
     compact_unflagged_kernel<<<(unsigned)blocks, 256, 0, st>>>(vals, flags, pre, n, out);
     SM_LAUNCHED();
 }
+// out[pre[i]] = vals[i] for every i with flag 1, as long as pre[i] < limit
+__global__ void compact_flagged_kernel(const uint64_t *__restrict__ vals, const uint64_t *__restrict__ flags,
+                                       const uint64_t *__restrict__ pre, uint64_t n, uint64_t limit, uint64_t *__restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        if (flags[i] && pre[i] < limit) out[pre[i]] = vals[i];
+}
+void launch_compact_flagged(const uint64_t *vals, const uint64_t *flags, const uint64_t *pre, uint64_t n, uint64_t limit,
+                            uint64_t *out, cudaStream_t st) {
+    if (!n) return;
+    uint64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    compact_flagged_kernel<<<(unsigned)blocks, 256, 0, st>>>(vals, flags, pre, n, limit, out);
+    SM_LAUNCHED();
+}
 
 // -------------------------------------------------------------------------------------
 // Matrix kernels.  CTA = 8 warps = 8 rows x 32 columns.

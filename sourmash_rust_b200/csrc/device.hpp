@@ -82,10 +82,21 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-// One per process (per device in use): the stream every kernel of the library
-// is launched on, small device scalars, and reusable scratch.
+// Which host thread's context last queued device work on an object (a sketch, a collection, a bloom
+// filter).  The reference's contract is "a handle may be used from any thread, but not concurrently"
+// (SURVEY 8(b) Threading): when an object turns up on another thread, that thread first waits for the
+// stream the object was last used on (Context::adopt), then carries on with its own.
+struct StreamOwner {
+    uint64_t ctx_id = 0;
+};
+
+// One per HOST THREAD (all on the process's one device): the stream every kernel launched from that
+// thread goes to, small device scalars, and reusable scratch.  Distinct handles driven from distinct
+// threads therefore share nothing but the device's memory pool -- no lock is held around a call
+// (utils.rs:14-16: the reference's only per-thread state is the error slot; here it is also this).
 struct Context {
     int device = -1;
+    uint64_t id = 0;  // never reused; 0 = none
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int sm_count = 148;
@@ -101,8 +112,11 @@ struct Context {
     cudaEvent_t k_events[6] = {nullptr};
     cudaEvent_t prep_event = nullptr;
 
-    static Context &get();      // creates on first use; throws if no CUDA device
-    static Context *peek();     // nullptr before first use
+    static Context &get();      // this thread's context; creates on first use; throws if no CUDA device
+    static Context *peek();     // nullptr before this thread's first use
+    void adopt(StreamOwner &o); // `o` was last used on another thread: wait for that thread's stream
+    ~Context();
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};  // compare_matrix's read-back pipeline
     void sync() { SM_CUDA(cudaStreamSynchronize(stream)); }
     void set_scalar(int idx, unsigned long long v);  // synchronous
     void read_scalars();                              // d_scalars -> h_scalars, synchronous

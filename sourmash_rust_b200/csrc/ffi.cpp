@@ -12,6 +12,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/sourmash_b200.h"
 #include "collection.hpp"
@@ -34,8 +35,43 @@ struct LastError {
 };
 thread_local LastError g_last_error;
 
-// one GPU context per process: serialise the calls that drive it
-std::recursive_mutex g_api_mutex;
+// Locking (SURVEY 8(b) Threading; utils.rs:14-16): there is no library-wide lock.  Every host thread has its own
+// stream and scratch (device.cu), the error slot is thread-local, and a call holds only the locks of the objects
+// it is handed -- so distinct handles are independent, as in the reference, and host-only calls (hash_murmur,
+// the scalar getters, string helpers) take no lock at all.  The per-object lock makes concurrent calls on ONE
+// handle safe as well (the reference's &self methods may be shared between threads; here even a read can
+// flush deferred work, i.e. mutate).
+typedef std::mutex Mu;
+struct Guard {  // locks up to two objects (the same object twice: once), in address order
+    Mu *a = nullptr, *b = nullptr;
+    explicit Guard(Mu &x) : a(&x) { a->lock(); }
+    Guard(Mu &x, Mu &y) : a(&x), b(&y) {
+        if (a == b) b = nullptr;
+        else if (b < a) std::swap(a, b);
+        a->lock();
+        if (b) b->lock();
+    }
+    ~Guard() {
+        if (b) b->unlock();
+        a->unlock();
+    }
+    Guard(const Guard &) = delete;
+    Guard &operator=(const Guard &) = delete;
+};
+struct GuardN {  // any number of objects
+    std::vector<Mu *> ms;
+    void add(Mu &m) { ms.push_back(&m); }
+    void lock() {
+        std::sort(ms.begin(), ms.end());
+        ms.erase(std::unique(ms.begin(), ms.end()), ms.end());
+        for (Mu *m : ms) m->lock();
+        locked = true;
+    }
+    ~GuardN() {
+        if (locked) for (size_t i = ms.size(); i-- > 0;) ms[i]->unlock();
+    }
+    bool locked = false;
+};
 
 void set_error(uint32_t code, const std::string &msg) {
     g_last_error.code = code;
@@ -45,7 +81,6 @@ void set_error(uint32_t code, const std::string &msg) {
 template <class T, class F>
 T landingpad(F &&body) {
     try {
-        std::lock_guard<std::recursive_mutex> lk(g_api_mutex);
         return body();
     } catch (const SourmashError &e) {
         set_error(e.code, e.what());
@@ -136,44 +171,47 @@ void kmerminhash_add_sequence(KmerMinHash *ptr, const char *sequence, bool force
     landingpad_void([&]() {
         MH *m = mh(ptr);
         nonnull(sequence, "sequence");
+        Guard lk(m->mu);
         m->add_sequence(reinterpret_cast<const uint8_t *>(sequence), strlen(sequence), force);
     });
 }
 void kmerminhash_add_hash(KmerMinHash *ptr, uint64_t h) {
-    landingpad_void([&]() { mh(ptr)->add_hash(h); });
+    landingpad_void([&]() { MH *m = mh(ptr); Guard lk(m->mu); m->add_hash(h); });
 }
 void kmerminhash_add_word(KmerMinHash *ptr, const char *word) {
     landingpad_void([&]() {
         MH *m = mh(ptr);
         nonnull(word, "word");
+        Guard lk(m->mu);
         m->add_word(reinterpret_cast<const uint8_t *>(word), strlen(word));
     });
 }
 void kmerminhash_add_from(KmerMinHash *ptr, const KmerMinHash *other) {
-    landingpad_void([&]() { mh(ptr)->add_from(*mh(other)); });
+    landingpad_void([&]() { MH *a = mh(ptr), *b = mh(other); Guard lk(a->mu, b->mu); a->add_from(*b); });
 }
 void kmerminhash_mins_push(KmerMinHash *ptr, uint64_t val) {
-    landingpad_void([&]() { mh(ptr)->mins_push(val); });
+    landingpad_void([&]() { MH *m = mh(ptr); Guard lk(m->mu); m->mins_push(val); });
 }
 void kmerminhash_abunds_push(KmerMinHash *ptr, uint64_t val) {
-    landingpad_void([&]() { mh(ptr)->abunds_push(val); });
+    landingpad_void([&]() { MH *m = mh(ptr); Guard lk(m->mu); m->abunds_push(val); });
 }
 
 // ---------------------------------------------------------------------------------------------
 // combine / compare
 // ---------------------------------------------------------------------------------------------
 void kmerminhash_merge(KmerMinHash *ptr, const KmerMinHash *other) {
-    landingpad_void([&]() { mh(ptr)->merge(*mh(other)); });
+    landingpad_void([&]() { MH *a = mh(ptr), *b = mh(other); Guard lk(a->mu, b->mu); a->merge(*b); });
 }
 double kmerminhash_compare(KmerMinHash *ptr, const KmerMinHash *other) {
-    return landingpad<double>([&]() { return mh(ptr)->compare(*mh(other)); });
+    return landingpad<double>([&]() { MH *a = mh(ptr), *b = mh(other); Guard lk(a->mu, b->mu); return a->compare(*b); });
 }
 uint64_t kmerminhash_count_common(KmerMinHash *ptr, const KmerMinHash *other) {
-    return landingpad<uint64_t>([&]() { return mh(ptr)->count_common(*mh(other)); });
+    return landingpad<uint64_t>([&]() { MH *a = mh(ptr), *b = mh(other); Guard lk(a->mu, b->mu); return a->count_common(*b); });
 }
 uint64_t kmerminhash_intersection(KmerMinHash *ptr, const KmerMinHash *other) {
     return landingpad<uint64_t>([&]() -> uint64_t {
         MH *a = mh(ptr), *b = mh(other);
+        Guard lk(a->mu, b->mu);
         try {
             return a->intersection_size(*b).second;
         } catch (const SourmashError &e) {
@@ -188,27 +226,31 @@ uint64_t kmerminhash_intersection(KmerMinHash *ptr, const KmerMinHash *other) {
 // read-out
 // ---------------------------------------------------------------------------------------------
 const uint64_t *kmerminhash_get_mins(KmerMinHash *ptr) {
-    return landingpad<const uint64_t *>([&]() { return (const uint64_t *)copy_out(mh(ptr)->mins()); });
+    return landingpad<const uint64_t *>([&]() { MH *m = mh(ptr); Guard lk(m->mu); return (const uint64_t *)copy_out(m->mins()); });
 }
 const uint64_t *kmerminhash_get_abunds(KmerMinHash *ptr) {
     return landingpad<const uint64_t *>([&]() -> const uint64_t * {
         MH *m = mh(ptr);
+        Guard lk(m->mu);
         if (!m->track_abundance()) return nullptr;
         return copy_out(m->abunds());
     });
 }
 uintptr_t kmerminhash_get_mins_size(KmerMinHash *ptr) {
-    return landingpad<uintptr_t>([&]() { return (uintptr_t)mh(ptr)->size(); });
+    return landingpad<uintptr_t>([&]() { MH *m = mh(ptr); Guard lk(m->mu); return (uintptr_t)m->size(); });
 }
 uintptr_t kmerminhash_get_abunds_size(KmerMinHash *ptr) {
     return landingpad<uintptr_t>([&]() -> uintptr_t {
         MH *m = mh(ptr);
+        Guard lk(m->mu);
         return m->track_abundance() ? m->abunds().size() : 0;
     });
 }
 uint64_t kmerminhash_get_min_idx(KmerMinHash *ptr, uint64_t idx) {
     return landingpad<uint64_t>([&]() {
-        const std::vector<uint64_t> &v = mh(ptr)->mins();
+        MH *m = mh(ptr);
+        Guard lk(m->mu);
+        const std::vector<uint64_t> &v = m->mins();
         if (idx >= v.size()) panic("index out of bounds: the len is " + std::to_string(v.size()) + " but the index is " + std::to_string(idx));
         return v[idx];
     });
@@ -216,6 +258,7 @@ uint64_t kmerminhash_get_min_idx(KmerMinHash *ptr, uint64_t idx) {
 uint64_t kmerminhash_get_abund_idx(KmerMinHash *ptr, uint64_t idx) {
     return landingpad<uint64_t>([&]() -> uint64_t {
         MH *m = mh(ptr);
+        Guard lk(m->mu);
         if (!m->track_abundance()) return 0;  // ffi.rs:161-163
         const std::vector<uint64_t> &v = m->abunds();
         if (idx >= v.size()) panic("index out of bounds: the len is " + std::to_string(v.size()) + " but the index is " + std::to_string(idx));
@@ -224,7 +267,7 @@ uint64_t kmerminhash_get_abund_idx(KmerMinHash *ptr, uint64_t idx) {
 }
 bool kmerminhash_is_protein(KmerMinHash *ptr) { return landingpad<bool>([&]() { return mh(ptr)->is_protein; }); }
 uint64_t kmerminhash_seed(KmerMinHash *ptr) { return landingpad<uint64_t>([&]() { return mh(ptr)->seed; }); }
-bool kmerminhash_track_abundance(KmerMinHash *ptr) { return landingpad<bool>([&]() { return mh(ptr)->track_abundance(); }); }
+bool kmerminhash_track_abundance(KmerMinHash *ptr) { return landingpad<bool>([&]() { MH *m = mh(ptr); Guard lk(m->mu); return m->track_abundance(); }); }
 uint32_t kmerminhash_num(KmerMinHash *ptr) { return landingpad<uint32_t>([&]() { return mh(ptr)->num; }); }
 uint32_t kmerminhash_ksize(KmerMinHash *ptr) { return landingpad<uint32_t>([&]() { return mh(ptr)->ksize; }); }
 uint64_t kmerminhash_max_hash(KmerMinHash *ptr) { return landingpad<uint64_t>([&]() { return mh(ptr)->max_hash; }); }
@@ -243,6 +286,7 @@ void signature_set_name(Signature *ptr, const char *name) {
     landingpad_void([&]() {
         SIG *s = sig(ptr);
         nonnull(name, "name");
+        Guard lk(s->mu);
         if (valid_utf8(name)) { s->has_name = true; s->name = name; }  // ffi.rs:356-359: ignored when not UTF-8
     });
 }
@@ -250,32 +294,36 @@ void signature_set_filename(Signature *ptr, const char *name) {
     landingpad_void([&]() {
         SIG *s = sig(ptr);
         nonnull(name, "name");
+        Guard lk(s->mu);
         if (valid_utf8(name)) { s->has_filename = true; s->filename = name; }
     });
 }
 void signature_push_mh(Signature *ptr, const KmerMinHash *other) {
-    landingpad_void([&]() { sig(ptr)->signatures.emplace_back(mh(other)->clone()); });
+    landingpad_void([&]() { SIG *s = sig(ptr); MH *m = mh(other); Guard lk(s->mu, m->mu); s->signatures.emplace_back(m->clone()); });
 }
 void signature_set_mh(Signature *ptr, const KmerMinHash *other) {
     landingpad_void([&]() {
         SIG *s = sig(ptr);
-        std::unique_ptr<MH> c(mh(other)->clone());
+        MH *m = mh(other);
+        Guard lk(s->mu, m->mu);
+        std::unique_ptr<MH> c(m->clone());
         s->signatures.clear();
         s->signatures.push_back(std::move(c));
     });
 }
 SourmashStr signature_get_name(Signature *ptr) {
-    return landingpad<SourmashStr>([&]() { SIG *s = sig(ptr); return str_from(s->has_name ? s->name : std::string()); });
+    return landingpad<SourmashStr>([&]() { SIG *s = sig(ptr); Guard lk(s->mu); return str_from(s->has_name ? s->name : std::string()); });
 }
 SourmashStr signature_get_filename(Signature *ptr) {
-    return landingpad<SourmashStr>([&]() { SIG *s = sig(ptr); return str_from(s->has_filename ? s->filename : std::string()); });
+    return landingpad<SourmashStr>([&]() { SIG *s = sig(ptr); Guard lk(s->mu); return str_from(s->has_filename ? s->filename : std::string()); });
 }
 SourmashStr signature_get_license(Signature *ptr) {
-    return landingpad<SourmashStr>([&]() { return str_from(sig(ptr)->license); });
+    return landingpad<SourmashStr>([&]() { SIG *s = sig(ptr); Guard lk(s->mu); return str_from(s->license); });
 }
 KmerMinHash *signature_first_mh(Signature *ptr) {
     return landingpad<KmerMinHash *>([&]() {
         SIG *s = sig(ptr);
+        Guard lk(s->mu);
         MH *out = s->signatures.empty() ? MH::make_default() : s->signatures[0]->clone();  // ffi.rs:466-471
         return reinterpret_cast<KmerMinHash *>(out);
     });
@@ -284,6 +332,7 @@ KmerMinHash **signature_get_mhs(Signature *ptr, uintptr_t *size) {
     return landingpad<KmerMinHash **>([&]() {
         SIG *s = sig(ptr);
         nonnull(size, "size");
+        Guard lk(s->mu);
         const size_t n = s->signatures.size();
         KmerMinHash **arr = static_cast<KmerMinHash **>(malloc((n ? n : 1) * sizeof(KmerMinHash *)));
         if (!arr) throw std::bad_alloc();
@@ -293,18 +342,23 @@ KmerMinHash **signature_get_mhs(Signature *ptr, uintptr_t *size) {
     });
 }
 bool signature_eq(Signature *ptr, Signature *other) {
-    return landingpad<bool>([&]() { return sig(ptr)->equals(*sig(other)); });
+    return landingpad<bool>([&]() { SIG *a = sig(ptr), *b = sig(other); Guard lk(a->mu, b->mu); return a->equals(*b); });
 }
 SourmashStr signature_save_json(Signature *ptr) {
     return landingpad<SourmashStr>([&]() {
         std::string out;
-        sig(ptr)->to_json(out);
+        SIG *s = sig(ptr);
+        Guard lk(s->mu);
+        s->to_json(out);
         return str_from(out);
     });
 }
 SourmashStr signatures_save_buffer(Signature **ptr, uintptr_t size) {
     return landingpad<SourmashStr>([&]() {
         nonnull(ptr, "ptr");
+        GuardN lk;
+        for (uintptr_t i = 0; i < size; i++) lk.add(sig(ptr[i])->mu);
+        lk.lock();
         SourmashStr r;
         size_t len = 0;
         r.data = smb200::signatures_to_json(reinterpret_cast<SIG *const *>(ptr), size, &len);
@@ -423,6 +477,23 @@ void smgpu_free_pinned(void *ptr) {
 }
 void kmerminhash_slice_free(const uint64_t *ptr) { free(const_cast<uint64_t *>(ptr)); }
 
+// north_star's names for the two similarity measures (the crate itself calls them compare and Leaf::containment)
+double kmerminhash_jaccard(KmerMinHash *ptr, const KmerMinHash *other) { return kmerminhash_compare(ptr, other); }
+double kmerminhash_containment(KmerMinHash *ptr, const KmerMinHash *other) {
+    return landingpad<double>([&]() { MH *a = mh(ptr), *b = mh(other); Guard lk(a->mu, b->mu); return a->containment(*b); });
+}
+const uint64_t *kmerminhash_intersection_hashes(KmerMinHash *ptr, const KmerMinHash *other, uintptr_t *n_common, uint64_t *size) {
+    return landingpad<const uint64_t *>([&]() {
+        MH *a = mh(ptr), *b = mh(other);
+        nonnull(n_common, "n_common");
+        Guard lk(a->mu, b->mu);
+        std::pair<std::vector<uint64_t>, uint64_t> r = a->intersection(*b);
+        *n_common = r.first.size();
+        if (size) *size = r.second;
+        return (const uint64_t *)copy_out(r.first);
+    });
+}
+
 void kmerminhash_add_sequences(KmerMinHash *const *mhs, uintptr_t n_mhs, const char *buf, const uint64_t *offsets,
                                uint64_t n_seqs, bool force, bool on_device) {
     landingpad_void([&]() {
@@ -445,7 +516,9 @@ void kmerminhash_add_sequences(KmerMinHash *const *mhs, uintptr_t n_mhs, const c
             if (offsets[0] != 0) smb200::throw_internal("offsets[0] must be 0");
             b.n_bytes = offsets[n_seqs];
         }
-        for (uintptr_t i = 0; i < n_mhs; i++) mh(mhs[i]);
+        GuardN lk;
+        for (uintptr_t i = 0; i < n_mhs; i++) lk.add(mh(mhs[i])->mu);
+        lk.lock();
         MH::add_sequences(reinterpret_cast<MH *const *>(mhs), (int)n_mhs, b, force);
     });
 }
@@ -461,7 +534,9 @@ void kmerminhash_add_reads(KmerMinHash *const *mhs, uintptr_t n_mhs, const char 
         b.read_len = read_len;
         b.n_bytes = n_reads * (uint64_t)read_len;
         b.on_device = on_device;
-        for (uintptr_t i = 0; i < n_mhs; i++) mh(mhs[i]);
+        GuardN lk;
+        for (uintptr_t i = 0; i < n_mhs; i++) lk.add(mh(mhs[i])->mu);
+        lk.lock();
         MH::add_sequences(reinterpret_cast<MH *const *>(mhs), (int)n_mhs, b, force);
     });
 }
@@ -469,12 +544,14 @@ void kmerminhash_set_mins(KmerMinHash *ptr, const uint64_t *mins, uintptr_t n, c
     landingpad_void([&]() {
         MH *m = mh(ptr);
         if (n) nonnull(mins, "mins");
+        Guard lk(m->mu);
         m->set_from_host(mins, n, m->track_abundance() ? abunds : nullptr, abunds ? n_abunds : 0);
     });
 }
 uintptr_t kmerminhash_copy_mins(KmerMinHash *ptr, uint64_t *mins, uint64_t *abunds, bool on_device) {
     return landingpad<uintptr_t>([&]() -> uintptr_t {
         MH *m = mh(ptr);
+        Guard lk(m->mu);
         size_t n = 0, na = 0;
         const uint64_t *dm = m->device_mins(&n);
         const uint64_t *da = m->device_abunds(&na);
@@ -487,7 +564,7 @@ uintptr_t kmerminhash_copy_mins(KmerMinHash *ptr, uint64_t *mins, uint64_t *abun
     });
 }
 SourmashStr kmerminhash_md5sum(KmerMinHash *ptr) {
-    return landingpad<SourmashStr>([&]() { return str_from(mh(ptr)->md5sum()); });
+    return landingpad<SourmashStr>([&]() { MH *m = mh(ptr); Guard lk(m->mu); return str_from(m->md5sum()); });
 }
 
 SketchCollection *smgpu_collection_new(void) {
@@ -498,12 +575,16 @@ void smgpu_collection_free(SketchCollection *c) {
     landingpad_void([&]() { delete reinterpret_cast<COLL *>(c); });
 }
 void smgpu_collection_push(SketchCollection *c, KmerMinHash *m) {
-    landingpad_void([&]() { coll(c)->push(*mh(m)); });
+    landingpad_void([&]() { COLL *cc = coll(c); MH *s = mh(m); Guard lk(cc->mu, s->mu); cc->push(*s); });
 }
 void smgpu_collection_push_signatures(SketchCollection *c, Signature *const *sigs, uintptr_t n) {
     landingpad_void([&]() {
         COLL *cc = coll(c);
         if (n) nonnull(sigs, "sigs");
+        GuardN lk;
+        lk.add(cc->mu);
+        for (uintptr_t i = 0; i < n; i++) lk.add(sig(sigs[i])->mu);
+        lk.lock();
         size_t extra = 0;
         for (uintptr_t i = 0; i < n; i++) {
             SIG *s = sig(sigs[i]);
@@ -533,11 +614,12 @@ SketchCollection *smgpu_sketch_collection(const char *buf, const uint64_t *offse
     });
 }
 uint64_t smgpu_collection_len(SketchCollection *c) {
-    return landingpad<uint64_t>([&]() { COLL *cc = coll(c); return cc->dirty ? (uint64_t)cc->h_nums.size() : cc->n_rows; });
+    return landingpad<uint64_t>([&]() { COLL *cc = coll(c); Guard lk(cc->mu); return cc->dirty ? (uint64_t)cc->h_nums.size() : cc->n_rows; });
 }
 uint64_t smgpu_collection_copy(SketchCollection *c, uint64_t *hashes, uint64_t *offsets) {
     return landingpad<uint64_t>([&]() -> uint64_t {
         COLL *cc = coll(c);
+        Guard lk(cc->mu);
         cc->finalize();
         smb200::Context &ctx = smb200::Context::get();
         if (offsets) std::copy(cc->h_offsets.begin(), cc->h_offsets.begin() + cc->n_rows + 1, offsets);
@@ -551,6 +633,7 @@ uint64_t smgpu_collection_copy(SketchCollection *c, uint64_t *hashes, uint64_t *
 uint64_t smgpu_collection_csr(SketchCollection *c, const uint64_t **hashes_dev, const uint64_t **offsets_dev) {
     return landingpad<uint64_t>([&]() {
         COLL *cc = coll(c);
+        Guard lk(cc->mu);
         cc->finalize();
         if (hashes_dev) *hashes_dev = cc->d_hashes.as<uint64_t>();
         if (offsets_dev) *offsets_dev = cc->d_offsets.as<uint64_t>();
@@ -561,14 +644,18 @@ void smgpu_compare_matrix(SketchCollection *rows, uint64_t r0, uint64_t nr, Sket
                           int32_t mode, uint32_t *common, uint32_t *size, double *ratio, uint64_t ld, bool out_on_device) {
     landingpad_void([&]() {
         if (mode != 0 && mode != 1) smb200::throw_internal("mode must be 0 (compare) or 1 (containment)");
-        smb200::compare_matrix(*coll(rows), r0, nr, *coll(cols), c0, nc, mode, common, size, ratio, ld, out_on_device);
+        COLL *r = coll(rows), *c = coll(cols);
+        Guard lk(r->mu, c->mu);
+        smb200::compare_matrix(*r, r0, nr, *c, c0, nc, mode, common, size, ratio, ld, out_on_device);
     });
 }
 uint64_t smgpu_scaffold_pairs(SketchCollection *c, uint64_t *pairs_first, uint64_t *pairs_second) {
     return landingpad<uint64_t>([&]() {
         nonnull(pairs_first, "pairs_first");
         nonnull(pairs_second, "pairs_second");
-        return smb200::scaffold_pairs(*coll(c), pairs_first, pairs_second);
+        COLL *cc = coll(c);
+        Guard lk(cc->mu);
+        return smb200::scaffold_pairs(*cc, pairs_first, pairs_second);
     });
 }
 void smgpu_fuse_multi_k(bool on) { smb200::g_fuse_multi_k = on; }
@@ -577,7 +664,9 @@ uint64_t smgpu_linear_find(SketchCollection *index, SketchCollection *queries, i
                            uint64_t *hit_offsets, uint64_t *hits, uint64_t hits_cap) {
     return landingpad<uint64_t>([&]() {
         if (mode != 0 && mode != 1) smb200::throw_internal("mode must be 0 (similarity) or 1 (containment)");
-        return smb200::linear_find(*coll(index), *coll(queries), mode, threshold, hit_offsets, hits, hits_cap);
+        COLL *ix = coll(index), *q = coll(queries);
+        Guard lk(ix->mu, q->mu);
+        return smb200::linear_find(*ix, *q, mode, threshold, hit_offsets, hits, hits_cap);
     });
 }
 
@@ -599,35 +688,42 @@ Nodegraph *smgpu_nodegraph_from_buffer(const uint8_t *data, uintptr_t len) {
     });
 }
 uintptr_t smgpu_nodegraph_save(Nodegraph *ng, uint8_t *out, uintptr_t cap) {
-    return landingpad<uintptr_t>([&]() -> uintptr_t { return ngp(ng)->save(out, out ? cap : 0); });
+    return landingpad<uintptr_t>([&]() -> uintptr_t { NG *g = ngp(ng); Guard lk(g->mu); return g->save(out, out ? cap : 0); });
 }
 uint64_t smgpu_nodegraph_count_many(Nodegraph *ng, const uint64_t *hashes, uint64_t n, uint8_t *is_new, bool on_device) {
     return landingpad<uint64_t>([&]() -> uint64_t {
         if (n) nonnull(hashes, "hashes");
-        return ngp(ng)->count_many(hashes, n, is_new, on_device);
+        NG *g = ngp(ng);
+        Guard lk(g->mu);
+        return g->count_many(hashes, n, is_new, on_device);
     });
 }
 uint64_t smgpu_nodegraph_get_many(Nodegraph *ng, const uint64_t *hashes, uint64_t n, uint8_t *present, bool on_device) {
     return landingpad<uint64_t>([&]() -> uint64_t {
         if (n) nonnull(hashes, "hashes");
-        return ngp(ng)->get_many(hashes, n, present, on_device);
+        NG *g = ngp(ng);
+        Guard lk(g->mu);
+        return g->get_many(hashes, n, present, on_device);
     });
 }
 uint64_t smgpu_nodegraph_matches(Nodegraph *ng, KmerMinHash *ptr) {
     return landingpad<uint64_t>([&]() -> uint64_t {
         size_t n = 0;
-        const uint64_t *dm = mh(ptr)->device_mins(&n);
-        return ngp(ng)->get_many(dm, n, nullptr, true);
+        NG *g = ngp(ng);
+        MH *m = mh(ptr);
+        Guard lk(g->mu, m->mu);
+        const uint64_t *dm = m->device_mins(&n);
+        return g->get_many(dm, n, nullptr, true);
     });
 }
 void smgpu_nodegraph_update(Nodegraph *ng, Nodegraph *other) {
-    landingpad_void([&]() { ngp(ng)->update(*ngp(other)); });
+    landingpad_void([&]() { NG *a = ngp(ng), *b = ngp(other); Guard lk(a->mu, b->mu); a->update(*b); });
 }
 double smgpu_nodegraph_similarity(Nodegraph *ng, Nodegraph *other) {
-    return landingpad<double>([&]() { return ngp(ng)->similarity(*ngp(other)); });
+    return landingpad<double>([&]() { NG *a = ngp(ng), *b = ngp(other); Guard lk(a->mu, b->mu); return a->similarity(*b); });
 }
 double smgpu_nodegraph_containment(Nodegraph *ng, Nodegraph *other) {
-    return landingpad<double>([&]() { return ngp(ng)->containment(*ngp(other)); });
+    return landingpad<double>([&]() { NG *a = ngp(ng), *b = ngp(other); Guard lk(a->mu, b->mu); return a->containment(*b); });
 }
 uintptr_t smgpu_nodegraph_tablesizes(Nodegraph *ng, uint64_t *out, uintptr_t cap) {
     return landingpad<uintptr_t>([&]() -> uintptr_t {
@@ -637,8 +733,8 @@ uintptr_t smgpu_nodegraph_tablesizes(Nodegraph *ng, uint64_t *out, uintptr_t cap
     });
 }
 uint64_t smgpu_nodegraph_ksize(Nodegraph *ng) { return landingpad<uint64_t>([&]() { return ngp(ng)->ksize; }); }
-uint64_t smgpu_nodegraph_n_occupied_bins(Nodegraph *ng) { return landingpad<uint64_t>([&]() { return ngp(ng)->occupied_bins; }); }
-uint64_t smgpu_nodegraph_unique_kmers(Nodegraph *ng) { return landingpad<uint64_t>([&]() { return ngp(ng)->unique_kmers; }); }
+uint64_t smgpu_nodegraph_n_occupied_bins(Nodegraph *ng) { return landingpad<uint64_t>([&]() { NG *g = ngp(ng); Guard lk(g->mu); return g->occupied_bins; }); }
+uint64_t smgpu_nodegraph_unique_kmers(Nodegraph *ng) { return landingpad<uint64_t>([&]() { NG *g = ngp(ng); Guard lk(g->mu); return g->unique_kmers; }); }
 uint64_t smgpu_sbt_find(uint32_t d, const uint64_t *node_positions, Nodegraph *const *nodes, const uint64_t *min_n_below,
                         uint64_t n_nodes, const uint64_t *leaf_positions, SketchCollection *leaves, SketchCollection *queries,
                         int32_t mode, double threshold, uint64_t *hit_offsets, uint64_t *hits, uint64_t hits_cap) {
@@ -648,6 +744,11 @@ uint64_t smgpu_sbt_find(uint32_t d, const uint64_t *node_positions, Nodegraph *c
         if (n_nodes) { nonnull(node_positions, "node_positions"); nonnull(nodes, "nodes"); nonnull(min_n_below, "min_n_below"); }
         for (uint64_t i = 0; i < n_nodes; i++) ngp(nodes[i]);
         COLL *l = coll(leaves);
+        GuardN lk;
+        lk.add(l->mu);
+        lk.add(coll(queries)->mu);
+        for (uint64_t i = 0; i < n_nodes; i++) lk.add(ngp(nodes[i])->mu);
+        lk.lock();
         l->finalize();
         if (l->n_rows) nonnull(leaf_positions, "leaf_positions");
         return smb200::sbt_find(d, node_positions, reinterpret_cast<NG *const *>(nodes), min_n_below, n_nodes, leaf_positions, *l,

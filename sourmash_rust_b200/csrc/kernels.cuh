@@ -135,6 +135,9 @@ void launch_mark_common(const uint64_t *a, uint64_t na, const uint64_t *b, uint6
 // out[i - pre[i]] = vals[i] for every unflagged i (pre = exclusive scan of flags)
 void launch_compact_unflagged(const uint64_t *vals, const uint64_t *flags, const uint64_t *pre, uint64_t n,
                               uint64_t *out, cudaStream_t st);
+// out[pre[i]] = vals[i] for every flagged i with pre[i] < limit
+void launch_compact_flagged(const uint64_t *vals, const uint64_t *flags, const uint64_t *pre, uint64_t n, uint64_t limit,
+                            uint64_t *out, cudaStream_t st);
 
 // CSR collections of sorted sketches: hashes[offsets[i] .. offsets[i+1]).
 // Block rows [r0, r0+nr) of the row collection x cols [c0, c0+nc) of the column collection; writes

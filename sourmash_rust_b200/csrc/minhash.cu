@@ -17,10 +17,14 @@
 #include "minhash.hpp"
 
 #include <atomic>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "kernels.cuh"
 #include "md5.hpp"
@@ -76,7 +80,7 @@ KmerMinHash::KmerMinHash(uint32_t num_, uint32_t ksize_, bool is_protein_, uint6
 // kDeferTotalCap a sketch flushes on every call until others have drained.
 static std::atomic<size_t> g_seq_pending_total{0};
 
-KmerMinHash::~KmerMinHash() { g_seq_pending_total -= seq_pending_.size(); }
+KmerMinHash::~KmerMinHash() {}
 
 KmerMinHash *KmerMinHash::clone() {
     flush();
@@ -90,7 +94,8 @@ KmerMinHash *KmerMinHash::clone() {
         c->n_mins_ = h_mins_.size();
         c->n_abunds_ = h_abunds_.size();
     } else {
-        Context &ctx = Context::get();
+        Context &ctx = home();
+        ctx.adopt(c->owner_);
         c->d_mins_.reserve((n_mins_ + 1) * 8);
         c->d_abunds_.reserve((n_abunds_ + 1) * 8);
         if (n_mins_) SM_CUDA(cudaMemcpyAsync(c->d_mins_.p, d_mins_.p, n_mins_ * 8, cudaMemcpyDeviceToDevice, ctx.stream));
@@ -104,6 +109,13 @@ KmerMinHash *KmerMinHash::clone() {
     return c;
 }
 
+// This thread's context, after waiting for whatever another thread may have left queued on this sketch.
+Context &KmerMinHash::home() {
+    Context &c = Context::get();
+    c.adopt(owner_);
+    return c;
+}
+
 KmerMinHash::Mode KmerMinHash::mode() const {
     if (num == 0 && max_hash != 0) return MODE_SCALED;
     if (num != 0 && max_hash == 0) return MODE_NUM;
@@ -113,7 +125,7 @@ KmerMinHash::Mode KmerMinHash::mode() const {
 unsigned long long *KmerMinHash::hs(int i) {
     if (!d_hs_.p) {
         d_hs_.reserve(64);
-        SM_CUDA(cudaMemsetAsync(d_hs_.p, 0, 64, Context::get().stream));
+        SM_CUDA(cudaMemsetAsync(d_hs_.p, 0, 64, home().stream));
     }
     return d_hs_.as<unsigned long long>() + i;
 }
@@ -127,8 +139,8 @@ void KmerMinHash::check_compatible(const KmerMinHash &other) const {
 
 // ---- host <-> device mirrors ------------------------------------------------------------------
 void KmerMinHash::ensure_dev() {
+    Context &ctx = home();
     if (dev_valid_) return;
-    Context &ctx = Context::get();
     n_mins_ = h_mins_.size();
     n_abunds_ = h_abunds_.size();
     d_mins_.reserve((n_mins_ + 1) * 8);
@@ -142,7 +154,7 @@ void KmerMinHash::ensure_dev() {
 void KmerMinHash::ensure_host() {
     flush();
     if (host_valid_) return;
-    Context &ctx = Context::get();
+    Context &ctx = home();
     h_mins_.resize(n_mins_);
     h_abunds_.resize(n_abunds_);
     if (n_mins_) SM_CUDA(cudaMemcpyAsync(h_mins_.data(), d_mins_.p, n_mins_ * 8, cudaMemcpyDeviceToHost, ctx.stream));
@@ -155,7 +167,7 @@ void KmerMinHash::require_sorted(const char *what) {
     if (sorted_ == 1) return;
     ensure_dev();
     if (sorted_ == -1) {
-        Context &ctx = Context::get();
+        Context &ctx = home();
         set_u64(ctx.dsc(SC_FLAG), 0, ctx.stream);
         launch_check_sorted(d_mins_.as<uint64_t>(), n_mins_, ctx.dsc(SC_FLAG), ctx.stream);
         ctx.read_scalars();
@@ -184,9 +196,7 @@ void KmerMinHash::abunds_push(uint64_t v) {
 }
 void KmerMinHash::set_from_host(const uint64_t *mins_in, size_t n, const uint64_t *abunds_in, size_t n_abunds) {
     pending_.clear();
-    g_seq_pending_total -= seq_pending_.size();
-    seq_pending_.clear();
-    seq_offsets_.assign(1, 0);
+    seq_stage_.drop();
     n_cand_ = 0;
     h_mins_.assign(mins_in, mins_in + n);
     if (abunds_in) h_abunds_.assign(abunds_in, abunds_in + n_abunds); else h_abunds_.clear();
@@ -272,7 +282,7 @@ void KmerMinHash::replay(Context &ctx, const uint64_t *d_events, uint64_t n_even
 void KmerMinHash::flush_pending() {
     flush_sequences();
     if (pending_.empty()) return;
-    Context &ctx = Context::get();
+    Context &ctx = home();
     ensure_dev();
     const uint64_t n = pending_.size();
     ctx.misc[7].reserve((n + 1) * 8);
@@ -302,7 +312,7 @@ void KmerMinHash::flush_pending() {
 
 void KmerMinHash::flush() {
     flush_pending();
-    if (n_cand_) ingest(Context::get(), false);
+    if (n_cand_) ingest(home(), false);
     // Many sketches may be alive at once (10^4..10^6): scratch that dwarfs the sketch itself goes back
     // to the stream-ordered pool (the next batch gets it again in microseconds); scratch of the same
     // order as the state stays, so a sketch that is read between batches does not churn.
@@ -317,7 +327,7 @@ void KmerMinHash::flush() {
 // candidates -> state.  Returns false (nothing committed, candidates dropped) when the threshold
 // was an estimate and turned out too tight to fill a num sketch.
 // ---------------------------------------------------------------------------------------------
-bool KmerMinHash::ingest(Context &ctx, bool thr_is_estimate) {
+bool KmerMinHash::ingest(Context &ctx, bool thr_is_estimate, uint64_t thr_value) {
     const uint64_t nc = n_cand_;
     n_cand_ = 0;
     if (nc == 0) return !(mode() == MODE_NUM && thr_is_estimate && n_mins_ < num);  // nothing kept: estimate too tight?
@@ -409,7 +419,16 @@ bool KmerMinHash::ingest(Context &ctx, bool thr_is_estimate) {
                   ctx.dsc(SC_NUNIQ), idx2, ctx.scan_tmp.p, st);
     ctx.read_scalars();
     const uint64_t n_new = ctx.h_scalars[SC_NUNIQ];
-    if (m == MODE_NUM && thr_is_estimate && n_new < num) return false;
+    if (m == MODE_NUM && thr_is_estimate) {
+        // The kernel kept only the batch's hashes <= thr_value.  The union is the true bottom-num exactly when its
+        // num-th smallest element is <= thr_value: every hash that was filtered away is larger than that.  Counting
+        // distinct elements alone is not enough -- elements of the OLD state above the estimate count too, and
+        // would hide batch hashes between the estimate and them.
+        if (n_new < num) return false;
+        uint64_t kth[2];
+        ctx.fetch2(out_k.as<uint64_t>() + (num - 1), out_k.as<uint64_t>() + (num - 1), kth);
+        if (kth[0] > thr_value) return false;
+    }
     const uint64_t n_keep = (num != 0 && n_new > num) ? num : n_new;
     if (quirk && n_new >= num) {
         // lib.rs:206-208: once the sketch is full, re-occurrences of its largest element X are
@@ -431,67 +450,161 @@ bool KmerMinHash::ingest(Context &ctx, bool thr_is_estimate) {
 // add_sequence / add_sequences
 // ---------------------------------------------------------------------------------------------
 // ---- deferral of short sequences ---------------------------------------------------------------------------
-// A caller of the unmodified reference ABI feeds reads one call at a time (150 bp per call in BASELINE cfg2); going to
-// the device per call costs 45 us whatever the length.  A short sequence that cannot raise an error -- only
-// ACGT/acgt, or force == true (invalid windows are skipped, lib.rs:268-273) -- is therefore appended to a host-side
-// batch and the call returns; the batch goes through add_sequences (which keeps per-sequence order semantics) when it
-// reaches kDeferFlushBytes or when anything reads, combines or otherwise touches the sketch (flush_pending() is the
-// gate).  A sequence that CAN raise InvalidDNA takes the synchronous path below -- after the deferred ones, in call
-// order -- so the error, and the partial mutation before it, belong to the call that caused them.
+// A caller of the unmodified reference ABI feeds reads one call at a time (150 bp per call in BASELINE cfg2,
+// ffi.rs:55-70); going to the device per call costs 45 us whatever the length.  A short sequence that cannot raise
+// an error -- only ACGT/acgt, or force == true (invalid windows are skipped, lib.rs:268-273) -- is therefore
+// appended to a host-side stage and the call returns; the stage goes through add_sequences (which keeps
+// per-sequence order semantics) when it reaches kDeferFlushBytes or when anything reads, combines or otherwise
+// touches the sketch (flush_pending() is the gate).  A sequence that CAN raise InvalidDNA takes the synchronous
+// path below -- after the deferred ones, in call order -- so the error, and the partial mutation before it,
+// belong to the call that caused them.  Every staged sequence is known to be free of errors, so the stage is
+// sketched with force = true whatever flags its calls carried.
+//
+// The stage starts as ordinary host memory and grows geometrically; a sketch that keeps streaming (past
+// kStagePinAt bytes) moves to a page-locked buffer from a small process-wide pool, so that its flushes copy at
+// PCIe rate, and gives it back when a read (not fullness) empties the stage.
 bool g_defer_small_sequences = [] {
     const char *e = getenv("SMB200_DEFER_SEQ");
     return !(e && e[0] == '0');
 }();
 namespace {
 const size_t kDeferMaxLen = size_t(1) << 16, kDeferFlushBytes = size_t(8) << 20;
+const size_t kStageFull = kDeferFlushBytes + kDeferMaxLen;  // a stage never holds more than this
+const size_t kStagePinAt = size_t(256) << 10;
 const size_t kDeferTotalCap = size_t(1) << 30;  // see g_seq_pending_total
-bool all_acgt(const uint8_t *s, size_t n) {
-    static const struct Lut {
-        uint8_t ok[256];
-        Lut() {
-            memset(ok, 0, sizeof ok);
-            for (const char *c = "ACGTacgt"; *c; c++) ok[(uint8_t)*c] = 1;
+const size_t kAccountGranule = size_t(64) << 10;
+const int kPinnedBuffersMax = 16;  // 16 x 8 MiB page-locked at most, whatever the number of sketches
+
+std::mutex g_pin_mutex;
+std::vector<uint8_t *> g_pin_free;
+int g_pin_live = 0;
+uint8_t *pinned_acquire() {
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mutex);
+        if (!g_pin_free.empty()) {
+            uint8_t *p = g_pin_free.back();
+            g_pin_free.pop_back();
+            return p;
         }
-    } lut;
+        if (g_pin_live >= kPinnedBuffersMax) return nullptr;
+        g_pin_live++;
+    }
+    void *p = nullptr;
+    if (cudaMallocHost(&p, kStageFull) != cudaSuccess) {
+        (void)cudaGetLastError();
+        std::lock_guard<std::mutex> lk(g_pin_mutex);
+        g_pin_live--;
+        return nullptr;
+    }
+    return static_cast<uint8_t *>(p);
+}
+void pinned_release(uint8_t *p) {
+    std::lock_guard<std::mutex> lk(g_pin_mutex);
+    g_pin_free.push_back(p);
+}
+
+// every byte one of ACGTacgt?  (16 bytes per step: fold the case bit away, compare with the four letters)
+bool all_acgt(const uint8_t *s, size_t n) {
+    size_t i = 0;
+#if defined(__SSE2__)
+    const __m128i up = _mm_set1_epi8((char)0xDF), a = _mm_set1_epi8('A'), c = _mm_set1_epi8('C'), g = _mm_set1_epi8('G'),
+                  t = _mm_set1_epi8('T');
+    __m128i ok = _mm_set1_epi8((char)0xFF);
+    for (; i + 16 <= n; i += 16) {
+        const __m128i x = _mm_and_si128(_mm_loadu_si128(reinterpret_cast<const __m128i *>(s + i)), up);
+        ok = _mm_and_si128(ok, _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(x, a), _mm_cmpeq_epi8(x, c)),
+                                            _mm_or_si128(_mm_cmpeq_epi8(x, g), _mm_cmpeq_epi8(x, t))));
+    }
+    if (_mm_movemask_epi8(ok) != 0xFFFF) return false;
+#endif
     uint8_t all = 1;
-    for (size_t i = 0; i < n; i++) all &= lut.ok[s[i]];
+    for (; i < n; i++) {
+        const uint8_t x = s[i] & 0xDF;
+        all &= (uint8_t)((x == 'A') | (x == 'C') | (x == 'G') | (x == 'T'));
+    }
     return all != 0;
 }
 }  // namespace
 
-void KmerMinHash::flush_sequences() {
-    if (seq_offsets_.size() <= 1) return;
-    std::vector<uint8_t> bytes;
+SeqStage::~SeqStage() { drop(); }
+void SeqStage::drop() {
+    if (p) {
+        if (pinned) pinned_release(p); else free(p);
+    }
+    if (accounted) g_seq_pending_total -= accounted;
+    p = nullptr;
+    n = cap = accounted = 0;
+    pinned = false;
+    offsets.assign(1, 0);
+}
+// room for `len` more bytes (len <= kDeferMaxLen, n < kDeferFlushBytes on entry)
+void SeqStage::grow(size_t len) {
+    const size_t need = n + len;
+    if (need >= kStagePinAt && !pinned) {
+        if (uint8_t *q = pinned_acquire()) {
+            if (n) memcpy(q, p, n);
+            free(p);
+            p = q;
+            cap = kStageFull;
+            pinned = true;
+            return;
+        }
+    }
+    size_t want = cap ? cap * 2 : 4096;
+    while (want < need) want *= 2;
+    want = std::min(want, kStageFull);
+    uint8_t *q = static_cast<uint8_t *>(realloc(p, want));
+    if (!q) throw std::bad_alloc();
+    p = q;
+    cap = want;
+}
+
+void KmerMinHash::flush_sequences(bool stage_full) {
+    SeqStage &sg = seq_stage_;
+    if (sg.offsets.size() <= 1) return;
+    // taken out first: add_sequences comes back here through flush_pending()
     std::vector<uint64_t> offs(1, 0);
-    bytes.swap(seq_pending_);   // taken out first: add_sequences comes back here through flush_pending()
-    offs.swap(seq_offsets_);
-    g_seq_pending_total -= bytes.size();
+    offs.swap(sg.offsets);
+    const size_t n_bytes = sg.n;
+    sg.n = 0;
     SeqBatch b;
-    b.buf = bytes.data();
+    b.buf = sg.p;
     b.offsets = offs.data();
     b.n_seqs = offs.size() - 1;
-    b.n_bytes = bytes.size();
+    b.n_bytes = n_bytes;
     KmerMinHash *self = this;
-    add_sequences(&self, 1, b, seq_force_);
-    if (seq_pending_.empty() && seq_offsets_.size() == 1) {  // keep the (already touched) storage for the next batch
-        bytes.clear();
-        offs.assign(1, 0);
-        seq_pending_.swap(bytes);
-        seq_offsets_.swap(offs);
+    try {
+        add_sequences(&self, 1, b, true);
+    } catch (...) {
+        sg.drop();
+        throw;
     }
+    if (sg.accounted) {
+        g_seq_pending_total -= sg.accounted;
+        sg.accounted = 0;
+    }
+    offs.assign(1, 0);      // keep the (already touched) storage for the next batch
+    sg.offsets.swap(offs);
+    if (!stage_full && sg.pinned) sg.drop();  // the caller went on to something else: page-locked memory goes back
 }
 
 void KmerMinHash::add_sequence(const uint8_t *seq, size_t len, bool force) {
     if (g_defer_small_sequences && !is_protein && ksize != 0 && len <= kDeferMaxLen && (force || all_acgt(seq, len))) {
-        Context::get();  // no device: fail on this call, as the synchronous path would
+        if (!Context::peek()) Context::get();  // no device: fail on this call, as the synchronous path would
         if (len < ksize) return;  // lib.rs:258: shorter than k adds nothing
         if (!pending_.empty()) flush_pending();  // add_hash events came first
-        if (seq_offsets_.size() > 1 && seq_force_ != force) flush_sequences();
-        seq_force_ = force;
-        seq_pending_.insert(seq_pending_.end(), seq, seq + len);
-        seq_offsets_.push_back(seq_pending_.size());
-        const size_t total = (g_seq_pending_total += len);
-        if (seq_pending_.size() >= kDeferFlushBytes || total > kDeferTotalCap) flush_sequences();
+        SeqStage &sg = seq_stage_;
+        if (sg.n + len > sg.cap) sg.grow(len);
+        memcpy(sg.p + sg.n, seq, len);
+        sg.n += len;
+        sg.offsets.push_back(sg.n);
+        bool over_cap = false;
+        if (sg.n > sg.accounted) {  // the process-wide total is kept in granules: one atomic per 64 KiB, not per call
+            const size_t add = (sg.n - sg.accounted + kAccountGranule - 1) / kAccountGranule * kAccountGranule;
+            sg.accounted += add;
+            over_cap = (g_seq_pending_total += add) > kDeferTotalCap;
+        }
+        if (sg.n >= kDeferFlushBytes || over_cap) flush_sequences(true);
         return;
     }
     SeqBatch b;
@@ -527,6 +640,7 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
     if (batch.offsets == nullptr && batch.read_len != 0 && n != batch.n_seqs * (uint64_t)batch.read_len)
         throw_internal("fixed-length batch: n_bytes != n_seqs * read_len");
     Context &ctx = Context::get();
+    for (int i = 0; i < n_mhs; i++) ctx.adopt(mhs[i]->owner_);
     cudaStream_t st = ctx.stream;
 
     // ---- per-sketch preparation: order-dependent work first, thresholds, candidate space -------
@@ -758,14 +872,15 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
                         ctx.sort_tmp_v.reserve((ne + 1) * 8);
                         ctx.scan_tmp.reserve(radix_sort_scan_bytes(ne) + 256);
                         radix_sort_pairs(mh.d_cand_pos_.as<uint64_t>(), mh.d_cand_hash_.as<uint64_t>(), ne,
-                                         ctx.sort_tmp_k.as<uint64_t>(), ctx.sort_tmp_v.as<uint64_t>(), bit_length(n),
+                                         ctx.sort_tmp_k.as<uint64_t>(), ctx.sort_tmp_v.as<uint64_t>(),
+                                         bit_length(mh.is_protein ? protein_slots(n, batch.n_seqs) : n),  // positions: residue slots
                                          ctx.scan_tmp.p, ctx.scan_tmp.cap, st);
                         mh.replay(ctx, mh.d_cand_hash_.as<uint64_t>(), ne);
                     }
                     break;
                 }
                 // MODE_NUM
-                if (mh.ingest(ctx, p.estimate)) break;
+                if (mh.ingest(ctx, p.estimate, p.thr_fallback)) break;
                 // estimate kept too few distinct hashes: widen and go again
                 p.thr_fallback = (p.thr_fallback > (U64_MAX >> 6)) ? U64_MAX : (p.thr_fallback << 6);
                 if (p.thr_fallback == U64_MAX) p.estimate = false;
@@ -808,7 +923,7 @@ void KmerMinHash::merge(KmerMinHash &other) {
     flush(); other.flush();
     ensure_dev(); other.ensure_dev();
     require_sorted("merge"); other.require_sorted("merge");
-    Context &ctx = Context::get();
+    Context &ctx = home();
     cudaStream_t st = ctx.stream;
     const uint64_t na = n_mins_, nb = other.n_mins_;
     const bool sa = has_abunds_, ob = other.has_abunds_;
@@ -874,7 +989,7 @@ static void pair_stats(KmerMinHash &a, KmerMinHash &b, uint32_t num, uint64_t ou
     size_t na, nb;
     const uint64_t *da = a.device_mins(&na);
     const uint64_t *db = b.device_mins(&nb);
-    Context &ctx = Context::get();
+    Context &ctx = Context::get();  // both sketches were re-homed to this thread by device_mins()
     launch_pair_stats(da, na, db, nb, num, ctx.dsc(SC_PAIR0), ctx.stream);
     ctx.read_scalars();
     out[0] = ctx.h_scalars[SC_PAIR0];
@@ -898,6 +1013,32 @@ std::pair<uint64_t, uint64_t> KmerMinHash::intersection_size(KmerMinHash &other)
     uint64_t o[3];
     pair_stats(*this, other, num, o);  // uses self.num (lib.rs:473-480)
     return {o[1], o[2]};
+}
+
+// lib.rs:438-468: the hashes of A n B that are also in combined = bottom_num(A u B), and |combined|.  A common
+// element's rank in the union grows with its position, so those are simply the FIRST `common` elements of A n B,
+// with `common` and |combined| as intersection_size gives them.
+std::pair<std::vector<uint64_t>, uint64_t> KmerMinHash::intersection(KmerMinHash &other) {
+    const std::pair<uint64_t, uint64_t> cs = intersection_size(other);
+    std::vector<uint64_t> out(cs.first);
+    if (cs.first) {
+        size_t na, nb;
+        const uint64_t *da = device_mins(&na);
+        const uint64_t *db = other.device_mins(&nb);
+        Context &ctx = Context::get();
+        cudaStream_t st = ctx.stream;
+        ctx.misc[0].reserve((na + 1) * 8);
+        ctx.misc[1].reserve((na + 1) * 8);
+        ctx.misc[2].reserve((cs.first + 1) * 8);
+        ctx.scan_tmp.reserve(scan_tmp_bytes(na) + 256);
+        uint64_t *flags = ctx.misc[0].as<uint64_t>(), *pre = ctx.misc[1].as<uint64_t>(), *kept = ctx.misc[2].as<uint64_t>();
+        launch_mark_common(da, na, db, nb, flags, st);
+        scan_exclusive_u64(flags, pre, na, ctx.scan_tmp.p, st);
+        launch_compact_flagged(da, flags, pre, na, cs.first, kept, st);
+        SM_CUDA(cudaMemcpyAsync(out.data(), kept, cs.first * 8, cudaMemcpyDeviceToHost, st));
+        ctx.sync();
+    }
+    return {std::move(out), cs.second};
 }
 
 double KmerMinHash::compare(KmerMinHash &other) {

@@ -9,6 +9,7 @@
 #pragma once
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -35,6 +36,22 @@ struct SeqBatch {
     bool on_device = false;
 };
 
+// Host-side stage of deferred add_sequence calls (minhash.cu, "deferral of short sequences"): the bytes of the
+// sequences back to back (plain or page-locked memory) and their end offsets.
+struct SeqStage {
+    uint8_t *p = nullptr;
+    size_t n = 0, cap = 0;
+    size_t accounted = 0;  // bytes this stage has added to the process-wide total of deferred bytes
+    bool pinned = false;
+    std::vector<uint64_t> offsets{0};
+    SeqStage() = default;
+    SeqStage(const SeqStage &) = delete;
+    SeqStage &operator=(const SeqStage &) = delete;
+    ~SeqStage();
+    void grow(size_t len);
+    void drop();
+};
+
 class KmerMinHash {
   public:
     // fields of the reference struct (lib.rs:37-46); mins/abunds live on the device
@@ -43,6 +60,7 @@ class KmerMinHash {
     bool is_protein;
     uint64_t seed;
     uint64_t max_hash;
+    std::mutex mu;  // held by the C ABI around every call that is handed this sketch (ffi.cpp, "Locking")
 
     // KmerMinHash::new (lib.rs:142-174)
     KmerMinHash(uint32_t num, uint32_t ksize, bool is_protein, uint64_t seed, uint64_t max_hash,
@@ -63,6 +81,8 @@ class KmerMinHash {
     void add_many(const uint64_t *hashes, size_t n);                   // lib.rs:412-417
     uint64_t count_common(KmerMinHash &other);                         // lib.rs:428-436
     std::pair<uint64_t, uint64_t> intersection_size(KmerMinHash &other);  // lib.rs:470-499
+    // the common hashes themselves, ascending, and |combined| (lib.rs:438-468)
+    std::pair<std::vector<uint64_t>, uint64_t> intersection(KmerMinHash &other);
     double compare(KmerMinHash &other);                                // lib.rs:501-508
     // Leaf<Signature>::similarity / containment with this sketch as the node (index.rs:131-160)
     double similarity(KmerMinHash &other) { return compare(other); }
@@ -102,16 +122,17 @@ class KmerMinHash {
     // add_hash events not yet ingested (stream order)
     std::vector<uint64_t> pending_;
     // small sequences of add_sequence calls not yet sketched (host side, call order; see add_sequence).  At most
-    // one of pending_ / seq_pending_ is non-empty at any time, so call order between the two kinds is kept.
-    std::vector<uint8_t> seq_pending_;
-    std::vector<uint64_t> seq_offsets_{0};
-    bool seq_force_ = false;
-    void flush_sequences();
+    // one of pending_ / seq_stage_ is non-empty at any time, so call order between the two kinds is kept.
+    SeqStage seq_stage_;
+    void flush_sequences(bool stage_full = false);
     // survivors of the sketch kernel not yet merged into the state (scaled sketches merge lazily)
     DevBuf d_cand_hash_, d_cand_pos_;
     uint64_t n_cand_ = 0;
     // per-handle device scalars: [0] candidate counter, [1] threshold, [2] first failing window
     DevBuf d_hs_;
+
+    StreamOwner owner_;  // thread context that last queued device work on this sketch
+    Context &home();
 
     enum Mode { MODE_SCALED, MODE_NUM, MODE_REPLAY };
     Mode mode() const;
@@ -123,7 +144,7 @@ class KmerMinHash {
     void ensure_host();
     void require_sorted(const char *what);
     void reserve_candidates(Context &ctx, uint64_t extra);
-    bool ingest(Context &ctx, bool thr_is_estimate);
+    bool ingest(Context &ctx, bool thr_is_estimate, uint64_t thr_value = ~0ull);
     void replay(Context &ctx, const uint64_t *d_events, uint64_t n_events);
     void commit(DevBuf &mins, DevBuf &abunds, size_t n_mins, size_t n_abunds);
 };

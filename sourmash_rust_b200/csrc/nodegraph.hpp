@@ -38,6 +38,7 @@ class Nodegraph {
     double similarity(Nodegraph &other);
     double containment(Nodegraph &other);
 
+    std::mutex mu;  // as KmerMinHash::mu (every method ends synchronised, so no stream hand-over is needed)
     std::vector<NgTable> tables;
     uint64_t ksize = 0, occupied_bins = 0, unique_kmers = 0;
     uint64_t total_words = 0, total_bits = 0;

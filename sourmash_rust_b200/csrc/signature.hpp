@@ -23,6 +23,8 @@ struct Signature {
     std::vector<std::unique_ptr<KmerMinHash>> signatures;
     double version = 0.4;                        // default_version, lib.rs:575-577
 
+    std::mutex mu;  // as KmerMinHash::mu; covers the sketches the signature owns
+
     Signature() = default;
     Signature *clone_meta() const;  // everything but the sketches
     bool equals(Signature &other);  // lib.rs:663-675

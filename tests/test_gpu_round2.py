@@ -1,0 +1,208 @@
+"""Round-2 additions, each against the CPU oracle through the C ABI:
+  * KmerMinHash::intersection returning the hashes (lib.rs:438-468), the jaccard / containment C names;
+  * the estimate-threshold acceptance rule of num sketches that are only partly full;
+  * host threads: distinct handles driven concurrently (SURVEY 8(b) Threading, utils.rs:14-16), a handle
+    moving between threads, concurrent readers of one handle."""
+import threading
+
+import numpy as np
+import pytest
+
+import sourmash_rust_b200 as smb
+from oracle import oracle as orc
+from util import MAX_HASH_1000, golden, make_reads, mutate, random_dna
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(g, o, ctx=None):
+    assert np.array_equal(g.mins_np(), o.mins_np()), ctx
+    ga, oa = g.abunds_np(), o.abunds_np()
+    assert (ga is None) == (oa is None), ctx
+    if ga is not None:
+        assert np.array_equal(ga, oa), ctx
+
+
+def _pair(num, k, mx=0, ab=False):
+    return smb.KmerMinHash(num, k, False, 42, mx, ab), orc.KmerMinHash(num, k, False, 42, mx, ab)
+
+
+# ------------------------------------------------------------------------------------------------
+# intersection (hashes), jaccard, containment
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("num,mx", [(500, 0), (50, 0), (0, MAX_HASH_1000 * 10), (0, 0), (200, MAX_HASH_1000 * 100)])
+def test_intersection_hashes_and_names(num, mx):
+    g0 = random_dna(60_000, 31)
+    g1 = mutate(g0, 0.02, 32)
+    a, oa = _pair(num, 21, mx)
+    b, ob = _pair(num, 21, mx)
+    a.add_sequence(g0); oa.add_sequence(g0)
+    b.add_sequence(g1); ob.add_sequence(g1)
+    for x, y, ox, oy in ((a, b, oa, ob), (b, a, ob, oa), (a, a, oa, oa)):
+        hashes, size = x.intersection(y)
+        ohashes, osize = ox.intersection(oy)
+        assert size == osize and np.array_equal(hashes, ohashes)
+        assert (len(hashes), size) == ox.intersection_size(oy)
+        assert x.jaccard(y) == ox.compare(oy) == x.compare(y)
+        c, oc = x.containment(y), ox.containment(oy)
+        assert c == oc or (np.isnan(c) and np.isnan(oc))
+    e, oe = _pair(num, 21, mx)
+    hashes, size = a.intersection(e)
+    assert len(hashes) == 0 and size == oa.intersection(oe)[1]
+    assert np.isnan(e.containment(a)) and np.isnan(oe.containment(oa))   # 0/0 (index.rs:152-154)
+    other_k = smb.KmerMinHash(num, 31, False, 42, mx)
+    for f in (a.jaccard, a.containment, a.intersection):
+        with pytest.raises(smb.SourmashError) as err:
+            f(other_k)
+        assert err.value.code == 101
+
+
+def test_intersection_hashes_on_the_reference_fixture():  # the (common, size) matrix SURVEY 8(c) lists
+    g = golden("sbt_v5_leaves.json")
+    mhs, omhs = [], []
+    for p in sorted(g["leaves"], key=int):           # tree positions 6..12
+        sk = g["leaves"][p]["sketch"]
+        m = smb.KmerMinHash(sk["num"], sk["ksize"], False, sk["seed"], sk["max_hash"])
+        m.set_mins(sk["mins"])
+        mhs.append(m)
+        om = orc.KmerMinHash(sk["num"], sk["ksize"], False, sk["seed"], sk["max_hash"])
+        for h in sk["mins"]:
+            om.mins_push(h)
+        omhs.append(om)
+    assert np.array_equal(mhs[1].intersection(mhs[5])[0], omhs[1].intersection(omhs[5])[0])
+    hashes, size = mhs[1].intersection(mhs[5])       # leaves 7 and 11: Jaccard 178/500
+    assert (len(hashes), size) == (178, 500)
+    assert np.all(np.diff(hashes.astype(np.uint64)) > 0)
+    assert set(hashes.tolist()) <= (set(mhs[1].mins_np().tolist()) & set(mhs[5].mins_np().tolist()))
+    assert mhs[1].containment(mhs[5]) == 268 / 500
+
+
+# ------------------------------------------------------------------------------------------------
+# partly full num sketch + a long sequence whose windows are mostly unusable: the estimated kernel
+# threshold keeps too few hashes, and elements of the old state above it must not make that look like enough
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("abund", [False, True])
+@pytest.mark.parametrize("kind", ["mostly_n", "tandem"])
+def test_partly_full_num_sketch_then_low_yield_long_sequence(abund, kind):
+    num, k = 500, 21
+    g, o = _pair(num, k, 0, abund)
+    short = random_dna(260, 5)            # 240 hashes: fewer than num
+    g.add_sequence(short); o.add_sequence(short)
+    assert 0 < g.size() < num
+    if kind == "mostly_n":
+        body = bytearray(b"N" * 400_000)
+        island = random_dna(3000, 6)      # ~2 980 valid windows in 400 kbp
+        for i in range(0, 3000, 100):
+            pos = 1000 + i * 130
+            body[pos:pos + 100] = island[i:i + 100]
+        long_seq = bytes(body)
+    else:
+        long_seq = random_dna(700, 7) * 300   # 210 kbp, 700 distinct windows
+    g.add_sequence(long_seq, True); o.add_sequence(long_seq, True)
+    _same(g, o)
+    g.add_sequence(random_dna(50_000, 8)); o.add_sequence(random_dna(50_000, 8))
+    _same(g, o)
+
+
+# ------------------------------------------------------------------------------------------------
+# host threads
+# ------------------------------------------------------------------------------------------------
+def test_distinct_handles_on_distinct_threads():
+    n_threads = 8
+    genome = random_dna(400_000, 77)
+    reads = [make_reads(genome, 3000, 150, 100 + t) for t in range(n_threads)]
+    big = [random_dna(300_000, 200 + t) for t in range(n_threads)]
+    results, errors = [None] * n_threads, []
+
+    def work(t):
+        try:
+            a = smb.KmerMinHash(0, 31, False, 42, MAX_HASH_1000 * 10, True)
+            b = smb.KmerMinHash(300, 21, False, 42, 0, t % 2 == 0)
+            rd = reads[t]
+            for i in range(0, len(rd), 150):            # the reference's calling pattern: one read per call
+                a.add_sequence(rd[i:i + 150])
+            for i in range(0, len(rd) // 2, 150):
+                b.add_sequence(rd[i:i + 150])
+            a.add_sequence(big[t]); b.add_sequence(big[t])  # the synchronous path
+            a.add_reads(rd, len(rd) // 150, 150)            # and the batch entry point
+            sig = smb.Signature()
+            sig.push_mh(a)
+            results[t] = (a.mins_np(), a.abunds_np(), b.mins_np(), b.abunds_np(), a.compare(a), a.count_common(a),
+                          sig.save_json())
+        except Exception as e:  # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(n_threads)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for t in range(n_threads):
+        oa = orc.KmerMinHash(0, 31, False, 42, MAX_HASH_1000 * 10, True)
+        ob = orc.KmerMinHash(300, 21, False, 42, 0, t % 2 == 0)
+        rd = reads[t]
+        oa.add_reads(rd, len(rd) // 150, 150)
+        ob.add_reads(rd[:225_000], 1500, 150)              # the reads starting below len(rd) // 2
+        oa.add_sequence(big[t]); ob.add_sequence(big[t])
+        oa.add_reads(rd, len(rd) // 150, 150)
+        am, aa, bm, ba, cmp_, cc, js = results[t]
+        assert np.array_equal(am, oa.mins_np()) and np.array_equal(aa, oa.abunds_np()), t
+        assert np.array_equal(bm, ob.mins_np()), t
+        if ba is not None:
+            assert np.array_equal(ba, ob.abunds_np()), t
+        assert cmp_ == 1.0 and cc == oa.size()
+        assert js == orc.signature_json([oa])
+
+
+def test_a_handle_moves_between_threads():
+    g, o = _pair(0, 21, MAX_HASH_1000 * 20, True)
+    chunks = [random_dna(120_000, 300 + i) for i in range(6)]
+    coll_holder = {}
+
+    def step(i):
+        g.add_sequence(chunks[i])                       # device work queued from this thread ...
+        for j in range(0, 3000, 150):
+            g.add_sequence(chunks[i][j:j + 150])        # ... and deferred reads left pending on the handle
+        if i == 3:
+            coll_holder["c"] = smb.SketchCollection.from_sketches([g])
+
+    for i in range(6):
+        th = threading.Thread(target=step, args=(i,))
+        th.start(); th.join()
+        o.add_sequence(chunks[i])
+        for j in range(0, 3000, 150):
+            o.add_sequence(chunks[i][j:j + 150])
+        if i == 3:
+            snap = o.mins_np()
+    _same(g, o)                                         # read on the main thread
+    assert np.array_equal(coll_holder["c"].rows_np()[0], snap)
+    common, size, ratio = smb.compare_matrix(coll_holder["c"], coll_holder["c"])   # a collection built on a thread that is gone
+    assert common[0, 0] == size[0, 0] == len(snap) and ratio[0, 0] == 1.0
+
+
+def test_concurrent_readers_of_one_handle():
+    a, oa = _pair(0, 31, MAX_HASH_1000 * 10, False)
+    b, ob = _pair(0, 31, MAX_HASH_1000 * 10, False)
+    g0 = random_dna(500_000, 41)
+    g1 = mutate(g0, 0.01, 42)
+    a.add_sequence(g0); oa.add_sequence(g0)
+    for i in range(0, len(g1) - 1000, 1000):            # b is left with deferred reads: the first reader flushes them
+        b.add_sequence(g1[i:i + 1030]); ob.add_sequence(g1[i:i + 1030])
+    want = (oa.compare(ob), oa.count_common(ob), ob.size())
+    got, errors = [], []
+
+    def reader():
+        try:
+            for _ in range(20):
+                got.append((a.compare(b), a.count_common(b), b.size()))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=reader) for _ in range(6)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    assert len(got) == 120 and all(x == want for x in got)

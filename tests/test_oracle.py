@@ -97,6 +97,18 @@ def test_sbt_v5_matrices():  # SURVEY 8(c) golden integers
     assert orc.count_common_matrix(leaves, leaves).tolist() == V5_COMMON
 
 
+def test_sbt_v5_intersection_hashes():  # lib.rs:438-468 over the same fixture: as many hashes as `compare` counts
+    g = golden("sbt_v5_leaves.json")
+    leaves = [_load(g["leaves"][p]["sketch"]) for p in sorted(g["leaves"], key=int)]
+    for i in range(7):
+        for j in range(7):
+            hashes, size = leaves[i].intersection(leaves[j])
+            assert (len(hashes), size) == (V5_COMPARE[i][j], 500)
+            a, b = set(leaves[i].mins_np().tolist()), set(leaves[j].mins_np().tolist())
+            union_bottom = set(sorted(a | b)[:500])
+            assert hashes.tolist() == sorted(a & b & union_bottom)
+
+
 def test_md5sum_fixtures():  # lib.rs:72-77 rule reproduces the stored md5sum of all sorted fixtures
     g = golden("sbt_v5_leaves.json")
     for leaf in g["leaves"].values():
