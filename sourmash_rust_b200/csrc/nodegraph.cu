@@ -73,16 +73,23 @@ __global__ void ng_get_kernel(const uint64_t *hashes, uint64_t n, const uint32_t
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
     if ((threadIdx.x & 31) == 0 && bal) atomicAdd(matches, (unsigned long long)__popc(bal));
 }
-// word-wise over the zipped tables: mode 0 = a |= b, mode 1 = popcounts of a & b and a | b
+// word-wise over the zipped tables: mode 0 = a |= b (only the bits of b below a's table length), mode 1 = popcounts
+// of a & b and a | b, mode 2 = *out2 = min(*out2, first table in which b has a set bit at or beyond a's length)
 __global__ void ng_words_kernel(uint32_t *a, const NgTable *ta, const uint32_t *b, const NgTable *tb, uint32_t nt, int mode,
                                 unsigned long long *out2) {
     unsigned long long n_and = 0, n_or = 0;
     for (uint32_t t = 0; t < nt; t++) {
         const uint64_t wa = (ta[t].len + 31) / 32, wb = (tb[t].len + 31) / 32, lo = wa < wb ? wa : wb, hi = wa < wb ? wb : wa;
+        const uint64_t edge = ta[t].len / 32;                            // the word a's table ends in
+        const uint32_t below = (1u << (ta[t].len % 32)) - 1u;            // its bits that are inside a's table
         for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < hi; w += (uint64_t)gridDim.x * blockDim.x) {
             const uint32_t x = w < wa ? a[ta[t].word_off + w] : 0u, y = w < wb ? b[tb[t].word_off + w] : 0u;
             if (mode == 0) {
-                if (w < lo && y) a[ta[t].word_off + w] = x | y;
+                const uint32_t yi = w == edge ? (y & below) : y;
+                if (w < lo && yi) a[ta[t].word_off + w] = x | yi;
+            } else if (mode == 2) {
+                const uint32_t beyond = w < edge ? 0u : (w == edge ? (y & ~below) : y);
+                if (beyond) atomicMin(out2, (unsigned long long)t);
             } else {
                 n_and += __popc(x & y);
                 n_or += __popc(x | y);
@@ -301,19 +308,32 @@ uint64_t Nodegraph::get_many(const uint64_t *hashes, uint64_t n, uint8_t *presen
 }
 
 // Nodegraph::update, nodegraph.rs:63-91: tables are zipped; every set bit of `other` is `put` into self.
-// (occupied_bins is deliberately left alone there.)  The reference panics when a set bit of `other`
-// lies beyond self's table; here a longer table on the other side is refused outright.
+// (occupied_bins is deliberately left alone there.)  The reference panics at the first set bit of `other` that lies
+// beyond self's table (FixedBitSet::put) -- tables in order, bits ascending -- so a LONGER table on the other side is
+// fine as long as its tail is clear, and on a panic the earlier tables and the in-range bits of the failing one have
+// already been put.
 void Nodegraph::update(Nodegraph &other) {
     const uint32_t nt = (uint32_t)std::min(tables.size(), other.tables.size());
-    for (uint32_t t = 0; t < nt; t++)
-        if (other.tables[t].len > tables[t].len)
-            throw SourmashError(ERR_PANIC, "sourmash panicked: Nodegraph::update: put at index beyond the table (tables of different size)");
     if (!nt) return;
     Context &ctx = Context::get();
-    ng_words_kernel<<<(unsigned)std::min<uint64_t>(2048, (total_words + NG_THREADS - 1) / NG_THREADS + 1), NG_THREADS, 0, ctx.stream>>>(
-        d_words.as<uint32_t>(), dev_tables(), other.words(), other.dev_tables(), nt, 0, nullptr);
+    bool longer = false;
+    for (uint32_t t = 0; t < nt; t++) longer |= other.tables[t].len > tables[t].len;
+    uint32_t nt_ok = nt;
+    const unsigned grid = (unsigned)std::min<uint64_t>(2048, (std::max(total_words, other.total_words) + NG_THREADS - 1) / NG_THREADS + 1);
+    if (longer) {
+        ctx.set_scalar(SC_PAIR0, nt);
+        ng_words_kernel<<<grid, NG_THREADS, 0, ctx.stream>>>(d_words.as<uint32_t>(), dev_tables(), other.words(), other.dev_tables(), nt,
+                                                               2, ctx.dsc(SC_PAIR0));
+        SM_LAUNCHED();
+        ctx.read_scalars();
+        nt_ok = (uint32_t)ctx.h_scalars[SC_PAIR0];
+    }
+    ng_words_kernel<<<grid, NG_THREADS, 0, ctx.stream>>>(d_words.as<uint32_t>(), dev_tables(), other.words(), other.dev_tables(),
+                                                           std::min(nt, nt_ok + 1), 0, nullptr);
     SM_LAUNCHED();
     ctx.sync();
+    if (nt_ok < nt)
+        throw SourmashError(ERR_PANIC, "sourmash panicked: Nodegraph::update: put at index beyond the table (tables of different size)");
 }
 
 void Nodegraph::and_or_counts(Nodegraph &other, uint64_t *n_and, uint64_t *n_or) {

@@ -72,22 +72,25 @@ def allgather_sketch_state(mins, abunds=None, group=None, device=None):
     if world == 1:
         return [(mins, abunds)]
     device = device or torch.device("cpu")
-    n = torch.tensor([len(mins)], dtype=torch.int64, device=device)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    # the two lengths travel separately: after KmerMinHash::merge the abundance vector is deliberately NOT
+    # truncated with mins (lib.rs:395-400), so len(abunds) may exceed len(mins)
+    n_ab = 0 if abunds is None else len(abunds)
+    n = torch.tensor([len(mins), n_ab], dtype=torch.int64, device=device)
+    sizes = [torch.zeros(2, dtype=torch.int64, device=device) for _ in range(world)]
     dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
-    width = max(1, max(sizes))
+    sizes = [(int(s[0].item()), int(s[1].item())) for s in sizes]
+    width = max(1, max(max(s) for s in sizes))
     cols = 2 if abunds is not None else 1
     buf = torch.zeros((cols, width), dtype=torch.int64, device=device)
     buf[0, :len(mins)] = torch.from_numpy(np.ascontiguousarray(mins, dtype=np.uint64).view(np.int64)).to(device)
     if abunds is not None:
-        buf[1, :len(mins)] = torch.from_numpy(np.ascontiguousarray(abunds, dtype=np.uint64).view(np.int64)).to(device)
+        buf[1, :n_ab] = torch.from_numpy(np.ascontiguousarray(abunds, dtype=np.uint64).view(np.int64)).to(device)
     full = torch.empty((world, cols, width), dtype=torch.int64, device=device)
     dist.all_gather_into_tensor(full.view(world * cols, width), buf, group=group)
     out = []
     for r in range(world):
-        m = full[r, 0, :sizes[r]].cpu().numpy().view(np.uint64).copy()
-        a = full[r, 1, :sizes[r]].cpu().numpy().view(np.uint64).copy() if abunds is not None else None
+        m = full[r, 0, :sizes[r][0]].cpu().numpy().view(np.uint64).copy()
+        a = full[r, 1, :sizes[r][1]].cpu().numpy().view(np.uint64).copy() if abunds is not None else None
         out.append((m, a))
     return out
 

@@ -164,6 +164,19 @@ def test_update_similarity_containment_random():
     _same_state(ga, oa)
     with pytest.raises(smb.SourmashError):
         gs.update(ga)
+    with pytest.raises(orc.SourmashError):
+        os_.update(oa)
+    _same_state(gs, os_)          # what was put before the first out-of-range bit stays (the panic comes mid-loop)
+    # a LONGER table on the other side is fine while no set bit lies beyond self's table (FixedBitSet::put
+    # only panics on the bit it is handed)
+    gl, ol = smb.Nodegraph([2000, 2003], 31), orc.Nodegraph([2000, 2003], 31)
+    low = [int(h) for h in r[:400] if int(h) % 2000 < 500 and int(h) % 2003 < 600]
+    assert len(low) > 5
+    gl.count_many(low); [ol.count(h) for h in low]
+    g5, o5 = smb.Nodegraph([500, 600], 31), orc.Nodegraph([500, 600], 31)
+    g5.update(gl); o5.update(ol)
+    _same_state(g5, o5)
+    assert g5.n_occupied_bins() == 0 and sum(g5.get_many(low)[1]) > 0
 
 
 @pytest.mark.parametrize("d,n_leaves,num,mx", [(2, 13, 200, 0), (3, 20, 0, 2**64 // 2000), (2, 1, 50, 0), (4, 9, 64, 0)])
