@@ -162,6 +162,38 @@ void smgpu_fuse_multi_k(bool on);
 uint64_t smgpu_linear_find(SketchCollection *index, SketchCollection *queries, int32_t mode, double threshold,
                            uint64_t *hit_offsets, uint64_t *hits, uint64_t hits_cap);
 
+/* ---- multi-GPU: one process per GPU, the exchange steps over NCCL inside the library ------------------------
+ * The reference is single-process; what shards is algebra: partial sketches combine by
+ * KmerMinHash::merge, matrix rows are independent, a partitioned LinearIndex concatenates its parts' hits.
+ * NCCL is bound at run time (libnccl.so.2; the copy the host program already loaded, if any).  The 128-byte id
+ * is made on one rank and handed to the others by the host program's own channel (MPI_Bcast, a file, ...);
+ * every function below marked "collective" must be called by all ranks, in the same order. */
+#define SMGPU_COMM_ID_BYTES 128
+void smgpu_comm_unique_id(uint8_t *id128);                                   /* ncclGetUniqueId */
+void smgpu_comm_init(const uint8_t *id128, int32_t rank, int32_t world);     /* collective; after smgpu_set_device */
+void smgpu_comm_destroy(void);
+int32_t smgpu_comm_rank(void);
+int32_t smgpu_comm_world(void);
+int32_t smgpu_comm_nccl_version(void);
+/* collective: a new collection holding every rank's rows in rank order (rank 0's rows first).  Each rank has
+ * checked its own rows (sorted, distinct) when it built `local`; the gathered rows are not checked again. */
+SketchCollection *smgpu_collection_allgather(SketchCollection *local);
+/* collective: this rank's row block of the all-vs-all matrix -- rows of `local` x the rows of ALL ranks -- as
+ * smgpu_compare_matrix(local, 0, n_local, all, 0, n_all, ...) would give it, where all =
+ * smgpu_collection_allgather(local), which is also what is returned (caller frees).  The hash table of the join is
+ * built over the local rows while the other ranks' rows are in flight over NVLink. */
+SketchCollection *smgpu_compare_matrix_allgather(SketchCollection *local, int32_t mode, uint32_t *common /*[host|device]*/,
+                                                 uint32_t *size /*[host|device]*/, double *ratio /*[host|device]*/,
+                                                 uint64_t ld, bool out_on_device);
+/* collective: every rank holds a partial sketch of one sample (its share of the reads); afterwards every rank
+ * holds  s_0.merge(s_1).merge(s_2)...  (src/lib.rs:307-403: set union, abundances summed), s_r = rank r's sketch */
+void smgpu_comm_allmerge(KmerMinHash *ptr);
+/* collective: smgpu_linear_find over an index partitioned by rank (rank r's rows follow those of ranks < r; the
+ * query batch is the same on every rank).  Every rank receives the hit lists of the whole index, ids global, in
+ * insertion order (src/index/linear.rs:34-44). */
+uint64_t smgpu_linear_find_sharded(SketchCollection *index_part, SketchCollection *queries, int32_t mode, double threshold,
+                                   uint64_t *hit_offsets, uint64_t *hits, uint64_t hits_cap);
+
 /* ---- Nodegraph (khmer bloom filter) and SBT search: src/index/nodegraph.rs, src/index/sbt.rs ------ */
 /* The reference keeps these behind its Rust API only (no extern "C" in src/ffi.rs); the functions
  * below give them the same C-ABI shape as the rest of this header.  Bitsets live in HBM. */

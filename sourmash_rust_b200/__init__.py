@@ -108,6 +108,16 @@ EXTENSION_ABI = {
     "smgpu_scaffold_pairs": (u64, [vp, vp, vp]),
     "smgpu_compare_path": (None, [i32]),
     "smgpu_linear_find": (u64, [vp, vp, i32, C.c_double, vp, vp, u64]),
+    "smgpu_comm_unique_id": (None, [vp]),
+    "smgpu_comm_init": (None, [vp, i32, i32]),
+    "smgpu_comm_destroy": (None, []),
+    "smgpu_comm_rank": (i32, []),
+    "smgpu_comm_world": (i32, []),
+    "smgpu_comm_nccl_version": (i32, []),
+    "smgpu_collection_allgather": (vp, [vp]),
+    "smgpu_compare_matrix_allgather": (vp, [vp, i32, vp, vp, vp, u64, cb]),
+    "smgpu_comm_allmerge": (None, [vp]),
+    "smgpu_linear_find_sharded": (u64, [vp, vp, i32, C.c_double, vp, vp, u64]),
     "smgpu_nodegraph_new": (vp, [vp, usz, u64]),
     "smgpu_nodegraph_free": (None, [vp]),
     "smgpu_nodegraph_from_buffer": (vp, [C.c_char_p, usz]),
@@ -590,6 +600,64 @@ def linear_find(index, queries, mode, threshold, hits_cap=None):
     total = _call("smgpu_linear_find", index._p, queries._p, 1 if mode == "containment" else 0, float(threshold),
                   _vp(offs), _vp(hits), cap)
     assert total <= cap
+    return [hits[int(offs[q]):int(offs[q + 1])].tolist() for q in range(nq)]
+
+
+# ---- multi-GPU (one process per GPU; NCCL inside the library) -------------------------------------------------
+def comm_unique_id() -> bytes:
+    buf = np.zeros(128, dtype=np.uint8)
+    _call("smgpu_comm_unique_id", _vp(buf))
+    return buf.tobytes()
+
+
+def comm_init(id_bytes: bytes, rank: int, world: int):
+    assert len(id_bytes) == 128
+    _call("smgpu_comm_init", _vp(np.frombuffer(id_bytes, dtype=np.uint8).copy()), rank, world)
+
+
+def comm_init_from_torch():
+    """Convenience for hosts that already run torch.distributed: rank 0 makes the id, broadcast hands it round."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        t = torch.from_numpy(np.frombuffer(comm_unique_id(), dtype=np.uint8).copy())
+    t = t.to(dev)
+    dist.broadcast(t, 0)
+    comm_init(t.cpu().numpy().tobytes(), rank, world)
+
+
+def comm_destroy():
+    _call("smgpu_comm_destroy")
+
+
+def comm_rank_world():
+    return lib().smgpu_comm_rank(), lib().smgpu_comm_world()
+
+
+def collection_allgather(local):
+    return SketchCollection(_ptr=_call("smgpu_collection_allgather", local._p))
+
+
+def compare_matrix_allgather_device(local, mode, common_ptr, size_ptr, ratio_ptr, ld):
+    """This rank's row block (local rows x all ranks' rows) into device memory; returns the gathered collection."""
+    return SketchCollection(_ptr=_call("smgpu_compare_matrix_allgather", local._p, 1 if mode == "containment" else 0,
+                                       _vp(common_ptr), _vp(size_ptr), _vp(ratio_ptr), ld, True))
+
+
+def comm_allmerge(mh):
+    _call("smgpu_comm_allmerge", mh._p)
+
+
+def linear_find_sharded(index_part, queries, mode, threshold, hits_cap):
+    nq = len(queries)
+    offs = np.zeros(nq + 1, dtype=np.uint64)
+    hits = np.zeros(max(1, hits_cap), dtype=np.uint64)
+    total = _call("smgpu_linear_find_sharded", index_part._p, queries._p, 1 if mode == "containment" else 0, float(threshold),
+                  _vp(offs), _vp(hits), hits_cap)
+    assert total <= hits_cap
     return [hits[int(offs[q]):int(offs[q + 1])].tolist() for q in range(nq)]
 
 

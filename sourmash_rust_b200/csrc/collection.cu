@@ -122,11 +122,55 @@ static int bit_length64(uint64_t x) {
     return b;
 }
 
+// The hash-grouped postings of a block's build side (join.cu), living in the calling thread's scratch
+// (ctx.join[0,1,6,7], sort_tmp_k/v, misc[1]): built either inside compare_block_device or ahead of it --
+// compare_matrix_allgather builds the table of a rank's own rows while the other ranks' rows are in flight.
+void join_table_build(Context &ctx, JoinTable &jt, const uint64_t *bh, const uint64_t *bo, uint64_t b0, uint64_t n_build,
+                      uint64_t n_bp, bool with_filter) {
+    cudaStream_t st = ctx.stream;
+    int log2_t = 12;
+    while ((1ull << log2_t) < 2 * n_bp) log2_t++;
+    const uint64_t T = 1ull << log2_t;
+    ctx.join[0].reserve((T + 2) * 8);
+    ctx.join[1].reserve((T + 2) * 8);
+    ctx.sort_tmp_k.reserve((T + 2) * 8);
+    ctx.sort_tmp_v.reserve((T + 2) * 4);
+    ctx.join[6].reserve((n_bp + 1) * 4);
+    ctx.join[7].reserve((n_bp + 1) * 4);
+    ctx.scan_tmp.reserve(scan_tmp_bytes(T + 2) + 256);
+    // presence filter in front of the key table (16 bits per build-side hash, 2^20 .. 2^30 bits)
+    int log2_f = 20;
+    while (log2_f < 30 && (1ull << log2_f) < 16 * n_bp) log2_f++;
+    uint32_t *filter = nullptr;
+    if (with_filter) {
+        ctx.misc[1].reserve((1ull << log2_f) / 8 + 256);
+        filter = ctx.misc[1].as<uint32_t>();
+    }
+    unsigned long long *tkey = ctx.join[0].as<unsigned long long>(), *tcount = ctx.join[1].as<unsigned long long>();
+    uint64_t *toff = ctx.sort_tmp_k.as<uint64_t>();
+    uint32_t *tcursor = ctx.sort_tmp_v.as<uint32_t>(), *slot_of = ctx.join[6].as<uint32_t>(), *grows = ctx.join[7].as<uint32_t>();
+    {
+        ProfScope prof(PROF_SORT, st);
+        SM_CUDA(cudaMemsetAsync(tkey, 0xFF, (T + 1) * 8, st));
+        SM_CUDA(cudaMemsetAsync(tcount, 0, (T + 2) * 8, st));
+        SM_CUDA(cudaMemsetAsync(tcursor, 0, (T + 1) * 4, st));
+        if (filter) SM_CUDA(cudaMemsetAsync(filter, 0, (1ull << log2_f) / 8, st));
+        launch_group_insert(bh, bo, b0, n_build, tkey, tcount, slot_of, log2_t, filter, log2_f, st);
+        scan_exclusive_u64(reinterpret_cast<uint64_t *>(tcount), toff, T + 2, ctx.scan_tmp.p, st);
+        launch_group_fill(bo, b0, n_build, slot_of, toff, tcursor, grows, st);
+    }
+    jt.valid = true;
+    jt.ctx_id = ctx.id;
+    jt.bh = bh; jt.bo = bo; jt.b0 = b0; jt.n_build = n_build; jt.n_bp = n_bp;
+    jt.log2_t = log2_t; jt.log2_f = log2_f; jt.has_filter = filter != nullptr;
+}
+
 // One block of the matrix into DEVICE outputs.  Picks the sparse path (inverted index: only pairs
 // sharing a hash are walked) when the number of (pair, shared hash) incidences is small against
 // the dense work, else the dense tile kernel.  Same integers either way.
-static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t nr, SketchCollection &cols, uint64_t c0,
-                                 uint64_t nc, int mode, uint32_t *common, uint32_t *size, double *ratio, uint64_t ld) {
+void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t nr, SketchCollection &cols, uint64_t c0,
+                          uint64_t nc, int mode, uint32_t *common, uint32_t *size, double *ratio, uint64_t ld,
+                          const JoinTable *prebuilt) {
     Context &ctx = Context::get();
     cudaStream_t st = ctx.stream;
     const uint64_t *rh = rows.d_hashes.as<uint64_t>(), *ro = rows.d_offsets.as<uint64_t>();
@@ -166,42 +210,24 @@ static void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t n
     const bool probe = sparse && g_compare_path != 3 && n_bp > 0 && n_bp < (1ull << 31) &&
                        !(rows.probe_dense_preferred && !force_sparse);
     if (probe) {
-        int log2_t = 12;
-        while ((1ull << log2_t) < 2 * n_bp) log2_t++;
-        const uint64_t T = 1ull << log2_t;
-        ctx.join[0].reserve((T + 2) * 8);
-        ctx.join[1].reserve((T + 2) * 8);
-        ctx.sort_tmp_k.reserve((T + 2) * 8);
-        ctx.sort_tmp_v.reserve((T + 2) * 4);
-        ctx.join[6].reserve((n_bp + 1) * 4);
-        ctx.join[7].reserve((n_bp + 1) * 4);
+        // the table: handed in (built over exactly this block's build side, on this thread's scratch) or built here;
+        // with a presence filter in front of it when the probing side is a different, larger collection
+        JoinTable own;
+        const JoinTable *jt = prebuilt;
+        if (!(jt && jt->valid && jt->ctx_id == ctx.id && jt->bh == bh && jt->bo == bo && jt->b0 == b0 && jt->n_build == n_build &&
+              jt->n_bp == n_bp)) {
+            const uint64_t n_pp = build_cols ? n_rp : n_c;
+            join_table_build(ctx, own, bh, bo, b0, n_build, n_bp, (&rows != &cols) && n_pp >= 4 * n_bp);
+            jt = &own;
+        }
+        const int log2_t = jt->log2_t, log2_f = jt->log2_f;
         const uint64_t n_words = (nr * nc + 63) / 64;
-        ctx.scan_tmp.reserve(scan_tmp_bytes(std::max<uint64_t>(T + 2, n_words)) + 256);
-        // presence filter in front of the key table when the probing side is a different, larger collection
-        // (16 bits per build-side hash, 2^20 .. 2^30 bits)
-        const uint64_t n_pp = build_cols ? n_rp : n_c;
-        const bool use_filter = (&rows != &cols) && n_pp >= 4 * n_bp;
-        int log2_f = 20;
-        while (log2_f < 30 && (1ull << log2_f) < 16 * n_bp) log2_f++;
-        uint32_t *filter = nullptr;
-        if (use_filter) {
-            ctx.misc[1].reserve((1ull << log2_f) / 8 + 256);
-            filter = ctx.misc[1].as<uint32_t>();
-        }
-        unsigned long long *tkey = ctx.join[0].as<unsigned long long>(), *tcount = ctx.join[1].as<unsigned long long>();
-        uint64_t *toff = ctx.sort_tmp_k.as<uint64_t>();
-        uint32_t *tcursor = ctx.sort_tmp_v.as<uint32_t>(), *slot_of = ctx.join[6].as<uint32_t>(), *grows = ctx.join[7].as<uint32_t>();
-        {
-            ProfScope prof(PROF_SORT, st);
-            SM_CUDA(cudaMemsetAsync(tkey, 0xFF, (T + 1) * 8, st));
-            SM_CUDA(cudaMemsetAsync(tcount, 0, (T + 2) * 8, st));
-            SM_CUDA(cudaMemsetAsync(tcursor, 0, (T + 1) * 4, st));
-            SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_CNT), 0, 8, st));
-            if (use_filter) SM_CUDA(cudaMemsetAsync(filter, 0, (1ull << log2_f) / 8, st));
-            launch_group_insert(bh, bo, b0, n_build, tkey, tcount, slot_of, log2_t, filter, log2_f, st);
-            scan_exclusive_u64(reinterpret_cast<uint64_t *>(tcount), toff, T + 2, ctx.scan_tmp.p, st);
-            launch_group_fill(bo, b0, n_build, slot_of, toff, tcursor, grows, st);
-        }
+        ctx.scan_tmp.reserve(scan_tmp_bytes(n_words) + 256);
+        const uint32_t *filter = jt->has_filter ? ctx.misc[1].as<uint32_t>() : nullptr;
+        const unsigned long long *tkey = ctx.join[0].as<unsigned long long>();
+        const uint64_t *toff = ctx.sort_tmp_k.as<uint64_t>();
+        const uint32_t *grows = ctx.join[7].as<uint32_t>();
+        SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_CNT), 0, 8, st));
         ProfScope prof(PROF_COMPARE, st);
         if (mode == 1) {
             uint32_t *cmat = common;
@@ -425,6 +451,21 @@ uint64_t scaffold_pairs(SketchCollection &c, uint64_t *pairs_first, uint64_t *pa
 
 uint64_t linear_find(SketchCollection &index, SketchCollection &queries, int mode, double threshold, uint64_t *hit_offsets,
                      uint64_t *hits, uint64_t hits_cap) {
+    std::vector<std::vector<uint64_t>> per_query = linear_find_lists(index, queries, mode, threshold);
+    const uint64_t nq = per_query.size();
+    uint64_t total = 0;
+    for (uint64_t q = 0; q < nq; q++) {
+        if (hit_offsets) hit_offsets[q] = total;
+        for (uint64_t id : per_query[q]) {
+            if (hits && total < hits_cap) hits[total] = id;
+            total++;
+        }
+    }
+    if (hit_offsets) hit_offsets[nq] = total;
+    return total;
+}
+
+std::vector<std::vector<uint64_t>> linear_find_lists(SketchCollection &index, SketchCollection &queries, int mode, double threshold) {
     index.check_compatible(queries);
     index.finalize();
     queries.finalize();
@@ -491,16 +532,7 @@ uint64_t linear_find(SketchCollection &index, SketchCollection &queries, int mod
             for (uint64_t cell : cellbuf) per_query[cell / bn].push_back(b0 + cell % bn);  // ascending index id per query
         }
     }
-    uint64_t total = 0;
-    for (uint64_t q = 0; q < nq; q++) {
-        if (hit_offsets) hit_offsets[q] = total;
-        for (uint64_t id : per_query[q]) {
-            if (hits && total < hits_cap) hits[total] = id;
-            total++;
-        }
-    }
-    if (hit_offsets) hit_offsets[nq] = total;
-    return total;
+    return per_query;
 }
 
 }  // namespace smb200

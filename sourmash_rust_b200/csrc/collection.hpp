@@ -41,11 +41,29 @@ struct SketchCollection {
 SketchCollection *sketch_collection(const uint8_t *buf, const uint64_t *offsets, uint64_t n_seqs, uint32_t num, uint32_t ksize,
                                     uint64_t seed, uint64_t max_hash, bool on_device);
 
+// see collection.cu: join_table_build
+struct JoinTable {
+    bool valid = false;
+    uint64_t ctx_id = 0;
+    const uint64_t *bh = nullptr, *bo = nullptr;
+    uint64_t b0 = 0, n_build = 0, n_bp = 0;
+    int log2_t = 0, log2_f = 0;
+    bool has_filter = false;
+};
+void join_table_build(Context &ctx, JoinTable &jt, const uint64_t *bh, const uint64_t *bo, uint64_t b0, uint64_t n_build,
+                      uint64_t n_bp, bool with_filter);
+// one block of the matrix into device outputs (common / size / ratio may be null)
+void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t nr, SketchCollection &cols, uint64_t c0, uint64_t nc,
+                          int mode, uint32_t *common, uint32_t *size, double *ratio, uint64_t ld,
+                          const JoinTable *prebuilt = nullptr);
+
 extern int g_compare_path;
 // see include/sourmash_b200.h
 void compare_matrix(SketchCollection &rows, uint64_t r0, uint64_t nr, SketchCollection &cols, uint64_t c0, uint64_t nc,
                     int mode, uint32_t *common, uint32_t *size, double *ratio, uint64_t ld, bool out_on_device);
 uint64_t scaffold_pairs(SketchCollection &c, uint64_t *pairs_first, uint64_t *pairs_second);
+// per query: the index row ids that hit, ascending (= insertion order)
+std::vector<std::vector<uint64_t>> linear_find_lists(SketchCollection &index, SketchCollection &queries, int mode, double threshold);
 uint64_t linear_find(SketchCollection &index, SketchCollection &queries, int mode, double threshold,
                      uint64_t *hit_offsets, uint64_t *hits, uint64_t hits_cap);
 

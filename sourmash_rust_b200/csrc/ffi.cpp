@@ -16,6 +16,7 @@
 
 #include "../../include/sourmash_b200.h"
 #include "collection.hpp"
+#include "comm.hpp"
 #include "kernels.cuh"
 #include "minhash.hpp"
 #include "nodegraph.hpp"
@@ -670,6 +671,46 @@ uint64_t smgpu_linear_find(SketchCollection *index, SketchCollection *queries, i
     });
 }
 
+
+// ---- multi-GPU: one process per GPU, NCCL inside the library (comm.cu) -----------------------------------
+void smgpu_comm_unique_id(uint8_t *id128) {
+    landingpad_void([&]() { nonnull(id128, "id128"); smb200::comm_unique_id(id128); });
+}
+void smgpu_comm_init(const uint8_t *id128, int32_t rank, int32_t world) {
+    landingpad_void([&]() { nonnull(id128, "id128"); smb200::comm_init(id128, rank, world); });
+}
+void smgpu_comm_destroy(void) { landingpad_void([&]() { smb200::comm_destroy(); }); }
+int32_t smgpu_comm_rank(void) { return smb200::comm_rank(); }
+int32_t smgpu_comm_world(void) { return smb200::comm_world(); }
+int32_t smgpu_comm_nccl_version(void) { return landingpad<int32_t>([&]() { return (int32_t)smb200::comm_nccl_version(); }); }
+SketchCollection *smgpu_collection_allgather(SketchCollection *local) {
+    return landingpad<SketchCollection *>([&]() {
+        COLL *l = coll(local);
+        Guard lk(l->mu);
+        return reinterpret_cast<SketchCollection *>(smb200::collection_allgather(*l));
+    });
+}
+SketchCollection *smgpu_compare_matrix_allgather(SketchCollection *local, int32_t mode, uint32_t *common, uint32_t *size, double *ratio,
+                                                 uint64_t ld, bool out_on_device) {
+    return landingpad<SketchCollection *>([&]() {
+        if (mode != 0 && mode != 1) smb200::throw_internal("mode must be 0 (compare) or 1 (containment)");
+        COLL *l = coll(local);
+        Guard lk(l->mu);
+        return reinterpret_cast<SketchCollection *>(smb200::compare_matrix_allgather(*l, mode, common, size, ratio, ld, out_on_device));
+    });
+}
+void smgpu_comm_allmerge(KmerMinHash *ptr) {
+    landingpad_void([&]() { MH *m = mh(ptr); Guard lk(m->mu); smb200::comm_allmerge(*m); });
+}
+uint64_t smgpu_linear_find_sharded(SketchCollection *index_part, SketchCollection *queries, int32_t mode, double threshold,
+                                   uint64_t *hit_offsets, uint64_t *hits, uint64_t hits_cap) {
+    return landingpad<uint64_t>([&]() {
+        if (mode != 0 && mode != 1) smb200::throw_internal("mode must be 0 (similarity) or 1 (containment)");
+        COLL *ix = coll(index_part), *q = coll(queries);
+        Guard lk(ix->mu, q->mu);
+        return smb200::linear_find_sharded(*ix, *q, mode, threshold, hit_offsets, hits, hits_cap);
+    });
+}
 
 // ---- Nodegraph / SBT (src/index/nodegraph.rs, src/index/sbt.rs) ---------------------------------------
 Nodegraph *smgpu_nodegraph_new(const uint64_t *tablesizes, uintptr_t n_tables, uint64_t ksize) {

@@ -205,6 +205,26 @@ void KmerMinHash::set_from_host(const uint64_t *mins_in, size_t n, const uint64_
     sorted_ = std::is_sorted(h_mins_.begin(), h_mins_.end(), [](uint64_t a, uint64_t b) { return a <= b; }) ? 1 : 0;
     if (n < 2) sorted_ = 1;
 }
+void KmerMinHash::take_state_of(KmerMinHash &o) {
+    check_compatible(o);
+    o.flush();
+    Context &ctx = home();
+    ctx.adopt(o.owner_);
+    pending_.clear();
+    seq_stage_.drop();
+    n_cand_ = 0;
+    has_abunds_ = o.has_abunds_;
+    std::swap(d_mins_, o.d_mins_);
+    std::swap(d_abunds_, o.d_abunds_);
+    h_mins_.swap(o.h_mins_);
+    h_abunds_.swap(o.h_abunds_);
+    n_mins_ = o.n_mins_; n_abunds_ = o.n_abunds_;
+    host_valid_ = o.host_valid_; dev_valid_ = o.dev_valid_;
+    sorted_ = o.sorted_;
+    o.n_mins_ = o.n_abunds_ = 0;
+    o.h_mins_.clear(); o.h_abunds_.clear();
+    o.host_valid_ = true; o.dev_valid_ = false;
+}
 const uint64_t *KmerMinHash::device_mins(size_t *n) {
     flush(); ensure_dev();
     *n = n_mins_;

@@ -105,6 +105,7 @@ class KmerMinHash {
     const uint64_t *device_mins(size_t *n);
     const uint64_t *device_abunds(size_t *n);
     void set_from_host(const uint64_t *mins, size_t n, const uint64_t *abunds, size_t n_abunds);
+    void take_state_of(KmerMinHash &other);  // mins / abundances (and whether they are tracked) move over; parameters must match
     std::string md5sum();                    // lib.rs:72-77,86
     bool equals(KmerMinHash &other);         // derived PartialEq (lib.rs:37)
 
