@@ -31,15 +31,18 @@ READ_LEN = 150
 GENOME_LEN = 100_000_000
 SEED_GENOME = 0x5EED0010
 SEED_READS = 0x5EED0011
-# From the ncu --set full capture of the sketch kernels (profiles/sketch_r1_summary.md): executed SASS
-# thread-instructions per window (smsp__inst_executed x 32 / windows), DRAM bytes per window
-# (dram__bytes_read + dram__bytes_write) and pipe utilisations; used for the integer-issue roofline and
-# roofline.traffic.  "multi" = the fused k=21/31/51 kernel (three hashes per window start).
-INSTR_PER_WINDOW = {21: 141.0, 31: 151.9, 51: 233.9, "multi": 483.2}
-DRAM_BYTES_PER_WINDOW = {21: 1.028, 31: 1.028, 51: 1.042, "multi": 1.035}
-NCU_ALU_PIPE_PCT = {21: 66.6, 31: 64.6, 51: 68.3, "multi": 66.1}
-NCU_FMAHEAVY_PIPE_PCT = {21: 65.0, 31: 68.0, 51: 67.1, "multi": 71.9}
-NCU_ISSUE_PCT = {21: 74.6, 31: 74.4, 51: 72.6, "multi": 74.1}
+# Executed SASS thread-instructions per window, DRAM bytes per window and pipe utilisations of the sketch kernels come
+# from the ncu --set full captures, through profiles/kernel_constants.json (written by tests/manual/ncu_summary.py
+# --json from the same report the committed summary table is made of) -- not pasted here, so they cannot go stale
+# silently: a kernel the file does not list gets nulls.
+KERNEL_OF = {21: "sketch_kernel<21,0,0>", 31: "sketch_kernel<31,0,0>", 51: "sketch_kernel<51,0,0>", "multi": "sketch_kernel<21,31,51>"}
+
+
+def kernel_constants():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "kernel_constants.json")))
+    except (OSError, ValueError):
+        return {}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -171,6 +174,26 @@ def cpu_sketch_rate(reads, n_reads, threads):
     return n_reads * READ_LEN / dt / 1e9, dt, sk
 
 
+def oracle_sketches(rows, num):
+    from oracle import oracle as orc
+    out = []
+    for r in rows:
+        o = orc.KmerMinHash(num, 31)
+        o.add_many(r)
+        out.append(o)
+    return out
+
+
+def cpu_compare_rate(rows, threads):
+    """all-vs-all KmerMinHash::compare of the given num=500 rows on `threads` host threads (oracle/baseline_mt.c)"""
+    from oracle import oracle as orc
+    osk = oracle_sketches(rows, rows.shape[1])
+    t0 = time.perf_counter()
+    common, size = orc.compare_matrix(osk, osk, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return len(osk) ** 2 / dt, dt, common, size
+
+
 def run_reference(args):
     """--impl reference: same metric/config on the host cores.  The Rust crate cannot be built in
     this image (no cargo/rustc), so this is the C restatement of its algorithm (oracle/oracle.c),
@@ -193,6 +216,24 @@ def run_reference(args):
         cpu_sketch_rate(batches[s % 2], per_step, threads)
     dt = time.perf_counter() - t0
     value = args.steps * per_step * READ_LEN / dt / 1e9
+    # compare half of the metric: a bounded block of cfg3 (2 000 x 2 000 pairs), all host threads
+    compare = None
+    if not args.no_compare:
+        nb = min(args.compare_sketches, 2000)
+        rows = planted_sketches(nb, 500, 0x5EED0100)
+        c_steps = max(1, min(args.steps, 3))
+        cpu_compare_rate(rows[:256], threads)
+        t0 = time.perf_counter()
+        for _ in range(c_steps):
+            rate, _, _, _ = cpu_compare_rate(rows, threads)
+        dtc = (time.perf_counter() - t0) / c_steps
+        compare = {"impl": "reference", "metric": "Jaccard comparisons/s all-vs-all", "value": nb * nb / dtc, "unit": "pairs/s",
+                   "ms_per_step": dtc * 1e3, "steps": c_steps, "higher_is_better": True,
+                   "config": "cfg3 (num=500, k=31, 100-member clusters): bounded sample, the first %d sketches all-vs-all "
+                             "(%d ordered pairs per step), rows spread over %d threads (oracle/baseline_mt.c); time includes "
+                             "loading the rows into the CPU sketches" % (nb, nb * nb, threads),
+                   "cpu_baseline": {"value": nb * nb / dtc, "unit": "pairs/s", "cores": threads, "kind": "port",
+                                    "sample": "%d x %d block of cfg3" % (nb, nb)}}
     line = {
         "impl": "reference", "metric": "Gbp/s sketched", "value": value, "unit": "Gbp/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
@@ -205,6 +246,7 @@ def run_reference(args):
                                    "(oracle/baseline_mt.c)" % (args.steps, per_step, threads)},
         "e2e": {"value": value, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "compare": compare,
     }
     print(json.dumps(line), flush=True)
 
@@ -255,6 +297,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     _, sm_count = smb.device_info()
     lib_stream = torch.cuda.ExternalStream(smb.stream_handle(), device=dev)
+    host_threads = max(1, (os.cpu_count() or 1) // world)   # host threads this rank may use
 
     def barrier():
         if world > 1:
@@ -291,33 +334,66 @@ def run_ours(args):
         host_batches.append(h)
     torch.cuda.synchronize()
 
-    def new_sketches():
-        return [smb.KmerMinHash(0, k, False, 42, MAX_HASH_1000, True) for k in KSIZES]
+    def new_sketches(ks=KSIZES):
+        return [smb.KmerMinHash(0, k, False, 42, MAX_HASH_1000, True) for k in ks]
 
     clocks = ClockSampler(local_rank)
     clocks.start()
     windows = []
+    total_bases = sum_over_ranks(float(args.steps * n_bytes))
+
+    def timed_device(ks):
+        """K steps of the batch entry point over device-resident batches; device ms (max over ranks), launches, sketches"""
+        mhs = new_sketches(ks)
+        for w in range(args.warmup):
+            smb.add_reads(mhs, dev_batches[w % n_batches].data_ptr(), R, READ_LEN, force=False, on_device=True)
+        for m in mhs:
+            m.size()
+        mhs = new_sketches(ks)
+        barrier()
+        launches0 = smb.launch_count()
+        t_wall0 = time.time()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(lib_stream)
+        for s in range(args.steps):
+            smb.add_reads(mhs, dev_batches[s % n_batches].data_ptr(), R, READ_LEN, force=False, on_device=True)
+        sizes = [m.size() for m in mhs]  # folds the last candidates into the sorted sketches
+        ev1.record(lib_stream)
+        barrier()
+        windows.append((t_wall0, time.time()))
+        return max_over_ranks(ev0.elapsed_time(ev1)), smb.launch_count() - launches0, mhs, sizes
+
+    def timed_e2e(ks):
+        """the same K steps from pinned HOST batches through the C ABI, sketches copied back to the host every step"""
+        out_m = [torch.zeros(1 << 22, dtype=torch.int64, pin_memory=True) for _ in ks]
+        out_a = [torch.zeros(1 << 22, dtype=torch.int64, pin_memory=True) for _ in ks]
+
+        def step(mhs, s):
+            smb.add_reads(mhs, host_batches[s % n_batches].data_ptr(), R, READ_LEN, force=False, on_device=False)
+            d2h = 0
+            for i, m in enumerate(mhs):
+                n = smb._call("kmerminhash_copy_mins", m._p, smb._vp(out_m[i].data_ptr()), smb._vp(out_a[i].data_ptr()), False)
+                d2h += 16 * n
+            return d2h
+
+        warm = new_sketches(ks)
+        for w in range(min(args.warmup, 2)):
+            step(warm, w)
+        mhs = new_sketches(ks)
+        barrier()
+        t_wall0 = time.time()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(lib_stream)
+        d2h_total = 0
+        for s in range(args.steps):
+            d2h_total += step(mhs, s)
+        e1.record(lib_stream)
+        barrier()
+        windows.append((t_wall0, time.time()))
+        return max_over_ranks(e0.elapsed_time(e1)), d2h_total, mhs
 
     # ---- device-resident path: `value` --------------------------------------------------------------
-    mhs = new_sketches()
-    for w in range(args.warmup):
-        smb.add_reads(mhs, dev_batches[w % n_batches].data_ptr(), R, READ_LEN, force=False, on_device=True)
-    for m in mhs:
-        m.size()
-    mhs = new_sketches()
-    barrier()
-    launches0 = smb.launch_count()
-    t_wall0 = time.time()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(lib_stream)
-    for s in range(args.steps):
-        smb.add_reads(mhs, dev_batches[s % n_batches].data_ptr(), R, READ_LEN, force=False, on_device=True)
-    sizes = [m.size() for m in mhs]  # folds the last candidates into the sorted sketches
-    ev1.record(lib_stream)
-    barrier()
-    windows.append((t_wall0, time.time()))
-    ms_dev = max_over_ranks(ev0.elapsed_time(ev1))
-    launches = smb.launch_count() - launches0
+    ms_dev, launches, mhs, sizes = timed_device(KSIZES)
     # the same K steps once more with per-kernel CUDA events: the three kernels of a step then run
     # one after the other on the library's stream (in the pass above they overlap at their edges on
     # three streams), so that each duration is the kernel's own -- the roofline's denominator
@@ -341,74 +417,103 @@ def run_ours(args):
         del mhs_k
     smb.fuse_multi_k(True)
     smb.profile_enable(False)
-    total_bases = sum_over_ranks(float(args.steps * n_bytes))
     value = total_bases / (ms_dev * 1e-3) / 1e9
     md5_dev = [m.md5sum() for m in mhs]
 
     # ---- end-to-end path: pinned host buffers in, sketches read back every step ------------------------
-    mhs2 = new_sketches()
-    # pinned host buffers for the sketches read back every step
-    out_m = [torch.zeros(1 << 22, dtype=torch.int64, pin_memory=True) for _ in KSIZES]
-    out_a = [torch.zeros(1 << 22, dtype=torch.int64, pin_memory=True) for _ in KSIZES]
-
-    def e2e_step(s):
-        smb.add_reads(mhs2, host_batches[s % n_batches].data_ptr(), R, READ_LEN, force=False, on_device=False)
-        d2h = 0
-        for i, m in enumerate(mhs2):
-            n = smb._call("kmerminhash_copy_mins", m._p, smb._vp(out_m[i].data_ptr()), smb._vp(out_a[i].data_ptr()), False)
-            d2h += 16 * n
-        return d2h
-
-    warm = new_sketches()
-    mhs2, keep = warm, mhs2
-    for w in range(min(args.warmup, 2)):
-        e2e_step(w)
-    mhs2 = keep
-    barrier()
-    t_wall0 = time.time()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(lib_stream)
-    d2h_total = 0
-    for s in range(args.steps):
-        d2h_total += e2e_step(s)
-    e1.record(lib_stream)
-    barrier()
-    windows.append((t_wall0, time.time()))
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    ms_e2e, d2h_total, mhs2 = timed_e2e(KSIZES)
     e2e_value = total_bases / (ms_e2e * 1e-3) / 1e9
     assert [m.md5sum() for m in mhs2] == md5_dev, "device-resident and host-fed paths disagree"
+    abunds_dev = [m.abunds_np() for m in mhs]
 
-    # ---- roofline of the dominant kernel (k=51 is the heaviest of the three; k=31 is the metric's k) ---
+    # ---- the BASELINE metric's literal configuration: ONE sketch, k=31, scaled=1000 -------------------------
+    ms_k31, launches_k31, mhs_k31, sizes_k31 = timed_device((31,))
+    ms_k31_e2e, d2h_k31, mhs_k31_h = timed_e2e((31,))
+    assert mhs_k31_h[0].md5sum() == mhs_k31[0].md5sum() == md5_dev[1]
+    k31 = {"metric": "Gbp/s sketched (k=31, scaled=1000)", "value": total_bases / (ms_k31 * 1e-3) / 1e9, "unit": "Gbp/s",
+           "ms_per_step": ms_k31 / args.steps, "gpu_launches": launches_k31,
+           "e2e": {"value": total_bases / (ms_k31_e2e * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": ms_k31_e2e / args.steps,
+                   "h2d_bytes_per_step": n_bytes, "d2h_bytes_per_step": d2h_k31 // max(1, args.steps)},
+           "config": "one KmerMinHash(num=0, k=31, max_hash=18446744073709552, track_abundance) through kmerminhash_add_reads, "
+                     "same read batches as the multi-k run"}
+
+    # ---- what the host side can deliver at most: bare pinned-host -> device copies, all ranks at once ---------------------
+    h2d_dst = torch.empty(n_bytes, dtype=torch.uint8, device=dev)
+    cp_stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(cp_stream):
+        h2d_dst.copy_(host_batches[0], non_blocking=True)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 4
+    with torch.cuda.stream(cp_stream):
+        c0.record(cp_stream)
+        for i in range(reps):
+            h2d_dst.copy_(host_batches[i % n_batches], non_blocking=True)
+        c1.record(cp_stream)
+    barrier()
+    h2d_gbs = n_bytes * reps / (max_over_ranks(c0.elapsed_time(c1)) * 1e-3) / 1e9   # per GPU, slowest rank
+    del h2d_dst
+
+    # ---- the reference's own calling pattern: one kmerminhash_add_sequence call per read and per k-size ---------
+    # (src/ffi.rs:55-70; a C loop over the unmodified symbol, sourmash_rust_b200/host/feed_reads.c).  Reads as
+    # NUL-terminated strings in host memory; T host threads, each feeding its own three sketches with its share of
+    # the batch; the timed region ends when every sketch has been flushed; the threads' sketches are then merged.
+    percall = None
+    if not args.no_percall:
+        T = max(1, min(args.percall_threads or 4, host_threads))
+        z = np.zeros((R, READ_LEN + 1), dtype=np.uint8)
+        z[:, :READ_LEN] = host_batches[0].numpy().reshape(R, READ_LEN)
+        pc_steps = max(1, min(args.steps, 3))
+        warm_reads = min(R // T // 8, 50_000)
+        secs, groups = 0.0, None
+        barrier()
+        t_wall0 = time.time()
+        for s in range(pc_steps):
+            groups = [new_sketches() for _ in range(T)]
+            secs += smb.feed_reads(groups, z, R, READ_LEN + 1, force=False, warm_reads=warm_reads)
+        windows.append((t_wall0, time.time()))
+        timed_reads = R - warm_reads * T
+        secs = max_over_ranks(secs)
+        # parity: thread sketches merged == the batch entry point over the same reads
+        merged = groups[0]
+        for g in groups[1:]:
+            for a, b in zip(merged, g):
+                a.merge(b)
+        chk = new_sketches()
+        smb.add_reads(chk, host_batches[0].data_ptr(), R, READ_LEN, force=False, on_device=False)
+        for a, b in zip(merged, chk):
+            assert a.md5sum() == b.md5sum() and np.array_equal(a.abunds_np(), b.abunds_np()), "per-call path differs from the batch path"
+        percall = {"value": sum_over_ranks(float(pc_steps * timed_reads * READ_LEN)) / secs / 1e9, "unit": "Gbp/s",
+                   "entry_point": "kmerminhash_add_sequence (include/sourmash.h), one call per read and per k-size",
+                   "host_threads_per_gpu": T, "calls_per_step": timed_reads * len(KSIZES),
+                   "ns_per_call_per_thread": secs / (pc_steps * timed_reads * len(KSIZES)) * T * 1e9,
+                   "ms_per_step": secs / pc_steps * 1e3, "h2d_bytes_per_step": timed_reads * READ_LEN * len(KSIZES),
+                   "parity_with_batch_path": True,
+                   "note": "host-bound: each call validates and stages its read on the host (deferred, flushed in 8 MiB "
+                           "batches per sketch); round 1 went to the device on every call: 45 us per call = 0.003 Gbp/s"}
+        del z, groups, merged, chk
+
+    # ---- roofline of the dominant kernel (the fused k=21/31/51 launch; k=31 is the metric's k) ---
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except (OSError, ValueError):
         pass
-    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+    consts = kernel_constants()
     k31_ms, k31_n = kern["sketch_k31"]
     km_ms, km_n = kern["sketch_multi"]
-    roof = None
     per_k = {}
     for k, kind in zip(KSIZES + ("multi",), ("sketch_k21", "sketch_k31", "sketch_k51", "sketch_multi")):
         ms, n = kern[kind]
         if n:
             per_k["k%s" % k] = {"launches": n, "avg_ms": ms / n, "gbp_s": args.steps * n_bytes / (ms * 1e-3) / 1e9}
-    if km_n:
-        # the dominant kernel of the timed step is the fused launch: it reads every base once
-        bytes_per_launch = args.steps * n_bytes / km_n  # 1 B (one ASCII base) per window start, SURVEY 8(d)
-        achieved = bytes_per_launch / (km_ms / km_n * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "sketch_kernel<21,31,51>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": DRAM_BYTES_PER_WINDOW["multi"] * bytes_per_launch,
-                "traffic_source": "ncu dram__bytes_read+write per window (profiles/sketch_r1_summary.md) x windows per launch",
-                "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": km_ms / km_n,
-                "duration_source": "CUDA events around each launch on the library's stream, separate pass of the same K steps",
-                "note": "HBM is not the binding resource of this kernel (three MurmurHash3 per byte read): see int_pipe"}
-    int_pipe = None
-    # ---- all-vs-all compare (cfg3), rows sharded by rank, CSR all-gathered over NCCL -------------------
+
+    # ---- all-vs-all compare (cfg3), rows sharded by rank, CSR all-gathered over NCCL inside the library -------------
     compare = None
     if not args.no_compare:
-        compare = bench_compare(args, smb, torch, dist, dev, rank, world, barrier, max_over_ranks, lib_stream, windows)
+        compare = bench_compare(args, smb, torch, dist, dev, rank, world, barrier, max_over_ranks, lib_stream, windows,
+                                host_threads, hbm_peak, peak_src)
 
     clocks.stop()
 
@@ -432,31 +537,46 @@ def run_ours(args):
         cpu["parity_checked"] = True
 
     clk = clocks.summary(windows)
+    roof = roof_hbm = None
     if rank == 0 and km_n:
-        # integer roofline of the fused kernel, two ways: (1) issue slots -- 4 warp instructions per clock
-        # per SM at the SM clock seen during the run; (2) the hash-only ceiling -- MurmurHash3 of
-        # register-resident k-mers and nothing else, measured live (smgpu_int_peak modes 10-12)
+        # The binding roof of the sketch kernels is integer issue, not HBM (three MurmurHash3 per byte read).  Two
+        # readings: (1) issue slots -- 4 warp instructions per clock per SM at the SM clock seen during the run, with the
+        # executed instruction count per window from the ncu capture; (2) the hash-only ceiling -- MurmurHash3 of
+        # register-resident k-mers and nothing else, measured live (smgpu_int_peak modes 10-12).
+        kc = consts.get(KERNEL_OF["multi"], {})
+        kc31 = consts.get(KERNEL_OF[31], {})
         mhz = clk.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
         issue_peak = 4 * 32 * sm_count * mhz * 1e6
-        inst_rate = INSTR_PER_WINDOW["multi"] * (args.steps * n_bytes) / (km_ms * 1e-3)
+        windows_per_launch = args.steps * n_bytes / km_n
+        launch_s = km_ms / km_n * 1e-3
         hash_rate = {k: smb.int_peak(mode, 256, sm_count * 8) for mode, k in ((10, 21), (11, 31), (12, 51))}
         ceiling = 1.0 / sum(1.0 / hash_rate[k] for k in KSIZES)  # windows/s if the three hashes were all there is
-        achieved_w = (args.steps * n_bytes) / (km_ms * 1e-3)
-        int_pipe = {"kernel": "sketch_kernel<21,31,51>", "achieved_tinstr_s": inst_rate / 1e12, "peak_tinstr_s": issue_peak / 1e12,
-                    "frac": inst_rate / issue_peak, "instr_per_window": INSTR_PER_WINDOW["multi"],
-                    "peak_source": "4 warp-instr/clk/SM x 32 lanes x %d SMs x %.0f MHz (sampled during the run)" % (sm_count, mhz),
-                    "ncu_issue_slots_pct": NCU_ISSUE_PCT["multi"], "ncu_alu_pipe_pct": NCU_ALU_PIPE_PCT["multi"],
-                    "ncu_fmaheavy_pipe_pct": NCU_FMAHEAVY_PIPE_PCT["multi"],
-                    "hash_only_ceiling": {"g_hashes_s": {"k%d" % k: hash_rate[k] / 1e9 for k in KSIZES},
-                                          "fused_gbp_s": ceiling / 1e9, "frac": achieved_w / ceiling,
-                                          "how": "MurmurHash3 x64_128 of register-resident k-mers, no staging / strand "
-                                                 "choice / shared memory (hash_peak_kernel), measured in this run"},
-                    "k31_kernel": {"gbp_s": args.steps * n_bytes / (k31_ms * 1e-3) / 1e9 if k31_n else None,
-                                   "instr_per_window": INSTR_PER_WINDOW[31],
-                                   "issue_frac": (INSTR_PER_WINDOW[31] * (args.steps * n_bytes) / (k31_ms * 1e-3) / issue_peak) if k31_n else None,
-                                   "hash_only_frac": (args.steps * n_bytes / (k31_ms * 1e-3) / hash_rate[31]) if k31_n else None},
-                    "note": "binding resource of the sketch kernels: ALU + FMA-heavy (IMAD) pipes; instruction counts and "
-                            "pipe utilisations from the ncu capture in profiles/"}
+        achieved_w = windows_per_launch / launch_s
+        ipw = kc.get("instr_per_unit")
+        roof = {"bound": "int_issue", "kernel": KERNEL_OF["multi"],
+                "achieved": ipw * achieved_w / 1e12 if ipw else None, "peak": issue_peak / 1e12, "unit": "Tinstr/s",
+                "frac": ipw * achieved_w / issue_peak if ipw else None,
+                "traffic": kc.get("dram_bytes_per_unit") * windows_per_launch if kc.get("dram_bytes_per_unit") else None,
+                "instr_per_window": ipw, "windows_per_launch": windows_per_launch, "avg_launch_ms": km_ms / km_n,
+                "peak_source": "4 warp-instr/clk/SM x 32 lanes x %d SMs x %.0f MHz (SM clock sampled during the run)" % (sm_count, mhz),
+                "constants_source": kc.get("source"),
+                "ncu": {"issue_slots_pct": kc.get("issue_pct"), "alu_pipe_pct": kc.get("alu_pct"), "fmaheavy_pipe_pct": kc.get("fmaheavy_pct")},
+                "duration_source": "CUDA events around each launch on the library's stream, separate pass of the same K steps",
+                "hash_only_ceiling": {"g_hashes_s": {"k%d" % k: hash_rate[k] / 1e9 for k in KSIZES},
+                                      "fused_gbp_s": ceiling / 1e9, "frac": achieved_w / ceiling,
+                                      "how": "MurmurHash3 x64_128 of register-resident k-mers, no staging / strand "
+                                             "choice / shared memory (hash_peak_kernel), measured in this run"},
+                "k31_kernel": {"gbp_s": args.steps * n_bytes / (k31_ms * 1e-3) / 1e9 if k31_n else None,
+                               "instr_per_window": kc31.get("instr_per_unit"),
+                               "issue_frac": (kc31["instr_per_unit"] * (args.steps * n_bytes) / (k31_ms * 1e-3) / issue_peak)
+                               if k31_n and kc31.get("instr_per_unit") else None,
+                               "hash_only_frac": (args.steps * n_bytes / (k31_ms * 1e-3) / hash_rate[31]) if k31_n else None},
+                "note": "binding resource of the sketch kernels: ALU + FMA-heavy (IMAD) pipes; HBM side in roofline_hbm"}
+        achieved_gbs = windows_per_launch / launch_s / 1e9   # 1 B (one ASCII base) per window start, SURVEY 8(d)
+        roof_hbm = {"bound": "hbm", "kernel": KERNEL_OF["multi"], "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved_gbs / hbm_peak, "traffic": roof["traffic"], "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": windows_per_launch,
+                    "note": "not the binding resource: the kernel reads each base once (ncu DRAM bytes per window in `traffic`)"}
     if rank == 0:
         line = {
             "metric": "Gbp/s sketched", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
@@ -468,9 +588,17 @@ def run_ours(args):
                        "l2": "inputs (%d MB per step) larger than the 126 MB L2; %d distinct batches cycled" % (n_bytes >> 20, n_batches),
                        "sketch_sizes": sizes, "host_numa_node": numa},
             "e2e": {"value": e2e_value, "unit": "Gbp/s", "h2d_bytes_per_step": n_bytes,
-                    "d2h_bytes_per_step": d2h_total // max(1, args.steps), "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": d2h_total // max(1, args.steps), "ms_per_step": ms_e2e / args.steps,
+                    "entry_point": "kmerminhash_add_reads (batch extension, include/sourmash_b200.h), pinned host buffers",
+                    "h2d_ceiling_gbs": h2d_gbs,
+                    "h2d_ceiling_note": "bare cudaMemcpyAsync of the same pinned batches, all ranks at once, per GPU (slowest "
+                                        "rank): what the host side can deliver; 1 B per base, so this is also the e2e "
+                                        "ceiling in Gbp/s per GPU",
+                    "frac_of_h2d_ceiling": (e2e_value / world) / h2d_gbs},
+            "e2e_per_call": percall,
+            "k31_scaled1000": k31,
             "gpu_launches": launches,
-            "roofline": roof, "int_pipe": int_pipe, "sketch_kernels": per_k,
+            "roofline": roof, "roofline_hbm": roof_hbm, "sketch_kernels": per_k,
             "cpu_baseline": cpu,
             "clocks": clk,
             "compare": compare,
@@ -480,32 +608,36 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def bench_compare(args, smb, torch, dist, dev, rank, world, barrier, max_over_ranks, lib_stream, windows):
+def bench_compare(args, smb, torch, dist, dev, rank, world, barrier, max_over_ranks, lib_stream, windows, host_threads,
+                  hbm_peak, peak_src):
     N, NUM = args.compare_sketches, 500
     rows = planted_sketches(N, NUM, 0x5EED0100)
     from sourmash_rust_b200 import sharding
     r0, r1 = sharding.shard_range(N, rank, world)
-    offsets = (np.arange(N + 1, dtype=np.uint64) * np.uint64(NUM))
-    offs_t = torch.from_numpy(offsets.view(np.int64)).to(dev)
-    mine = torch.from_numpy(rows[r0:r1].view(np.int64).copy()).to(dev)
-    common = torch.empty((r1 - r0, N), dtype=torch.int32, device=dev)
-    size = torch.empty((r1 - r0, N), dtype=torch.int32, device=dev)
-    ratio = torch.empty((r1 - r0, N), dtype=torch.float64, device=dev)
+    nr = r1 - r0
+    # the library's own communicator (NCCL inside libsourmash.so); the id travels over the host program's channel
+    if world > 1:
+        smb.comm_init_from_torch()
+    else:
+        smb.comm_init(smb.comm_unique_id(), 0, 1)
+    # this rank's sketches: a resident collection (rows checked sorted once, here); the step gathers and compares
+    local = smb.SketchCollection.from_csr(rows[r0:r1].reshape(-1), np.arange(nr + 1, dtype=np.uint64) * np.uint64(NUM),
+                                          nr, NUM, 31, 42, 0)
+    common = torch.empty((max(1, nr), N), dtype=torch.int32, device=dev)
+    size = torch.empty((max(1, nr), N), dtype=torch.int32, device=dev)
+    ratio = torch.empty((max(1, nr), N), dtype=torch.float64, device=dev)
     steps = max(1, min(args.steps, 5))
 
     def step():
-        full = sharding.allgather_rows(mine, N)  # NCCL all-gather of the packed sketches (no-op at N=1)
-        if world > 1:
-            torch.cuda.current_stream().synchronize()
-        coll = smb.SketchCollection.from_csr(full.data_ptr(), offs_t.data_ptr(), N, NUM, 31, 42, 0, on_device=True)
-        smb.compare_matrix_device(coll, coll, "compare", r0, r1 - r0, 0, N, common.data_ptr(), size.data_ptr(),
-                                  ratio.data_ptr(), N)
-        return coll
+        # all-gather of the packed sketches over NCCL/NVLink + this rank's row block, in one library call: the
+        # join's hash table over the rank's own rows is built while the other ranks' rows are in flight
+        return smb.compare_matrix_allgather_device(local, "compare", common.data_ptr(), size.data_ptr(), ratio.data_ptr(), N)
 
-    for _ in range(2):
+    for _ in range(3):
         step()
     smb.profile_enable(True)
-    smb.profile_read("compare", reset=True)
+    for kind in smb.PROFILE_KINDS:
+        smb.profile_read(kind, reset=True)
     barrier()
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -516,9 +648,28 @@ def bench_compare(args, smb, torch, dist, dev, rank, world, barrier, max_over_ra
     barrier()
     windows.append((t_wall0, time.time()))
     ms = max_over_ranks(e0.elapsed_time(e1)) / steps
-    kms, kn = smb.profile_read("compare", reset=True)
+    kern = {kind: smb.profile_read(kind, reset=True) for kind in smb.PROFILE_KINDS if kind.startswith(("compare", "join"))}
     smb.profile_enable(False)
-    # the same matrix with the data-driven path choice overridden: every pair walked (dense kernel)
+
+    # ---- parity on every rank: 10^6 sampled pairs of this rank's block against the oracle -------------
+    from oracle import oracle as orc
+    osk = oracle_sketches(rows, NUM)
+    rng = np.random.Generator(np.random.PCG64(77 + rank))
+    n_s = args.compare_samples
+    ii = rng.integers(0, max(1, nr), size=n_s)
+    jj = rng.integers(0, N, size=n_s)
+    rel = rng.random(n_s) < 0.5                      # half of the samples inside the row's own 100-member cluster (related pairs)
+    jj[rel] = ((r0 + ii[rel]) // 100) * 100 + rng.integers(0, 100, size=int(rel.sum()))
+    jj = np.minimum(jj, N - 1)
+    oc, osz = orc.compare_pairs(osk, r0 + ii, jj, nthreads=host_threads)
+    ti, tj = torch.from_numpy(ii).to(dev), torch.from_numpy(jj).to(dev)
+    gc, gs, gr = common[ti, tj].cpu().numpy(), size[ti, tj].cpu().numpy(), ratio[ti, tj].cpu().numpy()
+    ok = bool(np.array_equal(gc.astype(np.uint32), oc) and np.array_equal(gs.astype(np.uint32), osz) and
+              np.array_equal(gr, oc.astype(np.float64) / np.maximum(1, osz).astype(np.float64)))
+    assert ok, "rank %d: sampled pairs differ from the oracle" % rank
+    nonzero = int((oc > 0).sum())
+
+    # ---- the same matrix with the data-driven path choice overridden: every pair walked (dense kernel) --------------------
     smb.compare_path("dense")
     step()
     barrier()
@@ -529,16 +680,17 @@ def bench_compare(args, smb, torch, dist, dev, rank, world, barrier, max_over_ra
     barrier()
     ms_dense = max_over_ranks(e0.elapsed_time(e1)) / 2
     smb.compare_path("auto")
-    # end to end: host CSR in, f64 Jaccard matrix out to pinned host memory
-    out = torch.empty((r1 - r0, N), dtype=torch.float64, pin_memory=True)
-    # inputs in pinned host memory (numpy views of pinned torch buffers), as the sketch arm's are
-    rows_pin = torch.from_numpy(np.ascontiguousarray(rows).view(np.int64).reshape(-1)).pin_memory()
-    offs_pin = torch.from_numpy(np.ascontiguousarray(offsets).view(np.int64)).pin_memory()
+
+    # ---- end to end: host CSR in, f64 Jaccard matrix out to pinned host memory ----------------------------------------------
+    out = torch.empty((max(1, nr), N), dtype=torch.float64, pin_memory=True)
+    rows_pin = torch.from_numpy(np.ascontiguousarray(rows[r0:r1]).view(np.int64).reshape(-1)).pin_memory()
+    offs_pin = torch.from_numpy((np.arange(nr + 1, dtype=np.uint64) * np.uint64(NUM)).view(np.int64)).pin_memory()
     rows_c, offs_c = rows_pin.numpy().view(np.uint64), offs_pin.numpy().view(np.uint64)
 
     def e2e():
-        coll = smb.SketchCollection.from_csr(rows_c, offs_c, N, NUM, 31, 42, 0, on_device=False)
-        smb._call("smgpu_compare_matrix", coll._p, r0, r1 - r0, coll._p, 0, N, 0, None, None, smb._vp(out.data_ptr()), N, False)
+        # this rank's sketches from host memory (upload + sortedness check), gather, row block, matrix back to the host
+        loc = smb.SketchCollection.from_csr(rows_c, offs_c, nr, NUM, 31, 42, 0, on_device=False)
+        smb.SketchCollection(_ptr=smb._call("smgpu_compare_matrix_allgather", loc._p, 0, None, None, smb._vp(out.data_ptr()), N, False))
 
     e2e()
     barrier()
@@ -548,32 +700,44 @@ def bench_compare(args, smb, torch, dist, dev, rank, world, barrier, max_over_ra
     e1.record(lib_stream)
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / steps
-    # spot parity: 64 x 64 block against the oracle
-    ok = None
-    if rank == 0:
-        from oracle import oracle as orc
-        osk = []
-        for i in range(64):
-            o = orc.KmerMinHash(NUM, 31)
-            o.add_many(rows[i])
-            osk.append(o)
-        oc, osz = orc.compare_matrix(osk, osk)
-        ok = bool(np.array_equal(common[:64, :64].cpu().numpy(), oc.astype(np.int32)) and
-                  np.array_equal(out[:64, :64].numpy(), oc / np.maximum(1, osz)))
-        assert ok, "compare matrix differs from the oracle"
+    assert np.array_equal(out[:4].numpy(), ratio[:4].cpu().numpy())
+
+    # ---- CPU baseline of the compare half (rank 0, N=1 only): bounded block, all host threads --------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        nb = min(N, 2000)
+        rate, dt, oc2, osz2 = cpu_compare_rate(rows[:nb], os.cpu_count() or 1)
+        assert np.array_equal(common[:nb, :nb].cpu().numpy().astype(np.uint32), oc2), "compare matrix differs from the CPU block"
+        cpu = {"value": rate, "unit": "pairs/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "the first %d x %d block of the matrix (%.2f s on %d threads), three-pass KmerMinHash::compare per pair "
+                         "(oracle/baseline_mt.c)" % (nb, nb, dt, os.cpu_count() or 1), "parity_checked": True}
+    smb.comm_destroy()
+
     pairs = float(N) * float(N)
+    out_bytes = 16.0 * pairs / world     # u32 common + u32 size + f64 ratio per cell of this rank's block
+    kms = {k: (v[0] / steps) for k, v in kern.items() if v[1]}
     return {"metric": "Jaccard comparisons/s all-vs-all", "value": pairs / (ms * 1e-3), "unit": "pairs/s",
-            "config": "cfg3: %d sketches, num=500, k=31, full ordered matrix (common,size u32 + Jaccard f64), rows "
-                      "sharded over %d rank(s), CSR all-gathered over NCCL inside the step" % (N, world),
+            "config": "cfg3: %d sketches, num=500, k=31, 100 clusters of 100 (1 %% of the pairs related), full ordered matrix "
+                      "(common,size u32 + Jaccard f64), rows sharded over %d rank(s); each step = all-gather of the packed "
+                      "sketches over NCCL inside the library + this rank's row block (smgpu_compare_matrix_allgather)" % (N, world),
             "ms_per_step": ms, "steps": steps, "scaling": "strong",
-            "kernel_ms_per_step": (kms / kn * (kn / steps)) if kn else None,
+            "kernel_ms_per_step": kms,
             "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(rows_c.nbytes + offs_c.nbytes),
-                    "d2h_bytes_per_step": int((r1 - r0) * N * 8)},
-            "path": "auto: hash-grouped inverted-index join (row hashes in a hash table, column hashes probe it) finds the related pairs (here 1% of all), only those are walked",
+                    "d2h_bytes_per_step": int(nr * N * 8)},
+            "path": "auto: hash-grouped inverted-index join finds the related pairs (here 1 % of all: the figure is data-dependent), "
+                    "only those are walked; every-pair figure in dense_path",
             "dense_path": {"value": pairs / (ms_dense * 1e-3), "unit": "pairs/s", "ms_per_step": ms_dense,
                            "note": "every pair walked: rank-compressed fixed-length walk, smgpu_compare_path(1)"},
-            "operand_bytes_per_pair": 2 * NUM * 8, "parity_checked_64x64": ok}
+            "roofline": {"bound": "hbm", "kernel": "whole matrix step (join + fill_cells + walk_pairs)",
+                         "achieved": out_bytes / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": out_bytes / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": out_bytes,
+                         "note": "compulsory HBM traffic of a row block is its 16 B per cell of output; the step is bound by "
+                                 "integer issue and latency in the join and the pair walk, not by HBM (profiles/)"},
+            "cpu_baseline": cpu,
+            "operand_bytes_per_pair": 2 * NUM * 8,
+            "parity": {"sampled_pairs_per_rank": int(n_s), "related_samples": nonzero, "ranks_checked": world, "ok": ok}}
 
 
 def main():
@@ -584,8 +748,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads-per-step", type=int, default=1 << 21)
     ap.add_argument("--compare-sketches", type=int, default=10000)
+    ap.add_argument("--compare-samples", type=int, default=1_000_000)
+    ap.add_argument("--percall-threads", type=int, default=0)
     ap.add_argument("--no-compare", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-percall", action="store_true")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

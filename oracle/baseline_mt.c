@@ -105,3 +105,39 @@ void orc_mt_compare_matrix(OrcMinHash *const *rows, size_t nr, OrcMinHash *const
     for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
     free(jobs); free(th);
 }
+
+typedef struct {
+    OrcMinHash *const *mhs;
+    const uint64_t *ia, *ib;
+    size_t p0, p1;
+    uint32_t *common, *size;
+} pair_job;
+
+static void *pair_worker(void *arg) {
+    pair_job *j = (pair_job *)arg;
+    for (size_t p = j->p0; p < j->p1; p++) {
+        uint64_t cm, sz;
+        orc_mh_intersection_size(j->mhs[j->ia[p]], j->mhs[j->ib[p]], &cm, &sz);
+        j->common[p] = (uint32_t)cm;
+        j->size[p] = (uint32_t)sz;
+    }
+    return NULL;
+}
+
+/* KmerMinHash::compare integer parts of a LIST of pairs (mhs[ia[p]], mhs[ib[p]]): the sampled-pairs parity check
+ * of the full-size matrix, pairs split over threads */
+void orc_mt_compare_pairs(OrcMinHash *const *mhs, const uint64_t *ia, const uint64_t *ib, size_t n_pairs,
+                          uint32_t *common, uint32_t *size, int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
+    pair_job *jobs = (pair_job *)calloc((size_t)nthreads, sizeof(pair_job));
+    for (int t = 0; t < nthreads; t++) {
+        jobs[t].mhs = mhs; jobs[t].ia = ia; jobs[t].ib = ib;
+        jobs[t].p0 = n_pairs * (size_t)t / (size_t)nthreads;
+        jobs[t].p1 = n_pairs * (size_t)(t + 1) / (size_t)nthreads;
+        jobs[t].common = common; jobs[t].size = size;
+        pthread_create(&th[t], NULL, pair_worker, &jobs[t]);
+    }
+    for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    free(jobs); free(th);
+}

@@ -6,10 +6,10 @@ package.  Mirrors the reference's crate API names (KmerMinHash::new,
 add_sequence, add_hash, merge, compare, count_common, ...; src/lib.rs:141-513).
 """
 import ctypes as C
-
-import numpy as np
 import os
 import subprocess
+
+import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "liboracle.so")
@@ -69,6 +69,7 @@ def lib():
             "orc_free": (None, [vp]),
             "orc_mt_sketch_reads": (None, [C.c_char_p, sz, sz, C.POINTER(u32), i, u32, u64, i, i, C.POINTER(vp)]),
             "orc_mt_compare_matrix": (None, [C.POINTER(vp), sz, C.POINTER(vp), sz, vp, vp, i]),
+            "orc_mt_compare_pairs": (None, [C.POINTER(vp), vp, vp, sz, vp, vp, i]),
             "orc_ng_new": (vp, [C.POINTER(u64), sz, sz]),
             "orc_ng_free": (None, [vp]),
             "orc_ng_count": (i, [vp, u64]),
@@ -276,6 +277,17 @@ def compare_matrix(rows, cols, nthreads=1):
     size = np.zeros((len(rows), len(cols)), dtype=np.uint32)
     lib().orc_mt_compare_matrix(_ptr_array(rows), len(rows), _ptr_array(cols), len(cols),
                                 common.ctypes.data, size.ctypes.data, nthreads)
+    return common, size
+
+
+def compare_pairs(mhs, ia, ib, nthreads=1):
+    """(common, size) of KmerMinHash::compare for the pairs (mhs[ia[p]], mhs[ib[p]])"""
+    ia = np.ascontiguousarray(ia, dtype=np.uint64)
+    ib = np.ascontiguousarray(ib, dtype=np.uint64)
+    common = np.zeros(len(ia), dtype=np.uint32)
+    size = np.zeros(len(ia), dtype=np.uint32)
+    lib().orc_mt_compare_pairs(_ptr_array(mhs), ia.ctypes.data, ib.ctypes.data, len(ia), common.ctypes.data, size.ctypes.data,
+                               nthreads)
     return common, size
 
 

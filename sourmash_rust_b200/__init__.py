@@ -407,12 +407,13 @@ def add_sequences(mhs, buf, offsets, force=True, on_device=False, n_seqs=None):
 _feed = None
 
 
-def feed_reads(mh_groups, reads: np.ndarray, n_reads, stride, force=False):
+def feed_reads(mh_groups, reads, n_reads, stride, force=False, warm_reads=0, flush=True):
     """The reference's calling pattern for a read set, timed natively: a C loop (host/feed_reads.c) calls
-    kmerminhash_add_sequence once per read and per sketch.  `reads` holds n_reads NUL-terminated strings, one
-    every `stride` bytes; mh_groups is a list (one entry per host thread) of equally long lists of sketches --
-    thread t feeds its sketches with its contiguous share of the reads.  Returns the loop's wall time in seconds
-    (the sketches still hold deferred work: read them to include the flush)."""
+    kmerminhash_add_sequence once per read and per sketch.  `reads` (numpy array or raw host pointer) holds n_reads
+    NUL-terminated strings, one every `stride` bytes; mh_groups is a list (one entry per host thread) of equally
+    long lists of sketches -- thread t feeds its sketches with its contiguous share of the reads, the first
+    `warm_reads` of them untimed.  With `flush` the timed region ends with kmerminhash_get_mins_size on every
+    sketch, i.e. with all deferred work done.  Returns the timed region's wall time in seconds."""
     global _feed
     if _feed is None:
         path = os.path.join(_HERE, "libfeedreads.so")
@@ -420,14 +421,16 @@ def feed_reads(mh_groups, reads: np.ndarray, n_reads, stride, force=False):
             raise RuntimeError("%s is missing: run `python -m sourmash_rust_b200.build`" % path)
         F = C.CDLL(path)
         F.feed_reads_mt.restype = u64
-        F.feed_reads_mt.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int, vp, u64, u64, cb]
+        F.feed_reads_mt.argtypes = [vp, vp, C.POINTER(vp), C.c_int, C.c_int, vp, u64, u64, cb, u64]
         _feed = F
     n_mhs = len(mh_groups[0])
     assert all(len(g) == n_mhs for g in mh_groups)
     flat = (vp * (n_mhs * len(mh_groups)))(*[m._p for g in mh_groups for m in g])
     fn = C.cast(lib().kmerminhash_add_sequence, vp)
     lib().sourmash_err_clear()
-    ns = _feed.feed_reads_mt(fn, flat, n_mhs, len(mh_groups), _vp(reads), n_reads, stride, force)
+    size_fn = C.cast(lib().kmerminhash_get_mins_size, vp) if flush else None
+    ns = _feed.feed_reads_mt(fn, size_fn, flat, n_mhs, len(mh_groups), _vp(reads), n_reads, stride, force, warm_reads)
+    _check()
     return ns * 1e-9
 
 

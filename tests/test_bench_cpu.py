@@ -20,3 +20,14 @@ def test_reference_arm_prints_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and "workload" in d["config"]
+    # the compare half of the metric has a CPU arm too (a bounded block of cfg3)
+    c = d["compare"]
+    assert c["impl"] == "reference" and c["unit"] == "pairs/s" and c["value"] > 0 and c["cpu_baseline"]["kind"] == "port"
+
+
+def test_kernel_constants_file_names_the_kernels_bench_reads():
+    sys.path.insert(0, ROOT)
+    import bench
+    consts = bench.kernel_constants()
+    for key in bench.KERNEL_OF.values():
+        assert key in consts and consts[key]["instr_per_unit"] > 0 and consts[key]["dram_bytes_per_unit"] > 0, key
