@@ -617,9 +617,7 @@ def bench_compare(args, smb, torch, dist, dev, rank, world, barrier, max_over_ra
     nr = r1 - r0
     # the library's own communicator (NCCL inside libsourmash.so); the id travels over the host program's channel
     if world > 1:
-        smb.comm_init_from_torch()
-    else:
-        smb.comm_init(smb.comm_unique_id(), 0, 1)
+        smb.comm_init_from_torch()   # (one rank: no communicator needed, the collectives act as a world of one)
     # this rank's sketches: a resident collection (rows checked sorted once, here); the step gathers and compares
     local = smb.SketchCollection.from_csr(rows[r0:r1].reshape(-1), np.arange(nr + 1, dtype=np.uint64) * np.uint64(NUM),
                                           nr, NUM, 31, 42, 0)

@@ -167,7 +167,8 @@ uint64_t smgpu_linear_find(SketchCollection *index, SketchCollection *queries, i
  * KmerMinHash::merge, matrix rows are independent, a partitioned LinearIndex concatenates its parts' hits.
  * NCCL is bound at run time (libnccl.so.2; the copy the host program already loaded, if any).  The 128-byte id
  * is made on one rank and handed to the others by the host program's own channel (MPI_Bcast, a file, ...);
- * every function below marked "collective" must be called by all ranks, in the same order. */
+ * every function below marked "collective" must be called by all ranks, in the same order.  Without a
+ * communicator the collectives act as in a world of one rank (and NCCL is never loaded). */
 #define SMGPU_COMM_ID_BYTES 128
 void smgpu_comm_unique_id(uint8_t *id128);                                   /* ncclGetUniqueId */
 void smgpu_comm_init(const uint8_t *id128, int32_t rank, int32_t world);     /* collective; after smgpu_set_device */

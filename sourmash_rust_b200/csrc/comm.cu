@@ -192,10 +192,28 @@ int comm_nccl_version() {
 // thread waits for it: work that needs only local data overlaps the transfer.
 // ---------------------------------------------------------------------------------------------------------
 static SketchCollection *allgather_impl(SketchCollection &local, const std::function<void()> &before_wait) {
-    require_comm();
     Comm &c = g_comm;
     Context &ctx = Context::get();
     local.finalize();  // (rows were checked strictly ascending when the local collection was made: peers do the same)
+    if (!c.comm) {
+        // no communicator = a world of one: the gathered collection is a copy of the local one (NCCL is not loaded)
+        std::unique_ptr<SketchCollection> out(new SketchCollection());
+        ctx.adopt(out->owner);
+        out->have_params = local.have_params;
+        out->ksize = local.ksize; out->is_protein = local.is_protein; out->seed = local.seed; out->max_hash = local.max_hash;
+        out->n_rows = local.n_rows; out->n_hashes = local.n_hashes; out->max_len = local.max_len;
+        out->h_offsets.assign(local.h_offsets.begin(), local.h_offsets.begin() + local.n_rows + 1);
+        out->h_nums.assign(local.h_nums.begin(), local.h_nums.begin() + local.n_rows);
+        out->d_hashes.reserve((local.n_hashes + 4) * 8);
+        out->d_offsets.reserve((local.n_rows + 2) * 8);
+        out->d_nums.reserve((local.n_rows + 1) * 4);
+        if (local.n_hashes) SM_CUDA(cudaMemcpyAsync(out->d_hashes.p, local.d_hashes.p, local.n_hashes * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+        SM_CUDA(cudaMemcpyAsync(out->d_offsets.p, local.d_offsets.p, (local.n_rows + 1) * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+        if (local.n_rows) SM_CUDA(cudaMemcpyAsync(out->d_nums.p, local.d_nums.p, local.n_rows * 4, cudaMemcpyDeviceToDevice, ctx.stream));
+        if (before_wait) before_wait();
+        out->dirty = false;
+        return out.release();
+    }
     unsigned long long mine[HDR] = {local.n_rows, local.n_hashes, local.max_len, local.ksize, local.seed, local.max_hash,
                                     (unsigned long long)local.is_protein | ((unsigned long long)local.have_params << 1), 0};
     exchange_headers(mine);
@@ -271,7 +289,6 @@ SketchCollection *collection_allgather(SketchCollection &local) {
 SketchCollection *compare_matrix_allgather(SketchCollection &local, int mode, uint32_t *common, uint32_t *size, double *ratio,
                                            uint64_t ld, bool out_on_device) {
     std::lock_guard<std::mutex> lk(g_comm_mutex);
-    require_comm();
     Context &ctx = Context::get();
     local.finalize();
     JoinTable jt;
@@ -304,9 +321,8 @@ SketchCollection *compare_matrix_allgather(SketchCollection &local, int mode, ui
 // ---------------------------------------------------------------------------------------------------------
 void comm_allmerge(KmerMinHash &mh) {
     std::lock_guard<std::mutex> lk(g_comm_mutex);
-    require_comm();
     Comm &c = g_comm;
-    if (c.world == 1) return;
+    if (!c.comm || c.world == 1) return;  // a world of one: nothing to combine
     Context &ctx = Context::get();
     size_t n_m = 0, n_a = 0;
     const uint64_t *d_m = mh.device_mins(&n_m);
@@ -356,8 +372,8 @@ void comm_allmerge(KmerMinHash &mh) {
 uint64_t linear_find_sharded(SketchCollection &index_part, SketchCollection &queries, int mode, double threshold,
                              uint64_t *hit_offsets, uint64_t *hits, uint64_t hits_cap) {
     std::lock_guard<std::mutex> lk(g_comm_mutex);
-    require_comm();
     Comm &c = g_comm;
+    if (!c.comm) return linear_find(index_part, queries, mode, threshold, hit_offsets, hits, hits_cap);  // a world of one
     Context &ctx = Context::get();
     queries.finalize();
     const uint64_t nq = queries.n_rows;

@@ -12,11 +12,11 @@ pytestmark = pytest.mark.gpu
 WORKER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "workers", "comm_worker.py")
 
 
-def _run_world(world, tmp_path):
+def _run_world(world, tmp_path, no_comm=False):
     id_file = str(tmp_path / ("nccl_id_%d" % world))
     procs = []
     for r in range(world):
-        env = dict(os.environ, RANK=str(r), WORLD=str(world), LOCAL_RANK=str(r), COMM_ID_FILE=id_file)
+        env = dict(os.environ, RANK=str(r), WORLD=str(world), LOCAL_RANK=str(r), COMM_ID_FILE=id_file, NO_COMM="1" if no_comm else "0")
         procs.append(subprocess.Popen([sys.executable, WORKER], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = []
     for p in procs:
@@ -33,6 +33,10 @@ def _run_world(world, tmp_path):
 
 def test_collectives_world_1(tmp_path):
     _run_world(1, tmp_path)
+
+
+def test_collectives_without_a_communicator(tmp_path):
+    _run_world(1, tmp_path, no_comm=True)
 
 
 def test_collectives_world_2(tmp_path):
