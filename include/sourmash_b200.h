@@ -149,6 +149,12 @@ uint64_t smgpu_scaffold_pairs(SketchCollection *c, uint64_t *pairs_first, uint64
  * 4 = as 2, and a block whose probe found many incidences is not handed to the dense kernels.
  * Results are identical. */
 void smgpu_compare_path(int32_t path);
+/* How smgpu_linear_find counts shared hashes when a count decides the hit (containment; similarity of sketches
+ * without a num): 0 (default) = an index that is large against the query batch is STREAMED once past per-slice
+ * Bloom filters of the query hashes held in shared memory (the search then runs at the rate HBM delivers the
+ * index), anything smaller goes through the join of smgpu_compare_matrix; 1 = always the join; 2 = stream whenever
+ * the shapes allow it.  Results are identical. */
+void smgpu_find_path(int32_t path);
 /* Batch sketching of several k-sizes over the same sequences (smgpu_add_* with more than one
  * handle): on (default) = sketches with distinct k in {21, 31, 51} and one seed share a fused
  * launch that stages each tile of bases once; off = one launch per sketch.  Results are identical. */

@@ -107,6 +107,7 @@ EXTENSION_ABI = {
     "smgpu_compare_matrix": (None, [vp, u64, u64, vp, u64, u64, i32, vp, vp, vp, u64, cb]),
     "smgpu_scaffold_pairs": (u64, [vp, vp, vp]),
     "smgpu_compare_path": (None, [i32]),
+    "smgpu_find_path": (None, [i32]),
     "smgpu_linear_find": (u64, [vp, vp, i32, C.c_double, vp, vp, u64]),
     "smgpu_comm_unique_id": (None, [vp]),
     "smgpu_comm_init": (None, [vp, i32, i32]),
@@ -211,12 +212,17 @@ def profile_enable(on=True):
 
 
 PROFILE_KINDS = {"sketch_k21": 0, "sketch_k31": 1, "sketch_k51": 2, "sketch_other": 3, "compare": 4, "join_sort": 5,
-                 "sketch_multi": 6}
+                 "sketch_multi": 6, "find_stream": 7, "compare_walk": 8, "compare_probe": 9, "compare_fill": 10}
 
 
 def compare_path(path="auto"):
     """'auto' | 'dense' | 'sparse' | 'noprobe' (smgpu_compare_path)"""
     lib().smgpu_compare_path({"auto": 0, "dense": 1, "sparse": 2, "noprobe": 3, "probe": 4}[path])
+
+
+def find_path(path="auto"):
+    """'auto' | 'join' | 'stream' (smgpu_find_path)"""
+    lib().smgpu_find_path({"auto": 0, "join": 1, "stream": 2}[path])
 
 
 def fuse_multi_k(on=True):

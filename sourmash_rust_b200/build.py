@@ -11,7 +11,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libsourmash.so")
 FEED_SRC = os.path.join(HERE, "host", "feed_reads.c")   # a C caller's loop over the reference ABI (bench / percall timing)
 FEED_LIB = os.path.join(HERE, "libfeedreads.so")
-SOURCES = ["device.cu", "sketch.cu", "sortops.cu", "compare.cu", "join.cu", "protein.cu", "minhash.cu", "collection.cu", "sketch_many.cu", "nodegraph.cu", "comm.cu", "signature.cpp", "ffi.cpp"]
+SOURCES = ["device.cu", "sketch.cu", "sortops.cu", "compare.cu", "join.cu", "find_stream.cu", "protein.cu", "minhash.cu", "collection.cu", "sketch_many.cu", "nodegraph.cu", "comm.cu", "signature.cpp", "ffi.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-Wall",
          "-x", "cu"]

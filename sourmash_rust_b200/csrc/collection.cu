@@ -28,6 +28,26 @@ void SketchCollection::push(KmerMinHash &mh) {
     h_nums.push_back(mh.num);
     dirty = true;
     probe_checked = probe_dense_preferred = false;
+    parts_valid = false;
+}
+
+// slice bounds of every row (find_stream.cu), once per collection content
+void SketchCollection::ensure_partitions() {
+    finalize();
+    if (parts_valid) return;
+    Context &ctx = Context::get();
+    n_parts = find_stream_partitions(n_rows, n_hashes);
+    SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_TMAX), 0, 8, ctx.stream));
+    launch_rows_max(d_hashes.as<uint64_t>(), d_offsets.as<uint64_t>(), n_rows, ctx.dsc(SC_TMAX), ctx.stream);
+    ctx.read_scalars();
+    const uint64_t top = ctx.h_scalars[SC_TMAX];
+    part_shift = 0;
+    while (part_shift < 63 && (top >> part_shift) >= n_parts) part_shift++;   // n_parts << part_shift > top
+    d_part_off.reserve((size_t)(n_parts + 1) * std::max<uint64_t>(1, n_rows) * 4);
+    launch_part_offsets(d_hashes.as<uint64_t>(), d_offsets.as<uint64_t>(), n_rows, part_shift, n_parts, d_part_off.as<uint32_t>(),
+                        ctx.stream);
+    ctx.sync();
+    parts_valid = true;
 }
 
 void SketchCollection::finalize() {
@@ -114,6 +134,12 @@ static uint64_t find_block_cells_from_env() {
     return (m ? m : 1) << 20;
 }
 static const uint64_t g_find_block_cells = find_block_cells_from_env();
+// linear_find's count path: 0 = stream the index (find_stream.cu) when it is large against the query batch,
+// 1 = always the general join, 2 = stream whenever the shapes allow it, whatever the sizes (tests).  SMB200_FIND_PATH sets it.
+int g_find_path = [] {
+    const char *e = getenv("SMB200_FIND_PATH");
+    return e ? atoi(e) : 0;
+}();
 int g_compare_path = 0;  // 0 = choose from the data, 1 = dense tile kernel, 2 = inverted-index path, 3 = inverted index without the probe form
 
 static int bit_length64(uint64_t x) {
@@ -128,8 +154,10 @@ static int bit_length64(uint64_t x) {
 void join_table_build(Context &ctx, JoinTable &jt, const uint64_t *bh, const uint64_t *bo, uint64_t b0, uint64_t n_build,
                       uint64_t n_bp, bool with_filter) {
     cudaStream_t st = ctx.stream;
+    // slots: the power of two at or above 1.5 x the postings (postings of one hash share a slot, so the load is
+    // below 0.67 whatever the data; the memsets and the scan over the slots are a third of the build at 5 M postings)
     int log2_t = 12;
-    while ((1ull << log2_t) < 2 * n_bp) log2_t++;
+    while ((1ull << log2_t) < n_bp + n_bp / 2) log2_t++;
     const uint64_t T = 1ull << log2_t;
     ctx.join[0].reserve((T + 2) * 8);
     ctx.join[1].reserve((T + 2) * 8);
@@ -491,11 +519,34 @@ std::vector<std::vector<uint64_t>> linear_find_lists(SketchCollection &index, Sk
         for (uint32_t v : index.h_nums) index_unbounded &= v == 0;
         const bool count_sim = mode == 0 && index_unbounded;
         const bool count_path = (mode == 1 || count_sim) && threshold >= 0.0;
+        // a large index against a (much) smaller query batch: stream the index at HBM rate (find_stream.cu)
+        const bool stream = count_path && g_find_path != 1 && queries.n_hashes > 0 && queries.n_hashes < (1ull << 31) && nq < (1ull << 31) &&
+                            index.max_len < (1u << 31) &&
+                            (g_find_path == 2 || (index.n_hashes >= 4 * queries.n_hashes && index.n_hashes >= (1ull << 22)));
+        JoinTable qt;
+        if (stream) index.ensure_partitions();
         for (uint64_t b0 = 0; count_path && b0 < ni; b0 += block_rows) {
             const uint64_t bn = std::min(block_rows, ni - b0);
             uint32_t *cmat = ctx.misc[2].as<uint32_t>();  // cells * 8 bytes reserved: room for the u32 counts
             uint64_t *found = ctx.misc[3].as<uint64_t>();
-            compare_block_device(index, b0, bn, queries, 0, nq, 1, cmat, nullptr, nullptr, nq);
+            if (stream) {
+                // the index streams past per-slice Bloom filters of the query hashes held in shared memory (find_stream.cu)
+                if (b0 == 0) {   // the query side: exact table + filters, once per search
+                    join_table_build(ctx, qt, queries.d_hashes.as<uint64_t>(), queries.d_offsets.as<uint64_t>(), 0, nq, queries.n_hashes, false);
+                    ctx.misc[6].reserve(find_stream_filter_bytes(index.n_parts) + 256);
+                    SM_CUDA(cudaMemsetAsync(ctx.misc[6].p, 0, find_stream_filter_bytes(index.n_parts), st));
+                    launch_filters_build(queries.d_hashes.as<uint64_t>(), queries.n_hashes, index.part_shift, index.n_parts,
+                                         ctx.misc[6].as<uint32_t>(), st);
+                }
+                SM_CUDA(cudaMemsetAsync(cmat, 0, bn * nq * 4, st));
+                SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_FLAG), 0, 8, st));
+                launch_stream_probe(index.d_hashes.as<uint64_t>(), index.d_offsets.as<uint64_t>(), b0, bn, index.d_part_off.as<uint32_t>(),
+                                    index.n_rows, index.n_parts, ctx.misc[6].as<uint32_t>(), ctx.join[0].as<unsigned long long>(),
+                                    ctx.sort_tmp_k.as<uint64_t>(), ctx.join[7].as<uint32_t>(), qt.log2_t, cmat, nq,
+                                    reinterpret_cast<uint32_t *>(ctx.dsc(SC_FLAG)), ctx.sm_count, st);
+            } else {
+                compare_block_device(index, b0, bn, queries, 0, nq, 1, cmat, nullptr, nullptr, nq);
+            }
             SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_CNT), 0, 8, st));
             launch_count_hits(cmat, bn, nq, index.d_offsets.as<uint64_t>(), b0, count_sim ? queries.d_offsets.as<uint64_t>() : nullptr,
                               threshold, found, cells, ctx.dsc(SC_CNT), st);

@@ -27,6 +27,13 @@ struct SketchCollection {
     // compare path bookkeeping (collection.cu): has a block with these rows gone through the probe form of
     // the join yet, and did it find so many incidences that the dense kernels are the better choice
     bool probe_checked = false, probe_dense_preferred = false;
+    // find_stream.cu: where each (sorted) row meets each of n_parts equal slices of the hash range [0, n_parts << part_shift);
+    // built on the first large search over this collection, kept until it changes
+    DevBuf d_part_off;
+    uint32_t n_parts = 0;
+    int part_shift = 0;
+    bool parts_valid = false;
+    void ensure_partitions();
     std::mutex mu;      // as KmerMinHash::mu
     StreamOwner owner;  // thread context that last queued work on the device arrays (finalize() re-homes)
 
@@ -58,6 +65,7 @@ void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t nr, Sket
                           const JoinTable *prebuilt = nullptr);
 
 extern int g_compare_path;
+extern int g_find_path;
 // see include/sourmash_b200.h
 void compare_matrix(SketchCollection &rows, uint64_t r0, uint64_t nr, SketchCollection &cols, uint64_t c0, uint64_t nc,
                     int mode, uint32_t *common, uint32_t *size, double *ratio, uint64_t ld, bool out_on_device);

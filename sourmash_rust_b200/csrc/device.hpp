@@ -127,7 +127,7 @@ struct Context {
 // Per-kernel device timing (CUDA events on the launching stream), off unless enabled through
 // smgpu_profile_enable: bench.py's roofline numbers come from here.
 enum { PROF_SKETCH_K21 = 0, PROF_SKETCH_K31 = 1, PROF_SKETCH_K51 = 2, PROF_SKETCH_OTHER = 3, PROF_COMPARE = 4,
-       PROF_SORT = 5, PROF_SKETCH_MULTI = 6, PROF_KINDS = 7 };
+       PROF_SORT = 5, PROF_SKETCH_MULTI = 6, PROF_FIND = 7, PROF_WALK = 8, PROF_PROBE = 9, PROF_FILL = 10, PROF_KINDS = 11 };
 struct ProfScope {
     int kind;
     cudaStream_t st;

@@ -1,0 +1,258 @@
+// find_stream.cu -- LinearIndex::find (src/index/linear.rs:25-45) over a large index, HBM-bound.
+//
+// The count |node n query| of every (index sketch, query) cell decides containment (index.rs:146-160) and, for
+// sketches without a `num`, similarity (lib.rs:470-508).  One search streams the whole index past the query batch
+// once; the index is 10^2-10^3 times larger than the batch (BASELINE config 4: 40 GB against 40 MB), so the
+// search can run at the rate HBM delivers the index -- if each index hash costs no more than a few instructions
+// and no off-chip access of its own.  The join of collection.cu answers "is this hash in any query" with a read of
+// a bit table in L2 (random 32-byte sector per hash: 840 GB/s of index, 13 % of HBM).  Here that test is on chip:
+//
+//   * the hash range is cut into P equal slices ("partitions"); a sorted sketch meets slice p in ONE contiguous
+//     stretch, whose bounds are kept with the index (part_offsets, built once per collection in one pass);
+//   * per slice, the query hashes that fall into it go into a Bloom filter of 2^20 bits (two probes): 128 KB,
+//     which fits the shared memory of an SM;
+//   * a CTA takes a (slice, chunk of index rows) work item, holds that slice's filter in shared memory and streams
+//     the rows' stretches past it with coalesced loads: per index hash one multiply, two shared-memory reads;
+//   * only the hashes the filter lets through (true hits + ~2 % false positives) go to the exact table in global
+//     memory (the hash-grouped table over the queries, join.cu) and add to the count matrix, one atomic per
+//     (row, query) per warp step.
+#include <algorithm>
+
+#include "device.hpp"
+#include "kernels.cuh"
+
+namespace smb200 {
+
+namespace {
+
+constexpr int FS_THREADS = 1024;
+constexpr int FS_LOG2_F = 20;                              // filter bits per slice
+constexpr uint32_t FS_FILTER_WORDS = (1u << FS_LOG2_F) / 32;
+constexpr uint32_t FS_CHUNK_ROWS = 4096;                   // index rows per work item
+constexpr unsigned long long FS_MUL = 0xD6E8FEB86659FD93ull;
+constexpr unsigned long long FS_EMPTY = ~0ull;
+
+__device__ __forceinline__ void filter_bits(uint64_t h, uint32_t &b1, uint32_t &b2) {
+    const uint64_t m = h * FS_MUL;
+    b1 = (uint32_t)(m >> (64 - FS_LOG2_F));
+    b2 = (uint32_t)(m >> (64 - 2 * FS_LOG2_F)) & ((1u << FS_LOG2_F) - 1);
+}
+
+// largest hash of the collection (rows are sorted: the last element of each)
+__global__ void rows_max_kernel(const uint64_t *__restrict__ h, const uint64_t *__restrict__ off, uint64_t n_rows,
+                                unsigned long long *out) {
+    unsigned long long m = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+        const uint64_t b = off[r], e = off[r + 1];
+        if (e > b) m = max(m, (unsigned long long)h[e - 1]);
+    }
+    for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, d));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// part_off[q * n_rows + r] = number of hashes of row r below slice q (q = 0 .. P): slice p of row r is
+// [part_off[p], part_off[p + 1]).  One warp per row, one pass over its hashes.
+__global__ void __launch_bounds__(256) part_offsets_kernel(const uint64_t *__restrict__ h, const uint64_t *__restrict__ off,
+                                                           uint64_t n_rows, int shift, uint32_t P, uint32_t *__restrict__ part_off) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rows; r += warps) {
+        const uint64_t b = off[r], e = off[r + 1];
+        const uint32_t len = (uint32_t)(e - b);
+        for (uint32_t i = lane; i < len; i += 32) {
+            const int64_t cur = (int64_t)min((uint64_t)(P - 1), h[b + i] >> shift);
+            const int64_t prev = i ? (int64_t)min((uint64_t)(P - 1), h[b + i - 1] >> shift) : -1;
+            for (int64_t q = prev + 1; q <= cur; q++) part_off[(uint64_t)q * n_rows + r] = i;
+        }
+        if (lane == 0) {
+            const int64_t last = len ? (int64_t)min((uint64_t)(P - 1), h[e - 1] >> shift) : -1;
+            for (int64_t q = last + 1; q <= (int64_t)P; q++) part_off[(uint64_t)q * n_rows + r] = len;
+        }
+    }
+}
+
+// Bloom filters of the query hashes, one per slice (global memory; the probe kernel copies a slice's filter into
+// shared memory).  Query hashes at or beyond P << shift cannot occur in the index: skipped.
+__global__ void __launch_bounds__(256) filters_build_kernel(const uint64_t *__restrict__ qh, uint64_t n, int shift, uint32_t P,
+                                                            uint32_t *filters) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t h = qh[i];
+        const uint64_t p = h >> shift;
+        if (p >= P) continue;
+        uint32_t b1, b2;
+        filter_bits(h, b1, b2);
+        uint32_t *f = filters + p * FS_FILTER_WORDS;
+        atomicOr(&f[b1 >> 5], 1u << (b1 & 31));
+        atomicOr(&f[b2 >> 5], 1u << (b2 & 31));
+    }
+}
+
+struct StreamArgs {
+    const uint64_t *ih, *io;       // index CSR
+    uint64_t b0, bn;               // block of index rows
+    const uint32_t *part_off;      // [(P + 1)][n_rows_total]
+    uint64_t n_rows_total;
+    uint32_t P;
+    const uint32_t *filters;       // [P][FS_FILTER_WORDS]
+    const unsigned long long *tkey;  // exact table over the query hashes (join.cu: group_insert / group_fill)
+    const uint64_t *toff;
+    const uint32_t *grows;
+    int log2_t;
+    uint32_t *cmat;                // [bn][ld] counts
+    uint64_t ld;
+    uint32_t *work_ctr;            // zeroed
+};
+
+// exact lookup of the hashes the filter let through + count matrix update; the whole warp comes here together
+__device__ __forceinline__ void stream_hits(const StreamArgs &a, bool hit, uint64_t h, uint64_t row) {
+    uint64_t jb = 0, je = 0;
+    if (hit) {
+        const uint64_t T = 1ull << a.log2_t;
+        uint64_t s = (h * 0x9E3779B97F4A7C15ull) >> (64 - a.log2_t);
+        if (h == FS_EMPTY) {
+            s = T;
+        } else {
+            for (;;) {
+                const unsigned long long cur = __ldg(&a.tkey[s]);
+                if (cur == h) break;
+                if (cur == FS_EMPTY) { s = ~0ull; break; }
+                s = (s + 1) & (T - 1);
+            }
+        }
+        if (s != ~0ull) { jb = __ldg(&a.toff[s]); je = __ldg(&a.toff[s + 1]); }
+    }
+    // first query of each run: lanes that hit the same (row, query) cell add once
+    const bool have = je > jb;
+    const uint64_t cell = have ? row * a.ld + __ldg(&a.grows[jb]) : (~0ull - (threadIdx.x & 31));
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, cell);
+    if (have) {
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&a.cmat[cell], (uint32_t)__popc(peers));
+        for (uint64_t j = jb + 1; j < je; j++) atomicAdd(&a.cmat[row * a.ld + __ldg(&a.grows[j])], 1u);  // hash shared by several queries
+    }
+}
+
+__global__ void __launch_bounds__(FS_THREADS, 1) stream_probe_kernel(const StreamArgs a) {
+    extern __shared__ __align__(16) uint32_t s_filter[];
+    __shared__ uint32_t s_item;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_chunks = (uint32_t)((a.bn + FS_CHUNK_ROWS - 1) / FS_CHUNK_ROWS);
+    const uint32_t n_items = a.P * n_chunks;
+    uint32_t cur_p = ~0u;
+    for (;;) {
+        if (threadIdx.x == 0) s_item = atomicAdd(a.work_ctr, 1u);
+        __syncthreads();            // (also: every warp is done with the previous item's filter)
+        const uint32_t item = s_item;
+        __syncthreads();
+        if (item >= n_items) break;
+        const uint32_t p = item / n_chunks, chunk = item - p * n_chunks;   // slice-major: neighbours share a filter in L2
+        if (p != cur_p) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.filters + (size_t)p * FS_FILTER_WORDS);
+            uint4 *dst = reinterpret_cast<uint4 *>(s_filter);
+            for (uint32_t i = threadIdx.x; i < FS_FILTER_WORDS / 4; i += FS_THREADS) dst[i] = __ldg(src + i);
+            cur_p = p;
+            __syncthreads();
+        }
+        const uint64_t row_lo = (uint64_t)chunk * FS_CHUNK_ROWS, row_hi = min(a.bn, row_lo + FS_CHUNK_ROWS);
+        const uint32_t *po_lo = a.part_off + (uint64_t)p * a.n_rows_total + a.b0;
+        const uint32_t *po_hi = po_lo + a.n_rows_total;
+        // a warp takes 32 consecutive rows at a time: their bounds arrive with three coalesced loads
+        for (uint64_t g = row_lo + (uint64_t)warp * 32; g < row_hi; g += (FS_THREADS / 32) * 32) {
+            const uint64_t r = g + lane;
+            const bool valid = r < row_hi;
+            const uint64_t base = valid ? __ldg(&a.io[a.b0 + r]) : 0;
+            const uint32_t s = valid ? __ldg(&po_lo[r]) : 0, e = valid ? __ldg(&po_hi[r]) : 0;
+            const int n_in = (int)min((uint64_t)32, row_hi - g);
+            for (int k = 0; k < n_in; k += 2) {
+                // two rows per step, up to three loads each in flight before the first test
+                const int k1 = min(k + 1, n_in - 1);
+                const uint64_t *seg0 = a.ih + __shfl_sync(0xFFFFFFFFu, base, k);
+                const uint64_t *seg1 = a.ih + __shfl_sync(0xFFFFFFFFu, base, k1);
+                const uint32_t s0 = __shfl_sync(0xFFFFFFFFu, s, k), e0 = __shfl_sync(0xFFFFFFFFu, e, k);
+                const uint32_t s1 = __shfl_sync(0xFFFFFFFFu, s, k1), e1 = (k + 1 < n_in) ? __shfl_sync(0xFFFFFFFFu, e, k1) : s1;
+                uint64_t h[6];
+                bool in[6];
+#pragma unroll
+                for (int u = 0; u < 3; u++) {
+                    const uint32_t i0 = s0 + lane + 32 * u, i1 = s1 + lane + 32 * u;
+                    in[u] = i0 < e0;
+                    in[3 + u] = i1 < e1;
+                    h[u] = in[u] ? __ldcs(seg0 + i0) : 0;
+                    h[3 + u] = in[3 + u] ? __ldcs(seg1 + i1) : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 6; u++) {
+                    uint32_t b1, b2;
+                    filter_bits(h[u], b1, b2);
+                    const bool hit = in[u] && ((s_filter[b1 >> 5] >> (b1 & 31)) & (s_filter[b2 >> 5] >> (b2 & 31)) & 1u);
+                    if (__any_sync(0xFFFFFFFFu, hit)) stream_hits(a, hit, h[u], g + (u < 3 ? k : k1));
+                }
+                // stretches longer than 96 hashes: the rest, one load at a time
+                for (int side = 0; side < 2; side++) {
+                    const uint64_t *seg = side ? seg1 : seg0;
+                    const uint32_t ee = side ? e1 : e0;
+                    const uint64_t row = g + (side ? k1 : k);
+                    for (uint32_t i = (side ? s1 : s0) + 96; i < ee; i += 32) {   // warp-uniform bounds
+                        const bool inb = i + lane < ee;
+                        const uint64_t hh = inb ? __ldcs(seg + i + lane) : 0;
+                        uint32_t b1, b2;
+                        filter_bits(hh, b1, b2);
+                        const bool hit = inb && ((s_filter[b1 >> 5] >> (b1 & 31)) & (s_filter[b2 >> 5] >> (b2 & 31)) & 1u);
+                        if (__any_sync(0xFFFFFFFFu, hit)) stream_hits(a, hit, hh, row);
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// ---- host side ---------------------------------------------------------------------------------------------
+uint32_t find_stream_partitions(uint64_t n_rows, uint64_t n_hashes) {
+    // stretches of at least ~64 hashes on average, at most 64 slices
+    const uint64_t avg = n_rows ? n_hashes / n_rows : 0;
+    uint32_t P = 1;
+    while (P < 64 && (uint64_t)P * 2 * 64 <= avg) P *= 2;
+    return P;
+}
+
+void launch_rows_max(const uint64_t *h, const uint64_t *off, uint64_t n_rows, unsigned long long *out, cudaStream_t st) {
+    if (!n_rows) return;
+    rows_max_kernel<<<(unsigned)std::min<uint64_t>((n_rows + 255) / 256, 148 * 8), 256, 0, st>>>(h, off, n_rows, out);
+    SM_LAUNCHED();
+}
+void launch_part_offsets(const uint64_t *h, const uint64_t *off, uint64_t n_rows, int shift, uint32_t P, uint32_t *part_off,
+                         cudaStream_t st) {
+    if (!n_rows) return;
+    part_offsets_kernel<<<(unsigned)std::min<uint64_t>((n_rows * 32 + 255) / 256, 148 * 16), 256, 0, st>>>(h, off, n_rows, shift, P, part_off);
+    SM_LAUNCHED();
+}
+size_t find_stream_filter_bytes(uint32_t P) { return (size_t)P * FS_FILTER_WORDS * 4; }
+void launch_filters_build(const uint64_t *qh, uint64_t n, int shift, uint32_t P, uint32_t *filters, cudaStream_t st) {
+    if (!n) return;
+    filters_build_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(qh, n, shift, P, filters);
+    SM_LAUNCHED();
+}
+void launch_stream_probe(const uint64_t *ih, const uint64_t *io, uint64_t b0, uint64_t bn, const uint32_t *part_off,
+                         uint64_t n_rows_total, uint32_t P, const uint32_t *filters, const unsigned long long *tkey,
+                         const uint64_t *toff, const uint32_t *grows, int log2_t, uint32_t *cmat, uint64_t ld, uint32_t *work_ctr,
+                         int sm_count, cudaStream_t st) {
+    if (!bn) return;
+    static bool attr_set = false;
+    const size_t smem = (size_t)FS_FILTER_WORDS * 4;
+    if (!attr_set) {
+        SM_CUDA(cudaFuncSetAttribute(stream_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    StreamArgs a;
+    a.ih = ih; a.io = io; a.b0 = b0; a.bn = bn; a.part_off = part_off; a.n_rows_total = n_rows_total; a.P = P;
+    a.filters = filters; a.tkey = tkey; a.toff = toff; a.grows = grows; a.log2_t = log2_t; a.cmat = cmat; a.ld = ld;
+    a.work_ctr = work_ctr;
+    ProfScope prof(PROF_FIND, st);
+    stream_probe_kernel<<<sm_count, FS_THREADS, smem, st>>>(a);
+    SM_LAUNCHED();
+}
+
+}  // namespace smb200

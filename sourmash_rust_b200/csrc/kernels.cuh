@@ -205,6 +205,21 @@ void launch_walk_pairs(const uint64_t *pairs, uint64_t n_pairs, const uint64_t *
                        uint32_t *size, double *ratio, uint64_t ld, cudaStream_t st, const uint64_t *n_dev_a = nullptr,
                        const uint64_t *n_dev_b = nullptr, uint64_t nr_transposed = 0);
 
+// ---- find_stream.cu: LinearIndex::find over a large index at HBM rate (see the file header) -----------------
+uint32_t find_stream_partitions(uint64_t n_rows, uint64_t n_hashes);   // slices of the hash range (power of two, <= 64)
+void launch_rows_max(const uint64_t *h, const uint64_t *off, uint64_t n_rows, unsigned long long *out /*zeroed*/, cudaStream_t st);
+// part_off: (P + 1) x n_rows u32, slice-major: row r meets slice p in [part_off[p][r], part_off[p + 1][r])
+void launch_part_offsets(const uint64_t *h, const uint64_t *off, uint64_t n_rows, int shift, uint32_t P, uint32_t *part_off,
+                         cudaStream_t st);
+size_t find_stream_filter_bytes(uint32_t P);
+void launch_filters_build(const uint64_t *qh, uint64_t n, int shift, uint32_t P, uint32_t *filters /*zeroed*/, cudaStream_t st);
+// counts of shared hashes of index rows [b0, b0 + bn) x queries into cmat[(row - b0) * ld + query] (zeroed), through the
+// hash-grouped table over the QUERY hashes (launch_group_insert / launch_group_fill)
+void launch_stream_probe(const uint64_t *ih, const uint64_t *io, uint64_t b0, uint64_t bn, const uint32_t *part_off,
+                         uint64_t n_rows_total, uint32_t P, const uint32_t *filters, const unsigned long long *tkey,
+                         const uint64_t *toff, const uint32_t *grows, int log2_t, uint32_t *cmat, uint64_t ld, uint32_t *work_ctr /*zeroed*/,
+                         int sm_count, cudaStream_t st);
+
 // dense path for full num sketches: dense u32 ranks + fixed-length walk (join.cu)
 void launch_scatter_ranks(const uint64_t *keys, const uint64_t *vals, const uint64_t *pre, uint64_t n, uint32_t L,
                           uint64_t b_base, uint32_t *out, cudaStream_t st);

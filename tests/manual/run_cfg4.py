@@ -6,9 +6,10 @@ of one node.  Launch with torchrun (one process per GPU):
         tests/manual/run_cfg4.py --index 1000000
 
 Every rank holds N / world index sketches (sorted distinct random hashes <= max_hash) in HBM; each query is half the
-hashes of one index sketch plus fresh ones; the query batch is all-gathered, each rank runs smgpu_linear_find over its
-shard, hit lists are concatenated in rank order (= LinearIndex::find's insertion order).  Times are host wall clock
-around the search call, max over ranks."""
+hashes of one index sketch plus fresh ones; the query batch is all-gathered, then ONE library call per search
+(smgpu_linear_find_sharded: each rank searches its shard, the hit lists are exchanged over NCCL inside the library and
+concatenated in rank order = LinearIndex::find's insertion order).  Times are host wall clock around the search call,
+max over ranks; --local times the rank-local search (smgpu_linear_find) alone as well."""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
@@ -53,29 +54,43 @@ index = smb.SketchCollection.from_csr(idx.data_ptr(), offs_i.data_ptr(), per, 0,
 queries = smb.SketchCollection.from_csr(allq.data_ptr(), offs_q.data_ptr(), NQ, 0, 31, 42, MAX_HASH, on_device=True)
 del idx
 torch.cuda.empty_cache()
-times = []
-for rep in range(3):
+if world > 1:
+    smb.comm_init_from_torch()
+smb.profile_enable(True)
+times, local_times = [], []
+for rep in range(4):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    hits = smb.linear_find(index, queries, "containment", 0.1, hits_cap=64 * NQ)
+    hits = smb.linear_find_sharded(index, queries, "containment", 0.1, hits_cap=64 * NQ)   # global ids, every rank
     torch.cuda.synchronize(); times.append(time.perf_counter() - t0)
-t = torch.tensor([min(times[1:])], dtype=torch.float64, device=dev)
+    if rep == 0:
+        smb.profile_read("find_stream", reset=True)
+    if "--local" in sys.argv:
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        smb.linear_find(index, queries, "containment", 0.1, hits_cap=64 * NQ)
+        torch.cuda.synchronize(); local_times.append(time.perf_counter() - t0)
+kms, kn = smb.profile_read("find_stream", reset=True)
+t = torch.tensor([min(times[1:]), min(local_times[1:]) if local_times else 0.0, kms / max(1, kn)], dtype=torch.float64, device=dev)
 if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-# every query must be found by the rank that owns its source sketch, at the source's local row id
-own = all(int(src[j]) in hits[rank * qper + j] for j in range(qper))
-n_local = sum(len(h) for h in hits)
-stat = torch.tensor([n_local, int(own)], dtype=torch.int64, device=dev)
+# every query must be found at the GLOBAL row id of its source sketch (owner rank * per + local id)
+own = all((rank * per + int(src[j])) in hits[rank * qper + j] for j in range(qper))
+n_total = sum(len(h) for h in hits)
+stat = torch.tensor([n_total, int(own)], dtype=torch.int64, device=dev)
 mn = stat.clone()
 if world > 1:
-    dist.all_reduce(stat)
     dist.all_reduce(mn, op=dist.ReduceOp.MIN)
 if rank == 0:
-    sec = float(t.item())
+    sec, sec_local, k_ms = float(t[0].item()), float(t[1].item()), float(t[2].item())
+    shard_bytes = per * L * 8
     print(json.dumps({"workload": "cfg4: %d scaled=1000 queries x %d-sketch linear index (~%d hashes each), containment > 0.1" % (NQ, N, L),
-                      "n_gpus": world, "index_sketches_per_gpu": per, "index_bytes_per_gpu": per * L * 8,
-                      "search_ms": sec * 1e3, "pairs": N * NQ, "pairs_per_s": N * NQ / sec, "index_sketches_per_s": N / sec,
-                      "hits_total": int(stat[0].item()), "every_planted_source_found": bool(mn[1].item())}), flush=True)
+                      "n_gpus": world, "index_sketches_per_gpu": per, "index_bytes_per_gpu": shard_bytes,
+                      "search_ms": sec * 1e3, "local_search_ms": sec_local * 1e3 or None, "pairs": N * NQ, "pairs_per_s": N * NQ / sec,
+                      "index_sketches_per_s": N / sec,
+                      "stream_kernel_ms": k_ms or None, "stream_kernel_gbs": (shard_bytes / (k_ms * 1e-3) / 1e9) if k_ms else None,
+                      "whole_search_index_gbs_per_gpu": shard_bytes / sec / 1e9,
+                      "hits_total": int(stat[0].item()), "every_planted_source_found": bool(mn[1].item()),
+                      "find_path": os.environ.get("SMB200_FIND_PATH", "0")}), flush=True)
 if world > 1:
     dist.destroy_process_group()

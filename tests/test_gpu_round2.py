@@ -206,3 +206,69 @@ def test_concurrent_readers_of_one_handle():
         th.join()
     assert not errors, errors
     assert len(got) == 120 and all(x == want for x in got)
+
+
+# ------------------------------------------------------------------------------------------------
+# linear_find over a large index: the streaming path (csrc/find_stream.cu) against the oracle and the join path
+# ------------------------------------------------------------------------------------------------
+def _index_and_queries(n_index, n_q, lens, mx, num, seed, dup_queries=True):
+    r = np.random.Generator(np.random.PCG64(seed))
+    hi = mx if mx else 1 << 60
+    base = [np.unique(r.integers(0, hi, size=lens[1], dtype=np.uint64)) for _ in range(max(2, n_index // 20))]
+    rows = []
+    for i in range(n_index):
+        b = base[i % len(base)]
+        keep = b[r.random(b.size) < (0.05, 0.3, 0.6, 0.95)[i % 4]]
+        row = np.unique(np.concatenate([keep, r.integers(0, hi, size=int(r.integers(lens[0], lens[1])), dtype=np.uint64)]))
+        rows.append(row[:num] if num else row)
+    rows[1] = rows[1][:0]                      # an empty index sketch (containment 0/0 = NaN: never a hit)
+    rows[2] = rows[2][:3]
+    queries = []
+    for q in range(n_q):
+        row = np.unique(np.concatenate([base[q % len(base)][::2], r.integers(0, hi, size=int(r.integers(1, lens[1])), dtype=np.uint64)]))
+        queries.append(row[:num] if num else row)
+    if dup_queries and n_q > 3:
+        queries[3] = queries[0].copy()         # the same hashes in two queries: table runs longer than one
+        queries[2] = queries[2][:0]            # an empty query
+    return rows, queries
+
+
+def _colls(rows, num, mx):
+    g, o = [], []
+    for row in rows:
+        a, b = smb.KmerMinHash(num, 31, False, 42, mx), orc.KmerMinHash(num, 31, False, 42, mx)
+        a.set_mins(row); b.add_many(row)
+        g.append(a); o.append(b)
+    return smb.SketchCollection.from_sketches(g), o
+
+
+@pytest.mark.parametrize("n_index,n_q,lens,mx,num", [
+    (300, 12, (50, 2500), MAX_HASH_1000 * 4, 0),        # ragged scaled sketches, few slices
+    (150, 9, (7000, 9000), MAX_HASH_1000 * 8, 0),       # long sketches: 64 slices, stretches above and below 96 hashes
+    (5000, 6, (100, 400), MAX_HASH_1000, 0),            # more rows than one chunk of a work item
+    (400, 10, (300, 900), 0, 500),                      # num sketches (containment only decides by count)
+    (40, 40, (5, 60), MAX_HASH_1000, 0),                # tiny rows, as many queries as index sketches
+])
+def test_linear_find_streaming_path(n_index, n_q, lens, mx, num):
+    rows, queries = _index_and_queries(n_index, n_q, lens, mx, num, 1000 + n_index)
+    ic, o_index = _colls(rows, num, mx)
+    qc, o_queries = _colls(queries, num, mx)
+    try:
+        for mode in ("containment", "similarity"):
+            for thr in (0.0, 0.1, 0.6):
+                smb.find_path("join")
+                want = smb.linear_find(ic, qc, mode, thr)
+                smb.find_path("stream")
+                got = smb.linear_find(ic, qc, mode, thr)
+                assert got == want, (mode, thr)
+                for q in range(0, n_q, max(1, n_q // 4)):
+                    assert got[q] == orc.linear_find(o_index, o_queries[q], mode, thr), (mode, thr, q)
+        assert any(len(h) for h in got)
+        # the index changes: the slice bounds kept with it are rebuilt
+        extra = smb.KmerMinHash(num, 31, False, 42, mx)
+        extra.set_mins(queries[0])
+        ic.push(extra)
+        got = smb.linear_find(ic, qc, "containment", 0.5)
+        assert n_index in got[0] and (len(queries[3]) == 0 or n_index in got[3])
+    finally:
+        smb.find_path("auto")
