@@ -14,8 +14,9 @@
 //   * a CTA takes a (slice, chunk of index rows) work item, holds that slice's filter in shared memory and streams
 //     the rows' stretches past it with coalesced loads: per index hash one multiply, two shared-memory reads;
 //   * only the hashes the filter lets through (true hits + ~2 % false positives) go to the exact table in global
-//     memory (the hash-grouped table over the queries, join.cu) and add to the count matrix, one atomic per
-//     (row, query) per warp step.
+//     memory (the hash-grouped table over the queries, join.cu) and add to the count matrix.  They are parked in a
+//     shared-memory queue and resolved a thousand at a time between work items, so that the streaming loop never
+//     waits for an off-chip table read (with the lookup inline, half of all warp steps stalled on one: 566 GB/s).
 #include <algorithm>
 
 #include "device.hpp"
@@ -28,7 +29,7 @@ namespace {
 constexpr int FS_THREADS = 1024;
 constexpr int FS_LOG2_F = 20;                              // filter bits per slice
 constexpr uint32_t FS_FILTER_WORDS = (1u << FS_LOG2_F) / 32;
-constexpr uint32_t FS_CHUNK_ROWS = 4096;                   // index rows per work item
+constexpr uint32_t FS_CHUNK_ROWS = 2048;                   // index rows per work item
 constexpr unsigned long long FS_MUL = 0xD6E8FEB86659FD93ull;
 constexpr unsigned long long FS_EMPTY = ~0ull;
 
@@ -105,10 +106,11 @@ struct StreamArgs {
     uint32_t *work_ctr;            // zeroed
 };
 
-// exact lookup of the hashes the filter let through + count matrix update; the whole warp comes here together
-__device__ __forceinline__ void stream_hits(const StreamArgs &a, bool hit, uint64_t h, uint64_t row) {
+// Exact lookup of one hash the filter let through + count matrix update.  Called by all 32 lanes of a warp (lanes
+// without an entry pass have = false); lanes that reach the same (row, query) cell add once.
+__device__ __forceinline__ void stream_resolve(const StreamArgs &a, bool have, uint64_t h, uint64_t row) {
     uint64_t jb = 0, je = 0;
-    if (hit) {
+    if (have) {
         const uint64_t T = 1ull << a.log2_t;
         uint64_t s = (h * 0x9E3779B97F4A7C15ull) >> (64 - a.log2_t);
         if (h == FS_EMPTY) {
@@ -123,28 +125,58 @@ __device__ __forceinline__ void stream_hits(const StreamArgs &a, bool hit, uint6
         }
         if (s != ~0ull) { jb = __ldg(&a.toff[s]); je = __ldg(&a.toff[s + 1]); }
     }
-    // first query of each run: lanes that hit the same (row, query) cell add once
-    const bool have = je > jb;
-    const uint64_t cell = have ? row * a.ld + __ldg(&a.grows[jb]) : (~0ull - (threadIdx.x & 31));
+    const bool found = je > jb;
+    const uint64_t cell = found ? row * a.ld + __ldg(&a.grows[jb]) : (~0ull - (threadIdx.x & 31));
     const unsigned peers = __match_any_sync(0xFFFFFFFFu, cell);
-    if (have) {
+    if (found) {
         if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&a.cmat[cell], (uint32_t)__popc(peers));
         for (uint64_t j = jb + 1; j < je; j++) atomicAdd(&a.cmat[row * a.ld + __ldg(&a.grows[j])], 1u);  // hash shared by several queries
     }
 }
 
+// The streaming loop never waits for the exact table: a hash the filter lets through is parked, with its row, in a
+// shared-memory queue; the CTA empties the queue between work items, one entry per thread, so that the (dependent,
+// off-chip) table reads of a thousand entries are in flight together.  A full queue sends the warp to the table at once.
+constexpr uint32_t FS_QUEUE = 4096;   // entries (hash u64 + row u32): 48 KB beside the 128 KB filter
+
+__device__ __forceinline__ void stream_park(const StreamArgs &a, bool hit, uint64_t h, uint32_t row, uint64_t *q_hash, uint32_t *q_row,
+                                            uint32_t *q_n) {
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(q_n, (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+    const uint32_t at = base + __popc(m & ((1u << lane) - 1));
+    const bool fits = hit && at < FS_QUEUE;
+    if (fits) { q_hash[at] = h; q_row[at] = row; }
+    if (__any_sync(0xFFFFFFFFu, hit && !fits)) stream_resolve(a, hit && !fits, h, row);
+}
+
 __global__ void __launch_bounds__(FS_THREADS, 1) stream_probe_kernel(const StreamArgs a) {
-    extern __shared__ __align__(16) uint32_t s_filter[];
-    __shared__ uint32_t s_item;
+    extern __shared__ __align__(16) uint32_t s_mem[];
+    uint32_t *s_filter = s_mem;
+    uint64_t *q_hash = reinterpret_cast<uint64_t *>(s_mem + FS_FILTER_WORDS);
+    uint32_t *q_row = reinterpret_cast<uint32_t *>(q_hash + FS_QUEUE);
+    __shared__ uint32_t s_item, s_qn;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n_chunks = (uint32_t)((a.bn + FS_CHUNK_ROWS - 1) / FS_CHUNK_ROWS);
     const uint32_t n_items = a.P * n_chunks;
     uint32_t cur_p = ~0u;
+    if (threadIdx.x == 0) s_qn = 0;
     for (;;) {
         if (threadIdx.x == 0) s_item = atomicAdd(a.work_ctr, 1u);
-        __syncthreads();            // (also: every warp is done with the previous item's filter)
+        __syncthreads();            // (also: every warp is done streaming the previous item)
         const uint32_t item = s_item;
+        // empty the queue of the previous item: one entry per thread
+        const uint32_t n_q = min(s_qn, FS_QUEUE);
+        for (uint32_t i0 = 0; i0 < n_q; i0 += FS_THREADS) {   // CTA-uniform bounds
+            const uint32_t i = i0 + threadIdx.x;
+            const bool have = i < n_q;
+            stream_resolve(a, have, have ? q_hash[i] : 0, have ? q_row[i] : 0);
+        }
         __syncthreads();
+        if (threadIdx.x == 0) s_qn = 0;
         if (item >= n_items) break;
         const uint32_t p = item / n_chunks, chunk = item - p * n_chunks;   // slice-major: neighbours share a filter in L2
         if (p != cur_p) {
@@ -152,8 +184,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) stream_probe_kernel(const Strea
             uint4 *dst = reinterpret_cast<uint4 *>(s_filter);
             for (uint32_t i = threadIdx.x; i < FS_FILTER_WORDS / 4; i += FS_THREADS) dst[i] = __ldg(src + i);
             cur_p = p;
-            __syncthreads();
         }
+        __syncthreads();
         const uint64_t row_lo = (uint64_t)chunk * FS_CHUNK_ROWS, row_hi = min(a.bn, row_lo + FS_CHUNK_ROWS);
         const uint32_t *po_lo = a.part_off + (uint64_t)p * a.n_rows_total + a.b0;
         const uint32_t *po_hi = po_lo + a.n_rows_total;
@@ -186,20 +218,20 @@ __global__ void __launch_bounds__(FS_THREADS, 1) stream_probe_kernel(const Strea
                     uint32_t b1, b2;
                     filter_bits(h[u], b1, b2);
                     const bool hit = in[u] && ((s_filter[b1 >> 5] >> (b1 & 31)) & (s_filter[b2 >> 5] >> (b2 & 31)) & 1u);
-                    if (__any_sync(0xFFFFFFFFu, hit)) stream_hits(a, hit, h[u], g + (u < 3 ? k : k1));
+                    stream_park(a, hit, h[u], (uint32_t)(g + (u < 3 ? k : k1)), q_hash, q_row, &s_qn);
                 }
                 // stretches longer than 96 hashes: the rest, one load at a time
                 for (int side = 0; side < 2; side++) {
                     const uint64_t *seg = side ? seg1 : seg0;
                     const uint32_t ee = side ? e1 : e0;
-                    const uint64_t row = g + (side ? k1 : k);
+                    const uint32_t row = (uint32_t)(g + (side ? k1 : k));
                     for (uint32_t i = (side ? s1 : s0) + 96; i < ee; i += 32) {   // warp-uniform bounds
                         const bool inb = i + lane < ee;
                         const uint64_t hh = inb ? __ldcs(seg + i + lane) : 0;
                         uint32_t b1, b2;
                         filter_bits(hh, b1, b2);
                         const bool hit = inb && ((s_filter[b1 >> 5] >> (b1 & 31)) & (s_filter[b2 >> 5] >> (b2 & 31)) & 1u);
-                        if (__any_sync(0xFFFFFFFFu, hit)) stream_hits(a, hit, hh, row);
+                        stream_park(a, hit, hh, row, q_hash, q_row, &s_qn);
                     }
                 }
             }
@@ -241,7 +273,7 @@ void launch_stream_probe(const uint64_t *ih, const uint64_t *io, uint64_t b0, ui
                          int sm_count, cudaStream_t st) {
     if (!bn) return;
     static bool attr_set = false;
-    const size_t smem = (size_t)FS_FILTER_WORDS * 4;
+    const size_t smem = (size_t)FS_FILTER_WORDS * 4 + (size_t)FS_QUEUE * 12;
     if (!attr_set) {
         SM_CUDA(cudaFuncSetAttribute(stream_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
