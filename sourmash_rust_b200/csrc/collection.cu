@@ -40,11 +40,10 @@ void SketchCollection::ensure_partitions() {
     SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_TMAX), 0, 8, ctx.stream));
     launch_rows_max(d_hashes.as<uint64_t>(), d_offsets.as<uint64_t>(), n_rows, ctx.dsc(SC_TMAX), ctx.stream);
     ctx.read_scalars();
-    const uint64_t top = ctx.h_scalars[SC_TMAX];
-    part_shift = 0;
-    while (part_shift < 63 && (top >> part_shift) >= n_parts) part_shift++;   // n_parts << part_shift > top
+    part_top = ctx.h_scalars[SC_TMAX];
+    part_scale = find_stream_scale(part_top, n_parts);
     d_part_off.reserve((size_t)(n_parts + 1) * std::max<uint64_t>(1, n_rows) * 4);
-    launch_part_offsets(d_hashes.as<uint64_t>(), d_offsets.as<uint64_t>(), n_rows, part_shift, n_parts, d_part_off.as<uint32_t>(),
+    launch_part_offsets(d_hashes.as<uint64_t>(), d_offsets.as<uint64_t>(), n_rows, part_scale, n_parts, d_part_off.as<uint32_t>(),
                         ctx.stream);
     ctx.sync();
     parts_valid = true;
@@ -535,8 +534,8 @@ std::vector<std::vector<uint64_t>> linear_find_lists(SketchCollection &index, Sk
                     join_table_build(ctx, qt, queries.d_hashes.as<uint64_t>(), queries.d_offsets.as<uint64_t>(), 0, nq, queries.n_hashes, false);
                     ctx.misc[6].reserve(find_stream_filter_bytes(index.n_parts) + 256);
                     SM_CUDA(cudaMemsetAsync(ctx.misc[6].p, 0, find_stream_filter_bytes(index.n_parts), st));
-                    launch_filters_build(queries.d_hashes.as<uint64_t>(), queries.n_hashes, index.part_shift, index.n_parts,
-                                         ctx.misc[6].as<uint32_t>(), st);
+                    launch_filters_build(queries.d_hashes.as<uint64_t>(), queries.n_hashes, index.part_scale, index.part_top,
+                                         index.n_parts, ctx.misc[6].as<uint32_t>(), st);
                 }
                 SM_CUDA(cudaMemsetAsync(cmat, 0, bn * nq * 4, st));
                 SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_FLAG), 0, 8, st));

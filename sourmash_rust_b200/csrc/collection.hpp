@@ -27,11 +27,11 @@ struct SketchCollection {
     // compare path bookkeeping (collection.cu): has a block with these rows gone through the probe form of
     // the join yet, and did it find so many incidences that the dense kernels are the better choice
     bool probe_checked = false, probe_dense_preferred = false;
-    // find_stream.cu: where each (sorted) row meets each of n_parts equal slices of the hash range [0, n_parts << part_shift);
+    // find_stream.cu: where each (sorted) row meets each of n_parts equal slices of the hash range [0, part_top];
     // built on the first large search over this collection, kept until it changes
     DevBuf d_part_off;
     uint32_t n_parts = 0;
-    int part_shift = 0;
+    uint64_t part_top = 0, part_scale = 0;
     bool parts_valid = false;
     void ensure_partitions();
     std::mutex mu;      // as KmerMinHash::mu

@@ -10,13 +10,13 @@
 //   * the hash range is cut into P equal slices ("partitions"); a sorted sketch meets slice p in ONE contiguous
 //     stretch, whose bounds are kept with the index (part_offsets, built once per collection in one pass);
 //   * per slice, the query hashes that fall into it go into a Bloom filter of 2^20 bits (two probes): 128 KB,
-//     which fits the shared memory of an SM;
+//     which fits the shared memory of an SM (three probes: ~1 % false positives at 78 K keys per slice);
 //   * a CTA takes a (slice, chunk of index rows) work item, holds that slice's filter in shared memory and streams
 //     the rows' stretches past it with coalesced loads: per index hash one multiply, two shared-memory reads;
 //   * only the hashes the filter lets through (true hits + ~2 % false positives) go to the exact table in global
-//     memory (the hash-grouped table over the queries, join.cu) and add to the count matrix.  They are parked in a
-//     shared-memory queue and resolved a thousand at a time between work items, so that the streaming loop never
-//     waits for an off-chip table read (with the lookup inline, half of all warp steps stalled on one: 566 GB/s).
+//     memory (the hash-grouped table over the queries, join.cu) and add to the count matrix.  They are parked in the
+//     warp's shared-memory queue and resolved 32 at a time when it fills, so that a warp step does not wait for an
+//     off-chip table read (with the lookup inline, half of all warp steps stalled on one: 566 GB/s).
 #include <algorithm>
 
 #include "device.hpp"
@@ -33,10 +33,23 @@ constexpr uint32_t FS_CHUNK_ROWS = 2048;                   // index rows per wor
 constexpr unsigned long long FS_MUL = 0xD6E8FEB86659FD93ull;
 constexpr unsigned long long FS_EMPTY = ~0ull;
 
-__device__ __forceinline__ void filter_bits(uint64_t h, uint32_t &b1, uint32_t &b2) {
+// three filter bits per hash, from one 64-bit multiply
+__device__ __forceinline__ void filter_bits(uint64_t h, uint32_t &b1, uint32_t &b2, uint32_t &b3) {
     const uint64_t m = h * FS_MUL;
     b1 = (uint32_t)(m >> (64 - FS_LOG2_F));
     b2 = (uint32_t)(m >> (64 - 2 * FS_LOG2_F)) & ((1u << FS_LOG2_F) - 1);
+    b3 = (uint32_t)(m >> (64 - 3 * FS_LOG2_F)) & ((1u << FS_LOG2_F) - 1);
+}
+__device__ __forceinline__ bool filter_test(const uint32_t *f, uint64_t h) {
+    uint32_t b1, b2, b3;
+    filter_bits(h, b1, b2, b3);
+    return ((f[b1 >> 5] >> (b1 & 31)) & (f[b2 >> 5] >> (b2 & 31)) & (f[b3 >> 5] >> (b3 & 31)) & 1u) != 0;
+}
+// slice of the hash range a hash falls into: monotone in h, P - 1 for the largest hash of the index
+// (scale = floor(2^64 * P / (top + 1)), saturated)
+__device__ __forceinline__ uint32_t slice_of(uint64_t h, uint64_t scale, uint32_t P) {
+    const unsigned long long q = __umul64hi((unsigned long long)h, (unsigned long long)scale);
+    return q < (unsigned long long)(P - 1) ? (uint32_t)q : P - 1;
 }
 
 // largest hash of the collection (rows are sorted: the last element of each)
@@ -55,38 +68,38 @@ __global__ void rows_max_kernel(const uint64_t *__restrict__ h, const uint64_t *
 // part_off[q * n_rows + r] = number of hashes of row r below slice q (q = 0 .. P): slice p of row r is
 // [part_off[p], part_off[p + 1]).  One warp per row, one pass over its hashes.
 __global__ void __launch_bounds__(256) part_offsets_kernel(const uint64_t *__restrict__ h, const uint64_t *__restrict__ off,
-                                                           uint64_t n_rows, int shift, uint32_t P, uint32_t *__restrict__ part_off) {
+                                                           uint64_t n_rows, uint64_t scale, uint32_t P, uint32_t *__restrict__ part_off) {
     const int lane = threadIdx.x & 31;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rows; r += warps) {
         const uint64_t b = off[r], e = off[r + 1];
         const uint32_t len = (uint32_t)(e - b);
         for (uint32_t i = lane; i < len; i += 32) {
-            const int64_t cur = (int64_t)min((uint64_t)(P - 1), h[b + i] >> shift);
-            const int64_t prev = i ? (int64_t)min((uint64_t)(P - 1), h[b + i - 1] >> shift) : -1;
+            const int64_t cur = slice_of(h[b + i], scale, P);
+            const int64_t prev = i ? (int64_t)slice_of(h[b + i - 1], scale, P) : -1;
             for (int64_t q = prev + 1; q <= cur; q++) part_off[(uint64_t)q * n_rows + r] = i;
         }
         if (lane == 0) {
-            const int64_t last = len ? (int64_t)min((uint64_t)(P - 1), h[e - 1] >> shift) : -1;
+            const int64_t last = len ? (int64_t)slice_of(h[e - 1], scale, P) : -1;
             for (int64_t q = last + 1; q <= (int64_t)P; q++) part_off[(uint64_t)q * n_rows + r] = len;
         }
     }
 }
 
 // Bloom filters of the query hashes, one per slice (global memory; the probe kernel copies a slice's filter into
-// shared memory).  Query hashes at or beyond P << shift cannot occur in the index: skipped.
-__global__ void __launch_bounds__(256) filters_build_kernel(const uint64_t *__restrict__ qh, uint64_t n, int shift, uint32_t P,
-                                                            uint32_t *filters) {
+// shared memory).  Query hashes above the largest hash of the index cannot occur in it: skipped.
+__global__ void __launch_bounds__(256) filters_build_kernel(const uint64_t *__restrict__ qh, uint64_t n, uint64_t scale, uint64_t top,
+                                                            uint32_t P, uint32_t *filters) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint64_t h = qh[i];
-        const uint64_t p = h >> shift;
-        if (p >= P) continue;
-        uint32_t b1, b2;
-        filter_bits(h, b1, b2);
-        uint32_t *f = filters + p * FS_FILTER_WORDS;
+        if (h > top) continue;
+        uint32_t b1, b2, b3;
+        filter_bits(h, b1, b2, b3);
+        uint32_t *f = filters + (size_t)slice_of(h, scale, P) * FS_FILTER_WORDS;
         atomicOr(&f[b1 >> 5], 1u << (b1 & 31));
         atomicOr(&f[b2 >> 5], 1u << (b2 & 31));
+        atomicOr(&f[b3 >> 5], 1u << (b3 & 31));
     }
 }
 
@@ -134,49 +147,50 @@ __device__ __forceinline__ void stream_resolve(const StreamArgs &a, bool have, u
     }
 }
 
-// The streaming loop never waits for the exact table: a hash the filter lets through is parked, with its row, in a
-// shared-memory queue; the CTA empties the queue between work items, one entry per thread, so that the (dependent,
-// off-chip) table reads of a thousand entries are in flight together.  A full queue sends the warp to the table at once.
-constexpr uint32_t FS_QUEUE = 4096;   // entries (hash u64 + row u32): 48 KB beside the 128 KB filter
+// The streaming loop does not wait for the exact table: a hash the filter lets through is parked, with its row, in
+// the warp's own shared-memory queue; when the queue is nearly full the warp resolves it, 32 entries per step, while
+// the other warps of the CTA keep streaming.
+constexpr uint32_t FS_QUEUE = 192;    // entries per warp (hash u64 + row u32): 32 x 192 x 12 B = 72 KB beside the 128 KB filter
 
-__device__ __forceinline__ void stream_park(const StreamArgs &a, bool hit, uint64_t h, uint32_t row, uint64_t *q_hash, uint32_t *q_row,
-                                            uint32_t *q_n) {
+__device__ __forceinline__ void queue_drain(const StreamArgs &a, const uint64_t *q_hash, const uint32_t *q_row, uint32_t &cnt) {
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+    for (uint32_t i0 = 0; i0 < cnt; i0 += 32) {   // warp-uniform
+        const bool have = i0 + lane < cnt;
+        stream_resolve(a, have, have ? q_hash[i0 + lane] : 0, have ? q_row[i0 + lane] : 0);
+    }
+    __syncwarp();
+    cnt = 0;
+}
+__device__ __forceinline__ void queue_push(const StreamArgs &a, bool hit, uint64_t h, uint32_t row, uint64_t *q_hash, uint32_t *q_row,
+                                           uint32_t &cnt) {
     const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
     if (!m) return;
-    const int lane = threadIdx.x & 31;
-    uint32_t base = 0;
-    if (lane == __ffs(m) - 1) base = atomicAdd(q_n, (uint32_t)__popc(m));
-    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
-    const uint32_t at = base + __popc(m & ((1u << lane) - 1));
-    const bool fits = hit && at < FS_QUEUE;
-    if (fits) { q_hash[at] = h; q_row[at] = row; }
-    if (__any_sync(0xFFFFFFFFu, hit && !fits)) stream_resolve(a, hit && !fits, h, row);
+    if (hit) {
+        const uint32_t at = cnt + __popc(m & ((1u << (threadIdx.x & 31)) - 1));
+        q_hash[at] = h;
+        q_row[at] = row;
+    }
+    cnt += __popc(m);
+    if (cnt > FS_QUEUE - 32) queue_drain(a, q_hash, q_row, cnt);
 }
 
 __global__ void __launch_bounds__(FS_THREADS, 1) stream_probe_kernel(const StreamArgs a) {
     extern __shared__ __align__(16) uint32_t s_mem[];
     uint32_t *s_filter = s_mem;
-    uint64_t *q_hash = reinterpret_cast<uint64_t *>(s_mem + FS_FILTER_WORDS);
-    uint32_t *q_row = reinterpret_cast<uint32_t *>(q_hash + FS_QUEUE);
-    __shared__ uint32_t s_item, s_qn;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t *q_hash = reinterpret_cast<uint64_t *>(s_mem + FS_FILTER_WORDS) + (size_t)warp * FS_QUEUE;
+    uint32_t *q_row = reinterpret_cast<uint32_t *>(reinterpret_cast<uint64_t *>(s_mem + FS_FILTER_WORDS) + (size_t)(FS_THREADS / 32) * FS_QUEUE) +
+                      (size_t)warp * FS_QUEUE;
+    __shared__ uint32_t s_item;
     const uint32_t n_chunks = (uint32_t)((a.bn + FS_CHUNK_ROWS - 1) / FS_CHUNK_ROWS);
     const uint32_t n_items = a.P * n_chunks;
-    uint32_t cur_p = ~0u;
-    if (threadIdx.x == 0) s_qn = 0;
+    uint32_t cur_p = ~0u, q_cnt = 0;
     for (;;) {
         if (threadIdx.x == 0) s_item = atomicAdd(a.work_ctr, 1u);
-        __syncthreads();            // (also: every warp is done streaming the previous item)
+        __syncthreads();            // (also: every warp is done with the previous item's filter)
         const uint32_t item = s_item;
-        // empty the queue of the previous item: one entry per thread
-        const uint32_t n_q = min(s_qn, FS_QUEUE);
-        for (uint32_t i0 = 0; i0 < n_q; i0 += FS_THREADS) {   // CTA-uniform bounds
-            const uint32_t i = i0 + threadIdx.x;
-            const bool have = i < n_q;
-            stream_resolve(a, have, have ? q_hash[i] : 0, have ? q_row[i] : 0);
-        }
         __syncthreads();
-        if (threadIdx.x == 0) s_qn = 0;
         if (item >= n_items) break;
         const uint32_t p = item / n_chunks, chunk = item - p * n_chunks;   // slice-major: neighbours share a filter in L2
         if (p != cur_p) {
@@ -184,8 +198,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) stream_probe_kernel(const Strea
             uint4 *dst = reinterpret_cast<uint4 *>(s_filter);
             for (uint32_t i = threadIdx.x; i < FS_FILTER_WORDS / 4; i += FS_THREADS) dst[i] = __ldg(src + i);
             cur_p = p;
+            __syncthreads();
         }
-        __syncthreads();
         const uint64_t row_lo = (uint64_t)chunk * FS_CHUNK_ROWS, row_hi = min(a.bn, row_lo + FS_CHUNK_ROWS);
         const uint32_t *po_lo = a.part_off + (uint64_t)p * a.n_rows_total + a.b0;
         const uint32_t *po_hi = po_lo + a.n_rows_total;
@@ -214,12 +228,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) stream_probe_kernel(const Strea
                     h[3 + u] = in[3 + u] ? __ldcs(seg1 + i1) : 0;
                 }
 #pragma unroll
-                for (int u = 0; u < 6; u++) {
-                    uint32_t b1, b2;
-                    filter_bits(h[u], b1, b2);
-                    const bool hit = in[u] && ((s_filter[b1 >> 5] >> (b1 & 31)) & (s_filter[b2 >> 5] >> (b2 & 31)) & 1u);
-                    stream_park(a, hit, h[u], (uint32_t)(g + (u < 3 ? k : k1)), q_hash, q_row, &s_qn);
-                }
+                for (int u = 0; u < 6; u++)
+                    queue_push(a, in[u] && filter_test(s_filter, h[u]), h[u], (uint32_t)(g + (u < 3 ? k : k1)), q_hash, q_row, q_cnt);
                 // stretches longer than 96 hashes: the rest, one load at a time
                 for (int side = 0; side < 2; side++) {
                     const uint64_t *seg = side ? seg1 : seg0;
@@ -228,15 +238,13 @@ __global__ void __launch_bounds__(FS_THREADS, 1) stream_probe_kernel(const Strea
                     for (uint32_t i = (side ? s1 : s0) + 96; i < ee; i += 32) {   // warp-uniform bounds
                         const bool inb = i + lane < ee;
                         const uint64_t hh = inb ? __ldcs(seg + i + lane) : 0;
-                        uint32_t b1, b2;
-                        filter_bits(hh, b1, b2);
-                        const bool hit = inb && ((s_filter[b1 >> 5] >> (b1 & 31)) & (s_filter[b2 >> 5] >> (b2 & 31)) & 1u);
-                        stream_park(a, hit, hh, row, q_hash, q_row, &s_qn);
+                        queue_push(a, inb && filter_test(s_filter, hh), hh, row, q_hash, q_row, q_cnt);
                     }
                 }
             }
         }
     }
+    queue_drain(a, q_hash, q_row, q_cnt);
 }
 
 }  // namespace
@@ -255,16 +263,20 @@ void launch_rows_max(const uint64_t *h, const uint64_t *off, uint64_t n_rows, un
     rows_max_kernel<<<(unsigned)std::min<uint64_t>((n_rows + 255) / 256, 148 * 8), 256, 0, st>>>(h, off, n_rows, out);
     SM_LAUNCHED();
 }
-void launch_part_offsets(const uint64_t *h, const uint64_t *off, uint64_t n_rows, int shift, uint32_t P, uint32_t *part_off,
+uint64_t find_stream_scale(uint64_t top, uint32_t P) {
+    const unsigned __int128 q = (((unsigned __int128)P) << 64) / ((unsigned __int128)top + 1);
+    return q > (unsigned __int128)~0ull ? ~0ull : (uint64_t)q;
+}
+void launch_part_offsets(const uint64_t *h, const uint64_t *off, uint64_t n_rows, uint64_t scale, uint32_t P, uint32_t *part_off,
                          cudaStream_t st) {
     if (!n_rows) return;
-    part_offsets_kernel<<<(unsigned)std::min<uint64_t>((n_rows * 32 + 255) / 256, 148 * 16), 256, 0, st>>>(h, off, n_rows, shift, P, part_off);
+    part_offsets_kernel<<<(unsigned)std::min<uint64_t>((n_rows * 32 + 255) / 256, 148 * 16), 256, 0, st>>>(h, off, n_rows, scale, P, part_off);
     SM_LAUNCHED();
 }
 size_t find_stream_filter_bytes(uint32_t P) { return (size_t)P * FS_FILTER_WORDS * 4; }
-void launch_filters_build(const uint64_t *qh, uint64_t n, int shift, uint32_t P, uint32_t *filters, cudaStream_t st) {
+void launch_filters_build(const uint64_t *qh, uint64_t n, uint64_t scale, uint64_t top, uint32_t P, uint32_t *filters, cudaStream_t st) {
     if (!n) return;
-    filters_build_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(qh, n, shift, P, filters);
+    filters_build_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(qh, n, scale, top, P, filters);
     SM_LAUNCHED();
 }
 void launch_stream_probe(const uint64_t *ih, const uint64_t *io, uint64_t b0, uint64_t bn, const uint32_t *part_off,
@@ -273,7 +285,7 @@ void launch_stream_probe(const uint64_t *ih, const uint64_t *io, uint64_t b0, ui
                          int sm_count, cudaStream_t st) {
     if (!bn) return;
     static bool attr_set = false;
-    const size_t smem = (size_t)FS_FILTER_WORDS * 4 + (size_t)FS_QUEUE * 12;
+    const size_t smem = (size_t)FS_FILTER_WORDS * 4 + (size_t)(FS_THREADS / 32) * FS_QUEUE * 12;
     if (!attr_set) {
         SM_CUDA(cudaFuncSetAttribute(stream_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;

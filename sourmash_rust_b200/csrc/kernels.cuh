@@ -209,10 +209,13 @@ void launch_walk_pairs(const uint64_t *pairs, uint64_t n_pairs, const uint64_t *
 uint32_t find_stream_partitions(uint64_t n_rows, uint64_t n_hashes);   // slices of the hash range (power of two, <= 64)
 void launch_rows_max(const uint64_t *h, const uint64_t *off, uint64_t n_rows, unsigned long long *out /*zeroed*/, cudaStream_t st);
 // part_off: (P + 1) x n_rows u32, slice-major: row r meets slice p in [part_off[p][r], part_off[p + 1][r])
-void launch_part_offsets(const uint64_t *h, const uint64_t *off, uint64_t n_rows, int shift, uint32_t P, uint32_t *part_off,
+// slice of h = min(P - 1, mulhi(h, scale)), scale = floor(2^64 * P / (top + 1)): monotone, so a sorted row meets a slice in one stretch
+uint64_t find_stream_scale(uint64_t top, uint32_t P);
+void launch_part_offsets(const uint64_t *h, const uint64_t *off, uint64_t n_rows, uint64_t scale, uint32_t P, uint32_t *part_off,
                          cudaStream_t st);
 size_t find_stream_filter_bytes(uint32_t P);
-void launch_filters_build(const uint64_t *qh, uint64_t n, int shift, uint32_t P, uint32_t *filters /*zeroed*/, cudaStream_t st);
+void launch_filters_build(const uint64_t *qh, uint64_t n, uint64_t scale, uint64_t top, uint32_t P, uint32_t *filters /*zeroed*/,
+                          cudaStream_t st);
 // counts of shared hashes of index rows [b0, b0 + bn) x queries into cmat[(row - b0) * ld + query] (zeroed), through the
 // hash-grouped table over the QUERY hashes (launch_group_insert / launch_group_fill)
 void launch_stream_probe(const uint64_t *ih, const uint64_t *io, uint64_t b0, uint64_t bn, const uint32_t *part_off,
