@@ -36,7 +36,7 @@ void SketchCollection::ensure_partitions() {
     finalize();
     if (parts_valid) return;
     Context &ctx = Context::get();
-    n_parts = find_stream_partitions(n_rows, n_hashes);
+    n_parts = find_stream_partitions(n_rows, n_hashes, ctx.sm_count);
     SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_TMAX), 0, 8, ctx.stream));
     launch_rows_max(d_hashes.as<uint64_t>(), d_offsets.as<uint64_t>(), n_rows, ctx.dsc(SC_TMAX), ctx.stream);
     ctx.read_scalars();
@@ -532,17 +532,18 @@ std::vector<std::vector<uint64_t>> linear_find_lists(SketchCollection &index, Sk
                 // the index streams past per-slice Bloom filters of the query hashes held in shared memory (find_stream.cu)
                 if (b0 == 0) {   // the query side: exact table + filters, once per search
                     join_table_build(ctx, qt, queries.d_hashes.as<uint64_t>(), queries.d_offsets.as<uint64_t>(), 0, nq, queries.n_hashes, false);
-                    ctx.misc[6].reserve(find_stream_filter_bytes(index.n_parts) + 256);
+                    ctx.misc[6].reserve(find_stream_filter_bytes(index.n_parts) + (size_t)index.n_parts * 4 + 256);
                     SM_CUDA(cudaMemsetAsync(ctx.misc[6].p, 0, find_stream_filter_bytes(index.n_parts), st));
                     launch_filters_build(queries.d_hashes.as<uint64_t>(), queries.n_hashes, index.part_scale, index.part_top,
                                          index.n_parts, ctx.misc[6].as<uint32_t>(), st);
                 }
                 SM_CUDA(cudaMemsetAsync(cmat, 0, bn * nq * 4, st));
-                SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_FLAG), 0, 8, st));
+                uint32_t *work_ctr = ctx.misc[6].as<uint32_t>() + find_stream_filter_bytes(index.n_parts) / 4;  // behind the filters
+                SM_CUDA(cudaMemsetAsync(work_ctr, 0, (size_t)index.n_parts * 4, st));
                 launch_stream_probe(index.d_hashes.as<uint64_t>(), index.d_offsets.as<uint64_t>(), b0, bn, index.d_part_off.as<uint32_t>(),
                                     index.n_rows, index.n_parts, ctx.misc[6].as<uint32_t>(), ctx.join[0].as<unsigned long long>(),
                                     ctx.sort_tmp_k.as<uint64_t>(), ctx.join[7].as<uint32_t>(), qt.log2_t, cmat, nq,
-                                    reinterpret_cast<uint32_t *>(ctx.dsc(SC_FLAG)), ctx.sm_count, st);
+                                    work_ctr, ctx.sm_count, st);
             } else {
                 compare_block_device(index, b0, bn, queries, 0, nq, 1, cmat, nullptr, nullptr, nq);
             }

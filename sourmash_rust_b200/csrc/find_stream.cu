@@ -10,9 +10,10 @@
 //   * the hash range is cut into P equal slices ("partitions"); a sorted sketch meets slice p in ONE contiguous
 //     stretch, whose bounds are kept with the index (part_offsets, built once per collection in one pass);
 //   * per slice, the query hashes that fall into it go into a Bloom filter of 2^20 bits (two probes): 128 KB,
-//     which fits the shared memory of an SM (three probes: ~1 % false positives at 78 K keys per slice);
-//   * a CTA takes a (slice, chunk of index rows) work item, holds that slice's filter in shared memory and streams
-//     the rows' stretches past it with coalesced loads: per index hash one multiply, two shared-memory reads;
+//     which fits the shared memory of an SM (~1.6 % false positives at 68 K keys per slice);
+//   * a CTA belongs to one slice (P = SM count / CTAs per slice), holds that slice's filter in shared memory and
+//     streams the rows' stretches past it with coalesced loads: per index hash two 32-bit multiplies and two
+//     shared-memory reads; its warps take groups of 32 rows from the slice's counter, no barrier in the loop;
 //   * only the hashes the filter lets through (true hits + ~2 % false positives) go to the exact table in global
 //     memory (the hash-grouped table over the queries, join.cu) and add to the count matrix.  They are parked in the
 //     warp's shared-memory queue and resolved 32 at a time when it fills, so that a warp step does not wait for an
@@ -29,21 +30,19 @@ namespace {
 constexpr int FS_THREADS = 1024;
 constexpr int FS_LOG2_F = 20;                              // filter bits per slice
 constexpr uint32_t FS_FILTER_WORDS = (1u << FS_LOG2_F) / 32;
-constexpr uint32_t FS_CHUNK_ROWS = 2048;                   // index rows per work item
-constexpr unsigned long long FS_MUL = 0xD6E8FEB86659FD93ull;
 constexpr unsigned long long FS_EMPTY = ~0ull;
 
-// three filter bits per hash, from one 64-bit multiply
-__device__ __forceinline__ void filter_bits(uint64_t h, uint32_t &b1, uint32_t &b2, uint32_t &b3) {
-    const uint64_t m = h * FS_MUL;
-    b1 = (uint32_t)(m >> (64 - FS_LOG2_F));
-    b2 = (uint32_t)(m >> (64 - 2 * FS_LOG2_F)) & ((1u << FS_LOG2_F) - 1);
-    b3 = (uint32_t)(m >> (64 - 3 * FS_LOG2_F)) & ((1u << FS_LOG2_F) - 1);
+// two filter bits per hash: 32-bit multiplicative hashes of the folded hash (the hashes are MurmurHash3 outputs; within a
+// slice their high bits are all but constant, the low ones uniform)
+__device__ __forceinline__ void filter_bits(uint64_t h, uint32_t &b1, uint32_t &b2) {
+    const uint32_t x = (uint32_t)h ^ (uint32_t)(h >> 32);
+    b1 = (x * 0x9E3779B1u) >> (32 - FS_LOG2_F);
+    b2 = (x * 0x85EBCA6Bu) >> (32 - FS_LOG2_F);
 }
 __device__ __forceinline__ bool filter_test(const uint32_t *f, uint64_t h) {
-    uint32_t b1, b2, b3;
-    filter_bits(h, b1, b2, b3);
-    return ((f[b1 >> 5] >> (b1 & 31)) & (f[b2 >> 5] >> (b2 & 31)) & (f[b3 >> 5] >> (b3 & 31)) & 1u) != 0;
+    uint32_t b1, b2;
+    filter_bits(h, b1, b2);
+    return ((f[b1 >> 5] >> (b1 & 31)) & (f[b2 >> 5] >> (b2 & 31)) & 1u) != 0;
 }
 // slice of the hash range a hash falls into: monotone in h, P - 1 for the largest hash of the index
 // (scale = floor(2^64 * P / (top + 1)), saturated)
@@ -94,12 +93,11 @@ __global__ void __launch_bounds__(256) filters_build_kernel(const uint64_t *__re
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint64_t h = qh[i];
         if (h > top) continue;
-        uint32_t b1, b2, b3;
-        filter_bits(h, b1, b2, b3);
+        uint32_t b1, b2;
+        filter_bits(h, b1, b2);
         uint32_t *f = filters + (size_t)slice_of(h, scale, P) * FS_FILTER_WORDS;
         atomicOr(&f[b1 >> 5], 1u << (b1 & 31));
         atomicOr(&f[b2 >> 5], 1u << (b2 & 31));
-        atomicOr(&f[b3 >> 5], 1u << (b3 & 31));
     }
 }
 
@@ -116,7 +114,8 @@ struct StreamArgs {
     int log2_t;
     uint32_t *cmat;                // [bn][ld] counts
     uint64_t ld;
-    uint32_t *work_ctr;            // zeroed
+    uint32_t *work_ctr;            // P zeroed counters: next group of 32 rows of each slice
+    uint32_t ctas_per_slice;
 };
 
 // Exact lookup of one hash the filter let through + count matrix update.  Called by all 32 lanes of a warp (lanes
@@ -175,6 +174,9 @@ __device__ __forceinline__ void queue_push(const StreamArgs &a, bool hit, uint64
     if (cnt > FS_QUEUE - 32) queue_drain(a, q_hash, q_row, cnt);
 }
 
+// CTA b works on slice b / ctas_per_slice for the whole launch: it loads that slice's filter once and its warps take
+// groups of 32 consecutive index rows from the slice's counter until the block of rows is used up -- no CTA-wide
+// barrier after the filter is in place, so a warp that is resolving its queue holds nobody up.
 __global__ void __launch_bounds__(FS_THREADS, 1) stream_probe_kernel(const StreamArgs a) {
     extern __shared__ __align__(16) uint32_t s_mem[];
     uint32_t *s_filter = s_mem;
@@ -182,64 +184,59 @@ __global__ void __launch_bounds__(FS_THREADS, 1) stream_probe_kernel(const Strea
     uint64_t *q_hash = reinterpret_cast<uint64_t *>(s_mem + FS_FILTER_WORDS) + (size_t)warp * FS_QUEUE;
     uint32_t *q_row = reinterpret_cast<uint32_t *>(reinterpret_cast<uint64_t *>(s_mem + FS_FILTER_WORDS) + (size_t)(FS_THREADS / 32) * FS_QUEUE) +
                       (size_t)warp * FS_QUEUE;
-    __shared__ uint32_t s_item;
-    const uint32_t n_chunks = (uint32_t)((a.bn + FS_CHUNK_ROWS - 1) / FS_CHUNK_ROWS);
-    const uint32_t n_items = a.P * n_chunks;
-    uint32_t cur_p = ~0u, q_cnt = 0;
+    const uint32_t p = blockIdx.x / a.ctas_per_slice;
+    if (p >= a.P) return;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.filters + (size_t)p * FS_FILTER_WORDS);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_filter);
+        for (uint32_t i = threadIdx.x; i < FS_FILTER_WORDS / 4; i += FS_THREADS) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    uint32_t q_cnt = 0;
+    const uint32_t *po_lo = a.part_off + (uint64_t)p * a.n_rows_total + a.b0;
+    const uint32_t *po_hi = po_lo + a.n_rows_total;
+    const uint32_t n_groups = (uint32_t)((a.bn + 31) / 32);
     for (;;) {
-        if (threadIdx.x == 0) s_item = atomicAdd(a.work_ctr, 1u);
-        __syncthreads();            // (also: every warp is done with the previous item's filter)
-        const uint32_t item = s_item;
-        __syncthreads();
-        if (item >= n_items) break;
-        const uint32_t p = item / n_chunks, chunk = item - p * n_chunks;   // slice-major: neighbours share a filter in L2
-        if (p != cur_p) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(a.filters + (size_t)p * FS_FILTER_WORDS);
-            uint4 *dst = reinterpret_cast<uint4 *>(s_filter);
-            for (uint32_t i = threadIdx.x; i < FS_FILTER_WORDS / 4; i += FS_THREADS) dst[i] = __ldg(src + i);
-            cur_p = p;
-            __syncthreads();
-        }
-        const uint64_t row_lo = (uint64_t)chunk * FS_CHUNK_ROWS, row_hi = min(a.bn, row_lo + FS_CHUNK_ROWS);
-        const uint32_t *po_lo = a.part_off + (uint64_t)p * a.n_rows_total + a.b0;
-        const uint32_t *po_hi = po_lo + a.n_rows_total;
-        // a warp takes 32 consecutive rows at a time: their bounds arrive with three coalesced loads
-        for (uint64_t g = row_lo + (uint64_t)warp * 32; g < row_hi; g += (FS_THREADS / 32) * 32) {
-            const uint64_t r = g + lane;
-            const bool valid = r < row_hi;
-            const uint64_t base = valid ? __ldg(&a.io[a.b0 + r]) : 0;
-            const uint32_t s = valid ? __ldg(&po_lo[r]) : 0, e = valid ? __ldg(&po_hi[r]) : 0;
-            const int n_in = (int)min((uint64_t)32, row_hi - g);
-            for (int k = 0; k < n_in; k += 2) {
-                // two rows per step, up to three loads each in flight before the first test
-                const int k1 = min(k + 1, n_in - 1);
-                const uint64_t *seg0 = a.ih + __shfl_sync(0xFFFFFFFFu, base, k);
-                const uint64_t *seg1 = a.ih + __shfl_sync(0xFFFFFFFFu, base, k1);
-                const uint32_t s0 = __shfl_sync(0xFFFFFFFFu, s, k), e0 = __shfl_sync(0xFFFFFFFFu, e, k);
-                const uint32_t s1 = __shfl_sync(0xFFFFFFFFu, s, k1), e1 = (k + 1 < n_in) ? __shfl_sync(0xFFFFFFFFu, e, k1) : s1;
-                uint64_t h[6];
-                bool in[6];
+        uint32_t grp = 0;
+        if (lane == 0) grp = atomicAdd(a.work_ctr + p, 1u);
+        grp = __shfl_sync(0xFFFFFFFFu, grp, 0);
+        if (grp >= n_groups) break;
+        const uint64_t g = (uint64_t)grp * 32;
+        // the bounds of 32 consecutive rows arrive with three coalesced loads
+        const uint64_t r = g + lane;
+        const bool valid = r < a.bn;
+        const uint64_t base = valid ? __ldg(&a.io[a.b0 + r]) : 0;
+        const uint32_t s = valid ? __ldg(&po_lo[r]) : 0, e = valid ? __ldg(&po_hi[r]) : 0;
+        const int n_in = (int)min((uint64_t)32, a.bn - g);
+        for (int k = 0; k < n_in; k += 2) {
+            // two rows per step, up to three loads each in flight before the first test
+            const int k1 = min(k + 1, n_in - 1);
+            const uint64_t *seg0 = a.ih + __shfl_sync(0xFFFFFFFFu, base, k);
+            const uint64_t *seg1 = a.ih + __shfl_sync(0xFFFFFFFFu, base, k1);
+            const uint32_t s0 = __shfl_sync(0xFFFFFFFFu, s, k), e0 = __shfl_sync(0xFFFFFFFFu, e, k);
+            const uint32_t s1 = __shfl_sync(0xFFFFFFFFu, s, k1), e1 = (k + 1 < n_in) ? __shfl_sync(0xFFFFFFFFu, e, k1) : s1;
+            uint64_t h[6];
+            bool in[6];
 #pragma unroll
-                for (int u = 0; u < 3; u++) {
-                    const uint32_t i0 = s0 + lane + 32 * u, i1 = s1 + lane + 32 * u;
-                    in[u] = i0 < e0;
-                    in[3 + u] = i1 < e1;
-                    h[u] = in[u] ? __ldcs(seg0 + i0) : 0;
-                    h[3 + u] = in[3 + u] ? __ldcs(seg1 + i1) : 0;
-                }
+            for (int u = 0; u < 3; u++) {
+                const uint32_t i0 = s0 + lane + 32 * u, i1 = s1 + lane + 32 * u;
+                in[u] = i0 < e0;
+                in[3 + u] = i1 < e1;
+                h[u] = in[u] ? __ldcs(seg0 + i0) : 0;
+                h[3 + u] = in[3 + u] ? __ldcs(seg1 + i1) : 0;
+            }
 #pragma unroll
-                for (int u = 0; u < 6; u++)
-                    queue_push(a, in[u] && filter_test(s_filter, h[u]), h[u], (uint32_t)(g + (u < 3 ? k : k1)), q_hash, q_row, q_cnt);
-                // stretches longer than 96 hashes: the rest, one load at a time
-                for (int side = 0; side < 2; side++) {
-                    const uint64_t *seg = side ? seg1 : seg0;
-                    const uint32_t ee = side ? e1 : e0;
-                    const uint32_t row = (uint32_t)(g + (side ? k1 : k));
-                    for (uint32_t i = (side ? s1 : s0) + 96; i < ee; i += 32) {   // warp-uniform bounds
-                        const bool inb = i + lane < ee;
-                        const uint64_t hh = inb ? __ldcs(seg + i + lane) : 0;
-                        queue_push(a, inb && filter_test(s_filter, hh), hh, row, q_hash, q_row, q_cnt);
-                    }
+            for (int u = 0; u < 6; u++)
+                queue_push(a, in[u] && filter_test(s_filter, h[u]), h[u], (uint32_t)(g + (u < 3 ? k : k1)), q_hash, q_row, q_cnt);
+            // stretches longer than 96 hashes: the rest, one load at a time
+            for (int side = 0; side < 2; side++) {
+                const uint64_t *seg = side ? seg1 : seg0;
+                const uint32_t ee = side ? e1 : e0;
+                const uint32_t row = (uint32_t)(g + (side ? k1 : k));
+                for (uint32_t i = (side ? s1 : s0) + 96; i < ee; i += 32) {   // warp-uniform bounds
+                    const bool inb = i + lane < ee;
+                    const uint64_t hh = inb ? __ldcs(seg + i + lane) : 0;
+                    queue_push(a, inb && filter_test(s_filter, hh), hh, row, q_hash, q_row, q_cnt);
                 }
             }
         }
@@ -250,12 +247,13 @@ __global__ void __launch_bounds__(FS_THREADS, 1) stream_probe_kernel(const Strea
 }  // namespace
 
 // ---- host side ---------------------------------------------------------------------------------------------
-uint32_t find_stream_partitions(uint64_t n_rows, uint64_t n_hashes) {
-    // stretches of at least ~64 hashes on average, at most 64 slices
+uint32_t find_stream_partitions(uint64_t n_rows, uint64_t n_hashes, int sm_count) {
+    // One CTA per SM and a whole number of CTAs per slice: P = sm_count / c.  Stretches of about 64 hashes or more
+    // (two or three coalesced loads per row and slice), at most sm_count / 2 slices.
     const uint64_t avg = n_rows ? n_hashes / n_rows : 0;
-    uint32_t P = 1;
-    while (P < 64 && (uint64_t)P * 2 * 64 <= avg) P *= 2;
-    return P;
+    const uint32_t want = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sm_count / 2, avg / 64));
+    const uint32_t c = ((uint32_t)sm_count + want - 1) / want;   // CTAs per slice
+    return std::max<uint32_t>(1, (uint32_t)sm_count / c);
 }
 
 void launch_rows_max(const uint64_t *h, const uint64_t *off, uint64_t n_rows, unsigned long long *out, cudaStream_t st) {
@@ -294,8 +292,9 @@ void launch_stream_probe(const uint64_t *ih, const uint64_t *io, uint64_t b0, ui
     a.ih = ih; a.io = io; a.b0 = b0; a.bn = bn; a.part_off = part_off; a.n_rows_total = n_rows_total; a.P = P;
     a.filters = filters; a.tkey = tkey; a.toff = toff; a.grows = grows; a.log2_t = log2_t; a.cmat = cmat; a.ld = ld;
     a.work_ctr = work_ctr;
+    a.ctas_per_slice = std::max<uint32_t>(1, (uint32_t)sm_count / P);
     ProfScope prof(PROF_FIND, st);
-    stream_probe_kernel<<<sm_count, FS_THREADS, smem, st>>>(a);
+    stream_probe_kernel<<<P * a.ctas_per_slice, FS_THREADS, smem, st>>>(a);
     SM_LAUNCHED();
 }
 

@@ -206,7 +206,7 @@ void launch_walk_pairs(const uint64_t *pairs, uint64_t n_pairs, const uint64_t *
                        const uint64_t *n_dev_b = nullptr, uint64_t nr_transposed = 0);
 
 // ---- find_stream.cu: LinearIndex::find over a large index at HBM rate (see the file header) -----------------
-uint32_t find_stream_partitions(uint64_t n_rows, uint64_t n_hashes);   // slices of the hash range (power of two, <= 64)
+uint32_t find_stream_partitions(uint64_t n_rows, uint64_t n_hashes, int sm_count);   // slices of the hash range (SM count / k)
 void launch_rows_max(const uint64_t *h, const uint64_t *off, uint64_t n_rows, unsigned long long *out /*zeroed*/, cudaStream_t st);
 // part_off: (P + 1) x n_rows u32, slice-major: row r meets slice p in [part_off[p][r], part_off[p + 1][r])
 // slice of h = min(P - 1, mulhi(h, scale)), scale = floor(2^64 * P / (top + 1)): monotone, so a sorted row meets a slice in one stretch
@@ -220,7 +220,7 @@ void launch_filters_build(const uint64_t *qh, uint64_t n, uint64_t scale, uint64
 // hash-grouped table over the QUERY hashes (launch_group_insert / launch_group_fill)
 void launch_stream_probe(const uint64_t *ih, const uint64_t *io, uint64_t b0, uint64_t bn, const uint32_t *part_off,
                          uint64_t n_rows_total, uint32_t P, const uint32_t *filters, const unsigned long long *tkey,
-                         const uint64_t *toff, const uint32_t *grows, int log2_t, uint32_t *cmat, uint64_t ld, uint32_t *work_ctr /*zeroed*/,
+                         const uint64_t *toff, const uint32_t *grows, int log2_t, uint32_t *cmat, uint64_t ld, uint32_t *work_ctr /*P zeroed words*/,
                          int sm_count, cudaStream_t st);
 
 // dense path for full num sketches: dense u32 ranks + fixed-length walk (join.cu)

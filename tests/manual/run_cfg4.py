@@ -66,11 +66,13 @@ for rep in range(4):
     torch.cuda.synchronize(); times.append(time.perf_counter() - t0)
     if rep == 0:
         smb.profile_read("find_stream", reset=True)
+        smb.profile_read("join_sort", reset=True)
     if "--local" in sys.argv:
         torch.cuda.synchronize(); t0 = time.perf_counter()
         smb.linear_find(index, queries, "containment", 0.1, hits_cap=64 * NQ)
         torch.cuda.synchronize(); local_times.append(time.perf_counter() - t0)
 kms, kn = smb.profile_read("find_stream", reset=True)
+jms, jn = smb.profile_read("join_sort", reset=True)
 t = torch.tensor([min(times[1:]), min(local_times[1:]) if local_times else 0.0, kms / max(1, kn)], dtype=torch.float64, device=dev)
 if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -88,7 +90,7 @@ if rank == 0:
                       "n_gpus": world, "index_sketches_per_gpu": per, "index_bytes_per_gpu": shard_bytes,
                       "search_ms": sec * 1e3, "local_search_ms": sec_local * 1e3 or None, "pairs": N * NQ, "pairs_per_s": N * NQ / sec,
                       "index_sketches_per_s": N / sec,
-                      "stream_kernel_ms": k_ms or None, "stream_kernel_gbs": (shard_bytes / (k_ms * 1e-3) / 1e9) if k_ms else None,
+                      "query_table_build_ms": (jms / jn) if jn else None, "stream_kernel_ms": k_ms or None, "stream_kernel_gbs": (shard_bytes / (k_ms * 1e-3) / 1e9) if k_ms else None,
                       "whole_search_index_gbs_per_gpu": shard_bytes / sec / 1e9,
                       "hits_total": int(stat[0].item()), "every_planted_source_found": bool(mn[1].item()),
                       "find_path": os.environ.get("SMB200_FIND_PATH", "0")}), flush=True)
