@@ -10,9 +10,9 @@
 //   * the hash range is cut into P equal slices ("partitions"); a sorted sketch meets slice p in ONE contiguous
 //     stretch, whose bounds are kept with the index (part_offsets, built once per collection in one pass);
 //   * per slice, the query hashes that fall into it go into a Bloom filter of 2^20 bits (two probes): 128 KB,
-//     which fits the shared memory of an SM (~1.6 % false positives at 68 K keys per slice);
+//     which fits the shared memory of an SM (three probes: ~0.6 % false positives at 68 K keys per slice);
 //   * a CTA belongs to one slice (P = SM count / CTAs per slice), holds that slice's filter in shared memory and
-//     streams the rows' stretches past it with coalesced loads: per index hash two 32-bit multiplies and two
+//     streams the rows' stretches past it with coalesced loads: per index hash three 32-bit multiplies and three
 //     shared-memory reads; its warps take groups of 32 rows from the slice's counter, no barrier in the loop;
 //   * only the hashes the filter lets through (true hits + ~2 % false positives) go to the exact table in global
 //     memory (the hash-grouped table over the queries, join.cu) and add to the count matrix.  They are parked in the
@@ -32,17 +32,18 @@ constexpr int FS_LOG2_F = 20;                              // filter bits per sl
 constexpr uint32_t FS_FILTER_WORDS = (1u << FS_LOG2_F) / 32;
 constexpr unsigned long long FS_EMPTY = ~0ull;
 
-// two filter bits per hash: 32-bit multiplicative hashes of the folded hash (the hashes are MurmurHash3 outputs; within a
-// slice their high bits are all but constant, the low ones uniform)
-__device__ __forceinline__ void filter_bits(uint64_t h, uint32_t &b1, uint32_t &b2) {
+// three filter bits per hash: 32-bit multiplicative hashes of the folded hash (the hashes are MurmurHash3 outputs; within
+// a slice their high bits are all but constant, the low ones uniform)
+__device__ __forceinline__ void filter_bits(uint64_t h, uint32_t &b1, uint32_t &b2, uint32_t &b3) {
     const uint32_t x = (uint32_t)h ^ (uint32_t)(h >> 32);
     b1 = (x * 0x9E3779B1u) >> (32 - FS_LOG2_F);
     b2 = (x * 0x85EBCA6Bu) >> (32 - FS_LOG2_F);
+    b3 = (x * 0xC2B2AE35u) >> (32 - FS_LOG2_F);
 }
 __device__ __forceinline__ bool filter_test(const uint32_t *f, uint64_t h) {
-    uint32_t b1, b2;
-    filter_bits(h, b1, b2);
-    return ((f[b1 >> 5] >> (b1 & 31)) & (f[b2 >> 5] >> (b2 & 31)) & 1u) != 0;
+    uint32_t b1, b2, b3;
+    filter_bits(h, b1, b2, b3);
+    return ((f[b1 >> 5] >> (b1 & 31)) & (f[b2 >> 5] >> (b2 & 31)) & (f[b3 >> 5] >> (b3 & 31)) & 1u) != 0;
 }
 // slice of the hash range a hash falls into: monotone in h, P - 1 for the largest hash of the index
 // (scale = floor(2^64 * P / (top + 1)), saturated)
@@ -93,11 +94,12 @@ __global__ void __launch_bounds__(256) filters_build_kernel(const uint64_t *__re
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint64_t h = qh[i];
         if (h > top) continue;
-        uint32_t b1, b2;
-        filter_bits(h, b1, b2);
+        uint32_t b1, b2, b3;
+        filter_bits(h, b1, b2, b3);
         uint32_t *f = filters + (size_t)slice_of(h, scale, P) * FS_FILTER_WORDS;
         atomicOr(&f[b1 >> 5], 1u << (b1 & 31));
         atomicOr(&f[b2 >> 5], 1u << (b2 & 31));
+        atomicOr(&f[b3 >> 5], 1u << (b3 & 31));
     }
 }
 
@@ -138,6 +140,7 @@ __device__ __forceinline__ void stream_resolve(const StreamArgs &a, bool have, u
         if (s != ~0ull) { jb = __ldg(&a.toff[s]); je = __ldg(&a.toff[s + 1]); }
     }
     const bool found = je > jb;
+    if (!__any_sync(0xFFFFFFFFu, found)) return;   // nothing but false positives of the filter in this step
     const uint64_t cell = found ? row * a.ld + __ldg(&a.grows[jb]) : (~0ull - (threadIdx.x & 31));
     const unsigned peers = __match_any_sync(0xFFFFFFFFu, cell);
     if (found) {
@@ -208,37 +211,32 @@ __global__ void __launch_bounds__(FS_THREADS, 1) stream_probe_kernel(const Strea
         const uint64_t base = valid ? __ldg(&a.io[a.b0 + r]) : 0;
         const uint32_t s = valid ? __ldg(&po_lo[r]) : 0, e = valid ? __ldg(&po_hi[r]) : 0;
         const int n_in = (int)min((uint64_t)32, a.bn - g);
-        for (int k = 0; k < n_in; k += 2) {
-            // two rows per step, up to three loads each in flight before the first test
-            const int k1 = min(k + 1, n_in - 1);
-            const uint64_t *seg0 = a.ih + __shfl_sync(0xFFFFFFFFu, base, k);
-            const uint64_t *seg1 = a.ih + __shfl_sync(0xFFFFFFFFu, base, k1);
-            const uint32_t s0 = __shfl_sync(0xFFFFFFFFu, s, k), e0 = __shfl_sync(0xFFFFFFFFu, e, k);
-            const uint32_t s1 = __shfl_sync(0xFFFFFFFFu, s, k1), e1 = (k + 1 < n_in) ? __shfl_sync(0xFFFFFFFFu, e, k1) : s1;
-            uint64_t h[6];
-            bool in[6];
+        // one row per step, software-pipelined: the (up to three) loads of row k + 1 are issued before the hashes of row
+        // k are tested, so that a warp always has loads in flight
+        uint64_t cur[3], nxt[3];
+        const uint64_t *seg = a.ih + __shfl_sync(0xFFFFFFFFu, base, 0);
+        uint32_t cs = __shfl_sync(0xFFFFFFFFu, s, 0), ce = __shfl_sync(0xFFFFFFFFu, e, 0);
 #pragma unroll
-            for (int u = 0; u < 3; u++) {
-                const uint32_t i0 = s0 + lane + 32 * u, i1 = s1 + lane + 32 * u;
-                in[u] = i0 < e0;
-                in[3 + u] = i1 < e1;
-                h[u] = in[u] ? __ldcs(seg0 + i0) : 0;
-                h[3 + u] = in[3 + u] ? __ldcs(seg1 + i1) : 0;
+        for (int u = 0; u < 3; u++) cur[u] = (cs + lane + 32 * u < ce) ? __ldcs(seg + cs + lane + 32 * u) : 0;
+        for (int k = 0; k < n_in; k++) {
+            const int kn = min(k + 1, n_in - 1);
+            const uint64_t *nseg = a.ih + __shfl_sync(0xFFFFFFFFu, base, kn);
+            const uint32_t ns = __shfl_sync(0xFFFFFFFFu, s, kn);
+            const uint32_t ne = (k + 1 < n_in) ? __shfl_sync(0xFFFFFFFFu, e, kn) : ns;
+#pragma unroll
+            for (int u = 0; u < 3; u++) nxt[u] = (ns + lane + 32 * u < ne) ? __ldcs(nseg + ns + lane + 32 * u) : 0;
+            const uint32_t row = (uint32_t)(g + k);
+#pragma unroll
+            for (int u = 0; u < 3; u++)
+                queue_push(a, (cs + lane + 32 * u < ce) && filter_test(s_filter, cur[u]), cur[u], row, q_hash, q_row, q_cnt);
+            for (uint32_t i = cs + 96; i < ce; i += 32) {   // a stretch longer than 96 hashes: the rest, one load at a time
+                const bool inb = i + lane < ce;
+                const uint64_t hh = inb ? __ldcs(seg + i + lane) : 0;
+                queue_push(a, inb && filter_test(s_filter, hh), hh, row, q_hash, q_row, q_cnt);
             }
 #pragma unroll
-            for (int u = 0; u < 6; u++)
-                queue_push(a, in[u] && filter_test(s_filter, h[u]), h[u], (uint32_t)(g + (u < 3 ? k : k1)), q_hash, q_row, q_cnt);
-            // stretches longer than 96 hashes: the rest, one load at a time
-            for (int side = 0; side < 2; side++) {
-                const uint64_t *seg = side ? seg1 : seg0;
-                const uint32_t ee = side ? e1 : e0;
-                const uint32_t row = (uint32_t)(g + (side ? k1 : k));
-                for (uint32_t i = (side ? s1 : s0) + 96; i < ee; i += 32) {   // warp-uniform bounds
-                    const bool inb = i + lane < ee;
-                    const uint64_t hh = inb ? __ldcs(seg + i + lane) : 0;
-                    queue_push(a, inb && filter_test(s_filter, hh), hh, row, q_hash, q_row, q_cnt);
-                }
-            }
+            for (int u = 0; u < 3; u++) cur[u] = nxt[u];
+            seg = nseg; cs = ns; ce = ne;
         }
     }
     queue_drain(a, q_hash, q_row, q_cnt);
