@@ -10,10 +10,10 @@
 //   * the hash range is cut into P equal slices ("partitions"); a sorted sketch meets slice p in ONE contiguous
 //     stretch, whose bounds are kept with the index (part_offsets, built once per collection in one pass);
 //   * per slice, the query hashes that fall into it go into a Bloom filter of 2^20 bits (two probes): 128 KB,
-//     which fits the shared memory of an SM (three probes: ~0.6 % false positives at 68 K keys per slice);
+//     which fits the shared memory of an SM (blocked: one word, three bits per hash; ~0.8 % false positives);
 //   * a CTA belongs to one slice (P = SM count / CTAs per slice), holds that slice's filter in shared memory and
-//     streams the rows' stretches past it with coalesced loads: per index hash three 32-bit multiplies and three
-//     shared-memory reads; its warps take groups of 32 rows from the slice's counter, no barrier in the loop;
+//     streams the rows' stretches past it with coalesced loads: per index hash one 32-bit multiply and one
+//     shared-memory read; its warps take groups of 32 rows from the slice's counter, no barrier in the loop;
 //   * only the hashes the filter lets through (true hits + ~2 % false positives) go to the exact table in global
 //     memory (the hash-grouped table over the queries, join.cu) and add to the count matrix.  They are parked in the
 //     warp's shared-memory queue and resolved 32 at a time when it fills, so that a warp step does not wait for an
@@ -32,18 +32,19 @@ constexpr int FS_LOG2_F = 20;                              // filter bits per sl
 constexpr uint32_t FS_FILTER_WORDS = (1u << FS_LOG2_F) / 32;
 constexpr unsigned long long FS_EMPTY = ~0ull;
 
-// three filter bits per hash: 32-bit multiplicative hashes of the folded hash (the hashes are MurmurHash3 outputs; within
-// a slice their high bits are all but constant, the low ones uniform)
-__device__ __forceinline__ void filter_bits(uint64_t h, uint32_t &b1, uint32_t &b2, uint32_t &b3) {
-    const uint32_t x = (uint32_t)h ^ (uint32_t)(h >> 32);
-    b1 = (x * 0x9E3779B1u) >> (32 - FS_LOG2_F);
-    b2 = (x * 0x85EBCA6Bu) >> (32 - FS_LOG2_F);
-    b3 = (x * 0xC2B2AE35u) >> (32 - FS_LOG2_F);
+// Blocked Bloom filter: ONE 32-bit multiplicative hash of the folded hash picks a 32-bit word of the slice's filter (its
+// top 15 bits) and three bit positions inside that word (its low 15 bits): one shared-memory read and a dozen
+// instructions per index hash.  (The hashes are MurmurHash3 outputs; within a slice their high bits are all but
+// constant, the low ones uniform.)  At 68 K keys per slice: ~2 keys per word, ~0.8 % false positives.
+__device__ __forceinline__ void filter_word_mask(uint64_t h, uint32_t &word, uint32_t &mask) {
+    const uint32_t m = ((uint32_t)h ^ (uint32_t)(h >> 32)) * 0x9E3779B1u;
+    word = m >> (32 - (FS_LOG2_F - 5));
+    mask = (1u << (m & 31)) | (1u << ((m >> 5) & 31)) | (1u << ((m >> 10) & 31));
 }
 __device__ __forceinline__ bool filter_test(const uint32_t *f, uint64_t h) {
-    uint32_t b1, b2, b3;
-    filter_bits(h, b1, b2, b3);
-    return ((f[b1 >> 5] >> (b1 & 31)) & (f[b2 >> 5] >> (b2 & 31)) & (f[b3 >> 5] >> (b3 & 31)) & 1u) != 0;
+    uint32_t word, mask;
+    filter_word_mask(h, word, mask);
+    return (f[word] & mask) == mask;
 }
 // slice of the hash range a hash falls into: monotone in h, P - 1 for the largest hash of the index
 // (scale = floor(2^64 * P / (top + 1)), saturated)
@@ -94,12 +95,9 @@ __global__ void __launch_bounds__(256) filters_build_kernel(const uint64_t *__re
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint64_t h = qh[i];
         if (h > top) continue;
-        uint32_t b1, b2, b3;
-        filter_bits(h, b1, b2, b3);
-        uint32_t *f = filters + (size_t)slice_of(h, scale, P) * FS_FILTER_WORDS;
-        atomicOr(&f[b1 >> 5], 1u << (b1 & 31));
-        atomicOr(&f[b2 >> 5], 1u << (b2 & 31));
-        atomicOr(&f[b3 >> 5], 1u << (b3 & 31));
+        uint32_t word, mask;
+        filter_word_mask(h, word, mask);
+        atomicOr(&filters[(size_t)slice_of(h, scale, P) * FS_FILTER_WORDS + word], mask);
     }
 }
 
@@ -211,6 +209,13 @@ __global__ void __launch_bounds__(FS_THREADS, 1) stream_probe_kernel(const Strea
         const uint64_t base = valid ? __ldg(&a.io[a.b0 + r]) : 0;
         const uint32_t s = valid ? __ldg(&po_lo[r]) : 0, e = valid ? __ldg(&po_hi[r]) : 0;
         const int n_in = (int)min((uint64_t)32, a.bn - g);
+        // Each lane asks L2 for its own row's stretch (five or six 128-byte lines) a few steps before the warp gets to
+        // that row: the loads below then find their data in L2, and DRAM latency is off the warp's critical path.
+        auto prefetch_own = [&]() {
+            const char *lo = reinterpret_cast<const char *>(a.ih + base + s), *hi = reinterpret_cast<const char *>(a.ih + base + e);
+            for (const char *q = lo; q < hi; q += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+        };
+        if (lane < 16) prefetch_own();
         // one row per step, software-pipelined: the (up to three) loads of row k + 1 are issued before the hashes of row
         // k are tested, so that a warp always has loads in flight
         uint64_t cur[3], nxt[3];
@@ -219,6 +224,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) stream_probe_kernel(const Strea
 #pragma unroll
         for (int u = 0; u < 3; u++) cur[u] = (cs + lane + 32 * u < ce) ? __ldcs(seg + cs + lane + 32 * u) : 0;
         for (int k = 0; k < n_in; k++) {
+            if ((k & 7) == 0 && k + 16 < 40 && (lane >> 3) == (k >> 3) + 2) prefetch_own();   // rows k + 16 .. k + 23
             const int kn = min(k + 1, n_in - 1);
             const uint64_t *nseg = a.ih + __shfl_sync(0xFFFFFFFFu, base, kn);
             const uint32_t ns = __shfl_sync(0xFFFFFFFFu, s, kn);
@@ -226,9 +232,13 @@ __global__ void __launch_bounds__(FS_THREADS, 1) stream_probe_kernel(const Strea
 #pragma unroll
             for (int u = 0; u < 3; u++) nxt[u] = (ns + lane + 32 * u < ne) ? __ldcs(nseg + ns + lane + 32 * u) : 0;
             const uint32_t row = (uint32_t)(g + k);
+            bool hit[3];
 #pragma unroll
-            for (int u = 0; u < 3; u++)
-                queue_push(a, (cs + lane + 32 * u < ce) && filter_test(s_filter, cur[u]), cur[u], row, q_hash, q_row, q_cnt);
+            for (int u = 0; u < 3; u++) hit[u] = (cs + lane + 32 * u < ce) && filter_test(s_filter, cur[u]);
+            if (__any_sync(0xFFFFFFFFu, hit[0] | hit[1] | hit[2])) {
+#pragma unroll
+                for (int u = 0; u < 3; u++) queue_push(a, hit[u], cur[u], row, q_hash, q_row, q_cnt);
+            }
             for (uint32_t i = cs + 96; i < ce; i += 32) {   // a stretch longer than 96 hashes: the rest, one load at a time
                 const bool inb = i + lane < ce;
                 const uint64_t hh = inb ? __ldcs(seg + i + lane) : 0;
