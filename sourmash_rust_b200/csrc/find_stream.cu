@@ -29,6 +29,7 @@ namespace {
 
 constexpr int FS_THREADS = 1024;
 constexpr int FS_LOG2_F = 20;                              // filter bits per slice
+constexpr int FS_LOADS = 4;                                // pipelined loads per row and lane: stretches of up to 128 hashes
 constexpr uint32_t FS_FILTER_WORDS = (1u << FS_LOG2_F) / 32;
 constexpr unsigned long long FS_EMPTY = ~0ull;
 
@@ -175,6 +176,28 @@ __device__ __forceinline__ void queue_push(const StreamArgs &a, bool hit, uint64
     if (cnt > FS_QUEUE - 32) queue_drain(a, q_hash, q_row, cnt);
 }
 
+// the loaded hashes of one row's stretch [cs, ce) against the filter; hits go to the warp's queue
+__device__ __forceinline__ void stream_row(const StreamArgs &a, const uint32_t *s_filter, const uint64_t (&h)[FS_LOADS], const uint64_t *seg,
+                                           uint32_t cs, uint32_t ce, uint32_t row, uint64_t *q_hash, uint32_t *q_row, uint32_t &q_cnt) {
+    const int lane = threadIdx.x & 31;
+    bool hit[FS_LOADS];
+    bool any = false;
+#pragma unroll
+    for (int u = 0; u < FS_LOADS; u++) {   // branch-free: a lane beyond the stretch tests hash 0 and drops the answer
+        hit[u] = filter_test(s_filter, h[u]) & (cs + lane + 32 * u < ce);
+        any |= hit[u];
+    }
+    if (__any_sync(0xFFFFFFFFu, any)) {
+#pragma unroll
+        for (int u = 0; u < FS_LOADS; u++) queue_push(a, hit[u], h[u], row, q_hash, q_row, q_cnt);
+    }
+    for (uint32_t i = cs + 32 * FS_LOADS; i < ce; i += 32) {   // a longer stretch: the rest, one load at a time
+        const bool inb = i + lane < ce;
+        const uint64_t hh = inb ? __ldcs(seg + i + lane) : 0;
+        queue_push(a, inb & filter_test(s_filter, hh), hh, row, q_hash, q_row, q_cnt);
+    }
+}
+
 // CTA b works on slice b / ctas_per_slice for the whole launch: it loads that slice's filter once and its warps take
 // groups of 32 consecutive index rows from the slice's counter until the block of rows is used up -- no CTA-wide
 // barrier after the filter is in place, so a warp that is resolving its queue holds nobody up.
@@ -216,37 +239,36 @@ __global__ void __launch_bounds__(FS_THREADS, 1) stream_probe_kernel(const Strea
             for (const char *q = lo; q < hi; q += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
         };
         if (lane < 16) prefetch_own();
-        // one row per step, software-pipelined: the (up to three) loads of row k + 1 are issued before the hashes of row
-        // k are tested, so that a warp always has loads in flight
-        uint64_t cur[3], nxt[3];
-        const uint64_t *seg = a.ih + __shfl_sync(0xFFFFFFFFu, base, 0);
-        uint32_t cs = __shfl_sync(0xFFFFFFFFu, s, 0), ce = __shfl_sync(0xFFFFFFFFu, e, 0);
+        // One row per step, software-pipelined: the (up to FS_LOADS) loads of row k + 1 are issued before the hashes of
+        // row k are tested.  Two steps per trip with the two register sets swapping roles, so that nothing is copied.
+        uint64_t ha[FS_LOADS], hb[FS_LOADS];
+        const uint64_t *seg_a = a.ih + __shfl_sync(0xFFFFFFFFu, base, 0), *seg_b = seg_a;
+        uint32_t sa = __shfl_sync(0xFFFFFFFFu, s, 0), ea = __shfl_sync(0xFFFFFFFFu, e, 0), sb = 0, eb = 0;
 #pragma unroll
-        for (int u = 0; u < 3; u++) cur[u] = (cs + lane + 32 * u < ce) ? __ldcs(seg + cs + lane + 32 * u) : 0;
-        for (int k = 0; k < n_in; k++) {
-            if ((k & 7) == 0 && k + 16 < 40 && (lane >> 3) == (k >> 3) + 2) prefetch_own();   // rows k + 16 .. k + 23
-            const int kn = min(k + 1, n_in - 1);
-            const uint64_t *nseg = a.ih + __shfl_sync(0xFFFFFFFFu, base, kn);
-            const uint32_t ns = __shfl_sync(0xFFFFFFFFu, s, kn);
-            const uint32_t ne = (k + 1 < n_in) ? __shfl_sync(0xFFFFFFFFu, e, kn) : ns;
+        for (int u = 0; u < FS_LOADS; u++) ha[u] = (sa + lane + 32 * u < ea) ? __ldcs(seg_a + sa + lane + 32 * u) : 0;
+        for (int k = 0; k < n_in; k += 2) {
+            if ((k & 7) == 0 && (lane >> 3) == (k >> 3) + 2) prefetch_own();   // rows k + 16 .. k + 23
+            // ---- issue row k + 1 into set b, test row k from set a
+            {
+                const int kn = min(k + 1, n_in - 1);
+                seg_b = a.ih + __shfl_sync(0xFFFFFFFFu, base, kn);
+                sb = __shfl_sync(0xFFFFFFFFu, s, kn);
+                eb = (k + 1 < n_in) ? __shfl_sync(0xFFFFFFFFu, e, kn) : sb;
 #pragma unroll
-            for (int u = 0; u < 3; u++) nxt[u] = (ns + lane + 32 * u < ne) ? __ldcs(nseg + ns + lane + 32 * u) : 0;
-            const uint32_t row = (uint32_t)(g + k);
-            bool hit[3];
-#pragma unroll
-            for (int u = 0; u < 3; u++) hit[u] = (cs + lane + 32 * u < ce) && filter_test(s_filter, cur[u]);
-            if (__any_sync(0xFFFFFFFFu, hit[0] | hit[1] | hit[2])) {
-#pragma unroll
-                for (int u = 0; u < 3; u++) queue_push(a, hit[u], cur[u], row, q_hash, q_row, q_cnt);
+                for (int u = 0; u < FS_LOADS; u++) hb[u] = (sb + lane + 32 * u < eb) ? __ldcs(seg_b + sb + lane + 32 * u) : 0;
+                stream_row(a, s_filter, ha, seg_a, sa, ea, (uint32_t)(g + k), q_hash, q_row, q_cnt);
             }
-            for (uint32_t i = cs + 96; i < ce; i += 32) {   // a stretch longer than 96 hashes: the rest, one load at a time
-                const bool inb = i + lane < ce;
-                const uint64_t hh = inb ? __ldcs(seg + i + lane) : 0;
-                queue_push(a, inb && filter_test(s_filter, hh), hh, row, q_hash, q_row, q_cnt);
-            }
+            if (k + 1 >= n_in) break;
+            // ---- issue row k + 2 into set a, test row k + 1 from set b
+            {
+                const int kn = min(k + 2, n_in - 1);
+                seg_a = a.ih + __shfl_sync(0xFFFFFFFFu, base, kn);
+                sa = __shfl_sync(0xFFFFFFFFu, s, kn);
+                ea = (k + 2 < n_in) ? __shfl_sync(0xFFFFFFFFu, e, kn) : sa;
 #pragma unroll
-            for (int u = 0; u < 3; u++) cur[u] = nxt[u];
-            seg = nseg; cs = ns; ce = ne;
+                for (int u = 0; u < FS_LOADS; u++) ha[u] = (sa + lane + 32 * u < ea) ? __ldcs(seg_a + sa + lane + 32 * u) : 0;
+                stream_row(a, s_filter, hb, seg_b, sb, eb, (uint32_t)(g + k + 1), q_hash, q_row, q_cnt);
+            }
         }
     }
     queue_drain(a, q_hash, q_row, q_cnt);
@@ -256,10 +278,11 @@ __global__ void __launch_bounds__(FS_THREADS, 1) stream_probe_kernel(const Strea
 
 // ---- host side ---------------------------------------------------------------------------------------------
 uint32_t find_stream_partitions(uint64_t n_rows, uint64_t n_hashes, int sm_count) {
-    // One CTA per SM and a whole number of CTAs per slice: P = sm_count / c.  Stretches of about 64 hashes or more
-    // (two or three coalesced loads per row and slice), at most sm_count / 2 slices.
+    // One CTA per SM and a whole number of CTAs per slice: P = sm_count / c.  Stretches of about 100 hashes (three to
+    // four coalesced loads per row and slice: the per-row cost of the loop is spread over more hashes and DRAM sees
+    // longer pieces), at most sm_count / 2 slices.
     const uint64_t avg = n_rows ? n_hashes / n_rows : 0;
-    const uint32_t want = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sm_count / 2, avg / 64));
+    const uint32_t want = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sm_count / 2, avg / 100));
     const uint32_t c = ((uint32_t)sm_count + want - 1) / want;   // CTAs per slice
     return std::max<uint32_t>(1, (uint32_t)sm_count / c);
 }
