@@ -503,10 +503,6 @@ std::vector<std::vector<uint64_t>> linear_find_lists(SketchCollection &index, Sk
         cudaStream_t st = ctx.stream;
         const uint64_t block_rows = std::max<uint64_t>(1, std::min<uint64_t>(ni, (g_find_block_cells) / nq));
         const uint64_t cells = block_rows * nq;
-        ctx.misc[2].reserve(cells * 8);  // ratio, [index row][query]
-        ctx.misc[3].reserve((cells + 1) * 8);  // flags, [query][index row]
-        ctx.misc[4].reserve((cells + 1) * 8);  // scan
-        ctx.misc[5].reserve((cells + 1) * 8);  // compacted cell ids
         std::vector<uint64_t> cellbuf;
         // Containment with a threshold >= 0: a cell can only hit when the pair shares a hash, and the join leaves
         // the shared-hash COUNT of every cell in a u32 matrix.  One pass over that matrix picks the hits (count
@@ -522,8 +518,14 @@ std::vector<std::vector<uint64_t>> linear_find_lists(SketchCollection &index, Sk
         const bool stream = count_path && g_find_path != 1 && queries.n_hashes > 0 && queries.n_hashes < (1ull << 31) && nq < (1ull << 31) &&
                             index.max_len < (1u << 31) &&
                             (g_find_path == 2 || (index.n_hashes >= 4 * queries.n_hashes && index.n_hashes >= (1ull << 22)));
-        JoinTable qt;
+        int q_log2_t = 0;
         if (stream) index.ensure_partitions();
+        ctx.misc[3].reserve((cells + 1) * 8);      // flags, [query][index row] / the hit list of the count paths
+        if (!stream) ctx.misc[2].reserve(cells * 8);  // ratio or counts, [index row][query]
+        if (!count_path) {
+            ctx.misc[4].reserve((cells + 1) * 8);  // scan
+            ctx.misc[5].reserve((cells + 1) * 8);  // compacted cell ids
+        }
         for (uint64_t b0 = 0; count_path && b0 < ni; b0 += block_rows) {
             const uint64_t bn = std::min(block_rows, ni - b0);
             uint32_t *cmat = ctx.misc[2].as<uint32_t>();  // cells * 8 bytes reserved: room for the u32 counts
@@ -531,25 +533,48 @@ std::vector<std::vector<uint64_t>> linear_find_lists(SketchCollection &index, Sk
             if (stream) {
                 // the index streams past per-slice Bloom filters of the query hashes held in shared memory (find_stream.cu)
                 if (b0 == 0) {   // the query side: exact table + filters, once per search
-                    join_table_build(ctx, qt, queries.d_hashes.as<uint64_t>(), queries.d_offsets.as<uint64_t>(), 0, nq, queries.n_hashes, false);
+                    const size_t T = find_stream_table_slots(queries.n_hashes, &q_log2_t);
+                    ctx.join[0].reserve((T + 2) * 8);
+                    ctx.join[1].reserve((T + 2) * 4);
+                    ctx.join[6].reserve((queries.n_hashes + 1) * 4);
+                    ctx.join[7].reserve((queries.n_hashes + 1) * 4);
+                    launch_qtable_build(queries.d_hashes.as<uint64_t>(), queries.d_offsets.as<uint64_t>(), nq, queries.n_hashes,
+                                        ctx.join[0].as<unsigned long long>(), ctx.join[1].as<int32_t>(), ctx.join[6].as<int32_t>(),
+                                        ctx.join[7].as<uint32_t>(), q_log2_t, st);
                     ctx.misc[6].reserve(find_stream_filter_bytes(index.n_parts) + (size_t)index.n_parts * 4 + 256);
                     SM_CUDA(cudaMemsetAsync(ctx.misc[6].p, 0, find_stream_filter_bytes(index.n_parts), st));
                     launch_filters_build(queries.d_hashes.as<uint64_t>(), queries.n_hashes, index.part_scale, index.part_top,
                                          index.n_parts, ctx.misc[6].as<uint32_t>(), st);
+                    // count matrix / touched-row bitmap: zero from the last search, or zeroed now
+                    const size_t c_bytes = (size_t)block_rows * nq * 4, b_bytes = ((size_t)block_rows + 31) / 32 * 4 + 4;
+                    const bool grow = ctx.find_cmat.cap < c_bytes || ctx.find_bits.cap < b_bytes;
+                    ctx.find_cmat.reserve(c_bytes);
+                    ctx.find_bits.reserve(b_bytes);
+                    ctx.find_rows.reserve((size_t)block_rows * 4 + 4);
+                    if (grow || !ctx.find_clean) {
+                        SM_CUDA(cudaMemsetAsync(ctx.find_cmat.p, 0, ctx.find_cmat.cap, st));
+                        SM_CUDA(cudaMemsetAsync(ctx.find_bits.p, 0, ctx.find_bits.cap, st));
+                        SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_TOUCHED), 0, 8, st));
+                    }
+                    ctx.find_clean = false;   // until this search has cleaned up after itself
                 }
-                SM_CUDA(cudaMemsetAsync(cmat, 0, bn * nq * 4, st));
                 uint32_t *work_ctr = ctx.misc[6].as<uint32_t>() + find_stream_filter_bytes(index.n_parts) / 4;  // behind the filters
                 SM_CUDA(cudaMemsetAsync(work_ctr, 0, (size_t)index.n_parts * 4, st));
                 launch_stream_probe(index.d_hashes.as<uint64_t>(), index.d_offsets.as<uint64_t>(), b0, bn, index.d_part_off.as<uint32_t>(),
                                     index.n_rows, index.n_parts, ctx.misc[6].as<uint32_t>(), ctx.join[0].as<unsigned long long>(),
-                                    ctx.sort_tmp_k.as<uint64_t>(), ctx.join[7].as<uint32_t>(), qt.log2_t, cmat, nq,
-                                    work_ctr, ctx.sm_count, st);
+                                    ctx.join[1].as<int32_t>(), ctx.join[6].as<int32_t>(), ctx.join[7].as<uint32_t>(), q_log2_t,
+                                    ctx.find_cmat.as<uint32_t>(), nq, ctx.find_bits.as<uint32_t>(), ctx.find_rows.as<uint32_t>(),
+                                    ctx.dsc(SC_TOUCHED), work_ctr, ctx.sm_count, st);
+                SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_CNT), 0, 8, st));
+                launch_touched_hits(ctx.find_cmat.as<uint32_t>(), bn, nq, index.d_offsets.as<uint64_t>(), b0,
+                                    count_sim ? queries.d_offsets.as<uint64_t>() : nullptr, threshold, ctx.find_bits.as<uint32_t>(),
+                                    ctx.find_rows.as<uint32_t>(), ctx.dsc(SC_TOUCHED), found, cells, ctx.dsc(SC_CNT), ctx.sm_count, st);
             } else {
                 compare_block_device(index, b0, bn, queries, 0, nq, 1, cmat, nullptr, nullptr, nq);
+                SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_CNT), 0, 8, st));
+                launch_count_hits(cmat, bn, nq, index.d_offsets.as<uint64_t>(), b0, count_sim ? queries.d_offsets.as<uint64_t>() : nullptr,
+                                  threshold, found, cells, ctx.dsc(SC_CNT), st);
             }
-            SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_CNT), 0, 8, st));
-            launch_count_hits(cmat, bn, nq, index.d_offsets.as<uint64_t>(), b0, count_sim ? queries.d_offsets.as<uint64_t>() : nullptr,
-                              threshold, found, cells, ctx.dsc(SC_CNT), st);
             ctx.read_scalars();
             const uint64_t n_hit = ctx.h_scalars[SC_CNT];
             if (n_hit > cells) throw_internal("linear_find: hit list overflow");
@@ -561,6 +586,7 @@ std::vector<std::vector<uint64_t>> linear_find_lists(SketchCollection &index, Sk
             std::sort(cellbuf.begin(), cellbuf.end());  // cell id = query * bn + row: per query, ascending index id
             for (uint64_t cell : cellbuf) per_query[cell / bn].push_back(b0 + cell % bn);
         }
+        if (stream) ctx.find_clean = true;   // every block's hit pass has cleared what its probe wrote
         for (uint64_t b0 = 0; !count_path && b0 < ni; b0 += block_rows) {
             const uint64_t bn = std::min(block_rows, ni - b0);
             const uint64_t n_cells = bn * nq;

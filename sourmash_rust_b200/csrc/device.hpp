@@ -105,6 +105,10 @@ struct Context {
     unsigned long long *h_scalars = nullptr;  // pinned mirror
     // scratch
     DevBuf ascii, offsets, sort_tmp_k, sort_tmp_v, scan_tmp, misc[8], join[8];
+    // find_stream.cu: count matrix + touched-row bitmap that every search leaves all-zero again (the hit pass clears what
+    // it reads), so that a search does not start with a memset of half a gigabyte; find_clean: that invariant holds
+    DevBuf find_cmat, find_bits, find_rows;
+    bool find_clean = false;
     std::vector<cudaEvent_t> chunk_events;
 
     cudaStream_t copy_stream = nullptr;  // host->device staging, overlapped with `stream`
@@ -143,6 +147,6 @@ void set_requested_device(int dev);
 
 enum { SC_FIRST_BAD = 0, SC_NUNIQ = 1, SC_TMAX = 2, SC_CNT = 3, SC_FLAG = 4, SC_LEN = 5, SC_PAIR0 = 6, SC_PAIR1 = 7,
        SC_PAIR2 = 8, SC_THRESH = 9, SC_CAND0 = 10 /* .. SC_CAND0+5: per-handle candidate counters of one batch */,
-       SC_COUNT = 16 };
+       SC_TOUCHED = 16 /* find_stream: rows holding a count; zero between searches */, SC_COUNT = 24 };
 
 }  // namespace smb200

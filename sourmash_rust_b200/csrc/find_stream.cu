@@ -14,8 +14,8 @@
 //   * a CTA belongs to one slice (P = SM count / CTAs per slice), holds that slice's filter in shared memory and
 //     streams the rows' stretches past it with coalesced loads: per index hash one 32-bit multiply and one
 //     shared-memory read; its warps take groups of 32 rows from the slice's counter, no barrier in the loop;
-//   * only the hashes the filter lets through (true hits + ~2 % false positives) go to the exact table in global
-//     memory (the hash-grouped table over the queries, join.cu) and add to the count matrix.  They are parked in the
+//   * only the hashes the filter lets through (true hits + ~1 % false positives) go to the exact table in global
+//     memory (hash -> list of the queries holding it, built in one pass) and add to the count matrix.  They are parked in the
 //     warp's shared-memory queue and resolved 32 at a time when it fills, so that a warp step does not wait for an
 //     off-chip table read (with the lookup inline, half of all warp steps stalled on one: 566 GB/s).
 #include <algorithm>
@@ -109,20 +109,56 @@ struct StreamArgs {
     uint64_t n_rows_total;
     uint32_t P;
     const uint32_t *filters;       // [P][FS_FILTER_WORDS]
-    const unsigned long long *tkey;  // exact table over the query hashes (join.cu: group_insert / group_fill)
-    const uint64_t *toff;
-    const uint32_t *grows;
+    // exact table over the query hashes (qtable_build_kernel): open addressing on the hash; every posting (query hash
+    // occurrence) is a node of its hash's list, node i = posting i of the packed query array
+    const unsigned long long *tkey;
+    const int32_t *thead;          // slot -> first node, -1 = none
+    const int32_t *node_next;
+    const uint32_t *node_q;        // node -> query id
     int log2_t;
-    uint32_t *cmat;                // [bn][ld] counts
+    uint32_t *cmat;                // [bn][ld] counts; all zero on entry
     uint64_t ld;
+    uint32_t *touched_bits;        // bn bits, zero on entry: rows with at least one count
+    uint32_t *touched_rows;        // the same rows as a list ...
+    unsigned long long *n_touched; // ... of this many entries
     uint32_t *work_ctr;            // P zeroed counters: next group of 32 rows of each slice
     uint32_t ctas_per_slice;
 };
 
+// Exact table of the query side, built in ONE pass (no count / scan / fill as the join's grouped table needs): a posting
+// claims the slot of its hash (linear probing, atomicCAS) and pushes itself on the slot's list (atomicExch of the head).
+__global__ void __launch_bounds__(256) qtable_build_kernel(const uint64_t *__restrict__ qh, const uint64_t *__restrict__ qo, uint64_t nq,
+                                                           unsigned long long *tkey, int32_t *thead, int32_t *node_next,
+                                                           uint32_t *node_q, int log2_t) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t T = 1ull << log2_t;
+    for (uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nq; q += warps) {
+        const uint64_t b = qo[q], e = qo[q + 1];
+        for (uint64_t i = b + lane; i < e; i += 32) {
+            const unsigned long long h = qh[i];
+            uint64_t s;
+            if (h == FS_EMPTY) {
+                s = T;   // the one hash that looks like an empty slot has a slot of its own
+            } else {
+                s = (h * 0x9E3779B97F4A7C15ull) >> (64 - log2_t);
+                for (;;) {
+                    unsigned long long cur = tkey[s];
+                    if (cur == FS_EMPTY) cur = atomicCAS(&tkey[s], FS_EMPTY, h);
+                    if (cur == FS_EMPTY || cur == h) break;
+                    s = (s + 1) & (T - 1);
+                }
+            }
+            node_q[i] = (uint32_t)q;
+            node_next[i] = atomicExch(&thead[s], (int32_t)i);
+        }
+    }
+}
+
 // Exact lookup of one hash the filter let through + count matrix update.  Called by all 32 lanes of a warp (lanes
 // without an entry pass have = false); lanes that reach the same (row, query) cell add once.
 __device__ __forceinline__ void stream_resolve(const StreamArgs &a, bool have, uint64_t h, uint64_t row) {
-    uint64_t jb = 0, je = 0;
+    int32_t node = -1;
     if (have) {
         const uint64_t T = 1ull << a.log2_t;
         uint64_t s = (h * 0x9E3779B97F4A7C15ull) >> (64 - a.log2_t);
@@ -136,15 +172,25 @@ __device__ __forceinline__ void stream_resolve(const StreamArgs &a, bool have, u
                 s = (s + 1) & (T - 1);
             }
         }
-        if (s != ~0ull) { jb = __ldg(&a.toff[s]); je = __ldg(&a.toff[s + 1]); }
+        if (s != ~0ull) node = __ldg(&a.thead[s]);
     }
-    const bool found = je > jb;
-    if (!__any_sync(0xFFFFFFFFu, found)) return;   // nothing but false positives of the filter in this step
-    const uint64_t cell = found ? row * a.ld + __ldg(&a.grows[jb]) : (~0ull - (threadIdx.x & 31));
+    const bool found = node >= 0;
+    const unsigned any = __ballot_sync(0xFFFFFFFFu, found);
+    if (!any) return;   // nothing but false positives of the filter in this step
+    const int lane = threadIdx.x & 31;
+    const uint64_t cell = found ? row * a.ld + __ldg(&a.node_q[node]) : (~0ull - lane);
     const unsigned peers = __match_any_sync(0xFFFFFFFFu, cell);
     if (found) {
-        if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&a.cmat[cell], (uint32_t)__popc(peers));
-        for (uint64_t j = jb + 1; j < je; j++) atomicAdd(&a.cmat[row * a.ld + __ldg(&a.grows[j])], 1u);  // hash shared by several queries
+        if (lane == __ffs(peers) - 1) atomicAdd(&a.cmat[cell], (uint32_t)__popc(peers));
+        for (int32_t n = __ldg(&a.node_next[node]); n >= 0; n = __ldg(&a.node_next[n]))   // hash shared by several queries
+            atomicAdd(&a.cmat[row * a.ld + __ldg(&a.node_q[n])], 1u);
+    }
+    // rows that now hold a count: once each into the list the hit pass walks
+    const unsigned same_row = __match_any_sync(0xFFFFFFFFu, found ? row : (~0ull - lane));
+    if (found && lane == __ffs(same_row) - 1) {
+        const uint32_t bit = 1u << (row & 31);
+        const uint32_t old = atomicOr(&a.touched_bits[row >> 5], bit);
+        if (!(old & bit)) a.touched_rows[atomicAdd(a.n_touched, 1ull)] = (uint32_t)row;
     }
 }
 
@@ -232,13 +278,6 @@ __global__ void __launch_bounds__(FS_THREADS, 1) stream_probe_kernel(const Strea
         const uint64_t base = valid ? __ldg(&a.io[a.b0 + r]) : 0;
         const uint32_t s = valid ? __ldg(&po_lo[r]) : 0, e = valid ? __ldg(&po_hi[r]) : 0;
         const int n_in = (int)min((uint64_t)32, a.bn - g);
-        // Each lane asks L2 for its own row's stretch (five or six 128-byte lines) a few steps before the warp gets to
-        // that row: the loads below then find their data in L2, and DRAM latency is off the warp's critical path.
-        auto prefetch_own = [&]() {
-            const char *lo = reinterpret_cast<const char *>(a.ih + base + s), *hi = reinterpret_cast<const char *>(a.ih + base + e);
-            for (const char *q = lo; q < hi; q += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-        };
-        if (lane < 16) prefetch_own();
         // One row per step, software-pipelined: the (up to FS_LOADS) loads of row k + 1 are issued before the hashes of
         // row k are tested.  Two steps per trip with the two register sets swapping roles, so that nothing is copied.
         uint64_t ha[FS_LOADS], hb[FS_LOADS];
@@ -247,7 +286,6 @@ __global__ void __launch_bounds__(FS_THREADS, 1) stream_probe_kernel(const Strea
 #pragma unroll
         for (int u = 0; u < FS_LOADS; u++) ha[u] = (sa + lane + 32 * u < ea) ? __ldcs(seg_a + sa + lane + 32 * u) : 0;
         for (int k = 0; k < n_in; k += 2) {
-            if ((k & 7) == 0 && (lane >> 3) == (k >> 3) + 2) prefetch_own();   // rows k + 16 .. k + 23
             // ---- issue row k + 1 into set b, test row k from set a
             {
                 const int kn = min(k + 1, n_in - 1);
@@ -273,6 +311,36 @@ __global__ void __launch_bounds__(FS_THREADS, 1) stream_probe_kernel(const Strea
     }
     queue_drain(a, q_hash, q_row, q_cnt);
 }
+
+// Hits of one block of index rows from the counts: only rows that received a count are looked at (the list the probe
+// kernel wrote), and every cell, bit and list entry that is read is cleared again, so that the count matrix, the
+// touched-row bitmap and the counters are all-zero for the next block or search without a memset of the whole matrix.
+//   containment (index.rs:146-160): count / |node| > threshold;  similarity of sketches without a num (lib.rs:470-508):
+//   count / (|node| + |query| - count) > threshold.   found[] receives query * bn + row.
+__global__ void __launch_bounds__(256) touched_hits_kernel(uint32_t *cmat, uint64_t bn, uint64_t nq, const uint64_t *__restrict__ row_offsets,
+                                                           uint64_t b0, const uint64_t *__restrict__ q_offsets, double threshold,
+                                                           uint32_t *touched_bits, const uint32_t *__restrict__ touched_rows,
+                                                           const unsigned long long *n_touched, uint64_t *found, uint64_t cap,
+                                                           unsigned long long *n_found) {
+    const unsigned long long nt = *n_touched;
+    for (unsigned long long t = blockIdx.x; t < nt; t += gridDim.x) {
+        const uint64_t i = touched_rows[t];
+        if (threadIdx.x == 0) touched_bits[i >> 5] = 0;   // (several rows of one word: all of them are in the list)
+        const uint64_t la = row_offsets[b0 + i + 1] - row_offsets[b0 + i];
+        for (uint64_t j = threadIdx.x; j < nq; j += blockDim.x) {
+            const uint32_t cm = cmat[i * nq + j];
+            if (cm == 0) continue;
+            cmat[i * nq + j] = 0;
+            double den = (double)la;
+            if (q_offsets) den = (double)(la + (q_offsets[j + 1] - q_offsets[j]) - cm);  // >= 1 when cm >= 1
+            if ((double)cm / den > threshold) {
+                const unsigned long long at = atomicAdd(n_found, 1ull);
+                if (at < cap) found[at] = j * bn + i;
+            }
+        }
+    }
+}
+__global__ void clear_counter_kernel(unsigned long long *p) { *p = 0; }
 
 }  // namespace
 
@@ -308,10 +376,28 @@ void launch_filters_build(const uint64_t *qh, uint64_t n, uint64_t scale, uint64
     filters_build_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(qh, n, scale, top, P, filters);
     SM_LAUNCHED();
 }
+size_t find_stream_table_slots(uint64_t n_postings, int *log2_t_out) {
+    int log2_t = 12;
+    while ((1ull << log2_t) < 2 * n_postings) log2_t++;   // load <= 0.5
+    *log2_t_out = log2_t;
+    return (size_t)1 << log2_t;
+}
+void launch_qtable_build(const uint64_t *qh, const uint64_t *qo, uint64_t nq, uint64_t n_postings, unsigned long long *tkey,
+                         int32_t *thead, int32_t *node_next, uint32_t *node_q, int log2_t, cudaStream_t st) {
+    const size_t T = (size_t)1 << log2_t;
+    ProfScope prof(PROF_SORT, st);
+    SM_CUDA(cudaMemsetAsync(tkey, 0xFF, (T + 1) * 8, st));
+    SM_CUDA(cudaMemsetAsync(thead, 0xFF, (T + 1) * 4, st));
+    if (!nq || !n_postings) return;
+    qtable_build_kernel<<<(unsigned)std::min<uint64_t>((nq * 32 + 255) / 256, 148 * 16), 256, 0, st>>>(qh, qo, nq, tkey, thead, node_next,
+                                                                                                       node_q, log2_t);
+    SM_LAUNCHED();
+}
 void launch_stream_probe(const uint64_t *ih, const uint64_t *io, uint64_t b0, uint64_t bn, const uint32_t *part_off,
                          uint64_t n_rows_total, uint32_t P, const uint32_t *filters, const unsigned long long *tkey,
-                         const uint64_t *toff, const uint32_t *grows, int log2_t, uint32_t *cmat, uint64_t ld, uint32_t *work_ctr,
-                         int sm_count, cudaStream_t st) {
+                         const int32_t *thead, const int32_t *node_next, const uint32_t *node_q, int log2_t, uint32_t *cmat,
+                         uint64_t ld, uint32_t *touched_bits, uint32_t *touched_rows, unsigned long long *n_touched,
+                         uint32_t *work_ctr, int sm_count, cudaStream_t st) {
     if (!bn) return;
     static bool attr_set = false;
     const size_t smem = (size_t)FS_FILTER_WORDS * 4 + (size_t)(FS_THREADS / 32) * FS_QUEUE * 12;
@@ -321,11 +407,21 @@ void launch_stream_probe(const uint64_t *ih, const uint64_t *io, uint64_t b0, ui
     }
     StreamArgs a;
     a.ih = ih; a.io = io; a.b0 = b0; a.bn = bn; a.part_off = part_off; a.n_rows_total = n_rows_total; a.P = P;
-    a.filters = filters; a.tkey = tkey; a.toff = toff; a.grows = grows; a.log2_t = log2_t; a.cmat = cmat; a.ld = ld;
+    a.filters = filters; a.tkey = tkey; a.thead = thead; a.node_next = node_next; a.node_q = node_q; a.log2_t = log2_t;
+    a.cmat = cmat; a.ld = ld; a.touched_bits = touched_bits; a.touched_rows = touched_rows; a.n_touched = n_touched;
     a.work_ctr = work_ctr;
     a.ctas_per_slice = std::max<uint32_t>(1, (uint32_t)sm_count / P);
     ProfScope prof(PROF_FIND, st);
     stream_probe_kernel<<<P * a.ctas_per_slice, FS_THREADS, smem, st>>>(a);
+    SM_LAUNCHED();
+}
+void launch_touched_hits(uint32_t *cmat, uint64_t bn, uint64_t nq, const uint64_t *row_offsets, uint64_t b0, const uint64_t *q_offsets,
+                         double threshold, uint32_t *touched_bits, const uint32_t *touched_rows, unsigned long long *n_touched,
+                         uint64_t *found, uint64_t cap, unsigned long long *n_found, int sm_count, cudaStream_t st) {
+    touched_hits_kernel<<<sm_count * 8, 256, 0, st>>>(cmat, bn, nq, row_offsets, b0, q_offsets, threshold, touched_bits, touched_rows,
+                                                       n_touched, found, cap, n_found);
+    SM_LAUNCHED();
+    clear_counter_kernel<<<1, 1, 0, st>>>(n_touched);
     SM_LAUNCHED();
 }
 

@@ -216,12 +216,21 @@ void launch_part_offsets(const uint64_t *h, const uint64_t *off, uint64_t n_rows
 size_t find_stream_filter_bytes(uint32_t P);
 void launch_filters_build(const uint64_t *qh, uint64_t n, uint64_t scale, uint64_t top, uint32_t P, uint32_t *filters /*zeroed*/,
                           cudaStream_t st);
-// counts of shared hashes of index rows [b0, b0 + bn) x queries into cmat[(row - b0) * ld + query] (zeroed), through the
-// hash-grouped table over the QUERY hashes (launch_group_insert / launch_group_fill)
+// exact table of the query side: hash -> list of its postings (node i = posting i of the packed query array), one pass
+size_t find_stream_table_slots(uint64_t n_postings, int *log2_t_out);   // tkey: slots + 1 u64, thead: slots + 1 i32
+void launch_qtable_build(const uint64_t *qh, const uint64_t *qo, uint64_t nq, uint64_t n_postings, unsigned long long *tkey,
+                         int32_t *thead, int32_t *node_next, uint32_t *node_q, int log2_t, cudaStream_t st);
+// counts of shared hashes of index rows [b0, b0 + bn) x queries into cmat[(row - b0) * ld + query]; cmat, touched_bits
+// (bn bits), *n_touched and the P work counters must be zero on entry; rows that received a count are listed in touched_rows
 void launch_stream_probe(const uint64_t *ih, const uint64_t *io, uint64_t b0, uint64_t bn, const uint32_t *part_off,
                          uint64_t n_rows_total, uint32_t P, const uint32_t *filters, const unsigned long long *tkey,
-                         const uint64_t *toff, const uint32_t *grows, int log2_t, uint32_t *cmat, uint64_t ld, uint32_t *work_ctr /*P zeroed words*/,
-                         int sm_count, cudaStream_t st);
+                         const int32_t *thead, const int32_t *node_next, const uint32_t *node_q, int log2_t, uint32_t *cmat,
+                         uint64_t ld, uint32_t *touched_bits, uint32_t *touched_rows, unsigned long long *n_touched,
+                         uint32_t *work_ctr, int sm_count, cudaStream_t st);
+// hits (query * bn + row) from the counts of the touched rows; clears every cell, bit and counter it reads
+void launch_touched_hits(uint32_t *cmat, uint64_t bn, uint64_t nq, const uint64_t *row_offsets, uint64_t b0, const uint64_t *q_offsets,
+                         double threshold, uint32_t *touched_bits, const uint32_t *touched_rows, unsigned long long *n_touched,
+                         uint64_t *found, uint64_t cap, unsigned long long *n_found, int sm_count, cudaStream_t st);
 
 // dense path for full num sketches: dense u32 ranks + fixed-length walk (join.cu)
 void launch_scatter_ranks(const uint64_t *keys, const uint64_t *vals, const uint64_t *pre, uint64_t n, uint32_t L,
