@@ -153,7 +153,8 @@ void smgpu_compare_path(int32_t path);
  * without a num): 0 (default) = an index that is large against the query batch is STREAMED once past per-slice
  * Bloom filters of the query hashes held in shared memory (the search then runs at the rate HBM delivers the
  * index), anything smaller goes through the join of smgpu_compare_matrix; 1 = always the join; 2 = stream whenever
- * the shapes allow it.  Results are identical. */
+ * the shapes allow it; 3 = as 2 with a tiny buffer for the deferred lookups, which exercises the re-run of a
+ * block whose hits overflow it (tests).  Results are identical. */
 void smgpu_find_path(int32_t path);
 /* Batch sketching of several k-sizes over the same sequences (smgpu_add_* with more than one
  * handle): on (default) = sketches with distinct k in {21, 31, 51} and one seed share a fused

@@ -221,8 +221,8 @@ def compare_path(path="auto"):
 
 
 def find_path(path="auto"):
-    """'auto' | 'join' | 'stream' (smgpu_find_path)"""
-    lib().smgpu_find_path({"auto": 0, "join": 1, "stream": 2}[path])
+    """'auto' | 'join' | 'stream' | 'stream_small_spill' (smgpu_find_path)"""
+    lib().smgpu_find_path({"auto": 0, "join": 1, "stream": 2, "stream_small_spill": 3}[path])
 
 
 def fuse_multi_k(on=True):

@@ -134,7 +134,8 @@ static uint64_t find_block_cells_from_env() {
 }
 static const uint64_t g_find_block_cells = find_block_cells_from_env();
 // linear_find's count path: 0 = stream the index (find_stream.cu) when it is large against the query batch,
-// 1 = always the general join, 2 = stream whenever the shapes allow it, whatever the sizes (tests).  SMB200_FIND_PATH sets it.
+// 1 = always the general join, 2 = stream whenever the shapes allow it, whatever the sizes (tests), 3 = as 2 with a tiny
+// buffer for the written-out filter hits, which forces the re-run with in-kernel lookups (tests).  SMB200_FIND_PATH sets it.
 int g_find_path = [] {
     const char *e = getenv("SMB200_FIND_PATH");
     return e ? atoi(e) : 0;
@@ -517,7 +518,7 @@ std::vector<std::vector<uint64_t>> linear_find_lists(SketchCollection &index, Sk
         // a large index against a (much) smaller query batch: stream the index at HBM rate (find_stream.cu)
         const bool stream = count_path && g_find_path != 1 && queries.n_hashes > 0 && queries.n_hashes < (1ull << 31) && nq < (1ull << 31) &&
                             index.max_len < (1u << 31) &&
-                            (g_find_path == 2 || (index.n_hashes >= 4 * queries.n_hashes && index.n_hashes >= (1ull << 22)));
+                            (g_find_path >= 2 || (index.n_hashes >= 4 * queries.n_hashes && index.n_hashes >= (1ull << 22)));
         int q_log2_t = 0;
         if (stream) index.ensure_partitions();
         ctx.misc[3].reserve((cells + 1) * 8);      // flags, [query][index row] / the hit list of the count paths
@@ -538,9 +539,13 @@ std::vector<std::vector<uint64_t>> linear_find_lists(SketchCollection &index, Sk
                     ctx.join[1].reserve((T + 2) * 4);
                     ctx.join[6].reserve((queries.n_hashes + 1) * 4);
                     ctx.join[7].reserve((queries.n_hashes + 1) * 4);
+                    // the exact table is built on a second stream while the index streams past the filters
+                    SM_CUDA(cudaEventRecord(ctx.prep_event, st));
+                    SM_CUDA(cudaStreamWaitEvent(ctx.k_streams[0], ctx.prep_event, 0));
                     launch_qtable_build(queries.d_hashes.as<uint64_t>(), queries.d_offsets.as<uint64_t>(), nq, queries.n_hashes,
                                         ctx.join[0].as<unsigned long long>(), ctx.join[1].as<int32_t>(), ctx.join[6].as<int32_t>(),
-                                        ctx.join[7].as<uint32_t>(), q_log2_t, st);
+                                        ctx.join[7].as<uint32_t>(), q_log2_t, ctx.k_streams[0]);
+                    SM_CUDA(cudaEventRecord(ctx.k_events[0], ctx.k_streams[0]));
                     ctx.misc[6].reserve(find_stream_filter_bytes(index.n_parts) + (size_t)index.n_parts * 4 + 256);
                     SM_CUDA(cudaMemsetAsync(ctx.misc[6].p, 0, find_stream_filter_bytes(index.n_parts), st));
                     launch_filters_build(queries.d_hashes.as<uint64_t>(), queries.n_hashes, index.part_scale, index.part_top,
@@ -560,22 +565,46 @@ std::vector<std::vector<uint64_t>> linear_find_lists(SketchCollection &index, Sk
                 }
                 uint32_t *work_ctr = ctx.misc[6].as<uint32_t>() + find_stream_filter_bytes(index.n_parts) / 4;  // behind the filters
                 SM_CUDA(cudaMemsetAsync(work_ctr, 0, (size_t)index.n_parts * 4, st));
-                launch_stream_probe(index.d_hashes.as<uint64_t>(), index.d_offsets.as<uint64_t>(), b0, bn, index.d_part_off.as<uint32_t>(),
-                                    index.n_rows, index.n_parts, ctx.misc[6].as<uint32_t>(), ctx.join[0].as<unsigned long long>(),
-                                    ctx.join[1].as<int32_t>(), ctx.join[6].as<int32_t>(), ctx.join[7].as<uint32_t>(), q_log2_t,
-                                    ctx.find_cmat.as<uint32_t>(), nq, ctx.find_bits.as<uint32_t>(), ctx.find_rows.as<uint32_t>(),
-                                    ctx.dsc(SC_TOUCHED), work_ctr, ctx.sm_count, st);
-                SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_CNT), 0, 8, st));
-                launch_touched_hits(ctx.find_cmat.as<uint32_t>(), bn, nq, index.d_offsets.as<uint64_t>(), b0,
-                                    count_sim ? queries.d_offsets.as<uint64_t>() : nullptr, threshold, ctx.find_bits.as<uint32_t>(),
-                                    ctx.find_rows.as<uint32_t>(), ctx.dsc(SC_TOUCHED), found, cells, ctx.dsc(SC_CNT), ctx.sm_count, st);
+                // written-out filter hits: room for one in eight index hashes of the block (false positives are ~1 %)
+                const uint64_t blk_hashes = index.h_offsets[b0 + bn] - index.h_offsets[b0];
+                const uint64_t spill_cap = g_find_path == 3 ? 64 : std::min<uint64_t>(std::max<uint64_t>(blk_hashes / 8, 1ull << 20), 1ull << 27);
+                ctx.misc[4].reserve((spill_cap + 1) * 8);
+                ctx.misc[5].reserve((spill_cap + 1) * 4);
+                SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_SPILL), 0, 8, st));
+                auto probe = [&](bool deferred, int phase) {
+                    launch_stream_probe(index.d_hashes.as<uint64_t>(), index.d_offsets.as<uint64_t>(), b0, bn, index.d_part_off.as<uint32_t>(),
+                                        index.n_rows, index.n_parts, ctx.misc[6].as<uint32_t>(), ctx.join[0].as<unsigned long long>(),
+                                        ctx.join[1].as<int32_t>(), ctx.join[6].as<int32_t>(), ctx.join[7].as<uint32_t>(), q_log2_t,
+                                        ctx.find_cmat.as<uint32_t>(), nq, ctx.find_bits.as<uint32_t>(), ctx.find_rows.as<uint32_t>(),
+                                        ctx.dsc(SC_TOUCHED), work_ctr, deferred ? ctx.misc[4].as<uint64_t>() : nullptr, ctx.misc[5].as<uint32_t>(),
+                                        ctx.dsc(SC_SPILL), spill_cap, phase, ctx.sm_count, st);
+                };
+                auto hit_pass = [&]() {
+                    SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_CNT), 0, 8, st));
+                    launch_touched_hits(ctx.find_cmat.as<uint32_t>(), bn, nq, index.d_offsets.as<uint64_t>(), b0,
+                                        count_sim ? queries.d_offsets.as<uint64_t>() : nullptr, threshold, ctx.find_bits.as<uint32_t>(),
+                                        ctx.find_rows.as<uint32_t>(), ctx.dsc(SC_TOUCHED), found, cells, ctx.dsc(SC_CNT), ctx.sm_count, st);
+                };
+                probe(true, 0);
+                if (b0 == 0) SM_CUDA(cudaStreamWaitEvent(st, ctx.k_events[0], 0));   // the table is needed from here on
+                probe(true, 1);
+                hit_pass();
+                ctx.read_scalars();
+                if (ctx.h_scalars[SC_SPILL] > spill_cap) {
+                    // more filter hits than the buffer holds (a heavily related index): the counts were partial (the hit pass
+                    // has wiped them again) -- once more, with the lookups inside the probe kernel
+                    SM_CUDA(cudaMemsetAsync(work_ctr, 0, (size_t)index.n_parts * 4, st));
+                    probe(false, 0);
+                    hit_pass();
+                    ctx.read_scalars();
+                }
             } else {
                 compare_block_device(index, b0, bn, queries, 0, nq, 1, cmat, nullptr, nullptr, nq);
                 SM_CUDA(cudaMemsetAsync(ctx.dsc(SC_CNT), 0, 8, st));
                 launch_count_hits(cmat, bn, nq, index.d_offsets.as<uint64_t>(), b0, count_sim ? queries.d_offsets.as<uint64_t>() : nullptr,
                                   threshold, found, cells, ctx.dsc(SC_CNT), st);
+                ctx.read_scalars();
             }
-            ctx.read_scalars();
             const uint64_t n_hit = ctx.h_scalars[SC_CNT];
             if (n_hit > cells) throw_internal("linear_find: hit list overflow");
             cellbuf.resize(n_hit);

@@ -147,6 +147,7 @@ void set_requested_device(int dev);
 
 enum { SC_FIRST_BAD = 0, SC_NUNIQ = 1, SC_TMAX = 2, SC_CNT = 3, SC_FLAG = 4, SC_LEN = 5, SC_PAIR0 = 6, SC_PAIR1 = 7,
        SC_PAIR2 = 8, SC_THRESH = 9, SC_CAND0 = 10 /* .. SC_CAND0+5: per-handle candidate counters of one batch */,
-       SC_TOUCHED = 16 /* find_stream: rows holding a count; zero between searches */, SC_COUNT = 24 };
+       SC_TOUCHED = 16 /* find_stream: rows holding a count; zero between searches */,
+       SC_SPILL = 17 /* find_stream: hashes written out for the deferred lookup */, SC_COUNT = 24 };
 
 }  // namespace smb200

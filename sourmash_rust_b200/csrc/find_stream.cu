@@ -16,8 +16,11 @@
 //     shared-memory read; its warps take groups of 32 rows from the slice's counter, no barrier in the loop;
 //   * only the hashes the filter lets through (true hits + ~1 % false positives) go to the exact table in global
 //     memory (hash -> list of the queries holding it, built in one pass) and add to the count matrix.  They are parked in the
-//     warp's shared-memory queue and resolved 32 at a time when it fills, so that a warp step does not wait for an
-//     off-chip table read (with the lookup inline, half of all warp steps stalled on one: 566 GB/s).
+//     warp's shared-memory queue, so that a warp step does not wait for an off-chip table read (with the lookup
+//     inline, half of all warp steps stalled on one: 566 GB/s).  Normally the queues are written out to global memory
+//     and looked up by a second kernel: the exact table is BUILT on another stream while the index streams (the build
+//     is a third of a search at BASELINE config 4).  If the written-out list overflows its buffer (a heavily related
+//     index), the block is run again with the lookups done inside the probe kernel, queue by queue.
 #include <algorithm>
 
 #include "device.hpp"
@@ -123,6 +126,12 @@ struct StreamArgs {
     unsigned long long *n_touched; // ... of this many entries
     uint32_t *work_ctr;            // P zeroed counters: next group of 32 rows of each slice
     uint32_t ctas_per_slice;
+    // deferred mode: the hashes the filter lets through are not looked up by the probe kernel at all (the exact table is
+    // being built on another stream meanwhile) but written out; resolve_spill_kernel looks them up afterwards
+    uint64_t *spill_hash;          // nullptr = resolve inside the probe kernel
+    uint32_t *spill_row;
+    unsigned long long *spill_n;   // entries written (may exceed spill_cap: the excess is lost and the host re-runs the block)
+    uint64_t spill_cap;
 };
 
 // Exact table of the query side, built in ONE pass (no count / scan / fill as the join's grouped table needs): a posting
@@ -202,6 +211,16 @@ constexpr uint32_t FS_QUEUE = 192;    // entries per warp (hash u64 + row u32): 
 __device__ __forceinline__ void queue_drain(const StreamArgs &a, const uint64_t *q_hash, const uint32_t *q_row, uint32_t &cnt) {
     __syncwarp();
     const int lane = threadIdx.x & 31;
+    if (a.spill_hash) {   // deferred: one reservation per queue-full, coalesced copies
+        unsigned long long at = 0;
+        if (lane == 0 && cnt) at = atomicAdd(a.spill_n, (unsigned long long)cnt);
+        at = __shfl_sync(0xFFFFFFFFu, at, 0);
+        for (uint32_t i = lane; i < cnt; i += 32)
+            if (at + i < a.spill_cap) { a.spill_hash[at + i] = q_hash[i]; a.spill_row[at + i] = q_row[i]; }
+        __syncwarp();
+        cnt = 0;
+        return;
+    }
     for (uint32_t i0 = 0; i0 < cnt; i0 += 32) {   // warp-uniform
         const bool have = i0 + lane < cnt;
         stream_resolve(a, have, have ? q_hash[i0 + lane] : 0, have ? q_row[i0 + lane] : 0);
@@ -342,6 +361,16 @@ __global__ void __launch_bounds__(256) touched_hits_kernel(uint32_t *cmat, uint6
 }
 __global__ void clear_counter_kernel(unsigned long long *p) { *p = 0; }
 
+// deferred mode: exact lookups of everything the probe kernel wrote out, one entry per thread
+__global__ void __launch_bounds__(256) resolve_spill_kernel(const StreamArgs a) {
+    const unsigned long long n = min(*a.spill_n, (unsigned long long)a.spill_cap);
+    const unsigned long long n_round = (n + 31) / 32 * 32;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const bool have = i < n;   // whole warps stay together: stream_resolve votes
+        stream_resolve(a, have, have ? a.spill_hash[i] : 0, have ? a.spill_row[i] : 0);
+    }
+}
+
 }  // namespace
 
 // ---- host side ---------------------------------------------------------------------------------------------
@@ -397,7 +426,8 @@ void launch_stream_probe(const uint64_t *ih, const uint64_t *io, uint64_t b0, ui
                          uint64_t n_rows_total, uint32_t P, const uint32_t *filters, const unsigned long long *tkey,
                          const int32_t *thead, const int32_t *node_next, const uint32_t *node_q, int log2_t, uint32_t *cmat,
                          uint64_t ld, uint32_t *touched_bits, uint32_t *touched_rows, unsigned long long *n_touched,
-                         uint32_t *work_ctr, int sm_count, cudaStream_t st) {
+                         uint32_t *work_ctr, uint64_t *spill_hash, uint32_t *spill_row, unsigned long long *spill_n, uint64_t spill_cap,
+                         int phase, int sm_count, cudaStream_t st) {
     if (!bn) return;
     static bool attr_set = false;
     const size_t smem = (size_t)FS_FILTER_WORDS * 4 + (size_t)(FS_THREADS / 32) * FS_QUEUE * 12;
@@ -411,9 +441,16 @@ void launch_stream_probe(const uint64_t *ih, const uint64_t *io, uint64_t b0, ui
     a.cmat = cmat; a.ld = ld; a.touched_bits = touched_bits; a.touched_rows = touched_rows; a.n_touched = n_touched;
     a.work_ctr = work_ctr;
     a.ctas_per_slice = std::max<uint32_t>(1, (uint32_t)sm_count / P);
-    ProfScope prof(PROF_FIND, st);
-    stream_probe_kernel<<<P * a.ctas_per_slice, FS_THREADS, smem, st>>>(a);
-    SM_LAUNCHED();
+    a.spill_hash = spill_hash; a.spill_row = spill_row; a.spill_n = spill_n; a.spill_cap = spill_cap;
+    if (phase == 0) {          // stream the index (deferred when spill_hash is given, else resolving as it goes)
+        ProfScope prof(PROF_FIND, st);
+        stream_probe_kernel<<<P * a.ctas_per_slice, FS_THREADS, smem, st>>>(a);
+        SM_LAUNCHED();
+    } else {                   // deferred mode, second half: look the written-out hashes up
+        ProfScope prof(PROF_PROBE, st);
+        resolve_spill_kernel<<<sm_count * 8, 256, 0, st>>>(a);
+        SM_LAUNCHED();
+    }
 }
 void launch_touched_hits(uint32_t *cmat, uint64_t bn, uint64_t nq, const uint64_t *row_offsets, uint64_t b0, const uint64_t *q_offsets,
                          double threshold, uint32_t *touched_bits, const uint32_t *touched_rows, unsigned long long *n_touched,

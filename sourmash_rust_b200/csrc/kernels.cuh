@@ -226,7 +226,9 @@ void launch_stream_probe(const uint64_t *ih, const uint64_t *io, uint64_t b0, ui
                          uint64_t n_rows_total, uint32_t P, const uint32_t *filters, const unsigned long long *tkey,
                          const int32_t *thead, const int32_t *node_next, const uint32_t *node_q, int log2_t, uint32_t *cmat,
                          uint64_t ld, uint32_t *touched_bits, uint32_t *touched_rows, unsigned long long *n_touched,
-                         uint32_t *work_ctr, int sm_count, cudaStream_t st);
+                         uint32_t *work_ctr, uint64_t *spill_hash /*nullable: resolve inside the kernel*/, uint32_t *spill_row,
+                         unsigned long long *spill_n /*zeroed*/, uint64_t spill_cap, int phase /*0 = stream, 1 = resolve the spill*/,
+                         int sm_count, cudaStream_t st);
 // hits (query * bn + row) from the counts of the touched rows; clears every cell, bit and counter it reads
 void launch_touched_hits(uint32_t *cmat, uint64_t bn, uint64_t nq, const uint64_t *row_offsets, uint64_t b0, const uint64_t *q_offsets,
                          double threshold, uint32_t *touched_bits, const uint32_t *touched_rows, unsigned long long *n_touched,

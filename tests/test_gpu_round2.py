@@ -262,6 +262,9 @@ def test_linear_find_streaming_path(n_index, n_q, lens, mx, num):
                 smb.find_path("stream")
                 got = smb.linear_find(ic, qc, mode, thr)
                 assert got == want, (mode, thr)
+                smb.find_path("stream_small_spill")   # the written-out hits overflow: the block runs again, lookups in the kernel
+                assert smb.linear_find(ic, qc, mode, thr) == want, (mode, thr, "small spill")
+                smb.find_path("stream")
                 n_hits += sum(len(h) for h in got)
                 for q in range(0, n_q, max(1, n_q // 4)):
                     assert got[q] == orc.linear_find(o_index, o_queries[q], mode, thr), (mode, thr, q)
