@@ -519,7 +519,8 @@ std::vector<std::vector<uint64_t>> linear_find_lists(SketchCollection &index, Sk
         const bool stream = count_path && g_find_path != 1 && queries.n_hashes > 0 && queries.n_hashes < (1ull << 31) && nq < (1ull << 31) &&
                             index.max_len < (1u << 31) &&
                             (g_find_path >= 2 || (index.n_hashes >= 4 * queries.n_hashes && index.n_hashes >= (1ull << 22)));
-        int q_log2_t = 0;
+        uint32_t *q_tstart = nullptr;
+        uint64_t q_tscale = 0;
         if (stream) index.ensure_partitions();
         ctx.misc[3].reserve((cells + 1) * 8);      // flags, [query][index row] / the hit list of the count paths
         if (!stream) ctx.misc[2].reserve(cells * 8);  // ratio or counts, [index row][query]
@@ -534,18 +535,19 @@ std::vector<std::vector<uint64_t>> linear_find_lists(SketchCollection &index, Sk
             if (stream) {
                 // the index streams past per-slice Bloom filters of the query hashes held in shared memory (find_stream.cu)
                 if (b0 == 0) {   // the query side: exact table + filters, once per search
-                    const size_t T = find_stream_table_slots(queries.n_hashes, &q_log2_t);
-                    ctx.join[0].reserve((T + 2) * 8);
-                    ctx.join[1].reserve((T + 2) * 4);
-                    ctx.join[6].reserve((queries.n_hashes + 1) * 4);
-                    ctx.join[7].reserve((queries.n_hashes + 1) * 4);
-                    // the exact table is built on a second stream while the index streams past the filters
-                    SM_CUDA(cudaEventRecord(ctx.prep_event, st));
-                    SM_CUDA(cudaStreamWaitEvent(ctx.k_streams[0], ctx.prep_event, 0));
-                    launch_qtable_build(queries.d_hashes.as<uint64_t>(), queries.d_offsets.as<uint64_t>(), nq, queries.n_hashes,
+                    const size_t slots = find_stream_table_slots(queries.n_hashes);
+                    const uint32_t ts = find_stream_table_slices();
+                    ctx.join[0].reserve(slots * 8);                                   // keys
+                    ctx.join[1].reserve(slots * 4);                                   // list heads
+                    ctx.join[6].reserve((queries.n_hashes + 1) * 4);                  // node -> next
+                    ctx.join[7].reserve((queries.n_hashes + 1) * 4);                  // node -> query
+                    ctx.join[2].reserve(((size_t)ts + 1) * (nq + 1) * 4);             // where each query meets each table slice
+                    ctx.join[3].reserve(((size_t)ts + 2) * 8 + ((size_t)ts + 2) * 4); // sums, then slice starts
+                    q_tstart = reinterpret_cast<uint32_t *>(ctx.join[3].as<unsigned long long>() + ts + 2);
+                    launch_qtable_build(queries.d_hashes.as<uint64_t>(), queries.d_offsets.as<uint64_t>(), nq, index.part_top,
+                                        ctx.join[2].as<uint32_t>(), ctx.join[3].as<unsigned long long>(), q_tstart,
                                         ctx.join[0].as<unsigned long long>(), ctx.join[1].as<int32_t>(), ctx.join[6].as<int32_t>(),
-                                        ctx.join[7].as<uint32_t>(), q_log2_t, ctx.k_streams[0]);
-                    SM_CUDA(cudaEventRecord(ctx.k_events[0], ctx.k_streams[0]));
+                                        ctx.join[7].as<uint32_t>(), &q_tscale, st);
                     ctx.misc[6].reserve(find_stream_filter_bytes(index.n_parts) + (size_t)index.n_parts * 4 + 256);
                     SM_CUDA(cudaMemsetAsync(ctx.misc[6].p, 0, find_stream_filter_bytes(index.n_parts), st));
                     launch_filters_build(queries.d_hashes.as<uint64_t>(), queries.n_hashes, index.part_scale, index.part_top,
@@ -574,8 +576,8 @@ std::vector<std::vector<uint64_t>> linear_find_lists(SketchCollection &index, Sk
                 auto probe = [&](bool deferred, int phase) {
                     launch_stream_probe(index.d_hashes.as<uint64_t>(), index.d_offsets.as<uint64_t>(), b0, bn, index.d_part_off.as<uint32_t>(),
                                         index.n_rows, index.n_parts, ctx.misc[6].as<uint32_t>(), ctx.join[0].as<unsigned long long>(),
-                                        ctx.join[1].as<int32_t>(), ctx.join[6].as<int32_t>(), ctx.join[7].as<uint32_t>(), q_log2_t,
-                                        ctx.find_cmat.as<uint32_t>(), nq, ctx.find_bits.as<uint32_t>(), ctx.find_rows.as<uint32_t>(),
+                                        ctx.join[1].as<int32_t>(), ctx.join[6].as<int32_t>(), ctx.join[7].as<uint32_t>(), q_tstart, q_tscale,
+                                        index.part_top, ctx.find_cmat.as<uint32_t>(), nq, ctx.find_bits.as<uint32_t>(), ctx.find_rows.as<uint32_t>(),
                                         ctx.dsc(SC_TOUCHED), work_ctr, deferred ? ctx.misc[4].as<uint64_t>() : nullptr, ctx.misc[5].as<uint32_t>(),
                                         ctx.dsc(SC_SPILL), spill_cap, phase, ctx.sm_count, st);
                 };
@@ -586,7 +588,6 @@ std::vector<std::vector<uint64_t>> linear_find_lists(SketchCollection &index, Sk
                                         ctx.find_rows.as<uint32_t>(), ctx.dsc(SC_TOUCHED), found, cells, ctx.dsc(SC_CNT), ctx.sm_count, st);
                 };
                 probe(true, 0);
-                if (b0 == 0) SM_CUDA(cudaStreamWaitEvent(st, ctx.k_events[0], 0));   // the table is needed from here on
                 probe(true, 1);
                 hit_pass();
                 ctx.read_scalars();

@@ -15,7 +15,7 @@
 //     streams the rows' stretches past it with coalesced loads: per index hash one 32-bit multiply and one
 //     shared-memory read; its warps take groups of 32 rows from the slice's counter, no barrier in the loop;
 //   * only the hashes the filter lets through (true hits + ~1 % false positives) go to the exact table in global
-//     memory (hash -> list of the queries holding it, built in one pass) and add to the count matrix.  They are parked in the
+//     memory (hash -> list of the queries holding it; built slice by slice in shared memory) and add to the count matrix.  They are parked in the
 //     warp's shared-memory queue, so that a warp step does not wait for an off-chip table read (with the lookup
 //     inline, half of all warp steps stalled on one: 566 GB/s).  Normally the queues are written out to global memory
 //     and looked up by a second kernel: the exact table is BUILT on another stream while the index streams (the build
@@ -112,13 +112,15 @@ struct StreamArgs {
     uint64_t n_rows_total;
     uint32_t P;
     const uint32_t *filters;       // [P][FS_FILTER_WORDS]
-    // exact table over the query hashes (qtable_build_kernel): open addressing on the hash; every posting (query hash
+    // exact table over the query hashes (qtable_*_kernel): the hash range is cut into QT_SLICES table slices, slice t
+    // owns slots [tstart[t], tstart[t + 1]) (twice its keys), open addressing inside; every posting (query hash
     // occurrence) is a node of its hash's list, node i = posting i of the packed query array
     const unsigned long long *tkey;
     const int32_t *thead;          // slot -> first node, -1 = none
     const int32_t *node_next;
     const uint32_t *node_q;        // node -> query id
-    int log2_t;
+    const uint32_t *tstart;        // QT_SLICES + 1
+    uint64_t tscale, top;          // table slice of h = min(QT_SLICES - 1, mulhi(h, tscale)); no key above top
     uint32_t *cmat;                // [bn][ld] counts; all zero on entry
     uint64_t ld;
     uint32_t *touched_bits;        // bn bits, zero on entry: rows with at least one count
@@ -134,33 +136,84 @@ struct StreamArgs {
     uint64_t spill_cap;
 };
 
-// Exact table of the query side, built in ONE pass (no count / scan / fill as the join's grouped table needs): a posting
-// claims the slot of its hash (linear probing, atomicCAS) and pushes itself on the slot's list (atomicExch of the head).
-__global__ void __launch_bounds__(256) qtable_build_kernel(const uint64_t *__restrict__ qh, const uint64_t *__restrict__ qo, uint64_t nq,
-                                                           unsigned long long *tkey, int32_t *thead, int32_t *node_next,
-                                                           uint32_t *node_q, int log2_t) {
-    const int lane = threadIdx.x & 31;
-    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const uint64_t T = 1ull << log2_t;
-    for (uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nq; q += warps) {
-        const uint64_t b = qo[q], e = qo[q + 1];
-        for (uint64_t i = b + lane; i < e; i += 32) {
-            const unsigned long long h = qh[i];
-            uint64_t s;
-            if (h == FS_EMPTY) {
-                s = T;   // the one hash that looks like an empty slot has a slot of its own
-            } else {
-                s = (h * 0x9E3779B97F4A7C15ull) >> (64 - log2_t);
-                for (;;) {
-                    unsigned long long cur = tkey[s];
-                    if (cur == FS_EMPTY) cur = atomicCAS(&tkey[s], FS_EMPTY, h);
-                    if (cur == FS_EMPTY || cur == h) break;
-                    s = (s + 1) & (T - 1);
-                }
-            }
-            node_q[i] = (uint32_t)q;
-            node_next[i] = atomicExch(&thead[s], (int32_t)i);
+// ---- exact table of the query side --------------------------------------------------------------------------------
+// Global atomics are the slow way to build a hash table (5 M postings: 0.87 ms, a third of a search).  Instead the hash
+// range is cut into QT_SLICES table slices of a few thousand keys; a sorted query meets a slice in one stretch (bounds
+// from part_offsets_kernel, as for the index); ONE CTA builds a slice's part of the table in SHARED memory and writes
+// it out finished, so that the table needs no memset and no global atomic at all.  A slice too large for shared memory
+// (a skewed hash distribution) is built in place with global atomics by the same CTA.
+constexpr uint32_t QT_SLICES = 1024;
+constexpr uint32_t QT_SMEM_SLOTS = 12288;   // 12288 x (8 + 4) B = 144 KB
+
+__device__ __forceinline__ uint32_t qt_hash32(uint64_t h) { return ((uint32_t)h ^ (uint32_t)(h >> 32)) * 0x85EBCA6Bu; }
+
+// S[t] = sum over the queries of qpo[t][q]  (slot counts follow from differences)
+__global__ void __launch_bounds__(128) qt_sums_kernel(const uint32_t *__restrict__ qpo, uint64_t nq, unsigned long long *sums) {
+    const uint32_t t = blockIdx.x;
+    unsigned long long acc = 0;
+    for (uint64_t q = threadIdx.x; q < nq; q += blockDim.x) acc += qpo[(uint64_t)t * nq + q];
+    for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+    __shared__ unsigned long long part[4];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) sums[t] = part[0] + part[1] + part[2] + part[3];
+}
+// tstart[t] = first slot of slice t: every slice gets twice its postings + 32 slots
+__global__ void __launch_bounds__(1024) qt_starts_kernel(const unsigned long long *__restrict__ sums, uint32_t *tstart) {
+    __shared__ uint32_t sz[QT_SLICES];
+    const uint32_t t = threadIdx.x;
+    sz[t] = (uint32_t)(2 * (sums[t + 1] - sums[t]) + 32);
+    __syncthreads();
+    if (t == 0) {
+        uint32_t acc = 0;
+        for (uint32_t i = 0; i < QT_SLICES; i++) { tstart[i] = acc; acc += sz[i]; }
+        tstart[QT_SLICES] = acc;
+    }
+}
+template <bool SHARED>
+__device__ __forceinline__ void qt_insert(unsigned long long *key, int32_t *head, uint32_t size, unsigned long long h, int32_t node,
+                                          int32_t *node_next) {
+    uint32_t s = __umulhi(qt_hash32(h), size);
+    for (;;) {
+        unsigned long long cur = key[s];
+        if (cur == FS_EMPTY) cur = atomicCAS(&key[s], FS_EMPTY, h);
+        if (cur == FS_EMPTY || cur == h) break;
+        s = s + 1 == size ? 0 : s + 1;
+    }
+    node_next[node] = atomicExch(&head[s], node);
+}
+__global__ void __launch_bounds__(256) qtable_slice_kernel(const uint64_t *__restrict__ qh, const uint64_t *__restrict__ qo, uint64_t nq,
+                                                           const uint32_t *__restrict__ qpo, const uint32_t *__restrict__ tstart,
+                                                           uint64_t top, unsigned long long *tkey, int32_t *thead, int32_t *node_next,
+                                                           uint32_t *node_q) {
+    extern __shared__ __align__(16) unsigned long long s_key[];
+    const uint32_t t = blockIdx.x;
+    const uint32_t start = tstart[t], size = tstart[t + 1] - start;
+    const bool in_smem = size <= QT_SMEM_SLOTS;
+    unsigned long long *key = in_smem ? s_key : tkey + start;
+    int32_t *head = in_smem ? reinterpret_cast<int32_t *>(s_key + QT_SMEM_SLOTS) : thead + start;
+    for (uint32_t i = threadIdx.x; i < size; i += blockDim.x) { key[i] = FS_EMPTY; head[i] = -1; }
+    if (t == 0 && threadIdx.x == 0) {   // the slot of its own of the one hash that looks like an empty slot
+        tkey[tstart[QT_SLICES]] = FS_EMPTY;
+        thead[tstart[QT_SLICES]] = -1;
+    }
+    __syncthreads();
+    // a thread takes a query at a time: the (few) postings of that query inside this slice
+    for (uint64_t q = threadIdx.x; q < nq; q += blockDim.x) {
+        const uint64_t b = qo[q];
+        const uint32_t lo = qpo[(uint64_t)t * nq + q], hi = qpo[(uint64_t)(t + 1) * nq + q];
+        for (uint32_t i = lo; i < hi; i++) {
+            const unsigned long long h = qh[b + i];
+            node_q[b + i] = (uint32_t)q;
+            if (h > top) { node_next[b + i] = -1; continue; }   // cannot occur in the index
+            if (h == FS_EMPTY) { node_next[b + i] = atomicExch(&thead[tstart[QT_SLICES]], (int32_t)(b + i)); continue; }
+            if (in_smem) qt_insert<true>(key, head, size, h, (int32_t)(b + i), node_next);
+            else qt_insert<false>(key, head, size, h, (int32_t)(b + i), node_next);
         }
+    }
+    if (in_smem) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < size; i += blockDim.x) { tkey[start + i] = key[i]; thead[start + i] = head[i]; }
     }
 }
 
@@ -168,20 +221,21 @@ __global__ void __launch_bounds__(256) qtable_build_kernel(const uint64_t *__res
 // without an entry pass have = false); lanes that reach the same (row, query) cell add once.
 __device__ __forceinline__ void stream_resolve(const StreamArgs &a, bool have, uint64_t h, uint64_t row) {
     int32_t node = -1;
-    if (have) {
-        const uint64_t T = 1ull << a.log2_t;
-        uint64_t s = (h * 0x9E3779B97F4A7C15ull) >> (64 - a.log2_t);
+    if (have && h <= a.top) {
         if (h == FS_EMPTY) {
-            s = T;
+            node = __ldg(&a.thead[__ldg(&a.tstart[QT_SLICES])]);
         } else {
+            const unsigned long long tq = __umul64hi((unsigned long long)h, (unsigned long long)a.tscale);
+            const uint32_t t = tq < QT_SLICES - 1 ? (uint32_t)tq : QT_SLICES - 1;
+            const uint32_t start = __ldg(&a.tstart[t]), size = __ldg(&a.tstart[t + 1]) - start;
+            uint32_t s = __umulhi(qt_hash32(h), size);
             for (;;) {
-                const unsigned long long cur = __ldg(&a.tkey[s]);
-                if (cur == h) break;
-                if (cur == FS_EMPTY) { s = ~0ull; break; }
-                s = (s + 1) & (T - 1);
+                const unsigned long long cur = __ldg(&a.tkey[start + s]);
+                if (cur == h) { node = __ldg(&a.thead[start + s]); break; }
+                if (cur == FS_EMPTY) break;
+                s = s + 1 == size ? 0 : s + 1;
             }
         }
-        if (s != ~0ull) node = __ldg(&a.thead[s]);
     }
     const bool found = node >= 0;
     const unsigned any = __ballot_sync(0xFFFFFFFFu, found);
@@ -405,29 +459,36 @@ void launch_filters_build(const uint64_t *qh, uint64_t n, uint64_t scale, uint64
     filters_build_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(qh, n, scale, top, P, filters);
     SM_LAUNCHED();
 }
-size_t find_stream_table_slots(uint64_t n_postings, int *log2_t_out) {
-    int log2_t = 12;
-    while ((1ull << log2_t) < 2 * n_postings) log2_t++;   // load <= 0.5
-    *log2_t_out = log2_t;
-    return (size_t)1 << log2_t;
-}
-void launch_qtable_build(const uint64_t *qh, const uint64_t *qo, uint64_t nq, uint64_t n_postings, unsigned long long *tkey,
-                         int32_t *thead, int32_t *node_next, uint32_t *node_q, int log2_t, cudaStream_t st) {
-    const size_t T = (size_t)1 << log2_t;
+// Exact table of the query side.  qpo: (QT_SLICES + 1) x nq u32 scratch; sums: QT_SLICES + 1 u64 scratch; tstart: QT_SLICES + 1 u32;
+// tkey / thead: find_stream_table_slots(n_postings) entries; node_next / node_q: n_postings entries.
+size_t find_stream_table_slots(uint64_t n_postings) { return (size_t)(2 * n_postings + 32ull * QT_SLICES + 2); }
+uint32_t find_stream_table_slices() { return QT_SLICES; }
+void launch_qtable_build(const uint64_t *qh, const uint64_t *qo, uint64_t nq, uint64_t top, uint32_t *qpo, unsigned long long *sums,
+                         uint32_t *tstart, unsigned long long *tkey, int32_t *thead, int32_t *node_next, uint32_t *node_q,
+                         uint64_t *tscale_out, cudaStream_t st) {
+    const uint64_t tscale = find_stream_scale(top, QT_SLICES);
+    *tscale_out = tscale;
     ProfScope prof(PROF_SORT, st);
-    SM_CUDA(cudaMemsetAsync(tkey, 0xFF, (T + 1) * 8, st));
-    SM_CUDA(cudaMemsetAsync(thead, 0xFF, (T + 1) * 4, st));
-    if (!nq || !n_postings) return;
-    qtable_build_kernel<<<(unsigned)std::min<uint64_t>((nq * 32 + 255) / 256, 148 * 16), 256, 0, st>>>(qh, qo, nq, tkey, thead, node_next,
-                                                                                                       node_q, log2_t);
+    launch_part_offsets(qh, qo, nq, tscale, QT_SLICES, qpo, st);
+    qt_sums_kernel<<<QT_SLICES + 1, 128, 0, st>>>(qpo, nq, sums);
+    SM_LAUNCHED();
+    qt_starts_kernel<<<1, QT_SLICES, 0, st>>>(sums, tstart);
+    SM_LAUNCHED();
+    static bool attr_set = false;
+    const size_t smem = (size_t)QT_SMEM_SLOTS * 12;
+    if (!attr_set) {
+        SM_CUDA(cudaFuncSetAttribute(qtable_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    qtable_slice_kernel<<<QT_SLICES, 256, smem, st>>>(qh, qo, nq, qpo, tstart, top, tkey, thead, node_next, node_q);
     SM_LAUNCHED();
 }
 void launch_stream_probe(const uint64_t *ih, const uint64_t *io, uint64_t b0, uint64_t bn, const uint32_t *part_off,
                          uint64_t n_rows_total, uint32_t P, const uint32_t *filters, const unsigned long long *tkey,
-                         const int32_t *thead, const int32_t *node_next, const uint32_t *node_q, int log2_t, uint32_t *cmat,
-                         uint64_t ld, uint32_t *touched_bits, uint32_t *touched_rows, unsigned long long *n_touched,
-                         uint32_t *work_ctr, uint64_t *spill_hash, uint32_t *spill_row, unsigned long long *spill_n, uint64_t spill_cap,
-                         int phase, int sm_count, cudaStream_t st) {
+                         const int32_t *thead, const int32_t *node_next, const uint32_t *node_q, const uint32_t *tstart, uint64_t tscale,
+                         uint64_t top, uint32_t *cmat, uint64_t ld, uint32_t *touched_bits, uint32_t *touched_rows,
+                         unsigned long long *n_touched, uint32_t *work_ctr, uint64_t *spill_hash, uint32_t *spill_row,
+                         unsigned long long *spill_n, uint64_t spill_cap, int phase, int sm_count, cudaStream_t st) {
     if (!bn) return;
     static bool attr_set = false;
     const size_t smem = (size_t)FS_FILTER_WORDS * 4 + (size_t)(FS_THREADS / 32) * FS_QUEUE * 12;
@@ -437,7 +498,8 @@ void launch_stream_probe(const uint64_t *ih, const uint64_t *io, uint64_t b0, ui
     }
     StreamArgs a;
     a.ih = ih; a.io = io; a.b0 = b0; a.bn = bn; a.part_off = part_off; a.n_rows_total = n_rows_total; a.P = P;
-    a.filters = filters; a.tkey = tkey; a.thead = thead; a.node_next = node_next; a.node_q = node_q; a.log2_t = log2_t;
+    a.filters = filters; a.tkey = tkey; a.thead = thead; a.node_next = node_next; a.node_q = node_q; a.tstart = tstart;
+    a.tscale = tscale; a.top = top;
     a.cmat = cmat; a.ld = ld; a.touched_bits = touched_bits; a.touched_rows = touched_rows; a.n_touched = n_touched;
     a.work_ctr = work_ctr;
     a.ctas_per_slice = std::max<uint32_t>(1, (uint32_t)sm_count / P);

@@ -216,16 +216,20 @@ void launch_part_offsets(const uint64_t *h, const uint64_t *off, uint64_t n_rows
 size_t find_stream_filter_bytes(uint32_t P);
 void launch_filters_build(const uint64_t *qh, uint64_t n, uint64_t scale, uint64_t top, uint32_t P, uint32_t *filters /*zeroed*/,
                           cudaStream_t st);
-// exact table of the query side: hash -> list of its postings (node i = posting i of the packed query array), one pass
-size_t find_stream_table_slots(uint64_t n_postings, int *log2_t_out);   // tkey: slots + 1 u64, thead: slots + 1 i32
-void launch_qtable_build(const uint64_t *qh, const uint64_t *qo, uint64_t nq, uint64_t n_postings, unsigned long long *tkey,
-                         int32_t *thead, int32_t *node_next, uint32_t *node_q, int log2_t, cudaStream_t st);
+// exact table of the query side: hash -> list of its postings (node i = posting i of the packed query array), built per
+// table slice in shared memory.  qpo: (slices + 1) x nq u32 scratch; sums: slices + 1 u64 scratch; tstart: slices + 1 u32;
+// tkey (u64) / thead (i32): find_stream_table_slots(n_postings) entries; node_next (i32) / node_q (u32): n_postings entries
+size_t find_stream_table_slots(uint64_t n_postings);
+uint32_t find_stream_table_slices();
+void launch_qtable_build(const uint64_t *qh, const uint64_t *qo, uint64_t nq, uint64_t top, uint32_t *qpo, unsigned long long *sums,
+                         uint32_t *tstart, unsigned long long *tkey, int32_t *thead, int32_t *node_next, uint32_t *node_q,
+                         uint64_t *tscale_out, cudaStream_t st);
 // counts of shared hashes of index rows [b0, b0 + bn) x queries into cmat[(row - b0) * ld + query]; cmat, touched_bits
 // (bn bits), *n_touched and the P work counters must be zero on entry; rows that received a count are listed in touched_rows
 void launch_stream_probe(const uint64_t *ih, const uint64_t *io, uint64_t b0, uint64_t bn, const uint32_t *part_off,
                          uint64_t n_rows_total, uint32_t P, const uint32_t *filters, const unsigned long long *tkey,
-                         const int32_t *thead, const int32_t *node_next, const uint32_t *node_q, int log2_t, uint32_t *cmat,
-                         uint64_t ld, uint32_t *touched_bits, uint32_t *touched_rows, unsigned long long *n_touched,
+                         const int32_t *thead, const int32_t *node_next, const uint32_t *node_q, const uint32_t *tstart, uint64_t tscale,
+                         uint64_t top, uint32_t *cmat, uint64_t ld, uint32_t *touched_bits, uint32_t *touched_rows, unsigned long long *n_touched,
                          uint32_t *work_ctr, uint64_t *spill_hash /*nullable: resolve inside the kernel*/, uint32_t *spill_row,
                          unsigned long long *spill_n /*zeroed*/, uint64_t spill_cap, int phase /*0 = stream, 1 = resolve the spill*/,
                          int sm_count, cudaStream_t st);
