@@ -182,7 +182,7 @@ __device__ __forceinline__ void qt_insert(unsigned long long *key, int32_t *head
     }
     node_next[node] = atomicExch(&head[s], node);
 }
-__global__ void __launch_bounds__(256) qtable_slice_kernel(const uint64_t *__restrict__ qh, const uint64_t *__restrict__ qo, uint64_t nq,
+__global__ void __launch_bounds__(1024) qtable_slice_kernel(const uint64_t *__restrict__ qh, const uint64_t *__restrict__ qo, uint64_t nq,
                                                            const uint32_t *__restrict__ qpo, const uint32_t *__restrict__ tstart,
                                                            uint64_t top, unsigned long long *tkey, int32_t *thead, int32_t *node_next,
                                                            uint32_t *node_q) {
@@ -480,7 +480,7 @@ void launch_qtable_build(const uint64_t *qh, const uint64_t *qo, uint64_t nq, ui
         SM_CUDA(cudaFuncSetAttribute(qtable_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    qtable_slice_kernel<<<QT_SLICES, 256, smem, st>>>(qh, qo, nq, qpo, tstart, top, tkey, thead, node_next, node_q);
+    qtable_slice_kernel<<<QT_SLICES, 1024, smem, st>>>(qh, qo, nq, qpo, tstart, top, tkey, thead, node_next, node_q);
     SM_LAUNCHED();
 }
 void launch_stream_probe(const uint64_t *ih, const uint64_t *io, uint64_t b0, uint64_t bn, const uint32_t *part_off,

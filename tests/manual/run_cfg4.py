@@ -58,18 +58,21 @@ if world > 1:
     smb.comm_init_from_torch()
 smb.profile_enable(True)
 times, local_times = [], []
-for rep in range(4):
+cap = 64 * NQ
+h_offs, h_hits = np.zeros(NQ + 1, dtype=np.uint64), np.zeros(cap, dtype=np.uint64)   # the caller's result buffers (C ABI)
+for rep in range(6):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    hits = smb.linear_find_sharded(index, queries, "containment", 0.1, hits_cap=64 * NQ)   # global ids, every rank
+    total = smb._call("smgpu_linear_find_sharded", index._p, queries._p, 1, 0.1, smb._vp(h_offs), smb._vp(h_hits), cap)   # global ids, every rank
     torch.cuda.synchronize(); times.append(time.perf_counter() - t0)
+    hits = [h_hits[int(h_offs[q]):int(h_offs[q + 1])].tolist() for q in range(NQ)]
     if rep == 0:
         smb.profile_read("find_stream", reset=True)
         smb.profile_read("join_sort", reset=True)
     if "--local" in sys.argv:
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        smb.linear_find(index, queries, "containment", 0.1, hits_cap=64 * NQ)
+        smb._call("smgpu_linear_find", index._p, queries._p, 1, 0.1, smb._vp(h_offs), smb._vp(h_hits), cap)
         torch.cuda.synchronize(); local_times.append(time.perf_counter() - t0)
 kms, kn = smb.profile_read("find_stream", reset=True)
 jms, jn = smb.profile_read("join_sort", reset=True)
