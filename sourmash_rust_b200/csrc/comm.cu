@@ -306,11 +306,12 @@ SketchCollection *compare_matrix_allgather(SketchCollection &local, int mode, ui
     const uint64_t nr = local.n_rows, nc = all->n_rows;
     if (nr == 0 || nc == 0) return all.release();
     if (ld < nc) throw_internal("ld smaller than the block width");
-    if (out_on_device && nr * nc <= (1ull << 26)) {
+    if (out_on_device) {
         compare_block_device(local, 0, nr, *all, 0, nc, mode, common, size, ratio, ld, &jt);
         ctx.sync();
     } else {
-        // large blocks / host output: the blocked path (its first block cannot reuse the table: other row range)
+        // host output: row blocks through device scratch, copied back while the next block runs (a block covers
+        // part of the rows only, so the table built above does not apply)
         compare_matrix(local, 0, nr, *all, 0, nc, mode, common, size, ratio, ld, out_on_device);
     }
     return all.release();

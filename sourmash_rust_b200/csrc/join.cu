@@ -256,6 +256,7 @@ void launch_probe_group(bool count, bool build_cols, const unsigned long long *t
                         unsigned long long *bitmap, uint64_t n_build, unsigned long long *incidences, const uint32_t *filter,
                         int log2_f, cudaStream_t st) {
     if (!np) return;
+    ProfScope prof(PROF_PROBE, st);
     const bool smem_rows = !count && n_build <= PROBE_SMEM_ROWS;
     const size_t smem = smem_rows ? 8 * ((n_build + 31) / 32) * 4 : 0;
     // resident CTAs are limited by the shared-memory bitmaps: size the grid to what fits, a multiple of the SM count
@@ -453,6 +454,7 @@ void launch_fill_cells(const uint64_t *ro, const uint32_t *rnum, uint64_t r0, ui
                        uint64_t nc, int mode, const uint32_t *cmat, uint64_t cld, uint32_t *common, uint32_t *size,
                        double *ratio, uint64_t ld, cudaStream_t st) {
     if (!nr || !nc) return;
+    ProfScope prof(PROF_FILL, st);
     const unsigned gx = (unsigned)std::min<uint64_t>((nc + 255) / 256, 64);
     const unsigned gy = (unsigned)std::min<uint64_t>(nr, std::max<uint64_t>(1, (148 * 32) / gx));
     fill_cells_kernel<<<dim3(gx, gy), 256, 0, st>>>(ro, rnum, r0, nr, co, c0, nc, mode, cmat, cld, common, size, ratio, ld);
@@ -485,25 +487,27 @@ __global__ void __launch_bounds__(256) walk_pairs_kernel(const uint64_t *__restr
         const uint32_t limit = num ? num : 0xFFFFFFFFu;
         const uint64_t *a = rh + ab, *b = ch + bb;
         uint32_t x_i = 0, y_j = 0, c = 0, u = 0;
-        // lib.rs:470-499 in one pass.  The element after the current one is loaded one step ahead on both
-        // sides (whichever side advances, its next element is already in a register), so the load latency
-        // overlaps the compare chain instead of heading it.
-        uint64_t x = na ? __ldg(a) : 0, y = nb ? __ldg(b) : 0;
-        uint64_t xn = na > 1 ? __ldg(a + 1) : 0, yn = nb > 1 ? __ldg(b + 1) : 0;
-        while (x_i < na && y_j < nb && u < limit) {
-            const bool adv_a = x <= y, adv_b = y <= x;
-            c += (x == y);
-            if (adv_a) {
-                x_i++;
-                x = xn;
-                if (x_i + 1 < na) xn = __ldg(a + x_i + 1);
+        // lib.rs:470-499 in one pass.  The walk goes in stretches of s = min(left in A, left in B, left of the limit)
+        // steps: a step advances either side by at most one element, so inside a stretch neither list can run out and
+        // the step needs no bounds test at all -- two 64-bit compares, the count, and per side a predicated
+        // "take the element loaded one step ahead, load the one after it" (a row is followed by at least two readable
+        // hashes: the next row's, or the slack at the end of the CSR).  Lists of similar length need 2-4 stretches.
+        const uint64_t *pa = a, *pb = b;
+        uint64_t x = __ldg(pa), y = __ldg(pb);
+        uint64_t xn = __ldg(pa + 1), yn = __ldg(pb + 1);
+        for (;;) {
+            uint32_t s = min(min(na - x_i, nb - y_j), limit - u);
+            if (s == 0) break;
+            u += s;
+#pragma unroll 2
+            for (; s; s--) {
+                const bool adv_a = x <= y, adv_b = y <= x;
+                c += (adv_a && adv_b);
+                if (adv_a) { x = xn; pa++; xn = __ldg(pa + 1); }
+                if (adv_b) { y = yn; pb++; yn = __ldg(pb + 1); }
             }
-            if (adv_b) {
-                y_j++;
-                y = yn;
-                if (y_j + 1 < nb) yn = __ldg(b + y_j + 1);
-            }
-            u++;
+            x_i = (uint32_t)(pa - a);
+            y_j = (uint32_t)(pb - b);
         }
         const uint64_t uni = (uint64_t)u + (na - x_i) + (nb - y_j);
         const uint32_t sz = (uint32_t)((num != 0 && uni >= num) ? num : uni);
@@ -518,6 +522,7 @@ void launch_walk_pairs(const uint64_t *pairs, uint64_t n_pairs, const uint64_t *
                        uint32_t *size, double *ratio, uint64_t ld, cudaStream_t st, const uint64_t *n_dev_a,
                        const uint64_t *n_dev_b, uint64_t nr_transposed) {
     if (!n_pairs) return;
+    ProfScope prof(PROF_WALK, st);
     walk_pairs_kernel<<<blocks_for(n_pairs, 256, 148 * 16), 256, 0, st>>>(pairs, n_pairs, rh, ro, rnum, r0, ch, co, c0, nc, common,
                                                                         size, ratio, ld, n_dev_a, n_dev_b, nr_transposed);
     SM_LAUNCHED();

@@ -5,9 +5,10 @@ sharded over the GPUs of one node.  Launch with torchrun (one process per GPU):
         tests/manual/run_cfg5.py --genomes 100000 --cluster 100
 
 Each rank generates its own genomes on the device (clusters of related genomes: a random root, members with
-0.1-5 % substitutions), sketches them in one pass (smgpu_sketch_collection), the packed sketches are
-all-gathered over NCCL, and each rank computes its row block of the N x N matrix.  Times are device-side,
-max over ranks.  A few cells are checked against the per-object reference ABI."""
+0.1-5 % substitutions), sketches them in one pass (smgpu_sketch_collection); then ONE library call
+(smgpu_compare_matrix_allgather) all-gathers the packed sketches over NCCL inside the library -- building the
+join's hash table over the rank's own rows meanwhile -- and computes the rank's row block of the N x N matrix.
+Times are device-side, max over ranks.  A few cells are checked against the per-object reference ABI."""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
@@ -78,45 +79,43 @@ ref_j, ref_mins = ref[0].compare(ref[1]), [r.mins_np() for r in ref]
 del buf
 torch.cuda.empty_cache()
 
-# ---- exchange: all-gather of the packed sketches (variable row lengths) ---------------------------------------------
+# ---- exchange + compare: all-gather of the packed sketches inside the library, this rank's row block ------------------
 if world > 1:
-    warm = torch.empty(world * 1024, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(warm, torch.zeros(1024, dtype=torch.int64, device=dev))  # communicator set-up is not the exchange
+    smb.comm_init_from_torch()          # NCCL communicator of the library (set-up is not the exchange)
     dist.barrier()
     torch.cuda.synchronize()
-t_x0 = torch.cuda.Event(enable_timing=True); t_x1 = torch.cuda.Event(enable_timing=True); t_c1 = torch.cuda.Event(enable_timing=True)
-t_x0.record()
-h_ptr, o_ptr, total = mine.csr_device()
-my_h = torch.as_tensor(_Ptr(h_ptr, max(1, total)), device=dev)[:total]
-my_o = torch.as_tensor(_Ptr(o_ptr, per + 1), device=dev)
-lens = (my_o[1:] - my_o[:-1]).contiguous()
-from sourmash_rust_b200 import sharding
-full_h, full_o = sharding.allgather_csr(my_h, lens)  # lengths first, then the padded hash arrays; NCCL over NVLink
-if world == 1:
-    full_h = full_h.clone()
-torch.cuda.synchronize()
-t_x1.record()
-# ---- compare: this rank's row block of the N x N matrix -----------------------------------------------------------------
-coll = smb.SketchCollection.from_csr(full_h.data_ptr(), full_o.data_ptr(), N, 0, 31, 42, MAX_HASH, on_device=True)
 common = torch.empty((per, N), dtype=torch.int32, device=dev)
 size = torch.empty((per, N), dtype=torch.int32, device=dev)
 ratio = torch.empty((per, N), dtype=torch.float64, device=dev)
-smb.compare_matrix_device(coll, coll, "compare", lo, per, 0, N, common.data_ptr(), size.data_ptr(), ratio.data_ptr(), N)
+t_x0 = torch.cuda.Event(enable_timing=True); t_x1 = torch.cuda.Event(enable_timing=True); t_c1 = torch.cuda.Event(enable_timing=True)
+t_x0.record(lib_stream)
+full = smb.collection_allgather(mine)    # exchange alone, for the record
+t_x1.record(lib_stream)
 torch.cuda.synchronize()
-t_c1.record()
+del full
+if world > 1:
+    dist.barrier()
+t_x1b = torch.cuda.Event(enable_timing=True)
+t_x1b.record(lib_stream)
+coll = smb.compare_matrix_allgather_device(mine, "compare", common.data_ptr(), size.data_ptr(), ratio.data_ptr(), N)
+t_c1.record(lib_stream)
 torch.cuda.synchronize()
-exch_ms, cmp_ms = sync_max(t_x0.elapsed_time(t_x1)), sync_max(t_x1.elapsed_time(t_c1))
-# the same block once more: the first call also grew the library's scratch (GBs of hash table) out of fresh device memory
+exch_ms, cmp_ms = sync_max(t_x0.elapsed_time(t_x1)), sync_max(t_x1b.elapsed_time(t_c1))
+# the same once more: the first call also grew the library's scratch (GBs of hash table) out of fresh device memory
 t_w0 = torch.cuda.Event(enable_timing=True); t_w1 = torch.cuda.Event(enable_timing=True)
 if world > 1:
     dist.barrier()
-t_w0.record()
-smb.compare_matrix_device(coll, coll, "compare", lo, per, 0, N, common.data_ptr(), size.data_ptr(), ratio.data_ptr(), N)
-t_w1.record()
+t_w0.record(lib_stream)
+coll = smb.compare_matrix_allgather_device(mine, "compare", common.data_ptr(), size.data_ptr(), ratio.data_ptr(), N)
+t_w1.record(lib_stream)
 torch.cuda.synchronize()
 cmp_warm_ms = sync_max(t_w0.elapsed_time(t_w1))
+all_rows01 = None
 
 # ---- checks ------------------------------------------------------------------------------------------------------------
+h_ptr, o_ptr, total_h = coll.csr_device()
+full_o = torch.as_tensor(_Ptr(o_ptr, N + 1), device=dev)
+full_h = torch.as_tensor(_Ptr(h_ptr, max(1, total_h)), device=dev)
 rows01 = [full_h[int(full_o[lo + i].item()): int(full_o[lo + i + 1].item())].cpu().numpy().view(np.uint64) for i in (0, 1)]
 assert all(np.array_equal(a, b) for a, b in zip(rows01, ref_mins)), "one-pass sketch differs from the per-object ABI"
 assert float(ratio[0, lo + 1].item()) == ref_j, "matrix cell differs from kmerminhash_compare"
@@ -130,10 +129,11 @@ if rank == 0:
         "workload": "cfg5: %d genomes x %d bp, scaled=1000, k=31, clusters of %d; sketch + all-vs-all Jaccard" % (N, L, CLUSTER),
         "n_gpus": world, "genomes_per_gpu": per, "generate_s_per_rank": round(gen_s, 1),
         "sketch_ms": sketch_ms, "sketch_gbp_s": N * L / (sketch_ms * 1e-3) / 1e9,
-        "exchange_ms": exch_ms, "compare_ms": cmp_ms, "compare_again_ms": cmp_warm_ms, "pairs": N * N,
+        "exchange_alone_ms": exch_ms, "exchange_and_compare_ms": cmp_ms, "exchange_and_compare_again_ms": cmp_warm_ms, "pairs": N * N,
         "pairs_per_s": N * N / (cmp_ms * 1e-3), "pairs_per_s_again": N * N / (cmp_warm_ms * 1e-3),
-        "end_to_end_ms": sketch_ms + exch_ms + cmp_ms, "hashes_total": int(full_o[-1].item()),
+        "end_to_end_ms": sketch_ms + cmp_ms, "hashes_total": int(full_o[-1].item()),
         "related_pairs_ratio_gt_0.02": int(rel.item()), "spot_checks": "rows 0,1 and cell (0,1) equal the per-object ABI; diagonal = 1.0"}),
         flush=True)
 if world > 1:
+    smb.comm_destroy()
     dist.destroy_process_group()
