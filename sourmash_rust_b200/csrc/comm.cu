@@ -33,7 +33,8 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -77,7 +78,8 @@ void load_nccl() {
     g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(sym("ncclCommInitRank"));
     g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(sym("ncclCommDestroy"));
     g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(sym("ncclAllGather"));
-    g_nccl.Broadcast = reinterpret_cast<decltype(g_nccl.Broadcast)>(sym("ncclBroadcast"));
+    g_nccl.Send = reinterpret_cast<decltype(g_nccl.Send)>(sym("ncclSend"));
+    g_nccl.Recv = reinterpret_cast<decltype(g_nccl.Recv)>(sym("ncclRecv"));
     g_nccl.GroupStart = reinterpret_cast<decltype(g_nccl.GroupStart)>(sym("ncclGroupStart"));
     g_nccl.GroupEnd = reinterpret_cast<decltype(g_nccl.GroupEnd)>(sym("ncclGroupEnd"));
     g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(sym("ncclGetErrorString"));
@@ -92,11 +94,6 @@ __global__ void put_header_kernel(unsigned long long *dst, unsigned long long a,
 }
 __global__ void words_to_host_kernel(const unsigned long long *src, unsigned long long *dst, int n) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-}
-// lens[i] = offsets[i + 1] - offsets[i]
-__global__ void row_lens_kernel(const uint64_t *__restrict__ offsets, uint64_t n, uint64_t *__restrict__ lens) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) lens[i] = offsets[i + 1] - offsets[i];
 }
 // hits[i] += base for a rank's local row ids
 __global__ void add_base_kernel(uint64_t *__restrict__ v, uint64_t n, uint64_t base) {
@@ -120,14 +117,44 @@ void exchange_headers(const unsigned long long mine[HDR]) {
     SM_CUDA(cudaStreamSynchronize(c.stream));
 }
 
-// variable-size all-gather: rank r's `count[r]` elements land at recv + base[r] (grouped broadcasts: NCCL fuses them)
+// variable-size all-gather: rank r's `count[r]` elements land at recv + base[r].  Equal counts (fixed-width `num`
+// sketches, the usual case): one ncclAllGather.  Otherwise point-to-point sends and receives, which NCCL fuses into one
+// kernel inside a group (called between GroupStart / GroupEnd); the rank's own part is a device copy.
 void allgatherv(const void *send, void *recv, const std::vector<uint64_t> &count, const std::vector<uint64_t> &base,
                 size_t elem_bytes, ncclDataType_t type) {
     Comm &c = g_comm;
-    for (int r = 0; r < c.world; r++) {
-        if (!count[r]) continue;
-        SM_NCCL(g_nccl.Broadcast(send, static_cast<char *>(recv) + base[r] * elem_bytes, count[r], type, r, c.comm, c.stream));
+    bool equal = true;
+    for (int r = 0; r < c.world; r++) equal = equal && count[r] == count[0] && base[r] == (uint64_t)r * count[0];
+    if (equal) {
+        if (count[0]) SM_NCCL(g_nccl.AllGather(send, recv, count[0], type, c.comm, c.stream));
+        return;
     }
+    for (int r = 0; r < c.world; r++) {
+        if (r == c.rank) {
+            if (count[r])
+                SM_CUDA(cudaMemcpyAsync(static_cast<char *>(recv) + base[r] * elem_bytes, send, count[r] * elem_bytes,
+                                        cudaMemcpyDeviceToDevice, c.stream));
+            continue;
+        }
+        if (count[c.rank]) SM_NCCL(g_nccl.Send(send, count[c.rank], type, r, c.comm, c.stream));
+        if (count[r]) SM_NCCL(g_nccl.Recv(static_cast<char *>(recv) + base[r] * elem_bytes, count[r], type, r, c.comm, c.stream));
+    }
+}
+
+// [len, num] per row -> len as u64 (for the scan into offsets) and num
+__global__ void unpack_rowinfo_kernel(const uint2 *__restrict__ info, uint64_t n, uint64_t *__restrict__ lens, uint32_t *__restrict__ nums) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint2 v = info[i];
+        lens[i] = v.x;
+        nums[i] = v.y;
+    }
+}
+// [len, num] of the local rows
+__global__ void pack_rowinfo_kernel(const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ nums, uint64_t n, uint2 *__restrict__ info) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        info[i] = make_uint2((uint32_t)(offsets[i + 1] - offsets[i]), nums[i]);
 }
 
 }  // namespace
@@ -245,28 +272,35 @@ static SketchCollection *allgather_impl(SketchCollection &local, const std::func
     out->d_hashes.reserve((n_hashes + 4) * 8);
     out->d_offsets.reserve((n_rows + 2) * 8);
     out->d_nums.reserve((n_rows + 1) * 4);
-    // row lengths travel as u64 and are scanned into offsets on arrival; this thread's scratch: misc[0] = my
-    // lengths, misc[3] = everybody's (n_rows + 1 entries, the last one zero: its exclusive scan = offsets) -- not
-    // misc[1] or join[*], which the table build that overlaps the transfer uses
+    // per row, [length, num] travel as one 8-byte record; on arrival the lengths are scanned into offsets.  This
+    // thread's scratch: misc[0] = my records, misc[3] = everybody's, misc[2] = lengths as u64 (n_rows + 1 entries, the
+    // last one zero: its exclusive scan = offsets) -- not misc[1] or join[*], which the table build that overlaps the
+    // transfer uses
     ctx.misc[0].reserve((local.n_rows + 1) * 8);
-    ctx.misc[3].reserve((n_rows + 2) * 8);
-    uint64_t *my_lens = ctx.misc[0].as<uint64_t>(), *all_lens = ctx.misc[3].as<uint64_t>();
+    ctx.misc[3].reserve((n_rows + 1) * 8);
+    ctx.misc[2].reserve((n_rows + 2) * 8);
+    uint2 *my_info = ctx.misc[0].as<uint2>(), *all_info = ctx.misc[3].as<uint2>();
+    uint64_t *all_lens = ctx.misc[2].as<uint64_t>();
     if (local.n_rows) {
-        row_lens_kernel<<<(unsigned)std::min<uint64_t>((local.n_rows + 255) / 256, 148 * 8), 256, 0, ctx.stream>>>(
-            local.d_offsets.as<uint64_t>(), local.n_rows, my_lens);
+        pack_rowinfo_kernel<<<(unsigned)std::min<uint64_t>((local.n_rows + 255) / 256, 148 * 8), 256, 0, ctx.stream>>>(
+            local.d_offsets.as<uint64_t>(), local.d_nums.as<uint32_t>(), local.n_rows, my_info);
         SM_LAUNCHED();
     }
     SM_CUDA(cudaMemsetAsync(all_lens + n_rows, 0, 8, ctx.stream));
-    SM_CUDA(cudaEventRecord(c.ev_ready, ctx.stream));       // buffers allocated (stream-ordered) and lengths computed
+    SM_CUDA(cudaEventRecord(c.ev_ready, ctx.stream));       // buffers allocated (stream-ordered) and records packed
     SM_CUDA(cudaStreamWaitEvent(c.stream, c.ev_ready, 0));
     SM_NCCL(g_nccl.GroupStart());
     allgatherv(local.d_hashes.p, out->d_hashes.p, hashes, hash_base, 8, ncclUint64);
-    allgatherv(my_lens, all_lens, rows, row_base, 8, ncclUint64);
-    allgatherv(local.d_nums.p, out->d_nums.p, rows, row_base, 4, ncclUint32);
+    allgatherv(my_info, all_info, rows, row_base, 8, ncclUint64);
     SM_NCCL(g_nccl.GroupEnd());
     SM_CUDA(cudaEventRecord(c.ev_done, c.stream));
     if (before_wait) before_wait();
     SM_CUDA(cudaStreamWaitEvent(ctx.stream, c.ev_done, 0));
+    if (n_rows) {
+        unpack_rowinfo_kernel<<<(unsigned)std::min<uint64_t>((n_rows + 255) / 256, 148 * 8), 256, 0, ctx.stream>>>(
+            all_info, n_rows, all_lens, out->d_nums.as<uint32_t>());
+        SM_LAUNCHED();
+    }
     ctx.scan_tmp.reserve(scan_tmp_bytes(n_rows + 1) + 256);
     scan_exclusive_u64(all_lens, out->d_offsets.as<uint64_t>(), n_rows + 1, ctx.scan_tmp.p, ctx.stream);
     // host mirrors the block logic sizes its work from (collection.cu)
