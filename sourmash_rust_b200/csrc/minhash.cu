@@ -938,6 +938,49 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
 // ---------------------------------------------------------------------------------------------
 // merge / compare
 // ---------------------------------------------------------------------------------------------
+// merge when an abundance vector is NOT as long as its mins.  That state is the reference's own doing: merge
+// truncates mins to num and leaves the abundances as they are (lib.rs:395-400 "TODO: reduce this one too"), and
+// the next merge then walks two iterators of different length (lib.rs:316-389).  What comes out depends on the
+// order of the walk -- an abundance is taken when, and only when, the walk asks that side's iterator for one -- so
+// this (rare) case is replayed by ONE device thread, step by step as the reference takes them:
+//   other-only element: other's next abundance, if it has one left;
+//   common element: other's next, and if there was one, self's next, and if there was one too, their sum;
+//   self-only element: self's next, if there is one;
+//   other runs out first: everything self's abundance iterator still holds; leftover of other: all it still holds.
+__global__ void merge_out_of_step_kernel(const uint64_t *a, uint64_t na, const uint64_t *sa, uint64_t nsa, bool has_sa,
+                                         const uint64_t *b, uint64_t nb, const uint64_t *sb, uint64_t nsb, bool has_sb,
+                                         uint64_t *out, uint64_t *out_ab, unsigned long long *n_out, unsigned long long *n_out_ab) {
+    uint64_t i = 0, j = 0, ia = 0, ib = 0, m = 0, ma = 0;
+    bool broke = false;
+    while (i < na) {
+        if (j >= nb) {  // other exhausted: the rest of self, and ALL that is left of self's abundances
+            while (i < na) out[m++] = a[i++];
+            if (has_sa) while (ia < nsa) out_ab[ma++] = sa[ia++];
+            broke = true;
+            break;
+        }
+        const uint64_t x = b[j], v = a[i];
+        if (x < v) {
+            out[m++] = x; j++;
+            if (has_sb && ib < nsb) out_ab[ma++] = sb[ib++];
+        } else if (x == v) {
+            out[m++] = x; j++; i++;
+            if (has_sb && ib < nsb) {
+                const uint64_t vb = sb[ib++];
+                if (has_sa && ia < nsa) out_ab[ma++] = vb + sa[ia++];
+            }
+        } else {
+            out[m++] = v; i++;
+            if (has_sa && ia < nsa) out_ab[ma++] = sa[ia++];
+        }
+    }
+    (void)broke;
+    while (j < nb) out[m++] = b[j++];
+    if (has_sb) while (ib < nsb) out_ab[ma++] = sb[ib++];
+    *n_out = m;
+    *n_out_ab = ma;
+}
+
 void KmerMinHash::merge(KmerMinHash &other) {
     check_compatible(other);
     flush(); other.flush();
@@ -947,8 +990,20 @@ void KmerMinHash::merge(KmerMinHash &other) {
     cudaStream_t st = ctx.stream;
     const uint64_t na = n_mins_, nb = other.n_mins_;
     const bool sa = has_abunds_, ob = other.has_abunds_;
-    if (sa && n_abunds_ != na) throw_internal("abundances out of step with mins");
-    if (ob && other.n_abunds_ != nb) throw_internal("abundances out of step with mins");
+    if ((sa && n_abunds_ != na) || (ob && other.n_abunds_ != nb)) {
+        const uint64_t nsa = sa ? n_abunds_ : 0, nsb = ob ? other.n_abunds_ : 0;
+        d_mins_alt_.reserve((na + nb + 1) * 8);
+        d_abunds_alt_.reserve((nsa + nsb + 1) * 8);
+        merge_out_of_step_kernel<<<1, 1, 0, st>>>(d_mins_.as<uint64_t>(), na, d_abunds_.as<uint64_t>(), nsa, sa, other.d_mins_.as<uint64_t>(), nb,
+                                                  other.d_abunds_.as<uint64_t>(), nsb, ob, d_mins_alt_.as<uint64_t>(),
+                                                  d_abunds_alt_.as<uint64_t>(), ctx.dsc(SC_NUNIQ), ctx.dsc(SC_CNT));
+        SM_LAUNCHED();
+        ctx.read_scalars();
+        const uint64_t n_union = ctx.h_scalars[SC_NUNIQ], n_ab = ctx.h_scalars[SC_CNT];
+        has_abunds_ = true;  // lib.rs:393,400
+        commit(d_mins_alt_, d_abunds_alt_, (num != 0 && n_union >= num) ? num : n_union, n_ab);
+        return;
+    }
     const bool both = sa && ob;
     const uint64_t n_cat = na + nb;
     ctx.sort_tmp_k.reserve((n_cat + 1) * 8);

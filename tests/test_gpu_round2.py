@@ -277,3 +277,26 @@ def test_linear_find_streaming_path(n_index, n_q, lens, mx, num):
         assert n_index in got[0] and (len(queries[3]) == 0 or n_index in got[3])
     finally:
         smb.find_path("auto")
+
+
+# ------------------------------------------------------------------------------------------------
+# merge of a sketch whose abundances are out of step with its mins (the state lib.rs:395-400 leaves behind)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("track", [(True, True, True), (True, False, True), (False, True, True), (True, True, False)])
+def test_chained_merges_after_truncation(track):
+    num, k = 150, 21
+    seqs = [random_dna(4000, 900 + i) + random_dna(3000, 950) for i in range(3)]   # a shared stretch: common hashes
+    gs = [smb.KmerMinHash(num, k, False, 42, 0, t) for t in track]
+    os_ = [orc.KmerMinHash(num, k, False, 42, 0, t) for t in track]
+    for g, o, s in zip(gs, os_, seqs):
+        g.add_sequence(s); o.add_sequence(s)
+        g.add_sequence(s[:2000]); o.add_sequence(s[:2000])       # abundances above 1
+    gs[0].merge(gs[1]); os_[0].merge(os_[1])                      # mins truncated to num, abundances not
+    _same(gs[0], os_[0], "first merge")
+    assert len(gs[0].abunds_np()) != gs[0].size() or not (track[0] and track[1])
+    gs[0].merge(gs[2]); os_[0].merge(os_[2])                      # ... and merged again: walked step by step
+    _same(gs[0], os_[0], "second merge")
+    gs[2].merge(gs[0]); os_[2].merge(os_[0])                      # the out-of-step sketch on the other side
+    _same(gs[2], os_[2], "third merge")
+    gs[0].merge(gs[0].__class__(num, k, False, 42, 0, True)); os_[0].merge(orc.KmerMinHash(num, k, False, 42, 0, True))  # with an empty one
+    _same(gs[0], os_[0], "merge with empty")
