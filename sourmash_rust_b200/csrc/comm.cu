@@ -150,6 +150,14 @@ __global__ void unpack_rowinfo_kernel(const uint2 *__restrict__ info, uint64_t n
         nums[i] = v.y;
     }
 }
+// offsets[i] = i * len (i <= n), nums[i] = num
+__global__ void uniform_rows_kernel(uint64_t *__restrict__ offsets, uint32_t *__restrict__ nums, uint64_t n, uint64_t len, uint32_t num) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) {
+        offsets[i] = i * len;
+        if (i < n) nums[i] = num;
+    }
+}
 // [len, num] of the local rows
 __global__ void pack_rowinfo_kernel(const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ nums, uint64_t n, uint2 *__restrict__ info) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -241,15 +249,24 @@ static SketchCollection *allgather_impl(SketchCollection &local, const std::func
         out->dirty = false;
         return out.release();
     }
+    // rows all of one length and one num (a collection of full `num` sketches): said in the header, so that the
+    // receivers know every offset without seeing the row lengths
+    bool uniform = local.n_rows > 0 && local.max_len < (1u << 31);
+    const uint64_t len0 = local.n_rows ? local.h_offsets[1] - local.h_offsets[0] : 0;
+    for (uint64_t i = 0; uniform && i < local.n_rows; i++)
+        uniform = local.h_offsets[i + 1] - local.h_offsets[i] == len0 && local.h_nums[i] == local.h_nums[0];
+    const unsigned long long shape = uniform ? ((1ull << 63) | (len0 << 32) | local.h_nums[0]) : 0;
     unsigned long long mine[HDR] = {local.n_rows, local.n_hashes, local.max_len, local.ksize, local.seed, local.max_hash,
-                                    (unsigned long long)local.is_protein | ((unsigned long long)local.have_params << 1), 0};
+                                    (unsigned long long)local.is_protein | ((unsigned long long)local.have_params << 1), shape};
     exchange_headers(mine);
     const int W = c.world;
     std::vector<uint64_t> rows(W), hashes(W), row_base(W), hash_base(W);
     uint64_t n_rows = 0, n_hashes = 0, max_len = 0;
+    unsigned long long all_shape = 0;   // the one shape every non-empty rank reported, or 1 = not uniform
     std::unique_ptr<SketchCollection> out(new SketchCollection());
     for (int r = 0; r < W; r++) {
         const unsigned long long *h = c.h_hdr + (size_t)r * HDR;
+        if (h[0]) all_shape = (all_shape == 0 || all_shape == h[7]) && (h[7] >> 63) ? h[7] : 1;
         rows[r] = h[0]; hashes[r] = h[1];
         row_base[r] = n_rows; hash_base[r] = n_hashes;
         n_rows += h[0]; n_hashes += h[1];
@@ -272,6 +289,29 @@ static SketchCollection *allgather_impl(SketchCollection &local, const std::func
     out->d_hashes.reserve((n_hashes + 4) * 8);
     out->d_offsets.reserve((n_rows + 2) * 8);
     out->d_nums.reserve((n_rows + 1) * 4);
+    const bool all_uniform = (all_shape >> 63) != 0;
+    if (all_uniform) {
+        // every row of every rank has the same length and num: only the hashes travel; offsets are i * length
+        const uint64_t len = (all_shape >> 32) & 0x7FFFFFFFull;
+        const uint32_t num = (uint32_t)all_shape;
+        SM_CUDA(cudaEventRecord(c.ev_ready, ctx.stream));       // the output buffer is allocated (stream-ordered)
+        SM_CUDA(cudaStreamWaitEvent(c.stream, c.ev_ready, 0));
+        SM_NCCL(g_nccl.GroupStart());
+        allgatherv(local.d_hashes.p, out->d_hashes.p, hashes, hash_base, 8, ncclUint64);
+        SM_NCCL(g_nccl.GroupEnd());
+        SM_CUDA(cudaEventRecord(c.ev_done, c.stream));
+        uniform_rows_kernel<<<(unsigned)std::min<uint64_t>((n_rows + 256) / 256, 148 * 8), 256, 0, ctx.stream>>>(
+            out->d_offsets.as<uint64_t>(), out->d_nums.as<uint32_t>(), n_rows, len, num);
+        SM_LAUNCHED();
+        if (before_wait) before_wait();
+        SM_CUDA(cudaStreamWaitEvent(ctx.stream, c.ev_done, 0));
+        out->h_offsets.resize(n_rows + 1);
+        for (uint64_t i = 0; i <= n_rows; i++) out->h_offsets[i] = i * len;
+        out->h_nums.assign(n_rows, num);
+        if (out->h_offsets[n_rows] != n_hashes) throw_internal("all-gather: row lengths and hash counts disagree");
+        out->dirty = false;
+        return out.release();   // (nothing waits for the transfer here: the compare kernels are queued behind it)
+    }
     // per row, [length, num] travel as one 8-byte record; on arrival the lengths are scanned into offsets.  This
     // thread's scratch: misc[0] = my records, misc[3] = everybody's, misc[2] = lengths as u64 (n_rows + 1 entries, the
     // last one zero: its exclusive scan = offsets) -- not misc[1] or join[*], which the table build that overlaps the
