@@ -1,10 +1,18 @@
 """Summarises an ncu report into a markdown table for profiles/:
-   python tests/manual/ncu_summary.py REPORT.ncu-rep WINDOWS_PER_LAUNCH [title] > profiles/<name>.md
-Reads the report with `ncu -i ... --page raw --csv` (no GPU needed)."""
-import csv, io, subprocess, sys
+   python tests/manual/ncu_summary.py REPORT.ncu-rep UNITS_PER_LAUNCH [title] [--json profiles/kernel_constants.json --source profiles/<name>.md] > profiles/<name>.md
+Reads the report with `ncu -i ... --page raw --csv` (no GPU needed).  With --json, the per-kernel constants bench.py
+needs for its roofline objects (instructions / DRAM bytes per unit, pipe utilisations) are merged into that file under
+the kernel's name, so that they come from the same capture as the committed table."""
+import csv, io, json, os, subprocess, sys
 
-rep, units_per_launch = sys.argv[1], float(sys.argv[2])
-title = sys.argv[3] if len(sys.argv) > 3 else rep
+args = sys.argv[1:]
+json_path = source = None
+if "--json" in args:
+    i = args.index("--json"); json_path = args[i + 1]; del args[i:i + 2]
+if "--source" in args:
+    i = args.index("--source"); source = args[i + 1]; del args[i:i + 2]
+rep, units_per_launch = args[0], float(args[1])
+title = args[2] if len(args) > 2 else rep
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, body = rows[0], rows[1], rows[2:]
@@ -89,3 +97,23 @@ print("| **DRAM bytes per unit (read+write)** | " + " | ".join(
     fmt((to_bytes(r, "dram__bytes_read.sum") + to_bytes(r, "dram__bytes_write.sum")) / units_per_launch) for r in body) + " |")
 print("| **achieved DRAM GB/s** | " + " | ".join(
     fmt((to_bytes(r, "dram__bytes_read.sum") + to_bytes(r, "dram__bytes_write.sum")) / dur_s(r) / 1e9) for r in body) + " |")
+
+if json_path:
+    try:
+        consts = json.load(open(json_path))
+    except (OSError, ValueError):
+        consts = {}
+    for n, r in zip(names, body):
+        key = n.replace(" ", "").replace("<unnamed>::", "").replace("unnamed>::", "")
+        consts[key] = {
+            "instr_per_unit": per_unit(r, "smsp__inst_executed.sum", 32.0),
+            "dram_bytes_per_unit": (to_bytes(r, "dram__bytes_read.sum") + to_bytes(r, "dram__bytes_write.sum")) / units_per_launch,
+            "issue_pct": val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "alu_pct": val(r, "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+            "fmaheavy_pct": val(r, "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+            "dram_pct": val(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+            "units_per_launch": units_per_launch,
+            "source": source or os.path.basename(rep),
+        }
+    json.dump(consts, open(json_path, "w"), indent=1, sort_keys=True)
+    open(json_path, "a").write("\n")

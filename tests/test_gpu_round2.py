@@ -300,3 +300,32 @@ def test_chained_merges_after_truncation(track):
     _same(gs[2], os_[2], "third merge")
     gs[0].merge(gs[0].__class__(num, k, False, 42, 0, True)); os_[0].merge(orc.KmerMinHash(num, k, False, 42, 0, True))  # with an empty one
     _same(gs[0], os_[0], "merge with empty")
+
+
+def test_host_threads_add_up():
+    """Eight host threads, each feeding its own sketch through the unmodified kmerminhash_add_sequence (a C loop,
+    host/feed_reads.c), against one thread feeding the same reads: no library-wide lock, so the aggregate rate
+    must go up (it is host-bound: validation + staging of each read), and every thread's sketch must be right."""
+    n, L = 400_000, 150
+    genome = random_dna(1_000_000, 5)
+    reads = np.frombuffer(make_reads(genome, n, L, 6), dtype=np.uint8).reshape(n, L)
+    z = np.zeros((n, L + 1), dtype=np.uint8)
+    z[:, :L] = reads
+
+    def run(threads):
+        groups = [[smb.KmerMinHash(0, 31, False, 42, MAX_HASH_1000, True)] for _ in range(threads)]
+        secs = smb.feed_reads(groups, z, n, L + 1, warm_reads=10_000)
+        return (n - 10_000 * threads) * L / secs, groups
+
+    rate1, g1 = run(1)
+    rate8, g8 = run(8)
+    assert rate8 > 1.3 * rate1, (rate1, rate8)
+    # parity: thread t fed reads [t * n / 8, (t + 1) * n / 8)
+    per = n // 8
+    for t in (0, 3, 7):
+        o = orc.KmerMinHash(0, 31, False, 42, MAX_HASH_1000, True)
+        o.add_reads(reads[t * per:(t + 1) * per].tobytes(), per, L)
+        _same(g8[t][0], o, t)
+    o = orc.KmerMinHash(0, 31, False, 42, MAX_HASH_1000, True)
+    o.add_reads(reads.tobytes(), n, L)
+    _same(g1[0][0], o)
