@@ -490,11 +490,14 @@ __global__ void __launch_bounds__(256) walk_pairs_kernel(const uint64_t *__restr
         // lib.rs:470-499 in one pass.  The walk goes in stretches of s = min(left in A, left in B, left of the limit)
         // steps: a step advances either side by at most one element, so inside a stretch neither list can run out and
         // the step needs no bounds test at all -- two 64-bit compares, the count, and per side a predicated
-        // "take the element loaded one step ahead, load the one after it" (a row is followed by at least two readable
-        // hashes: the next row's, or the slack at the end of the CSR).  Lists of similar length need 2-4 stretches.
+        // "take the element loaded two steps ahead, load the one after" (a row is followed by at least three readable
+        // hashes: the next row's, or the slack at the end of the CSR).  Two elements ahead, because the loads come from
+        // L2 (~300 cycles) and a step is ~20 instructions: one element ahead left the walk waiting on them
+        // (ncu: issue slots 55 % busy, long-scoreboard stalls on top).  Lists of similar length need 2-4 stretches.
         const uint64_t *pa = a, *pb = b;
         uint64_t x = __ldg(pa), y = __ldg(pb);
         uint64_t xn = __ldg(pa + 1), yn = __ldg(pb + 1);
+        uint64_t xnn = __ldg(pa + 2), ynn = __ldg(pb + 2);
         for (;;) {
             uint32_t s = min(min(na - x_i, nb - y_j), limit - u);
             if (s == 0) break;
@@ -503,8 +506,8 @@ __global__ void __launch_bounds__(256) walk_pairs_kernel(const uint64_t *__restr
             for (; s; s--) {
                 const bool adv_a = x <= y, adv_b = y <= x;
                 c += (adv_a && adv_b);
-                if (adv_a) { x = xn; pa++; xn = __ldg(pa + 1); }
-                if (adv_b) { y = yn; pb++; yn = __ldg(pb + 1); }
+                if (adv_a) { x = xn; xn = xnn; pa++; xnn = __ldg(pa + 2); }
+                if (adv_b) { y = yn; yn = ynn; pb++; ynn = __ldg(pb + 2); }
             }
             x_i = (uint32_t)(pa - a);
             y_j = (uint32_t)(pb - b);
