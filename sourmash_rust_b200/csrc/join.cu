@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(256) probe_group_kernel(const unsigned long lo
                                                           const uint64_t *__restrict__ po, uint64_t p0, uint64_t np, uint32_t *cmat,
                                                           uint64_t ld, unsigned long long *bitmap, uint64_t n_build,
                                                           unsigned long long *incidences, const uint32_t *__restrict__ filter,
-                                                          int log2_f, bool smem_rows) {
+                                                          int log2_f, bool smem_rows, uint32_t split) {
     // `filter` (optional): one presence bit per build-side hash in a table small enough to stay in L2.  When
     // the two sides are unrelated collections (a query batch against an index) almost every probing hash is
     // turned away by that one bit instead of a random read in the (much larger) key table.
@@ -172,8 +172,13 @@ __global__ void __launch_bounds__(256) probe_group_kernel(const unsigned long lo
     extern __shared__ uint32_t s_probe[];
     const uint32_t row_words = (uint32_t)((n_build + 31) / 32);
     uint32_t *s_rows = (!COUNT && smem_rows) ? s_probe + (threadIdx.x >> 5) * row_words : nullptr;
-    for (uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < np; p += warps) {
-        const uint64_t b = po[p0 + p], e = po[p0 + p + 1];
+    // A probing sketch is cut into `split` parts, one warp each: in a row shard of an all-vs-all matrix only the few
+    // sketches related to the shard's rows have any hits, and one warp per sketch left most of the GPU idle while
+    // those few warps walked their runs (8 GPUs, cfg3: 1 250 busy warps of 10 000).
+    for (uint64_t wi = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < np * split; wi += warps) {
+        const uint64_t p = wi / split, part = wi - p * split;
+        const uint64_t b0 = po[p0 + p], len = po[p0 + p + 1] - b0;
+        const uint64_t b = b0 + len * part / split, e = b0 + len * (part + 1) / split;
         if (s_rows) {
             for (uint32_t w = lane; w < row_words; w += 32) s_rows[w] = 0;
             __syncwarp();
@@ -262,14 +267,15 @@ void launch_probe_group(bool count, bool build_cols, const unsigned long long *t
     // resident CTAs are limited by the shared-memory bitmaps: size the grid to what fits, a multiple of the SM count
     unsigned per_sm = 8;
     if (smem) per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 1024)));
-    const unsigned grid = blocks_for(np * 32, 256, 148 * std::max(2u, per_sm * 2));
+    const uint32_t split = np >= 32768 ? 1u : (uint32_t)std::min<uint64_t>(8, (32768 + np - 1) / np);
+    const unsigned grid = blocks_for(np * split * 32, 256, 148 * std::max(2u, per_sm * 2));
     static bool attr_set = false;
     if (!attr_set) {
         SM_CUDA(cudaFuncSetAttribute(probe_group_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         SM_CUDA(cudaFuncSetAttribute(probe_group_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr_set = true;
     }
-#define SM_PROBE(C, B) probe_group_kernel<C, B><<<grid, 256, smem, st>>>(tkey, toff, grows, log2_t, ph, po, p0, np, cmat, ld, bitmap, n_build, incidences, filter, log2_f, smem_rows)
+#define SM_PROBE(C, B) probe_group_kernel<C, B><<<grid, 256, smem, st>>>(tkey, toff, grows, log2_t, ph, po, p0, np, cmat, ld, bitmap, n_build, incidences, filter, log2_f, smem_rows, split)
     if (count) { if (build_cols) SM_PROBE(true, true); else SM_PROBE(true, false); }
     else { if (build_cols) SM_PROBE(false, true); else SM_PROBE(false, false); }
 #undef SM_PROBE
