@@ -106,6 +106,12 @@ SketchCollection *SketchCollection::from_csr(const uint64_t *hashes, const uint6
     return c.release();
 }
 
+bool SketchCollection::uniform_num(uint64_t first, uint64_t n) const {
+    for (uint64_t i = 1; i < n; i++)
+        if (h_nums[first + i] != h_nums[first]) return false;
+    return true;
+}
+
 void SketchCollection::check_compatible(const SketchCollection &o) const {
     if (!have_params || !o.have_params) return;
     if (ksize != o.ksize) throw SourmashError(ERR_MISMATCH_KSIZES, "different ksizes cannot be compared");
@@ -293,8 +299,10 @@ void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t nr, Sket
             if (cap) {
                 ctx.join[5].reserve((cap + 1) * 8);
                 launch_expand_bits(bitmap, pre, n_words, ctx.join[5].as<uint64_t>(), st, cap);
+                // the whole square of ONE collection whose sketches share a `num`: each unordered pair is walked once
+                const bool symmetric = (&rows == &cols) && r0 == c0 && nr == nc && rows.uniform_num(r0, nr);
                 launch_walk_pairs(ctx.join[5].as<uint64_t>(), cap, rh, ro, rnum, r0, ch, co, c0, nc, common, size, ratio, ld, st,
-                                  pre + (n_words - 1), counts + (n_words - 1), build_cols ? 0 : nr);  // probe-major cell ids
+                                  pre + (n_words - 1), counts + (n_words - 1), build_cols ? 0 : nr, symmetric);  // probe-major cell ids
             }
         }
         // The probe path is exact whatever the data; whether the dense kernels would have been faster

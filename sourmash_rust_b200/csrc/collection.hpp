@@ -42,6 +42,7 @@ struct SketchCollection {
                                       uint32_t ksize, uint64_t seed, uint64_t max_hash, bool on_device);
     void finalize();  // upload staged rows
     void check_compatible(const SketchCollection &other) const;  // lib.rs:176-190
+    bool uniform_num(uint64_t first, uint64_t n) const;          // rows [first, first + n) share one `num`
 };
 
 // one fresh sketch per sequence of the batch, in one pass (sketch_many.cu); see include/sourmash_b200.h

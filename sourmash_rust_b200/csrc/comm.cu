@@ -380,9 +380,12 @@ SketchCollection *compare_matrix_allgather(SketchCollection &local, int mode, ui
     const uint64_t nr = local.n_rows, nc = all->n_rows;
     if (nr == 0 || nc == 0) return all.release();
     if (ld < nc) throw_internal("ld smaller than the block width");
+    const bool alone = !g_comm.comm || g_comm.world == 1;   // one rank: rows and columns are the same sketches
     if (out_on_device) {
-        compare_block_device(local, 0, nr, *all, 0, nc, mode, common, size, ratio, ld, &jt);
+        compare_block_device(local, 0, nr, alone ? local : *all, 0, nc, mode, common, size, ratio, ld, &jt);
         ctx.sync();
+    } else if (alone) {
+        compare_matrix(local, 0, nr, local, 0, nc, mode, common, size, ratio, ld, out_on_device);
     } else {
         // host output: row blocks through device scratch, copied back while the next block runs (a block covers
         // part of the rows only, so the table built above does not apply)

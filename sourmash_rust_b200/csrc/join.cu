@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(256) walk_pairs_kernel(const uint64_t *__restr
                                                          const uint64_t *__restrict__ ch, const uint64_t *__restrict__ co,
                                                          uint64_t c0, uint64_t nc, uint32_t *common, uint32_t *size,
                                                          double *ratio, uint64_t ld, const uint64_t *n_dev_a,
-                                                         const uint64_t *n_dev_b, uint64_t nr_transposed) {
+                                                         const uint64_t *n_dev_b, uint64_t nr_transposed, bool symmetric) {
     // the pair count either comes from the host or is read here as *n_dev_a + *n_dev_b (the tail of the
     // bitmap scan), capped by n_pairs: the launch then needs no host round trip
     if (n_dev_a) {
@@ -487,6 +487,9 @@ __global__ void __launch_bounds__(256) walk_pairs_kernel(const uint64_t *__restr
         uint64_t i, j;
         if (nr_transposed) { j = cell / nr_transposed; i = cell - j * nr_transposed; }  // column-major cell ids (probe join)
         else { i = cell / nc; j = cell - i * nc; }
+        // rows and columns are the same sketches with one `num`: compare(a, b) == compare(b, a) (lib.rs:470-508 is
+        // symmetric but for self.num), so a pair is walked once and written to both cells
+        if (symmetric && i > j) continue;
         const uint64_t ab = ro[r0 + i], bb = co[c0 + j];
         const uint32_t na = (uint32_t)(ro[r0 + i + 1] - ab), nb = (uint32_t)(co[c0 + j + 1] - bb);
         const uint32_t num = rnum ? rnum[r0 + i] : 0;
@@ -521,19 +524,26 @@ __global__ void __launch_bounds__(256) walk_pairs_kernel(const uint64_t *__restr
         const uint64_t uni = (uint64_t)u + (na - x_i) + (nb - y_j);
         const uint32_t sz = (uint32_t)((num != 0 && uni >= num) ? num : uni);
         const size_t at = (size_t)i * ld + j;
+        const double rt = (double)c / (double)(sz > 1 ? sz : 1);
         if (common) common[at] = c;
         if (size) size[at] = sz;
-        if (ratio) ratio[at] = (double)c / (double)(sz > 1 ? sz : 1);
+        if (ratio) ratio[at] = rt;
+        if (symmetric && i != j) {
+            const size_t ta = (size_t)j * ld + i;
+            if (common) common[ta] = c;
+            if (size) size[ta] = sz;
+            if (ratio) ratio[ta] = rt;
+        }
     }
 }
 void launch_walk_pairs(const uint64_t *pairs, uint64_t n_pairs, const uint64_t *rh, const uint64_t *ro, const uint32_t *rnum,
                        uint64_t r0, const uint64_t *ch, const uint64_t *co, uint64_t c0, uint64_t nc, uint32_t *common,
                        uint32_t *size, double *ratio, uint64_t ld, cudaStream_t st, const uint64_t *n_dev_a,
-                       const uint64_t *n_dev_b, uint64_t nr_transposed) {
+                       const uint64_t *n_dev_b, uint64_t nr_transposed, bool symmetric) {
     if (!n_pairs) return;
     ProfScope prof(PROF_WALK, st);
     walk_pairs_kernel<<<blocks_for(n_pairs, 256, 148 * 16), 256, 0, st>>>(pairs, n_pairs, rh, ro, rnum, r0, ch, co, c0, nc, common,
-                                                                        size, ratio, ld, n_dev_a, n_dev_b, nr_transposed);
+                                                                        size, ratio, ld, n_dev_a, n_dev_b, nr_transposed, symmetric);
     SM_LAUNCHED();
 }
 

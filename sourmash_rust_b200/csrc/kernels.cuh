@@ -203,7 +203,7 @@ void launch_fill_cells(const uint64_t *ro, const uint32_t *rnum, uint64_t r0, ui
 void launch_walk_pairs(const uint64_t *pairs, uint64_t n_pairs, const uint64_t *rh, const uint64_t *ro, const uint32_t *rnum,
                        uint64_t r0, const uint64_t *ch, const uint64_t *co, uint64_t c0, uint64_t nc, uint32_t *common,
                        uint32_t *size, double *ratio, uint64_t ld, cudaStream_t st, const uint64_t *n_dev_a = nullptr,
-                       const uint64_t *n_dev_b = nullptr, uint64_t nr_transposed = 0);
+                       const uint64_t *n_dev_b = nullptr, uint64_t nr_transposed = 0, bool symmetric = false);
 
 // ---- find_stream.cu: LinearIndex::find over a large index at HBM rate (see the file header) -----------------
 uint32_t find_stream_partitions(uint64_t n_rows, uint64_t n_hashes, int sm_count);   // slices of the hash range (SM count / k)
