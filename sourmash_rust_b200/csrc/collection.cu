@@ -146,6 +146,10 @@ int g_find_path = [] {
     const char *e = getenv("SMB200_FIND_PATH");
     return e ? atoi(e) : 0;
 }();
+int g_walk_form = [] {   // SMB200_WALK_FORM=1: always the one-thread-per-pair walk (A/B runs, tests)
+    const char *e = getenv("SMB200_WALK_FORM");
+    return e ? atoi(e) : 0;
+}();
 int g_compare_path = 0;  // 0 = choose from the data, 1 = dense tile kernel, 2 = inverted-index path, 3 = inverted index without the probe form
 
 static int bit_length64(uint64_t x) {
@@ -301,8 +305,13 @@ void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t nr, Sket
                 launch_expand_bits(bitmap, pre, n_words, ctx.join[5].as<uint64_t>(), st, cap);
                 // the whole square of ONE collection whose sketches share a `num`: each unordered pair is walked once
                 const bool symmetric = (&rows == &cols) && r0 == c0 && nr == nc && rows.uniform_num(r0, nr);
-                launch_walk_pairs(ctx.join[5].as<uint64_t>(), cap, rh, ro, rnum, r0, ch, co, c0, nc, common, size, ratio, ld, st,
-                                  pre + (n_words - 1), counts + (n_words - 1), build_cols ? 0 : nr, symmetric);  // probe-major cell ids
+                // short sketches (both together at most 1024 hashes): one warp per pair, lists in shared memory (join.cu)
+                if (g_walk_form != 1 && walk_pairs_warp_fits(rows.max_len, cols.max_len))
+                    launch_walk_pairs_warp(ctx.join[5].as<uint64_t>(), cap, rh, ro, rnum, r0, ch, co, c0, nc, common, size, ratio, ld, st,
+                                           pre + (n_words - 1), counts + (n_words - 1), build_cols ? 0 : nr, symmetric);
+                else
+                    launch_walk_pairs(ctx.join[5].as<uint64_t>(), cap, rh, ro, rnum, r0, ch, co, c0, nc, common, size, ratio, ld, st,
+                                      pre + (n_words - 1), counts + (n_words - 1), build_cols ? 0 : nr, symmetric);  // probe-major cell ids
             }
         }
         // The probe path is exact whatever the data; whether the dense kernels would have been faster
@@ -390,7 +399,10 @@ void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t nr, Sket
     if (n_pairs) {
         ctx.join[5].reserve((n_pairs + 1) * 8);
         launch_expand_bits(bitmap, pre, n_words, ctx.join[5].as<uint64_t>(), st);
-        launch_walk_pairs(ctx.join[5].as<uint64_t>(), n_pairs, rh, ro, rnum, r0, ch, co, c0, nc, common, size, ratio, ld, st);
+        if (g_walk_form != 1 && walk_pairs_warp_fits(rows.max_len, cols.max_len))
+            launch_walk_pairs_warp(ctx.join[5].as<uint64_t>(), n_pairs, rh, ro, rnum, r0, ch, co, c0, nc, common, size, ratio, ld, st);
+        else
+            launch_walk_pairs(ctx.join[5].as<uint64_t>(), n_pairs, rh, ro, rnum, r0, ch, co, c0, nc, common, size, ratio, ld, st);
     }
 }
 

@@ -238,6 +238,14 @@ void launch_touched_hits(uint32_t *cmat, uint64_t bn, uint64_t nq, const uint64_
                          double threshold, uint32_t *touched_bits, const uint32_t *touched_rows, unsigned long long *n_touched,
                          uint64_t *found, uint64_t cap, unsigned long long *n_found, int sm_count, cudaStream_t st);
 
+// the same walk, one WARP per pair (lists staged in shared memory, merge-path split over the lanes): for blocks whose
+// longest row + longest column fit walk_pairs_warp_fits()
+bool walk_pairs_warp_fits(uint32_t max_row_len, uint32_t max_col_len);
+void launch_walk_pairs_warp(const uint64_t *pairs, uint64_t n_pairs, const uint64_t *rh, const uint64_t *ro, const uint32_t *rnum,
+                            uint64_t r0, const uint64_t *ch, const uint64_t *co, uint64_t c0, uint64_t nc, uint32_t *common,
+                            uint32_t *size, double *ratio, uint64_t ld, cudaStream_t st, const uint64_t *n_dev_a = nullptr,
+                            const uint64_t *n_dev_b = nullptr, uint64_t nr_transposed = 0, bool symmetric = false);
+
 // dense path for full num sketches: dense u32 ranks + fixed-length walk (join.cu)
 void launch_scatter_ranks(const uint64_t *keys, const uint64_t *vals, const uint64_t *pre, uint64_t n, uint32_t L,
                           uint64_t b_base, uint32_t *out, cudaStream_t st);
