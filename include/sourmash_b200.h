@@ -149,6 +149,11 @@ uint64_t smgpu_scaffold_pairs(SketchCollection *c, uint64_t *pairs_first, uint64
  * 4 = as 2, and a block whose probe found many incidences is not handed to the dense kernels.
  * Results are identical. */
 void smgpu_compare_path(int32_t path);
+/* How the related pairs of a block are walked (src/lib.rs:470-499 per pair): 0 (default) = one thread per pair;
+ * 2 = one warp per pair (merge-path split over the lanes, both lists staged in shared memory) where the two
+ * sketches together hold at most 1024 hashes.  Results are identical; the warp form measured slower and is kept for
+ * A/B runs. */
+void smgpu_walk_form(int32_t form);
 /* How smgpu_linear_find counts shared hashes when a count decides the hit (containment; similarity of sketches
  * without a num): 0 (default) = an index that is large against the query batch is STREAMED once past per-slice
  * Bloom filters of the query hashes held in shared memory (the search then runs at the rate HBM delivers the

@@ -108,6 +108,7 @@ EXTENSION_ABI = {
     "smgpu_scaffold_pairs": (u64, [vp, vp, vp]),
     "smgpu_compare_path": (None, [i32]),
     "smgpu_find_path": (None, [i32]),
+    "smgpu_walk_form": (None, [i32]),
     "smgpu_linear_find": (u64, [vp, vp, i32, C.c_double, vp, vp, u64]),
     "smgpu_comm_unique_id": (None, [vp]),
     "smgpu_comm_init": (None, [vp, i32, i32]),
@@ -218,6 +219,11 @@ PROFILE_KINDS = {"sketch_k21": 0, "sketch_k31": 1, "sketch_k51": 2, "sketch_othe
 def compare_path(path="auto"):
     """'auto' | 'dense' | 'sparse' | 'noprobe' (smgpu_compare_path)"""
     lib().smgpu_compare_path({"auto": 0, "dense": 1, "sparse": 2, "noprobe": 3, "probe": 4}[path])
+
+
+def walk_form(form="thread"):
+    """'thread' | 'warp' (smgpu_walk_form)"""
+    lib().smgpu_walk_form({"thread": 0, "warp": 2}[form])
 
 
 def find_path(path="auto"):

@@ -146,7 +146,10 @@ int g_find_path = [] {
     const char *e = getenv("SMB200_FIND_PATH");
     return e ? atoi(e) : 0;
 }();
-int g_walk_form = [] {   // SMB200_WALK_FORM=1: always the one-thread-per-pair walk (A/B runs, tests)
+// How the related pairs are walked: 0 (default) = one thread per pair; 2 = one WARP per pair (merge-path split, lists
+// in shared memory) where both sketches together hold at most 1024 hashes.  The warp form is exact and kept for A/B
+// runs -- it measured 3.8x SLOWER than the thread form on cfg3.  SMB200_WALK_FORM / smgpu_walk_form.
+int g_walk_form = [] {
     const char *e = getenv("SMB200_WALK_FORM");
     return e ? atoi(e) : 0;
 }();
@@ -306,7 +309,7 @@ void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t nr, Sket
                 // the whole square of ONE collection whose sketches share a `num`: each unordered pair is walked once
                 const bool symmetric = (&rows == &cols) && r0 == c0 && nr == nc && rows.uniform_num(r0, nr);
                 // short sketches (both together at most 1024 hashes): one warp per pair, lists in shared memory (join.cu)
-                if (g_walk_form != 1 && walk_pairs_warp_fits(rows.max_len, cols.max_len))
+                if (g_walk_form == 2 && walk_pairs_warp_fits(rows.max_len, cols.max_len))
                     launch_walk_pairs_warp(ctx.join[5].as<uint64_t>(), cap, rh, ro, rnum, r0, ch, co, c0, nc, common, size, ratio, ld, st,
                                            pre + (n_words - 1), counts + (n_words - 1), build_cols ? 0 : nr, symmetric);
                 else
@@ -399,7 +402,7 @@ void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t nr, Sket
     if (n_pairs) {
         ctx.join[5].reserve((n_pairs + 1) * 8);
         launch_expand_bits(bitmap, pre, n_words, ctx.join[5].as<uint64_t>(), st);
-        if (g_walk_form != 1 && walk_pairs_warp_fits(rows.max_len, cols.max_len))
+        if (g_walk_form == 2 && walk_pairs_warp_fits(rows.max_len, cols.max_len))
             launch_walk_pairs_warp(ctx.join[5].as<uint64_t>(), n_pairs, rh, ro, rnum, r0, ch, co, c0, nc, common, size, ratio, ld, st);
         else
             launch_walk_pairs(ctx.join[5].as<uint64_t>(), n_pairs, rh, ro, rnum, r0, ch, co, c0, nc, common, size, ratio, ld, st);

@@ -67,6 +67,7 @@ void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t nr, Sket
 
 extern int g_compare_path;
 extern int g_find_path;
+extern int g_walk_form;
 // see include/sourmash_b200.h
 void compare_matrix(SketchCollection &rows, uint64_t r0, uint64_t nr, SketchCollection &cols, uint64_t c0, uint64_t nc,
                     int mode, uint32_t *common, uint32_t *size, double *ratio, uint64_t ld, bool out_on_device);

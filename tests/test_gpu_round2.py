@@ -331,3 +331,39 @@ def test_host_threads_add_up():
     o = orc.KmerMinHash(0, 31, False, 42, MAX_HASH_1000, True)
     o.add_reads(reads.tobytes(), n, L)
     _same(g1[0][0], o)
+
+
+# ------------------------------------------------------------------------------------------------
+# the warp-cooperative form of the pair walk (join.cu: merge-path split over the lanes) against the thread form + oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("num,lens", [(400, (400, 401)), (0, (0, 500)), (100, (30, 300)), (512, (512, 513))])
+def test_warp_form_of_the_pair_walk(num, lens):
+    r = np.random.Generator(np.random.PCG64(num + 17))
+    base = [np.unique(r.integers(0, 1 << 60, size=700, dtype=np.uint64)) for _ in range(6)]
+    rows, g_sk, o_sk = [], [], []
+    for i in range(150):
+        b = base[i % 6]
+        keep = b[r.random(b.size) < (0.2, 0.6, 0.95)[i % 3]]
+        row = np.unique(np.concatenate([keep, r.integers(0, 1 << 60, size=200, dtype=np.uint64)]))
+        row = row[: int(r.integers(lens[0], lens[1]))]
+        if num and i % 7 == 0:
+            row = row[: num // 3]                   # not full: the union may hold fewer than num elements
+        rows.append(row)
+        g, o = smb.KmerMinHash(num, 31, False, 42, 0), orc.KmerMinHash(num, 31, False, 42, 0)
+        g.set_mins(row); o.add_many(row)
+        g_sk.append(g); o_sk.append(o)
+    coll = smb.SketchCollection.from_sketches(g_sk)
+    part = smb.SketchCollection.from_sketches(g_sk[20:60])
+    oc, osz = orc.compare_matrix(o_sk, o_sk)
+    try:
+        for form in ("warp", "thread"):
+            smb.walk_form(form)
+            smb.compare_path("sparse")
+            common, size, ratio = smb.compare_matrix(coll, coll)             # the whole square: each unordered pair once
+            assert np.array_equal(common, oc) and np.array_equal(size, osz), form
+            assert np.array_equal(ratio, oc.astype(np.float64) / np.maximum(1, osz).astype(np.float64)), form
+            common, size, _ = smb.compare_matrix(part, coll)                 # a row shard against everything
+            assert np.array_equal(common, oc[20:60]) and np.array_equal(size, osz[20:60]), form
+    finally:
+        smb.walk_form("thread")
+        smb.compare_path("auto")
