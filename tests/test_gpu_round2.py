@@ -349,7 +349,8 @@ def test_warp_form_of_the_pair_walk(num, lens):
         if num and i % 7 == 0:
             row = row[: num // 3]                   # not full: the union may hold fewer than num elements
         rows.append(row)
-        g, o = smb.KmerMinHash(num, 31, False, 42, 0), orc.KmerMinHash(num, 31, False, 42, 0)
+        mx = 0 if num else 1 << 60                  # (num = 0 needs a max_hash: scaled sketches)
+        g, o = smb.KmerMinHash(num, 31, False, 42, mx), orc.KmerMinHash(num, 31, False, 42, mx)
         g.set_mins(row); o.add_many(row)
         g_sk.append(g); o_sk.append(o)
     coll = smb.SketchCollection.from_sketches(g_sk)
