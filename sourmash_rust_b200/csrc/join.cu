@@ -214,8 +214,17 @@ __global__ void __launch_bounds__(256) probe_group_kernel(const unsigned long lo
             if (!COUNT && s_rows) {
                 // related rows of this probing sketch are collected in the warp's shared-memory bitmap: the
                 // hundreds of repeat hits per pair cost a shared-memory test, not a global one
+                // (four row ids per trip, loaded together: the loop is otherwise one dependent L2 load per incidence)
+                for (; j + 4 <= je; j += 4) {
+                    const uint32_t q0 = __ldg(&grows[j]), q1 = __ldg(&grows[j + 1]), q2 = __ldg(&grows[j + 2]), q3 = __ldg(&grows[j + 3]);
+                    const uint32_t m0 = 1u << (q0 & 31), m1 = 1u << (q1 & 31), m2 = 1u << (q2 & 31), m3 = 1u << (q3 & 31);
+                    if (!(s_rows[q0 >> 5] & m0)) atomicOr(&s_rows[q0 >> 5], m0);
+                    if (!(s_rows[q1 >> 5] & m1)) atomicOr(&s_rows[q1 >> 5], m1);
+                    if (!(s_rows[q2 >> 5] & m2)) atomicOr(&s_rows[q2 >> 5], m2);
+                    if (!(s_rows[q3 >> 5] & m3)) atomicOr(&s_rows[q3 >> 5], m3);
+                }
                 for (; j < je; j++) {
-                    const uint32_t q = grows[j];
+                    const uint32_t q = __ldg(&grows[j]);
                     const uint32_t m = 1u << (q & 31);
                     if (!(s_rows[q >> 5] & m)) atomicOr(&s_rows[q >> 5], m);
                 }
