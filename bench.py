@@ -454,6 +454,45 @@ def run_ours(args):
     h2d_gbs = n_bytes * reps / (max_over_ranks(c0.elapsed_time(c1)) * 1e-3) / 1e9   # per GPU, slowest rank
     del h2d_dst
 
+    # ---- NOT a reference format: the same reads 2 bits per base from pinned host memory (a quarter of the PCIe bytes) ----
+    packed = None
+    if not args.no_packed:
+        packed_batches = []
+        for hb in host_batches:
+            pk = smb.pack_2bit(hb.numpy().reshape(R, READ_LEN), READ_LEN)
+            t = torch.empty(pk.size, dtype=torch.uint8, pin_memory=True)
+            t.copy_(torch.from_numpy(pk.reshape(-1)))
+            packed_batches.append(t)
+        out_m = [torch.zeros(1 << 22, dtype=torch.int64, pin_memory=True) for _ in KSIZES]
+        out_a = [torch.zeros(1 << 22, dtype=torch.int64, pin_memory=True) for _ in KSIZES]
+
+        def p_step(sk, s):
+            smb.add_reads_2bit(sk, packed_batches[s % n_batches].data_ptr(), R, READ_LEN)
+            for i, m in enumerate(sk):
+                smb._call("kmerminhash_copy_mins", m._p, smb._vp(out_m[i].data_ptr()), smb._vp(out_a[i].data_ptr()), False)
+
+        warm = new_sketches()
+        for w in range(2):
+            p_step(warm, w)
+        pm = new_sketches()
+        barrier()
+        t_wall0 = time.time()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(lib_stream)
+        for s in range(args.steps):
+            p_step(pm, s)
+        e1.record(lib_stream)
+        barrier()
+        windows.append((t_wall0, time.time()))
+        ms_p = max_over_ranks(e0.elapsed_time(e1))
+        assert [m.md5sum() for m in pm] == md5_dev, "2-bit input and ASCII input disagree"
+        packed = {"value": total_bases / (ms_p * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": ms_p / args.steps,
+                  "h2d_bytes_per_step": int(packed_batches[0].numel()),
+                  "entry_point": "kmerminhash_add_reads_2bit (include/sourmash_b200.h): NOT a reference input format -- reads 2 bits "
+                                 "per base in pinned host memory, expanded to ASCII on the device behind the copy; same sketches "
+                                 "(md5 asserted)", "parity_with_ascii_path": True}
+        del packed_batches, pm, warm
+
     # ---- the reference's own calling pattern: one kmerminhash_add_sequence call per read and per k-size ---------
     # (src/ffi.rs:55-70; a C loop over the unmodified symbol, sourmash_rust_b200/host/feed_reads.c).  Reads as
     # NUL-terminated strings in host memory; T host threads, each feeding its own three sketches with its share of
@@ -596,6 +635,7 @@ def run_ours(args):
                                         "ceiling in Gbp/s per GPU",
                     "frac_of_h2d_ceiling": (e2e_value / world) / h2d_gbs},
             "e2e_per_call": percall,
+            "e2e_packed_2bit": packed,
             "k31_scaled1000": k31,
             "gpu_launches": launches,
             "roofline": roof, "roofline_hbm": roof_hbm, "sketch_kernels": per_k,
@@ -751,6 +791,7 @@ def main():
     ap.add_argument("--no-compare", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-percall", action="store_true")
+    ap.add_argument("--no-packed", action="store_true")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -76,6 +76,13 @@ void kmerminhash_add_sequences(KmerMinHash *const *mhs, uintptr_t n_mhs, const c
 /* same for n_reads fixed-length reads stored back to back (no offsets array) */
 void kmerminhash_add_reads(KmerMinHash *const *mhs, uintptr_t n_mhs, const char *buf /*[host|device]*/,
                            uint64_t n_reads, uint32_t read_len, bool force, bool on_device);
+/* NOT A REFERENCE FORMAT -- an input format of this build only.  The same as kmerminhash_add_reads for reads stored
+ * 2 bits per base: A = 0, C = 1, G = 2, T = 3; base i of a read in bits 2*(i % 4) .. 2*(i % 4) + 1 of its byte i / 4;
+ * every read starts on a byte boundary ((read_len + 3) / 4 bytes per read, padding bits ignored).  A quarter of the
+ * bytes cross PCIe; the device expands them to the ASCII the kernels read, behind the copy.  Results are those of
+ * kmerminhash_add_reads over the ASCII form.  (No invalid bases can be expressed, so no error can arise.) */
+void kmerminhash_add_reads_2bit(KmerMinHash *const *mhs, uintptr_t n_mhs, const uint8_t *packed /*[host|device]*/,
+                                uint64_t n_reads, uint32_t read_len, bool on_device);
 /* replace the sketch content: equivalent to a fresh sketch followed by n kmerminhash_mins_push and
  * n_abunds kmerminhash_abunds_push calls (src/ffi.rs:143-150,179-188); abunds may be NULL */
 void kmerminhash_set_mins(KmerMinHash *ptr, const uint64_t *mins, uintptr_t n, const uint64_t *abunds,

@@ -92,6 +92,7 @@ EXTENSION_ABI = {
     "kmerminhash_intersection_hashes": (p_u64, [vp, vp, C.POINTER(usz), C.POINTER(u64)]),
     "kmerminhash_add_sequences": (None, [C.POINTER(vp), usz, vp, vp, u64, cb, cb]),
     "kmerminhash_add_reads": (None, [C.POINTER(vp), usz, vp, u64, u32, cb, cb]),
+    "kmerminhash_add_reads_2bit": (None, [C.POINTER(vp), usz, vp, u64, u32, cb]),
     "kmerminhash_set_mins": (None, [vp, vp, usz, vp, usz]),
     "kmerminhash_copy_mins": (usz, [vp, vp, vp, cb]),
     "kmerminhash_md5sum": (SourmashStr, [vp]),
@@ -402,6 +403,25 @@ def add_reads(mhs, buf, n_reads, read_len, force=True, on_device=False):
     """kmerminhash_add_reads: every read added to every sketch of `mhs` in one pass."""
     keep = buf if (on_device or isinstance(buf, (int, np.ndarray))) else bytes(buf)  # int = raw pointer
     _call("kmerminhash_add_reads", _handles(mhs), len(mhs), _vp(keep), n_reads, read_len, force, on_device)
+
+
+def add_reads_2bit(mhs, packed, n_reads, read_len, on_device=False):
+    """kmerminhash_add_reads_2bit (NOT a reference format): reads stored 2 bits per base, see include/sourmash_b200.h."""
+    keep = packed if (on_device or isinstance(packed, (int, np.ndarray))) else bytes(packed)
+    _call("kmerminhash_add_reads_2bit", _handles(mhs), len(mhs), _vp(keep), n_reads, read_len, on_device)
+
+
+def pack_2bit(reads: np.ndarray, read_len: int) -> np.ndarray:
+    """Host helper for tests / benches: ASCII reads (n x read_len uint8, ACGT only) -> the 2-bit form above."""
+    r = np.ascontiguousarray(reads, dtype=np.uint8).reshape(-1, read_len)
+    lut = np.zeros(256, dtype=np.uint8)
+    lut[list(b"ACGT")] = [0, 1, 2, 3]
+    codes = lut[r]
+    pad = (-read_len) % 4
+    if pad:
+        codes = np.concatenate([codes, np.zeros((codes.shape[0], pad), dtype=np.uint8)], axis=1)
+    q = codes.reshape(codes.shape[0], -1, 4)
+    return np.ascontiguousarray(q[:, :, 0] | (q[:, :, 1] << 2) | (q[:, :, 2] << 4) | (q[:, :, 3] << 6))
 
 
 def add_sequences(mhs, buf, offsets, force=True, on_device=False, n_seqs=None):

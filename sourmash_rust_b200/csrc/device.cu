@@ -160,12 +160,12 @@ Context::~Context() {
     }
     if (!stream || cudaStreamSynchronize(stream) != cudaSuccess) {  // runtime already torn down: nothing to give back
         (void)cudaGetLastError();
-        ascii.p = offsets.p = sort_tmp_k.p = sort_tmp_v.p = scan_tmp.p = find_cmat.p = find_bits.p = find_rows.p = nullptr;
+        ascii.p = offsets.p = packed.p = sort_tmp_k.p = sort_tmp_v.p = scan_tmp.p = find_cmat.p = find_bits.p = find_rows.p = nullptr;
         for (DevBuf &b : misc) b.p = nullptr;
         for (DevBuf &b : join) b.p = nullptr;
         return;
     }
-    DevBuf *all[] = {&ascii, &offsets, &sort_tmp_k, &sort_tmp_v, &scan_tmp, &find_cmat, &find_bits, &find_rows};
+    DevBuf *all[] = {&ascii, &offsets, &packed, &sort_tmp_k, &sort_tmp_v, &scan_tmp, &find_cmat, &find_bits, &find_rows};
     for (DevBuf *b : all) { if (b->p) cudaFreeAsync(b->p, stream); b->p = nullptr; b->cap = 0; }
     for (DevBuf &b : misc) { if (b.p) cudaFreeAsync(b.p, stream); b.p = nullptr; b.cap = 0; }
     for (DevBuf &b : join) { if (b.p) cudaFreeAsync(b.p, stream); b.p = nullptr; b.cap = 0; }

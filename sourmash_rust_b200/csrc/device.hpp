@@ -104,7 +104,7 @@ struct Context {
     unsigned long long *d_scalars = nullptr;
     unsigned long long *h_scalars = nullptr;  // pinned mirror
     // scratch
-    DevBuf ascii, offsets, sort_tmp_k, sort_tmp_v, scan_tmp, misc[8], join[8];
+    DevBuf ascii, offsets, packed, sort_tmp_k, sort_tmp_v, scan_tmp, misc[8], join[8];
     // find_stream.cu: count matrix + touched-row bitmap that every search leaves all-zero again (the hit pass clears what
     // it reads), so that a search does not start with a memset of half a gigabyte; find_clean: that invariant holds
     DevBuf find_cmat, find_bits, find_rows;

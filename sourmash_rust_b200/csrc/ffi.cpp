@@ -541,6 +541,24 @@ void kmerminhash_add_reads(KmerMinHash *const *mhs, uintptr_t n_mhs, const char 
         MH::add_sequences(reinterpret_cast<MH *const *>(mhs), (int)n_mhs, b, force);
     });
 }
+void kmerminhash_add_reads_2bit(KmerMinHash *const *mhs, uintptr_t n_mhs, const uint8_t *packed, uint64_t n_reads, uint32_t read_len,
+                                bool on_device) {
+    landingpad_void([&]() {
+        nonnull(mhs, "mhs");
+        if (n_reads == 0 || read_len == 0) return;
+        nonnull(packed, "packed");
+        smb200::SeqBatch b;
+        b.packed2 = packed;
+        b.n_seqs = n_reads;
+        b.read_len = read_len;
+        b.n_bytes = n_reads * (uint64_t)read_len;
+        b.on_device = on_device;
+        GuardN lk;
+        for (uintptr_t i = 0; i < n_mhs; i++) lk.add(mh(mhs[i])->mu);
+        lk.lock();
+        MH::add_sequences(reinterpret_cast<MH *const *>(mhs), (int)n_mhs, b, true);   // every base is one of ACGT: nothing can fail
+    });
+}
 void kmerminhash_set_mins(KmerMinHash *ptr, const uint64_t *mins, uintptr_t n, const uint64_t *abunds, uintptr_t n_abunds) {
     landingpad_void([&]() {
         MH *m = mh(ptr);

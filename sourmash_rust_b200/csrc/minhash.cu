@@ -63,6 +63,36 @@ __global__ void iota_ones_kernel(uint64_t *v, uint64_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) v[i] = 1;
 }
 
+// 2-bit packed reads -> ASCII (kmerminhash_add_reads_2bit): 16 output bytes per thread, reads [r0, r1)
+__global__ void __launch_bounds__(256) unpack_2bit_kernel(const uint8_t *__restrict__ packed, uint8_t *__restrict__ ascii, uint64_t r0,
+                                                          uint64_t r1, uint32_t read_len) {
+    const uint32_t bpr = (read_len + 3) / 4;
+    const uint64_t o_lo = r0 * read_len, o_hi = r1 * read_len;   // output byte range; o_lo is what the caller aligned to 16
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 16;
+    for (uint64_t o = (o_lo & ~15ull) + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; o < o_hi; o += stride) {
+        uint64_t r = o / read_len;
+        uint32_t i = (uint32_t)(o - r * read_len);
+        uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+            const uint64_t ob = o + b;
+            uint32_t ch = 0;
+            if (ob >= o_lo && ob < o_hi) {
+                const uint32_t code = (packed[r * bpr + (i >> 2)] >> (2 * (i & 3))) & 3u;
+                ch = (0x54474341u >> (8 * code)) & 0xFFu;   // "ACGT"
+            }
+            w[b >> 2] |= ch << (8 * (b & 3));
+            if (++i == read_len) { i = 0; r++; }
+        }
+        if (o >= o_lo && o + 16 <= o_hi) {
+            *reinterpret_cast<uint4 *>(ascii + o) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {   // a group cut by the range: its bytes one by one (the neighbours belong to another launch)
+            for (int b = 0; b < 16; b++)
+                if (o + b >= o_lo && o + b < o_hi) ascii[o + b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+        }
+    }
+}
+
 static int bit_length(uint64_t x) {
     int b = 0;
     while (x) { b++; x >>= 1; }
@@ -702,11 +732,21 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
     // ---- bring the batch to the device (chunked, overlapped with the kernels) ------------------
     const uint8_t *d_buf = nullptr;
     const uint64_t *d_off = nullptr;
-    if (batch.on_device) {
+    const uint32_t bpr = (batch.read_len + 3) / 4;   // packed bytes per read
+    if (batch.packed2 && (batch.offsets || batch.read_len == 0)) throw_internal("2-bit input needs fixed-length reads");
+    if (batch.on_device && batch.packed2) {
+        // packed reads already in HBM: expand them in one go, then as a device-resident ASCII batch
+        ctx.ascii.reserve(((n + 15) & ~15ull) + 256);
+        unpack_2bit_kernel<<<(unsigned)std::min<uint64_t>((n / 16 + 256) / 256, 148 * 16), 256, 0, st>>>(batch.packed2, ctx.ascii.as<uint8_t>(),
+                                                                                                     0, batch.n_seqs, batch.read_len);
+        SM_LAUNCHED();
+        d_buf = ctx.ascii.as<uint8_t>();
+    } else if (batch.on_device) {
         if ((reinterpret_cast<uintptr_t>(batch.buf) & 15) != 0) throw_internal("device sequence buffer must be 16-byte aligned");
         d_buf = batch.buf;
         d_off = batch.offsets;
     } else {
+        if (batch.packed2) ctx.packed.reserve((size_t)batch.n_seqs * bpr + 256);
         ctx.ascii.reserve(((n + 15) & ~15ull) + 256);
         d_buf = ctx.ascii.as<uint8_t>();
         if (batch.offsets) {
@@ -795,8 +835,21 @@ void KmerMinHash::add_sequences(KmerMinHash *const *mhs, int n_mhs, const SeqBat
             uint64_t len = std::min<uint64_t>(chunk, left);
             if (left > (2ull << 20)) len = std::min<uint64_t>(len, std::max<uint64_t>((left / 2 + 4095) & ~4095ull, 2ull << 20));
             chunk = std::min<uint64_t>(chunk * 2, CHUNK_MAX);
-            SM_CUDA(cudaMemcpyAsync(const_cast<uint8_t *>(d_buf) + copied, batch.buf + copied, len, cudaMemcpyHostToDevice,
-                                    ctx.copy_stream));
+            if (batch.packed2) {
+                // whole reads per chunk: a quarter of the bytes cross PCIe, the copy stream expands them behind the copy
+                const uint64_t r0 = copied / batch.read_len;
+                const uint64_t r1 = std::min<uint64_t>(batch.n_seqs, std::max<uint64_t>(r0 + 1, (copied + len) / batch.read_len));
+                SM_CUDA(cudaMemcpyAsync(ctx.packed.as<uint8_t>() + r0 * bpr, batch.packed2 + r0 * bpr, (r1 - r0) * bpr, cudaMemcpyHostToDevice,
+                                        ctx.copy_stream));
+                const uint64_t out_bytes = (r1 - r0) * batch.read_len;
+                unpack_2bit_kernel<<<(unsigned)std::min<uint64_t>((out_bytes / 16 + 256) / 256, 148 * 8), 256, 0, ctx.copy_stream>>>(
+                    ctx.packed.as<uint8_t>(), const_cast<uint8_t *>(d_buf), r0, r1, batch.read_len);
+                SM_LAUNCHED();
+                len = r1 * batch.read_len - copied;
+            } else {
+                SM_CUDA(cudaMemcpyAsync(const_cast<uint8_t *>(d_buf) + copied, batch.buf + copied, len, cudaMemcpyHostToDevice,
+                                        ctx.copy_stream));
+            }
             copied += len;
             if (ev_i >= ctx.chunk_events.size()) {
                 cudaEvent_t e;

@@ -34,6 +34,10 @@ struct SeqBatch {
     uint32_t read_len = 0;
     uint64_t n_bytes = 0;
     bool on_device = false;
+    // NON-REFERENCE input format (kmerminhash_add_reads_2bit): fixed-length reads, 2 bits per base (A=0 C=1 G=2 T=3;
+    // base i of a read in bits 2*(i%4).. of its byte i/4; every read starts on a byte boundary).  When set, `buf` is
+    // unused and n_bytes = n_seqs * read_len is the size of the ASCII form the device expands it into.
+    const uint8_t *packed2 = nullptr;
 };
 
 // Host-side stage of deferred add_sequence calls (minhash.cu, "deferral of short sequences"): the bytes of the

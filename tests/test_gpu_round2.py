@@ -368,3 +368,33 @@ def test_warp_form_of_the_pair_walk(num, lens):
     finally:
         smb.walk_form("thread")
         smb.compare_path("auto")
+
+
+# ------------------------------------------------------------------------------------------------
+# 2-bit packed reads (an input format of this build, not of the reference): same sketches as the ASCII form
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_reads,read_len", [(120_000, 150), (5000, 151), (3000, 64), (7, 33), (1, 21)])
+def test_packed_2bit_reads_equal_ascii(n_reads, read_len):
+    genome = random_dna(max(400_000, 4 * read_len), 60 + read_len)
+    reads = np.frombuffer(make_reads(genome, n_reads, read_len, 61), dtype=np.uint8).reshape(n_reads, read_len)
+    packed = smb.pack_2bit(reads, read_len)
+    assert packed.shape == (n_reads, (read_len + 3) // 4)
+    ks = [k for k in (21, 31, 51) if k <= read_len]
+    want = [smb.KmerMinHash(0, k, False, 42, MAX_HASH_1000 * 5, True) for k in ks]
+    smb.add_reads(want, reads.tobytes(), n_reads, read_len)
+    got = [smb.KmerMinHash(0, k, False, 42, MAX_HASH_1000 * 5, True) for k in ks]
+    smb.add_reads_2bit(got, packed, n_reads, read_len)                      # host buffer: chunks cross PCIe packed
+    for g, w in zip(got, want):
+        assert np.array_equal(g.mins_np(), w.mins_np()) and np.array_equal(g.abunds_np(), w.abunds_np())
+    o = orc.KmerMinHash(0, ks[0], False, 42, MAX_HASH_1000 * 5, True)
+    o.add_reads(reads[:20_000].tobytes(), min(n_reads, 20_000), read_len)
+    chk = smb.KmerMinHash(0, ks[0], False, 42, MAX_HASH_1000 * 5, True)
+    smb.add_reads_2bit([chk], packed[:20_000], min(n_reads, 20_000), read_len)
+    _same(chk, o)
+    import torch                                                             # packed reads already in HBM
+    dev_packed = torch.from_numpy(packed.copy()).cuda()
+    num_sk = smb.KmerMinHash(300, ks[0], False, 42, 0, True)
+    num_ref = smb.KmerMinHash(300, ks[0], False, 42, 0, True)
+    smb.add_reads_2bit([num_sk], dev_packed.data_ptr(), n_reads, read_len, on_device=True)
+    smb.add_reads([num_ref], reads.tobytes(), n_reads, read_len)
+    assert np.array_equal(num_sk.mins_np(), num_ref.mins_np()) and np.array_equal(num_sk.abunds_np(), num_ref.abunds_np())
