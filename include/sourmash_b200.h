@@ -161,6 +161,12 @@ void smgpu_compare_path(int32_t path);
  * sketches together hold at most 1024 hashes.  Results are identical; the warp form measured slower and is kept for
  * A/B runs. */
 void smgpu_walk_form(int32_t form);
+/* smgpu_compare_matrix_allgather with device outputs over sketches of one length (full `num` sketches): with
+ * `stages` > 1 the gathered hashes travel in that many groups of point-to-point exchanges (peers by ring distance) and
+ * the join probes each group's sketches while the next group is on the wire.  1 (default; SMB200_GATHER_STAGES) = one
+ * ncclAllGather, the join's probe behind it -- measured equal or faster on 4 GPUs.  Returns the previous value; `stages` < 1 only reads it.  Every rank must use the same value.
+ * Results are identical. */
+int32_t smgpu_gather_stages(int32_t stages);
 /* How smgpu_linear_find counts shared hashes when a count decides the hit (containment; similarity of sketches
  * without a num): 0 (default) = an index that is large against the query batch is STREAMED once past per-slice
  * Bloom filters of the query hashes held in shared memory (the search then runs at the rate HBM delivers the

@@ -164,8 +164,11 @@ static int bit_length64(uint64_t x) {
 // The hash-grouped postings of a block's build side (join.cu), living in the calling thread's scratch
 // (ctx.join[0,1,6,7], sort_tmp_k/v, misc[1]): built either inside compare_block_device or ahead of it --
 // compare_matrix_allgather builds the table of a rank's own rows while the other ranks' rows are in flight.
+// `side` (optional): the kernels go to that stream instead of the thread's own -- the scratch is still reserved in the
+// thread's stream order, `side` starts behind `side_go` recorded there, and the caller makes its stream wait for `side`
+// before the table (or the scratch) is touched again.
 void join_table_build(Context &ctx, JoinTable &jt, const uint64_t *bh, const uint64_t *bo, uint64_t b0, uint64_t n_build,
-                      uint64_t n_bp, bool with_filter) {
+                      uint64_t n_bp, bool with_filter, cudaStream_t side, cudaEvent_t side_go) {
     cudaStream_t st = ctx.stream;
     // slots: the power of two at or above 1.5 x the postings (postings of one hash share a slot, so the load is
     // below 0.67 whatever the data; the memsets and the scan over the slots are a third of the build at 5 M postings)
@@ -190,6 +193,11 @@ void join_table_build(Context &ctx, JoinTable &jt, const uint64_t *bh, const uin
     unsigned long long *tkey = ctx.join[0].as<unsigned long long>(), *tcount = ctx.join[1].as<unsigned long long>();
     uint64_t *toff = ctx.sort_tmp_k.as<uint64_t>();
     uint32_t *tcursor = ctx.sort_tmp_v.as<uint32_t>(), *slot_of = ctx.join[6].as<uint32_t>(), *grows = ctx.join[7].as<uint32_t>();
+    if (side) {
+        SM_CUDA(cudaEventRecord(side_go, ctx.stream));
+        SM_CUDA(cudaStreamWaitEvent(side, side_go, 0));
+        st = side;
+    }
     {
         ProfScope prof(PROF_SORT, st);
         SM_CUDA(cudaMemsetAsync(tkey, 0xFF, (T + 1) * 8, st));
@@ -209,9 +217,15 @@ void join_table_build(Context &ctx, JoinTable &jt, const uint64_t *bh, const uin
 // One block of the matrix into DEVICE outputs.  Picks the sparse path (inverted index: only pairs
 // sharing a hash are walked) when the number of (pair, shared hash) incidences is small against
 // the dense work, else the dense tile kernel.  Same integers either way.
+void wait_arrivals(cudaStream_t st, const std::vector<ColumnArrival> *arrivals) {
+    if (!arrivals) return;
+    for (const ColumnArrival &a : *arrivals)
+        if (a.ready) SM_CUDA(cudaStreamWaitEvent(st, a.ready, 0));
+}
+
 void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t nr, SketchCollection &cols, uint64_t c0,
                           uint64_t nc, int mode, uint32_t *common, uint32_t *size, double *ratio, uint64_t ld,
-                          const JoinTable *prebuilt) {
+                          const JoinTable *prebuilt, const std::vector<ColumnArrival> *arrivals) {
     Context &ctx = Context::get();
     cudaStream_t st = ctx.stream;
     const uint64_t *rh = rows.d_hashes.as<uint64_t>(), *ro = rows.d_offsets.as<uint64_t>();
@@ -250,6 +264,27 @@ void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t nr, Sket
     const uint64_t b0 = build_cols ? c0 : r0, p0 = build_cols ? r0 : c0, n_probe = build_cols ? nr : nc;
     const bool probe = sparse && g_compare_path != 3 && n_bp > 0 && n_bp < (1ull << 31) &&
                        !(rows.probe_dense_preferred && !force_sparse);
+    // Column hashes still in flight: the probe form with the table over the ROWS takes the parts as they land (each part
+    // is its own probe launch, behind that part's event); everything else needs all of them now.
+    const bool staged = arrivals && probe && !build_cols && c0 == 0;
+    if (arrivals && !staged) wait_arrivals(st, arrivals);
+    auto probe_columns = [&](bool count, const unsigned long long *tkey, const uint64_t *toff, const uint32_t *grows, int log2_t,
+                             uint32_t *cmat, uint64_t cld, unsigned long long *bitmap, const uint32_t *filter, int log2_f) {
+        if (!staged) {
+            launch_probe_group(count, build_cols, tkey, toff, grows, log2_t, ph, po, p0, n_probe, cmat, cld, bitmap, n_build, ctx.dsc(SC_CNT),
+                               filter, log2_f, st);
+            return;
+        }
+        uint64_t covered = 0;
+        for (const ColumnArrival &a : *arrivals) {
+            if (a.c_end > nc || a.c_begin > a.c_end) throw_internal("column arrivals outside the block");
+            if (a.ready) SM_CUDA(cudaStreamWaitEvent(st, a.ready, 0));
+            launch_probe_group(count, false, tkey, toff, grows, log2_t, ph, po, p0, a.c_end - a.c_begin, cmat, cld, bitmap, n_build,
+                               ctx.dsc(SC_CNT), filter, log2_f, st, a.c_begin);
+            covered += a.c_end - a.c_begin;
+        }
+        if (covered != nc) throw_internal("column arrivals do not cover the block");
+    };
     if (probe) {
         // the table: handed in (built over exactly this block's build side, on this thread's scratch) or built here;
         // with a presence filter in front of it when the probing side is a different, larger collection
@@ -279,8 +314,7 @@ void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t nr, Sket
                 cld = nc;
             }
             SM_CUDA(cudaMemset2DAsync(cmat, cld * 4, 0, nc * 4, nr, st));
-            launch_probe_group(true, build_cols, tkey, toff, grows, log2_t, ph, po, p0, n_probe, cmat, cld, nullptr, n_build, ctx.dsc(SC_CNT), filter,
-                               log2_f, st);
+            probe_columns(true, tkey, toff, grows, log2_t, cmat, cld, nullptr, filter, log2_f);
             if (size || ratio || cmat != common)  // (counts only, straight into the caller's matrix: nothing left to do)
                 launch_fill_cells(ro, rnum, r0, nr, co, c0, nc, 1, cmat, cld, common, size, ratio, ld, st);
         } else {
@@ -290,9 +324,9 @@ void compare_block_device(SketchCollection &rows, uint64_t r0, uint64_t nr, Sket
             unsigned long long *bitmap = ctx.join[2].as<unsigned long long>();
             uint64_t *counts = ctx.join[3].as<uint64_t>(), *pre = ctx.join[4].as<uint64_t>();
             SM_CUDA(cudaMemsetAsync(bitmap, 0, n_words * 8, st));
-            launch_probe_group(false, build_cols, tkey, toff, grows, log2_t, ph, po, p0, n_probe, nullptr, 0, bitmap, n_build, ctx.dsc(SC_CNT),
-                               filter, log2_f, st);
+            // (the unrelated-pair values need row lengths only: written first, they overlap a transfer the probe waits for)
             launch_fill_cells(ro, rnum, r0, nr, co, c0, nc, 0, nullptr, 0, common, size, ratio, ld, st);  // as if unrelated
+            probe_columns(false, tkey, toff, grows, log2_t, nullptr, 0, bitmap, filter, log2_f);
             launch_popc_words(bitmap, n_words, counts, st);
             scan_exclusive_u64(counts, pre, n_words, ctx.scan_tmp.p, st);
             // the pair list can hold every cell of a block of up to 2^26 cells: then the walk reads its

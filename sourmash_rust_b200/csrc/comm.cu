@@ -17,6 +17,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -47,6 +48,9 @@ struct Comm {
     int rank = 0, world = 1;
     cudaStream_t stream = nullptr;            // collectives run here, beside the calling thread's compute stream
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+    std::vector<cudaEvent_t> ev_stage;        // one per group of a staged gather (made on first use)
+    cudaStream_t build_stream = nullptr;      // the join table of a rank's own rows is built here, beside the exchange
+    cudaEvent_t ev_build_go = nullptr, ev_build_done = nullptr;
     unsigned long long *d_hdr = nullptr;      // [HDR] mine + [world * HDR] everybody's
     unsigned long long *h_hdr = nullptr;      // pinned mirror of the gathered part
 };
@@ -107,14 +111,19 @@ void require_comm() {
 
 // every rank's 8-word header, on the host (one small all-gather + one kernel store into pinned memory: the only
 // host round trip of an exchange whose sizes are not known in advance)
-void exchange_headers(const unsigned long long mine[HDR]) {
+// (in two halves: what the caller queues between them runs while the headers are on their way)
+void exchange_headers_begin(const unsigned long long mine[HDR]) {
     Comm &c = g_comm;
     put_header_kernel<<<1, 1, 0, c.stream>>>(c.d_hdr, mine[0], mine[1], mine[2], mine[3], mine[4], mine[5], mine[6], mine[7]);
     SM_LAUNCHED();
     SM_NCCL(g_nccl.AllGather(c.d_hdr, c.d_hdr + HDR, HDR, ncclUint64, c.comm, c.stream));
     words_to_host_kernel<<<1, 64, 0, c.stream>>>(c.d_hdr + HDR, c.h_hdr, c.world * HDR);
     SM_LAUNCHED();
-    SM_CUDA(cudaStreamSynchronize(c.stream));
+}
+void exchange_headers_finish() { SM_CUDA(cudaStreamSynchronize(g_comm.stream)); }
+void exchange_headers(const unsigned long long mine[HDR]) {
+    exchange_headers_begin(mine);
+    exchange_headers_finish();
 }
 
 // variable-size all-gather: rank r's `count[r]` elements land at recv + base[r].  Equal counts (fixed-width `num`
@@ -167,6 +176,14 @@ __global__ void pack_rowinfo_kernel(const uint64_t *__restrict__ offsets, const 
 
 }  // namespace
 
+// groups a uniform gather is cut into when the compare that follows can take its columns part by part
+// (1 = one ncclAllGather and one wait); SMB200_GATHER_STAGES / smgpu_gather_stages
+int g_gather_stages = [] {
+    const char *e = getenv("SMB200_GATHER_STAGES");
+    const int v = e ? atoi(e) : 1;
+    return v < 1 ? 1 : (v > 16 ? 16 : v);
+}();
+
 // ---------------------------------------------------------------------------------------------------------
 void comm_unique_id(uint8_t out[COMM_ID_BYTES]) {
     load_nccl();
@@ -189,9 +206,16 @@ void comm_init(const uint8_t id_bytes[COMM_ID_BYTES], int rank, int world) {
     c.rank = rank;
     c.world = world;
     SM_NCCL(g_nccl.CommInitRank(&c.comm, world, id, rank));
-    SM_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    // the collectives' stream has the greatest priority: NCCL's few CTAs are placed ahead of the queued CTAs of a
+    // GPU-filling table build or probe on the compute streams instead of waiting for those kernels to drain
+    int prio_least = 0, prio_greatest = 0;
+    SM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    SM_CUDA(cudaStreamCreateWithPriority(&c.stream, cudaStreamNonBlocking, prio_greatest));
     SM_CUDA(cudaEventCreateWithFlags(&c.ev_ready, cudaEventDisableTiming));
     SM_CUDA(cudaEventCreateWithFlags(&c.ev_done, cudaEventDisableTiming));
+    SM_CUDA(cudaStreamCreateWithFlags(&c.build_stream, cudaStreamNonBlocking));
+    SM_CUDA(cudaEventCreateWithFlags(&c.ev_build_go, cudaEventDisableTiming));
+    SM_CUDA(cudaEventCreateWithFlags(&c.ev_build_done, cudaEventDisableTiming));
     SM_CUDA(cudaMalloc(&c.d_hdr, (size_t)(world + 1) * HDR * 8));
     SM_CUDA(cudaMallocHost(&c.h_hdr, (size_t)world * HDR * 8));
     g_comm = c;
@@ -208,6 +232,11 @@ void comm_destroy() {
     cudaStreamDestroy(g_comm.stream);
     cudaEventDestroy(g_comm.ev_ready);
     cudaEventDestroy(g_comm.ev_done);
+    for (cudaEvent_t e : g_comm.ev_stage) cudaEventDestroy(e);
+    cudaStreamSynchronize(g_comm.build_stream);
+    cudaStreamDestroy(g_comm.build_stream);
+    cudaEventDestroy(g_comm.ev_build_go);
+    cudaEventDestroy(g_comm.ev_build_done);
     cudaFree(g_comm.d_hdr);
     cudaFreeHost(g_comm.h_hdr);
     g_comm = Comm();
@@ -223,10 +252,16 @@ int comm_nccl_version() {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// all-gather of a packed collection.  `before_wait` runs after the exchange has been queued and before this
-// thread waits for it: work that needs only local data overlaps the transfer.
+// all-gather of a packed collection.  `meanwhile` (optional) is called once the header exchange has been queued and
+// before this thread waits for it: what it queues needs local data only and runs beside the exchange.
 // ---------------------------------------------------------------------------------------------------------
-static SketchCollection *allgather_impl(SketchCollection &local, const std::function<void()> &before_wait) {
+// `arrivals` (optional, filled only for uniform rows on more than one rank): the compute stream is NOT made to wait for
+// the hashes; the caller waits for each listed event before it touches that part (collection.hpp: ColumnArrival).  With
+// g_gather_stages > 1 they travel in that many groups of point-to-point exchanges (peers by ring distance), one event
+// per group; otherwise as one ncclAllGather with one event.
+static SketchCollection *allgather_impl(SketchCollection &local, const std::function<void()> &meanwhile,
+                                        std::vector<ColumnArrival> *arrivals = nullptr) {
+    if (arrivals) arrivals->clear();
     Comm &c = g_comm;
     Context &ctx = Context::get();
     local.finalize();  // (rows were checked strictly ascending when the local collection was made: peers do the same)
@@ -245,7 +280,7 @@ static SketchCollection *allgather_impl(SketchCollection &local, const std::func
         if (local.n_hashes) SM_CUDA(cudaMemcpyAsync(out->d_hashes.p, local.d_hashes.p, local.n_hashes * 8, cudaMemcpyDeviceToDevice, ctx.stream));
         SM_CUDA(cudaMemcpyAsync(out->d_offsets.p, local.d_offsets.p, (local.n_rows + 1) * 8, cudaMemcpyDeviceToDevice, ctx.stream));
         if (local.n_rows) SM_CUDA(cudaMemcpyAsync(out->d_nums.p, local.d_nums.p, local.n_rows * 4, cudaMemcpyDeviceToDevice, ctx.stream));
-        if (before_wait) before_wait();
+        if (meanwhile) meanwhile();
         out->dirty = false;
         return out.release();
     }
@@ -258,7 +293,9 @@ static SketchCollection *allgather_impl(SketchCollection &local, const std::func
     const unsigned long long shape = uniform ? ((1ull << 63) | (len0 << 32) | local.h_nums[0]) : 0;
     unsigned long long mine[HDR] = {local.n_rows, local.n_hashes, local.max_len, local.ksize, local.seed, local.max_hash,
                                     (unsigned long long)local.is_protein | ((unsigned long long)local.have_params << 1), shape};
-    exchange_headers(mine);
+    exchange_headers_begin(mine);
+    if (meanwhile) meanwhile();
+    exchange_headers_finish();
     const int W = c.world;
     std::vector<uint64_t> rows(W), hashes(W), row_base(W), hash_base(W);
     uint64_t n_rows = 0, n_hashes = 0, max_len = 0;
@@ -296,15 +333,49 @@ static SketchCollection *allgather_impl(SketchCollection &local, const std::func
         const uint32_t num = (uint32_t)all_shape;
         SM_CUDA(cudaEventRecord(c.ev_ready, ctx.stream));       // the output buffer is allocated (stream-ordered)
         SM_CUDA(cudaStreamWaitEvent(c.stream, c.ev_ready, 0));
-        SM_NCCL(g_nccl.GroupStart());
-        allgatherv(local.d_hashes.p, out->d_hashes.p, hashes, hash_base, 8, ncclUint64);
-        SM_NCCL(g_nccl.GroupEnd());
-        SM_CUDA(cudaEventRecord(c.ev_done, c.stream));
+        const int G = std::min(g_gather_stages, W - 1);
+        const bool deferred = arrivals && W > 1;          // the caller waits, part by part
+        const bool grouped = deferred && g_gather_stages > 1;
+        if (grouped) {
+            // own rows: a device copy on the compute stream; peers at ring distance d, in G groups of distances -- each
+            // group is one fused NCCL kernel, and its parts can be probed while the next group is on the wire
+            uint64_t *dst = out->d_hashes.as<uint64_t>();
+            if (hashes[c.rank])
+                SM_CUDA(cudaMemcpyAsync(dst + hash_base[c.rank], local.d_hashes.p, hashes[c.rank] * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+            arrivals->push_back({row_base[c.rank], row_base[c.rank] + rows[c.rank], nullptr});
+            while ((int)c.ev_stage.size() < G) {
+                cudaEvent_t e;
+                SM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                c.ev_stage.push_back(e);
+            }
+            int d = 1;
+            for (int g = 0; g < G; g++) {
+                const int d_end = 1 + (int)((uint64_t)(W - 1) * (g + 1) / G);   // distances [d, d_end)
+                SM_NCCL(g_nccl.GroupStart());
+                for (int dd = d; dd < d_end; dd++) {
+                    const int to = (c.rank + dd) % W, from = (c.rank - dd + W) % W;
+                    if (hashes[c.rank]) SM_NCCL(g_nccl.Send(local.d_hashes.p, hashes[c.rank], ncclUint64, to, c.comm, c.stream));
+                    if (hashes[from]) SM_NCCL(g_nccl.Recv(dst + hash_base[from], hashes[from], ncclUint64, from, c.comm, c.stream));
+                }
+                SM_NCCL(g_nccl.GroupEnd());
+                SM_CUDA(cudaEventRecord(c.ev_stage[g], c.stream));
+                for (int dd = d; dd < d_end; dd++) {
+                    const int from = (c.rank - dd + W) % W;
+                    arrivals->push_back({row_base[from], row_base[from] + rows[from], c.ev_stage[g]});
+                }
+                d = d_end;
+            }
+        } else {
+            SM_NCCL(g_nccl.GroupStart());
+            allgatherv(local.d_hashes.p, out->d_hashes.p, hashes, hash_base, 8, ncclUint64);
+            SM_NCCL(g_nccl.GroupEnd());
+            SM_CUDA(cudaEventRecord(c.ev_done, c.stream));
+            if (deferred) arrivals->push_back({0, n_rows, c.ev_done});
+        }
         uniform_rows_kernel<<<(unsigned)std::min<uint64_t>((n_rows + 256) / 256, 148 * 8), 256, 0, ctx.stream>>>(
             out->d_offsets.as<uint64_t>(), out->d_nums.as<uint32_t>(), n_rows, len, num);
         SM_LAUNCHED();
-        if (before_wait) before_wait();
-        SM_CUDA(cudaStreamWaitEvent(ctx.stream, c.ev_done, 0));
+        if (!deferred) SM_CUDA(cudaStreamWaitEvent(ctx.stream, c.ev_done, 0));
         out->h_offsets.resize(n_rows + 1);
         for (uint64_t i = 0; i <= n_rows; i++) out->h_offsets[i] = i * len;
         out->h_nums.assign(n_rows, num);
@@ -314,8 +385,8 @@ static SketchCollection *allgather_impl(SketchCollection &local, const std::func
     }
     // per row, [length, num] travel as one 8-byte record; on arrival the lengths are scanned into offsets.  This
     // thread's scratch: misc[0] = my records, misc[3] = everybody's, misc[2] = lengths as u64 (n_rows + 1 entries, the
-    // last one zero: its exclusive scan = offsets) -- not misc[1] or join[*], which the table build that overlaps the
-    // transfer uses
+    // last one zero: its exclusive scan = offsets), join[5] = scan scratch -- not misc[1], scan_tmp, sort_tmp_* or
+    // join[0,1,6,7], which the table build that overlaps the transfer uses
     ctx.misc[0].reserve((local.n_rows + 1) * 8);
     ctx.misc[3].reserve((n_rows + 1) * 8);
     ctx.misc[2].reserve((n_rows + 2) * 8);
@@ -334,15 +405,15 @@ static SketchCollection *allgather_impl(SketchCollection &local, const std::func
     allgatherv(my_info, all_info, rows, row_base, 8, ncclUint64);
     SM_NCCL(g_nccl.GroupEnd());
     SM_CUDA(cudaEventRecord(c.ev_done, c.stream));
-    if (before_wait) before_wait();
     SM_CUDA(cudaStreamWaitEvent(ctx.stream, c.ev_done, 0));
     if (n_rows) {
         unpack_rowinfo_kernel<<<(unsigned)std::min<uint64_t>((n_rows + 255) / 256, 148 * 8), 256, 0, ctx.stream>>>(
             all_info, n_rows, all_lens, out->d_nums.as<uint32_t>());
         SM_LAUNCHED();
     }
-    ctx.scan_tmp.reserve(scan_tmp_bytes(n_rows + 1) + 256);
-    scan_exclusive_u64(all_lens, out->d_offsets.as<uint64_t>(), n_rows + 1, ctx.scan_tmp.p, ctx.stream);
+    // (scan scratch: join[5], not scan_tmp -- compare_matrix_allgather's table build may be using that on its own stream)
+    ctx.join[5].reserve(scan_tmp_bytes(n_rows + 1) + 256);
+    scan_exclusive_u64(all_lens, out->d_offsets.as<uint64_t>(), n_rows + 1, ctx.join[5].p, ctx.stream);
     // host mirrors the block logic sizes its work from (collection.cu)
     out->h_offsets.resize(n_rows + 1);
     out->h_nums.resize(n_rows);
@@ -371,18 +442,52 @@ SketchCollection *compare_matrix_allgather(SketchCollection &local, int mode, ui
     const uint64_t n_rp = local.n_hashes;
     const bool will_probe = (g_compare_path == 0 || g_compare_path == 2 || g_compare_path == 4) && n_rp > 0 && n_rp < (1ull << 31) &&
                             local.n_rows < (1ull << 31) && !(local.probe_dense_preferred && g_compare_path == 0);
-    std::unique_ptr<SketchCollection> all(allgather_impl(local, [&]() {
-        if (will_probe)
-            join_table_build(ctx, jt, local.d_hashes.as<uint64_t>(), local.d_offsets.as<uint64_t>(), 0, local.n_rows, n_rp,
-                             g_comm.world >= 4);
-    }));
-    local.check_compatible(*all);
-    const uint64_t nr = local.n_rows, nc = all->n_rows;
-    if (nr == 0 || nc == 0) return all.release();
-    if (ld < nc) throw_internal("ld smaller than the block width");
+    // (device outputs, probe form: the gathered rows may still be arriving when the block starts -- see allgather_impl)
+    std::vector<ColumnArrival> arrivals;
     const bool alone = !g_comm.comm || g_comm.world == 1;   // one rank: rows and columns are the same sketches
+    // Queued while the headers are on their way and on a stream of its own: neither the host round trip of the headers
+    // nor the transfer (whose buffers are allocated in this thread's stream order) waits for it.  Whatever happens below, this
+    // thread's stream waits for the build before it goes on (the table lives in the thread's scratch).
+    struct JoinBuild {
+        cudaStream_t st = nullptr;
+        void join() {
+            if (st && cudaStreamWaitEvent(st, g_comm.ev_build_done, 0) != cudaSuccess) (void)cudaGetLastError();
+            st = nullptr;
+        }
+        ~JoinBuild() { join(); }
+    } join_build;
+    auto build_table = [&]() {
+        if (!will_probe) return;
+        const bool beside = !alone;
+        join_table_build(ctx, jt, local.d_hashes.as<uint64_t>(), local.d_offsets.as<uint64_t>(), 0, local.n_rows, n_rp,
+                         g_comm.world >= 4, beside ? g_comm.build_stream : nullptr, g_comm.ev_build_go);
+        if (beside) {
+            SM_CUDA(cudaEventRecord(g_comm.ev_build_done, g_comm.build_stream));
+            join_build.st = ctx.stream;
+        }
+    };
+    std::unique_ptr<SketchCollection> all(allgather_impl(local, build_table, (will_probe && out_on_device && !alone) ? &arrivals : nullptr));
+    join_build.join();
+    const std::vector<ColumnArrival> *arr = arrivals.empty() ? nullptr : &arrivals;
+    const uint64_t nr = local.n_rows, nc = all->n_rows;
+    try {
+        local.check_compatible(*all);
+        if (nr != 0 && nc != 0 && ld < nc) throw_internal("ld smaller than the block width");
+    } catch (...) {
+        wait_arrivals(ctx.stream, arr);   // (the gathered buffers are released in stream order)
+        throw;
+    }
+    if (nr == 0 || nc == 0) {
+        wait_arrivals(ctx.stream, arr);
+        return all.release();
+    }
     if (out_on_device) {
-        compare_block_device(local, 0, nr, alone ? local : *all, 0, nc, mode, common, size, ratio, ld, &jt);
+        try {
+            compare_block_device(local, 0, nr, alone ? local : *all, 0, nc, mode, common, size, ratio, ld, &jt, arr);
+        } catch (...) {
+            wait_arrivals(ctx.stream, arr);
+            throw;
+        }
         ctx.sync();
     } else if (alone) {
         compare_matrix(local, 0, nr, local, 0, nc, mode, common, size, ratio, ld, out_on_device);

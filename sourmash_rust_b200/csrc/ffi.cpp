@@ -678,6 +678,11 @@ uint64_t smgpu_scaffold_pairs(SketchCollection *c, uint64_t *pairs_first, uint64
     });
 }
 void smgpu_fuse_multi_k(bool on) { smb200::g_fuse_multi_k = on; }
+int32_t smgpu_gather_stages(int32_t stages) {
+    const int32_t before = smb200::g_gather_stages;
+    if (stages >= 1) smb200::g_gather_stages = stages > 16 ? 16 : stages;
+    return before;
+}
 void smgpu_walk_form(int32_t form) { smb200::g_walk_form = form == 2 ? 2 : 0; }
 void smgpu_find_path(int32_t path) { smb200::g_find_path = (path >= 0 && path <= 3) ? path : 0; }
 void smgpu_compare_path(int32_t path) { smb200::g_compare_path = (path >= 1 && path <= 4) ? path : 0; }

@@ -166,7 +166,9 @@ __global__ void __launch_bounds__(256) probe_group_kernel(const unsigned long lo
                                                           const uint64_t *__restrict__ po, uint64_t p0, uint64_t np, uint32_t *cmat,
                                                           uint64_t ld, unsigned long long *bitmap, uint64_t n_build,
                                                           unsigned long long *incidences, const uint32_t *__restrict__ filter,
-                                                          int log2_f, bool smem_rows, uint32_t split) {
+                                                          int log2_f, bool smem_rows, uint32_t split, uint64_t p_first) {
+    // Probing sketches p_first .. p_first + np - 1 of the block (a block whose probing side arrives in parts is
+    // probed part by part; cell ids stay those of the whole block).
     // `filter` (optional): one presence bit per build-side hash in a table small enough to stay in L2.  When
     // the two sides are unrelated collections (a query batch against an index) almost every probing hash is
     // turned away by that one bit instead of a random read in the (much larger) key table.
@@ -182,7 +184,8 @@ __global__ void __launch_bounds__(256) probe_group_kernel(const unsigned long lo
     // sketches related to the shard's rows have any hits, and one warp per sketch left most of the GPU idle while
     // those few warps walked their runs (8 GPUs, cfg3: 1 250 busy warps of 10 000).
     for (uint64_t wi = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < np * split; wi += warps) {
-        const uint64_t p = wi / split, part = wi - p * split;
+        const uint64_t pl = wi / split, part = wi - pl * split;
+        const uint64_t p = p_first + pl;
         const uint64_t b0 = po[p0 + p], len = po[p0 + p + 1] - b0;
         const uint64_t b = b0 + len * part / split, e = b0 + len * (part + 1) / split;
         if (s_rows) {
@@ -276,7 +279,7 @@ void launch_group_fill(const uint64_t *ro, uint64_t r0, uint64_t nr, const uint3
 void launch_probe_group(bool count, bool build_cols, const unsigned long long *tkey, const uint64_t *toff, const uint32_t *grows,
                         int log2_t, const uint64_t *ph, const uint64_t *po, uint64_t p0, uint64_t np, uint32_t *cmat, uint64_t ld,
                         unsigned long long *bitmap, uint64_t n_build, unsigned long long *incidences, const uint32_t *filter,
-                        int log2_f, cudaStream_t st) {
+                        int log2_f, cudaStream_t st, uint64_t p_first) {
     if (!np) return;
     ProfScope prof(PROF_PROBE, st);
     const bool smem_rows = !count && n_build <= PROBE_SMEM_ROWS;
@@ -292,7 +295,7 @@ void launch_probe_group(bool count, bool build_cols, const unsigned long long *t
         SM_CUDA(cudaFuncSetAttribute(probe_group_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr_set = true;
     }
-#define SM_PROBE(C, B) probe_group_kernel<C, B><<<grid, 256, smem, st>>>(tkey, toff, grows, log2_t, ph, po, p0, np, cmat, ld, bitmap, n_build, incidences, filter, log2_f, smem_rows, split)
+#define SM_PROBE(C, B) probe_group_kernel<C, B><<<grid, 256, smem, st>>>(tkey, toff, grows, log2_t, ph, po, p0, np, cmat, ld, bitmap, n_build, incidences, filter, log2_f, smem_rows, split, p_first)
     if (count) { if (build_cols) SM_PROBE(true, true); else SM_PROBE(true, false); }
     else { if (build_cols) SM_PROBE(false, true); else SM_PROBE(false, false); }
 #undef SM_PROBE

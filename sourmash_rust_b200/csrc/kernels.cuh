@@ -184,11 +184,13 @@ void launch_group_fill(const uint64_t *ro, uint64_t r0, uint64_t nr, const uint3
                        uint32_t *tcursor, uint32_t *grows, cudaStream_t st);
 // the table was built over the rows (build_cols = false) or the columns of the block; the other side's
 // sketches [p0, p0 + np) probe it.  count: counts into cmat[r * ld + c], else related-pairs bitmap with
-// bit = probe sketch * n_build + build sketch; *incidences += hits
+// bit = probe sketch * n_build + build sketch; *incidences += hits.  p_first: probe only sketches p0 + p_first ..
+// p0 + p_first + np - 1, with the cell ids of the whole block (a probing side that arrives in parts).
 void launch_probe_group(bool count, bool build_cols, const unsigned long long *tkey, const uint64_t *toff, const uint32_t *grows,
                         int log2_t, const uint64_t *ph, const uint64_t *po, uint64_t p0, uint64_t np, uint32_t *cmat, uint64_t ld,
                         unsigned long long *bitmap, uint64_t n_build, unsigned long long *incidences,
-                        const uint32_t *filter /*nullable: presence bits filled by launch_group_insert*/, int log2_f, cudaStream_t st);
+                        const uint32_t *filter /*nullable: presence bits filled by launch_group_insert*/, int log2_f, cudaStream_t st,
+                        uint64_t p_first = 0);
 void launch_incidences_shared(bool count, const uint64_t *keys, const uint64_t *vals, uint64_t n, uint64_t row_lo,
                               uint64_t nr, uint32_t *cmat, uint64_t ld, unsigned long long *bitmap, uint64_t nc,
                               cudaStream_t st);

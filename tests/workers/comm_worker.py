@@ -77,8 +77,11 @@ for kind, num, mx, n_rows in (("num", 200, 0, 96), ("scaled", 0, MAX_HASH_1000, 
     # 2. this rank's row block, gather overlapped with the local table build, against the one-process matrix
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank)))
     for mode in ("compare", "containment"):
-        for path in ("auto", "sparse", "dense"):
+        # (the sparse path over uniform rows takes the gathered columns group by group while they arrive: any number of
+        # groups, one included, must give the same block)
+        for path, stages in (("auto", 1), ("sparse", 1), ("sparse", 2), ("sparse", 3), ("sparse", 16), ("dense", 1)):
             smb.compare_path(path)
+            smb.gather_stages(stages)
             nr = hi - lo
             common = torch.full((max(1, nr), n_rows), -1, dtype=torch.int32, device=dev)
             size = torch.full((max(1, nr), n_rows), -1, dtype=torch.int32, device=dev)
@@ -91,6 +94,7 @@ for kind, num, mx, n_rows in (("num", 200, 0, 96), ("scaled", 0, MAX_HASH_1000, 
                 assert np.array_equal(size.cpu().numpy()[:nr].astype(np.uint32), ws), (kind, mode, path)
                 assert np.array_equal(ratio.cpu().numpy()[:nr], wr, equal_nan=True), (kind, mode, path)
         smb.compare_path("auto")
+        smb.gather_stages(1)
     # ... and against the oracle (first rows of the block)
     if hi > lo:
         osk = []
