@@ -60,5 +60,37 @@ def build_library(force=False, verbose=False):
     return LIB
 
 
+def build_tsan(verbose=False):
+    """A ThreadSanitizer build of the same sources (host code instrumented; device code as usual) under build/tsan/, for
+    tests/test_tsan_cpu.py.  Never the library the package loads."""
+    out_dir = os.path.join(OBJ, "tsan")
+    lib = os.path.join(out_dir, "libsourmash_tsan.so")
+    if os.path.exists(lib) and all(os.path.getmtime(d) <= os.path.getmtime(lib) for d in _deps()):
+        return lib
+    os.makedirs(out_dir, exist_ok=True)
+    san = ["-Xcompiler", "-fsanitize=thread,-g,-fno-omit-frame-pointer"]
+
+    def compile_one(src):
+        obj = os.path.join(out_dir, os.path.splitext(src)[0] + ".o")
+        r = subprocess.run([NVCC] + FLAGS + san + ["-c", os.path.join(CSRC, src), "-o", obj],
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc (tsan) failed for %s:\n%s" % (src, r.stdout))
+        return obj
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    r = subprocess.run([NVCC, "-shared", "-o", lib] + objs + san + ["-lcudart_static", "-lpthread", "-ldl", "-lrt", "-lz"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link (tsan) failed:\n" + r.stdout)
+    if verbose:
+        print("built", lib)
+    return lib
+
+
 if __name__ == "__main__":
-    build_library(force="--force" in sys.argv, verbose=True)
+    if "--tsan" in sys.argv:
+        build_tsan(verbose=True)
+    else:
+        build_library(force="--force" in sys.argv, verbose=True)
