@@ -105,10 +105,6 @@ __global__ void add_base_kernel(uint64_t *__restrict__ v, uint64_t n, uint64_t b
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) v[i] += base;
 }
 
-void require_comm() {
-    if (!g_comm.comm) throw_internal("no communicator: call smgpu_comm_init first");
-}
-
 // every rank's 8-word header, on the host (one small all-gather + one kernel store into pinned memory: the only
 // host round trip of an exchange whose sizes are not known in advance)
 // (in two halves: what the caller queues between them runs while the headers are on their way)
